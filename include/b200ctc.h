@@ -1,0 +1,137 @@
+/* b200ctc.h -- C ABI of libb200ctc.so, the B200-native CTC prefix beam-search decoder.
+ *
+ * The reference (kensho-technologies/pyctcdecode 0.6.0) has no FFI: its "plugin API" for
+ * this path is the Python class BeamSearchDecoderCTC.  This header is the boundary a
+ * maintainer of the reference would bind with ctypes/cffi to replace the body of
+ * decode()/decode_batch()/decode_beams()/decode_beams_batch() -- see INTEGRATION.md.
+ * Each entry point cites the reference interface it replaces (paths relative to
+ * /root/reference/pyctcdecode/).
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a
+ * negative B2C_E_* code (b2c_last_error() gives the message for the calling thread); the
+ * library owns every object it returns until the matching *_free/_destroy; inputs stay
+ * caller-owned and are never modified (reference decoder.py:762-765 allocates instead of
+ * mutating); calls are synchronous and use the decoder's own CUDA stream; a decoder handle
+ * may be used from one thread at a time.  There is no CPU fallback: without a CUDA device
+ * b2c_decoder_create fails with B2C_E_CUDA.
+ */
+#ifndef B200CTC_H
+#define B200CTC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2C_E_OK 0
+#define B2C_E_ARG (-1)      /* bad argument (python side raises ValueError, like decoder.py:335-344) */
+#define B2C_E_CUDA (-2)     /* CUDA runtime failure / no device */
+#define B2C_E_IO (-3)       /* cannot read the ARPA file */
+#define B2C_E_NOMEM (-4)
+#define B2C_E_INTERNAL (-5)
+
+#define B2C_DTYPE_F32 0
+#define B2C_DTYPE_F64 1
+
+typedef struct b2c_lm b2c_lm_t;            /* flattened n-gram model (host blob + device copies) */
+typedef struct b2c_decoder b2c_decoder_t;  /* one decoder bound to one CUDA device */
+typedef struct b2c_result b2c_result_t;    /* results of one decode_batch call */
+
+const char* b2c_last_error(void);
+int b2c_version(void);
+/* number of visible CUDA devices (0 when there is none) */
+int b2c_device_count(void);
+
+/* ---- n-gram model ------------------------------------------------------------------------
+ * Replaces kenlm.Model(kenlm_model_path) + _prepare_unigram_set + CharTrie.fromkeys
+ * (decoder.py:1074-1096, language_model.py:87-103, :237-269).  `unigrams` NULL or
+ * n_unigrams < 0 means "no unigram list" (LanguageModel(unigrams=None)). ARPA text only. */
+int b2c_lm_build_from_arpa(const char* arpa_path, const char* const* unigrams, long n_unigrams, b2c_lm_t** out);
+/* the relocatable blob (for a NCCL broadcast) and its reconstruction on another rank */
+int b2c_lm_blob(const b2c_lm_t* lm, const void** data, size_t* size);
+int b2c_lm_from_blob(const void* data, size_t size, b2c_lm_t** out);
+/* make the model resident on `device` by cudaMemcpy, or adopt a device copy that already
+ * exists (e.g. the torch tensor an NCCL broadcast wrote); adopted memory stays caller-owned */
+int b2c_lm_upload(b2c_lm_t* lm, int device);
+int b2c_lm_adopt_device_blob(b2c_lm_t* lm, int device, const void* device_ptr, size_t size);
+void b2c_lm_destroy(b2c_lm_t* lm);
+/* kenlm.Model look-alike queries, evaluated on the host copy of the tables
+ * (language_model.py:95,306,312-314,347,352) */
+int b2c_lm_order(const b2c_lm_t* lm);
+int b2c_lm_contains(const b2c_lm_t* lm, const char* word);
+int b2c_lm_in_unigrams(const b2c_lm_t* lm, const char* word);
+int b2c_lm_has_prefix(const b2c_lm_t* lm, const char* prefix);
+/* state: `words` most recent first; BaseScore writes the out state and returns log10 p */
+typedef struct { uint32_t words[5]; float backoff[5]; uint32_t length; } b2c_lm_state_t;
+void b2c_lm_begin_sentence(const b2c_lm_t* lm, b2c_lm_state_t* st);
+void b2c_lm_null_context(const b2c_lm_t* lm, b2c_lm_state_t* st);
+float b2c_lm_base_score(const b2c_lm_t* lm, const b2c_lm_state_t* in, const char* word, b2c_lm_state_t* out);
+
+/* ---- decoder -----------------------------------------------------------------------------
+ * Replaces BeamSearchDecoderCTC.__init__ (decoder.py:275-290).  `labels` are the NORMALISED
+ * labels (Alphabet.labels, alphabet.py:139-148): "" is the CTC blank, " " the word separator
+ * of a regular alphabet, U+2581-prefixed pieces start a word in a BPE alphabet.
+ * `lm` may be NULL.  The decoder keeps a reference to `lm` (destroy the decoder first). */
+int b2c_decoder_create(const char* const* labels, int n_labels, int is_bpe, b2c_lm_t* lm, int device,
+                       b2c_decoder_t** out);
+void b2c_decoder_destroy(b2c_decoder_t* dec);
+/* LanguageModel.reset_params (language_model.py:271-301): plain scalars handed to the kernels */
+int b2c_decoder_set_params(b2c_decoder_t* dec, double alpha, double beta, double unk_score_offset,
+                           int lm_score_boundary);
+
+typedef struct {
+    int beam_width;            /* DEFAULT_BEAM_WIDTH 100          (constants.py:8)  */
+    double beam_prune_logp;    /* DEFAULT_PRUNE_LOGP -10          (constants.py:10) */
+    double token_min_logp;     /* DEFAULT_MIN_TOKEN_LOGP -5       (constants.py:12) */
+    int prune_history;         /* decode(): 1 (decoder.py:888); decode_beams(): 0  */
+    const char* const* hotwords; /* raw hotword strings, split on whitespace like language_model.py:160-166 */
+    int n_hotwords;
+    double hotword_weight;     /* DEFAULT_HOTWORD_WEIGHT 10       (constants.py:9)  */
+    int max_out_beams;         /* 1 for decode()/decode_batch(); beam_width for decode_beams*() */
+    const b2c_lm_state_t* lm_start_states; /* NULL, or one start state per utterance (lm_start_state, decoder.py:612-625) */
+} b2c_decode_opts_t;
+void b2c_decode_opts_default(b2c_decode_opts_t* opts);
+
+/* Replaces decode_batch / decode_beams_batch (decoder.py:801-857, :895-945) and, with
+ * n_utts == 1, decode / decode_beams (:730-775, :859-893).
+ *   logits[i]  -> C-contiguous [T[i], V] matrix of dtype (B2C_DTYPE_*), host pointers when
+ *                 is_device == 0 (copied host->device inside the call), device pointers on the
+ *                 decoder's device when is_device != 0 (used in place when contiguous);
+ *   ragged T and T == 0 are allowed.                                                      */
+int b2c_decode_batch(b2c_decoder_t* dec, const void* const* logits, const int32_t* T, int n_utts, int dtype,
+                     int is_device, const b2c_decode_opts_t* opts, b2c_result_t** out);
+
+/* ---- results (OutputBeam, decoder.py:102-118, built at :653-667) ------------------------- */
+void b2c_result_free(b2c_result_t* res);
+int b2c_result_n_utts(const b2c_result_t* res);
+int b2c_result_n_beams(const b2c_result_t* res, int utt);
+const char* b2c_result_text(const b2c_result_t* res, int utt, int beam);          /* utf-8 */
+double b2c_result_logit_score(const b2c_result_t* res, int utt, int beam);
+double b2c_result_lm_score(const b2c_result_t* res, int utt, int beam);
+int b2c_result_n_words(const b2c_result_t* res, int utt, int beam);
+const char* b2c_result_word(const b2c_result_t* res, int utt, int beam, int word);
+/* 2 * n_words ints: (start_frame, end_frame) per word */
+const int32_t* b2c_result_frames(const b2c_result_t* res, int utt, int beam);
+/* LM state after the last word (OutputBeam.last_lm_state); returns 0 when there is no LM */
+int b2c_result_lm_state(const b2c_result_t* res, int utt, int beam, b2c_lm_state_t* out);
+
+/* ---- measurement hooks (bench.py) ---------------------------------------------------------
+ * Device time of the kernels of the LAST decode call, measured with CUDA events on the
+ * decoder's stream, and launch / traffic counters. */
+typedef struct {
+    float ms_prepare;          /* prepare kernel (normalise + token select)               */
+    float ms_beam;             /* beam-search kernel                                       */
+    float ms_total;            /* first H2D copy .. last D2H copy                          */
+    int launches;              /* kernels launched                                         */
+    long long h2d_bytes, d2h_bytes;
+    long long frames;          /* sum of T                                                 */
+    long long tokens;          /* selected (frame, token) pairs                            */
+} b2c_timings_t;
+int b2c_decoder_last_timings(const b2c_decoder_t* dec, b2c_timings_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200CTC_H */

@@ -1,0 +1,965 @@
+// b200ctc -- C ABI implementation (include/b200ctc.h): kernels, workspace layout, batch
+// orchestration, result assembly.  Compiled by nvcc for sm_100a into libb200ctc.so.
+// With -DB2C_HOSTSIM (tests/hostsim only) the same file is compiled by g++ against a stub of
+// the CUDA runtime and runs the kernel bodies block by block on the CPU so that kernel logic
+// can be tested where there is no GPU; that build is never loaded by the product package.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#ifdef B2C_HOSTSIM
+#include "cuda_shim.h"
+#else
+#include <cuda_runtime.h>
+#endif
+
+#include "../../include/b200ctc.h"
+#include "b2c_beam.h"
+#include "b2c_common.h"
+#include "b2c_lm_host.h"
+#include "b2c_prepare.h"
+
+#define B2C_VERSION 100
+#define B2C_BEAM_THREADS 128
+#define B2C_PREP_THREADS (B2C_PREP_WARPS * 32)
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CUDA_OK(expr)                                                                         \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess)                                                                \
+            return fail(B2C_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));     \
+    } while (0)
+
+// =========================================================================================
+// workspace layout (shared memory + per-slot HBM workspace), computed on the host and
+// interpreted by the kernel
+// =========================================================================================
+struct B2cLayout {
+    int W;                      // beam_width (capacity of the beam tables)
+    u32 cap_s, ht_s;            // shared-memory candidate tier
+    u32 cap_g, ht_g;            // HBM candidate tier (0: absent)
+    int beams_in_smem;
+    u32 chain_cap, text_cap;
+    int V;
+    u32 smem_bytes;
+    u64 gws_bytes;              // per slot
+    // offsets
+    u32 s_sc, s_tab[2], s_sel, s_tier;
+    u64 g_tab[2], g_sel, g_tier, g_tk, g_chain, g_text;
+};
+
+static inline u64 al16(u64 x) { return (x + 15) & ~15ull; }
+static inline u64 tab_bytes(int W) { return 6 * al16(8ull * W) + 4 * al16(4ull * W) + 2 * al16(2ull * W) + 64; }
+static inline u64 sel_bytes(int W) { return al16(8ull * W) + 3 * al16(4ull * W) + 64; }
+static inline u64 tier_bytes(u32 cap, u32 ht) { return al16(8ull * cap) * 2 + al16(4ull * cap) * 2 + al16(4ull * ht) * 4 + 64; }
+
+B2C_HD u8* b2c_carve(u8*& p, u64 bytes) {
+    u8* r = p;
+    p += (bytes + 15) & ~15ull;
+    return r;
+}
+B2C_HD void b2c_carve_tab(u8* base, int W, B2cBeamTab& t) {
+    u8* p = base;
+    t.logit = reinterpret_cast<double*>(b2c_carve(p, 8ull * W));
+    t.lm_hw = reinterpret_cast<double*>(b2c_carve(p, 8ull * W));
+    t.pscore = reinterpret_cast<double*>(b2c_carve(p, 8ull * W));
+    t.text_hash = reinterpret_cast<u64*>(b2c_carve(p, 8ull * W));
+    t.part_hash = reinterpret_cast<u64*>(b2c_carve(p, 8ull * W));
+    t.hist_hash = reinterpret_cast<u64*>(b2c_carve(p, 8ull * W));
+    t.text_node = reinterpret_cast<u32*>(b2c_carve(p, 4ull * W));
+    t.chain = reinterpret_cast<u32*>(b2c_carve(p, 4ull * W));
+    t.pf_s = reinterpret_cast<int*>(b2c_carve(p, 4ull * W));
+    t.pf_e = reinterpret_cast<int*>(b2c_carve(p, 4ull * W));
+    t.last_tok = reinterpret_cast<u16*>(b2c_carve(p, 2ull * W));
+    t.part_len = reinterpret_cast<u16*>(b2c_carve(p, 2ull * W));
+}
+B2C_HD void b2c_carve_tier(u8* base, u32 cap, u32 ht, B2cCandTier& c) {
+    u8* p = base;
+    c.cap = cap;
+    c.ht_cap = ht;
+    c.ckey = reinterpret_cast<u64*>(b2c_carve(p, 8ull * cap));
+    c.cfold = reinterpret_cast<double*>(b2c_carve(p, 8ull * cap));
+    c.cslot = reinterpret_cast<u32*>(b2c_carve(p, 4ull * cap));
+    c.sidx = reinterpret_cast<u32*>(b2c_carve(p, 4ull * cap));
+    c.ht_idx = reinterpret_cast<u32*>(b2c_carve(p, 4ull * ht));
+    c.ht_min = reinterpret_cast<u32*>(b2c_carve(p, 4ull * ht));
+    c.ht_max = reinterpret_cast<u32*>(b2c_carve(p, 4ull * ht));
+    c.ht_cnt = reinterpret_cast<u32*>(b2c_carve(p, 4ull * ht));
+}
+
+static u32 pow2_ge(u32 x) {
+    u32 p = 16;
+    while (p < x) p <<= 1;
+    return p;
+}
+
+static B2cLayout make_layout(int W, int V, int T_max, bool full_caps, u32 smem_budget) {
+    B2cLayout L;
+    std::memset(&L, 0, sizeof(L));
+    L.W = W;
+    L.V = V;
+    const u64 worst = static_cast<u64>(W) * static_cast<u64>(V);
+    // shared-memory tier: as many candidates as fit the budget next to the beam tables
+    u64 fixed = 64 + sel_bytes(W);
+    L.beams_in_smem = (fixed + 2 * tab_bytes(W) + tier_bytes(256, 512) <= smem_budget) ? 1 : 0;
+    if (L.beams_in_smem) fixed += 2 * tab_bytes(W);
+    u32 cap = 4096;
+    while (cap > 64 && fixed + tier_bytes(cap, pow2_ge(2 * cap)) > smem_budget) cap >>= 1;
+    // do not reserve more than the worst case needs, and keep typical configs at ~512
+    u32 want = static_cast<u32>(std::min<u64>(worst, 512));
+    want = std::max<u32>(pow2_ge(want), 64);
+    cap = std::min(cap, want);
+    L.cap_s = cap;
+    L.ht_s = pow2_ge(2 * cap);
+    if (worst > cap) {
+        L.cap_g = static_cast<u32>(std::min<u64>(worst, 0x7FFFFFFFull));
+        L.ht_g = pow2_ge(2 * L.cap_g);
+    }
+    const u64 wt = static_cast<u64>(W) * static_cast<u64>(std::max(T_max, 1));
+    L.chain_cap = static_cast<u32>(std::min<u64>(wt + 16, 0x7FFFFFF0ull));
+    L.text_cap = static_cast<u32>(std::min<u64>(full_caps ? wt + 16 : wt / 4 + 4096, 0x7FFFFFF0ull));
+    // shared memory offsets
+    u64 s = 0;
+    L.s_sc = static_cast<u32>(s); s += 64;
+    if (L.beams_in_smem) {
+        L.s_tab[0] = static_cast<u32>(s); s += tab_bytes(W);
+        L.s_tab[1] = static_cast<u32>(s); s += tab_bytes(W);
+    }
+    L.s_sel = static_cast<u32>(s); s += sel_bytes(W);
+    L.s_tier = static_cast<u32>(s); s += tier_bytes(L.cap_s, L.ht_s);
+    L.smem_bytes = static_cast<u32>(s);
+    // HBM workspace offsets
+    u64 g = 0;
+    if (!L.beams_in_smem) {
+        L.g_tab[0] = g; g += tab_bytes(W);
+        L.g_tab[1] = g; g += tab_bytes(W);
+    }
+    L.g_tier = g; if (L.cap_g) g += tier_bytes(L.cap_g, L.ht_g);
+    L.g_tk = g; g += al16(4ull * V) + al16(static_cast<u64>(V)) + 64;
+    L.g_chain = g; g += al16(sizeof(B2cChain) * static_cast<u64>(L.chain_cap));
+    L.g_text = g; g += al16(sizeof(B2cText) * static_cast<u64>(L.text_cap));
+    L.gws_bytes = (g + 255) & ~255ull;
+    return L;
+}
+
+// =========================================================================================
+// kernels
+// =========================================================================================
+struct B2cBeamArgs {
+    B2cParams P;
+    B2cLayout L;
+    int n_utts;
+    const int* order;          // utterance ids, longest first
+    u32* next;                 // work queue head
+    const u64* frame_off;
+    const int* T;
+    const u32* tok_start;
+    const u16* tok_ids;
+    const double* tok_lp;
+    u8* gws;                   // [slots][L.gws_bytes]
+    const B2cLmState* start_states;  // optional [n_utts]
+    // outputs
+    int* out_nbeams;
+    int* out_status;
+    double* out_scores;
+    int* out_ntok;
+    int* out_nwords;
+    u32* out_toks;
+    int* out_frames;
+    B2cLmState* out_states;
+};
+
+B2C_HD void b2c_beam_block(const B2cBeamArgs& A, int slot, u8* smem) {
+    const B2cLayout& L = A.L;
+    u8* g = A.gws + static_cast<u64>(slot) * L.gws_bytes;
+    B2cWork W;
+    W.sc = reinterpret_cast<B2cScalars*>(smem + L.s_sc);
+    if (L.beams_in_smem) {
+        b2c_carve_tab(smem + L.s_tab[0], L.W, W.cur);
+        b2c_carve_tab(smem + L.s_tab[1], L.W, W.nxt);
+    } else {
+        b2c_carve_tab(g + L.g_tab[0], L.W, W.cur);
+        b2c_carve_tab(g + L.g_tab[1], L.W, W.nxt);
+    }
+    {
+        u8* p = smem + L.s_sel;
+        W.phk = reinterpret_cast<u64*>(b2c_carve(p, 8ull * L.W));
+        W.ord = reinterpret_cast<u32*>(b2c_carve(p, 4ull * L.W));
+        W.pslot = reinterpret_cast<u32*>(b2c_carve(p, 4ull * L.W));
+        W.newidx = reinterpret_cast<u32*>(b2c_carve(p, 4ull * L.W));
+    }
+    b2c_carve_tier(smem + L.s_tier, L.cap_s, L.ht_s, W.tier_s);
+    if (L.cap_g) b2c_carve_tier(g + L.g_tier, L.cap_g, L.ht_g, W.tier_g);
+    else W.tier_g = W.tier_s;
+    {
+        u8* p = g + L.g_tk;
+        W.tk_ffirst = reinterpret_cast<u32*>(b2c_carve(p, 4ull * L.V));
+        W.tk_fall = reinterpret_cast<u8*>(b2c_carve(p, static_cast<u64>(L.V)));
+    }
+    W.chain = reinterpret_cast<B2cChain*>(g + L.g_chain);
+    W.chain_cap = L.chain_cap;
+    W.text = reinterpret_cast<B2cText*>(g + L.g_text);
+    W.text_cap = L.text_cap;
+    u32* s_cur = reinterpret_cast<u32*>(smem + L.s_sc + 56);  // queue ticket of this CTA
+
+    while (true) {
+        B2C_LEADER { *s_cur = b2c_atomic_add_u32(A.next, 1u); }
+        B2C_SYNC();
+        const u32 q = *s_cur;
+        if (q >= static_cast<u32>(A.n_utts)) break;
+        const int u = A.order[q];
+        const int Tn = A.T[u];
+        const u64 f0 = A.frame_off[u];
+        const u32* ts = A.tok_start + f0 + static_cast<u64>(u);
+        const u16* ids = A.tok_ids + f0 * static_cast<u64>(A.P.V);
+        const double* lps = A.tok_lp + f0 * static_cast<u64>(A.P.V);
+        b2c_utt_begin(A.P, W, A.start_states ? A.start_states + u : nullptr);
+        for (int t = 0; t < Tn; ++t) {
+            const u32 a = ts[t], b = ts[t + 1];
+            b2c_frame_step(A.P, W, t, ids + a, lps + a, static_cast<int>(b - a));
+        }
+        B2cOut O;
+        const u64 ob = static_cast<u64>(A.P.out_beams);
+        O.n_beams = A.out_nbeams + u;
+        O.status = A.out_status + u;
+        O.scores = A.out_scores + static_cast<u64>(u) * ob * 2;
+        O.n_tok = A.out_ntok + static_cast<u64>(u) * ob;
+        O.n_words = A.out_nwords + static_cast<u64>(u) * ob;
+        O.stride = static_cast<u32>(Tn) + 1;
+        O.toks = A.out_toks + ob * (f0 + static_cast<u64>(u));
+        O.frames = A.out_frames + 2 * ob * (f0 + static_cast<u64>(u));
+        O.states = A.out_states + static_cast<u64>(u) * ob;
+        b2c_finalize(A.P, W, O);
+    }
+}
+
+#ifndef B2C_HOSTSIM
+template <class T>
+__global__ void __launch_bounds__(B2C_PREP_THREADS) b2c_prepare_kernel(const B2cPrepArgs A) {
+    __shared__ B2cPrepShared sh;
+    b2c_prepare_block<T>(A, static_cast<int>(blockIdx.x), static_cast<int>(blockIdx.x), &sh);
+}
+__global__ void __launch_bounds__(B2C_BEAM_THREADS) b2c_beam_kernel(const B2cBeamArgs A) {
+    extern __shared__ __align__(16) u8 b2c_smem[];
+    b2c_beam_block(A, static_cast<int>(blockIdx.x), b2c_smem);
+}
+#endif
+
+// =========================================================================================
+// objects
+// =========================================================================================
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            e = cudaMalloc(&p, bytes);
+            want = bytes;
+        }
+        if (e != cudaSuccess) { p = nullptr; return fail(B2C_E_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class U> U* as() const { return static_cast<U*>(p); }
+};
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e != cudaSuccess) { p = nullptr; return fail(B2C_E_NOMEM, std::string("cudaMallocHost: ") + cudaGetErrorString(e)); }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <class U> U* as() const { return static_cast<U*>(p); }
+};
+
+struct b2c_lm {
+    B2cLmHost host;
+    std::map<int, const void*> dev;       // device -> blob address
+    std::map<int, void*> owned;           // device -> memory we allocated
+    std::mutex mu;
+};
+
+struct b2c_decoder {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int V = 0, is_bpe = 0;
+    std::vector<std::string> labels, clean;
+    std::vector<B2cTok> toks;
+    b2c_lm* lm = nullptr;
+    double alpha = 0.5, beta = 1.5, unk = -10.0;
+    int score_boundary = 1;
+    int n_sm = 1;
+    size_t smem_optin = 48 * 1024;
+    DevBuf d_toks, d_logits, d_meta, d_tok_start, d_tok_ids, d_tok_lp, d_rowsum, d_set, d_isprob, d_ws, d_hot, d_states,
+        d_out_small, d_out_toks, d_out_frames;
+    PinBuf h_meta, h_out_small, h_out_toks, h_out_frames;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    b2c_timings_t tm;
+};
+
+struct BeamRes {
+    std::string text;
+    std::vector<std::string> words;
+    std::vector<int32_t> frames;
+    double logit = 0, lm = 0;
+    B2cLmState st;
+};
+struct b2c_result {
+    std::vector<std::vector<BeamRes>> utts;
+    bool has_lm = false;
+};
+
+// hotword table (language_model.py:152-189): every code-point prefix of every hotword unigram
+static void build_hot(const b2c_decode_opts_t* o, std::vector<B2cHot>& tab, int& n_hot, int& min_len_all) {
+    std::map<u64, std::pair<u32, u32>> pref;  // key -> (min_len, is_word)
+    n_hot = 0;
+    min_len_all = 0;
+    for (int i = 0; i < o->n_hotwords; ++i) {
+        const char* s = o->hotwords[i];
+        if (!s) continue;
+        const size_t L = std::strlen(s);
+        size_t p = 0;
+        while (p < L) {
+            while (p < L && std::isspace(static_cast<unsigned char>(s[p]))) ++p;
+            size_t q = p;
+            while (q < L && !std::isspace(static_cast<unsigned char>(s[q]))) ++q;
+            if (q > p) {
+                ++n_hot;
+                const u32 nchars = b2c_utf8_len(s + p, q - p);
+                if (min_len_all == 0 || static_cast<int>(nchars) < min_len_all) min_len_all = static_cast<int>(nchars);
+                u64 h = 0;
+                for (size_t k = p; k < q; ++k) {
+                    h = b2c_addmod61(b2c_mulmod61(h, B2C_HASH_BASE), static_cast<u64>(static_cast<unsigned char>(s[k])) + 1);
+                    const bool boundary = (k + 1 == q) || ((static_cast<unsigned char>(s[k + 1]) & 0xC0) != 0x80);
+                    if (!boundary) continue;
+                    auto it = pref.find(h + 1);
+                    const u32 is_word = (k + 1 == q) ? 1u : 0u;
+                    if (it == pref.end()) pref[h + 1] = {nchars, is_word};
+                    else {
+                        if (nchars < it->second.first) it->second.first = nchars;
+                        it->second.second |= is_word;
+                    }
+                }
+            }
+            p = q;
+        }
+    }
+    u64 size = 16;
+    while (size < pref.size() * 2 + 2) size <<= 1;
+    tab.assign(size, B2cHot{0, 0, 0});
+    for (auto& kv : pref) {
+        u64 slot = b2c_mix64(kv.first) & (size - 1);
+        while (tab[slot].key != 0) slot = (slot + 1) & (size - 1);
+        tab[slot] = B2cHot{kv.first, kv.second.first, kv.second.second};
+    }
+}
+
+static void assemble_beam(const b2c_decoder* d, const u32* toks, int nt, const int* frames, int nw, BeamRes& br) {
+    std::string word;
+    br.words.clear();
+    for (int i = nt - 1; i >= 0; --i) {
+        const u32 tok = toks[i] & 0xFFFFu, kind = toks[i] >> 16;
+        if (kind == B2C_CK_CONT) {
+            word += d->labels[tok];
+        } else {
+            if (!word.empty()) br.words.push_back(word);
+            word = (kind == B2C_CK_BPE) ? d->clean[tok] : std::string();
+        }
+    }
+    if (!word.empty()) br.words.push_back(word);
+    br.text.clear();
+    for (size_t i = 0; i < br.words.size(); ++i) {
+        if (i) br.text += ' ';
+        br.text += br.words[i];
+    }
+    br.frames.resize(static_cast<size_t>(nw) * 2);
+    for (int w = 0; w < nw; ++w) {
+        br.frames[2 * w] = frames[2 * (nw - 1 - w)];
+        br.frames[2 * w + 1] = frames[2 * (nw - 1 - w) + 1];
+    }
+    // zip(text.split(), text_frames) (decoder.py:661) truncates to the shorter list
+    const size_t n = std::min(br.words.size(), static_cast<size_t>(nw));
+    br.words.resize(n);
+    br.frames.resize(n * 2);
+}
+
+struct MetaHost {   // one pinned staging block -> one H2D copy
+    std::vector<u64> frame_off;
+    std::vector<int> T, order;
+};
+
+template <class T>
+static int launch_prepare(b2c_decoder* d, const B2cPrepArgs& A, int n_utts) {
+#ifdef B2C_HOSTSIM
+    (void)d;
+    std::unique_ptr<B2cPrepShared> sh(new B2cPrepShared());
+    for (int u = 0; u < n_utts; ++u) b2c_prepare_block<T>(A, u, 0, sh.get());
+#else
+    b2c_prepare_kernel<T><<<n_utts, B2C_PREP_THREADS, 0, d->stream>>>(A);
+    CUDA_OK(cudaGetLastError());
+#endif
+    return 0;
+}
+
+static int launch_beam(b2c_decoder* d, const B2cBeamArgs& A, int slots) {
+#ifdef B2C_HOSTSIM
+    (void)d;
+    std::vector<u8> smem(A.L.smem_bytes + 64);
+    for (int s = 0; s < slots; ++s) b2c_beam_block(A, s, smem.data());
+#else
+    if (A.L.smem_bytes > 48 * 1024)
+        CUDA_OK(cudaFuncSetAttribute(b2c_beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(A.L.smem_bytes)));
+    b2c_beam_kernel<<<slots, B2C_BEAM_THREADS, A.L.smem_bytes, d->stream>>>(A);
+    CUDA_OK(cudaGetLastError());
+#endif
+    return 0;
+}
+
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+extern "C" {
+
+const char* b2c_last_error(void) { return g_err.c_str(); }
+int b2c_version(void) { return B2C_VERSION; }
+int b2c_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+// ---- language model -----------------------------------------------------------------------
+int b2c_lm_build_from_arpa(const char* arpa_path, const char* const* unigrams, long n_unigrams, b2c_lm_t** out) {
+    if (!arpa_path || !out) return fail(B2C_E_ARG, "null argument");
+    std::unique_ptr<b2c_lm> lm(new b2c_lm());
+    if (!b2c_lm_build(lm->host, arpa_path, unigrams, n_unigrams)) return fail(B2C_E_IO, lm->host.error);
+    *out = lm.release();
+    return 0;
+}
+int b2c_lm_blob(const b2c_lm_t* lm, const void** data, size_t* size) {
+    if (!lm || !data || !size) return fail(B2C_E_ARG, "null argument");
+    *data = lm->host.blob.data();
+    *size = lm->host.blob.size();
+    return 0;
+}
+int b2c_lm_from_blob(const void* data, size_t size, b2c_lm_t** out) {
+    if (!data || !out || size < sizeof(B2cLmHeader)) return fail(B2C_E_ARG, "bad blob");
+    const B2cLmHeader* h = static_cast<const B2cLmHeader*>(data);
+    if (h->magic != B2C_LM_MAGIC || h->total_bytes != size) return fail(B2C_E_ARG, "not a b200ctc LM blob");
+    std::unique_ptr<b2c_lm> lm(new b2c_lm());
+    lm->host.blob.assign(static_cast<const unsigned char*>(data), static_cast<const unsigned char*>(data) + size);
+    *out = lm.release();
+    return 0;
+}
+int b2c_lm_upload(b2c_lm_t* lm, int device) {
+    if (!lm) return fail(B2C_E_ARG, "null lm");
+    std::lock_guard<std::mutex> lk(lm->mu);
+    if (lm->dev.count(device)) return 0;
+    CUDA_OK(cudaSetDevice(device));
+    void* p = nullptr;
+    CUDA_OK(cudaMalloc(&p, lm->host.blob.size()));
+    CUDA_OK(cudaMemcpy(p, lm->host.blob.data(), lm->host.blob.size(), cudaMemcpyHostToDevice));
+    lm->dev[device] = p;
+    lm->owned[device] = p;
+    return 0;
+}
+int b2c_lm_adopt_device_blob(b2c_lm_t* lm, int device, const void* device_ptr, size_t size) {
+    if (!lm || !device_ptr) return fail(B2C_E_ARG, "null argument");
+    if (size != lm->host.blob.size()) return fail(B2C_E_ARG, "device blob size mismatch");
+    std::lock_guard<std::mutex> lk(lm->mu);
+    lm->dev[device] = device_ptr;
+    return 0;
+}
+void b2c_lm_destroy(b2c_lm_t* lm) {
+    if (!lm) return;
+    for (auto& kv : lm->owned) {
+        cudaSetDevice(kv.first);
+        cudaFree(kv.second);
+    }
+    delete lm;
+}
+int b2c_lm_order(const b2c_lm_t* lm) { return lm ? lm->host.header()->order : 0; }
+static B2cLmView host_view(const b2c_lm_t* lm) { return lm->host.view(lm->host.blob.data()); }
+int b2c_lm_contains(const b2c_lm_t* lm, const char* word) {
+    if (!lm || !word) return 0;
+    B2cLmView v = host_view(lm);
+    size_t n = std::strlen(word);
+    if (n == 0) return 0;
+    return b2c_vocab_find(v, b2c_hash_bytes(word, n)) ? 1 : 0;
+}
+int b2c_lm_in_unigrams(const b2c_lm_t* lm, const char* word) {
+    if (!lm || !word) return 0;
+    B2cLmView v = host_view(lm);
+    size_t n = std::strlen(word);
+    if (n == 0) return 0;
+    const B2cVocab* e = b2c_vocab_find(v, b2c_hash_bytes(word, n));
+    return (e && (e->flags & 1u)) ? 1 : 0;
+}
+int b2c_lm_has_prefix(const b2c_lm_t* lm, const char* prefix) {
+    if (!lm || !prefix) return 0;
+    B2cLmView v = host_view(lm);
+    size_t n = std::strlen(prefix);
+    if (n == 0) return v.n_unigrams > 0 ? 1 : 0;
+    return b2c_prefix_contains(v, b2c_hash_bytes(prefix, n)) ? 1 : 0;
+}
+static void to_internal(const b2c_lm_state_t* s, B2cLmState& o) {
+    o.length = s->length;
+    for (int i = 0; i < B2C_MAX_HIST; ++i) { o.words[i] = s->words[i]; o.backoff[i] = s->backoff[i]; }
+}
+static void from_internal(const B2cLmState& s, b2c_lm_state_t* o) {
+    o->length = s.length;
+    for (int i = 0; i < B2C_MAX_HIST; ++i) {
+        o->words[i] = i < static_cast<int>(s.length) ? s.words[i] : 0;
+        o->backoff[i] = i < static_cast<int>(s.length) ? s.backoff[i] : 0.0f;
+    }
+}
+void b2c_lm_begin_sentence(const b2c_lm_t* lm, b2c_lm_state_t* st) {
+    std::memset(st, 0, sizeof(*st));
+    if (!lm) return;
+    B2cLmView v = host_view(lm);
+    st->length = 1;
+    st->words[0] = v.bos_id;
+    st->backoff[0] = v.uni[v.bos_id].backoff;
+}
+void b2c_lm_null_context(const b2c_lm_t*, b2c_lm_state_t* st) { std::memset(st, 0, sizeof(*st)); }
+float b2c_lm_base_score(const b2c_lm_t* lm, const b2c_lm_state_t* in, const char* word, b2c_lm_state_t* out) {
+    B2cLmView v = host_view(lm);
+    B2cLmState a, b;
+    to_internal(in, a);
+    u32 wid = 0;
+    size_t n = std::strlen(word);
+    if (n) {
+        const B2cVocab* e = b2c_vocab_find(v, b2c_hash_bytes(word, n));
+        if (e) wid = e->id;
+    }
+    std::memset(&b, 0, sizeof(b));
+    float r = b2c_lm_base_score(v, a, wid, b);
+    from_internal(b, out);
+    return r;
+}
+
+// ---- decoder ------------------------------------------------------------------------------
+static const char* BPE_MARK = "\xE2\x96\x81";
+
+int b2c_decoder_create(const char* const* labels, int n_labels, int is_bpe, b2c_lm_t* lm, int device, b2c_decoder_t** out) {
+    if (!labels || n_labels <= 0 || n_labels > 65534 || !out) return fail(B2C_E_ARG, "bad labels");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+        return fail(B2C_E_CUDA, "no CUDA device: libb200ctc has no CPU path");
+    if (device < 0 || device >= ndev) return fail(B2C_E_ARG, "bad device index");
+    std::unique_ptr<b2c_decoder> d(new b2c_decoder());
+    d->device = device;
+    d->V = n_labels;
+    d->is_bpe = is_bpe ? 1 : 0;
+    d->lm = lm;
+    std::memset(&d->tm, 0, sizeof(d->tm));
+    bool have_blank = false;
+    for (int i = 0; i < n_labels; ++i) {
+        std::string s = labels[i] ? labels[i] : "";
+        if (s.find(' ') != std::string::npos && s != " ")
+            return fail(B2C_E_ARG, "labels containing a space inside a longer string are not supported");
+        B2cTok t;
+        std::memset(&t, 0, sizeof(t));
+        std::string clean = s;
+        if (s.empty()) { t.flags |= B2C_TF_BLANK; have_blank = true; }
+        if (!d->is_bpe && s == " ") t.flags |= B2C_TF_SPACE;
+        if (d->is_bpe) {
+            if (s.size() >= 3 && s.compare(0, 3, BPE_MARK) == 0) { t.flags |= B2C_TF_BPE_LEAD; clean = clean.substr(3); }
+            if (s.size() >= 3 && s.compare(s.size() - 3, 3, BPE_MARK) == 0) {
+                t.flags |= B2C_TF_BPE_TRAIL;
+                clean = clean.size() >= 3 ? clean.substr(0, clean.size() - 3) : std::string();
+            }
+        }
+        t.raw_hash = b2c_hash_bytes(s.data(), s.size());
+        t.raw_pow = b2c_pow_bytes(s.size());
+        t.clean_hash = b2c_hash_bytes(clean.data(), clean.size());
+        t.raw_nchars = static_cast<u16>(b2c_utf8_len(s.data(), s.size()));
+        t.clean_nchars = static_cast<u16>(b2c_utf8_len(clean.data(), clean.size()));
+        t.canon = static_cast<u16>(i);
+        for (int j = 0; j < i; ++j)
+            if (d->labels[j] == s) { t.canon = static_cast<u16>(j); break; }
+        d->labels.push_back(s);
+        d->clean.push_back(clean);
+        d->toks.push_back(t);
+    }
+    if (!have_blank) return fail(B2C_E_ARG, "labels must contain the CTC blank \"\" (pass Alphabet.labels)");
+    CUDA_OK(cudaSetDevice(device));
+    CUDA_OK(cudaStreamCreate(&d->stream));
+    for (int i = 0; i < 6; ++i) CUDA_OK(cudaEventCreate(&d->ev[i]));
+    int v = 0;
+    CUDA_OK(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device));
+    d->n_sm = v;
+    CUDA_OK(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    d->smem_optin = static_cast<size_t>(v);
+    if (d->d_toks.ensure(sizeof(B2cTok) * n_labels)) return B2C_E_NOMEM;
+    CUDA_OK(cudaMemcpy(d->d_toks.p, d->toks.data(), sizeof(B2cTok) * n_labels, cudaMemcpyHostToDevice));
+    if (lm) {
+        int rc = b2c_lm_upload(lm, device);
+        if (rc) return rc;
+    }
+    *out = d.release();
+    return 0;
+}
+
+void b2c_decoder_destroy(b2c_decoder_t* d) {
+    if (!d) return;
+    cudaSetDevice(d->device);
+    if (d->stream) cudaStreamSynchronize(d->stream);
+    DevBuf* bufs[] = {&d->d_toks, &d->d_logits, &d->d_meta, &d->d_tok_start, &d->d_tok_ids, &d->d_tok_lp, &d->d_rowsum, &d->d_set,
+                      &d->d_isprob, &d->d_ws, &d->d_hot, &d->d_states, &d->d_out_small, &d->d_out_toks, &d->d_out_frames};
+    for (DevBuf* b : bufs) b->release();
+    PinBuf* pins[] = {&d->h_meta, &d->h_out_small, &d->h_out_toks, &d->h_out_frames};
+    for (PinBuf* b : pins) b->release();
+    for (int i = 0; i < 6; ++i) if (d->ev[i]) cudaEventDestroy(d->ev[i]);
+    if (d->stream) cudaStreamDestroy(d->stream);
+    delete d;
+}
+
+int b2c_decoder_set_params(b2c_decoder_t* d, double alpha, double beta, double unk, int boundary) {
+    if (!d) return fail(B2C_E_ARG, "null decoder");
+    d->alpha = alpha;
+    d->beta = beta;
+    d->unk = unk;
+    d->score_boundary = boundary ? 1 : 0;
+    return 0;
+}
+
+void b2c_decode_opts_default(b2c_decode_opts_t* o) {
+    std::memset(o, 0, sizeof(*o));
+    o->beam_width = 100;
+    o->beam_prune_logp = -10.0;
+    o->token_min_logp = -5.0;
+    o->prune_history = 0;
+    o->hotword_weight = 10.0;
+    o->max_out_beams = 1;
+}
+
+int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t* T, int n_utts, int dtype, int is_device,
+                     const b2c_decode_opts_t* opts, b2c_result_t** out) {
+    if (!d || !opts || !out || n_utts < 0 || (n_utts > 0 && (!logits || !T))) return fail(B2C_E_ARG, "null argument");
+    if (dtype != B2C_DTYPE_F32 && dtype != B2C_DTYPE_F64) return fail(B2C_E_ARG, "dtype must be B2C_DTYPE_F32 or B2C_DTYPE_F64");
+    if (opts->beam_width < 1) return fail(B2C_E_ARG, "beam_width must be >= 1");
+    if (opts->beam_width > 65535) return fail(B2C_E_ARG, "beam_width above 65535 is not supported");
+    std::unique_ptr<b2c_result> res(new b2c_result());
+    res->utts.resize(n_utts);
+    res->has_lm = d->lm != nullptr;
+    if (n_utts == 0) { *out = res.release(); return 0; }
+    CUDA_OK(cudaSetDevice(d->device));
+    const int V = d->V;
+    const size_t esz = dtype == B2C_DTYPE_F32 ? 4 : 8;
+    std::memset(&d->tm, 0, sizeof(d->tm));
+
+    // ---- batch geometry -------------------------------------------------------------------
+    std::vector<u64> frame_off(n_utts);
+    u64 total_frames = 0;
+    int T_max = 0;
+    for (int i = 0; i < n_utts; ++i) {
+        if (T[i] < 0) return fail(B2C_E_ARG, "negative T");
+        if (T[i] > 0 && !logits[i]) return fail(B2C_E_ARG, "null logits pointer");
+        frame_off[i] = total_frames;
+        total_frames += static_cast<u64>(T[i]);
+        T_max = std::max(T_max, static_cast<int>(T[i]));
+    }
+    std::vector<int> order(n_utts);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return T[a] > T[b]; });
+    const int OB = std::max(1, std::min(opts->max_out_beams, opts->beam_width));
+
+    // ---- parameters -----------------------------------------------------------------------
+    B2cParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.V = V;
+    P.is_bpe = d->is_bpe;
+    P.beam_width = opts->beam_width;
+    P.prune_history = opts->prune_history ? 1 : 0;
+    P.out_beams = OB;
+    P.prune_logp = opts->beam_prune_logp;
+    P.token_min_logp = opts->token_min_logp;
+    P.alpha = d->alpha; P.beta = d->beta; P.unk_offset = d->unk;
+    P.log_base_change = 0x1.26bb1bbb55516p+1;  // 1.0 / math.log10(math.e) (constants.py:18)
+    P.score_boundary = d->score_boundary;
+    P.hot_weight = opts->hotword_weight;
+    P.toks = d->d_toks.as<B2cTok>();
+    if (d->lm) {
+        auto it = d->lm->dev.find(d->device);
+        if (it == d->lm->dev.end()) return fail(B2C_E_INTERNAL, "language model is not resident on this device");
+        P.lm = d->lm->host.view(it->second);
+        if (P.lm.order > B2C_MAX_ORDER) return fail(B2C_E_ARG, "n-gram order too large");
+    }
+    P.hist_n = std::max(1, P.lm.order - 1);
+    std::vector<B2cHot> hot;
+    build_hot(opts, hot, P.n_hot, P.hot_min_len_all);
+    if (d->d_hot.ensure(hot.size() * sizeof(B2cHot))) return B2C_E_NOMEM;
+    P.hot = d->d_hot.as<B2cHot>();
+    P.hot_mask = hot.size() - 1;
+
+    // ---- buffers --------------------------------------------------------------------------
+    const u64 n_entries = std::max<u64>(total_frames * static_cast<u64>(V), 1);
+    const bool contiguous_dev = [&]() {
+        if (!is_device) return false;
+        for (int i = 0; i + 1 < n_utts; ++i) {
+            if (T[i + 1] == 0) continue;
+            const char* expect = static_cast<const char*>(logits[0]) + frame_off[i + 1] * V * esz;
+            if (static_cast<const char*>(logits[i + 1]) != expect) return false;
+        }
+        return T[0] > 0 || n_utts == 1;
+    }();
+    if (!contiguous_dev && d->d_logits.ensure(std::max<u64>(total_frames * V * esz, 16))) return B2C_E_NOMEM;
+    const size_t meta_bytes = al16(8ull * n_utts) + 2 * al16(4ull * n_utts) + 16;
+    if (d->d_meta.ensure(meta_bytes) || d->h_meta.ensure(meta_bytes)) return B2C_E_NOMEM;
+    if (d->d_tok_start.ensure(4 * (total_frames + n_utts + 1)) || d->d_tok_ids.ensure(2 * n_entries) ||
+        d->d_tok_lp.ensure(8 * n_entries) || d->d_rowsum.ensure(std::max<u64>(8 * total_frames, 16)) ||
+        d->d_isprob.ensure(4ull * n_utts))
+        return B2C_E_NOMEM;
+    u32 set_cap = 16;
+    while (set_cap < 8u * (static_cast<u32>(V) + 1)) set_cap <<= 1;
+    if (V > 32) {
+        if (d->d_set.ensure(2ull * set_cap * 2 * B2C_PREP_WARPS * n_utts)) return B2C_E_NOMEM;
+    }
+    // layout + slots
+    const u32 smem_budget = static_cast<u32>(std::min<size_t>(d->smem_optin, 200 * 1024));
+    auto plan = [&](bool full, B2cLayout& L, int& slots) {
+        L = make_layout(opts->beam_width, V, T_max, full, smem_budget);
+        int per_sm = static_cast<int>(std::max<u64>(1, std::min<u64>(16, (220 * 1024) / std::max<u32>(L.smem_bytes, 1024))));
+        slots = std::min(n_utts, d->n_sm * per_sm);
+        // keep the HBM workspace bounded (16 GiB)
+        const u64 budget = 16ull << 30;
+        if (static_cast<u64>(slots) * L.gws_bytes > budget) slots = static_cast<int>(std::max<u64>(1, budget / L.gws_bytes));
+    };
+    B2cLayout L;
+    int slots = 1;
+    plan(false, L, slots);
+    if (L.smem_bytes > d->smem_optin) return fail(B2C_E_ARG, "beam_width too large for the shared-memory selection arrays");
+    if (d->d_ws.ensure(static_cast<u64>(slots) * L.gws_bytes)) return B2C_E_NOMEM;
+    // outputs
+    const u64 off_nb = 0, off_st = al16(4ull * n_utts), off_sc = off_st + al16(4ull * n_utts),
+              off_nt = off_sc + al16(16ull * OB * n_utts), off_nw = off_nt + al16(4ull * OB * n_utts),
+              off_ls = off_nw + al16(4ull * OB * n_utts), small_bytes = off_ls + al16(sizeof(B2cLmState) * static_cast<u64>(OB) * n_utts);
+    const u64 tok_bytes = 4ull * OB * (total_frames + n_utts), frm_bytes = 2 * tok_bytes;
+    if (d->d_out_small.ensure(small_bytes) || d->h_out_small.ensure(small_bytes) || d->d_out_toks.ensure(tok_bytes) ||
+        d->h_out_toks.ensure(tok_bytes) || d->d_out_frames.ensure(frm_bytes) || d->h_out_frames.ensure(frm_bytes))
+        return B2C_E_NOMEM;
+    if (opts->lm_start_states) {
+        if (d->d_states.ensure(sizeof(B2cLmState) * static_cast<u64>(n_utts))) return B2C_E_NOMEM;
+    }
+
+    // ---- host -> device -------------------------------------------------------------------
+    cudaStream_t st = d->stream;
+    CUDA_OK(cudaEventRecord(d->ev[0], st));
+    u8* hm = d->h_meta.as<u8>();
+    u64* h_fo = reinterpret_cast<u64*>(hm);
+    int* h_T = reinterpret_cast<int*>(hm + al16(8ull * n_utts));
+    int* h_ord = reinterpret_cast<int*>(hm + al16(8ull * n_utts) + al16(4ull * n_utts));
+    u32* h_next = reinterpret_cast<u32*>(hm + al16(8ull * n_utts) + 2 * al16(4ull * n_utts));
+    for (int i = 0; i < n_utts; ++i) { h_fo[i] = frame_off[i]; h_T[i] = T[i]; h_ord[i] = order[i]; }
+    *h_next = 0;
+    CUDA_OK(cudaMemcpyAsync(d->d_meta.p, hm, meta_bytes, cudaMemcpyHostToDevice, st));
+    u8* dm = d->d_meta.as<u8>();
+    const u64* d_fo = reinterpret_cast<const u64*>(dm);
+    const int* d_T = reinterpret_cast<const int*>(dm + al16(8ull * n_utts));
+    const int* d_ord = reinterpret_cast<const int*>(dm + al16(8ull * n_utts) + al16(4ull * n_utts));
+    u32* d_next = reinterpret_cast<u32*>(dm + al16(8ull * n_utts) + 2 * al16(4ull * n_utts));
+    d->tm.h2d_bytes += static_cast<long long>(meta_bytes);
+    const void* d_logits = nullptr;
+    if (contiguous_dev) {
+        d_logits = logits[0];
+    } else {
+        d_logits = d->d_logits.p;
+        // coalesce runs of utterances that are adjacent in the source into one copy
+        int i = 0;
+        while (i < n_utts) {
+            if (T[i] == 0) { ++i; continue; }
+            int j = i;
+            u64 bytes = static_cast<u64>(T[i]) * V * esz;
+            while (j + 1 < n_utts && T[j + 1] > 0 &&
+                   static_cast<const char*>(logits[j + 1]) == static_cast<const char*>(logits[i]) + bytes) {
+                ++j;
+                bytes += static_cast<u64>(T[j]) * V * esz;
+            }
+            CUDA_OK(cudaMemcpyAsync(d->d_logits.as<char>() + frame_off[i] * V * esz, logits[i], bytes,
+                                    is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+            if (!is_device) d->tm.h2d_bytes += static_cast<long long>(bytes);
+            i = j + 1;
+        }
+    }
+    CUDA_OK(cudaMemcpyAsync(d->d_hot.p, hot.data(), hot.size() * sizeof(B2cHot), cudaMemcpyHostToDevice, st));
+    const B2cLmState* d_start = nullptr;
+    std::vector<B2cLmState> start_host;
+    if (opts->lm_start_states) {
+        start_host.resize(n_utts);
+        for (int i = 0; i < n_utts; ++i) to_internal(opts->lm_start_states + i, start_host[i]);
+        CUDA_OK(cudaMemcpyAsync(d->d_states.p, start_host.data(), sizeof(B2cLmState) * n_utts, cudaMemcpyHostToDevice, st));
+        d_start = d->d_states.as<B2cLmState>();
+    }
+
+    // ---- prepare kernel ---------------------------------------------------------------------
+    B2cPrepArgs PA;
+    std::memset(&PA, 0, sizeof(PA));
+    PA.logits = d_logits;
+    PA.frame_off = d_fo;
+    PA.T = d_T;
+    PA.V = V;
+    PA.token_min_logp = opts->token_min_logp;
+    PA.tok_start = d->d_tok_start.as<u32>();
+    PA.tok_ids = d->d_tok_ids.as<u16>();
+    PA.tok_lp = d->d_tok_lp.as<double>();
+    PA.rowsum = d->d_rowsum.p;
+    PA.set_scratch = d->d_set.as<u16>();
+    PA.set_cap = set_cap;
+    PA.is_prob = d->d_isprob.as<int>();
+    CUDA_OK(cudaEventRecord(d->ev[1], st));
+    int rc = dtype == B2C_DTYPE_F32 ? launch_prepare<float>(d, PA, n_utts) : launch_prepare<double>(d, PA, n_utts);
+    if (rc) return rc;
+    CUDA_OK(cudaEventRecord(d->ev[2], st));
+    d->tm.launches += 1;
+
+    // ---- beam kernel (+ one retry with worst-case arenas for utterances that overflowed) --------
+    B2cBeamArgs BA;
+    std::memset(&BA, 0, sizeof(BA));
+    BA.P = P;
+    BA.L = L;
+    BA.n_utts = n_utts;
+    BA.order = d_ord;
+    BA.next = d_next;
+    BA.frame_off = d_fo;
+    BA.T = d_T;
+    BA.tok_start = PA.tok_start;
+    BA.tok_ids = PA.tok_ids;
+    BA.tok_lp = PA.tok_lp;
+    BA.gws = d->d_ws.as<u8>();
+    BA.start_states = d_start;
+    u8* ds = d->d_out_small.as<u8>();
+    BA.out_nbeams = reinterpret_cast<int*>(ds + off_nb);
+    BA.out_status = reinterpret_cast<int*>(ds + off_st);
+    BA.out_scores = reinterpret_cast<double*>(ds + off_sc);
+    BA.out_ntok = reinterpret_cast<int*>(ds + off_nt);
+    BA.out_nwords = reinterpret_cast<int*>(ds + off_nw);
+    BA.out_states = reinterpret_cast<B2cLmState*>(ds + off_ls);
+    BA.out_toks = d->d_out_toks.as<u32>();
+    BA.out_frames = d->d_out_frames.as<int>();
+    rc = launch_beam(d, BA, slots);
+    if (rc) return rc;
+    CUDA_OK(cudaEventRecord(d->ev[3], st));
+    d->tm.launches += 1;
+
+    // ---- device -> host -------------------------------------------------------------------
+    CUDA_OK(cudaMemcpyAsync(d->h_out_small.p, d->d_out_small.p, small_bytes, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(d->h_out_toks.p, d->d_out_toks.p, tok_bytes, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(d->h_out_frames.p, d->d_out_frames.p, frm_bytes, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaEventRecord(d->ev[4], st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    d->tm.d2h_bytes += static_cast<long long>(small_bytes + tok_bytes + frm_bytes);
+
+    u8* hs = d->h_out_small.as<u8>();
+    int* h_status = reinterpret_cast<int*>(hs + off_st);
+    std::vector<int> failed;
+    for (int i = 0; i < n_utts; ++i) if (h_status[i] != B2C_OK) failed.push_back(i);
+    if (!failed.empty()) {
+        // second pass: only the failed utterances, worst-case arenas
+        B2cLayout L2;
+        int slots2 = 1;
+        plan(true, L2, slots2);
+        slots2 = std::min<int>(slots2, static_cast<int>(failed.size()));
+        if (d->d_ws.ensure(static_cast<u64>(slots2) * L2.gws_bytes)) return B2C_E_NOMEM;
+        for (size_t i = 0; i < failed.size(); ++i) h_ord[i] = failed[i];
+        *h_next = 0;
+        CUDA_OK(cudaMemcpyAsync(const_cast<int*>(d_ord), h_ord, 4 * failed.size(), cudaMemcpyHostToDevice, st));
+        CUDA_OK(cudaMemcpyAsync(d_next, h_next, 4, cudaMemcpyHostToDevice, st));
+        BA.L = L2;
+        BA.gws = d->d_ws.as<u8>();
+        BA.n_utts = static_cast<int>(failed.size());
+        rc = launch_beam(d, BA, slots2);
+        if (rc) return rc;
+        d->tm.launches += 1;
+        CUDA_OK(cudaMemcpyAsync(d->h_out_small.p, d->d_out_small.p, small_bytes, cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaMemcpyAsync(d->h_out_toks.p, d->d_out_toks.p, tok_bytes, cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaMemcpyAsync(d->h_out_frames.p, d->d_out_frames.p, frm_bytes, cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaStreamSynchronize(st));
+        for (int i : failed)
+            if (h_status[i] != B2C_OK) return fail(B2C_E_INTERNAL, "beam kernel workspace overflow (status " + std::to_string(h_status[i]) + ")");
+    }
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, d->ev[1], d->ev[2]) == cudaSuccess) d->tm.ms_prepare = ms;
+    if (cudaEventElapsedTime(&ms, d->ev[2], d->ev[3]) == cudaSuccess) d->tm.ms_beam = ms;
+    if (cudaEventElapsedTime(&ms, d->ev[0], d->ev[4]) == cudaSuccess) d->tm.ms_total = ms;
+    d->tm.frames = static_cast<long long>(total_frames);
+    // total selected tokens = last tok_start of the last utterance ... summed per utterance is not
+    // available without a reduction; report the last utterance's end offset only when B == 1
+    d->tm.tokens = 0;
+
+    // ---- assemble results -------------------------------------------------------------------
+    const int* h_nb = reinterpret_cast<const int*>(hs + off_nb);
+    const double* h_sc = reinterpret_cast<const double*>(hs + off_sc);
+    const int* h_nt = reinterpret_cast<const int*>(hs + off_nt);
+    const int* h_nw = reinterpret_cast<const int*>(hs + off_nw);
+    const B2cLmState* h_ls = reinterpret_cast<const B2cLmState*>(hs + off_ls);
+    const u32* h_toks = d->h_out_toks.as<u32>();
+    const int* h_frames = d->h_out_frames.as<int>();
+    for (int u = 0; u < n_utts; ++u) {
+        const int nb = h_nb[u];
+        res->utts[u].resize(nb);
+        const u64 base = static_cast<u64>(OB) * (frame_off[u] + static_cast<u64>(u));
+        const u64 stride = static_cast<u64>(T[u]) + 1;
+        for (int r = 0; r < nb; ++r) {
+            BeamRes& br = res->utts[u][r];
+            const u64 k = static_cast<u64>(u) * OB + r;
+            br.logit = h_sc[2 * k];
+            br.lm = h_sc[2 * k + 1];
+            br.st = h_ls[k];
+            assemble_beam(d, h_toks + base + r * stride, h_nt[k], h_frames + 2 * (base + r * stride), h_nw[k], br);
+        }
+    }
+    *out = res.release();
+    return 0;
+}
+
+// ---- results ------------------------------------------------------------------------------
+void b2c_result_free(b2c_result_t* r) { delete r; }
+int b2c_result_n_utts(const b2c_result_t* r) { return r ? static_cast<int>(r->utts.size()) : 0; }
+int b2c_result_n_beams(const b2c_result_t* r, int u) { return static_cast<int>(r->utts[u].size()); }
+const char* b2c_result_text(const b2c_result_t* r, int u, int b) { return r->utts[u][b].text.c_str(); }
+double b2c_result_logit_score(const b2c_result_t* r, int u, int b) { return r->utts[u][b].logit; }
+double b2c_result_lm_score(const b2c_result_t* r, int u, int b) { return r->utts[u][b].lm; }
+int b2c_result_n_words(const b2c_result_t* r, int u, int b) { return static_cast<int>(r->utts[u][b].words.size()); }
+const char* b2c_result_word(const b2c_result_t* r, int u, int b, int w) { return r->utts[u][b].words[w].c_str(); }
+const int32_t* b2c_result_frames(const b2c_result_t* r, int u, int b) { return r->utts[u][b].frames.data(); }
+int b2c_result_lm_state(const b2c_result_t* r, int u, int b, b2c_lm_state_t* out) {
+    if (!r->has_lm) return 0;
+    from_internal(r->utts[u][b].st, out);
+    return 1;
+}
+int b2c_decoder_last_timings(const b2c_decoder_t* d, b2c_timings_t* out) {
+    if (!d || !out) return fail(B2C_E_ARG, "null argument");
+    *out = d->tm;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,83 @@
+// b200ctc -- the tiny execution-model layer the kernel bodies are written against.
+//
+// Kernel bodies are written as a sequence of phases separated by block barriers:
+//
+//     B2C_FOR(i, n) { ... work item i ... }      // items strided over the CTA's threads
+//     B2C_SYNC();
+//     B2C_LEADER { ... one thread ... }
+//
+// Compiled by nvcc for sm_100a these are the obvious CUDA constructs.  Compiled by g++ with
+// B2C_HOSTSIM (tests/hostsim only -- NOT a product fallback, the product library contains no
+// CPU path) a phase is a plain loop over all items and a barrier is a no-op, i.e. one legal
+// interleaving of the CUDA execution.  Code outside B2C_FOR / B2C_LEADER between barriers
+// must be block-uniform (it reads only kernel arguments and shared scalars).
+#pragma once
+#include "b2c_common.h"
+
+#if defined(__CUDA_ARCH__)
+#define B2C_FOR(i, n) for (int i = static_cast<int>(threadIdx.x); i < static_cast<int>(n); i += static_cast<int>(blockDim.x))
+#define B2C_SYNC() __syncthreads()
+#define B2C_LEADER if (threadIdx.x == 0)
+#define B2C_FOR_WARP(w, nw) for (int w = static_cast<int>(threadIdx.x >> 5), _once = 1; _once; _once = 0)
+#define B2C_NWARPS() (static_cast<int>(blockDim.x >> 5))
+#else
+#define B2C_FOR(i, n) for (int i = 0; i < static_cast<int>(n); ++i)
+#define B2C_SYNC() ((void)0)
+#define B2C_LEADER if (true)
+#define B2C_FOR_WARP(w, nw) for (int w = 0; w < static_cast<int>(nw); ++w)
+#define B2C_NWARPS() (8)
+#endif
+
+// block-scope atomics on shared or global memory
+B2C_HD u32 b2c_atomic_cas_u32(u32* p, u32 cmp, u32 val) {
+#if defined(__CUDA_ARCH__)
+    return atomicCAS(p, cmp, val);
+#else
+    u32 old = *p;
+    if (old == cmp) *p = val;
+    return old;
+#endif
+}
+B2C_HD u32 b2c_atomic_add_u32(u32* p, u32 v) {
+#if defined(__CUDA_ARCH__)
+    return atomicAdd(p, v);
+#else
+    u32 old = *p;
+    *p = old + v;
+    return old;
+#endif
+}
+B2C_HD void b2c_atomic_min_u32(u32* p, u32 v) {
+#if defined(__CUDA_ARCH__)
+    atomicMin(p, v);
+#else
+    if (v < *p) *p = v;
+#endif
+}
+B2C_HD void b2c_atomic_max_u32(u32* p, u32 v) {
+#if defined(__CUDA_ARCH__)
+    atomicMax(p, v);
+#else
+    if (v > *p) *p = v;
+#endif
+}
+B2C_HD void b2c_atomic_max_u64(u64* p, u64 v) {
+#if defined(__CUDA_ARCH__)
+    atomicMax(p, v);
+#else
+    if (v > *p) *p = v;
+#endif
+}
+B2C_HD void b2c_atomic_or_u32(u32* p, u32 v) {
+#if defined(__CUDA_ARCH__)
+    atomicOr(p, v);
+#else
+    *p |= v;
+#endif
+}
+
+// _sum_log_scores (reference decoder.py:170-177), float64, symmetric in its arguments
+B2C_HD double b2c_sum_log_scores(double s1, double s2) {
+    if (s1 >= s2) return s1 + log(1 + exp(s2 - s1));
+    return s2 + log(1 + exp(s1 - s2));
+}

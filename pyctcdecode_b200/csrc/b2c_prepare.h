@@ -1,0 +1,503 @@
+// b200ctc -- prepare kernel body: input normalisation + per-frame token selection.
+//
+// One CTA per utterance.  Restates reference decoder.py:756-765 (probabilities vs logits,
+// log-softmax, clipping) and decoder.py:444-445 (tokens >= token_min_logp united with the
+// argmax, in CPython set iteration order) and writes one compact (token id, log-prob) list
+// per frame, so that the beam kernel never touches the [T,V] matrix again.
+//
+// Streaming and HBM bound: every logit is read from HBM once (the second and third pass of
+// a row hit L1/L2), algorithmic bytes per frame = V * sizeof(dtype).
+//
+// Numerical definition shared with the oracle (oracle/ctc_oracle.cpp normalise_rows):
+//   logits branch  d = fl_T(x - max), S = sum exp((double)d) in "warp order" (32 lane-strided
+//                  partial sums, then xor butterfly 16,8,4,2,1), lp = fl_T((double)d - log S),
+//                  clipped in float64 to [log(1e-15), 0];
+//   probs branch   lp = fl_T(log((double)clip(x, fl_T(1e-15), 1)));
+//   the branch decision is math.isclose(x.sum(axis=1).mean(), 1) evaluated bit-exactly like
+//   numpy does (pairwise summation in the input dtype).
+#pragma once
+#include "b2c_cta.h"
+
+// ---------------------------------------------------------------------------------------
+// numpy pairwise summation (numpy/_core/src/umath/loops_utils.h.src, PW_BLOCKSIZE = 128)
+// ---------------------------------------------------------------------------------------
+template <class T>
+B2C_HD T b2c_np_leaf_sum(const T* a, long n) {
+    if (n < 8) {
+        T res = static_cast<T>(-0.0);
+        for (long i = 0; i < n; ++i) res = res + a[i];
+        return res;
+    }
+    T r0 = a[0], r1 = a[1], r2 = a[2], r3 = a[3], r4 = a[4], r5 = a[5], r6 = a[6], r7 = a[7];
+    long i;
+    for (i = 8; i < n - (n % 8); i += 8) {
+        r0 = r0 + a[i + 0]; r1 = r1 + a[i + 1]; r2 = r2 + a[i + 2]; r3 = r3 + a[i + 3];
+        r4 = r4 + a[i + 4]; r5 = r5 + a[i + 5]; r6 = r6 + a[i + 6]; r7 = r7 + a[i + 7];
+    }
+    T res = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
+    for (; i < n; ++i) res = res + a[i];
+    return res;
+}
+
+// full pairwise sum; `leaf` returns the sum of the leaf block [off, off+n) (n <= 128)
+struct B2cPwFrame { long off, n; int st; };
+template <class T, class LeafFn>
+B2C_HD T b2c_np_pairwise_generic(long n, LeafFn leaf) {
+    B2cPwFrame stk[48];
+    T left[48];
+    int sp = 0;
+    T ret = static_cast<T>(0);
+    stk[0].off = 0; stk[0].n = n; stk[0].st = 0;
+    sp = 1;
+    while (sp > 0) {
+        B2cPwFrame& f = stk[sp - 1];
+        if (f.n <= 128) { ret = leaf(f.off, f.n); --sp; continue; }
+        long n2 = f.n / 2;
+        n2 -= n2 % 8;
+        if (f.st == 0) {
+            f.st = 1;
+            stk[sp].off = f.off; stk[sp].n = n2; stk[sp].st = 0;
+            ++sp;
+        } else if (f.st == 1) {
+            left[sp - 1] = ret;
+            f.st = 2;
+            stk[sp].off = f.off + n2; stk[sp].n = f.n - n2; stk[sp].st = 0;
+            ++sp;
+        } else {
+            ret = left[sp - 1] + ret;
+            --sp;
+        }
+    }
+    return ret;
+}
+template <class T>
+struct B2cLeafDirect {
+    const T* a;
+    B2C_HD T operator()(long off, long n) const { return b2c_np_leaf_sum(a + off, n); }
+};
+template <class T>
+B2C_HD T b2c_np_pairwise(const T* a, long n) {
+    B2cLeafDirect<T> lf;
+    lf.a = a;
+    return b2c_np_pairwise_generic<T>(n, lf);
+}
+
+// math.isclose(x, 1.0) with the default rel_tol=1e-9, abs_tol=0
+B2C_HD bool b2c_isclose_one(double x) {
+    if (x == 1.0) return true;
+    if (!(x - x == 0.0)) return false;  // inf or nan
+    double diff = fabs(1.0 - x);
+    return (diff <= fabs(1e-9 * 1.0)) || (diff <= fabs(1e-9 * x));
+}
+
+// ---------------------------------------------------------------------------------------
+// per-element log-probability
+// ---------------------------------------------------------------------------------------
+template <class T>
+B2C_HD double b2c_lp_logit(T x, T m, double ls) {
+    const T d = x - m;
+    double lp = static_cast<double>(static_cast<T>(static_cast<double>(d) - ls));
+    if (lp < B2C_LOG_MIN_CLIP) lp = B2C_LOG_MIN_CLIP;
+    if (lp > 0.0) lp = 0.0;
+    return lp;
+}
+template <class T>
+B2C_HD double b2c_lp_prob(T x) {
+    const T lo = static_cast<T>(1e-15);
+    T c = x;
+    if (c < lo) c = lo;
+    if (c > static_cast<T>(1)) c = static_cast<T>(1);
+    return static_cast<double>(static_cast<T>(log(static_cast<double>(c))));
+}
+template <class T>
+B2C_HD double b2c_lp(T x, bool is_prob, T m, double ls) { return is_prob ? b2c_lp_prob<T>(x) : b2c_lp_logit<T>(x, m, ls); }
+
+// ---------------------------------------------------------------------------------------
+// CPython 3.12 set of small non-negative ints (Objects/setobject.c), tables of u16.
+// Two ping-pong buffers of `cap` entries each; 0xFFFF marks an empty slot.
+// ---------------------------------------------------------------------------------------
+struct B2cPySet {
+    u16* buf[2];
+    int cur;
+    u32 mask, fill;
+};
+B2C_HD void b2c_pyset_clear(u16* t, u32 size) { for (u32 i = 0; i < size; ++i) t[i] = 0xFFFFu; }
+B2C_HD void b2c_pyset_init(B2cPySet& s, u16* b0, u16* b1) {
+    s.buf[0] = b0; s.buf[1] = b1; s.cur = 0; s.mask = 7; s.fill = 0;
+    b2c_pyset_clear(b0, 8);
+}
+B2C_HD void b2c_pyset_insert_clean(u16* t, u32 mask, u32 key) {
+    u32 perturb = key;
+    u32 i = key & mask;
+    while (true) {
+        if (t[i] == 0xFFFFu) { t[i] = static_cast<u16>(key); return; }
+        if (i + 9 <= mask) {
+            for (u32 j = 1; j <= 9; ++j)
+                if (t[i + j] == 0xFFFFu) { t[i + j] = static_cast<u16>(key); return; }
+        }
+        perturb >>= 5;
+        i = (i * 5 + 1 + perturb) & mask;
+    }
+}
+B2C_HD void b2c_pyset_resize(B2cPySet& s, u32 minused) {
+    u32 newsize = 8;
+    while (newsize <= minused) newsize <<= 1;
+    u16* old = s.buf[s.cur];
+    u16* nt = s.buf[s.cur ^ 1];
+    b2c_pyset_clear(nt, newsize);
+    for (u32 i = 0; i <= s.mask; ++i)
+        if (old[i] != 0xFFFFu) b2c_pyset_insert_clean(nt, newsize - 1, old[i]);
+    s.cur ^= 1;
+    s.mask = newsize - 1;
+}
+B2C_HD void b2c_pyset_add(B2cPySet& s, u32 key) {
+    u16* t = s.buf[s.cur];
+    u32 perturb = key;
+    u32 i = key & s.mask;
+    while (true) {
+        const u32 probes = (i + 9 <= s.mask) ? 9u : 0u;
+        for (u32 j = 0; j <= probes; ++j) {
+            const u16 e = t[i + j];
+            if (e == 0xFFFFu) {
+                t[i + j] = static_cast<u16>(key);
+                ++s.fill;
+                if (s.fill * 5 >= s.mask * 3) b2c_pyset_resize(s, s.fill > 50000 ? s.fill * 2 : s.fill * 4);
+                return;
+            }
+            if (e == key) return;
+        }
+        perturb >>= 5;
+        i = (i * 5 + 1 + perturb) & s.mask;
+    }
+}
+// result = copy(s) | {extra}: set_copy (set_merge into an empty set) then set_merge of a 1-element set.
+// On return s holds the result; iterate slots 0..mask ascending for the iteration order.
+B2C_HD void b2c_pyset_copy_or(B2cPySet& s, u32 extra) {
+    // --- copy: new empty table with mask 7 receives all of s
+    const u32 used = s.fill;
+    u32 nmask = 7;
+    if (used > 0) {
+        if ((0 + used) * 5 >= nmask * 3) {
+            u32 newsize = 8;
+            while (newsize <= used * 2) newsize <<= 1;
+            nmask = newsize - 1;
+        }
+        if (nmask != s.mask) {
+            // different size: set_insert_clean in slot order of the source
+            u16* old = s.buf[s.cur];
+            u16* nt = s.buf[s.cur ^ 1];
+            b2c_pyset_clear(nt, nmask + 1);
+            for (u32 i = 0; i <= s.mask; ++i)
+                if (old[i] != 0xFFFFu) b2c_pyset_insert_clean(nt, nmask, old[i]);
+            s.cur ^= 1;
+            s.mask = nmask;
+        }
+        // same size: slots are copied verbatim -> nothing to do
+    } else {
+        b2c_pyset_clear(s.buf[s.cur], 8);
+        s.mask = 7;
+    }
+    // --- merge {extra}
+    if ((s.fill + 1) * 5 >= s.mask * 3) b2c_pyset_resize(s, (s.fill + 1) * 2);
+    if (s.fill == 0) {
+        // empty target, same mask (7) as the one-element source: slot copy
+        s.buf[s.cur][extra & 7] = static_cast<u16>(extra);
+        s.fill = 1;
+        return;
+    }
+    b2c_pyset_add(s, extra);
+}
+
+// ---------------------------------------------------------------------------------------
+// kernel body
+// ---------------------------------------------------------------------------------------
+struct B2cPrepArgs {
+    const void* logits;      // packed [total_frames, V]
+    const u64* frame_off;    // [B]
+    const int* T;            // [B]
+    int V;
+    double token_min_logp;
+    u32* tok_start;          // [total_frames + B]: utterance u owns [frame_off[u]+u, +T+1)
+    u16* tok_ids;            // [total_frames * V]: utterance u owns [frame_off[u]*V, ...)
+    double* tok_lp;
+    void* rowsum;            // [total_frames] scratch, input dtype
+    u16* set_scratch;        // [grid][nwarps][2][set_cap] spill space for large token sets
+    u32 set_cap;             // power of two >= 8 * (V + 1)
+    int* is_prob;            // [B] decision taken (diagnostics / tests)
+};
+
+#define B2C_PREP_WARPS 8
+#define B2C_PREP_SMEM_SET 128       // entries per smem set buffer (enough for 32 selected tokens)
+#define B2C_PREP_LEAF_CAP 1024
+
+struct B2cPrepShared {
+    double leaf_sum[B2C_PREP_LEAF_CAP];
+    u32 counts[B2C_PREP_WARPS];
+    u32 base;
+    int is_prob;
+    u16 sets[B2C_PREP_WARPS][2][B2C_PREP_SMEM_SET];
+};
+
+template <class T>
+struct B2cLeafShared {
+    const double* sums;
+    mutable int next;
+    B2C_HD T operator()(long, long) const { return static_cast<T>(sums[next++]); }
+};
+
+// row statistics: max, log-sum-exp, argmax of the clipped log-probs, and the selected set
+// fed in ascending order into `set`.  Warp-cooperative on the device, a plain loop in hostsim.
+template <class T>
+B2C_HD void b2c_prep_row(const T* row, int V, bool is_prob, double thr, int lane, B2cPySet& set, T& m_out,
+                         double& ls_out, int& amax_out, u32& nsel_out) {
+#if defined(__CUDA_ARCH__)
+    const unsigned full = 0xFFFFFFFFu;
+    T m = static_cast<T>(0);
+    double ls = 0.0;
+    if (!is_prob) {
+        bool have = false;
+        for (int v = lane; v < V; v += 32) {
+            const T x = row[v];
+            if (!have || x > m) { m = x; have = true; }
+        }
+        for (int off = 16; off >= 1; off >>= 1) {
+            const T o = __shfl_xor_sync(full, m, off);
+            const int oh = __shfl_xor_sync(full, have ? 1 : 0, off);
+            if (oh && (!have || o > m)) { m = o; have = true; }
+        }
+        if (!(static_cast<double>(m) - static_cast<double>(m) == 0.0)) m = static_cast<T>(0);
+        double part = 0.0;
+        for (int v = lane; v < V; v += 32) part += exp(static_cast<double>(static_cast<T>(row[v] - m)));
+        for (int off = 16; off >= 1; off >>= 1) part = part + __shfl_xor_sync(full, part, off);
+        ls = log(part);
+    }
+    // argmax (first maximum) and selection
+    double best = 0.0;
+    int besti = -1;
+    u32 nsel = 0;
+    if (lane == 0) b2c_pyset_init(set, set.buf[0], set.buf[1]);
+    for (int base = 0; base < V; base += 32) {
+        const int v = base + lane;
+        bool sel = false;
+        if (v < V) {
+            const double lp = b2c_lp<T>(row[v], is_prob, m, ls);
+            if (besti < 0 || lp > best) { best = lp; besti = v; }
+            sel = lp >= thr;
+        }
+        unsigned mask = __ballot_sync(full, sel);
+        nsel += __popc(mask);
+        if (lane == 0) {
+            while (mask) {
+                const int bit = __ffs(mask) - 1;
+                mask &= mask - 1;
+                b2c_pyset_add(set, static_cast<u32>(base + bit));
+            }
+        }
+        __syncwarp();
+    }
+    for (int off = 16; off >= 1; off >>= 1) {
+        const double ob = __shfl_xor_sync(full, best, off);
+        const int oi = __shfl_xor_sync(full, besti, off);
+        if (oi >= 0 && (besti < 0 || ob > best || (ob == best && oi < besti))) { best = ob; besti = oi; }
+    }
+    m_out = m; ls_out = ls; amax_out = besti; nsel_out = nsel;
+#else
+    (void)lane;
+    T m = static_cast<T>(0);
+    double ls = 0.0;
+    if (!is_prob) {
+        m = row[0];
+        for (int v = 1; v < V; ++v) if (row[v] > m) m = row[v];
+        if (!(static_cast<double>(m) - static_cast<double>(m) == 0.0)) m = static_cast<T>(0);
+        double part[32];
+        for (int l = 0; l < 32; ++l) {
+            double s = 0.0;
+            for (int v = l; v < V; v += 32) s += exp(static_cast<double>(static_cast<T>(row[v] - m)));
+            part[l] = s;
+        }
+        for (int off = 16; off >= 1; off >>= 1) {
+            double nxt[32];
+            for (int l = 0; l < 32; ++l) nxt[l] = part[l] + part[l ^ off];
+            for (int l = 0; l < 32; ++l) part[l] = nxt[l];
+        }
+        ls = log(part[0]);
+    }
+    double best = 0.0;
+    int besti = -1;
+    u32 nsel = 0;
+    b2c_pyset_init(set, set.buf[0], set.buf[1]);
+    for (int v = 0; v < V; ++v) {
+        const double lp = b2c_lp<T>(row[v], is_prob, m, ls);
+        if (besti < 0 || lp > best) { best = lp; besti = v; }
+        if (lp >= thr) { ++nsel; b2c_pyset_add(set, static_cast<u32>(v)); }
+    }
+    m_out = m; ls_out = ls; amax_out = besti; nsel_out = nsel;
+#endif
+}
+
+template <class T>
+B2C_HD void b2c_prepare_block(const B2cPrepArgs& A, int u, int block_idx, B2cPrepShared* sh) {
+    const int Tn = A.T[u];
+    const int V = A.V;
+    const u64 f0 = A.frame_off[u];
+    const T* x = static_cast<const T*>(A.logits) + f0 * static_cast<u64>(V);
+    T* rs = static_cast<T*>(A.rowsum) + f0;
+    u32* tstart = A.tok_start + f0 + static_cast<u64>(u);
+    u16* ids = A.tok_ids + f0 * static_cast<u64>(V);
+    double* lps = A.tok_lp + f0 * static_cast<u64>(V);
+
+    // ---- phase A: numpy-exact row sums ---------------------------------------------------
+    B2C_FOR(t, Tn) { rs[t] = b2c_np_pairwise<T>(x + static_cast<u64>(t) * V, V); }
+    B2C_SYNC();
+    // ---- phase B: mean of the row sums in numpy order, then math.isclose(mean, 1) ---------
+    // leaves of the pairwise tree over the T row sums are summed in parallel
+    int n_leaf = 0;
+    {
+        // count leaves (block-uniform, cheap)
+        long stack_n[48];
+        int sp = 0;
+        stack_n[sp++] = Tn;
+        while (sp > 0) {
+            long n = stack_n[--sp];
+            if (n <= 128) { ++n_leaf; continue; }
+            long n2 = n / 2;
+            n2 -= n2 % 8;
+            stack_n[sp++] = n - n2;
+            stack_n[sp++] = n2;
+        }
+    }
+    const bool par_leaves = n_leaf <= B2C_PREP_LEAF_CAP && Tn > 128;
+    if (par_leaves) {
+        B2C_FOR(lf, n_leaf) {
+            // locate leaf number lf by walking the same tree (depth <= ~12)
+            long off = 0, n = Tn;
+            int idx = lf;
+            while (n > 128) {
+                long n2 = n / 2;
+                n2 -= n2 % 8;
+                // number of leaves in the left subtree
+                int nl = 0;
+                {
+                    long st[48];
+                    int sp = 0;
+                    st[sp++] = n2;
+                    while (sp > 0) {
+                        long q = st[--sp];
+                        if (q <= 128) { ++nl; continue; }
+                        long q2 = q / 2;
+                        q2 -= q2 % 8;
+                        st[sp++] = q - q2;
+                        st[sp++] = q2;
+                    }
+                }
+                if (idx < nl) { n = n2; } else { idx -= nl; off += n2; n = n - n2; }
+            }
+            sh->leaf_sum[lf] = static_cast<double>(b2c_np_leaf_sum<T>(rs + off, n));
+        }
+        B2C_SYNC();
+    }
+    B2C_LEADER {
+        int isp = 0;
+        if (Tn > 0) {
+            T tot;
+            if (par_leaves) {
+                B2cLeafShared<T> lf;
+                lf.sums = sh->leaf_sum;
+                lf.next = 0;
+                tot = b2c_np_pairwise_generic<T>(Tn, lf);
+            } else {
+                tot = b2c_np_pairwise<T>(rs, Tn);
+            }
+            const T mean = tot / static_cast<T>(Tn);
+            isp = b2c_isclose_one(static_cast<double>(mean)) ? 1 : 0;
+        }
+        sh->is_prob = isp;
+        sh->base = 0;
+        A.is_prob[u] = isp;
+    }
+    B2C_SYNC();
+    const bool is_prob = sh->is_prob != 0;
+
+    // ---- phase C: one warp per frame, 8 frames per round --------------------------------
+    const int nw = B2C_NWARPS();
+    const int rounds = (Tn + nw - 1) / nw;
+#if defined(__CUDA_ARCH__)
+    const int lane = static_cast<int>(threadIdx.x & 31);
+#else
+    const int lane = 0;
+    // hostsim keeps the per-warp state of a round in arrays
+    B2cPySet h_set[B2C_PREP_WARPS];
+    T h_m[B2C_PREP_WARPS];
+    double h_ls[B2C_PREP_WARPS];
+    int h_amax[B2C_PREP_WARPS];
+    u32 h_nsel[B2C_PREP_WARPS];
+#endif
+    for (int r = 0; r < rounds; ++r) {
+#if defined(__CUDA_ARCH__)
+        B2cPySet set;
+        T m = static_cast<T>(0);
+        double ls = 0.0;
+        int amax = 0;
+        u32 nsel = 0;
+#endif
+        B2C_FOR_WARP(w, nw) {
+            const int t = r * nw + w;
+#if !defined(__CUDA_ARCH__)
+            B2cPySet& set = h_set[w];
+            T& m = h_m[w];
+            double& ls = h_ls[w];
+            int& amax = h_amax[w];
+            u32& nsel = h_nsel[w];
+#endif
+            u32 cnt = 0;
+            if (t < Tn) {
+                const T* row = x + static_cast<u64>(t) * V;
+                // set buffers: shared memory while the table fits, HBM scratch otherwise
+                const bool small = V <= 32;
+                u16* b0 = small ? sh->sets[w][0] : A.set_scratch + ((static_cast<u64>(block_idx) * nw + w) * 2 + 0) * A.set_cap;
+                u16* b1 = small ? sh->sets[w][1] : A.set_scratch + ((static_cast<u64>(block_idx) * nw + w) * 2 + 1) * A.set_cap;
+                set.buf[0] = b0;
+                set.buf[1] = b1;
+                b2c_prep_row<T>(row, V, is_prob, A.token_min_logp, lane, set, m, ls, amax, nsel);
+                if (lane == 0) {
+                    b2c_pyset_copy_or(set, static_cast<u32>(amax));
+                    cnt = set.fill;
+                    sh->counts[w] = cnt;
+                }
+            } else if (lane == 0) {
+                sh->counts[w] = 0;
+            }
+        }
+        B2C_SYNC();
+        B2C_FOR_WARP(w, nw) {
+            const int t = r * nw + w;
+#if !defined(__CUDA_ARCH__)
+            B2cPySet& set = h_set[w];
+            T& m = h_m[w];
+            double& ls = h_ls[w];
+#endif
+            if (t < Tn && lane == 0) {
+                u32 off = sh->base;
+                for (int q = 0; q < w; ++q) off += sh->counts[q];
+                tstart[t] = off;
+                const T* row = x + static_cast<u64>(t) * V;
+                const u16* tab = set.buf[set.cur];
+                for (u32 s = 0; s <= set.mask; ++s) {
+                    const u16 tok = tab[s];
+                    if (tok == 0xFFFFu) continue;
+                    ids[off] = tok;
+                    lps[off] = b2c_lp<T>(row[tok], is_prob, m, ls);
+                    ++off;
+                }
+            }
+        }
+        B2C_SYNC();
+        B2C_LEADER {
+            u32 tot = 0;
+            for (int q = 0; q < nw; ++q) tot += sh->counts[q];
+            sh->base += tot;
+        }
+        B2C_SYNC();
+    }
+    B2C_LEADER { tstart[Tn] = sh->base; }
+}

@@ -1,0 +1,353 @@
+"""BeamSearchDecoderCTC / build_ctcdecoder with the reference's call surface, dispatching the
+whole beam search to the sm_100a kernels through the C ABI (include/b200ctc.h).
+
+What stays on the host: argument checking (reference decoder.py:330-344), packaging the list
+of [T_i, V] matrices into one ``b2c_decode_batch`` call, turning results into ``OutputBeam``.
+What moved to the GPU: input normalisation (:756-765), the per-frame loop of
+``_partial_decode_logits`` (:443-554), LM / hotword fusion (:346-424), ``_finalize_beams``
+(:558-602).  ``pool`` arguments are accepted and ignored: utterance parallelism is one CTA per
+utterance on the device (and one rank per GPU above that), not ``multiprocessing``.
+"""
+import ctypes as C
+import logging
+import os
+import threading
+from typing import Any, Collection, Dict, Iterable, List, NamedTuple, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from . import _lib
+from .alphabet import Alphabet, verify_alphabet_coverage
+from .constants import (
+    DEFAULT_ALPHA,
+    DEFAULT_BEAM_WIDTH,
+    DEFAULT_BETA,
+    DEFAULT_HOTWORD_WEIGHT,
+    DEFAULT_MIN_TOKEN_LOGP,
+    DEFAULT_PRUNE_BEAMS,
+    DEFAULT_PRUNE_LOGP,
+    DEFAULT_SCORE_LM_BOUNDARY,
+    DEFAULT_UNK_LOGP_OFFSET,
+)
+from .language_model import (
+    AbstractLanguageModel,
+    AbstractLMState,
+    B200LMState,
+    HotwordScorer,
+    LanguageModel,
+    MultiLanguageModel,
+    NgramModel,
+    load_unigram_set_from_arpa,
+)
+
+logger = logging.getLogger(__name__)
+
+Frames = Tuple[int, int]
+WordFrames = Tuple[str, Frames]
+
+
+class OutputBeam(NamedTuple):
+    """reference decoder.py:102-118; a NamedTuple so that both ``beam.text`` and the
+    positional access HF's Wav2Vec2ProcessorWithLM uses (``beam[0]`` ... ``beam[4]``) work."""
+
+    text: str
+    last_lm_state: Optional[AbstractLMState]
+    text_frames: List[WordFrames]
+    logit_score: float
+    lm_score: float
+
+    def get_mp_safe_beam(self) -> "OutputBeam":
+        state = None if self.last_lm_state is None else self.last_lm_state.get_mp_safe_state()
+        return self._replace(last_lm_state=state)
+
+
+def _default_device() -> int:
+    env = os.environ.get("B200CTC_DEVICE")
+    if env is not None:
+        return int(env)
+    return int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def _as_matrix(logits: Any) -> Tuple[Any, int, int, int, bool]:
+    """-> (owner, address, T, dtype_code, is_device).  float32/float64 are passed through, integer
+    inputs are computed in float64 like numpy would, half precision is widened to float32."""
+    if hasattr(logits, "is_cuda") and hasattr(logits, "data_ptr"):  # torch tensor
+        t = logits
+        if t.dim() != 2:
+            raise ValueError("Input logits have %s dimensions, but need 2: (time, vocabulary)" % t.dim())
+        import torch
+
+        if t.dtype not in (torch.float32, torch.float64):
+            t = t.to(torch.float64 if not t.dtype.is_floating_point else torch.float32)
+        t = t.contiguous()
+        if t.is_cuda:
+            return t, t.data_ptr(), t.shape[0], 0 if t.dtype == torch.float32 else 1, True
+        return t, t.data_ptr(), t.shape[0], 0 if t.dtype == torch.float32 else 1, False
+    arr = np.asarray(logits)
+    if arr.ndim != 2:
+        raise ValueError("Input logits have %s dimensions, but need 2: (time, vocabulary)" % arr.ndim)
+    if arr.dtype == np.float32:
+        arr = np.ascontiguousarray(arr)
+        code = 0
+    elif arr.dtype == np.float16:
+        arr = np.ascontiguousarray(arr, dtype=np.float32)
+        code = 0
+    else:
+        arr = np.ascontiguousarray(arr, dtype=np.float64)
+        code = 1
+    return arr, arr.ctypes.data, arr.shape[0], code, False
+
+
+class BeamSearchDecoderCTC:
+    # the language model lives in a class variable keyed by a random token, like the reference
+    # (decoder.py:262-269), so that code poking at model_container keeps working
+    model_container: Dict[bytes, Optional[AbstractLanguageModel]] = {}
+
+    _ALPHABET_SERIALIZED_FILENAME = "alphabet.json"
+    _LANGUAGE_MODEL_SERIALIZED_DIRECTORY = "language_model"
+
+    def __init__(self, alphabet: Alphabet, language_model: Optional[AbstractLanguageModel] = None,
+                 device: Optional[int] = None) -> None:
+        self._alphabet = alphabet
+        self._idx2vocab = {n: c for n, c in enumerate(self._alphabet.labels)}
+        self._is_bpe = alphabet.is_bpe
+        self._model_key = os.urandom(16)
+        BeamSearchDecoderCTC.model_container[self._model_key] = language_model
+        self._device = device
+        self._handles: Dict[int, int] = {}   # device -> b2c_decoder_t*
+        self._lock = threading.Lock()
+
+    # ---- life cycle ---------------------------------------------------------------------
+    def reset_params(self, alpha: Optional[float] = None, beta: Optional[float] = None,
+                     unk_score_offset: Optional[float] = None, lm_score_boundary: Optional[bool] = None) -> None:
+        language_model = self._language_model
+        if language_model is None:
+            return
+        params: Dict[str, Any] = {}
+        if alpha is not None:
+            params["alpha"] = alpha
+        if beta is not None:
+            params["beta"] = beta
+        if unk_score_offset is not None:
+            params["unk_score_offset"] = unk_score_offset
+        if lm_score_boundary is not None:
+            params["score_boundary"] = lm_score_boundary
+        language_model.reset_params(**params)
+
+    @classmethod
+    def clear_class_models(cls) -> None:
+        cls.model_container = {}
+
+    def cleanup(self) -> None:
+        if self._model_key in BeamSearchDecoderCTC.model_container:
+            del BeamSearchDecoderCTC.model_container[self._model_key]
+
+    @property
+    def _language_model(self) -> Optional[AbstractLanguageModel]:
+        return BeamSearchDecoderCTC.model_container[self._model_key]
+
+    def __del__(self) -> None:
+        if _lib._lib is None:
+            return
+        for h in getattr(self, "_handles", {}).values():
+            try:
+                _lib._lib.b2c_decoder_destroy(h)
+            except Exception:  # pragma: no cover
+                pass
+        self._handles = {}
+
+    # ---- device objects -------------------------------------------------------------------
+    def _handle(self, device: Optional[int] = None) -> int:
+        dev = device if device is not None else (self._device if self._device is not None else _default_device())
+        with self._lock:
+            h = self._handles.get(dev)
+            if h is None:
+                lm = self._language_model
+                if isinstance(lm, MultiLanguageModel):
+                    raise NotImplementedError("MultiLanguageModel is not supported by the B200 kernels yet")
+                if lm is not None and not isinstance(lm, LanguageModel):
+                    raise TypeError("language_model must be a pyctcdecode_b200 LanguageModel")
+                labels = self._alphabet.labels
+                out = C.c_void_p()
+                lm_handle = lm.ngram_model._h() if lm is not None else None
+                _lib.check(_lib.lib().b2c_decoder_create(_lib.cstr_array(labels), len(labels), int(self._is_bpe),
+                                                         lm_handle, dev, C.byref(out)))
+                h = self._handles[dev] = out.value
+        return h
+
+    def _check_logits_dimension(self, logits: Any) -> None:
+        """reference decoder.py:330-344"""
+        shape = tuple(logits.shape)
+        if len(shape) != 2:
+            raise ValueError("Input logits have %s dimensions, but need 2: (time, vocabulary)" % len(shape))
+        if shape[-1] != len(self._idx2vocab):
+            raise ValueError("Input logits shape is %s, but vocabulary is size %s. Need logits of shape: "
+                             "(time, vocabulary)" % (shape, len(self._idx2vocab)))
+
+    # ---- the one place that talks to the kernels ------------------------------------------
+    def _run(self, logits_list: Sequence[Any], beam_width: int, beam_prune_logp: float, token_min_logp: float,
+             prune_history: bool, hotwords: Optional[Iterable[str]], hotword_weight: float, max_out_beams: int,
+             lm_start_states: Optional[Sequence[Optional[AbstractLMState]]] = None, with_state: bool = True,
+             device: Optional[int] = None) -> List[List[OutputBeam]]:
+        for logits in logits_list:
+            self._check_logits_dimension(logits)
+        n = len(logits_list)
+        if n == 0:
+            return []
+        mats = [_as_matrix(x) for x in logits_list]
+        codes = {m[3] for m in mats}
+        devs = {m[4] for m in mats}
+        if len(codes) > 1 or len(devs) > 1:  # mixed batch: bring everything to host float64
+            mats = [_as_matrix(np.asarray(x.cpu() if hasattr(x, "cpu") else x, dtype=np.float64)) for x in logits_list]
+        dtype_code, is_device = mats[0][3], mats[0][4]
+        handle = self._handle(device)
+        lm = self._language_model
+        L = _lib.lib()
+        if lm is not None:
+            _lib.check(L.b2c_decoder_set_params(handle, float(lm.alpha), float(lm.beta), float(lm.unk_score_offset),
+                                                int(bool(lm.score_boundary))))
+        opts = _lib.DecodeOpts()
+        L.b2c_decode_opts_default(C.byref(opts))
+        opts.beam_width = int(beam_width)
+        opts.beam_prune_logp = float(beam_prune_logp)
+        opts.token_min_logp = float(token_min_logp)
+        opts.prune_history = int(bool(prune_history))
+        hot = [s.strip() for s in (hotwords or []) if len(s.strip()) > 0]
+        hot_arr = _lib.cstr_array(hot)
+        opts.hotwords = C.cast(hot_arr, C.POINTER(C.c_char_p))
+        opts.n_hotwords = len(hot)
+        opts.hotword_weight = float(hotword_weight)
+        opts.max_out_beams = int(max_out_beams)
+        states_arr = None
+        if lm is not None and lm_start_states is not None and any(s is not None for s in lm_start_states):
+            states_arr = (_lib.LMState * n)()
+            for i, s in enumerate(lm_start_states):
+                st = s if s is not None else lm.get_start_state()
+                if not isinstance(st, B200LMState):
+                    raise AssertionError("Wrong input state type found. Expected B200LMState, got %s" % type(st))
+                states_arr[i] = st._to_c()
+            opts.lm_start_states = C.cast(states_arr, C.POINTER(_lib.LMState))
+        ptrs = (C.c_void_p * n)(*[m[1] for m in mats])
+        Ts = (C.c_int32 * n)(*[m[2] for m in mats])
+        res = C.c_void_p()
+        _lib.check(L.b2c_decode_batch(handle, ptrs, Ts, n, dtype_code, int(is_device), C.byref(opts), C.byref(res)))
+        try:
+            out: List[List[OutputBeam]] = []
+            st = _lib.LMState()
+            for u in range(n):
+                beams = []
+                for b in range(L.b2c_result_n_beams(res, u)):
+                    nw = L.b2c_result_n_words(res, u, b)
+                    fr = L.b2c_result_frames(res, u, b)
+                    frames = [(L.b2c_result_word(res, u, b, w).decode("utf-8"), (fr[2 * w], fr[2 * w + 1])) for w in range(nw)]
+                    state = None
+                    if with_state and L.b2c_result_lm_state(res, u, b, C.byref(st)):
+                        state = B200LMState._from_c(st)
+                    beams.append(OutputBeam(L.b2c_result_text(res, u, b).decode("utf-8"), state, frames,
+                                            L.b2c_result_logit_score(res, u, b), L.b2c_result_lm_score(res, u, b)))
+                out.append(beams)
+        finally:
+            L.b2c_result_free(res)
+        return out
+
+    def last_timings(self, device: Optional[int] = None) -> Dict[str, float]:
+        """Device-side timings of the last decode call (CUDA events on the decoder's stream)."""
+        tm = _lib.Timings()
+        _lib.check(_lib.lib().b2c_decoder_last_timings(self._handle(device), C.byref(tm)))
+        return {name: getattr(tm, name) for name, _ in _lib.Timings._fields_}
+
+    # ---- public decoding API (signatures of reference decoder.py:730-945) ------------------
+    def decode_beams(self, logits: Any, beam_width: int = DEFAULT_BEAM_WIDTH, beam_prune_logp: float = DEFAULT_PRUNE_LOGP,
+                     token_min_logp: float = DEFAULT_MIN_TOKEN_LOGP, prune_history: bool = DEFAULT_PRUNE_BEAMS,
+                     hotwords: Optional[Iterable[str]] = None, hotword_weight: float = DEFAULT_HOTWORD_WEIGHT,
+                     lm_start_state: Optional[AbstractLMState] = None) -> List[OutputBeam]:
+        return self._run([logits], beam_width, beam_prune_logp, token_min_logp, prune_history, hotwords, hotword_weight,
+                         max_out_beams=beam_width, lm_start_states=[lm_start_state])[0]
+
+    def decode_beams_batch(self, pool: Any, logits_list: Sequence[Any], beam_width: int = DEFAULT_BEAM_WIDTH,
+                           beam_prune_logp: float = DEFAULT_PRUNE_LOGP, token_min_logp: float = DEFAULT_MIN_TOKEN_LOGP,
+                           prune_history: bool = DEFAULT_PRUNE_BEAMS, hotwords: Optional[Iterable[str]] = None,
+                           hotword_weight: float = DEFAULT_HOTWORD_WEIGHT) -> List[List[OutputBeam]]:
+        # the reference strips the LM state for multiprocessing (decoder.py:797-799); keep that
+        return self._run(list(logits_list), beam_width, beam_prune_logp, token_min_logp, prune_history, hotwords,
+                         hotword_weight, max_out_beams=beam_width, with_state=False)
+
+    def decode(self, logits: Any, beam_width: int = DEFAULT_BEAM_WIDTH, beam_prune_logp: float = DEFAULT_PRUNE_LOGP,
+               token_min_logp: float = DEFAULT_MIN_TOKEN_LOGP, hotwords: Optional[Iterable[str]] = None,
+               hotword_weight: float = DEFAULT_HOTWORD_WEIGHT, lm_start_state: Optional[AbstractLMState] = None) -> str:
+        beams = self._run([logits], beam_width, beam_prune_logp, token_min_logp, True, hotwords, hotword_weight,
+                          max_out_beams=1, lm_start_states=[lm_start_state], with_state=False)[0]
+        return beams[0].text
+
+    def decode_batch(self, pool: Any, logits_list: Sequence[Any], beam_width: int = DEFAULT_BEAM_WIDTH,
+                     beam_prune_logp: float = DEFAULT_PRUNE_LOGP, token_min_logp: float = DEFAULT_MIN_TOKEN_LOGP,
+                     hotwords: Optional[Iterable[str]] = None, hotword_weight: float = DEFAULT_HOTWORD_WEIGHT) -> List[str]:
+        beams = self._run(list(logits_list), beam_width, beam_prune_logp, token_min_logp, True, hotwords, hotword_weight,
+                          max_out_beams=1, with_state=False)
+        return [b[0].text for b in beams]
+
+    # ---- streaming: out of scope this round -------------------------------
+    def get_starting_state(self) -> Any:
+        raise NotImplementedError("streaming decode (get_starting_state / partial_decode_beams) is not implemented "
+                                  "in pyctcdecode_b200 yet; use decode_beams(..., lm_start_state=...) per chunk")
+
+    def partial_decode_beams(self, *args: Any, **kwargs: Any) -> Any:
+        raise NotImplementedError("streaming decode (partial_decode_beams) is not implemented in pyctcdecode_b200 yet")
+
+    # ---- serialisation (reference decoder.py:947-1005): file plumbing only ------------------
+    def save_to_dir(self, filepath: str) -> None:
+        with open(os.path.join(filepath, self._ALPHABET_SERIALIZED_FILENAME), "w") as fh:
+            fh.write(self._alphabet.dumps())
+        lm = self._language_model
+        if lm is not None:
+            lm_path = os.path.join(filepath, self._LANGUAGE_MODEL_SERIALIZED_DIRECTORY)
+            os.makedirs(lm_path)
+            lm.save_to_dir(lm_path)
+
+    @staticmethod
+    def parse_directory_contents(filepath: str) -> Dict[str, Union[str, None]]:
+        contents = [c for c in os.listdir(filepath) if not c.startswith(".") and not c.startswith("__")]
+        if BeamSearchDecoderCTC._ALPHABET_SERIALIZED_FILENAME not in contents:
+            raise ValueError("Could not find alphabet file %s. Found %s" % (BeamSearchDecoderCTC._ALPHABET_SERIALIZED_FILENAME, contents))
+        contents.remove(BeamSearchDecoderCTC._ALPHABET_SERIALIZED_FILENAME)
+        lm_directory: Optional[str] = None
+        if contents:
+            if BeamSearchDecoderCTC._LANGUAGE_MODEL_SERIALIZED_DIRECTORY not in contents:
+                raise ValueError("Count not find language model directory. Looking for %s, found %s"
+                                 % (BeamSearchDecoderCTC._LANGUAGE_MODEL_SERIALIZED_DIRECTORY, contents))
+            lm_directory = os.path.join(filepath, BeamSearchDecoderCTC._LANGUAGE_MODEL_SERIALIZED_DIRECTORY)
+        return {"alphabet": os.path.join(filepath, BeamSearchDecoderCTC._ALPHABET_SERIALIZED_FILENAME),
+                "language_model": lm_directory}
+
+    @classmethod
+    def load_from_dir(cls, filepath: str, unigram_encoding: Optional[str] = None) -> "BeamSearchDecoderCTC":
+        names = cls.parse_directory_contents(filepath)
+        with open(names["alphabet"]) as fh:  # type: ignore[arg-type]
+            alphabet = Alphabet.loads(fh.read())
+        lm = None
+        if names["language_model"] is not None:
+            lm = LanguageModel.load_from_dir(names["language_model"], unigram_encoding=unigram_encoding)
+        return cls(alphabet, language_model=lm)
+
+
+def build_ctcdecoder(labels: List[str], kenlm_model_path: Optional[str] = None, unigrams: Optional[Collection[str]] = None,
+                     alpha: float = DEFAULT_ALPHA, beta: float = DEFAULT_BETA,
+                     unk_score_offset: float = DEFAULT_UNK_LOGP_OFFSET,
+                     lm_score_boundary: bool = DEFAULT_SCORE_LM_BOUNDARY, device: Optional[int] = None) -> BeamSearchDecoderCTC:
+    """Same arguments and semantics as reference decoder.py:1051-1099; ``kenlm_model_path`` must be
+    an ARPA file (KenLM binaries are not readable without the kenlm package)."""
+    ngram = None if kenlm_model_path is None else NgramModel(kenlm_model_path)
+    if unigrams is None and kenlm_model_path is not None:
+        if kenlm_model_path.endswith(".arpa"):
+            unigrams = load_unigram_set_from_arpa(kenlm_model_path)
+        else:
+            logger.warning("Unigrams not provided and cannot be automatically determined from LM file (only "
+                           "arpa format). Decoding accuracy might be reduced.")
+    alphabet = Alphabet.build_alphabet(labels)
+    if unigrams is not None:
+        verify_alphabet_coverage(alphabet, unigrams)
+    language_model: Optional[AbstractLanguageModel] = None
+    if ngram is not None:
+        language_model = LanguageModel(ngram, unigrams, alpha=alpha, beta=beta, unk_score_offset=unk_score_offset,
+                                       score_boundary=lm_score_boundary)
+    return BeamSearchDecoderCTC(alphabet, language_model, device=device)

@@ -59,3 +59,14 @@ def beams_match(expected, got, tol=2e-4, exact_order=True):
         if abs(e["lm_score"] - g[3]) > tol + 1e-6 * abs(e["lm_score"]):
             return "beam %d lm %r != %r" % (i, g[3], e["lm_score"])
     return ""
+
+
+def build_product_decoder(pkg, labels, **kw):
+    """build_ctcdecoder, except for unigrams == [] where the reference itself divides by zero in
+    verify_alphabet_coverage and its test assembles the pieces by hand (tests/test_decoder.py:266)."""
+    if kw.get("unigrams") == []:
+        lm = pkg.LanguageModel(pkg.NgramModel(kw["kenlm_model_path"]), [], alpha=kw.get("alpha", 0.5),
+                               beta=kw.get("beta", 1.5), unk_score_offset=kw.get("unk_score_offset", -10.0),
+                               score_boundary=kw.get("lm_score_boundary", True))
+        return pkg.BeamSearchDecoderCTC(pkg.Alphabet.build_alphabet(labels), lm)
+    return pkg.build_ctcdecoder(labels, **kw)

@@ -1,0 +1,136 @@
+"""CPU tests of the KERNEL LOGIC: the product host code (pyctcdecode_b200) is pointed at the
+tests/hostsim simulation build of the very same kernel sources (see tests/hostsim/cuda_shim.h)
+and compared with the oracle and with the golden vectors of the unmodified reference.
+This does not replace the `-m gpu` parity tests; it is how kernel logic is kept testable in a
+container without a GPU."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from tests import goldens, synth
+
+HOSTSIM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim")
+
+
+@pytest.fixture(scope="module")
+def sim():
+    subprocess.check_call(["make", "-s", "-C", HOSTSIM])
+    import pyctcdecode_b200
+    from pyctcdecode_b200 import _lib
+    _lib.use_library(os.path.join(HOSTSIM, "libb200ctc_hostsim.so"))
+    yield pyctcdecode_b200
+    _lib._lib = None
+
+
+def _beams(out):
+    return [(b.text, b.text_frames, b.logit_score, b.lm_score) for b in out]
+
+
+def _names():
+    return [c["name"] for c in goldens.load()["meta"]["cases"]]
+
+
+@pytest.mark.parametrize("name", _names())
+def test_hostsim_matches_reference_golden(sim, golden, name):
+    case = next(c for c in golden["meta"]["cases"] if c["name"] == name)
+    dec = goldens.build_product_decoder(sim, case["labels"], **goldens.lm_kwargs(golden, case))
+    x = golden["arrays"][case["array"]]
+    got = _beams(dec.decode_beams(x, **case["decode"]))
+    assert goldens.beams_match(case["beams"], got) == ""
+    kw = {k: v for k, v in case["decode"].items() if k != "prune_history"}
+    assert dec.decode(x, **kw) == case["decode_text"]
+
+
+FAMILIES = {
+    "B_nolm": (dict(kind="char", vocab="B", n_words=400, lm_order=0), {}),
+    "B_3gram": (dict(kind="char", vocab="B", n_words=400, lm_order=3), dict(alpha=0.5, beta=1.0)),
+    "A_2gram": (dict(kind="char", vocab="A", n_words=400, lm_order=2), dict()),
+    "B_5gram": (dict(kind="char", vocab="B", n_words=150, lm_order=5), dict(alpha=0.9, beta=0.3, unk_score_offset=-4.0)),
+    "C_bpe": (dict(kind="bpe", n_words=400, lm_order=0), {}),
+    "C_bpe_4gram": (dict(kind="bpe", n_words=400, lm_order=4), dict(alpha=0.7, beta=2.0)),
+}
+
+
+def _compare(ref, got, tol=1e-9):
+    assert len(ref) == len(got)
+    for r, g in zip(ref, got):
+        assert r[0] == g[0]
+        assert [(w, tuple(f)) for w, f in r[1]] == [(w, tuple(f)) for w, f in g[1]]
+        assert abs(r[2] - g[2]) <= tol * max(1.0, abs(r[2]))
+        assert abs(r[3] - g[3]) <= tol * max(1.0, abs(r[3]))
+
+
+@pytest.mark.parametrize("fam", sorted(FAMILIES))
+def test_hostsim_vs_oracle_random(sim, fam):
+    wkw, lmkw = FAMILIES[fam]
+    wl = synth.make_workload(wkw)
+    kw = dict(lmkw)
+    if wl.arpa:
+        kw.update(kenlm_model_path=wl.arpa, unigrams=wl.words)
+    dec = sim.build_ctcdecoder(wl.labels, **kw)
+    ora = orc.OracleDecoder(wl.labels, **kw)
+    rng = np.random.default_rng(99)
+    n_cases = 18 if wl.V <= 64 else 8
+    for i in range(n_cases):
+        T = int(rng.integers(0, 140 if wl.V <= 64 else 50))
+        regime = ["peaky", "diffuse", "flat"][i % 3] if wl.V <= 64 else ["peaky", "diffuse"][i % 2]
+        x = wl.utterance(700 + i, T, regime) if T else np.zeros((0, wl.V), np.float32)
+        if i % 5 == 4:
+            x = x.astype(np.float64)
+        if i % 7 == 6 and T:
+            e = np.exp(x - x.max(1, keepdims=True))
+            x = (e / e.sum(1, keepdims=True)).astype(x.dtype)
+        dkw = dict(beam_width=[100, 3, 17, 1][i % 4], prune_history=bool(i % 2), beam_prune_logp=[-10.0, -4.0, -25.0][i % 3],
+                   token_min_logp=[-5.0, -8.0][i % 2])
+        if i % 4 == 2:
+            dkw.update(hotwords=[wl.words[2], wl.words[7] + " " + wl.words[9]], hotword_weight=7.5)
+        _compare(ora.decode_beams(x, **dkw), _beams(dec.decode_beams(x, **dkw)))
+
+
+def test_hostsim_ragged_batch_matches_single(sim):
+    wl = synth.make_workload(FAMILIES["B_3gram"][0])
+    kw = dict(FAMILIES["B_3gram"][1], kenlm_model_path=wl.arpa, unigrams=wl.words)
+    dec = sim.build_ctcdecoder(wl.labels, **kw)
+    ora = orc.OracleDecoder(wl.labels, **kw)
+    Ts = [40, 0, 77, 5, 120, 1, 33]
+    xs = [wl.utterance(900 + i, T, "diffuse" if i % 2 else "peaky") if T else np.zeros((0, wl.V), np.float32) for i, T in enumerate(Ts)]
+    texts = dec.decode_batch(None, xs, beam_width=25)
+    assert texts == ora.decode_batch(xs, beam_width=25)
+    beams = dec.decode_beams_batch(None, xs, beam_width=25)
+    for x, b in zip(xs, beams):
+        _compare(ora.decode_beams(x, beam_width=25), _beams(b))
+        assert all(o.last_lm_state is None for o in b)
+
+
+def test_hostsim_duplicate_blank_labels_and_state(sim):
+    # two pad-like labels normalise to the same blank string; they must behave as one token
+    labels = ["<pad>", "[PAD]", "a", "b", " "]
+    dec = sim.build_ctcdecoder(labels)
+    ora = orc.OracleDecoder(labels)
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((40, 5)).astype(np.float32) * 2
+    _compare(ora.decode_beams(x, beam_width=12), _beams(dec.decode_beams(x, beam_width=12)))
+
+
+def test_hostsim_lm_start_state_roundtrip(sim, golden):
+    case = next(c for c in golden["meta"]["cases"] if c["name"] == "stateful_lm")
+    dec = goldens.build_product_decoder(sim, case["labels"], **goldens.lm_kwargs(golden, case))
+    probs = golden["arrays"]["bunny_bunny_probs"]
+    # reference tests/test_decoder.py:447-456
+    assert dec.decode(probs[:4]) + " " + dec.decode(probs[4:]) == "bugs bugs"
+    top = dec.decode_beams(probs[:4])[0]
+    assert top.last_lm_state is not None
+    text = top.text + " " + dec.decode_beams(probs[4:], lm_start_state=top.last_lm_state)[0].text
+    assert text == "bugs bunny"
+
+
+def test_hostsim_errors(sim):
+    dec = sim.build_ctcdecoder(synth.LIBRI_LABELS)
+    with pytest.raises(ValueError):
+        dec.decode(np.zeros((4, 7), np.float32))
+    with pytest.raises(ValueError):
+        dec.decode(np.zeros((4,), np.float32))
+    assert dec.decode(np.zeros((0, 29))) == ""
