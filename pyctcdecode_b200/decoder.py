@@ -184,21 +184,53 @@ class BeamSearchDecoderCTC:
             raise ValueError("Input logits shape is %s, but vocabulary is size %s. Need logits of shape: "
                              "(time, vocabulary)" % (shape, len(self._idx2vocab)))
 
+    def _as_packed_batch(self, logits_list: Any) -> Optional[Tuple[Any, int, int, int, int, bool]]:
+        """A single 3-D [B, T, V] float32/float64 numpy array or torch tensor -> (owner, address,
+        B, T, dtype_code, is_device); anything else -> None (generic per-utterance path)."""
+        V = len(self._idx2vocab)
+        if hasattr(logits_list, "data_ptr") and hasattr(logits_list, "is_cuda"):
+            import torch
+
+            t = logits_list
+            if t.dim() != 3 or t.dtype not in (torch.float32, torch.float64):
+                return None
+            if t.shape[2] != V:
+                raise ValueError("Input logits shape is %s, but vocabulary is size %s. Need logits of shape: "
+                                 "(time, vocabulary)" % (tuple(t.shape[1:]), V))
+            t = t.contiguous()
+            return t, t.data_ptr(), t.shape[0], t.shape[1], 0 if t.dtype == torch.float32 else 1, bool(t.is_cuda)
+        if isinstance(logits_list, np.ndarray) and logits_list.ndim == 3 and logits_list.dtype in (np.float32, np.float64):
+            if logits_list.shape[2] != V:
+                raise ValueError("Input logits shape is %s, but vocabulary is size %s. Need logits of shape: "
+                                 "(time, vocabulary)" % (logits_list.shape[1:], V))
+            a = np.ascontiguousarray(logits_list)
+            return a, a.ctypes.data, a.shape[0], a.shape[1], 0 if a.dtype == np.float32 else 1, False
+        return None
+
     # ---- the one place that talks to the kernels ------------------------------------------
     def _run(self, logits_list: Sequence[Any], beam_width: int, beam_prune_logp: float, token_min_logp: float,
              prune_history: bool, hotwords: Optional[Iterable[str]], hotword_weight: float, max_out_beams: int,
              lm_start_states: Optional[Sequence[Optional[AbstractLMState]]] = None, with_state: bool = True,
-             device: Optional[int] = None) -> List[List[OutputBeam]]:
-        for logits in logits_list:
-            self._check_logits_dimension(logits)
-        n = len(logits_list)
-        if n == 0:
-            return []
-        mats = [_as_matrix(x) for x in logits_list]
-        codes = {m[3] for m in mats}
-        devs = {m[4] for m in mats}
-        if len(codes) > 1 or len(devs) > 1:  # mixed batch: bring everything to host float64
-            mats = [_as_matrix(np.asarray(x.cpu() if hasattr(x, "cpu") else x, dtype=np.float64)) for x in logits_list]
+             device: Optional[int] = None, texts_only: bool = False) -> Any:
+        packed = self._as_packed_batch(logits_list)
+        if packed is not None:
+            # one [B, T, V] array / tensor: no per-utterance conversion, pointers by arithmetic
+            owner, base, n, t_each, dtype_code, is_device = packed
+            if n == 0:
+                return []
+            step = t_each * len(self._idx2vocab) * (4 if dtype_code == 0 else 8)
+            mats = [(owner, base + i * step, t_each, dtype_code, is_device) for i in range(n)]
+        else:
+            for logits in logits_list:
+                self._check_logits_dimension(logits)
+            n = len(logits_list)
+            if n == 0:
+                return []
+            mats = [_as_matrix(x) for x in logits_list]
+            codes = {m[3] for m in mats}
+            devs = {m[4] for m in mats}
+            if len(codes) > 1 or len(devs) > 1:  # mixed batch: bring everything to host float64
+                mats = [_as_matrix(np.asarray(x.cpu() if hasattr(x, "cpu") else x, dtype=np.float64)) for x in logits_list]
         dtype_code, is_device = mats[0][3], mats[0][4]
         handle = self._handle(device)
         lm = self._language_model
@@ -232,6 +264,8 @@ class BeamSearchDecoderCTC:
         res = C.c_void_p()
         _lib.check(L.b2c_decode_batch(handle, ptrs, Ts, n, dtype_code, int(is_device), C.byref(opts), C.byref(res)))
         try:
+            if texts_only:
+                return [L.b2c_result_text(res, u, 0).decode("utf-8") for u in range(n)]
             out: List[List[OutputBeam]] = []
             st = _lib.LMState()
             for u in range(n):
@@ -269,7 +303,7 @@ class BeamSearchDecoderCTC:
                            prune_history: bool = DEFAULT_PRUNE_BEAMS, hotwords: Optional[Iterable[str]] = None,
                            hotword_weight: float = DEFAULT_HOTWORD_WEIGHT) -> List[List[OutputBeam]]:
         # the reference strips the LM state for multiprocessing (decoder.py:797-799); keep that
-        return self._run(list(logits_list), beam_width, beam_prune_logp, token_min_logp, prune_history, hotwords,
+        return self._run(logits_list, beam_width, beam_prune_logp, token_min_logp, prune_history, hotwords,
                          hotword_weight, max_out_beams=beam_width, with_state=False)
 
     def decode(self, logits: Any, beam_width: int = DEFAULT_BEAM_WIDTH, beam_prune_logp: float = DEFAULT_PRUNE_LOGP,
@@ -282,9 +316,8 @@ class BeamSearchDecoderCTC:
     def decode_batch(self, pool: Any, logits_list: Sequence[Any], beam_width: int = DEFAULT_BEAM_WIDTH,
                      beam_prune_logp: float = DEFAULT_PRUNE_LOGP, token_min_logp: float = DEFAULT_MIN_TOKEN_LOGP,
                      hotwords: Optional[Iterable[str]] = None, hotword_weight: float = DEFAULT_HOTWORD_WEIGHT) -> List[str]:
-        beams = self._run(list(logits_list), beam_width, beam_prune_logp, token_min_logp, True, hotwords, hotword_weight,
-                          max_out_beams=1, with_state=False)
-        return [b[0].text for b in beams]
+        return self._run(logits_list, beam_width, beam_prune_logp, token_min_logp, True, hotwords, hotword_weight,
+                         max_out_beams=1, with_state=False, texts_only=True)
 
     # ---- streaming: out of scope this round -------------------------------
     def get_starting_state(self) -> Any:

@@ -1,0 +1,173 @@
+"""GPU parity tests (`pytest -m gpu`, run on the B200 box): the CUDA path through the C ABI
+against (a) the golden vectors generated from the unmodified reference, (b) the CPU oracle on
+seeded inputs at sizes the oracle finishes in seconds, (c) size-independent properties at
+BASELINE.json's full sizes.  Nothing here reads /root/reference.
+
+Tolerances: transcripts and word frames must be identical; beam scores within 1e-9 relative of
+the oracle (same float64 operation order; only CUDA's vs glibc's exp/log can differ in the
+last bit) and within 2e-4 absolute of the numpy-evaluated reference goldens (numpy computes
+the float32 log-softmax with its own SIMD exp/log)."""
+import os
+
+import numpy as np
+import pytest
+
+from tests import goldens, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import __graft_entry__ as g
+    g.build()
+    import pyctcdecode_b200
+    from pyctcdecode_b200 import _lib
+    _lib._lib = None  # make sure the real CUDA library is bound, not a test build
+    L = _lib.lib()
+    assert _lib.library_path() == _lib.DEFAULT_LIBRARY
+    assert L.b2c_device_count() >= 1, "no CUDA device"
+    return pyctcdecode_b200
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle import oracle
+    oracle.build()
+    return oracle
+
+
+def _beams(out):
+    return [(b.text, b.text_frames, b.logit_score, b.lm_score) for b in out]
+
+
+def _compare(ref, got, tol=1e-9):
+    assert len(ref) == len(got)
+    for r, g in zip(ref, got):
+        assert r[0] == g[0]
+        assert [(w, tuple(f)) for w, f in r[1]] == [(w, tuple(f)) for w, f in g[1]]
+        assert abs(r[2] - g[2]) <= tol * max(1.0, abs(r[2]))
+        assert abs(r[3] - g[3]) <= tol * max(1.0, abs(r[3]))
+
+
+def _names():
+    return [c["name"] for c in goldens.load()["meta"]["cases"]]
+
+
+@pytest.mark.parametrize("name", _names())
+def test_gpu_matches_reference_golden(pkg, golden, name):
+    case = next(c for c in golden["meta"]["cases"] if c["name"] == name)
+    dec = goldens.build_product_decoder(pkg, case["labels"], **goldens.lm_kwargs(golden, case))
+    x = golden["arrays"][case["array"]]
+    assert goldens.beams_match(case["beams"], _beams(dec.decode_beams(x, **case["decode"]))) == ""
+    kw = {k: v for k, v in case["decode"].items() if k != "prune_history"}
+    assert dec.decode(x, **kw) == case["decode_text"]
+
+
+FAMILIES = {
+    "B_nolm": (dict(kind="char", vocab="B", n_words=400, lm_order=0), {}),
+    "B_3gram": (dict(kind="char", vocab="B", n_words=400, lm_order=3), dict(alpha=0.5, beta=1.0)),
+    "A_2gram": (dict(kind="char", vocab="A", n_words=400, lm_order=2), dict()),
+    "B_5gram": (dict(kind="char", vocab="B", n_words=150, lm_order=5), dict(alpha=0.9, beta=0.3, unk_score_offset=-4.0)),
+    "C_bpe": (dict(kind="bpe", n_words=400, lm_order=0), {}),
+    "C_bpe_4gram": (dict(kind="bpe", n_words=400, lm_order=4), dict(alpha=0.7, beta=2.0)),
+}
+
+
+@pytest.mark.parametrize("fam", sorted(FAMILIES))
+def test_gpu_vs_oracle_random(pkg, orc, fam):
+    wkw, lmkw = FAMILIES[fam]
+    wl = synth.make_workload(wkw)
+    kw = dict(lmkw)
+    if wl.arpa:
+        kw.update(kenlm_model_path=wl.arpa, unigrams=wl.words)
+    dec = pkg.build_ctcdecoder(wl.labels, **kw)
+    ora = orc.OracleDecoder(wl.labels, **kw)
+    rng = np.random.default_rng(99)
+    n_cases = 18 if wl.V <= 64 else 8
+    for i in range(n_cases):
+        T = int(rng.integers(0, 140 if wl.V <= 64 else 50))
+        regime = ["peaky", "diffuse", "flat"][i % 3] if wl.V <= 64 else ["peaky", "diffuse"][i % 2]
+        x = wl.utterance(700 + i, T, regime) if T else np.zeros((0, wl.V), np.float32)
+        if i % 5 == 4:
+            x = x.astype(np.float64)
+        if i % 7 == 6 and T:
+            e = np.exp(x - x.max(1, keepdims=True))
+            x = (e / e.sum(1, keepdims=True)).astype(x.dtype)
+        dkw = dict(beam_width=[100, 3, 17, 1][i % 4], prune_history=bool(i % 2), beam_prune_logp=[-10.0, -4.0, -25.0][i % 3],
+                   token_min_logp=[-5.0, -8.0][i % 2])
+        if i % 4 == 2:
+            dkw.update(hotwords=[wl.words[2], wl.words[7] + " " + wl.words[9]], hotword_weight=7.5)
+        _compare(ora.decode_beams(x, **dkw), _beams(dec.decode_beams(x, **dkw)))
+
+
+@pytest.mark.parametrize("regime,lm_order,B", [("peaky", 0, 48), ("diffuse", 0, 12), ("peaky", 3, 48), ("diffuse", 3, 16)])
+def test_gpu_vs_oracle_headline_shape(pkg, orc, regime, lm_order, B):
+    """Wav2Vec2-shaped utterances (T=1000, V=32, beam=100): decode_batch() transcripts identical to
+    the oracle's decode(), decode_beams_batch() beams identical incl. frames and scores."""
+    wl = synth.CharWorkload("B", n_words=5000, lm_order=lm_order)
+    kw = dict(kenlm_model_path=wl.arpa, unigrams=wl.words, alpha=0.5, beta=1.0) if lm_order else {}
+    dec = pkg.build_ctcdecoder(wl.labels, **kw)
+    ora = orc.OracleDecoder(wl.labels, **kw)
+    xs = wl.batch(10_000, B, 1000, regime)
+    threads = os.cpu_count() or 1
+    assert dec.decode_batch(None, xs, beam_width=100) == ora.decode_batch(xs, n_threads=threads, beam_width=100)
+    got = dec.decode_beams_batch(None, xs[:8], beam_width=100)
+    want = ora.decode_beams_batch(xs[:8], n_threads=threads, beam_width=100)
+    for w, g in zip(want, got):
+        _compare(w, _beams(g))
+
+
+def test_gpu_bpe_hotwords_batch(pkg, orc):
+    """Conformer-like BPE vocabulary (V=1024, T=500) with a 4-gram model and hotwords."""
+    wl = synth.BpeWorkload(n_words=3000, lm_order=4)
+    kw = dict(kenlm_model_path=wl.arpa, unigrams=wl.words, alpha=0.5, beta=1.0)
+    dec = pkg.build_ctcdecoder(wl.labels, **kw)
+    ora = orc.OracleDecoder(wl.labels, **kw)
+    xs = wl.batch(20_000, 24, 500, "peaky") + wl.batch(21_000, 4, 300, "diffuse")
+    hot = wl.hotwords()
+    threads = os.cpu_count() or 1
+    assert dec.decode_batch(None, xs, beam_width=100, hotwords=hot) == ora.decode_batch(xs, n_threads=threads, beam_width=100, hotwords=hot)
+
+
+def test_gpu_full_size_properties(pkg):
+    """BASELINE config C2 (B=256, T=1000, V=32, beam=100): size-independent properties --
+    batch decode equals per-utterance decode (shards are independent), repeat calls are
+    bit-identical, device-resident input equals host input, any permutation of the batch gives
+    the permuted result."""
+    import torch
+
+    wl = synth.CharWorkload("B", n_words=20000, lm_order=0)
+    dec = pkg.build_ctcdecoder(wl.labels)
+    xs = wl.batch(1, 256, 1000, "peaky")
+    full = dec.decode_batch(None, xs, beam_width=100)
+    assert full == dec.decode_batch(None, xs, beam_width=100)
+    for i in (0, 17, 101, 255):
+        assert dec.decode(xs[i], beam_width=100) == full[i]
+    perm = np.random.default_rng(0).permutation(256)
+    assert dec.decode_batch(None, [xs[i] for i in perm], beam_width=100) == [full[i] for i in perm]
+    dev = torch.from_numpy(np.stack(xs)).cuda()
+    assert dec.decode_batch(None, [dev[i] for i in range(256)], beam_width=100) == full
+    assert all(len(t) > 0 for t in full)
+
+
+def test_gpu_beam_width_sweep(pkg, orc):
+    wl = synth.CharWorkload("B", n_words=5000, lm_order=0)
+    dec = pkg.build_ctcdecoder(wl.labels)
+    ora = orc.OracleDecoder(wl.labels)
+    xs = wl.batch(30_000, 6, 400, "peaky")
+    for bw in (10, 50, 500, 2000):
+        assert dec.decode_batch(None, xs, beam_width=bw) == ora.decode_batch(xs, n_threads=os.cpu_count() or 1, beam_width=bw)
+
+
+def test_gpu_ragged_and_empty(pkg, orc):
+    wl = synth.CharWorkload("A", n_words=400, lm_order=2)
+    kw = dict(kenlm_model_path=wl.arpa, unigrams=wl.words)
+    dec = pkg.build_ctcdecoder(wl.labels, **kw)
+    ora = orc.OracleDecoder(wl.labels, **kw)
+    Ts = [40, 0, 77, 5, 120, 1, 33, 0]
+    xs = [wl.utterance(900 + i, T, "diffuse" if i % 2 else "peaky") if T else np.zeros((0, wl.V), np.float32) for i, T in enumerate(Ts)]
+    assert dec.decode_batch(None, xs, beam_width=25) == ora.decode_batch(xs, beam_width=25)
+    assert dec.decode_batch(None, [], beam_width=25) == []
+    with pytest.raises(ValueError):
+        dec.decode(np.zeros((4, 7), np.float32))

@@ -1,0 +1,137 @@
+"""CPU tests of the host side: alphabet normalisation against the reference's outputs, the
+reference-compatible objects (LanguageModel, HotwordScorer, OutputBeam), argument errors, and
+that the CUDA library exports every symbol include/b200ctc.h declares (no compute calls)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+from tests import goldens
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_alphabet_matches_reference_outputs(golden):
+    from pyctcdecode_b200.alphabet import Alphabet
+    for case in golden["meta"]["alphabet"]:
+        al = Alphabet.build_alphabet(case["labels"])
+        assert al.labels == case["normalized"]
+        assert al.is_bpe == case["is_bpe"]
+        assert Alphabet.loads(al.dumps()).labels == al.labels
+
+
+def test_alphabet_rejects_what_the_reference_rejects():
+    from pyctcdecode_b200.alphabet import Alphabet
+    with pytest.raises(ValueError):
+        Alphabet.build_alphabet(["a", "a", "b"])          # duplicates (alphabet.py:116-117)
+    with pytest.raises(ValueError):
+        Alphabet.build_alphabet(["▁a", "b c", ""])        # space inside a BPE vocabulary (:119-120)
+    with pytest.raises(ValueError):
+        Alphabet.loads('{"labels": [], "is_bpe": false, "x": 1}')
+
+
+def test_hotword_scorer_semantics():
+    # reference tests/test_language_model.py:19-70
+    from pyctcdecode_b200 import HotwordScorer
+    hs = HotwordScorer.build_scorer(["tyrion lannister", "hodor"], weight=10.0)
+    assert hs.score("i work with hodor and friends") == 10.0
+    assert hs.score("we can match tyrion only") == 10.0
+    assert hs.score("hodor is friends with hodor") == 20.0
+    assert hs.score("do not match hodor, or anything else here") == 0.0
+    assert "hod" in hs and "dor" not in hs and "hodor" in hs and "lann" in hs
+    assert HotwordScorer.build_scorer(["hodor,"]).score("please match hodor, but not hodor") == 10.0
+    assert "U.S" in HotwordScorer.build_scorer(["U.S.A."])
+    assert hs.score_partial_token("hod") == 10.0 * 3 / 5
+    assert hs.score_partial_token("xyz") == 0.0
+
+
+def test_output_beam_is_tuple_and_attribute_accessible():
+    from pyctcdecode_b200 import OutputBeam
+    b = OutputBeam("bugs bunny", None, [("bugs", (0, 4)), ("bunny", (7, 13))], -2.85, 0.146)
+    assert b.text == b[0] == "bugs bunny" and b[4] == b.lm_score
+    assert b.get_mp_safe_beam() == b
+
+
+def test_reset_params_type_checks():
+    # reference language_model.py:281-300: wrong types raise ValueError
+    from pyctcdecode_b200.language_model import LanguageModel
+    lm = LanguageModel.__new__(LanguageModel)
+    lm.alpha, lm.beta, lm.unk_score_offset, lm.score_boundary = 0.5, 1.5, -10.0, True
+    lm.reset_params(alpha=0.7, score_boundary=False)
+    assert lm.alpha == 0.7 and lm.score_boundary is False
+    for bad in (dict(alpha=1), dict(beta="x"), dict(unk_score_offset=2), dict(score_boundary=1)):
+        with pytest.raises(ValueError):
+            lm.reset_params(**bad)
+
+
+def test_cuda_library_exports_every_declared_symbol():
+    import __graft_entry__ as g
+    g.build()
+    header = open(os.path.join(ROOT, "include", "b200ctc.h")).read()
+    declared = set(re.findall(r"\b(b2c_[a-z_0-9]+)\s*\(", header))
+    declared -= {n for n in declared if n.endswith("_t")}
+    lib = ctypes.CDLL(os.path.join(ROOT, "pyctcdecode_b200", "libb200ctc.so"))
+    missing = [n for n in sorted(declared) if not hasattr(lib, n)]
+    assert not missing, missing
+    assert len(declared) >= 30
+    lib.b2c_version.restype = ctypes.c_int
+    assert lib.b2c_version() >= 100
+    # sm_100a code must be in the binary
+    out = subprocess.run(["cuobjdump", "-lelf", os.path.join(ROOT, "pyctcdecode_b200", "libb200ctc.so")],
+                         stdout=subprocess.PIPE, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_product_fails_loudly_without_gpu_or_library(monkeypatch):
+    """No CPU fallback: in this container (no CUDA device) creating a decoder handle must raise."""
+    import pyctcdecode_b200 as pkg
+    from pyctcdecode_b200 import _lib
+    _lib._lib = None
+    if _lib.lib().b2c_device_count() > 0:
+        pytest.skip("a GPU is present")
+    dec = pkg.build_ctcdecoder(["a", "b", " "])
+    import numpy as np
+    with pytest.raises(Exception) as ei:
+        dec.decode(np.zeros((3, 4), np.float32))
+    assert "CUDA" in str(ei.value) or "cuda" in str(ei.value)
+    _lib._lib = None
+    monkeypatch.setattr(_lib, "DEFAULT_LIBRARY", "/nonexistent/libb200ctc.so")
+    with pytest.raises(RuntimeError):
+        _lib.lib()
+    _lib._lib = None
+
+
+def test_lm_host_queries_match_oracle(golden, tmp_path):
+    """NgramModel (kenlm.Model look-alike over the flattened tables) against the oracle's engine
+    on an order-3 model with non-zero backoffs."""
+    import subprocess as sp
+    sp.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "hostsim")])
+    from oracle import oracle as orc
+    from pyctcdecode_b200 import _lib
+    from pyctcdecode_b200.language_model import B200LMState, NgramModel
+    from tests import synth
+    from tests.test_oracle import ARPA3
+    _lib.use_library(os.path.join(ROOT, "tests", "hostsim", "libb200ctc_hostsim.so"))
+    try:
+        p = tmp_path / "t.arpa"
+        p.write_text(ARPA3)
+        for path in (str(p), synth.CharWorkload("A", n_words=200, lm_order=4).arpa):
+            mine, ref = NgramModel(path), orc.OracleNgram(path)
+            assert mine.order == ref.order
+            words = ["a", "b", "c", "zzz", "", "</s>", "ab", "e", "t", "ta", "at"]
+            for bos in (True, False):
+                st, rst = B200LMState(), ref.start_state(bos=bos)
+                (mine.BeginSentenceWrite if bos else mine.NullContextWrite)(st)
+                for i in range(40):
+                    w = words[(i * 7 + (3 if bos else 5)) % len(words)]
+                    out = B200LMState()
+                    s = mine.BaseScore(st, w, out)
+                    rs, rout = ref.base_score(rst, w)
+                    assert s == rs, (path, w)
+                    assert list(out.words) == rout.get()[0]
+                    assert (w in mine) == (w in ref)
+                    st, rst = out, rout
+    finally:
+        _lib._lib = None
