@@ -63,7 +63,7 @@ struct B2cLayout {
 static inline u64 al16(u64 x) { return (x + 15) & ~15ull; }
 static inline u64 tab_bytes(int W) { return 6 * al16(8ull * W) + 4 * al16(4ull * W) + 2 * al16(2ull * W) + 64; }
 static inline u64 sel_bytes(int W) { return al16(8ull * W) + 3 * al16(4ull * W) + 64; }
-static inline u64 tier_bytes(u32 cap, u32 ht) { return al16(8ull * cap) * 2 + al16(4ull * cap) * 2 + al16(4ull * ht) * 4 + 64; }
+static inline u64 tier_bytes(u32 cap, u32 ht) { return al16(8ull * cap) * 2 + al16(4ull * cap) * 3 + al16(4ull * ht) * 4 + 64; }
 
 B2C_HD u8* b2c_carve(u8*& p, u64 bytes) {
     u8* r = p;
@@ -93,6 +93,7 @@ B2C_HD void b2c_carve_tier(u8* base, u32 cap, u32 ht, B2cCandTier& c) {
     c.cfold = reinterpret_cast<double*>(b2c_carve(p, 8ull * cap));
     c.cslot = reinterpret_cast<u32*>(b2c_carve(p, 4ull * cap));
     c.sidx = reinterpret_cast<u32*>(b2c_carve(p, 4ull * cap));
+    c.spre = reinterpret_cast<u32*>(b2c_carve(p, 4ull * cap));
     c.ht_idx = reinterpret_cast<u32*>(b2c_carve(p, 4ull * ht));
     c.ht_min = reinterpret_cast<u32*>(b2c_carve(p, 4ull * ht));
     c.ht_max = reinterpret_cast<u32*>(b2c_carve(p, 4ull * ht));
@@ -105,32 +106,37 @@ static u32 pow2_ge(u32 x) {
     return p;
 }
 
-static B2cLayout make_layout(int W, int V, int T_max, bool full_caps, u32 smem_budget) {
+// cap_request > 0: "fast" layout -- shared-memory candidate tier of exactly cap_request entries, no
+// HBM tier, beam tables in shared memory (the caller checks smem_bytes against the budget).
+// cap_request == 0: general layout -- what fits in shared memory plus an HBM tier sized for the
+// worst case beam_width * V.
+static B2cLayout make_layout(int W, int V, int T_max, bool full_caps, u32 smem_budget, u32 cap_request) {
     B2cLayout L;
     std::memset(&L, 0, sizeof(L));
     L.W = W;
     L.V = V;
     const u64 worst = static_cast<u64>(W) * static_cast<u64>(V);
-    // shared-memory tier: as many candidates as fit the budget next to the beam tables
     u64 fixed = 64 + sel_bytes(W);
-    L.beams_in_smem = (fixed + 2 * tab_bytes(W) + tier_bytes(256, 512) <= smem_budget) ? 1 : 0;
-    if (L.beams_in_smem) fixed += 2 * tab_bytes(W);
-    u32 cap = 4096;
-    while (cap > 64 && fixed + tier_bytes(cap, pow2_ge(2 * cap)) > smem_budget) cap >>= 1;
-    // do not reserve more than the worst case needs, and keep typical configs at ~512
-    u32 want = static_cast<u32>(std::min<u64>(worst, 512));
-    want = std::max<u32>(pow2_ge(want), 64);
-    cap = std::min(cap, want);
-    L.cap_s = cap;
-    L.ht_s = pow2_ge(2 * cap);
-    if (worst > cap) {
-        L.cap_g = static_cast<u32>(std::min<u64>(worst, 0x7FFFFFFFull));
-        L.ht_g = pow2_ge(2 * L.cap_g);
+    if (cap_request) {
+        L.beams_in_smem = 1;
+        fixed += 2 * tab_bytes(W);
+        L.cap_s = cap_request;
+        L.ht_s = pow2_ge(2 * cap_request);
+    } else {
+        L.beams_in_smem = (fixed + 2 * tab_bytes(W) + tier_bytes(256, 512) <= smem_budget) ? 1 : 0;
+        if (L.beams_in_smem) fixed += 2 * tab_bytes(W);
+        u32 cap = 512;
+        while (cap > 64 && fixed + tier_bytes(cap, pow2_ge(2 * cap)) > smem_budget) cap >>= 1;
+        L.cap_s = cap;
+        L.ht_s = pow2_ge(2 * cap);
+        if (worst > cap) {
+            L.cap_g = static_cast<u32>(std::min<u64>(worst, 0x7FFFFFFFull));
+            L.ht_g = pow2_ge(2 * L.cap_g);
+        }
     }
     const u64 wt = static_cast<u64>(W) * static_cast<u64>(std::max(T_max, 1));
     L.chain_cap = static_cast<u32>(std::min<u64>(wt + 16, 0x7FFFFFF0ull));
     L.text_cap = static_cast<u32>(std::min<u64>(full_caps ? wt + 16 : wt / 4 + 4096, 0x7FFFFFF0ull));
-    // shared memory offsets
     u64 s = 0;
     L.s_sc = static_cast<u32>(s); s += 64;
     if (L.beams_in_smem) {
@@ -140,7 +146,6 @@ static B2cLayout make_layout(int W, int V, int T_max, bool full_caps, u32 smem_b
     L.s_sel = static_cast<u32>(s); s += sel_bytes(W);
     L.s_tier = static_cast<u32>(s); s += tier_bytes(L.cap_s, L.ht_s);
     L.smem_bytes = static_cast<u32>(s);
-    // HBM workspace offsets
     u64 g = 0;
     if (!L.beams_in_smem) {
         L.g_tab[0] = g; g += tab_bytes(W);
@@ -181,12 +186,16 @@ struct B2cBeamArgs {
     B2cLmState* out_states;
 };
 
+// kFast: every frame of every utterance handed to this launch fits the shared-memory candidate
+// tier (the host guarantees beam_width * max tokens-per-frame <= cap_s) and the beam tables are in
+// shared memory; the general variant works through generic pointers and may use the HBM tier.
+template <bool kFast>
 B2C_HD void b2c_beam_block(const B2cBeamArgs& A, int slot, u8* smem) {
     const B2cLayout& L = A.L;
     u8* g = A.gws + static_cast<u64>(slot) * L.gws_bytes;
     B2cWork W;
     W.sc = reinterpret_cast<B2cScalars*>(smem + L.s_sc);
-    if (L.beams_in_smem) {
+    if (kFast || L.beams_in_smem) {
         b2c_carve_tab(smem + L.s_tab[0], L.W, W.cur);
         b2c_carve_tab(smem + L.s_tab[1], L.W, W.nxt);
     } else {
@@ -201,7 +210,7 @@ B2C_HD void b2c_beam_block(const B2cBeamArgs& A, int slot, u8* smem) {
         W.newidx = reinterpret_cast<u32*>(b2c_carve(p, 4ull * L.W));
     }
     b2c_carve_tier(smem + L.s_tier, L.cap_s, L.ht_s, W.tier_s);
-    if (L.cap_g) b2c_carve_tier(g + L.g_tier, L.cap_g, L.ht_g, W.tier_g);
+    if (!kFast && L.cap_g) b2c_carve_tier(g + L.g_tier, L.cap_g, L.ht_g, W.tier_g);
     else W.tier_g = W.tier_s;
     {
         u8* p = g + L.g_tk;
@@ -228,7 +237,7 @@ B2C_HD void b2c_beam_block(const B2cBeamArgs& A, int slot, u8* smem) {
         b2c_utt_begin(A.P, W, A.start_states ? A.start_states + u : nullptr);
         for (int t = 0; t < Tn; ++t) {
             const u32 a = ts[t], b = ts[t + 1];
-            b2c_frame_step(A.P, W, t, ids + a, lps + a, static_cast<int>(b - a));
+            b2c_frame_step<kFast>(A.P, W, t, ids + a, lps + a, static_cast<int>(b - a));
         }
         B2cOut O;
         const u64 ob = static_cast<u64>(A.P.out_beams);
@@ -251,9 +260,10 @@ __global__ void __launch_bounds__(B2C_PREP_THREADS) b2c_prepare_kernel(const B2c
     __shared__ B2cPrepShared sh;
     b2c_prepare_block<T>(A, static_cast<int>(blockIdx.x), static_cast<int>(blockIdx.x), &sh);
 }
-__global__ void __launch_bounds__(B2C_BEAM_THREADS) b2c_beam_kernel(const B2cBeamArgs A) {
+template <bool kFast>
+__global__ void __launch_bounds__(B2C_BEAM_THREADS, kFast ? 4 : 2) b2c_beam_kernel(const B2cBeamArgs A) {
     extern __shared__ __align__(16) u8 b2c_smem[];
-    b2c_beam_block(A, static_cast<int>(blockIdx.x), b2c_smem);
+    b2c_beam_block<kFast>(A, static_cast<int>(blockIdx.x), b2c_smem);
 }
 #endif
 
@@ -317,9 +327,9 @@ struct b2c_decoder {
     int score_boundary = 1;
     int n_sm = 1;
     size_t smem_optin = 48 * 1024;
-    DevBuf d_toks, d_logits, d_meta, d_tok_start, d_tok_ids, d_tok_lp, d_rowsum, d_set, d_isprob, d_ws, d_hot, d_states,
+    DevBuf d_maxk, d_toks, d_logits, d_meta, d_tok_start, d_tok_ids, d_tok_lp, d_rowsum, d_set, d_isprob, d_ws, d_hot, d_states,
         d_out_small, d_out_toks, d_out_frames;
-    PinBuf h_meta, h_out_small, h_out_toks, h_out_frames;
+    PinBuf h_maxk, h_meta, h_out_small, h_out_toks, h_out_frames;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     b2c_timings_t tm;
 };
@@ -428,15 +438,24 @@ static int launch_prepare(b2c_decoder* d, const B2cPrepArgs& A, int n_utts) {
     return 0;
 }
 
-static int launch_beam(b2c_decoder* d, const B2cBeamArgs& A, int slots) {
+static int launch_beam(b2c_decoder* d, const B2cBeamArgs& A, int slots, bool fast) {
 #ifdef B2C_HOSTSIM
     (void)d;
     std::vector<u8> smem(A.L.smem_bytes + 64);
-    for (int s = 0; s < slots; ++s) b2c_beam_block(A, s, smem.data());
+    for (int s = 0; s < slots; ++s) {
+        if (fast) b2c_beam_block<true>(A, s, smem.data());
+        else b2c_beam_block<false>(A, s, smem.data());
+    }
 #else
-    if (A.L.smem_bytes > 48 * 1024)
-        CUDA_OK(cudaFuncSetAttribute(b2c_beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(A.L.smem_bytes)));
-    b2c_beam_kernel<<<slots, B2C_BEAM_THREADS, A.L.smem_bytes, d->stream>>>(A);
+    if (fast) {
+        if (A.L.smem_bytes > 48 * 1024)
+            CUDA_OK(cudaFuncSetAttribute(b2c_beam_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(A.L.smem_bytes)));
+        b2c_beam_kernel<true><<<slots, B2C_BEAM_THREADS, A.L.smem_bytes, d->stream>>>(A);
+    } else {
+        if (A.L.smem_bytes > 48 * 1024)
+            CUDA_OK(cudaFuncSetAttribute(b2c_beam_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(A.L.smem_bytes)));
+        b2c_beam_kernel<false><<<slots, B2C_BEAM_THREADS, A.L.smem_bytes, d->stream>>>(A);
+    }
     CUDA_OK(cudaGetLastError());
 #endif
     return 0;
@@ -633,10 +652,10 @@ void b2c_decoder_destroy(b2c_decoder_t* d) {
     if (!d) return;
     cudaSetDevice(d->device);
     if (d->stream) cudaStreamSynchronize(d->stream);
-    DevBuf* bufs[] = {&d->d_toks, &d->d_logits, &d->d_meta, &d->d_tok_start, &d->d_tok_ids, &d->d_tok_lp, &d->d_rowsum, &d->d_set,
+    DevBuf* bufs[] = {&d->d_maxk, &d->d_toks, &d->d_logits, &d->d_meta, &d->d_tok_start, &d->d_tok_ids, &d->d_tok_lp, &d->d_rowsum, &d->d_set,
                       &d->d_isprob, &d->d_ws, &d->d_hot, &d->d_states, &d->d_out_small, &d->d_out_toks, &d->d_out_frames};
     for (DevBuf* b : bufs) b->release();
-    PinBuf* pins[] = {&d->h_meta, &d->h_out_small, &d->h_out_toks, &d->h_out_frames};
+    PinBuf* pins[] = {&d->h_maxk, &d->h_meta, &d->h_out_small, &d->h_out_toks, &d->h_out_frames};
     for (PinBuf* b : pins) b->release();
     for (int i = 0; i < 6; ++i) if (d->ev[i]) cudaEventDestroy(d->ev[i]);
     if (d->stream) cudaStreamDestroy(d->stream);
@@ -733,7 +752,7 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
         return T[0] > 0 || n_utts == 1;
     }();
     if (!contiguous_dev && d->d_logits.ensure(std::max<u64>(total_frames * V * esz, 16))) return B2C_E_NOMEM;
-    const size_t meta_bytes = al16(8ull * n_utts) + 2 * al16(4ull * n_utts) + 16;
+    const size_t meta_bytes = al16(8ull * n_utts) + 3 * al16(4ull * n_utts) + 64;
     if (d->d_meta.ensure(meta_bytes) || d->h_meta.ensure(meta_bytes)) return B2C_E_NOMEM;
     if (d->d_tok_start.ensure(4 * (total_frames + n_utts + 1)) || d->d_tok_ids.ensure(2 * n_entries) ||
         d->d_tok_lp.ensure(8 * n_entries) || d->d_rowsum.ensure(std::max<u64>(8 * total_frames, 16)) ||
@@ -744,21 +763,8 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     if (V > 32) {
         if (d->d_set.ensure(2ull * set_cap * 2 * B2C_PREP_WARPS * n_utts)) return B2C_E_NOMEM;
     }
-    // layout + slots
+    if (d->d_maxk.ensure(4ull * n_utts) || d->h_maxk.ensure(4ull * n_utts)) return B2C_E_NOMEM;
     const u32 smem_budget = static_cast<u32>(std::min<size_t>(d->smem_optin, 200 * 1024));
-    auto plan = [&](bool full, B2cLayout& L, int& slots) {
-        L = make_layout(opts->beam_width, V, T_max, full, smem_budget);
-        int per_sm = static_cast<int>(std::max<u64>(1, std::min<u64>(16, (220 * 1024) / std::max<u32>(L.smem_bytes, 1024))));
-        slots = std::min(n_utts, d->n_sm * per_sm);
-        // keep the HBM workspace bounded (16 GiB)
-        const u64 budget = 16ull << 30;
-        if (static_cast<u64>(slots) * L.gws_bytes > budget) slots = static_cast<int>(std::max<u64>(1, budget / L.gws_bytes));
-    };
-    B2cLayout L;
-    int slots = 1;
-    plan(false, L, slots);
-    if (L.smem_bytes > d->smem_optin) return fail(B2C_E_ARG, "beam_width too large for the shared-memory selection arrays");
-    if (d->d_ws.ensure(static_cast<u64>(slots) * L.gws_bytes)) return B2C_E_NOMEM;
     // outputs
     const u64 off_nb = 0, off_st = al16(4ull * n_utts), off_sc = off_st + al16(4ull * n_utts),
               off_nt = off_sc + al16(16ull * OB * n_utts), off_nw = off_nt + al16(4ull * OB * n_utts),
@@ -777,16 +783,17 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     u8* hm = d->h_meta.as<u8>();
     u64* h_fo = reinterpret_cast<u64*>(hm);
     int* h_T = reinterpret_cast<int*>(hm + al16(8ull * n_utts));
-    int* h_ord = reinterpret_cast<int*>(hm + al16(8ull * n_utts) + al16(4ull * n_utts));
-    u32* h_next = reinterpret_cast<u32*>(hm + al16(8ull * n_utts) + 2 * al16(4ull * n_utts));
-    for (int i = 0; i < n_utts; ++i) { h_fo[i] = frame_off[i]; h_T[i] = T[i]; h_ord[i] = order[i]; }
-    *h_next = 0;
-    CUDA_OK(cudaMemcpyAsync(d->d_meta.p, hm, meta_bytes, cudaMemcpyHostToDevice, st));
+    const size_t off_ord = al16(8ull * n_utts) + al16(4ull * n_utts);
+    const size_t off_next = off_ord + 2 * al16(4ull * n_utts);
+    int* h_ord = reinterpret_cast<int*>(hm + off_ord);           // [2 * n_utts]: class lists, then retry list
+    u32* h_next = reinterpret_cast<u32*>(hm + off_next);         // [16] one queue head per launch
+    for (int i = 0; i < n_utts; ++i) { h_fo[i] = frame_off[i]; h_T[i] = T[i]; }
+    CUDA_OK(cudaMemcpyAsync(d->d_meta.p, hm, off_ord, cudaMemcpyHostToDevice, st));
     u8* dm = d->d_meta.as<u8>();
     const u64* d_fo = reinterpret_cast<const u64*>(dm);
     const int* d_T = reinterpret_cast<const int*>(dm + al16(8ull * n_utts));
-    const int* d_ord = reinterpret_cast<const int*>(dm + al16(8ull * n_utts) + al16(4ull * n_utts));
-    u32* d_next = reinterpret_cast<u32*>(dm + al16(8ull * n_utts) + 2 * al16(4ull * n_utts));
+    int* d_ord = reinterpret_cast<int*>(dm + off_ord);
+    u32* d_next = reinterpret_cast<u32*>(dm + off_next);
     d->tm.h2d_bytes += static_cast<long long>(meta_bytes);
     const void* d_logits = nullptr;
     if (contiguous_dev) {
@@ -835,26 +842,42 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     PA.set_scratch = d->d_set.as<u16>();
     PA.set_cap = set_cap;
     PA.is_prob = d->d_isprob.as<int>();
+    PA.max_k = d->d_maxk.as<u32>();
     CUDA_OK(cudaEventRecord(d->ev[1], st));
     int rc = dtype == B2C_DTYPE_F32 ? launch_prepare<float>(d, PA, n_utts) : launch_prepare<double>(d, PA, n_utts);
     if (rc) return rc;
     CUDA_OK(cudaEventRecord(d->ev[2], st));
     d->tm.launches += 1;
 
-    // ---- beam kernel (+ one retry with worst-case arenas for utterances that overflowed) --------
+    // ---- size the beam kernel from the token statistics of this batch ---------------------------
+    CUDA_OK(cudaMemcpyAsync(d->h_maxk.p, d->d_maxk.p, 4ull * n_utts, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    const u32* h_maxk = d->h_maxk.as<u32>();
+    // capacity classes of the shared-memory candidate tier: an utterance whose worst frame can
+    // produce beam_width * max_k candidates goes to the smallest class that holds them, or to the
+    // general kernel (HBM tier) when no class fits into shared memory
+    static const u32 kCaps[4] = {512, 1024, 2048, 4096};
+    bool cap_ok[4];
+    for (int c = 0; c < 4; ++c)
+        cap_ok[c] = make_layout(opts->beam_width, V, 1, false, smem_budget, kCaps[c]).smem_bytes <= smem_budget;
+    std::vector<std::vector<int>> classes(5);   // 0..3 fast classes, 4 general
+    for (int q = 0; q < n_utts; ++q) {
+        const int u = order[q];                 // keeps longest-first order inside every class
+        const u64 need = std::min<u64>(static_cast<u64>(opts->beam_width) * std::max<u32>(h_maxk[u], 1u),
+                                       static_cast<u64>(opts->beam_width) * static_cast<u64>(V));
+        int cls = 4;
+        for (int c = 0; c < 4; ++c)
+            if (cap_ok[c] && need <= kCaps[c]) { cls = c; break; }
+        classes[cls].push_back(u);
+    }
     B2cBeamArgs BA;
     std::memset(&BA, 0, sizeof(BA));
     BA.P = P;
-    BA.L = L;
-    BA.n_utts = n_utts;
-    BA.order = d_ord;
-    BA.next = d_next;
     BA.frame_off = d_fo;
     BA.T = d_T;
     BA.tok_start = PA.tok_start;
     BA.tok_ids = PA.tok_ids;
     BA.tok_lp = PA.tok_lp;
-    BA.gws = d->d_ws.as<u8>();
     BA.start_states = d_start;
     u8* ds = d->d_out_small.as<u8>();
     BA.out_nbeams = reinterpret_cast<int*>(ds + off_nb);
@@ -865,10 +888,53 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     BA.out_states = reinterpret_cast<B2cLmState*>(ds + off_ls);
     BA.out_toks = d->d_out_toks.as<u32>();
     BA.out_frames = d->d_out_frames.as<int>();
-    rc = launch_beam(d, BA, slots);
-    if (rc) return rc;
+
+    struct Launch { int cls; size_t ord_off; int count; B2cLayout L; int slots; };
+    auto plan = [&](const std::vector<int>& utts, int cls, bool full, size_t ord_off) {
+        Launch ln;
+        ln.cls = cls;
+        ln.ord_off = ord_off;
+        ln.count = static_cast<int>(utts.size());
+        int tmax = 1;
+        for (int u : utts) tmax = std::max(tmax, static_cast<int>(T[u]));
+        ln.L = make_layout(opts->beam_width, V, tmax, full, smem_budget, cls < 4 ? kCaps[cls] : 0);
+        const int by_smem = static_cast<int>(std::max<u64>(1, (220 * 1024) / std::max<u32>(ln.L.smem_bytes + 1024, 2048)));
+        const int per_sm = std::min(by_smem, 4);   // ~128 registers x 128 threads -> 4 CTAs per SM
+        ln.slots = std::min(ln.count, d->n_sm * per_sm);
+        const u64 budget = 16ull << 30;            // keep the HBM workspace bounded
+        if (static_cast<u64>(ln.slots) * ln.L.gws_bytes > budget)
+            ln.slots = static_cast<int>(std::max<u64>(1, budget / ln.L.gws_bytes));
+        return ln;
+    };
+    std::vector<Launch> launches;
+    size_t ord_used = 0;
+    for (int c = 0; c < 5; ++c) {
+        if (classes[c].empty()) continue;
+        launches.push_back(plan(classes[c], c, false, ord_used));
+        for (int u : classes[c]) h_ord[ord_used++] = u;
+    }
+    for (size_t i = 0; i < 16; ++i) h_next[i] = 0;
+    CUDA_OK(cudaMemcpyAsync(d_ord, h_ord, 4 * ord_used, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(d_next, h_next, 64, cudaMemcpyHostToDevice, st));
+    u64 ws_need = 0;
+    for (const Launch& ln : launches) {
+        if (ln.L.smem_bytes > d->smem_optin) return fail(B2C_E_ARG, "beam_width too large for the shared-memory selection arrays");
+        ws_need = std::max(ws_need, static_cast<u64>(ln.slots) * ln.L.gws_bytes);
+    }
+    if (d->d_ws.ensure(ws_need)) return B2C_E_NOMEM;
+    CUDA_OK(cudaEventRecord(d->ev[5], st));
+    int qi = 0;
+    for (const Launch& ln : launches) {
+        BA.L = ln.L;
+        BA.n_utts = ln.count;
+        BA.order = d_ord + ln.ord_off;
+        BA.next = d_next + (qi++);
+        BA.gws = d->d_ws.as<u8>();
+        rc = launch_beam(d, BA, ln.slots, ln.cls < 4);
+        if (rc) return rc;
+        d->tm.launches += 1;
+    }
     CUDA_OK(cudaEventRecord(d->ev[3], st));
-    d->tm.launches += 1;
 
     // ---- device -> host -------------------------------------------------------------------
     CUDA_OK(cudaMemcpyAsync(d->h_out_small.p, d->d_out_small.p, small_bytes, cudaMemcpyDeviceToHost, st));
@@ -876,27 +942,24 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     CUDA_OK(cudaMemcpyAsync(d->h_out_frames.p, d->d_out_frames.p, frm_bytes, cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaEventRecord(d->ev[4], st));
     CUDA_OK(cudaStreamSynchronize(st));
-    d->tm.d2h_bytes += static_cast<long long>(small_bytes + tok_bytes + frm_bytes);
+    d->tm.d2h_bytes += static_cast<long long>(small_bytes + tok_bytes + frm_bytes + 4ull * n_utts);
 
     u8* hs = d->h_out_small.as<u8>();
     int* h_status = reinterpret_cast<int*>(hs + off_st);
     std::vector<int> failed;
     for (int i = 0; i < n_utts; ++i) if (h_status[i] != B2C_OK) failed.push_back(i);
     if (!failed.empty()) {
-        // second pass: only the failed utterances, worst-case arenas
-        B2cLayout L2;
-        int slots2 = 1;
-        plan(true, L2, slots2);
-        slots2 = std::min<int>(slots2, static_cast<int>(failed.size()));
-        if (d->d_ws.ensure(static_cast<u64>(slots2) * L2.gws_bytes)) return B2C_E_NOMEM;
-        for (size_t i = 0; i < failed.size(); ++i) h_ord[i] = failed[i];
-        *h_next = 0;
-        CUDA_OK(cudaMemcpyAsync(const_cast<int*>(d_ord), h_ord, 4 * failed.size(), cudaMemcpyHostToDevice, st));
-        CUDA_OK(cudaMemcpyAsync(d_next, h_next, 4, cudaMemcpyHostToDevice, st));
-        BA.L = L2;
+        // second pass for utterances whose arenas overflowed: general kernel, worst-case arenas
+        Launch ln = plan(failed, 4, true, static_cast<size_t>(n_utts));
+        if (d->d_ws.ensure(static_cast<u64>(ln.slots) * ln.L.gws_bytes)) return B2C_E_NOMEM;
+        for (size_t i = 0; i < failed.size(); ++i) h_ord[n_utts + i] = failed[i];
+        CUDA_OK(cudaMemcpyAsync(d_ord + n_utts, h_ord + n_utts, 4 * failed.size(), cudaMemcpyHostToDevice, st));
+        BA.L = ln.L;
+        BA.n_utts = ln.count;
+        BA.order = d_ord + n_utts;
+        BA.next = d_next + 15;
         BA.gws = d->d_ws.as<u8>();
-        BA.n_utts = static_cast<int>(failed.size());
-        rc = launch_beam(d, BA, slots2);
+        rc = launch_beam(d, BA, ln.slots, false);
         if (rc) return rc;
         d->tm.launches += 1;
         CUDA_OK(cudaMemcpyAsync(d->h_out_small.p, d->d_out_small.p, small_bytes, cudaMemcpyDeviceToHost, st));
@@ -904,11 +967,12 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
         CUDA_OK(cudaMemcpyAsync(d->h_out_frames.p, d->d_out_frames.p, frm_bytes, cudaMemcpyDeviceToHost, st));
         CUDA_OK(cudaStreamSynchronize(st));
         for (int i : failed)
-            if (h_status[i] != B2C_OK) return fail(B2C_E_INTERNAL, "beam kernel workspace overflow (status " + std::to_string(h_status[i]) + ")");
+            if (h_status[i] != B2C_OK)
+                return fail(B2C_E_INTERNAL, "beam kernel workspace overflow (status " + std::to_string(h_status[i]) + ")");
     }
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, d->ev[1], d->ev[2]) == cudaSuccess) d->tm.ms_prepare = ms;
-    if (cudaEventElapsedTime(&ms, d->ev[2], d->ev[3]) == cudaSuccess) d->tm.ms_beam = ms;
+    if (cudaEventElapsedTime(&ms, d->ev[5], d->ev[3]) == cudaSuccess) d->tm.ms_beam = ms;
     if (cudaEventElapsedTime(&ms, d->ev[0], d->ev[4]) == cudaSuccess) d->tm.ms_total = ms;
     d->tm.frames = static_cast<long long>(total_frames);
     // total selected tokens = last tok_start of the last utterance ... summed per utterance is not

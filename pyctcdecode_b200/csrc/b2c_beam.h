@@ -46,6 +46,7 @@ struct B2cCandTier {     // per-frame candidate working set (shared memory tier 
     double* cfold;       // merged logit_score of group leaders
     u32* cslot;
     u32* sidx;           // survivors (candidate indices)
+    u32* spre;           // survivors: high 32 bits of the order-preserving score key (dense)
     u32* ht_idx;         // slot -> representative candidate
     u32* ht_min;         // slot -> first member (dict position)
     u32* ht_max;         // slot -> last member (metadata)
@@ -163,7 +164,11 @@ B2C_HD double b2c_combine_score(const B2cParams& P, double logit, double lm_hw, 
     return s + 0.0;                                        // -0.0 -> +0.0 so that key order == float order
 }
 
-B2C_HD const B2cCandTier& b2c_pick_tier(const B2cWork& W, u32 M) { return (M <= W.tier_s.cap) ? W.tier_s : W.tier_g; }
+B2C_HD B2cCandTier b2c_pick_tier(const B2cWork& W, u32 M) {
+    B2cCandTier c = W.tier_s;
+    if (M > W.tier_s.cap) c = W.tier_g;
+    return c;
+}
 
 B2C_HD u32 b2c_ht_size(u32 M) {
     u32 h = 16;
@@ -186,29 +191,91 @@ B2C_HD void b2c_group_insert(const B2cCandTier& C, u32 hmask, u32 i) {
     b2c_atomic_add_u32(&C.ht_cnt[slot], 1u);
 }
 
-// rank survivors by (lm_score desc, enumeration index asc); ranks < width go to W.ord
-B2C_HD void b2c_rank_survivors(const B2cWork& W, const B2cCandTier& C, u32 m, u32 width) {
+// rank survivors by (lm_score desc, enumeration index asc); ranks < width go to W.ord.
+// Counting rank over a dense array of 32-bit key prefixes (uniform index -> one broadcast
+// shared-memory load per comparison); the full 64-bit key and the enumeration index are only
+// consulted when two prefixes are equal.
+B2C_HD void b2c_rank_survivors(u32* ord, const B2cCandTier& C, u32 m, u32 width) {
     B2C_FOR(a, m) {
         const u32 ia = C.sidx[a];
         const u64 ka = C.ckey[ia];
+        const u32 ha = static_cast<u32>(ka >> 32);
         u32 rank = 0;
-        for (u32 j = 0; j < m; ++j) {
+        u32 j = 0;
+        for (; j + 4 <= m; j += 4) {
+            const u32 h0 = C.spre[j], h1 = C.spre[j + 1], h2 = C.spre[j + 2], h3 = C.spre[j + 3];
+            rank += (h0 > ha) + (h1 > ha) + (h2 > ha) + (h3 > ha);
+            if (h0 == ha || h1 == ha || h2 == ha || h3 == ha) {
+                for (u32 q = j; q < j + 4; ++q) {
+                    if (q == static_cast<u32>(a) || C.spre[q] != ha) continue;
+                    const u32 iq = C.sidx[q];
+                    const u64 kq = C.ckey[iq];
+                    rank += (kq > ka || (kq == ka && iq < ia)) ? 1u : 0u;
+                }
+            }
+        }
+        for (; j < m; ++j) {
+            const u32 hj = C.spre[j];
+            if (hj > ha) { ++rank; continue; }
+            if (hj != ha || j == static_cast<u32>(a)) continue;
             const u32 ij = C.sidx[j];
             const u64 kj = C.ckey[ij];
             rank += (kj > ka || (kj == ka && ij < ia)) ? 1u : 0u;
         }
-        if (rank < width) W.ord[rank] = ia;
+        if (rank < width) ord[rank] = ia;
     }
+}
+
+// i -> (i / n, i % n) without an integer division (float reciprocal + exact correction)
+B2C_HD void b2c_divmod(u32 i, u32 n, float rcp, u32& q, u32& r) {
+    if (i >= (1u << 22)) { q = i / n; r = i - q * n; return; }
+    q = static_cast<u32>(static_cast<float>(i) * rcp);
+    r = i - q * n;
+    if (static_cast<int>(r) < 0) { --q; r += n; }
+    else if (r >= n) { ++q; r -= n; }
+}
+
+// compaction of the ranks that survive the history prune: newidx[pos] = rank, ascending
+B2C_HD void b2c_compact_kept(const u32* pslot, u32* newidx, u32* n_new, u32 nsel) {
+#if defined(__CUDA_ARCH__)
+    if (threadIdx.x < 32) {
+        const u32 lane = threadIdx.x;
+        const u32 per = (nsel + 31) >> 5;
+        const u32 beg = lane * per;
+        const u32 end = beg + per < nsel ? beg + per : nsel;
+        u32 cnt = 0;
+        for (u32 r = beg; r < end; ++r) cnt += (pslot[r] != B2C_NONE_U32) ? 1u : 0u;
+        u32 incl = cnt;
+        for (int off = 1; off < 32; off <<= 1) {
+            const u32 v = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+            if (lane >= static_cast<u32>(off)) incl += v;
+        }
+        u32 pos = incl - cnt;
+        for (u32 r = beg; r < end; ++r)
+            if (pslot[r] != B2C_NONE_U32) newidx[pos++] = r;
+        if (lane == 31) *n_new = incl;
+    }
+#else
+    u32 pos = 0;
+    for (u32 r = 0; r < nsel; ++r)
+        if (pslot[r] != B2C_NONE_U32) newidx[pos++] = r;
+    *n_new = pos;
+#endif
 }
 
 // -----------------------------------------------------------------------------------------
 // one frame
 // -----------------------------------------------------------------------------------------
+// kFast: the candidate tier is the shared-memory one (chosen by the caller when M fits); all
+// table views are value copies so that the compiler keeps them in registers and can prove the
+// shared-memory address space of every access.
+template <bool kFast>
 B2C_HD void b2c_frame_step(const B2cParams& P, B2cWork& W, int t, const u16* tk_id, const double* tk_lp, int K) {
     B2cScalars* sc = W.sc;
     const u32 n = sc->n_beams;
     const u32 M = n * static_cast<u32>(K);
-    const B2cCandTier& C = b2c_pick_tier(W, M);
+    const float rcp_n = 1.0f / static_cast<float>(n);
+    const B2cCandTier C = kFast ? W.tier_s : ((M <= W.tier_s.cap) ? W.tier_s : W.tier_g);
     if (M > C.cap) {  // cannot happen when the HBM tier is sized beam_width * V
         B2C_LEADER { sc->status = B2C_ERR_CAND_FULL; }
         B2C_SYNC();
@@ -216,7 +283,12 @@ B2C_HD void b2c_frame_step(const B2cParams& P, B2cWork& W, int t, const u16* tk_
     }
     const u32 H = b2c_ht_size(M);
     const u32 hmask = H - 1;
-    const B2cBeamTab& cur = W.cur;
+    const B2cBeamTab cur = W.cur;
+    const B2cBeamTab nx = W.nxt;
+    u32* const ord = W.ord;
+    u64* const phk = W.phk;
+    u32* const pslot = W.pslot;
+    u32* const newidx = W.newidx;
 
     // ---- phase 0 (BPE only): who consumes force_next_break -------------------------------
     if (P.is_bpe) {
@@ -258,7 +330,8 @@ B2C_HD void b2c_frame_step(const B2cParams& P, B2cWork& W, int t, const u16* tk_
         C.ht_cnt[s] = 0;
     }
     B2C_FOR(i, M) {
-        const u32 k = static_cast<u32>(i) / n, b = static_cast<u32>(i) - k * n;
+        u32 k, b;
+        b2c_divmod(static_cast<u32>(i), n, rcp_n, k, b);
         const bool forced = P.is_bpe && (W.tk_fall[k] || W.tk_ffirst[k] == b);
         B2cExp e;
         b2c_expand(P, cur, b, tk_id[k], forced, t, e);
@@ -278,16 +351,18 @@ B2C_HD void b2c_frame_step(const B2cParams& P, B2cWork& W, int t, const u16* tk_
         const u32 last = C.ht_max[slot], cnt = C.ht_cnt[slot];
         // members of a group normally share the token; tokens with identical label strings
         // (string compare in the reference) may merge across tokens, so decode every index
-        const u32 k0 = static_cast<u32>(i) / n, b0 = static_cast<u32>(i) - k0 * n;
-        const u32 kl = last / n, bl = last - kl * n;
+        u32 k0, b0, kl, bl;
+        b2c_divmod(static_cast<u32>(i), n, rcp_n, k0, b0);
+        b2c_divmod(last, n, rcp_n, kl, bl);
         double s = cur.logit[b0] + tk_lp[k0];
         if (cnt == 2) {
             s = b2c_sum_log_scores(s, cur.logit[bl] + tk_lp[kl]);
         } else if (cnt > 2) {
             for (u32 j = static_cast<u32>(i) + 1; j <= last; ++j) {
                 if (C.cslot[j] != slot) continue;
-                const u32 kj = j / n;
-                s = b2c_sum_log_scores(s, cur.logit[j - kj * n] + tk_lp[kj]);
+                u32 kj, bj;
+                b2c_divmod(j, n, rcp_n, kj, bj);
+                s = b2c_sum_log_scores(s, cur.logit[bj] + tk_lp[kj]);
             }
         }
         C.cfold[i] = s;
@@ -313,14 +388,19 @@ B2C_HD void b2c_frame_step(const B2cParams& P, B2cWork& W, int t, const u16* tk_
     const double thr = b2c_key_f64(sc->max_key) + P.prune_logp;
     B2C_FOR(i, M) {
         if (C.ht_min[C.cslot[i]] != static_cast<u32>(i)) continue;
-        if (b2c_key_f64(C.ckey[i]) >= thr) C.sidx[b2c_atomic_add_u32(&sc->n_surv, 1u)] = static_cast<u32>(i);
+        const u64 key = C.ckey[i];
+        if (b2c_key_f64(key) >= thr) {
+            const u32 pos = b2c_atomic_add_u32(&sc->n_surv, 1u);
+            C.sidx[pos] = static_cast<u32>(i);
+            C.spre[pos] = static_cast<u32>(key >> 32);
+        }
     }
     B2C_SYNC();
 
     // ---- phase 5: stable top-N (decoder.py:548) ------------------------------------------
     const u32 m = sc->n_surv;
     const u32 nsel = m < static_cast<u32>(P.beam_width) ? m : static_cast<u32>(P.beam_width);
-    b2c_rank_survivors(W, C, m, nsel);
+    b2c_rank_survivors(ord, C, m, nsel);
     B2C_SYNC();
 
     // ---- phase 6: history prune (decoder.py:550-552) -------------------------------------
@@ -329,9 +409,10 @@ B2C_HD void b2c_frame_step(const B2cParams& P, B2cWork& W, int t, const u16* tk_
         const u32 H2 = b2c_ht_size(nsel), h2mask = H2 - 1;
         B2C_FOR(s, H2) { C.ht_idx[s] = B2C_NONE_U32; C.ht_min[s] = B2C_NONE_U32; }
         B2C_FOR(r, nsel) {
-            const u32 i = W.ord[r];
+            const u32 i = ord[r];
             const u32 last = C.ht_max[C.cslot[i]];
-            const u32 k = last / n, bl = last - k * n;
+            u32 k, bl;
+            b2c_divmod(last, n, rcp_n, k, bl);
             const bool forced = P.is_bpe && (W.tk_fall[k] || W.tk_ffirst[k] == bl);
             B2cExp e;
             b2c_expand(P, cur, bl, tk_id[k], forced, t, e);
@@ -343,52 +424,42 @@ B2C_HD void b2c_frame_step(const B2cParams& P, B2cWork& W, int t, const u16* tk_
                 for (int w = static_cast<int>(keep) - 1; w >= 0; --w) hh = b2c_hist_fold(hh, par.win[w]);
                 hh = b2c_hist_fold(hh, e.word_hash);
             }
-            W.phk[r] = b2c_beam_key(hh, e.part_hash, e.part_len, e.canon);
+            phk[r] = b2c_beam_key(hh, e.part_hash, e.part_len, e.canon);
         }
         B2C_SYNC();
         // the prune table reuses ht_idx / ht_min (free after phase 4); ht_max / cslot / cfold of
         // the candidate grouping stay valid for the commit phase
         B2C_FOR(r, nsel) {
-            const u64 key = W.phk[r];
+            const u64 key = phk[r];
             u32 slot = static_cast<u32>(b2c_mix64(key)) & h2mask;
             while (true) {
                 u32 rep = b2c_atomic_cas_u32(&C.ht_idx[slot], B2C_NONE_U32, static_cast<u32>(r));
-                if (rep == B2C_NONE_U32 || W.phk[rep] == key) break;
+                if (rep == B2C_NONE_U32 || phk[rep] == key) break;
                 slot = (slot + 1) & h2mask;
             }
-            W.pslot[r] = slot;
+            pslot[r] = slot;
             b2c_atomic_min_u32(&C.ht_min[slot], static_cast<u32>(r));
         }
         B2C_SYNC();
         B2C_FOR(r, nsel) {
-            if (C.ht_min[W.pslot[r]] != static_cast<u32>(r)) { W.pslot[r] = B2C_NONE_U32; }
+            if (C.ht_min[pslot[r]] != static_cast<u32>(r)) { pslot[r] = B2C_NONE_U32; }
         }
         B2C_SYNC();
-        B2C_FOR(r, nsel) {
-            if (W.pslot[r] == B2C_NONE_U32) continue;
-            u32 pos = 0;
-            for (int q = 0; q < r; ++q) pos += (W.pslot[q] != B2C_NONE_U32) ? 1u : 0u;
-            W.newidx[pos] = static_cast<u32>(r);
-        }
-        B2C_LEADER {
-            u32 c = 0;
-            for (u32 r = 0; r < nsel; ++r) c += (W.pslot[r] != B2C_NONE_U32) ? 1u : 0u;
-            sc->n_new = c;
-        }
+        b2c_compact_kept(pslot, newidx, &sc->n_new, nsel);
         B2C_SYNC();
         n_new = sc->n_new;
     }
 
     // ---- phase 7: commit the surviving beams ---------------------------------------------
     B2C_FOR(j, n_new) {
-        const u32 r = P.prune_history ? W.newidx[j] : static_cast<u32>(j);
-        const u32 i = W.ord[r];
+        const u32 r = P.prune_history ? newidx[j] : static_cast<u32>(j);
+        const u32 i = ord[r];
         const u32 last = C.ht_max[C.cslot[i]];
-        const u32 k = last / n, bl = last - k * n;
+        u32 k, bl;
+        b2c_divmod(last, n, rcp_n, k, bl);
         const bool forced = P.is_bpe && (W.tk_fall[k] || W.tk_ffirst[k] == bl);
         B2cExp e;
         b2c_expand(P, cur, bl, tk_id[k], forced, t, e);
-        const B2cBeamTab& nx = W.nxt;
         nx.logit[j] = C.cfold[i];
         nx.text_hash[j] = e.text_hash;
         nx.part_hash[j] = e.part_hash;
@@ -520,9 +591,9 @@ struct B2cOut {              // per-utterance output views (HBM)
 B2C_HD void b2c_finalize(const B2cParams& P, B2cWork& W, const B2cOut& O) {
     B2cScalars* sc = W.sc;
     const u32 n = sc->n_beams;
-    const B2cCandTier& C = b2c_pick_tier(W, n);
+    const B2cCandTier C = b2c_pick_tier(W, n);
     const u32 H = b2c_ht_size(n), hmask = H - 1;
-    const B2cBeamTab& cur = W.cur;
+    const B2cBeamTab cur = W.cur;
     B2C_FOR(s, H) { C.ht_idx[s] = B2C_NONE_U32; C.ht_min[s] = B2C_NONE_U32; C.ht_max[s] = 0; C.ht_cnt[s] = 0; }
     B2C_FOR(b, n) {
         const u64 th = cur.part_len[b] ? b2c_text_append(cur.text_hash[b], cur.part_hash[b]) : cur.text_hash[b];
@@ -562,12 +633,16 @@ B2C_HD void b2c_finalize(const B2cParams& P, B2cWork& W, const B2cOut& O) {
     const double thr = b2c_key_f64(sc->max_key) + P.prune_logp;
     B2C_FOR(b, n) {
         if (C.ht_min[C.cslot[b]] != static_cast<u32>(b)) continue;
-        if (b2c_key_f64(C.ckey[b]) >= thr) C.sidx[b2c_atomic_add_u32(&sc->n_surv, 1u)] = static_cast<u32>(b);
+        if (b2c_key_f64(C.ckey[b]) >= thr) {
+            const u32 pos = b2c_atomic_add_u32(&sc->n_surv, 1u);
+            C.sidx[pos] = static_cast<u32>(b);
+            C.spre[pos] = static_cast<u32>(C.ckey[b] >> 32);
+        }
     }
     B2C_SYNC();
     const u32 m = sc->n_surv;
     const u32 nsel = m < static_cast<u32>(P.beam_width) ? m : static_cast<u32>(P.beam_width);
-    b2c_rank_survivors(W, C, m, nsel);
+    b2c_rank_survivors(W.ord, C, m, nsel);
     B2C_SYNC();
     const u32 n_out = nsel < static_cast<u32>(P.out_beams) ? nsel : static_cast<u32>(P.out_beams);
     B2C_LEADER { *O.n_beams = static_cast<int>(n_out); *O.status = static_cast<int>(sc->status); }

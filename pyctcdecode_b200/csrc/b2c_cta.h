@@ -14,6 +14,12 @@
 #pragma once
 #include "b2c_common.h"
 
+#if defined(__CUDACC__)
+#define B2C_NOINLINE __noinline__
+#else
+#define B2C_NOINLINE __attribute__((noinline))
+#endif
+
 #if defined(__CUDA_ARCH__)
 #define B2C_FOR(i, n) for (int i = static_cast<int>(threadIdx.x); i < static_cast<int>(n); i += static_cast<int>(blockDim.x))
 #define B2C_SYNC() __syncthreads()

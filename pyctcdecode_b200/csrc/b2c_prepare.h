@@ -224,6 +224,7 @@ struct B2cPrepArgs {
     u16* set_scratch;        // [grid][nwarps][2][set_cap] spill space for large token sets
     u32 set_cap;             // power of two >= 8 * (V + 1)
     int* is_prob;            // [B] decision taken (diagnostics / tests)
+    u32* max_k;              // [B] largest per-frame token count of the utterance (sizes the beam kernel)
 };
 
 #define B2C_PREP_WARPS 8
@@ -234,6 +235,7 @@ struct B2cPrepShared {
     double leaf_sum[B2C_PREP_LEAF_CAP];
     u32 counts[B2C_PREP_WARPS];
     u32 base;
+    u32 max_k;
     int is_prob;
     u16 sets[B2C_PREP_WARPS][2][B2C_PREP_SMEM_SET];
 };
@@ -413,6 +415,7 @@ B2C_HD void b2c_prepare_block(const B2cPrepArgs& A, int u, int block_idx, B2cPre
         }
         sh->is_prob = isp;
         sh->base = 0;
+        sh->max_k = 0;
         A.is_prob[u] = isp;
     }
     B2C_SYNC();
@@ -493,11 +496,15 @@ B2C_HD void b2c_prepare_block(const B2cPrepArgs& A, int u, int block_idx, B2cPre
         }
         B2C_SYNC();
         B2C_LEADER {
-            u32 tot = 0;
-            for (int q = 0; q < nw; ++q) tot += sh->counts[q];
+            u32 tot = 0, mx = sh->max_k;
+            for (int q = 0; q < nw; ++q) {
+                tot += sh->counts[q];
+                if (sh->counts[q] > mx) mx = sh->counts[q];
+            }
             sh->base += tot;
+            sh->max_k = mx;
         }
         B2C_SYNC();
     }
-    B2C_LEADER { tstart[Tn] = sh->base; }
+    B2C_LEADER { tstart[Tn] = sh->base; A.max_k[u] = sh->max_k; }
 }
