@@ -62,7 +62,8 @@ struct B2cLayout {
 
 static inline u64 al16(u64 x) { return (x + 15) & ~15ull; }
 static inline u64 tab_bytes(int W) { return 6 * al16(8ull * W) + 4 * al16(4ull * W) + 2 * al16(2ull * W) + 64; }
-static inline u64 sel_bytes(int W) { return al16(8ull * W) + 3 * al16(4ull * W) + 64; }
+B2C_HD u32 pt_cap_for(int W) { u32 p = 16; while (p < 2u * static_cast<u32>(W)) p <<= 1; return p; }
+static inline u64 sel_bytes(int W) { return al16(8ull * W) + 3 * al16(4ull * W) + 2 * al16(4ull * pt_cap_for(W)) + 2 * al16(4ull * B2C_NBUCKET) + 64; }
 static inline u64 tier_bytes(u32 cap, u32 ht) { return al16(8ull * cap) * 2 + al16(4ull * cap) * 3 + al16(4ull * ht) * 4 + 64; }
 
 B2C_HD u8* b2c_carve(u8*& p, u64 bytes) {
@@ -92,8 +93,8 @@ B2C_HD void b2c_carve_tier(u8* base, u32 cap, u32 ht, B2cCandTier& c) {
     c.ckey = reinterpret_cast<u64*>(b2c_carve(p, 8ull * cap));
     c.cfold = reinterpret_cast<double*>(b2c_carve(p, 8ull * cap));
     c.cslot = reinterpret_cast<u32*>(b2c_carve(p, 4ull * cap));
-    c.sidx = reinterpret_cast<u32*>(b2c_carve(p, 4ull * cap));
-    c.spre = reinterpret_cast<u32*>(b2c_carve(p, 4ull * cap));
+    c.cnext = reinterpret_cast<u32*>(b2c_carve(p, 4ull * cap));
+    c.clast = reinterpret_cast<u32*>(b2c_carve(p, 4ull * cap));
     c.ht_idx = reinterpret_cast<u32*>(b2c_carve(p, 4ull * ht));
     c.ht_min = reinterpret_cast<u32*>(b2c_carve(p, 4ull * ht));
     c.ht_max = reinterpret_cast<u32*>(b2c_carve(p, 4ull * ht));
@@ -208,6 +209,11 @@ B2C_HD void b2c_beam_block(const B2cBeamArgs& A, int slot, u8* smem) {
         W.ord = reinterpret_cast<u32*>(b2c_carve(p, 4ull * L.W));
         W.pslot = reinterpret_cast<u32*>(b2c_carve(p, 4ull * L.W));
         W.newidx = reinterpret_cast<u32*>(b2c_carve(p, 4ull * L.W));
+        W.pt_cap = pt_cap_for(L.W);
+        W.pt_idx = reinterpret_cast<u32*>(b2c_carve(p, 4ull * W.pt_cap));
+        W.pt_min = reinterpret_cast<u32*>(b2c_carve(p, 4ull * W.pt_cap));
+        W.bcnt = reinterpret_cast<u32*>(b2c_carve(p, 4ull * B2C_NBUCKET));
+        W.bhead = reinterpret_cast<u32*>(b2c_carve(p, 4ull * B2C_NBUCKET));
     }
     b2c_carve_tier(smem + L.s_tier, L.cap_s, L.ht_s, W.tier_s);
     if (!kFast && L.cap_g) b2c_carve_tier(g + L.g_tier, L.cap_g, L.ht_g, W.tier_g);
@@ -234,10 +240,11 @@ B2C_HD void b2c_beam_block(const B2cBeamArgs& A, int slot, u8* smem) {
         const u32* ts = A.tok_start + f0 + static_cast<u64>(u);
         const u16* ids = A.tok_ids + f0 * static_cast<u64>(A.P.V);
         const double* lps = A.tok_lp + f0 * static_cast<u64>(A.P.V);
-        b2c_utt_begin(A.P, W, A.start_states ? A.start_states + u : nullptr);
+        b2c_utt_begin(A.P, W, A.start_states ? A.start_states + u : nullptr, Tn > 0 ? static_cast<int>(ts[1] - ts[0]) : 1);
         for (int t = 0; t < Tn; ++t) {
             const u32 a = ts[t], b = ts[t + 1];
-            b2c_frame_step<kFast>(A.P, W, t, ids + a, lps + a, static_cast<int>(b - a));
+            const int K_next = (t + 1 < Tn) ? static_cast<int>(ts[t + 2] - b) : 1;
+            b2c_frame_step<kFast>(A.P, W, t, ids + a, lps + a, static_cast<int>(b - a), K_next);
         }
         B2cOut O;
         const u64 ob = static_cast<u64>(A.P.out_beams);
@@ -331,6 +338,9 @@ struct b2c_decoder {
         d_out_small, d_out_toks, d_out_frames;
     PinBuf h_maxk, h_meta, h_out_small, h_out_toks, h_out_frames;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t cls_stream[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // one per capacity class
+    cudaEvent_t cls_done[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t fork_ev = nullptr;
     b2c_timings_t tm;
 };
 
@@ -438,9 +448,10 @@ static int launch_prepare(b2c_decoder* d, const B2cPrepArgs& A, int n_utts) {
     return 0;
 }
 
-static int launch_beam(b2c_decoder* d, const B2cBeamArgs& A, int slots, bool fast) {
+static int launch_beam(b2c_decoder* d, const B2cBeamArgs& A, int slots, bool fast, cudaStream_t stream) {
 #ifdef B2C_HOSTSIM
     (void)d;
+    (void)stream;
     std::vector<u8> smem(A.L.smem_bytes + 64);
     for (int s = 0; s < slots; ++s) {
         if (fast) b2c_beam_block<true>(A, s, smem.data());
@@ -450,11 +461,11 @@ static int launch_beam(b2c_decoder* d, const B2cBeamArgs& A, int slots, bool fas
     if (fast) {
         if (A.L.smem_bytes > 48 * 1024)
             CUDA_OK(cudaFuncSetAttribute(b2c_beam_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(A.L.smem_bytes)));
-        b2c_beam_kernel<true><<<slots, B2C_BEAM_THREADS, A.L.smem_bytes, d->stream>>>(A);
+        b2c_beam_kernel<true><<<slots, B2C_BEAM_THREADS, A.L.smem_bytes, stream>>>(A);
     } else {
         if (A.L.smem_bytes > 48 * 1024)
             CUDA_OK(cudaFuncSetAttribute(b2c_beam_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(A.L.smem_bytes)));
-        b2c_beam_kernel<false><<<slots, B2C_BEAM_THREADS, A.L.smem_bytes, d->stream>>>(A);
+        b2c_beam_kernel<false><<<slots, B2C_BEAM_THREADS, A.L.smem_bytes, stream>>>(A);
     }
     CUDA_OK(cudaGetLastError());
 #endif
@@ -633,6 +644,11 @@ int b2c_decoder_create(const char* const* labels, int n_labels, int is_bpe, b2c_
     CUDA_OK(cudaSetDevice(device));
     CUDA_OK(cudaStreamCreate(&d->stream));
     for (int i = 0; i < 6; ++i) CUDA_OK(cudaEventCreate(&d->ev[i]));
+    for (int i = 0; i < 5; ++i) {
+        CUDA_OK(cudaStreamCreate(&d->cls_stream[i]));
+        CUDA_OK(cudaEventCreate(&d->cls_done[i]));
+    }
+    CUDA_OK(cudaEventCreate(&d->fork_ev));
     int v = 0;
     CUDA_OK(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device));
     d->n_sm = v;
@@ -658,6 +674,11 @@ void b2c_decoder_destroy(b2c_decoder_t* d) {
     PinBuf* pins[] = {&d->h_maxk, &d->h_meta, &d->h_out_small, &d->h_out_toks, &d->h_out_frames};
     for (PinBuf* b : pins) b->release();
     for (int i = 0; i < 6; ++i) if (d->ev[i]) cudaEventDestroy(d->ev[i]);
+    for (int i = 0; i < 5; ++i) {
+        if (d->cls_stream[i]) cudaStreamDestroy(d->cls_stream[i]);
+        if (d->cls_done[i]) cudaEventDestroy(d->cls_done[i]);
+    }
+    if (d->fork_ev) cudaEventDestroy(d->fork_ev);
     if (d->stream) cudaStreamDestroy(d->stream);
     delete d;
 }
@@ -916,23 +937,35 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     for (size_t i = 0; i < 16; ++i) h_next[i] = 0;
     CUDA_OK(cudaMemcpyAsync(d_ord, h_ord, 4 * ord_used, cudaMemcpyHostToDevice, st));
     CUDA_OK(cudaMemcpyAsync(d_next, h_next, 64, cudaMemcpyHostToDevice, st));
+    // the classes run CONCURRENTLY (one stream each, forked from / joined to the decoder's stream):
+    // each launch's makespan is about one utterance's latency, serialising them would multiply it
     u64 ws_need = 0;
+    std::vector<u64> ws_off;
     for (const Launch& ln : launches) {
         if (ln.L.smem_bytes > d->smem_optin) return fail(B2C_E_ARG, "beam_width too large for the shared-memory selection arrays");
-        ws_need = std::max(ws_need, static_cast<u64>(ln.slots) * ln.L.gws_bytes);
+        ws_off.push_back(ws_need);
+        ws_need += static_cast<u64>(ln.slots) * ln.L.gws_bytes;
     }
     if (d->d_ws.ensure(ws_need)) return B2C_E_NOMEM;
     CUDA_OK(cudaEventRecord(d->ev[5], st));
+    CUDA_OK(cudaEventRecord(d->fork_ev, st));
     int qi = 0;
     for (const Launch& ln : launches) {
+        cudaStream_t cs = launches.size() > 1 ? d->cls_stream[ln.cls] : st;
+        if (cs != st) CUDA_OK(cudaStreamWaitEvent(cs, d->fork_ev, 0));
         BA.L = ln.L;
         BA.n_utts = ln.count;
         BA.order = d_ord + ln.ord_off;
-        BA.next = d_next + (qi++);
-        BA.gws = d->d_ws.as<u8>();
-        rc = launch_beam(d, BA, ln.slots, ln.cls < 4);
+        BA.next = d_next + qi;
+        BA.gws = d->d_ws.as<u8>() + ws_off[qi];
+        ++qi;
+        rc = launch_beam(d, BA, ln.slots, ln.cls < 4, cs);
         if (rc) return rc;
         d->tm.launches += 1;
+        if (cs != st) {
+            CUDA_OK(cudaEventRecord(d->cls_done[ln.cls], cs));
+            CUDA_OK(cudaStreamWaitEvent(st, d->cls_done[ln.cls], 0));
+        }
     }
     CUDA_OK(cudaEventRecord(d->ev[3], st));
 
@@ -959,7 +992,7 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
         BA.order = d_ord + n_utts;
         BA.next = d_next + 15;
         BA.gws = d->d_ws.as<u8>();
-        rc = launch_beam(d, BA, ln.slots, false);
+        rc = launch_beam(d, BA, ln.slots, false, st);
         if (rc) return rc;
         d->tm.launches += 1;
         CUDA_OK(cudaMemcpyAsync(d->h_out_small.p, d->d_out_small.p, small_bytes, cudaMemcpyDeviceToHost, st));

@@ -39,17 +39,19 @@ struct B2cScalars {
     u32 n_beams, n_surv, n_new, chain_used, text_used, status, force_break, n_sel;
 };
 
+#define B2C_NBUCKET 256      // score buckets of the O(m) ranking (monotone in the score)
+
 struct B2cCandTier {     // per-frame candidate working set (shared memory tier or HBM tier)
     u32 cap;             // candidates
     u32 ht_cap;          // hash slots (power of two >= 2*cap)
-    u64* ckey;           // merge key, later order-preserving lm_score key of group leaders
+    u64* ckey;           // merge key; after fusion: order-preserving lm_score key of group leaders, 0 otherwise
     double* cfold;       // merged logit_score of group leaders
-    u32* cslot;
-    u32* sidx;           // survivors (candidate indices)
-    u32* spre;           // survivors: high 32 bits of the order-preserving score key (dense)
+    u32* cslot;          // candidate -> group slot
+    u32* cnext;          // bucket list link (leaders that survive the score threshold)
+    u32* clast;          // leader -> last member of its group (metadata donor)
     u32* ht_idx;         // slot -> representative candidate
     u32* ht_min;         // slot -> first member (dict position)
-    u32* ht_max;         // slot -> last member (metadata)
+    u32* ht_max;         // slot -> last member
     u32* ht_cnt;
 };
 
@@ -60,8 +62,13 @@ struct B2cWork {
     // selection (capacity beam_width)
     u32* ord;            // rank -> candidate index
     u64* phk;            // rank -> history-prune key
-    u32* pslot;
+    u32* pslot;          // rank -> slot in the prune table
     u32* newidx;         // new beam -> rank
+    u32* pt_idx;         // history-prune table: slot -> representative rank
+    u32* pt_min;         //                      slot -> best rank with that key
+    u32 pt_cap;          // power of two >= 2 * beam_width
+    u32* bcnt;           // [B2C_NBUCKET] survivors per score bucket, then exclusive prefix
+    u32* bhead;          // [B2C_NBUCKET] list heads
     // per-frame token side arrays for BPE force_next_break (capacity V, HBM)
     u32* tk_ffirst;
     u8* tk_fall;
@@ -176,13 +183,22 @@ B2C_HD u32 b2c_ht_size(u32 M) {
     return h;
 }
 
-// group candidates with equal keys: slot bookkeeping shared by the frame step and finalisation
-B2C_HD void b2c_group_insert(const B2cCandTier& C, u32 hmask, u32 i) {
-    const u64 key = C.ckey[i];
+B2C_HD void b2c_fence_block() {
+#if defined(__CUDA_ARCH__)
+    __threadfence_block();
+#endif
+}
+
+// group candidates with equal keys.  The caller has stored C.ckey[i] and issued a block fence;
+// a thread that loses the slot race reads the winner's key, which the winner published
+// (store, fence) before its CAS.
+B2C_HD void b2c_group_insert(const B2cCandTier& C, u32 hmask, u32 i, u64 key) {
     u32 slot = static_cast<u32>(b2c_mix64(key)) & hmask;
     while (true) {
-        u32 rep = b2c_atomic_cas_u32(&C.ht_idx[slot], B2C_NONE_U32, i);
-        if (rep == B2C_NONE_U32 || C.ckey[rep] == key) break;
+        const u32 rep = b2c_atomic_cas_u32(&C.ht_idx[slot], B2C_NONE_U32, i);
+        if (rep == B2C_NONE_U32) break;
+        b2c_fence_block();
+        if (C.ckey[rep] == key) break;
         slot = (slot + 1) & hmask;
     }
     C.cslot[i] = slot;
@@ -191,39 +207,17 @@ B2C_HD void b2c_group_insert(const B2cCandTier& C, u32 hmask, u32 i) {
     b2c_atomic_add_u32(&C.ht_cnt[slot], 1u);
 }
 
-// rank survivors by (lm_score desc, enumeration index asc); ranks < width go to W.ord.
-// Counting rank over a dense array of 32-bit key prefixes (uniform index -> one broadcast
-// shared-memory load per comparison); the full 64-bit key and the enumeration index are only
-// consulted when two prefixes are equal.
-B2C_HD void b2c_rank_survivors(u32* ord, const B2cCandTier& C, u32 m, u32 width) {
-    B2C_FOR(a, m) {
-        const u32 ia = C.sidx[a];
-        const u64 ka = C.ckey[ia];
-        const u32 ha = static_cast<u32>(ka >> 32);
-        u32 rank = 0;
-        u32 j = 0;
-        for (; j + 4 <= m; j += 4) {
-            const u32 h0 = C.spre[j], h1 = C.spre[j + 1], h2 = C.spre[j + 2], h3 = C.spre[j + 3];
-            rank += (h0 > ha) + (h1 > ha) + (h2 > ha) + (h3 > ha);
-            if (h0 == ha || h1 == ha || h2 == ha || h3 == ha) {
-                for (u32 q = j; q < j + 4; ++q) {
-                    if (q == static_cast<u32>(a) || C.spre[q] != ha) continue;
-                    const u32 iq = C.sidx[q];
-                    const u64 kq = C.ckey[iq];
-                    rank += (kq > ka || (kq == ka && iq < ia)) ? 1u : 0u;
-                }
-            }
-        }
-        for (; j < m; ++j) {
-            const u32 hj = C.spre[j];
-            if (hj > ha) { ++rank; continue; }
-            if (hj != ha || j == static_cast<u32>(a)) continue;
-            const u32 ij = C.sidx[j];
-            const u64 kj = C.ckey[ij];
-            rank += (kj > ka || (kj == ka && ij < ia)) ? 1u : 0u;
-        }
-        if (rank < width) ord[rank] = ia;
+// clear the grouping table (first H slots), the score buckets and the history-prune table for the
+// next use; called in a phase where none of them is read any more
+B2C_HD void b2c_clear_tables(const B2cWork& W, const B2cCandTier& C, u32 H) {
+    B2C_FOR(s, H) {
+        C.ht_idx[s] = B2C_NONE_U32;
+        C.ht_min[s] = B2C_NONE_U32;
+        C.ht_max[s] = 0;
+        C.ht_cnt[s] = 0;
     }
+    B2C_FOR(s, B2C_NBUCKET) { W.bcnt[s] = 0; W.bhead[s] = B2C_NONE_U32; }
+    B2C_FOR(s, W.pt_cap) { W.pt_idx[s] = B2C_NONE_U32; W.pt_min[s] = B2C_NONE_U32; }
 }
 
 // i -> (i / n, i % n) without an integer division (float reciprocal + exact correction)
@@ -235,8 +229,48 @@ B2C_HD void b2c_divmod(u32 i, u32 n, float rcp, u32& q, u32& r) {
     else if (r >= n) { ++q; r -= n; }
 }
 
+// score bucket, monotone non-increasing in the score: a larger score never gets a larger bucket
+B2C_HD u32 b2c_bucket(double max_score, double score, double scale) {
+    const double d = (max_score - score) * scale;
+    u32 b = d >= static_cast<double>(B2C_NBUCKET - 1) ? static_cast<u32>(B2C_NBUCKET - 1) : static_cast<u32>(d);
+    return b;
+}
+B2C_HD double b2c_bucket_scale(double prune_logp) {
+    double range = -prune_logp;
+    if (!(range >= 1.0)) range = 1.0;      // also catches NaN
+    if (range > 32.0) range = 32.0;
+    return static_cast<double>(B2C_NBUCKET) / range;
+}
+
+// exclusive prefix over the bucket counts (one warp), total -> *n_total
+B2C_HD void b2c_bucket_scan(u32* bcnt, u32* n_total) {
+#if defined(__CUDA_ARCH__)
+    if (threadIdx.x < 32) {
+        const u32 lane = threadIdx.x;
+        const u32 per = B2C_NBUCKET / 32;
+        u32 v[B2C_NBUCKET / 32];
+        u32 sum = 0;
+#pragma unroll
+        for (u32 q = 0; q < per; ++q) { v[q] = bcnt[lane * per + q]; sum += v[q]; }
+        u32 incl = sum;
+        for (int off = 1; off < 32; off <<= 1) {
+            const u32 o = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+            if (lane >= static_cast<u32>(off)) incl += o;
+        }
+        u32 run = incl - sum;
+#pragma unroll
+        for (u32 q = 0; q < per; ++q) { bcnt[lane * per + q] = run; run += v[q]; }
+        if (lane == 31) *n_total = incl;
+    }
+#else
+    u32 run = 0;
+    for (u32 b = 0; b < B2C_NBUCKET; ++b) { const u32 c = bcnt[b]; bcnt[b] = run; run += c; }
+    *n_total = run;
+#endif
+}
+
 // compaction of the ranks that survive the history prune: newidx[pos] = rank, ascending
-B2C_HD void b2c_compact_kept(const u32* pslot, u32* newidx, u32* n_new, u32 nsel) {
+B2C_HD void b2c_compact_kept(const u32* pslot, const u32* pt_min, u32* newidx, u32* n_new, u32 nsel) {
 #if defined(__CUDA_ARCH__)
     if (threadIdx.x < 32) {
         const u32 lane = threadIdx.x;
@@ -244,7 +278,7 @@ B2C_HD void b2c_compact_kept(const u32* pslot, u32* newidx, u32* n_new, u32 nsel
         const u32 beg = lane * per;
         const u32 end = beg + per < nsel ? beg + per : nsel;
         u32 cnt = 0;
-        for (u32 r = beg; r < end; ++r) cnt += (pslot[r] != B2C_NONE_U32) ? 1u : 0u;
+        for (u32 r = beg; r < end; ++r) cnt += (pt_min[pslot[r]] == r) ? 1u : 0u;
         u32 incl = cnt;
         for (int off = 1; off < 32; off <<= 1) {
             const u32 v = __shfl_up_sync(0xFFFFFFFFu, incl, off);
@@ -252,43 +286,48 @@ B2C_HD void b2c_compact_kept(const u32* pslot, u32* newidx, u32* n_new, u32 nsel
         }
         u32 pos = incl - cnt;
         for (u32 r = beg; r < end; ++r)
-            if (pslot[r] != B2C_NONE_U32) newidx[pos++] = r;
+            if (pt_min[pslot[r]] == r) newidx[pos++] = r;
         if (lane == 31) *n_new = incl;
     }
 #else
     u32 pos = 0;
     for (u32 r = 0; r < nsel; ++r)
-        if (pslot[r] != B2C_NONE_U32) newidx[pos++] = r;
+        if (pt_min[pslot[r]] == r) newidx[pos++] = r;
     *n_new = pos;
 #endif
 }
 
 // -----------------------------------------------------------------------------------------
-// one frame
+// one frame.  Barriers: fuse(keys+group) | fold+score | threshold+bucket | scan | rank(+history
+// keys) | compaction | commit(+clear for the next frame)  -> 7 (6 without history pruning).
+// kFast: the candidate tier is the shared-memory one; all table views are value copies so that the
+// compiler keeps them in registers and can prove the shared-memory address space of every access.
+// On entry the grouping table (first ht_size(n*K) slots), the buckets and the prune table are clear.
 // -----------------------------------------------------------------------------------------
-// kFast: the candidate tier is the shared-memory one (chosen by the caller when M fits); all
-// table views are value copies so that the compiler keeps them in registers and can prove the
-// shared-memory address space of every access.
 template <bool kFast>
-B2C_HD void b2c_frame_step(const B2cParams& P, B2cWork& W, int t, const u16* tk_id, const double* tk_lp, int K) {
+B2C_HD void b2c_frame_step(const B2cParams& P, B2cWork& W, int t, const u16* tk_id, const double* tk_lp, int K, int K_next) {
     B2cScalars* sc = W.sc;
     const u32 n = sc->n_beams;
     const u32 M = n * static_cast<u32>(K);
     const float rcp_n = 1.0f / static_cast<float>(n);
-    const B2cCandTier C = kFast ? W.tier_s : ((M <= W.tier_s.cap) ? W.tier_s : W.tier_g);
-    if (M > C.cap) {  // cannot happen when the HBM tier is sized beam_width * V
+    const B2cCandTier C = kFast ? W.tier_s : b2c_pick_tier(W, M);
+    if (M > C.cap) {  // cannot happen: the host sizes the tiers from beam_width and the token counts
         B2C_LEADER { sc->status = B2C_ERR_CAND_FULL; }
         B2C_SYNC();
         return;
     }
-    const u32 H = b2c_ht_size(M);
-    const u32 hmask = H - 1;
+    const u32 hmask = b2c_ht_size(M) - 1;
     const B2cBeamTab cur = W.cur;
     const B2cBeamTab nx = W.nxt;
     u32* const ord = W.ord;
     u64* const phk = W.phk;
     u32* const pslot = W.pslot;
     u32* const newidx = W.newidx;
+    u32* const bcnt = W.bcnt;
+    u32* const bhead = W.bhead;
+    u32* const pt_idx = W.pt_idx;
+    u32* const pt_min = W.pt_min;
+    const u32 ptmask = W.pt_cap - 1;
 
     // ---- phase 0 (BPE only): who consumes force_next_break -------------------------------
     if (P.is_bpe) {
@@ -322,32 +361,25 @@ B2C_HD void b2c_frame_step(const B2cParams& P, B2cWork& W, int t, const u16* tk_
         B2C_SYNC();
     }
 
-    // ---- phase 1: merge keys, clear the grouping table ----------------------------------
-    B2C_FOR(s, H) {
-        C.ht_idx[s] = B2C_NONE_U32;
-        C.ht_min[s] = B2C_NONE_U32;
-        C.ht_max[s] = 0;
-        C.ht_cnt[s] = 0;
-    }
+    // ---- phase 1: merge keys + grouping (publish key, fence, claim slot) ------------------
     B2C_FOR(i, M) {
         u32 k, b;
         b2c_divmod(static_cast<u32>(i), n, rcp_n, k, b);
         const bool forced = P.is_bpe && (W.tk_fall[k] || W.tk_ffirst[k] == b);
         B2cExp e;
         b2c_expand(P, cur, b, tk_id[k], forced, t, e);
-        C.ckey[i] = b2c_beam_key(e.text_hash, e.part_hash, e.part_len, e.canon);
+        const u64 key = b2c_beam_key(e.text_hash, e.part_hash, e.part_len, e.canon);
+        C.ckey[i] = key;
+        b2c_fence_block();
+        b2c_group_insert(C, hmask, static_cast<u32>(i), key);
     }
-    B2C_LEADER { sc->max_key = 0; sc->n_surv = 0; }
+    B2C_LEADER { sc->max_key = 0; }
     B2C_SYNC();
 
-    // ---- phase 2: group equal keys -------------------------------------------------------
-    B2C_FOR(i, M) { b2c_group_insert(C, hmask, static_cast<u32>(i)); }
-    B2C_SYNC();
-
-    // ---- phase 3: fold scores of each group, LM / hotword fusion, running max ------------
+    // ---- phase 2: fold scores of each group, LM / hotword fusion, running max ------------
     B2C_FOR(i, M) {
         const u32 slot = C.cslot[i];
-        if (C.ht_min[slot] != static_cast<u32>(i)) continue;
+        if (C.ht_min[slot] != static_cast<u32>(i)) { C.ckey[i] = 0; continue; }
         const u32 last = C.ht_max[slot], cnt = C.ht_cnt[slot];
         // members of a group normally share the token; tokens with identical label strings
         // (string compare in the reference) may merge across tokens, so decode every index
@@ -366,6 +398,7 @@ B2C_HD void b2c_frame_step(const B2cParams& P, B2cWork& W, int t, const u16* tk_
             }
         }
         C.cfold[i] = s;
+        C.clast[i] = last;
         const bool forced = P.is_bpe && (W.tk_fall[kl] || W.tk_ffirst[kl] == bl);
         B2cExp e;
         b2c_expand(P, cur, bl, tk_id[kl], forced, t, e);
@@ -384,33 +417,49 @@ B2C_HD void b2c_frame_step(const B2cParams& P, B2cWork& W, int t, const u16* tk_
     }
     B2C_SYNC();
 
-    // ---- phase 4: score threshold (decoder.py:545-546) ----------------------------------
-    const double thr = b2c_key_f64(sc->max_key) + P.prune_logp;
+    // ---- phase 3: score threshold (decoder.py:545-546) + monotone score buckets ------------
+    const double max_score = b2c_key_f64(sc->max_key);
+    const double thr = max_score + P.prune_logp;
+    const double bscale = b2c_bucket_scale(P.prune_logp);
     B2C_FOR(i, M) {
-        if (C.ht_min[C.cslot[i]] != static_cast<u32>(i)) continue;
         const u64 key = C.ckey[i];
-        if (b2c_key_f64(key) >= thr) {
-            const u32 pos = b2c_atomic_add_u32(&sc->n_surv, 1u);
-            C.sidx[pos] = static_cast<u32>(i);
-            C.spre[pos] = static_cast<u32>(key >> 32);
+        if (key == 0) continue;
+        const double sco = b2c_key_f64(key);
+        if (sco >= thr) {
+            const u32 b = b2c_bucket(max_score, sco, bscale);
+            b2c_atomic_add_u32(&bcnt[b], 1u);
+#if defined(__CUDA_ARCH__)
+            C.cnext[i] = atomicExch(&bhead[b], static_cast<u32>(i));
+#else
+            C.cnext[i] = bhead[b];
+            bhead[b] = static_cast<u32>(i);
+#endif
+        } else {
+            C.ckey[i] = 0;
         }
     }
     B2C_SYNC();
-
-    // ---- phase 5: stable top-N (decoder.py:548) ------------------------------------------
-    const u32 m = sc->n_surv;
-    const u32 nsel = m < static_cast<u32>(P.beam_width) ? m : static_cast<u32>(P.beam_width);
-    b2c_rank_survivors(ord, C, m, nsel);
+    b2c_bucket_scan(bcnt, &sc->n_surv);
     B2C_SYNC();
 
-    // ---- phase 6: history prune (decoder.py:550-552) -------------------------------------
-    u32 n_new = nsel;
-    if (P.prune_history) {
-        const u32 H2 = b2c_ht_size(nsel), h2mask = H2 - 1;
-        B2C_FOR(s, H2) { C.ht_idx[s] = B2C_NONE_U32; C.ht_min[s] = B2C_NONE_U32; }
-        B2C_FOR(r, nsel) {
-            const u32 i = ord[r];
-            const u32 last = C.ht_max[C.cslot[i]];
+    // ---- phase 4: stable top-N (decoder.py:548): rank = bucket prefix + exact order inside the
+    //      bucket; the history-prune key of every selected candidate goes into the prune table ----
+    const u32 m = sc->n_surv;
+    const u32 nsel = m < static_cast<u32>(P.beam_width) ? m : static_cast<u32>(P.beam_width);
+    B2C_FOR(i, M) {
+        const u64 key = C.ckey[i];
+        if (key == 0) continue;
+        const u32 b = b2c_bucket(max_score, b2c_key_f64(key), bscale);
+        u32 rank = bcnt[b];
+        for (u32 j = bhead[b]; j != B2C_NONE_U32; j = C.cnext[j]) {
+            if (j == static_cast<u32>(i)) continue;
+            const u64 kj = C.ckey[j];
+            rank += (kj > key || (kj == key && j < static_cast<u32>(i))) ? 1u : 0u;
+        }
+        if (rank >= nsel) continue;
+        ord[rank] = static_cast<u32>(i);
+        if (P.prune_history) {
+            const u32 last = C.clast[i];
             u32 k, bl;
             b2c_divmod(last, n, rcp_n, k, bl);
             const bool forced = P.is_bpe && (W.tk_fall[k] || W.tk_ffirst[k] == bl);
@@ -424,37 +473,36 @@ B2C_HD void b2c_frame_step(const B2cParams& P, B2cWork& W, int t, const u16* tk_
                 for (int w = static_cast<int>(keep) - 1; w >= 0; --w) hh = b2c_hist_fold(hh, par.win[w]);
                 hh = b2c_hist_fold(hh, e.word_hash);
             }
-            phk[r] = b2c_beam_key(hh, e.part_hash, e.part_len, e.canon);
-        }
-        B2C_SYNC();
-        // the prune table reuses ht_idx / ht_min (free after phase 4); ht_max / cslot / cfold of
-        // the candidate grouping stay valid for the commit phase
-        B2C_FOR(r, nsel) {
-            const u64 key = phk[r];
-            u32 slot = static_cast<u32>(b2c_mix64(key)) & h2mask;
+            const u64 hk = b2c_beam_key(hh, e.part_hash, e.part_len, e.canon);
+            phk[rank] = hk;
+            b2c_fence_block();
+            u32 slot = static_cast<u32>(b2c_mix64(hk)) & ptmask;
             while (true) {
-                u32 rep = b2c_atomic_cas_u32(&C.ht_idx[slot], B2C_NONE_U32, static_cast<u32>(r));
-                if (rep == B2C_NONE_U32 || phk[rep] == key) break;
-                slot = (slot + 1) & h2mask;
+                const u32 rep = b2c_atomic_cas_u32(&pt_idx[slot], B2C_NONE_U32, rank);
+                if (rep == B2C_NONE_U32) break;
+                b2c_fence_block();
+                if (phk[rep] == hk) break;
+                slot = (slot + 1) & ptmask;
             }
-            pslot[r] = slot;
-            b2c_atomic_min_u32(&C.ht_min[slot], static_cast<u32>(r));
+            pslot[rank] = slot;
+            b2c_atomic_min_u32(&pt_min[slot], rank);
         }
-        B2C_SYNC();
-        B2C_FOR(r, nsel) {
-            if (C.ht_min[pslot[r]] != static_cast<u32>(r)) { pslot[r] = B2C_NONE_U32; }
-        }
-        B2C_SYNC();
-        b2c_compact_kept(pslot, newidx, &sc->n_new, nsel);
+    }
+    B2C_SYNC();
+
+    // ---- phase 5: history prune (decoder.py:550-552): keep the best rank of every key -------
+    u32 n_new = nsel;
+    if (P.prune_history) {
+        b2c_compact_kept(pslot, pt_min, newidx, &sc->n_new, nsel);
         B2C_SYNC();
         n_new = sc->n_new;
     }
 
-    // ---- phase 7: commit the surviving beams ---------------------------------------------
+    // ---- phase 6: commit the surviving beams; clear the tables for the next frame ------------
     B2C_FOR(j, n_new) {
         const u32 r = P.prune_history ? newidx[j] : static_cast<u32>(j);
         const u32 i = ord[r];
-        const u32 last = C.ht_max[C.cslot[i]];
+        const u32 last = C.clast[i];
         u32 k, bl;
         b2c_divmod(last, n, rcp_n, k, bl);
         const bool forced = P.is_bpe && (W.tk_fall[k] || W.tk_ffirst[k] == bl);
@@ -523,6 +571,13 @@ B2C_HD void b2c_frame_step(const B2cParams& P, B2cWork& W, int t, const u16* tk_
         else if (e.part_len > 0) ps = b2c_partial_score(P, e.part_hash, e.part_len);
         nx.pscore[j] = ps;
     }
+    {
+        const u32 M_next = n_new * static_cast<u32>(K_next);
+        const B2cCandTier Cn = kFast ? W.tier_s : b2c_pick_tier(W, M_next);
+        u32 Hn = b2c_ht_size(M_next);
+        if (Hn > Cn.ht_cap) Hn = Cn.ht_cap;
+        b2c_clear_tables(W, Cn, Hn);
+    }
     B2C_LEADER { sc->n_beams = n_new; }
     B2C_SYNC();
     b2c_swap_tabs(W.cur, W.nxt);
@@ -531,7 +586,12 @@ B2C_HD void b2c_frame_step(const B2cParams& P, B2cWork& W, int t, const u16* tk_
 // -----------------------------------------------------------------------------------------
 // start of an utterance: EMPTY_START_BEAM (decoder.py:130,628) and the root text node
 // -----------------------------------------------------------------------------------------
-B2C_HD void b2c_utt_begin(const B2cParams& P, B2cWork& W, const B2cLmState* start_state) {
+B2C_HD void b2c_utt_begin(const B2cParams& P, B2cWork& W, const B2cLmState* start_state, int K_first) {
+    {
+        const u32 M0 = static_cast<u32>(K_first > 0 ? K_first : 1);
+        const B2cCandTier C0 = b2c_pick_tier(W, M0);
+        b2c_clear_tables(W, C0, b2c_ht_size(M0));
+    }
     B2C_LEADER {
         B2cScalars* sc = W.sc;
         sc->n_beams = 1;
@@ -589,36 +649,34 @@ struct B2cOut {              // per-utterance output views (HBM)
 };
 
 B2C_HD void b2c_finalize(const B2cParams& P, B2cWork& W, const B2cOut& O) {
+    // on entry the grouping table is clear for ht_size(n_beams) slots (last commit / utt_begin)
     B2cScalars* sc = W.sc;
     const u32 n = sc->n_beams;
     const B2cCandTier C = b2c_pick_tier(W, n);
-    const u32 H = b2c_ht_size(n), hmask = H - 1;
+    const u32 hmask = b2c_ht_size(n) - 1;
     const B2cBeamTab cur = W.cur;
-    B2C_FOR(s, H) { C.ht_idx[s] = B2C_NONE_U32; C.ht_min[s] = B2C_NONE_U32; C.ht_max[s] = 0; C.ht_cnt[s] = 0; }
     B2C_FOR(b, n) {
         const u64 th = cur.part_len[b] ? b2c_text_append(cur.text_hash[b], cur.part_hash[b]) : cur.text_hash[b];
-        C.ckey[b] = b2c_beam_key(th, 0, 0, B2C_NO_TOK);
+        const u64 key = b2c_beam_key(th, 0, 0, B2C_NO_TOK);
+        C.ckey[b] = key;
+        b2c_fence_block();
+        b2c_group_insert(C, hmask, static_cast<u32>(b), key);
     }
     B2C_LEADER { sc->max_key = 0; sc->n_surv = 0; }
     B2C_SYNC();
-    B2C_FOR(b, n) { b2c_group_insert(C, hmask, static_cast<u32>(b)); }
-    B2C_SYNC();
     B2C_FOR(b, n) {
         const u32 slot = C.cslot[b];
-        if (C.ht_min[slot] != static_cast<u32>(b)) continue;
+        if (C.ht_min[slot] != static_cast<u32>(b)) { C.ckey[b] = 0; continue; }
         const u32 last = C.ht_max[slot];
         double s = cur.logit[b];
         for (u32 j = static_cast<u32>(b) + 1; j <= last; ++j)
             if (C.cslot[j] == slot) s = b2c_sum_log_scores(s, cur.logit[j]);
         C.cfold[b] = s;
+        C.clast[b] = last;
         // the LAST duplicate decides the (text, next_word) split that gets scored with is_eos
         // (decoder.py:387-395: an empty next_word is scored as a word -> <unk>)
         double lm_hw;
-        if (P.lm.order > 0) {
-            B2cTextNew tn;
-            b2c_text_extend(P, W.text[cur.text_node[last]], cur.part_hash[last], cur.part_len[last], true, tn);
-            lm_hw = tn.lm_hw;
-        } else if (cur.part_len[last] > 0) {
+        if (P.lm.order > 0 || cur.part_len[last] > 0) {
             B2cTextNew tn;
             b2c_text_extend(P, W.text[cur.text_node[last]], cur.part_hash[last], cur.part_len[last], true, tn);
             lm_hw = tn.lm_hw;
@@ -632,24 +690,32 @@ B2C_HD void b2c_finalize(const B2cParams& P, B2cWork& W, const B2cOut& O) {
     B2C_SYNC();
     const double thr = b2c_key_f64(sc->max_key) + P.prune_logp;
     B2C_FOR(b, n) {
-        if (C.ht_min[C.cslot[b]] != static_cast<u32>(b)) continue;
-        if (b2c_key_f64(C.ckey[b]) >= thr) {
-            const u32 pos = b2c_atomic_add_u32(&sc->n_surv, 1u);
-            C.sidx[pos] = static_cast<u32>(b);
-            C.spre[pos] = static_cast<u32>(C.ckey[b] >> 32);
-        }
+        const u64 key = C.ckey[b];
+        if (key == 0) continue;
+        if (b2c_key_f64(key) >= thr) b2c_atomic_add_u32(&sc->n_surv, 1u);
+        else C.ckey[b] = 0;
     }
     B2C_SYNC();
+    // once per utterance: plain counting rank over the <= beam_width survivors
     const u32 m = sc->n_surv;
     const u32 nsel = m < static_cast<u32>(P.beam_width) ? m : static_cast<u32>(P.beam_width);
-    b2c_rank_survivors(W.ord, C, m, nsel);
+    B2C_FOR(b, n) {
+        const u64 key = C.ckey[b];
+        if (key == 0) continue;
+        u32 rank = 0;
+        for (u32 j = 0; j < n; ++j) {
+            const u64 kj = C.ckey[j];
+            rank += (kj > key || (kj == key && kj != 0 && j < static_cast<u32>(b))) ? 1u : 0u;
+        }
+        if (rank < nsel) W.ord[rank] = static_cast<u32>(b);
+    }
     B2C_SYNC();
     const u32 n_out = nsel < static_cast<u32>(P.out_beams) ? nsel : static_cast<u32>(P.out_beams);
     B2C_LEADER { *O.n_beams = static_cast<int>(n_out); *O.status = static_cast<int>(sc->status); }
     // ---- backtrack: one thread per output beam walks its chain ---------------------------
     B2C_FOR(r, n_out) {
         const u32 b = W.ord[r];
-        const u32 last = C.ht_max[C.cslot[b]];
+        const u32 last = C.clast[b];
         O.scores[2 * r] = C.cfold[b];
         O.scores[2 * r + 1] = b2c_key_f64(C.ckey[b]);
         B2cLmState st;

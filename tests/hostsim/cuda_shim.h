@@ -33,6 +33,7 @@ inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = nullptr; return cudaSuccess; }
 inline cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
 inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
 inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
 inline cudaError_t cudaDeviceGetAttribute(int* v, int attr, int) {
     *v = (attr == cudaDevAttrMultiProcessorCount) ? 4 : 227 * 1024;
