@@ -183,6 +183,9 @@ def main():
         torch.cuda.set_device(local_rank)
     import pyctcdecode_b200 as pkg
     from pyctcdecode_b200 import sharding
+    if os.environ.get("B200CTC_PROFILING_LIB"):   # opt-in phase-clock build (profiles/README.md), never the default
+        from pyctcdecode_b200 import _lib
+        _lib.use_library(os.environ["B200CTC_PROFILING_LIB"])
 
     wl = make_workload(spec)
     kw = dict(spec["lm"])

@@ -171,7 +171,7 @@ struct B2cBeamArgs {
     u32* next;                 // work queue head
     const u64* frame_off;
     const int* T;
-    const u32* tok_start;
+    const B2cFrameRec* tok_rec;
     const u16* tok_ids;
     const double* tok_lp;
     u8* gws;                   // [slots][L.gws_bytes]
@@ -185,6 +185,7 @@ struct B2cBeamArgs {
     u32* out_toks;
     int* out_frames;
     B2cLmState* out_states;
+    u64* phase_clk;            // [16] profiling builds only (-DB2C_PHASE_CLOCKS)
 };
 
 // kFast: every frame of every utterance handed to this launch fits the shared-memory candidate
@@ -228,6 +229,10 @@ B2C_HD void b2c_beam_block(const B2cBeamArgs& A, int slot, u8* smem) {
     W.text = reinterpret_cast<B2cText*>(g + L.g_text);
     W.text_cap = L.text_cap;
     u32* s_cur = reinterpret_cast<u32*>(smem + L.s_sc + 56);  // queue ticket of this CTA
+#if defined(B2C_PHASE_CLOCKS) && defined(__CUDA_ARCH__)
+    for (int q = 0; q < 16; ++q) W.clk[q] = 0;
+    W.clk_last = clock64();
+#endif
 
     while (true) {
         B2C_LEADER { *s_cur = b2c_atomic_add_u32(A.next, 1u); }
@@ -237,14 +242,20 @@ B2C_HD void b2c_beam_block(const B2cBeamArgs& A, int slot, u8* smem) {
         const int u = A.order[q];
         const int Tn = A.T[u];
         const u64 f0 = A.frame_off[u];
-        const u32* ts = A.tok_start + f0 + static_cast<u64>(u);
-        const u16* ids = A.tok_ids + f0 * static_cast<u64>(A.P.V);
-        const double* lps = A.tok_lp + f0 * static_cast<u64>(A.P.V);
-        b2c_utt_begin(A.P, W, A.start_states ? A.start_states + u : nullptr, Tn > 0 ? static_cast<int>(ts[1] - ts[0]) : 1);
+        const B2cFrameRec* recs = A.tok_rec + f0;
+        B2cFrameRec rec;
+        rec.off = 0;
+        rec.cnt = 1;
+        if (Tn > 0) rec = recs[0];
+        b2c_utt_begin(A.P, W, A.start_states ? A.start_states + u : nullptr, static_cast<int>(rec.cnt));
         for (int t = 0; t < Tn; ++t) {
-            const u32 a = ts[t], b = ts[t + 1];
-            const int K_next = (t + 1 < Tn) ? static_cast<int>(ts[t + 2] - b) : 1;
-            b2c_frame_step<kFast>(A.P, W, t, ids + a, lps + a, static_cast<int>(b - a), K_next);
+            B2cFrameRec nxt;
+            nxt.off = 0;
+            nxt.cnt = 1;
+            if (t + 1 < Tn) nxt = recs[t + 1];      // one frame ahead: hides the load latency
+            const u64 base = (f0 + static_cast<u64>(t & ~(B2C_RUN - 1))) * static_cast<u64>(A.P.V) + rec.off;
+            b2c_frame_step<kFast>(A.P, W, t, A.tok_ids + base, A.tok_lp + base, static_cast<int>(rec.cnt), static_cast<int>(nxt.cnt));
+            rec = nxt;
         }
         B2cOut O;
         const u64 ob = static_cast<u64>(A.P.out_beams);
@@ -258,14 +269,28 @@ B2C_HD void b2c_beam_block(const B2cBeamArgs& A, int slot, u8* smem) {
         O.frames = A.out_frames + 2 * ob * (f0 + static_cast<u64>(u));
         O.states = A.out_states + static_cast<u64>(u) * ob;
         b2c_finalize(A.P, W, O);
+        B2C_MARK(8);
     }
+#if defined(B2C_PHASE_CLOCKS) && defined(__CUDA_ARCH__)
+    if (threadIdx.x == 0 && A.phase_clk)
+        for (int q = 0; q < 16; ++q) atomicAdd(A.phase_clk + q, W.clk[q]);
+#endif
 }
 
 #ifndef B2C_HOSTSIM
 template <class T>
-__global__ void __launch_bounds__(B2C_PREP_THREADS) b2c_prepare_kernel(const B2cPrepArgs A) {
+__global__ void __launch_bounds__(B2C_PREP_THREADS) b2c_rowsum_kernel(const B2cPrepArgs A) {
+    b2c_rowsum_block<T>(A, static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x));
+}
+template <class T>
+__global__ void __launch_bounds__(128) b2c_decide_kernel(const B2cPrepArgs A) {
+    __shared__ B2cDecideShared sh;
+    b2c_decide_block<T>(A, static_cast<int>(blockIdx.x), &sh);
+}
+template <class T>
+__global__ void __launch_bounds__(B2C_PREP_THREADS) b2c_tokens_kernel(const B2cPrepArgs A) {
     __shared__ B2cPrepShared sh;
-    b2c_prepare_block<T>(A, static_cast<int>(blockIdx.x), static_cast<int>(blockIdx.x), &sh);
+    b2c_tokens_block<T>(A, static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x), &sh);
 }
 template <bool kFast>
 __global__ void __launch_bounds__(B2C_BEAM_THREADS, kFast ? 4 : 2) b2c_beam_kernel(const B2cBeamArgs A) {
@@ -334,7 +359,7 @@ struct b2c_decoder {
     int score_boundary = 1;
     int n_sm = 1;
     size_t smem_optin = 48 * 1024;
-    DevBuf d_maxk, d_toks, d_logits, d_meta, d_tok_start, d_tok_ids, d_tok_lp, d_rowsum, d_set, d_isprob, d_ws, d_hot, d_states,
+    DevBuf d_clk, d_maxk, d_toks, d_logits, d_meta, d_tok_start, d_tok_ids, d_tok_lp, d_rowsum, d_set, d_isprob, d_ws, d_hot, d_states,
         d_out_small, d_out_toks, d_out_frames;
     PinBuf h_maxk, h_meta, h_out_small, h_out_toks, h_out_frames;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -436,13 +461,18 @@ struct MetaHost {   // one pinned staging block -> one H2D copy
 };
 
 template <class T>
-static int launch_prepare(b2c_decoder* d, const B2cPrepArgs& A, int n_utts) {
+static int launch_prepare(b2c_decoder* d, const B2cPrepArgs& A, int n_utts, int grid_rows, int grid_tok) {
 #ifdef B2C_HOSTSIM
     (void)d;
+    for (int b = 0; b < grid_rows; ++b) b2c_rowsum_block<T>(A, b, grid_rows);
+    std::unique_ptr<B2cDecideShared> dsh(new B2cDecideShared());
+    for (int u = 0; u < n_utts; ++u) b2c_decide_block<T>(A, u, dsh.get());
     std::unique_ptr<B2cPrepShared> sh(new B2cPrepShared());
-    for (int u = 0; u < n_utts; ++u) b2c_prepare_block<T>(A, u, 0, sh.get());
+    for (int b = 0; b < grid_tok; ++b) b2c_tokens_block<T>(A, b, grid_tok, sh.get());
 #else
-    b2c_prepare_kernel<T><<<n_utts, B2C_PREP_THREADS, 0, d->stream>>>(A);
+    b2c_rowsum_kernel<T><<<grid_rows, B2C_PREP_THREADS, 0, d->stream>>>(A);
+    b2c_decide_kernel<T><<<n_utts, 128, 0, d->stream>>>(A);
+    b2c_tokens_kernel<T><<<grid_tok, B2C_PREP_THREADS, 0, d->stream>>>(A);
     CUDA_OK(cudaGetLastError());
 #endif
     return 0;
@@ -668,7 +698,7 @@ void b2c_decoder_destroy(b2c_decoder_t* d) {
     if (!d) return;
     cudaSetDevice(d->device);
     if (d->stream) cudaStreamSynchronize(d->stream);
-    DevBuf* bufs[] = {&d->d_maxk, &d->d_toks, &d->d_logits, &d->d_meta, &d->d_tok_start, &d->d_tok_ids, &d->d_tok_lp, &d->d_rowsum, &d->d_set,
+    DevBuf* bufs[] = {&d->d_clk, &d->d_maxk, &d->d_toks, &d->d_logits, &d->d_meta, &d->d_tok_start, &d->d_tok_ids, &d->d_tok_lp, &d->d_rowsum, &d->d_set,
                       &d->d_isprob, &d->d_ws, &d->d_hot, &d->d_states, &d->d_out_small, &d->d_out_toks, &d->d_out_frames};
     for (DevBuf* b : bufs) b->release();
     PinBuf* pins[] = {&d->h_maxk, &d->h_meta, &d->h_out_small, &d->h_out_toks, &d->h_out_frames};
@@ -747,6 +777,7 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     P.log_base_change = 0x1.26bb1bbb55516p+1;  // 1.0 / math.log10(math.e) (constants.py:18)
     P.score_boundary = d->score_boundary;
     P.hot_weight = opts->hotword_weight;
+    P.bucket_scale = b2c_bucket_scale(opts->beam_prune_logp);
     P.toks = d->d_toks.as<B2cTok>();
     if (d->lm) {
         auto it = d->lm->dev.find(d->device);
@@ -773,16 +804,21 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
         return T[0] > 0 || n_utts == 1;
     }();
     if (!contiguous_dev && d->d_logits.ensure(std::max<u64>(total_frames * V * esz, 16))) return B2C_E_NOMEM;
-    const size_t meta_bytes = al16(8ull * n_utts) + 3 * al16(4ull * n_utts) + 64;
+    const size_t meta_bytes = al16(8ull * n_utts) + 3 * al16(4ull * n_utts) + 64 + al16(8ull * (n_utts + 1));
     if (d->d_meta.ensure(meta_bytes) || d->h_meta.ensure(meta_bytes)) return B2C_E_NOMEM;
-    if (d->d_tok_start.ensure(4 * (total_frames + n_utts + 1)) || d->d_tok_ids.ensure(2 * n_entries) ||
+    if (d->d_tok_start.ensure(8 * (total_frames + 1)) || d->d_tok_ids.ensure(2 * n_entries) ||
         d->d_tok_lp.ensure(8 * n_entries) || d->d_rowsum.ensure(std::max<u64>(8 * total_frames, 16)) ||
         d->d_isprob.ensure(4ull * n_utts))
         return B2C_E_NOMEM;
     u32 set_cap = 16;
     while (set_cap < 8u * (static_cast<u32>(V) + 1)) set_cap <<= 1;
+    std::vector<u64> run_off(n_utts + 1, 0);
+    for (int i = 0; i < n_utts; ++i) run_off[i + 1] = run_off[i] + (static_cast<u64>(T[i]) + B2C_RUN - 1) / B2C_RUN;
+    const u64 total_runs = run_off[n_utts];
+    const int grid_rows = static_cast<int>(std::max<u64>(1, std::min<u64>((total_frames + 31) / 32, static_cast<u64>(d->n_sm) * 8)));
+    const int grid_tok = static_cast<int>(std::max<u64>(1, std::min<u64>((total_runs + B2C_PREP_WARPS - 1) / B2C_PREP_WARPS, static_cast<u64>(d->n_sm) * 8)));
     if (V > 32) {
-        if (d->d_set.ensure(2ull * set_cap * 2 * B2C_PREP_WARPS * n_utts)) return B2C_E_NOMEM;
+        if (d->d_set.ensure(2ull * set_cap * 2 * B2C_PREP_WARPS * grid_tok)) return B2C_E_NOMEM;
     }
     if (d->d_maxk.ensure(4ull * n_utts) || d->h_maxk.ensure(4ull * n_utts)) return B2C_E_NOMEM;
     const u32 smem_budget = static_cast<u32>(std::min<size_t>(d->smem_optin, 200 * 1024));
@@ -804,8 +840,11 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     u8* hm = d->h_meta.as<u8>();
     u64* h_fo = reinterpret_cast<u64*>(hm);
     int* h_T = reinterpret_cast<int*>(hm + al16(8ull * n_utts));
-    const size_t off_ord = al16(8ull * n_utts) + al16(4ull * n_utts);
+    const size_t off_run = al16(8ull * n_utts) + al16(4ull * n_utts);
+    const size_t off_ord = off_run + al16(8ull * (n_utts + 1));
     const size_t off_next = off_ord + 2 * al16(4ull * n_utts);
+    u64* h_run = reinterpret_cast<u64*>(hm + off_run);
+    for (int i = 0; i <= n_utts; ++i) h_run[i] = run_off[i];
     int* h_ord = reinterpret_cast<int*>(hm + off_ord);           // [2 * n_utts]: class lists, then retry list
     u32* h_next = reinterpret_cast<u32*>(hm + off_next);         // [16] one queue head per launch
     for (int i = 0; i < n_utts; ++i) { h_fo[i] = frame_off[i]; h_T[i] = T[i]; }
@@ -856,7 +895,10 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     PA.T = d_T;
     PA.V = V;
     PA.token_min_logp = opts->token_min_logp;
-    PA.tok_start = d->d_tok_start.as<u32>();
+    PA.run_off = reinterpret_cast<const u64*>(dm + off_run);
+    PA.n_utts = n_utts;
+    PA.total_frames = total_frames;
+    PA.tok_rec = d->d_tok_start.as<B2cFrameRec>();
     PA.tok_ids = d->d_tok_ids.as<u16>();
     PA.tok_lp = d->d_tok_lp.as<double>();
     PA.rowsum = d->d_rowsum.p;
@@ -864,11 +906,13 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     PA.set_cap = set_cap;
     PA.is_prob = d->d_isprob.as<int>();
     PA.max_k = d->d_maxk.as<u32>();
+    CUDA_OK(cudaMemsetAsync(d->d_maxk.p, 0, 4ull * n_utts, st));
     CUDA_OK(cudaEventRecord(d->ev[1], st));
-    int rc = dtype == B2C_DTYPE_F32 ? launch_prepare<float>(d, PA, n_utts) : launch_prepare<double>(d, PA, n_utts);
+    int rc = dtype == B2C_DTYPE_F32 ? launch_prepare<float>(d, PA, n_utts, grid_rows, grid_tok)
+                                    : launch_prepare<double>(d, PA, n_utts, grid_rows, grid_tok);
     if (rc) return rc;
     CUDA_OK(cudaEventRecord(d->ev[2], st));
-    d->tm.launches += 1;
+    d->tm.launches += 3;
 
     // ---- size the beam kernel from the token statistics of this batch ---------------------------
     CUDA_OK(cudaMemcpyAsync(d->h_maxk.p, d->d_maxk.p, 4ull * n_utts, cudaMemcpyDeviceToHost, st));
@@ -896,7 +940,7 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     BA.P = P;
     BA.frame_off = d_fo;
     BA.T = d_T;
-    BA.tok_start = PA.tok_start;
+    BA.tok_rec = PA.tok_rec;
     BA.tok_ids = PA.tok_ids;
     BA.tok_lp = PA.tok_lp;
     BA.start_states = d_start;
@@ -909,6 +953,11 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     BA.out_states = reinterpret_cast<B2cLmState*>(ds + off_ls);
     BA.out_toks = d->d_out_toks.as<u32>();
     BA.out_frames = d->d_out_frames.as<int>();
+#if defined(B2C_PHASE_CLOCKS)
+    if (d->d_clk.ensure(16 * 8)) return B2C_E_NOMEM;
+    CUDA_OK(cudaMemsetAsync(d->d_clk.p, 0, 16 * 8, st));
+    BA.phase_clk = d->d_clk.as<u64>();
+#endif
 
     struct Launch { int cls; size_t ord_off; int count; B2cLayout L; int slots; };
     auto plan = [&](const std::vector<int>& utts, int cls, bool full, size_t ord_off) {
@@ -1003,6 +1052,15 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
             if (h_status[i] != B2C_OK)
                 return fail(B2C_E_INTERNAL, "beam kernel workspace overflow (status " + std::to_string(h_status[i]) + ")");
     }
+#if defined(B2C_PHASE_CLOCKS)
+    {
+        u64 hc[16];
+        CUDA_OK(cudaMemcpy(hc, d->d_clk.p, sizeof(hc), cudaMemcpyDeviceToHost));
+        std::fprintf(stderr, "[b2c phase clocks, summed over CTAs, Mcycles]");
+        for (int q = 0; q < 9; ++q) std::fprintf(stderr, " p%d=%.2f", q, hc[q] / 1e6);
+        std::fprintf(stderr, "  frames=%llu\n", static_cast<unsigned long long>(total_frames));
+    }
+#endif
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, d->ev[1], d->ev[2]) == cudaSuccess) d->tm.ms_prepare = ms;
     if (cudaEventElapsedTime(&ms, d->ev[5], d->ev[3]) == cudaSuccess) d->tm.ms_beam = ms;

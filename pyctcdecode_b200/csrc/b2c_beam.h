@@ -77,6 +77,10 @@ struct B2cWork {
     u32 chain_cap;
     B2cText* text;
     u32 text_cap;
+#if defined(B2C_PHASE_CLOCKS)
+    u64 clk[16];
+    long long clk_last;
+#endif
 };
 
 struct B2cExp {
@@ -297,6 +301,14 @@ B2C_HD void b2c_compact_kept(const u32* pslot, const u32* pt_min, u32* newidx, u
 #endif
 }
 
+// opt-in phase timing (-DB2C_PHASE_CLOCKS, profiling builds only): thread 0 accumulates the cycles
+// between consecutive marks into W.clk[]
+#if defined(B2C_PHASE_CLOCKS) && defined(__CUDA_ARCH__)
+#define B2C_MARK(idx) do { if (threadIdx.x == 0) { const long long _c = clock64(); W.clk[idx] += static_cast<u64>(_c - W.clk_last); W.clk_last = _c; } } while (0)
+#else
+#define B2C_MARK(idx) ((void)0)
+#endif
+
 // -----------------------------------------------------------------------------------------
 // one frame.  Barriers: fuse(keys+group) | fold+score | threshold+bucket | scan | rank(+history
 // keys) | compaction | commit(+clear for the next frame)  -> 7 (6 without history pruning).
@@ -316,6 +328,7 @@ B2C_HD void b2c_frame_step(const B2cParams& P, B2cWork& W, int t, const u16* tk_
         B2C_SYNC();
         return;
     }
+    B2C_MARK(0);
     const u32 hmask = b2c_ht_size(M) - 1;
     const B2cBeamTab cur = W.cur;
     const B2cBeamTab nx = W.nxt;
@@ -375,6 +388,7 @@ B2C_HD void b2c_frame_step(const B2cParams& P, B2cWork& W, int t, const u16* tk_
     }
     B2C_LEADER { sc->max_key = 0; }
     B2C_SYNC();
+    B2C_MARK(1);
 
     // ---- phase 2: fold scores of each group, LM / hotword fusion, running max ------------
     B2C_FOR(i, M) {
@@ -416,11 +430,12 @@ B2C_HD void b2c_frame_step(const B2cParams& P, B2cWork& W, int t, const u16* tk_
         b2c_atomic_max_u64(&sc->max_key, key);
     }
     B2C_SYNC();
+    B2C_MARK(2);
 
     // ---- phase 3: score threshold (decoder.py:545-546) + monotone score buckets ------------
     const double max_score = b2c_key_f64(sc->max_key);
     const double thr = max_score + P.prune_logp;
-    const double bscale = b2c_bucket_scale(P.prune_logp);
+    const double bscale = P.bucket_scale;
     B2C_FOR(i, M) {
         const u64 key = C.ckey[i];
         if (key == 0) continue;
@@ -439,8 +454,10 @@ B2C_HD void b2c_frame_step(const B2cParams& P, B2cWork& W, int t, const u16* tk_
         }
     }
     B2C_SYNC();
+    B2C_MARK(3);
     b2c_bucket_scan(bcnt, &sc->n_surv);
     B2C_SYNC();
+    B2C_MARK(4);
 
     // ---- phase 4: stable top-N (decoder.py:548): rank = bucket prefix + exact order inside the
     //      bucket; the history-prune key of every selected candidate goes into the prune table ----
@@ -489,12 +506,14 @@ B2C_HD void b2c_frame_step(const B2cParams& P, B2cWork& W, int t, const u16* tk_
         }
     }
     B2C_SYNC();
+    B2C_MARK(5);
 
     // ---- phase 5: history prune (decoder.py:550-552): keep the best rank of every key -------
     u32 n_new = nsel;
     if (P.prune_history) {
         b2c_compact_kept(pslot, pt_min, newidx, &sc->n_new, nsel);
         B2C_SYNC();
+        B2C_MARK(6);
         n_new = sc->n_new;
     }
 
@@ -580,6 +599,7 @@ B2C_HD void b2c_frame_step(const B2cParams& P, B2cWork& W, int t, const u16* tk_
     }
     B2C_LEADER { sc->n_beams = n_new; }
     B2C_SYNC();
+    B2C_MARK(7);
     b2c_swap_tabs(W.cur, W.nxt);
 }
 

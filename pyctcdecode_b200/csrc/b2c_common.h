@@ -161,6 +161,7 @@ struct B2cParams {
     int n_hot;                 // number of hotword unigrams (0: none)
     int hot_min_len_all;       // shortest hotword (answer for the empty prefix)
     double hot_weight;
+    double bucket_scale;       // score buckets per nat for the O(m) ranking (host computed)
     const B2cHot* hot; u64 hot_mask;
     const B2cTok* toks;
     B2cLmView lm;
@@ -184,13 +185,6 @@ struct B2cText {               // one distinct "text" (sequence of finished word
     B2cLmState st;
     u32 hw_count;              // hotword unigram matches in the text
     u32 n_win;
-};
-
-// token lists produced by the prepare kernel (one compact list per frame)
-struct B2cFrameToks {
-    const u32* start;          // [T+1] offsets relative to the utterance region
-    const u16* ids;
-    const double* lp;
 };
 
 #define B2C_LOG_MIN_CLIP (-0x1.144f69ff9ffc4p+5)   // np.log(1e-15)

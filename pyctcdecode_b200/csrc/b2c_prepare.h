@@ -209,36 +209,80 @@ B2C_HD void b2c_pyset_copy_or(B2cPySet& s, u32 extra) {
 }
 
 // ---------------------------------------------------------------------------------------
-// kernel body
+// kernel bodies.  Three launches:
+//   rowsum  -- numpy-order sum of every logit row (coalesced: 8 lanes per row, 4 rows per warp)
+//   decide  -- per utterance: numpy-order mean of the row sums, math.isclose(mean, 1)
+//   tokens  -- one warp per RUN of 8 consecutive frames of one utterance, persistent grid, no
+//              block barrier: log-softmax, clip, token selection, CPython set order, compact lists
+// Token lists are compact inside a run; the run starting at frame t0 of utterance u owns the
+// entry range beginning at (frame_off[u] + t0) * V.
 // ---------------------------------------------------------------------------------------
-struct B2cPrepArgs {
-    const void* logits;      // packed [total_frames, V]
-    const u64* frame_off;    // [B]
-    const int* T;            // [B]
-    int V;
-    double token_min_logp;
-    u32* tok_start;          // [total_frames + B]: utterance u owns [frame_off[u]+u, +T+1)
-    u16* tok_ids;            // [total_frames * V]: utterance u owns [frame_off[u]*V, ...)
-    double* tok_lp;
-    void* rowsum;            // [total_frames] scratch, input dtype
-    u16* set_scratch;        // [grid][nwarps][2][set_cap] spill space for large token sets
-    u32 set_cap;             // power of two >= 8 * (V + 1)
-    int* is_prob;            // [B] decision taken (diagnostics / tests)
-    u32* max_k;              // [B] largest per-frame token count of the utterance (sizes the beam kernel)
-};
-
+#define B2C_RUN 8                   // frames per run
 #define B2C_PREP_WARPS 8
 #define B2C_PREP_SMEM_SET 128       // entries per smem set buffer (enough for 32 selected tokens)
 #define B2C_PREP_LEAF_CAP 1024
 
-struct B2cPrepShared {
-    double leaf_sum[B2C_PREP_LEAF_CAP];
-    u32 counts[B2C_PREP_WARPS];
-    u32 base;
-    u32 max_k;
-    int is_prob;
-    u16 sets[B2C_PREP_WARPS][2][B2C_PREP_SMEM_SET];
+struct B2cFrameRec { u32 off; u32 cnt; };   // token list of one frame: offset inside its run, length
+
+struct B2cPrepArgs {
+    const void* logits;      // packed [total_frames, V]
+    const u64* frame_off;    // [B]
+    const int* T;            // [B]
+    const u64* run_off;      // [B+1] exclusive prefix of ceil(T/8)
+    int n_utts;
+    u64 total_frames;
+    int V;
+    double token_min_logp;
+    B2cFrameRec* tok_rec;    // [total_frames]
+    u16* tok_ids;            // [total_frames * V]
+    double* tok_lp;
+    void* rowsum;            // [total_frames] scratch, input dtype
+    u16* set_scratch;        // [total warps][2][set_cap] spill space for large token sets
+    u32 set_cap;             // power of two >= 8 * (V + 1)
+    int* is_prob;            // [B]
+    u32* max_k;              // [B] largest per-frame token count (zeroed before the launch)
 };
+
+// ---- rowsum ---------------------------------------------------------------------------------
+template <class T>
+B2C_HD void b2c_rowsum_block(const B2cPrepArgs& A, int block_idx, int n_blocks) {
+    const T* x = static_cast<const T*>(A.logits);
+    T* rs = static_cast<T*>(A.rowsum);
+    const int V = A.V;
+#if defined(__CUDA_ARCH__)
+    const unsigned full = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31, j = lane & 7, g = lane >> 3;
+    const u64 warp = static_cast<u64>(block_idx) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const u64 n_warps = static_cast<u64>(n_blocks) * (blockDim.x >> 5);
+    if (V >= 8 && V <= 128) {
+        // numpy's 8 accumulators are the 8 lanes of a group; xor-butterfly 1,2,4 reproduces
+        // ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)); the tail (n % 8) is added sequentially
+        const int body = V - (V % 8);
+        for (u64 r0 = warp * 4; r0 < A.total_frames; r0 += n_warps * 4) {
+            const u64 r = r0 + g;
+            const bool ok = r < A.total_frames;
+            const T* a = x + (ok ? r : 0) * static_cast<u64>(V);
+            T acc = a[j];
+            for (int i = 8; i < body; i += 8) acc = acc + a[i + j];
+            acc = acc + __shfl_xor_sync(full, acc, 1);
+            acc = acc + __shfl_xor_sync(full, acc, 2);
+            acc = acc + __shfl_xor_sync(full, acc, 4);
+            for (int i = body; i < V; ++i) acc = acc + a[i];
+            if (ok && j == 0) rs[r] = acc;
+        }
+        return;
+    }
+    // generic: one thread per row, numpy's recursion evaluated sequentially
+    for (u64 r = warp * 32 + lane; r < A.total_frames; r += n_warps * 32) rs[r] = b2c_np_pairwise<T>(x + r * static_cast<u64>(V), V);
+#else
+    if (block_idx == 0)
+        for (u64 r = 0; r < A.total_frames; ++r) rs[r] = b2c_np_pairwise<T>(x + r * static_cast<u64>(V), V);
+    (void)n_blocks;
+#endif
+}
+
+// ---- decide ---------------------------------------------------------------------------------
+struct B2cDecideShared { double leaf_sum[B2C_PREP_LEAF_CAP]; };
 
 template <class T>
 struct B2cLeafShared {
@@ -246,6 +290,63 @@ struct B2cLeafShared {
     mutable int next;
     B2C_HD T operator()(long, long) const { return static_cast<T>(sums[next++]); }
 };
+
+B2C_HD int b2c_count_leaves(long n) {
+    long st[48];
+    int sp = 0, nl = 0;
+    st[sp++] = n;
+    while (sp > 0) {
+        long q = st[--sp];
+        if (q <= 128) { ++nl; continue; }
+        long q2 = q / 2;
+        q2 -= q2 % 8;
+        st[sp++] = q - q2;
+        st[sp++] = q2;
+    }
+    return nl;
+}
+
+template <class T>
+B2C_HD void b2c_decide_block(const B2cPrepArgs& A, int u, B2cDecideShared* sh) {
+    const int Tn = A.T[u];
+    const T* rs = static_cast<const T*>(A.rowsum) + A.frame_off[u];
+    const int n_leaf = b2c_count_leaves(Tn);
+    const bool par_leaves = n_leaf <= B2C_PREP_LEAF_CAP && Tn > 128;
+    if (par_leaves) {
+        B2C_FOR(lf, n_leaf) {
+            long off = 0, n = Tn;
+            int idx = lf;
+            while (n > 128) {
+                long n2 = n / 2;
+                n2 -= n2 % 8;
+                const int nl = b2c_count_leaves(n2);
+                if (idx < nl) { n = n2; } else { idx -= nl; off += n2; n = n - n2; }
+            }
+            sh->leaf_sum[lf] = static_cast<double>(b2c_np_leaf_sum<T>(rs + off, n));
+        }
+        B2C_SYNC();
+    }
+    B2C_LEADER {
+        int isp = 0;
+        if (Tn > 0) {
+            T tot;
+            if (par_leaves) {
+                B2cLeafShared<T> lf;
+                lf.sums = sh->leaf_sum;
+                lf.next = 0;
+                tot = b2c_np_pairwise_generic<T>(Tn, lf);
+            } else {
+                tot = b2c_np_pairwise<T>(rs, Tn);
+            }
+            const T mean = tot / static_cast<T>(Tn);
+            isp = b2c_isclose_one(static_cast<double>(mean)) ? 1 : 0;
+        }
+        A.is_prob[u] = isp;
+    }
+}
+
+// ---- tokens ---------------------------------------------------------------------------------
+struct B2cPrepShared { u16 sets[B2C_PREP_WARPS][2][B2C_PREP_SMEM_SET]; };
 
 // row statistics: max, log-sum-exp, argmax of the clipped log-probs, and the selected set
 // fed in ascending order into `set`.  Warp-cooperative on the device, a plain loop in hostsim.
@@ -273,7 +374,6 @@ B2C_HD void b2c_prep_row(const T* row, int V, bool is_prob, double thr, int lane
         for (int off = 16; off >= 1; off >>= 1) part = part + __shfl_xor_sync(full, part, off);
         ls = log(part);
     }
-    // argmax (first maximum) and selection
     double best = 0.0;
     int besti = -1;
     u32 nsel = 0;
@@ -337,174 +437,79 @@ B2C_HD void b2c_prep_row(const T* row, int V, bool is_prob, double thr, int lane
 #endif
 }
 
+// one run (<= 8 frames) handled by one warp
 template <class T>
-B2C_HD void b2c_prepare_block(const B2cPrepArgs& A, int u, int block_idx, B2cPrepShared* sh) {
+B2C_HD void b2c_tokens_run(const B2cPrepArgs& A, u64 run, int lane, u16* set0, u16* set1) {
+    // locate the utterance of this run (binary search over the prefix of runs per utterance)
+    int lo = 0, hi = A.n_utts - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (A.run_off[mid] <= run) lo = mid; else hi = mid - 1;
+    }
+    const int u = lo;
     const int Tn = A.T[u];
+    const int t0 = static_cast<int>(run - A.run_off[u]) * B2C_RUN;
+    const int t1 = t0 + B2C_RUN < Tn ? t0 + B2C_RUN : Tn;
     const int V = A.V;
     const u64 f0 = A.frame_off[u];
+    const bool is_prob = A.is_prob[u] != 0;
     const T* x = static_cast<const T*>(A.logits) + f0 * static_cast<u64>(V);
-    T* rs = static_cast<T*>(A.rowsum) + f0;
-    u32* tstart = A.tok_start + f0 + static_cast<u64>(u);
-    u16* ids = A.tok_ids + f0 * static_cast<u64>(V);
-    double* lps = A.tok_lp + f0 * static_cast<u64>(V);
-
-    // ---- phase A: numpy-exact row sums ---------------------------------------------------
-    B2C_FOR(t, Tn) { rs[t] = b2c_np_pairwise<T>(x + static_cast<u64>(t) * V, V); }
-    B2C_SYNC();
-    // ---- phase B: mean of the row sums in numpy order, then math.isclose(mean, 1) ---------
-    // leaves of the pairwise tree over the T row sums are summed in parallel
-    int n_leaf = 0;
-    {
-        // count leaves (block-uniform, cheap)
-        long stack_n[48];
-        int sp = 0;
-        stack_n[sp++] = Tn;
-        while (sp > 0) {
-            long n = stack_n[--sp];
-            if (n <= 128) { ++n_leaf; continue; }
-            long n2 = n / 2;
-            n2 -= n2 % 8;
-            stack_n[sp++] = n - n2;
-            stack_n[sp++] = n2;
-        }
-    }
-    const bool par_leaves = n_leaf <= B2C_PREP_LEAF_CAP && Tn > 128;
-    if (par_leaves) {
-        B2C_FOR(lf, n_leaf) {
-            // locate leaf number lf by walking the same tree (depth <= ~12)
-            long off = 0, n = Tn;
-            int idx = lf;
-            while (n > 128) {
-                long n2 = n / 2;
-                n2 -= n2 % 8;
-                // number of leaves in the left subtree
-                int nl = 0;
-                {
-                    long st[48];
-                    int sp = 0;
-                    st[sp++] = n2;
-                    while (sp > 0) {
-                        long q = st[--sp];
-                        if (q <= 128) { ++nl; continue; }
-                        long q2 = q / 2;
-                        q2 -= q2 % 8;
-                        st[sp++] = q - q2;
-                        st[sp++] = q2;
-                    }
-                }
-                if (idx < nl) { n = n2; } else { idx -= nl; off += n2; n = n - n2; }
-            }
-            sh->leaf_sum[lf] = static_cast<double>(b2c_np_leaf_sum<T>(rs + off, n));
-        }
-        B2C_SYNC();
-    }
-    B2C_LEADER {
-        int isp = 0;
-        if (Tn > 0) {
-            T tot;
-            if (par_leaves) {
-                B2cLeafShared<T> lf;
-                lf.sums = sh->leaf_sum;
-                lf.next = 0;
-                tot = b2c_np_pairwise_generic<T>(Tn, lf);
-            } else {
-                tot = b2c_np_pairwise<T>(rs, Tn);
-            }
-            const T mean = tot / static_cast<T>(Tn);
-            isp = b2c_isclose_one(static_cast<double>(mean)) ? 1 : 0;
-        }
-        sh->is_prob = isp;
-        sh->base = 0;
-        sh->max_k = 0;
-        A.is_prob[u] = isp;
-    }
-    B2C_SYNC();
-    const bool is_prob = sh->is_prob != 0;
-
-    // ---- phase C: one warp per frame, 8 frames per round --------------------------------
-    const int nw = B2C_NWARPS();
-    const int rounds = (Tn + nw - 1) / nw;
-#if defined(__CUDA_ARCH__)
-    const int lane = static_cast<int>(threadIdx.x & 31);
-#else
-    const int lane = 0;
-    // hostsim keeps the per-warp state of a round in arrays
-    B2cPySet h_set[B2C_PREP_WARPS];
-    T h_m[B2C_PREP_WARPS];
-    double h_ls[B2C_PREP_WARPS];
-    int h_amax[B2C_PREP_WARPS];
-    u32 h_nsel[B2C_PREP_WARPS];
-#endif
-    for (int r = 0; r < rounds; ++r) {
-#if defined(__CUDA_ARCH__)
+    const u64 base = (f0 + static_cast<u64>(t0)) * static_cast<u64>(V);
+    u16* ids = A.tok_ids + base;
+    double* lps = A.tok_lp + base;
+    u32 off = 0, mx = 0;
+    for (int t = t0; t < t1; ++t) {
+        const T* row = x + static_cast<u64>(t) * V;
         B2cPySet set;
-        T m = static_cast<T>(0);
-        double ls = 0.0;
-        int amax = 0;
-        u32 nsel = 0;
-#endif
-        B2C_FOR_WARP(w, nw) {
-            const int t = r * nw + w;
-#if !defined(__CUDA_ARCH__)
-            B2cPySet& set = h_set[w];
-            T& m = h_m[w];
-            double& ls = h_ls[w];
-            int& amax = h_amax[w];
-            u32& nsel = h_nsel[w];
-#endif
-            u32 cnt = 0;
-            if (t < Tn) {
-                const T* row = x + static_cast<u64>(t) * V;
-                // set buffers: shared memory while the table fits, HBM scratch otherwise
-                const bool small = V <= 32;
-                u16* b0 = small ? sh->sets[w][0] : A.set_scratch + ((static_cast<u64>(block_idx) * nw + w) * 2 + 0) * A.set_cap;
-                u16* b1 = small ? sh->sets[w][1] : A.set_scratch + ((static_cast<u64>(block_idx) * nw + w) * 2 + 1) * A.set_cap;
-                set.buf[0] = b0;
-                set.buf[1] = b1;
-                b2c_prep_row<T>(row, V, is_prob, A.token_min_logp, lane, set, m, ls, amax, nsel);
-                if (lane == 0) {
-                    b2c_pyset_copy_or(set, static_cast<u32>(amax));
-                    cnt = set.fill;
-                    sh->counts[w] = cnt;
-                }
-            } else if (lane == 0) {
-                sh->counts[w] = 0;
+        set.buf[0] = set0;
+        set.buf[1] = set1;
+        T m;
+        double ls;
+        int amax;
+        u32 nsel;
+        b2c_prep_row<T>(row, V, is_prob, A.token_min_logp, lane, set, m, ls, amax, nsel);
+        if (lane == 0) {
+            b2c_pyset_copy_or(set, static_cast<u32>(amax));
+            const u32 cnt = set.fill;
+            B2cFrameRec rec;
+            rec.off = off;
+            rec.cnt = cnt;
+            A.tok_rec[f0 + static_cast<u64>(t)] = rec;
+            const u16* tab = set.buf[set.cur];
+            for (u32 s = 0; s <= set.mask; ++s) {
+                const u16 tok = tab[s];
+                if (tok == 0xFFFFu) continue;
+                ids[off] = tok;
+                lps[off] = b2c_lp<T>(row[tok], is_prob, m, ls);
+                ++off;
             }
+            if (cnt > mx) mx = cnt;
         }
-        B2C_SYNC();
-        B2C_FOR_WARP(w, nw) {
-            const int t = r * nw + w;
-#if !defined(__CUDA_ARCH__)
-            B2cPySet& set = h_set[w];
-            T& m = h_m[w];
-            double& ls = h_ls[w];
+#if defined(__CUDA_ARCH__)
+        __syncwarp();
 #endif
-            if (t < Tn && lane == 0) {
-                u32 off = sh->base;
-                for (int q = 0; q < w; ++q) off += sh->counts[q];
-                tstart[t] = off;
-                const T* row = x + static_cast<u64>(t) * V;
-                const u16* tab = set.buf[set.cur];
-                for (u32 s = 0; s <= set.mask; ++s) {
-                    const u16 tok = tab[s];
-                    if (tok == 0xFFFFu) continue;
-                    ids[off] = tok;
-                    lps[off] = b2c_lp<T>(row[tok], is_prob, m, ls);
-                    ++off;
-                }
-            }
-        }
-        B2C_SYNC();
-        B2C_LEADER {
-            u32 tot = 0, mx = sh->max_k;
-            for (int q = 0; q < nw; ++q) {
-                tot += sh->counts[q];
-                if (sh->counts[q] > mx) mx = sh->counts[q];
-            }
-            sh->base += tot;
-            sh->max_k = mx;
-        }
-        B2C_SYNC();
     }
-    B2C_LEADER { tstart[Tn] = sh->base; A.max_k[u] = sh->max_k; }
+    if (lane == 0 && mx > 0) b2c_atomic_max_u32(&A.max_k[u], mx);
+}
+
+template <class T>
+B2C_HD void b2c_tokens_block(const B2cPrepArgs& A, int block_idx, int n_blocks, B2cPrepShared* sh) {
+    const u64 total_runs = A.run_off[A.n_utts];
+    const bool small = A.V <= 32;
+#if defined(__CUDA_ARCH__)
+    const int w = static_cast<int>(threadIdx.x >> 5), lane = static_cast<int>(threadIdx.x & 31);
+    const u64 gw = static_cast<u64>(block_idx) * B2C_PREP_WARPS + w;
+    const u64 n_warps = static_cast<u64>(n_blocks) * B2C_PREP_WARPS;
+    u16* b0 = small ? sh->sets[w][0] : A.set_scratch + (gw * 2 + 0) * A.set_cap;
+    u16* b1 = small ? sh->sets[w][1] : A.set_scratch + (gw * 2 + 1) * A.set_cap;
+    for (u64 run = gw; run < total_runs; run += n_warps) b2c_tokens_run<T>(A, run, lane, b0, b1);
+#else
+    for (int w = 0; w < B2C_PREP_WARPS; ++w) {
+        const u64 gw = static_cast<u64>(block_idx) * B2C_PREP_WARPS + w;
+        const u64 n_warps = static_cast<u64>(n_blocks) * B2C_PREP_WARPS;
+        u16* b0 = small ? sh->sets[w][0] : A.set_scratch + (gw * 2 + 0) * A.set_cap;
+        u16* b1 = small ? sh->sets[w][1] : A.set_scratch + (gw * 2 + 1) * A.set_cap;
+        for (u64 run = gw; run < total_runs; run += n_warps) b2c_tokens_run<T>(A, run, 0, b0, b1);
+    }
+#endif
 }
