@@ -63,8 +63,8 @@ struct B2cLayout {
 static inline u64 al16(u64 x) { return (x + 15) & ~15ull; }
 static inline u64 tab_bytes(int W) { return 6 * al16(8ull * W) + 4 * al16(4ull * W) + 2 * al16(2ull * W) + 64; }
 B2C_HD u32 pt_cap_for(int W) { u32 p = 16; while (p < 2u * static_cast<u32>(W)) p <<= 1; return p; }
-static inline u64 sel_bytes(int W) { return al16(8ull * W) + 3 * al16(4ull * W) + 2 * al16(4ull * pt_cap_for(W)) + 2 * al16(4ull * B2C_NBUCKET) + 64; }
-static inline u64 tier_bytes(u32 cap, u32 ht) { return al16(8ull * cap) * 2 + al16(4ull * cap) * 3 + al16(4ull * ht) * 4 + 64; }
+static inline u64 sel_bytes(int W) { return al16(8ull * W) + 2 * al16(4ull * W) + 2 * al16(4ull * pt_cap_for(W)) + (2 + B2C_MAXWARPS) * al16(4ull * B2C_NBUCKET) + 64; }
+static inline u64 tier_bytes(u32 cap, u32 ht) { return al16(8ull * cap) * 4 + al16(4ull * cap) * 4 + al16(4ull * ht) * 4 + 64; }
 
 B2C_HD u8* b2c_carve(u8*& p, u64 bytes) {
     u8* r = p;
@@ -92,6 +92,9 @@ B2C_HD void b2c_carve_tier(u8* base, u32 cap, u32 ht, B2cCandTier& c) {
     c.ht_cap = ht;
     c.ckey = reinterpret_cast<u64*>(b2c_carve(p, 8ull * cap));
     c.cfold = reinterpret_cast<double*>(b2c_carve(p, 8ull * cap));
+    c.cth = reinterpret_cast<u64*>(b2c_carve(p, 8ull * cap));
+    c.cph = reinterpret_cast<u64*>(b2c_carve(p, 8ull * cap));
+    c.cmeta = reinterpret_cast<u32*>(b2c_carve(p, 4ull * cap));
     c.cslot = reinterpret_cast<u32*>(b2c_carve(p, 4ull * cap));
     c.cnext = reinterpret_cast<u32*>(b2c_carve(p, 4ull * cap));
     c.clast = reinterpret_cast<u32*>(b2c_carve(p, 4ull * cap));
@@ -209,12 +212,12 @@ B2C_HD void b2c_beam_block(const B2cBeamArgs& A, int slot, u8* smem) {
         W.phk = reinterpret_cast<u64*>(b2c_carve(p, 8ull * L.W));
         W.ord = reinterpret_cast<u32*>(b2c_carve(p, 4ull * L.W));
         W.pslot = reinterpret_cast<u32*>(b2c_carve(p, 4ull * L.W));
-        W.newidx = reinterpret_cast<u32*>(b2c_carve(p, 4ull * L.W));
         W.pt_cap = pt_cap_for(L.W);
         W.pt_idx = reinterpret_cast<u32*>(b2c_carve(p, 4ull * W.pt_cap));
         W.pt_min = reinterpret_cast<u32*>(b2c_carve(p, 4ull * W.pt_cap));
         W.bcnt = reinterpret_cast<u32*>(b2c_carve(p, 4ull * B2C_NBUCKET));
         W.bhead = reinterpret_cast<u32*>(b2c_carve(p, 4ull * B2C_NBUCKET));
+        W.bpre = reinterpret_cast<u32*>(b2c_carve(p, 4ull * B2C_NBUCKET * B2C_MAXWARPS));
     }
     b2c_carve_tier(smem + L.s_tier, L.cap_s, L.ht_s, W.tier_s);
     if (!kFast && L.cap_g) b2c_carve_tier(g + L.g_tier, L.cap_g, L.ht_g, W.tier_g);
@@ -248,6 +251,9 @@ B2C_HD void b2c_beam_block(const B2cBeamArgs& A, int slot, u8* smem) {
         rec.cnt = 1;
         if (Tn > 0) rec = recs[0];
         b2c_utt_begin(A.P, W, A.start_states ? A.start_states + u : nullptr, static_cast<int>(rec.cnt));
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
         for (int t = 0; t < Tn; ++t) {
             B2cFrameRec nxt;
             nxt.off = 0;

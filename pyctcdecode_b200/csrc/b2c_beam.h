@@ -8,16 +8,31 @@
 //
 // Order dependence of the reference that is reproduced exactly:
 //   * candidates are enumerated token-major in the CPython set order of the frame's tokens
-//     (computed by the prepare kernel), beams in rank order inside a token;
+//     (computed by the prepare kernels), beams in rank order inside a token;
 //   * a merged group sits at the position of its FIRST member, takes the metadata (frames,
 //     text/next_word split) of its LAST member, and folds scores left to right;
 //   * ties in lm_score keep enumeration order (heapq.nlargest is stable);
 //   * the single force_next_break flag of BPE alphabets (:442,474-482).
 //
-// Phases are separated by block barriers; see b2c_cta.h for the execution-model macros.
+// Per-frame structure (4 block barriers):
+//   A  expand every (token, beam) pair ONCE, cache the result, group equal keys      | barrier
+//   B  group leaders: fold scores, LM / hotword fusion, score bucket, running max     | barrier
+//   C  every warp scans the buckets (redundantly); leaders above the threshold get their
+//      exact rank = bucket prefix + order inside the bucket; history keys are grouped  | barrier
+//   D  every warp compacts the kept ranks (redundantly) and commits its share of the new
+//      beams; tables are cleared for the next frame                                    | barrier
+// The latency of a frame, not its instruction count, bounds a single utterance, so rare paths
+// (n-gram word scoring, prefix / hotword probes, BPE force logic, finalisation) are kept out of
+// line to keep the hot loop small in the instruction cache.
 #pragma once
 #include "b2c_cta.h"
 #include "b2c_lm.h"
+
+#if defined(__CUDACC__)
+#define B2C_HDN __host__ __device__ __noinline__
+#else
+#define B2C_HDN __attribute__((noinline))
+#endif
 
 struct B2cBeamTab {
     double* logit;      // logit_score
@@ -36,18 +51,26 @@ struct B2cBeamTab {
 
 struct B2cScalars {
     u64 max_key;
-    u32 n_beams, n_surv, n_new, chain_used, text_used, status, force_break, n_sel;
+    double prev_max;     // best lm_score of the previous frame: reference point of the score buckets
+    u32 n_beams, n_sel, n_new, chain_used, text_used, status, force_break;
+    u32 flags;           // B2C_FL_*: mode bits re-read from shared memory every frame so that the compiler
+                         // cannot unswitch (= replicate) the frame loop on them
 };
+enum { B2C_FL_BPE = 1, B2C_FL_PRUNE = 2, B2C_FL_LM = 4, B2C_FL_PSCORE = 8 };
 
 #define B2C_NBUCKET 256      // score buckets of the O(m) ranking (monotone in the score)
+#define B2C_MAXWARPS 4       // warps per CTA of the beam kernel
 
 struct B2cCandTier {     // per-frame candidate working set (shared memory tier or HBM tier)
     u32 cap;             // candidates
     u32 ht_cap;          // hash slots (power of two >= 2*cap)
-    u64* ckey;           // merge key; after fusion: order-preserving lm_score key of group leaders, 0 otherwise
+    u64* ckey;           // merge key; after phase B: order-preserving lm_score key of group leaders, 0 otherwise
     double* cfold;       // merged logit_score of group leaders
+    u64* cth;            // cached expansion: text hash of the candidate
+    u64* cph;            //                   partial-word hash | branch type << 61
+    u32* cmeta;          //                   partial length | canonical token << 16
     u32* cslot;          // candidate -> group slot
-    u32* cnext;          // bucket list link (leaders that survive the score threshold)
+    u32* cnext;          // bucket list link
     u32* clast;          // leader -> last member of its group (metadata donor)
     u32* ht_idx;         // slot -> representative candidate
     u32* ht_min;         // slot -> first member (dict position)
@@ -63,12 +86,12 @@ struct B2cWork {
     u32* ord;            // rank -> candidate index
     u64* phk;            // rank -> history-prune key
     u32* pslot;          // rank -> slot in the prune table
-    u32* newidx;         // new beam -> rank
     u32* pt_idx;         // history-prune table: slot -> representative rank
     u32* pt_min;         //                      slot -> best rank with that key
     u32 pt_cap;          // power of two >= 2 * beam_width
-    u32* bcnt;           // [B2C_NBUCKET] survivors per score bucket, then exclusive prefix
+    u32* bcnt;           // [B2C_NBUCKET] leaders per score bucket
     u32* bhead;          // [B2C_NBUCKET] list heads
+    u32* bpre;           // [B2C_MAXWARPS][B2C_NBUCKET] exclusive prefix, one private copy per warp
     // per-frame token side arrays for BPE force_next_break (capacity V, HBM)
     u32* tk_ffirst;
     u8* tk_fall;
@@ -83,16 +106,7 @@ struct B2cWork {
 #endif
 };
 
-struct B2cExp {
-    int type;            // 0 blank/repeat, 1 BPE word start, 2 space, 3 continuation
-    u32 canon;
-    u64 text_hash;
-    u64 part_hash;
-    u32 part_len;
-    u64 word_hash;       // finished word (types 1,2) -- valid when word_len > 0
-    u32 word_len;
-    int pf_s, pf_e;
-};
+#define B2C_PH_MASK B2C_P61
 
 B2C_HD void b2c_swap_tabs(B2cBeamTab& a, B2cBeamTab& b) {
     B2cBeamTab t = a;
@@ -100,72 +114,156 @@ B2C_HD void b2c_swap_tabs(B2cBeamTab& a, B2cBeamTab& b) {
     b = t;
 }
 
-// one (token, beam) pair of the reference's double loop (decoder.py:447-534)
-B2C_HD void b2c_expand(const B2cParams& P, const B2cBeamTab& cur, int b, u32 tok, bool forced, int t, B2cExp& e) {
-    const B2cTok ti = P.toks[tok];
-    e.canon = ti.canon;
-    const u32 plen = cur.part_len[b];
-    const u64 ph = cur.part_hash[b];
-    e.word_len = 0;
-    e.word_hash = 0;
-    if ((ti.flags & B2C_TF_BLANK) || cur.last_tok[b] == ti.canon) {                  // (i)
-        e.type = 0;
-        e.text_hash = cur.text_hash[b];
-        e.part_hash = ph;
-        e.part_len = plen;
-        e.pf_s = cur.pf_s[b];
-        e.pf_e = (ti.flags & B2C_TF_BLANK) ? cur.pf_e[b] : t + 1;
-    } else if (P.is_bpe && ((ti.flags & B2C_TF_BPE_LEAD) || forced)) {                // (ii)
-        e.type = 1;
-        e.text_hash = plen ? b2c_text_append(cur.text_hash[b], ph) : cur.text_hash[b];
-        e.word_hash = ph;
-        e.word_len = plen;
-        e.part_hash = ti.clean_hash;
-        e.part_len = ti.clean_nchars;
-        e.pf_s = t;
-        e.pf_e = t + 1;
-    } else if (!P.is_bpe && (ti.flags & B2C_TF_SPACE)) {                              // (iii)
-        e.type = 2;
-        e.text_hash = plen ? b2c_text_append(cur.text_hash[b], ph) : cur.text_hash[b];
-        e.word_hash = ph;
-        e.word_len = plen;
-        e.part_hash = 0;
-        e.part_len = 0;
-        e.pf_s = -1;
-        e.pf_e = -1;
-    } else {                                                                          // (iv)
-        e.type = 3;
-        e.text_hash = cur.text_hash[b];
-        e.part_hash = b2c_hash_append(ph, ti.raw_hash, ti.raw_pow);
-        e.part_len = plen + ti.raw_nchars;
-        e.pf_s = cur.pf_s[b] < 0 ? t : cur.pf_s[b];
-        e.pf_e = t + 1;
-    }
+B2C_HD int b2c_warp_id() {
+#if defined(__CUDA_ARCH__)
+    return static_cast<int>(threadIdx.x >> 5);
+#else
+    return 0;
+#endif
 }
 
+// ---------------------------------------------------------------------------------------
+// out-of-line rare paths
+// ---------------------------------------------------------------------------------------
 // text-level quantities of "text + word" (reference _get_lm_beams cache miss, decoder.py:388-395)
 struct B2cTextNew {
     double raw_lm, lm_hw;
     u32 hw_count;
     B2cLmState st;
 };
-B2C_HD void b2c_text_extend(const B2cParams& P, const B2cText& parent, u64 word_hash, u32 word_len, bool is_eos,
-                            B2cTextNew& out) {
-    out.hw_count = parent.hw_count + b2c_hot_is_word(P, word_hash, word_len);
+B2C_HDN void b2c_text_extend(B2cParams P, const B2cText* parent, u64 word_hash, u32 word_len, int is_eos, B2cTextNew* out) {
+    out->hw_count = parent->hw_count + b2c_hot_is_word(P, word_hash, word_len);
     if (P.lm.order > 0) {
-        double sc = b2c_lm_score_word(P, parent.st, word_hash, word_len, is_eos, out.st);
-        out.raw_lm = parent.raw_lm + sc;
-        out.lm_hw = out.raw_lm + P.hot_weight * static_cast<double>(out.hw_count);
+        B2cLmState in = parent->st;
+        double sc = b2c_lm_score_word(P, in, word_hash, word_len, is_eos != 0, out->st);
+        out->raw_lm = parent->raw_lm + sc;
+        out->lm_hw = out->raw_lm + P.hot_weight * static_cast<double>(out->hw_count);
     } else {
-        out.raw_lm = 0.0;
-        out.st.length = 0;
-        out.lm_hw = P.hot_weight * static_cast<double>(out.hw_count);
+        out->raw_lm = 0.0;
+        out->st.length = 0;
+        out->lm_hw = P.hot_weight * static_cast<double>(out->hw_count);
     }
 }
 
-B2C_HD double b2c_combine_score(const B2cParams& P, double logit, double lm_hw, double pscore, u32 part_len) {
+// score of an unfinished word, scalar arguments only (no parameter block copy on this path)
+B2C_HDN double b2c_partial_score_ool(int n_hot, const B2cHot* hot, u64 hot_mask, double hot_weight, int hot_min_len_all,
+                                     int lm_order, int have_unigrams, const u64* prefixes, u64 prefix_mask,
+                                     double unk_offset, u64 part_hash, u32 part_len) {
+    if (n_hot > 0) {
+        if (part_len == 0) return hot_weight * 0 / hot_min_len_all;
+        const u64 key = part_hash + 1;
+        u64 slot = b2c_mix64(key) & hot_mask;
+        while (true) {
+            const B2cHot* e = hot + slot;
+            const u64 k = e->key;
+            if (k == key) return hot_weight * static_cast<double>(part_len) / static_cast<double>(e->min_len);
+            if (k == 0) break;
+            slot = (slot + 1) & hot_mask;
+        }
+    }
+    if (lm_order == 0) return 0.0;
+    double is_oov = 1.0;
+    if (have_unigrams) {
+        const u64 key = part_hash + 1;
+        u64 slot = b2c_mix64(key) & prefix_mask;
+        while (true) {
+            const u64 k = prefixes[slot];
+            if (k == key) { is_oov = 0.0; break; }
+            if (k == 0) break;
+            slot = (slot + 1) & prefix_mask;
+        }
+    }
+    double unk = unk_offset * is_oov;
+    if (part_len > B2C_AVG_TOKEN_LEN) unk = unk * static_cast<double>(part_len) / B2C_AVG_TOKEN_LEN;
+    return unk;
+}
+B2C_HD double b2c_partial_score_of(const B2cParams& P, bool need, u64 part_hash, u32 part_len) {
+    if (!need) return 0.0;
+    return b2c_partial_score_ool(P.n_hot, P.hot, P.hot_mask, P.hot_weight, P.hot_min_len_all, P.lm.order,
+                                 P.lm.have_unigrams, P.lm.prefixes, P.lm.prefix_mask, P.unk_offset, part_hash, part_len);
+}
+
+// history-prune hash of "text + word" (last hist_n words)
+B2C_HDN u64 b2c_hist_extend(const B2cText* par, int hist_n, u64 word_hash) {
+    const u32 keep = (par->n_win + 1 < static_cast<u32>(hist_n)) ? par->n_win : static_cast<u32>(hist_n) - 1;
+    u64 hh = B2C_HIST_SEED;
+    for (int w = static_cast<int>(keep) - 1; w >= 0; --w) hh = b2c_hist_fold(hh, par->win[w]);
+    return b2c_hist_fold(hh, word_hash);
+}
+
+// a surviving beam finished a word: create the text node (LM state, raw score, hotword count, history)
+struct B2cTextCommit { u32 node; double lm_hw; u64 hist_hash; };
+B2C_HDN void b2c_commit_text(B2cParams P, B2cText* arena, u32 text_cap, u32* text_used, u32* status, u32 parent_id,
+                             u64 word_hash, u32 word_len, B2cTextCommit* out) {
+    const B2cText* par = arena + parent_id;
+    B2cTextNew tn;
+    b2c_text_extend(P, par, word_hash, word_len, 0, &tn);
+    out->lm_hw = tn.lm_hw;
+    out->node = parent_id;
+    const u32 keep = (par->n_win + 1 < static_cast<u32>(P.hist_n)) ? par->n_win : static_cast<u32>(P.hist_n) - 1;
+    B2cText nt;
+    nt.win[0] = word_hash;
+    for (u32 w = 0; w < keep; ++w) nt.win[w + 1] = par->win[w];
+    for (u32 w = keep + 1; w < B2C_MAX_HIST; ++w) nt.win[w] = 0;
+    nt.n_win = keep + 1;
+    u64 hh = B2C_HIST_SEED;
+    for (int w = static_cast<int>(nt.n_win) - 1; w >= 0; --w) hh = b2c_hist_fold(hh, nt.win[w]);
+    nt.hist_hash = hh;
+    out->hist_hash = hh;
+    nt.raw_lm = tn.raw_lm;
+    nt.st = tn.st;
+    nt.hw_count = tn.hw_count;
+    const u32 id = b2c_atomic_add_u32(text_used, 1u);
+    if (id < text_cap) {
+        arena[id] = nt;
+        out->node = id;
+    } else {
+        b2c_atomic_or_u32(status, B2C_ERR_TEXT_FULL);
+    }
+}
+
+// log-sum-exp merge, out of line: float64 exp + log are ~150 instructions that only merged groups need
+B2C_HDN double b2c_sum_log_scores_ool(double s1, double s2) { return b2c_sum_log_scores(s1, s2); }
+
+// BPE only: who consumes force_next_break (decoder.py:442,474-482); contains two block barriers
+B2C_HDN void b2c_bpe_force(const B2cTok* toks, const u16* tk_id, int K, const u16* last_tok, u32 n, u32* ffirst, u8* fall,
+                           u32* force_break) {
+    B2C_FOR(k, K) {
+        const B2cTok ti = toks[tk_id[k]];
+        u32 first = B2C_NONE_U32;
+        if (!(ti.flags & B2C_TF_BLANK)) {
+            for (u32 b = 0; b < n; ++b)
+                if (last_tok[b] != ti.canon) { first = b; break; }
+        }
+        ffirst[k] = first;
+    }
+    B2C_SYNC();
+    B2C_LEADER {
+        u32 F = *force_break;
+        for (int k = 0; k < K; ++k) {
+            const u16 fl = toks[tk_id[k]].flags;
+            const u32 first = ffirst[k];
+            u8 all = 0;
+            u32 one = B2C_NONE_U32;
+            if (first != B2C_NONE_U32) {
+                const u32 trail = (fl & B2C_TF_BPE_TRAIL) ? 1u : 0u;
+                if (fl & B2C_TF_BPE_LEAD) { all = 1; F = trail; }
+                else if (F) { one = first; all = static_cast<u8>(trail); F = trail; }
+            }
+            ffirst[k] = one;
+            fall[k] = all;
+        }
+        *force_break = F;
+    }
+    B2C_SYNC();
+}
+
+// ---------------------------------------------------------------------------------------
+// small inline helpers of the hot path
+// ---------------------------------------------------------------------------------------
+B2C_HD double b2c_combine_score(bool has_lm, double logit, double lm_hw, double pscore, u32 part_len) {
     double s;
-    if (P.lm.order > 0) {
+    if (has_lm) {
         double l = lm_hw;                                  // decoder.py:396-420
         if (part_len > 0) l += pscore;
         s = logit + l;
@@ -233,71 +331,61 @@ B2C_HD void b2c_divmod(u32 i, u32 n, float rcp, u32& q, u32& r) {
     else if (r >= n) { ++q; r -= n; }
 }
 
-// score bucket, monotone non-increasing in the score: a larger score never gets a larger bucket
-B2C_HD u32 b2c_bucket(double max_score, double score, double scale) {
-    const double d = (max_score - score) * scale;
-    u32 b = d >= static_cast<double>(B2C_NBUCKET - 1) ? static_cast<u32>(B2C_NBUCKET - 1) : static_cast<u32>(d);
-    return b;
+// score bucket relative to a reference score, monotone non-increasing in the score: a larger score
+// never gets a larger bucket (scores above the reference share bucket 0, far-away ones the last)
+B2C_HD u32 b2c_bucket(double ref, double score, double scale) {
+    const double d = (ref - score) * scale;
+    if (!(d > 0.0)) return 0;
+    return d >= static_cast<double>(B2C_NBUCKET - 1) ? static_cast<u32>(B2C_NBUCKET - 1) : static_cast<u32>(d);
 }
 B2C_HD double b2c_bucket_scale(double prune_logp) {
-    double range = -prune_logp;
+    double range = -prune_logp + 2.0;      // the reference point is the previous frame's best score
     if (!(range >= 1.0)) range = 1.0;      // also catches NaN
-    if (range > 32.0) range = 32.0;
+    if (range > 34.0) range = 34.0;
     return static_cast<double>(B2C_NBUCKET) / range;
 }
 
-// exclusive prefix over the bucket counts (one warp), total -> *n_total
-B2C_HD void b2c_bucket_scan(u32* bcnt, u32* n_total) {
+// exclusive prefix over the bucket counts, computed by the calling warp into ITS copy `pre`
+B2C_HD void b2c_bucket_scan_warp(const u32* bcnt, u32* pre) {
 #if defined(__CUDA_ARCH__)
-    if (threadIdx.x < 32) {
-        const u32 lane = threadIdx.x;
-        const u32 per = B2C_NBUCKET / 32;
-        u32 v[B2C_NBUCKET / 32];
-        u32 sum = 0;
+    const u32 lane = threadIdx.x & 31;
+    const u32 per = B2C_NBUCKET / 32;
+    u32 v[B2C_NBUCKET / 32];
+    u32 sum = 0;
 #pragma unroll
-        for (u32 q = 0; q < per; ++q) { v[q] = bcnt[lane * per + q]; sum += v[q]; }
-        u32 incl = sum;
-        for (int off = 1; off < 32; off <<= 1) {
-            const u32 o = __shfl_up_sync(0xFFFFFFFFu, incl, off);
-            if (lane >= static_cast<u32>(off)) incl += o;
-        }
-        u32 run = incl - sum;
-#pragma unroll
-        for (u32 q = 0; q < per; ++q) { bcnt[lane * per + q] = run; run += v[q]; }
-        if (lane == 31) *n_total = incl;
+    for (u32 q = 0; q < per; ++q) { v[q] = bcnt[lane * per + q]; sum += v[q]; }
+    u32 incl = sum;
+    for (int off = 1; off < 32; off <<= 1) {
+        const u32 o = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+        if (lane >= static_cast<u32>(off)) incl += o;
     }
+    u32 run = incl - sum;
+#pragma unroll
+    for (u32 q = 0; q < per; ++q) { pre[lane * per + q] = run; run += v[q]; }
+    __syncwarp();
 #else
     u32 run = 0;
-    for (u32 b = 0; b < B2C_NBUCKET; ++b) { const u32 c = bcnt[b]; bcnt[b] = run; run += c; }
-    *n_total = run;
+    for (u32 b = 0; b < B2C_NBUCKET; ++b) { pre[b] = run; run += bcnt[b]; }
 #endif
 }
 
-// compaction of the ranks that survive the history prune: newidx[pos] = rank, ascending
-B2C_HD void b2c_compact_kept(const u32* pslot, const u32* pt_min, u32* newidx, u32* n_new, u32 nsel) {
+B2C_HD void b2c_block_max_u64(u64 v, u64* target) {
 #if defined(__CUDA_ARCH__)
-    if (threadIdx.x < 32) {
-        const u32 lane = threadIdx.x;
-        const u32 per = (nsel + 31) >> 5;
-        const u32 beg = lane * per;
-        const u32 end = beg + per < nsel ? beg + per : nsel;
-        u32 cnt = 0;
-        for (u32 r = beg; r < end; ++r) cnt += (pt_min[pslot[r]] == r) ? 1u : 0u;
-        u32 incl = cnt;
-        for (int off = 1; off < 32; off <<= 1) {
-            const u32 v = __shfl_up_sync(0xFFFFFFFFu, incl, off);
-            if (lane >= static_cast<u32>(off)) incl += v;
-        }
-        u32 pos = incl - cnt;
-        for (u32 r = beg; r < end; ++r)
-            if (pt_min[pslot[r]] == r) newidx[pos++] = r;
-        if (lane == 31) *n_new = incl;
+    for (int off = 16; off >= 1; off >>= 1) {
+        const u64 o = __shfl_xor_sync(0xFFFFFFFFu, v, off);
+        if (o > v) v = o;
     }
+    if ((threadIdx.x & 31) == 0 && v) atomicMax(target, v);
 #else
-    u32 pos = 0;
-    for (u32 r = 0; r < nsel; ++r)
-        if (pt_min[pslot[r]] == r) newidx[pos++] = r;
-    *n_new = pos;
+    if (v > *target) *target = v;
+#endif
+}
+B2C_HD void b2c_block_add_u32(u32 v, u32* target) {
+#if defined(__CUDA_ARCH__)
+    for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, off);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(target, v);
+#else
+    *target += v;
 #endif
 }
 
@@ -309,12 +397,79 @@ B2C_HD void b2c_compact_kept(const u32* pslot, const u32* pt_min, u32* newidx, u
 #define B2C_MARK(idx) ((void)0)
 #endif
 
+// one new beam: rank r of this frame becomes beam j of the next frame
+template <class Tier>
+B2C_HD void b2c_commit_one(const B2cParams& P, const B2cWork& W, const Tier& C, const B2cBeamTab& cur, const B2cBeamTab& nx,
+                           const u16* tk_id, u32 n, float rcp_n, int t, u32 j, u32 r, u32 flags) {
+    B2cScalars* sc = W.sc;
+    const u32 i = W.ord[r];
+    const u32 last = C.clast[i];
+    u32 k, bl;
+    b2c_divmod(last, n, rcp_n, k, bl);
+    const u64 cph = C.cph[last];
+    const u32 type = static_cast<u32>(cph >> 61);
+    const u64 part_hash = cph & B2C_PH_MASK;
+    const u32 meta = C.cmeta[last];
+    const u32 part_len = meta & 0xFFFFu;
+    nx.logit[j] = C.cfold[i];
+    nx.text_hash[j] = C.cth[last];
+    nx.part_hash[j] = part_hash;
+    nx.part_len[j] = static_cast<u16>(part_len);
+    nx.last_tok[j] = static_cast<u16>(meta >> 16);
+    // partial_frames (decoder.py:454-461,495,513,519-523)
+    const int ps0 = cur.pf_s[bl], pe0 = cur.pf_e[bl];
+    int pfs, pfe;
+    if (type == 0) { pfs = ps0; pfe = (P.toks[tk_id[k]].flags & B2C_TF_BLANK) ? pe0 : t + 1; }
+    else if (type == 1) { pfs = t; pfe = t + 1; }
+    else if (type == 2) { pfs = -1; pfe = -1; }
+    else { pfs = ps0 < 0 ? t : ps0; pfe = t + 1; }
+    nx.pf_s[j] = pfs;
+    nx.pf_e[j] = pfe;
+    const u32 word_len = (type == 1 || type == 2) ? static_cast<u32>(cur.part_len[bl]) : 0u;
+    // backtrack chain
+    u32 chain = cur.chain[bl];
+    if (type != 0) {
+        const u32 id = b2c_atomic_add_u32(&sc->chain_used, 1u);
+        if (id < W.chain_cap) {
+            B2cChain c;
+            c.parent = chain;
+            c.tok = tk_id[k];
+            c.kind = type == 3 ? B2C_CK_CONT : (type == 2 ? B2C_CK_SPACE : B2C_CK_BPE);
+            c.has_word = word_len > 0 ? 1 : 0;
+            c.ws = ps0;
+            c.we = pe0;
+            W.chain[id] = c;
+            chain = id;
+        } else {
+            b2c_atomic_or_u32(&sc->status, B2C_ERR_CHAIN_FULL);
+        }
+    }
+    nx.chain[j] = chain;
+    // text level
+    u32 tnode = cur.text_node[bl];
+    double lm_hw = cur.lm_hw[bl];
+    u64 hh = cur.hist_hash[bl];
+    if (word_len > 0) {
+        B2cTextCommit tc;
+        b2c_commit_text(P, W.text, W.text_cap, &sc->text_used, &sc->status, tnode, cur.part_hash[bl], word_len, &tc);
+        tnode = tc.node;
+        lm_hw = tc.lm_hw;
+        hh = tc.hist_hash;
+    }
+    nx.text_node[j] = tnode;
+    nx.lm_hw[j] = lm_hw;
+    nx.hist_hash[j] = hh;
+    double ps = 0.0;
+    if (type == 0) ps = cur.pscore[bl];
+    else if (part_len > 0) ps = b2c_partial_score_of(P, (flags & B2C_FL_PSCORE) != 0, part_hash, part_len);
+    nx.pscore[j] = ps;
+}
+
 // -----------------------------------------------------------------------------------------
-// one frame.  Barriers: fuse(keys+group) | fold+score | threshold+bucket | scan | rank(+history
-// keys) | compaction | commit(+clear for the next frame)  -> 7 (6 without history pruning).
-// kFast: the candidate tier is the shared-memory one; all table views are value copies so that the
-// compiler keeps them in registers and can prove the shared-memory address space of every access.
-// On entry the grouping table (first ht_size(n*K) slots), the buckets and the prune table are clear.
+// one frame.  kFast: the candidate tier is the shared-memory one; all table views are value copies
+// so that the compiler keeps them in registers and can prove the shared-memory address space of
+// every access.  On entry the grouping table (first ht_size(n*K) slots), the buckets and the
+// prune table are clear (previous frame's phase D / b2c_utt_begin).
 // -----------------------------------------------------------------------------------------
 template <bool kFast>
 B2C_HD void b2c_frame_step(const B2cParams& P, B2cWork& W, int t, const u16* tk_id, const double* tk_lp, int K, int K_next) {
@@ -335,261 +490,178 @@ B2C_HD void b2c_frame_step(const B2cParams& P, B2cWork& W, int t, const u16* tk_
     u32* const ord = W.ord;
     u64* const phk = W.phk;
     u32* const pslot = W.pslot;
-    u32* const newidx = W.newidx;
     u32* const bcnt = W.bcnt;
     u32* const bhead = W.bhead;
+    u32* const bpre = W.bpre + static_cast<u32>(b2c_warp_id()) * B2C_NBUCKET;
     u32* const pt_idx = W.pt_idx;
     u32* const pt_min = W.pt_min;
     const u32 ptmask = W.pt_cap - 1;
+    const double ref = sc->prev_max;
+    const double bscale = P.bucket_scale;
+    const u32 flags = sc->flags;
+    const bool is_bpe = (flags & B2C_FL_BPE) != 0, prune = (flags & B2C_FL_PRUNE) != 0;
 
-    // ---- phase 0 (BPE only): who consumes force_next_break -------------------------------
-    if (P.is_bpe) {
-        B2C_FOR(k, K) {
-            const B2cTok ti = P.toks[tk_id[k]];
-            u32 first = B2C_NONE_U32;
-            if (!(ti.flags & B2C_TF_BLANK)) {
-                for (u32 b = 0; b < n; ++b)
-                    if (cur.last_tok[b] != ti.canon) { first = b; break; }
-            }
-            W.tk_ffirst[k] = first;
-        }
-        B2C_SYNC();
-        B2C_LEADER {
-            u32 F = sc->force_break;
-            for (int k = 0; k < K; ++k) {
-                const u16 fl = P.toks[tk_id[k]].flags;
-                const u32 first = W.tk_ffirst[k];
-                u8 all = 0;
-                u32 one = B2C_NONE_U32;
-                if (first != B2C_NONE_U32) {
-                    const u32 trail = (fl & B2C_TF_BPE_TRAIL) ? 1u : 0u;
-                    if (fl & B2C_TF_BPE_LEAD) { all = 1; F = trail; }
-                    else if (F) { one = first; all = static_cast<u8>(trail); F = trail; }
-                }
-                W.tk_ffirst[k] = one;
-                W.tk_fall[k] = all;
-            }
-            sc->force_break = F;
-        }
-        B2C_SYNC();
-    }
+    if (is_bpe) b2c_bpe_force(P.toks, tk_id, K, cur.last_tok, n, W.tk_ffirst, W.tk_fall, &sc->force_break);
 
-    // ---- phase 1: merge keys + grouping (publish key, fence, claim slot) ------------------
+    // ---- phase A: expand once, cache, merge key, grouping (publish key, fence, claim slot) -----
     B2C_FOR(i, M) {
         u32 k, b;
         b2c_divmod(static_cast<u32>(i), n, rcp_n, k, b);
-        const bool forced = P.is_bpe && (W.tk_fall[k] || W.tk_ffirst[k] == b);
-        B2cExp e;
-        b2c_expand(P, cur, b, tk_id[k], forced, t, e);
-        const u64 key = b2c_beam_key(e.text_hash, e.part_hash, e.part_len, e.canon);
+        const B2cTok ti = P.toks[tk_id[k]];
+        const u32 plen = cur.part_len[b];
+        const u64 ph = cur.part_hash[b];
+        u64 th = cur.text_hash[b];
+        u64 nph;
+        u32 nplen, type;
+        if ((ti.flags & B2C_TF_BLANK) || cur.last_tok[b] == ti.canon) {                        // (i)
+            type = 0; nph = ph; nplen = plen;
+        } else if (is_bpe && ((ti.flags & B2C_TF_BPE_LEAD) || W.tk_fall[k] || W.tk_ffirst[k] == b)) {       // (ii)
+            type = 1; nph = ti.clean_hash; nplen = ti.clean_nchars;
+            if (plen) th = b2c_text_append(th, ph);
+        } else if (!is_bpe && (ti.flags & B2C_TF_SPACE)) {                                     // (iii)
+            type = 2; nph = 0; nplen = 0;
+            if (plen) th = b2c_text_append(th, ph);
+        } else {                                                                               // (iv)
+            type = 3; nph = b2c_hash_append(ph, ti.raw_hash, ti.raw_pow); nplen = plen + ti.raw_nchars;
+        }
+        C.cth[i] = th;
+        C.cph[i] = nph | (static_cast<u64>(type) << 61);
+        C.cmeta[i] = (nplen & 0xFFFFu) | (static_cast<u32>(ti.canon) << 16);
+        const u64 key = b2c_beam_key(th, nph, nplen, ti.canon);
         C.ckey[i] = key;
         b2c_fence_block();
         b2c_group_insert(C, hmask, static_cast<u32>(i), key);
     }
-    B2C_LEADER { sc->max_key = 0; }
+    B2C_LEADER { sc->max_key = 0; sc->n_sel = 0; }
     B2C_SYNC();
     B2C_MARK(1);
 
-    // ---- phase 2: fold scores of each group, LM / hotword fusion, running max ------------
-    B2C_FOR(i, M) {
-        const u32 slot = C.cslot[i];
-        if (C.ht_min[slot] != static_cast<u32>(i)) { C.ckey[i] = 0; continue; }
-        const u32 last = C.ht_max[slot], cnt = C.ht_cnt[slot];
-        // members of a group normally share the token; tokens with identical label strings
-        // (string compare in the reference) may merge across tokens, so decode every index
-        u32 k0, b0, kl, bl;
-        b2c_divmod(static_cast<u32>(i), n, rcp_n, k0, b0);
-        b2c_divmod(last, n, rcp_n, kl, bl);
-        double s = cur.logit[b0] + tk_lp[k0];
-        if (cnt == 2) {
-            s = b2c_sum_log_scores(s, cur.logit[bl] + tk_lp[kl]);
-        } else if (cnt > 2) {
-            for (u32 j = static_cast<u32>(i) + 1; j <= last; ++j) {
+    // ---- phase B: fold scores of each group, LM / hotword fusion, bucket, running max ----------
+    {
+        u64 tmax = 0;
+        B2C_FOR(i, M) {
+            const u32 slot = C.cslot[i];
+            if (C.ht_min[slot] != static_cast<u32>(i)) { C.ckey[i] = 0; continue; }
+            const u32 last = C.ht_max[slot], cnt = C.ht_cnt[slot];
+            // members of a group normally share the token; tokens with identical label strings
+            // (string compare in the reference) may merge across tokens, so decode every index
+            u32 k0, b0, kl, bl;
+            b2c_divmod(static_cast<u32>(i), n, rcp_n, k0, b0);
+            b2c_divmod(last, n, rcp_n, kl, bl);
+            double s = cur.logit[b0] + tk_lp[k0];
+            for (u32 j = (cnt == 2) ? last : static_cast<u32>(i) + 1; cnt > 1 && j <= last; ++j) {
                 if (C.cslot[j] != slot) continue;
                 u32 kj, bj;
                 b2c_divmod(j, n, rcp_n, kj, bj);
-                s = b2c_sum_log_scores(s, cur.logit[bj] + tk_lp[kj]);
+                s = b2c_sum_log_scores_ool(s, cur.logit[bj] + tk_lp[kj]);
             }
+            C.cfold[i] = s;
+            C.clast[i] = last;
+            const u64 cph = C.cph[last];
+            const u32 type = static_cast<u32>(cph >> 61);
+            const u32 part_len = C.cmeta[last] & 0xFFFFu;
+            double lm_hw = cur.lm_hw[bl];
+            if ((type == 1 || type == 2) && cur.part_len[bl] > 0) {
+                B2cTextNew tn;
+                b2c_text_extend(P, W.text + cur.text_node[bl], cur.part_hash[bl], cur.part_len[bl], 0, &tn);
+                lm_hw = tn.lm_hw;
+            }
+            double ps = 0.0;
+            if (type == 0) ps = cur.pscore[bl];
+            else if (part_len > 0) ps = b2c_partial_score_of(P, (flags & B2C_FL_PSCORE) != 0, cph & B2C_PH_MASK, part_len);
+            const double sco = b2c_combine_score((flags & B2C_FL_LM) != 0, s, lm_hw, ps, part_len);
+            const u64 key = b2c_f64_key(sco);
+            C.ckey[i] = key;
+            const u32 bkt = b2c_bucket(ref, sco, bscale);
+            b2c_atomic_add_u32(&bcnt[bkt], 1u);
+#if defined(__CUDA_ARCH__)
+            C.cnext[i] = atomicExch(&bhead[bkt], static_cast<u32>(i));
+#else
+            C.cnext[i] = bhead[bkt];
+            bhead[bkt] = static_cast<u32>(i);
+#endif
+            if (key > tmax) tmax = key;
         }
-        C.cfold[i] = s;
-        C.clast[i] = last;
-        const bool forced = P.is_bpe && (W.tk_fall[kl] || W.tk_ffirst[kl] == bl);
-        B2cExp e;
-        b2c_expand(P, cur, bl, tk_id[kl], forced, t, e);
-        double lm_hw = cur.lm_hw[bl];
-        if (e.word_len > 0) {
-            B2cTextNew tn;
-            b2c_text_extend(P, W.text[cur.text_node[bl]], e.word_hash, e.word_len, false, tn);
-            lm_hw = tn.lm_hw;
-        }
-        double ps = 0.0;
-        if (e.type == 0) ps = cur.pscore[bl];
-        else if (e.part_len > 0) ps = b2c_partial_score(P, e.part_hash, e.part_len);
-        const u64 key = b2c_f64_key(b2c_combine_score(P, s, lm_hw, ps, e.part_len));
-        C.ckey[i] = key;
-        b2c_atomic_max_u64(&sc->max_key, key);
+        b2c_block_max_u64(tmax, &sc->max_key);
     }
     B2C_SYNC();
     B2C_MARK(2);
 
-    // ---- phase 3: score threshold (decoder.py:545-546) + monotone score buckets ------------
+    // ---- phase C: threshold (decoder.py:545-546), stable top-N (decoder.py:548): rank = bucket
+    //      prefix + exact order inside the bucket; history keys of the selected go to the prune table
+    b2c_bucket_scan_warp(bcnt, bpre);
     const double max_score = b2c_key_f64(sc->max_key);
     const double thr = max_score + P.prune_logp;
-    const double bscale = P.bucket_scale;
-    B2C_FOR(i, M) {
-        const u64 key = C.ckey[i];
-        if (key == 0) continue;
-        const double sco = b2c_key_f64(key);
-        if (sco >= thr) {
-            const u32 b = b2c_bucket(max_score, sco, bscale);
-            b2c_atomic_add_u32(&bcnt[b], 1u);
-#if defined(__CUDA_ARCH__)
-            C.cnext[i] = atomicExch(&bhead[b], static_cast<u32>(i));
-#else
-            C.cnext[i] = bhead[b];
-            bhead[b] = static_cast<u32>(i);
-#endif
-        } else {
-            C.ckey[i] = 0;
+    const u32 width = static_cast<u32>(P.beam_width);
+    {
+        u32 my_sel = 0;
+        B2C_FOR(i, M) {
+            const u64 key = C.ckey[i];
+            if (key == 0) continue;
+            const double sco = b2c_key_f64(key);
+            if (!(sco >= thr)) continue;
+            const u32 bkt = b2c_bucket(ref, sco, bscale);
+            u32 rank = bpre[bkt];
+            for (u32 j = bhead[bkt]; j != B2C_NONE_U32; j = C.cnext[j]) {
+                if (j == static_cast<u32>(i)) continue;
+                const u64 kj = C.ckey[j];
+                rank += (kj > key || (kj == key && j < static_cast<u32>(i))) ? 1u : 0u;
+            }
+            if (rank >= width) continue;
+            ord[rank] = static_cast<u32>(i);
+            ++my_sel;
+            if (prune) {
+                const u32 last = C.clast[i];
+                u32 kl, bl;
+                b2c_divmod(last, n, rcp_n, kl, bl);
+                const u64 cph = C.cph[last];
+                const u32 type = static_cast<u32>(cph >> 61);
+                const u32 meta = C.cmeta[last];
+                u64 hh = cur.hist_hash[bl];
+                if ((type == 1 || type == 2) && cur.part_len[bl] > 0)
+                    hh = b2c_hist_extend(W.text + cur.text_node[bl], P.hist_n, cur.part_hash[bl]);
+                const u64 hk = b2c_beam_key(hh, cph & B2C_PH_MASK, meta & 0xFFFFu, meta >> 16);
+                phk[rank] = hk;
+                b2c_fence_block();
+                u32 slot = static_cast<u32>(b2c_mix64(hk)) & ptmask;
+                while (true) {
+                    const u32 rep = b2c_atomic_cas_u32(&pt_idx[slot], B2C_NONE_U32, rank);
+                    if (rep == B2C_NONE_U32) break;
+                    b2c_fence_block();
+                    if (phk[rep] == hk) break;
+                    slot = (slot + 1) & ptmask;
+                }
+                pslot[rank] = slot;
+                b2c_atomic_min_u32(&pt_min[slot], rank);
+            }
         }
+        b2c_block_add_u32(my_sel, &sc->n_sel);
     }
     B2C_SYNC();
     B2C_MARK(3);
-    b2c_bucket_scan(bcnt, &sc->n_surv);
-    B2C_SYNC();
-    B2C_MARK(4);
 
-    // ---- phase 4: stable top-N (decoder.py:548): rank = bucket prefix + exact order inside the
-    //      bucket; the history-prune key of every selected candidate goes into the prune table ----
-    const u32 m = sc->n_surv;
-    const u32 nsel = m < static_cast<u32>(P.beam_width) ? m : static_cast<u32>(P.beam_width);
-    B2C_FOR(i, M) {
-        const u64 key = C.ckey[i];
-        if (key == 0) continue;
-        const u32 b = b2c_bucket(max_score, b2c_key_f64(key), bscale);
-        u32 rank = bcnt[b];
-        for (u32 j = bhead[b]; j != B2C_NONE_U32; j = C.cnext[j]) {
-            if (j == static_cast<u32>(i)) continue;
-            const u64 kj = C.ckey[j];
-            rank += (kj > key || (kj == key && j < static_cast<u32>(i))) ? 1u : 0u;
-        }
-        if (rank >= nsel) continue;
-        ord[rank] = static_cast<u32>(i);
-        if (P.prune_history) {
-            const u32 last = C.clast[i];
-            u32 k, bl;
-            b2c_divmod(last, n, rcp_n, k, bl);
-            const bool forced = P.is_bpe && (W.tk_fall[k] || W.tk_ffirst[k] == bl);
-            B2cExp e;
-            b2c_expand(P, cur, bl, tk_id[k], forced, t, e);
-            u64 hh = cur.hist_hash[bl];
-            if (e.word_len > 0) {
-                const B2cText& par = W.text[cur.text_node[bl]];
-                const u32 keep = (par.n_win + 1 < static_cast<u32>(P.hist_n)) ? par.n_win : static_cast<u32>(P.hist_n) - 1;
-                hh = B2C_HIST_SEED;
-                for (int w = static_cast<int>(keep) - 1; w >= 0; --w) hh = b2c_hist_fold(hh, par.win[w]);
-                hh = b2c_hist_fold(hh, e.word_hash);
-            }
-            const u64 hk = b2c_beam_key(hh, e.part_hash, e.part_len, e.canon);
-            phk[rank] = hk;
-            b2c_fence_block();
-            u32 slot = static_cast<u32>(b2c_mix64(hk)) & ptmask;
-            while (true) {
-                const u32 rep = b2c_atomic_cas_u32(&pt_idx[slot], B2C_NONE_U32, rank);
-                if (rep == B2C_NONE_U32) break;
-                b2c_fence_block();
-                if (phk[rep] == hk) break;
-                slot = (slot + 1) & ptmask;
-            }
-            pslot[rank] = slot;
-            b2c_atomic_min_u32(&pt_min[slot], rank);
+    // ---- phase D: history prune (decoder.py:550-552) = keep the best rank of every key; every warp
+    //      compacts the kept ranks redundantly and commits the blocks of 32 ranks it owns ----------
+    const u32 nsel = sc->n_sel;
+    u32 n_new = 0;
+#if defined(__CUDA_ARCH__)
+    {
+        const u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        const u32 lt = (1u << lane) - 1u;
+        for (u32 blk = 0; blk * 32 < nsel; ++blk) {
+            const u32 r = blk * 32 + lane;
+            const bool kept = r < nsel && (!prune || pt_min[pslot[r]] == r);
+            const u32 mask = __ballot_sync(0xFFFFFFFFu, kept);
+            if (kept && (blk % nw) == w) b2c_commit_one(P, W, C, cur, nx, tk_id, n, rcp_n, t, n_new + __popc(mask & lt), r, flags);
+            n_new += __popc(mask);
         }
     }
-    B2C_SYNC();
-    B2C_MARK(5);
-
-    // ---- phase 5: history prune (decoder.py:550-552): keep the best rank of every key -------
-    u32 n_new = nsel;
-    if (P.prune_history) {
-        b2c_compact_kept(pslot, pt_min, newidx, &sc->n_new, nsel);
-        B2C_SYNC();
-        B2C_MARK(6);
-        n_new = sc->n_new;
+#else
+    for (u32 r = 0; r < nsel; ++r) {
+        const bool kept = !prune || pt_min[pslot[r]] == r;
+        if (kept) b2c_commit_one(P, W, C, cur, nx, tk_id, n, rcp_n, t, n_new++, r, flags);
     }
-
-    // ---- phase 6: commit the surviving beams; clear the tables for the next frame ------------
-    B2C_FOR(j, n_new) {
-        const u32 r = P.prune_history ? newidx[j] : static_cast<u32>(j);
-        const u32 i = ord[r];
-        const u32 last = C.clast[i];
-        u32 k, bl;
-        b2c_divmod(last, n, rcp_n, k, bl);
-        const bool forced = P.is_bpe && (W.tk_fall[k] || W.tk_ffirst[k] == bl);
-        B2cExp e;
-        b2c_expand(P, cur, bl, tk_id[k], forced, t, e);
-        nx.logit[j] = C.cfold[i];
-        nx.text_hash[j] = e.text_hash;
-        nx.part_hash[j] = e.part_hash;
-        nx.part_len[j] = static_cast<u16>(e.part_len);
-        nx.last_tok[j] = static_cast<u16>(e.canon);
-        nx.pf_s[j] = e.pf_s;
-        nx.pf_e[j] = e.pf_e;
-        // backtrack chain
-        u32 chain = cur.chain[bl];
-        if (e.type != 0) {
-            const u32 id = b2c_atomic_add_u32(&sc->chain_used, 1u);
-            if (id < W.chain_cap) {
-                B2cChain c;
-                c.parent = chain;
-                c.tok = static_cast<u16>(tk_id[k]);
-                c.kind = e.type == 3 ? B2C_CK_CONT : (e.type == 2 ? B2C_CK_SPACE : B2C_CK_BPE);
-                c.has_word = e.word_len > 0 ? 1 : 0;
-                c.ws = cur.pf_s[bl];
-                c.we = cur.pf_e[bl];
-                W.chain[id] = c;
-                chain = id;
-            } else {
-                b2c_atomic_or_u32(&sc->status, B2C_ERR_CHAIN_FULL);
-            }
-        }
-        nx.chain[j] = chain;
-        // text level
-        u32 tnode = cur.text_node[bl];
-        double lm_hw = cur.lm_hw[bl];
-        u64 hh = cur.hist_hash[bl];
-        if (e.word_len > 0) {
-            const B2cText& par = W.text[tnode];
-            B2cTextNew tn;
-            b2c_text_extend(P, par, e.word_hash, e.word_len, false, tn);
-            lm_hw = tn.lm_hw;
-            const u32 id = b2c_atomic_add_u32(&sc->text_used, 1u);
-            if (id < W.text_cap) {
-                B2cText nt;
-                const u32 keep = (par.n_win + 1 < static_cast<u32>(P.hist_n)) ? par.n_win : static_cast<u32>(P.hist_n) - 1;
-                nt.win[0] = e.word_hash;
-                for (u32 w = 0; w < keep; ++w) nt.win[w + 1] = par.win[w];
-                for (u32 w = keep + 1; w < B2C_MAX_HIST; ++w) nt.win[w] = 0;
-                nt.n_win = keep + 1;
-                hh = B2C_HIST_SEED;
-                for (int w = static_cast<int>(nt.n_win) - 1; w >= 0; --w) hh = b2c_hist_fold(hh, nt.win[w]);
-                nt.hist_hash = hh;
-                nt.raw_lm = tn.raw_lm;
-                nt.st = tn.st;
-                nt.hw_count = tn.hw_count;
-                W.text[id] = nt;
-                tnode = id;
-            } else {
-                b2c_atomic_or_u32(&sc->status, B2C_ERR_TEXT_FULL);
-            }
-        }
-        nx.text_node[j] = tnode;
-        nx.lm_hw[j] = lm_hw;
-        nx.hist_hash[j] = hh;
-        double ps = 0.0;
-        if (e.type == 0) ps = cur.pscore[bl];
-        else if (e.part_len > 0) ps = b2c_partial_score(P, e.part_hash, e.part_len);
-        nx.pscore[j] = ps;
-    }
+#endif
     {
         const u32 M_next = n_new * static_cast<u32>(K_next);
         const B2cCandTier Cn = kFast ? W.tier_s : b2c_pick_tier(W, M_next);
@@ -597,16 +669,16 @@ B2C_HD void b2c_frame_step(const B2cParams& P, B2cWork& W, int t, const u16* tk_
         if (Hn > Cn.ht_cap) Hn = Cn.ht_cap;
         b2c_clear_tables(W, Cn, Hn);
     }
-    B2C_LEADER { sc->n_beams = n_new; }
+    B2C_LEADER { sc->n_beams = n_new; sc->prev_max = max_score; }
     B2C_SYNC();
-    B2C_MARK(7);
+    B2C_MARK(4);
     b2c_swap_tabs(W.cur, W.nxt);
 }
 
 // -----------------------------------------------------------------------------------------
 // start of an utterance: EMPTY_START_BEAM (decoder.py:130,628) and the root text node
 // -----------------------------------------------------------------------------------------
-B2C_HD void b2c_utt_begin(const B2cParams& P, B2cWork& W, const B2cLmState* start_state, int K_first) {
+B2C_HDN void b2c_utt_begin(B2cParams P, B2cWork W, const B2cLmState* start_state, int K_first) {
     {
         const u32 M0 = static_cast<u32>(K_first > 0 ? K_first : 1);
         const B2cCandTier C0 = b2c_pick_tier(W, M0);
@@ -619,6 +691,13 @@ B2C_HD void b2c_utt_begin(const B2cParams& P, B2cWork& W, const B2cLmState* star
         sc->text_used = 1;
         sc->status = B2C_OK;
         sc->force_break = 0;
+        sc->prev_max = 0.0;
+        u32 fl = 0;
+        if (P.is_bpe) fl |= B2C_FL_BPE;
+        if (P.prune_history) fl |= B2C_FL_PRUNE;
+        if (P.lm.order > 0) fl |= B2C_FL_LM;
+        if (P.n_hot > 0 || P.lm.order > 0) fl |= B2C_FL_PSCORE;
+        sc->flags = fl;
         B2cText root;
         for (int w = 0; w < B2C_MAX_HIST; ++w) { root.win[w] = 0; root.st.words[w] = 0; root.st.backoff[w] = 0.0f; }
         root.n_win = 0;
@@ -654,7 +733,8 @@ B2C_HD void b2c_utt_begin(const B2cParams& P, B2cWork& W, const B2cLmState* star
 }
 
 // -----------------------------------------------------------------------------------------
-// _finalize_beams(force_next_word=True, is_end=True) + output (decoder.py:558-667)
+// _finalize_beams(force_next_word=True, is_end=True) + output (decoder.py:558-667); once per
+// utterance, out of line
 // -----------------------------------------------------------------------------------------
 struct B2cOut {              // per-utterance output views (HBM)
     int* n_beams;            // [1]
@@ -668,8 +748,8 @@ struct B2cOut {              // per-utterance output views (HBM)
     u32 stride;              // T + 1
 };
 
-B2C_HD void b2c_finalize(const B2cParams& P, B2cWork& W, const B2cOut& O) {
-    // on entry the grouping table is clear for ht_size(n_beams) slots (last commit / utt_begin)
+B2C_HDN void b2c_finalize(B2cParams P, B2cWork W, B2cOut O) {
+    // on entry the grouping table is clear for ht_size(n_beams) slots (last phase D / utt_begin)
     B2cScalars* sc = W.sc;
     const u32 n = sc->n_beams;
     const B2cCandTier C = b2c_pick_tier(W, n);
@@ -682,7 +762,7 @@ B2C_HD void b2c_finalize(const B2cParams& P, B2cWork& W, const B2cOut& O) {
         b2c_fence_block();
         b2c_group_insert(C, hmask, static_cast<u32>(b), key);
     }
-    B2C_LEADER { sc->max_key = 0; sc->n_surv = 0; }
+    B2C_LEADER { sc->max_key = 0; sc->n_sel = 0; }
     B2C_SYNC();
     B2C_FOR(b, n) {
         const u32 slot = C.cslot[b];
@@ -698,12 +778,12 @@ B2C_HD void b2c_finalize(const B2cParams& P, B2cWork& W, const B2cOut& O) {
         double lm_hw;
         if (P.lm.order > 0 || cur.part_len[last] > 0) {
             B2cTextNew tn;
-            b2c_text_extend(P, W.text[cur.text_node[last]], cur.part_hash[last], cur.part_len[last], true, tn);
+            b2c_text_extend(P, W.text + cur.text_node[last], cur.part_hash[last], cur.part_len[last], 1, &tn);
             lm_hw = tn.lm_hw;
         } else {
             lm_hw = cur.lm_hw[last];
         }
-        const u64 key = b2c_f64_key(b2c_combine_score(P, s, lm_hw, 0.0, 0));
+        const u64 key = b2c_f64_key(b2c_combine_score(P.lm.order > 0, s, lm_hw, 0.0, 0));
         C.ckey[b] = key;
         b2c_atomic_max_u64(&sc->max_key, key);
     }
@@ -712,12 +792,12 @@ B2C_HD void b2c_finalize(const B2cParams& P, B2cWork& W, const B2cOut& O) {
     B2C_FOR(b, n) {
         const u64 key = C.ckey[b];
         if (key == 0) continue;
-        if (b2c_key_f64(key) >= thr) b2c_atomic_add_u32(&sc->n_surv, 1u);
+        if (b2c_key_f64(key) >= thr) b2c_atomic_add_u32(&sc->n_sel, 1u);
         else C.ckey[b] = 0;
     }
     B2C_SYNC();
-    // once per utterance: plain counting rank over the <= beam_width survivors
-    const u32 m = sc->n_surv;
+    // once per utterance: plain counting rank over the survivors
+    const u32 m = sc->n_sel;
     const u32 nsel = m < static_cast<u32>(P.beam_width) ? m : static_cast<u32>(P.beam_width);
     B2C_FOR(b, n) {
         const u64 key = C.ckey[b];
@@ -725,7 +805,7 @@ B2C_HD void b2c_finalize(const B2cParams& P, B2cWork& W, const B2cOut& O) {
         u32 rank = 0;
         for (u32 j = 0; j < n; ++j) {
             const u64 kj = C.ckey[j];
-            rank += (kj > key || (kj == key && kj != 0 && j < static_cast<u32>(b))) ? 1u : 0u;
+            rank += (kj > key || (kj == key && j < static_cast<u32>(b))) ? 1u : 0u;
         }
         if (rank < nsel) W.ord[rank] = static_cast<u32>(b);
     }
@@ -743,7 +823,7 @@ B2C_HD void b2c_finalize(const B2cParams& P, B2cWork& W, const B2cOut& O) {
         for (int w = 0; w < B2C_MAX_HIST; ++w) { st.words[w] = 0; st.backoff[w] = 0.0f; }
         if (P.lm.order > 0) {
             B2cTextNew tn;
-            b2c_text_extend(P, W.text[cur.text_node[last]], cur.part_hash[last], cur.part_len[last], true, tn);
+            b2c_text_extend(P, W.text + cur.text_node[last], cur.part_hash[last], cur.part_len[last], 1, &tn);
             st = tn.st;
         }
         O.states[r] = st;
@@ -769,5 +849,6 @@ B2C_HD void b2c_finalize(const B2cParams& P, B2cWork& W, const B2cOut& O) {
         O.n_tok[r] = static_cast<int>(nt);
         O.n_words[r] = static_cast<int>(nw);
     }
+    // leave the tables clear for the next utterance handled by this CTA (utt_begin clears again)
     B2C_SYNC();
 }
