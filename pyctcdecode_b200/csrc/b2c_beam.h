@@ -309,8 +309,9 @@ B2C_HD void b2c_group_insert(const B2cCandTier& C, u32 hmask, u32 i, u64 key) {
     b2c_atomic_add_u32(&C.ht_cnt[slot], 1u);
 }
 
-// clear the grouping table (first H slots), the score buckets and the history-prune table for the
-// next use; called in a phase where none of them is read any more
+// clear the grouping table (first H slots) and the score buckets for the next frame; called in
+// phase D, where neither is read any more.  (The history-prune table IS read in phase D by every
+// warp's compaction loop, so it is cleared in phase A of the next frame instead.)
 B2C_HD void b2c_clear_tables(const B2cWork& W, const B2cCandTier& C, u32 H) {
     B2C_FOR(s, H) {
         C.ht_idx[s] = B2C_NONE_U32;
@@ -319,7 +320,6 @@ B2C_HD void b2c_clear_tables(const B2cWork& W, const B2cCandTier& C, u32 H) {
         C.ht_cnt[s] = 0;
     }
     B2C_FOR(s, B2C_NBUCKET) { W.bcnt[s] = 0; W.bhead[s] = B2C_NONE_U32; }
-    B2C_FOR(s, W.pt_cap) { W.pt_idx[s] = B2C_NONE_U32; W.pt_min[s] = B2C_NONE_U32; }
 }
 
 // i -> (i / n, i % n) without an integer division (float reciprocal + exact correction)
@@ -504,6 +504,7 @@ B2C_HD void b2c_frame_step(const B2cParams& P, B2cWork& W, int t, const u16* tk_
     if (is_bpe) b2c_bpe_force(P.toks, tk_id, K, cur.last_tok, n, W.tk_ffirst, W.tk_fall, &sc->force_break);
 
     // ---- phase A: expand once, cache, merge key, grouping (publish key, fence, claim slot) -----
+    if (prune) { B2C_FOR(s, W.pt_cap) { pt_idx[s] = B2C_NONE_U32; pt_min[s] = B2C_NONE_U32; } }
     B2C_FOR(i, M) {
         u32 k, b;
         b2c_divmod(static_cast<u32>(i), n, rcp_n, k, b);
