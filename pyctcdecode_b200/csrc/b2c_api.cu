@@ -46,63 +46,10 @@ static int fail(int code, const std::string& msg) {
 // workspace layout (shared memory + per-slot HBM workspace), computed on the host and
 // interpreted by the kernel
 // =========================================================================================
-struct B2cLayout {
-    int W;                      // beam_width (capacity of the beam tables)
-    u32 cap_s, ht_s;            // shared-memory candidate tier
-    u32 cap_g, ht_g;            // HBM candidate tier (0: absent)
-    int beams_in_smem;
-    u32 chain_cap, text_cap;
-    int V;
-    u32 smem_bytes;
-    u64 gws_bytes;              // per slot
-    // offsets
-    u32 s_sc, s_tab[2], s_sel, s_tier;
-    u64 g_tab[2], g_sel, g_tier, g_tk, g_chain, g_text;
-};
-
 static inline u64 al16(u64 x) { return (x + 15) & ~15ull; }
 static inline u64 tab_bytes(int W) { return 6 * al16(8ull * W) + 4 * al16(4ull * W) + 2 * al16(2ull * W) + 64; }
-B2C_HD u32 pt_cap_for(int W) { u32 p = 16; while (p < 2u * static_cast<u32>(W)) p <<= 1; return p; }
 static inline u64 sel_bytes(int W) { return al16(8ull * W) + 2 * al16(4ull * W) + 2 * al16(4ull * pt_cap_for(W)) + (2 + B2C_MAXWARPS) * al16(4ull * B2C_NBUCKET) + 64; }
 static inline u64 tier_bytes(u32 cap, u32 ht) { return al16(8ull * cap) * 4 + al16(4ull * cap) * 4 + al16(4ull * ht) * 4 + 64; }
-
-B2C_HD u8* b2c_carve(u8*& p, u64 bytes) {
-    u8* r = p;
-    p += (bytes + 15) & ~15ull;
-    return r;
-}
-B2C_HD void b2c_carve_tab(u8* base, int W, B2cBeamTab& t) {
-    u8* p = base;
-    t.logit = reinterpret_cast<double*>(b2c_carve(p, 8ull * W));
-    t.lm_hw = reinterpret_cast<double*>(b2c_carve(p, 8ull * W));
-    t.pscore = reinterpret_cast<double*>(b2c_carve(p, 8ull * W));
-    t.text_hash = reinterpret_cast<u64*>(b2c_carve(p, 8ull * W));
-    t.part_hash = reinterpret_cast<u64*>(b2c_carve(p, 8ull * W));
-    t.hist_hash = reinterpret_cast<u64*>(b2c_carve(p, 8ull * W));
-    t.text_node = reinterpret_cast<u32*>(b2c_carve(p, 4ull * W));
-    t.chain = reinterpret_cast<u32*>(b2c_carve(p, 4ull * W));
-    t.pf_s = reinterpret_cast<int*>(b2c_carve(p, 4ull * W));
-    t.pf_e = reinterpret_cast<int*>(b2c_carve(p, 4ull * W));
-    t.last_tok = reinterpret_cast<u16*>(b2c_carve(p, 2ull * W));
-    t.part_len = reinterpret_cast<u16*>(b2c_carve(p, 2ull * W));
-}
-B2C_HD void b2c_carve_tier(u8* base, u32 cap, u32 ht, B2cCandTier& c) {
-    u8* p = base;
-    c.cap = cap;
-    c.ht_cap = ht;
-    c.ckey = reinterpret_cast<u64*>(b2c_carve(p, 8ull * cap));
-    c.cfold = reinterpret_cast<double*>(b2c_carve(p, 8ull * cap));
-    c.cth = reinterpret_cast<u64*>(b2c_carve(p, 8ull * cap));
-    c.cph = reinterpret_cast<u64*>(b2c_carve(p, 8ull * cap));
-    c.cmeta = reinterpret_cast<u32*>(b2c_carve(p, 4ull * cap));
-    c.cslot = reinterpret_cast<u32*>(b2c_carve(p, 4ull * cap));
-    c.cnext = reinterpret_cast<u32*>(b2c_carve(p, 4ull * cap));
-    c.clast = reinterpret_cast<u32*>(b2c_carve(p, 4ull * cap));
-    c.ht_idx = reinterpret_cast<u32*>(b2c_carve(p, 4ull * ht));
-    c.ht_min = reinterpret_cast<u32*>(b2c_carve(p, 4ull * ht));
-    c.ht_max = reinterpret_cast<u32*>(b2c_carve(p, 4ull * ht));
-    c.ht_cnt = reinterpret_cast<u32*>(b2c_carve(p, 4ull * ht));
-}
 
 static u32 pow2_ge(u32 x) {
     u32 p = 16;
@@ -114,7 +61,7 @@ static u32 pow2_ge(u32 x) {
 // HBM tier, beam tables in shared memory (the caller checks smem_bytes against the budget).
 // cap_request == 0: general layout -- what fits in shared memory plus an HBM tier sized for the
 // worst case beam_width * V.
-static B2cLayout make_layout(int W, int V, int T_max, bool full_caps, u32 smem_budget, u32 cap_request) {
+static B2cLayout make_layout(int W, int V, int T_max, bool full_caps, u32 smem_budget, u32 cap_request, u64 worst_m = 0) {
     B2cLayout L;
     std::memset(&L, 0, sizeof(L));
     L.W = W;
@@ -126,6 +73,10 @@ static B2cLayout make_layout(int W, int V, int T_max, bool full_caps, u32 smem_b
         fixed += 2 * tab_bytes(W);
         L.cap_s = cap_request;
         L.ht_s = pow2_ge(2 * cap_request);
+        if (worst_m > cap_request) {   // rare oversize frames of a fast-class utterance use the HBM tier
+            L.cap_g = static_cast<u32>(std::min<u64>(worst_m, 0x7FFFFFFFull));
+            L.ht_g = pow2_ge(2 * L.cap_g);
+        }
     } else {
         L.beams_in_smem = (fixed + 2 * tab_bytes(W) + tier_bytes(256, 512) <= smem_budget) ? 1 : 0;
         if (L.beams_in_smem) fixed += 2 * tab_bytes(W);
@@ -199,38 +150,8 @@ B2C_HD void b2c_beam_block(const B2cBeamArgs& A, int slot, u8* smem) {
     const B2cLayout& L = A.L;
     u8* g = A.gws + static_cast<u64>(slot) * L.gws_bytes;
     B2cWork W;
-    W.sc = reinterpret_cast<B2cScalars*>(smem + L.s_sc);
-    if (kFast || L.beams_in_smem) {
-        b2c_carve_tab(smem + L.s_tab[0], L.W, W.cur);
-        b2c_carve_tab(smem + L.s_tab[1], L.W, W.nxt);
-    } else {
-        b2c_carve_tab(g + L.g_tab[0], L.W, W.cur);
-        b2c_carve_tab(g + L.g_tab[1], L.W, W.nxt);
-    }
-    {
-        u8* p = smem + L.s_sel;
-        W.phk = reinterpret_cast<u64*>(b2c_carve(p, 8ull * L.W));
-        W.ord = reinterpret_cast<u32*>(b2c_carve(p, 4ull * L.W));
-        W.pslot = reinterpret_cast<u32*>(b2c_carve(p, 4ull * L.W));
-        W.pt_cap = pt_cap_for(L.W);
-        W.pt_idx = reinterpret_cast<u32*>(b2c_carve(p, 4ull * W.pt_cap));
-        W.pt_min = reinterpret_cast<u32*>(b2c_carve(p, 4ull * W.pt_cap));
-        W.bcnt = reinterpret_cast<u32*>(b2c_carve(p, 4ull * B2C_NBUCKET));
-        W.bhead = reinterpret_cast<u32*>(b2c_carve(p, 4ull * B2C_NBUCKET));
-        W.bpre = reinterpret_cast<u32*>(b2c_carve(p, 4ull * B2C_NBUCKET * B2C_MAXWARPS));
-    }
-    b2c_carve_tier(smem + L.s_tier, L.cap_s, L.ht_s, W.tier_s);
-    if (!kFast && L.cap_g) b2c_carve_tier(g + L.g_tier, L.cap_g, L.ht_g, W.tier_g);
-    else W.tier_g = W.tier_s;
-    {
-        u8* p = g + L.g_tk;
-        W.tk_ffirst = reinterpret_cast<u32*>(b2c_carve(p, 4ull * L.V));
-        W.tk_fall = reinterpret_cast<u8*>(b2c_carve(p, static_cast<u64>(L.V)));
-    }
-    W.chain = reinterpret_cast<B2cChain*>(g + L.g_chain);
-    W.chain_cap = L.chain_cap;
-    W.text = reinterpret_cast<B2cText*>(g + L.g_text);
-    W.text_cap = L.text_cap;
+    b2c_make_work(L, smem, g, 0, kFast || L.beams_in_smem, W);
+    int parity = 0;      // which beam table is current (the out-of-line step rebuilds its descriptor from it)
     u32* s_cur = reinterpret_cast<u32*>(smem + L.s_sc + 56);  // queue ticket of this CTA
 #if defined(B2C_PHASE_CLOCKS) && defined(__CUDA_ARCH__)
     for (int q = 0; q < 16; ++q) W.clk[q] = 0;
@@ -260,7 +181,13 @@ B2C_HD void b2c_beam_block(const B2cBeamArgs& A, int slot, u8* smem) {
             nxt.cnt = 1;
             if (t + 1 < Tn) nxt = recs[t + 1];      // one frame ahead: hides the load latency
             const u64 base = (f0 + static_cast<u64>(t & ~(B2C_RUN - 1))) * static_cast<u64>(A.P.V) + rec.off;
-            b2c_frame_step<kFast>(A.P, W, t, A.tok_ids + base, A.tok_lp + base, static_cast<int>(rec.cnt), static_cast<int>(nxt.cnt));
+            if (kFast && W.sc->n_beams * rec.cnt > L.cap_s) {
+                b2c_frame_step_slow(A.P, L, smem, g, parity, t, A.tok_ids + base, A.tok_lp + base, static_cast<int>(rec.cnt), static_cast<int>(nxt.cnt));
+                b2c_swap_tabs(W.cur, W.nxt);   // the out-of-line step swapped its private descriptor
+            } else {
+                b2c_frame_step<kFast>(A.P, W, t, A.tok_ids + base, A.tok_lp + base, static_cast<int>(rec.cnt), static_cast<int>(nxt.cnt));
+            }
+            parity ^= 1;
             rec = nxt;
         }
         B2cOut O;
@@ -365,9 +292,9 @@ struct b2c_decoder {
     int score_boundary = 1;
     int n_sm = 1;
     size_t smem_optin = 48 * 1024;
-    DevBuf d_clk, d_maxk, d_toks, d_logits, d_meta, d_tok_start, d_tok_ids, d_tok_lp, d_rowsum, d_set, d_isprob, d_ws, d_hot, d_states,
+    DevBuf d_sumk, d_clk, d_maxk, d_toks, d_logits, d_meta, d_tok_start, d_tok_ids, d_tok_lp, d_rowsum, d_set, d_isprob, d_ws, d_hot, d_states,
         d_out_small, d_out_toks, d_out_frames;
-    PinBuf h_maxk, h_meta, h_out_small, h_out_toks, h_out_frames;
+    PinBuf h_sumk, h_maxk, h_meta, h_out_small, h_out_toks, h_out_frames;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaStream_t cls_stream[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // one per capacity class
     cudaEvent_t cls_done[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -704,10 +631,10 @@ void b2c_decoder_destroy(b2c_decoder_t* d) {
     if (!d) return;
     cudaSetDevice(d->device);
     if (d->stream) cudaStreamSynchronize(d->stream);
-    DevBuf* bufs[] = {&d->d_clk, &d->d_maxk, &d->d_toks, &d->d_logits, &d->d_meta, &d->d_tok_start, &d->d_tok_ids, &d->d_tok_lp, &d->d_rowsum, &d->d_set,
+    DevBuf* bufs[] = {&d->d_sumk, &d->d_clk, &d->d_maxk, &d->d_toks, &d->d_logits, &d->d_meta, &d->d_tok_start, &d->d_tok_ids, &d->d_tok_lp, &d->d_rowsum, &d->d_set,
                       &d->d_isprob, &d->d_ws, &d->d_hot, &d->d_states, &d->d_out_small, &d->d_out_toks, &d->d_out_frames};
     for (DevBuf* b : bufs) b->release();
-    PinBuf* pins[] = {&d->h_maxk, &d->h_meta, &d->h_out_small, &d->h_out_toks, &d->h_out_frames};
+    PinBuf* pins[] = {&d->h_sumk, &d->h_maxk, &d->h_meta, &d->h_out_small, &d->h_out_toks, &d->h_out_frames};
     for (PinBuf* b : pins) b->release();
     for (int i = 0; i < 6; ++i) if (d->ev[i]) cudaEventDestroy(d->ev[i]);
     for (int i = 0; i < 5; ++i) {
@@ -826,7 +753,9 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     if (V > 32) {
         if (d->d_set.ensure(2ull * set_cap * 2 * B2C_PREP_WARPS * grid_tok)) return B2C_E_NOMEM;
     }
-    if (d->d_maxk.ensure(4ull * n_utts) || d->h_maxk.ensure(4ull * n_utts)) return B2C_E_NOMEM;
+    if (d->d_maxk.ensure(4ull * n_utts) || d->h_maxk.ensure(4ull * n_utts) || d->d_sumk.ensure(4ull * n_utts) ||
+        d->h_sumk.ensure(4ull * n_utts))
+        return B2C_E_NOMEM;
     const u32 smem_budget = static_cast<u32>(std::min<size_t>(d->smem_optin, 200 * 1024));
     // outputs
     const u64 off_nb = 0, off_st = al16(4ull * n_utts), off_sc = off_st + al16(4ull * n_utts),
@@ -912,7 +841,9 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     PA.set_cap = set_cap;
     PA.is_prob = d->d_isprob.as<int>();
     PA.max_k = d->d_maxk.as<u32>();
+    PA.sum_k = d->d_sumk.as<u32>();
     CUDA_OK(cudaMemsetAsync(d->d_maxk.p, 0, 4ull * n_utts, st));
+    CUDA_OK(cudaMemsetAsync(d->d_sumk.p, 0, 4ull * n_utts, st));
     CUDA_OK(cudaEventRecord(d->ev[1], st));
     int rc = dtype == B2C_DTYPE_F32 ? launch_prepare<float>(d, PA, n_utts, grid_rows, grid_tok)
                                     : launch_prepare<double>(d, PA, n_utts, grid_rows, grid_tok);
@@ -922,11 +853,14 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
 
     // ---- size the beam kernel from the token statistics of this batch ---------------------------
     CUDA_OK(cudaMemcpyAsync(d->h_maxk.p, d->d_maxk.p, 4ull * n_utts, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(d->h_sumk.p, d->d_sumk.p, 4ull * n_utts, cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaStreamSynchronize(st));
     const u32* h_maxk = d->h_maxk.as<u32>();
-    // capacity classes of the shared-memory candidate tier: an utterance whose worst frame can
-    // produce beam_width * max_k candidates goes to the smallest class that holds them, or to the
-    // general kernel (HBM tier) when no class fits into shared memory
+    const u32* h_sumk = d->h_sumk.as<u32>();
+    // capacity classes of the shared-memory candidate tier, sized for the TYPICAL frame of the
+    // utterance (2.5 x its mean tokens per frame, at least 4): the few wider frames of such an
+    // utterance take the out-of-line HBM-tier step inside the same kernel.  Utterances whose typical
+    // frame does not fit any class go to the general kernel.
     static const u32 kCaps[4] = {512, 1024, 2048, 4096};
     bool cap_ok[4];
     for (int c = 0; c < 4; ++c)
@@ -934,7 +868,9 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     std::vector<std::vector<int>> classes(5);   // 0..3 fast classes, 4 general
     for (int q = 0; q < n_utts; ++q) {
         const int u = order[q];                 // keeps longest-first order inside every class
-        const u64 need = std::min<u64>(static_cast<u64>(opts->beam_width) * std::max<u32>(h_maxk[u], 1u),
+        const double mean_k = T[u] > 0 ? static_cast<double>(h_sumk[u]) / T[u] : 1.0;
+        const u32 typ_k = std::min<u32>(std::max<u32>(h_maxk[u], 1u), std::max<u32>(4u, static_cast<u32>(std::ceil(2.5 * mean_k))));
+        const u64 need = std::min<u64>(static_cast<u64>(opts->beam_width) * typ_k,
                                        static_cast<u64>(opts->beam_width) * static_cast<u64>(V));
         int cls = 4;
         for (int c = 0; c < 4; ++c)
@@ -972,8 +908,13 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
         ln.ord_off = ord_off;
         ln.count = static_cast<int>(utts.size());
         int tmax = 1;
-        for (int u : utts) tmax = std::max(tmax, static_cast<int>(T[u]));
-        ln.L = make_layout(opts->beam_width, V, tmax, full, smem_budget, cls < 4 ? kCaps[cls] : 0);
+        u32 kmax = 1;
+        for (int u : utts) {
+            tmax = std::max(tmax, static_cast<int>(T[u]));
+            kmax = std::max(kmax, h_maxk[u]);
+        }
+        const u64 worst_m = static_cast<u64>(opts->beam_width) * std::min<u32>(kmax, static_cast<u32>(V));
+        ln.L = make_layout(opts->beam_width, V, tmax, full, smem_budget, cls < 4 ? kCaps[cls] : 0, worst_m);
         const int by_smem = static_cast<int>(std::max<u64>(1, (220 * 1024) / std::max<u32>(ln.L.smem_bytes + 1024, 2048)));
         const int per_sm = std::min(by_smem, 4);   // ~128 registers x 128 threads -> 4 CTAs per SM
         ln.slots = std::min(ln.count, d->n_sm * per_sm);

@@ -108,6 +108,101 @@ struct B2cWork {
 
 #define B2C_PH_MASK B2C_P61
 
+// ---------------------------------------------------------------------------------------
+// workspace layout (shared memory + per-slot HBM workspace): computed on the host
+// (b2c_api.cu make_layout), interpreted here
+// ---------------------------------------------------------------------------------------
+struct B2cLayout {
+    int W;                      // beam_width (capacity of the beam tables)
+    u32 cap_s, ht_s;            // shared-memory candidate tier
+    u32 cap_g, ht_g;            // HBM candidate tier (0: absent)
+    int beams_in_smem;
+    u32 chain_cap, text_cap;
+    int V;
+    u32 smem_bytes;
+    u64 gws_bytes;              // per slot
+    // offsets
+    u32 s_sc, s_tab[2], s_sel, s_tier;
+    u64 g_tab[2], g_sel, g_tier, g_tk, g_chain, g_text;
+};
+
+B2C_HD u32 pt_cap_for(int W) { u32 p = 16; while (p < 2u * static_cast<u32>(W)) p <<= 1; return p; }
+
+B2C_HD u8* b2c_carve(u8*& p, u64 bytes) {
+    u8* r = p;
+    p += (bytes + 15) & ~15ull;
+    return r;
+}
+B2C_HD void b2c_carve_tab(u8* base, int W, B2cBeamTab& t) {
+    u8* p = base;
+    t.logit = reinterpret_cast<double*>(b2c_carve(p, 8ull * W));
+    t.lm_hw = reinterpret_cast<double*>(b2c_carve(p, 8ull * W));
+    t.pscore = reinterpret_cast<double*>(b2c_carve(p, 8ull * W));
+    t.text_hash = reinterpret_cast<u64*>(b2c_carve(p, 8ull * W));
+    t.part_hash = reinterpret_cast<u64*>(b2c_carve(p, 8ull * W));
+    t.hist_hash = reinterpret_cast<u64*>(b2c_carve(p, 8ull * W));
+    t.text_node = reinterpret_cast<u32*>(b2c_carve(p, 4ull * W));
+    t.chain = reinterpret_cast<u32*>(b2c_carve(p, 4ull * W));
+    t.pf_s = reinterpret_cast<int*>(b2c_carve(p, 4ull * W));
+    t.pf_e = reinterpret_cast<int*>(b2c_carve(p, 4ull * W));
+    t.last_tok = reinterpret_cast<u16*>(b2c_carve(p, 2ull * W));
+    t.part_len = reinterpret_cast<u16*>(b2c_carve(p, 2ull * W));
+}
+B2C_HD void b2c_carve_tier(u8* base, u32 cap, u32 ht, B2cCandTier& c) {
+    u8* p = base;
+    c.cap = cap;
+    c.ht_cap = ht;
+    c.ckey = reinterpret_cast<u64*>(b2c_carve(p, 8ull * cap));
+    c.cfold = reinterpret_cast<double*>(b2c_carve(p, 8ull * cap));
+    c.cth = reinterpret_cast<u64*>(b2c_carve(p, 8ull * cap));
+    c.cph = reinterpret_cast<u64*>(b2c_carve(p, 8ull * cap));
+    c.cmeta = reinterpret_cast<u32*>(b2c_carve(p, 4ull * cap));
+    c.cslot = reinterpret_cast<u32*>(b2c_carve(p, 4ull * cap));
+    c.cnext = reinterpret_cast<u32*>(b2c_carve(p, 4ull * cap));
+    c.clast = reinterpret_cast<u32*>(b2c_carve(p, 4ull * cap));
+    c.ht_idx = reinterpret_cast<u32*>(b2c_carve(p, 4ull * ht));
+    c.ht_min = reinterpret_cast<u32*>(b2c_carve(p, 4ull * ht));
+    c.ht_max = reinterpret_cast<u32*>(b2c_carve(p, 4ull * ht));
+    c.ht_cnt = reinterpret_cast<u32*>(b2c_carve(p, 4ull * ht));
+}
+
+
+// build the work descriptor of one CTA; `parity` says which of the two beam tables is current
+B2C_HD void b2c_make_work(const B2cLayout& L, u8* smem, u8* g, int parity, bool beams_s, B2cWork& W) {
+    W.sc = reinterpret_cast<B2cScalars*>(smem + L.s_sc);
+    if (beams_s) {
+        b2c_carve_tab(smem + L.s_tab[parity], L.W, W.cur);
+        b2c_carve_tab(smem + L.s_tab[parity ^ 1], L.W, W.nxt);
+    } else {
+        b2c_carve_tab(g + L.g_tab[parity], L.W, W.cur);
+        b2c_carve_tab(g + L.g_tab[parity ^ 1], L.W, W.nxt);
+    }
+    {
+        u8* p = smem + L.s_sel;
+        W.phk = reinterpret_cast<u64*>(b2c_carve(p, 8ull * L.W));
+        W.ord = reinterpret_cast<u32*>(b2c_carve(p, 4ull * L.W));
+        W.pslot = reinterpret_cast<u32*>(b2c_carve(p, 4ull * L.W));
+        W.pt_cap = pt_cap_for(L.W);
+        W.pt_idx = reinterpret_cast<u32*>(b2c_carve(p, 4ull * W.pt_cap));
+        W.pt_min = reinterpret_cast<u32*>(b2c_carve(p, 4ull * W.pt_cap));
+        W.bcnt = reinterpret_cast<u32*>(b2c_carve(p, 4ull * B2C_NBUCKET));
+        W.bhead = reinterpret_cast<u32*>(b2c_carve(p, 4ull * B2C_NBUCKET));
+        W.bpre = reinterpret_cast<u32*>(b2c_carve(p, 4ull * B2C_NBUCKET * B2C_MAXWARPS));
+    }
+    b2c_carve_tier(smem + L.s_tier, L.cap_s, L.ht_s, W.tier_s);
+    if (L.cap_g) b2c_carve_tier(g + L.g_tier, L.cap_g, L.ht_g, W.tier_g);
+    else W.tier_g = W.tier_s;
+    {
+        u8* p = g + L.g_tk;
+        W.tk_ffirst = reinterpret_cast<u32*>(b2c_carve(p, 4ull * L.V));
+        W.tk_fall = reinterpret_cast<u8*>(b2c_carve(p, static_cast<u64>(L.V)));
+    }
+    W.chain = reinterpret_cast<B2cChain*>(g + L.g_chain);
+    W.chain_cap = L.chain_cap;
+    W.text = reinterpret_cast<B2cText*>(g + L.g_text);
+    W.text_cap = L.text_cap;
+}
+
 B2C_HD void b2c_swap_tabs(B2cBeamTab& a, B2cBeamTab& b) {
     B2cBeamTab t = a;
     a = b;
@@ -665,7 +760,7 @@ B2C_HD void b2c_frame_step(const B2cParams& P, B2cWork& W, int t, const u16* tk_
 #endif
     {
         const u32 M_next = n_new * static_cast<u32>(K_next);
-        const B2cCandTier Cn = kFast ? W.tier_s : b2c_pick_tier(W, M_next);
+        const B2cCandTier Cn = b2c_pick_tier(W, M_next);   // the next frame may take the other tier
         u32 Hn = b2c_ht_size(M_next);
         if (Hn > Cn.ht_cap) Hn = Cn.ht_cap;
         b2c_clear_tables(W, Cn, Hn);
@@ -674,6 +769,17 @@ B2C_HD void b2c_frame_step(const B2cParams& P, B2cWork& W, int t, const u16* tk_
     B2C_SYNC();
     B2C_MARK(4);
     b2c_swap_tabs(W.cur, W.nxt);
+}
+
+// frames whose candidate count exceeds the shared-memory tier (a few very wide frames per
+// utterance, flat logits) take this out-of-line copy that works on the HBM tier through generic
+// pointers.  It operates on a COPY of the work descriptor so that the hot path's descriptor never
+// has its address taken (which would push it to local memory).
+B2C_HDN void b2c_frame_step_slow(B2cParams P, B2cLayout L, u8* smem, u8* g, int parity, int t, const u16* tk_id,
+                                 const double* tk_lp, int K, int K_next) {
+    B2cWork Wc;
+    b2c_make_work(L, smem, g, parity, true, Wc);
+    b2c_frame_step<false>(P, Wc, t, tk_id, tk_lp, K, K_next);   // the caller swaps its own tables
 }
 
 // -----------------------------------------------------------------------------------------

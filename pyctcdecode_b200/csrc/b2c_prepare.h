@@ -241,6 +241,7 @@ struct B2cPrepArgs {
     u32 set_cap;             // power of two >= 8 * (V + 1)
     int* is_prob;            // [B]
     u32* max_k;              // [B] largest per-frame token count (zeroed before the launch)
+    u32* sum_k;              // [B] total number of selected tokens (zeroed before the launch)
 };
 
 // ---- rowsum ---------------------------------------------------------------------------------
@@ -489,7 +490,10 @@ B2C_HD void b2c_tokens_run(const B2cPrepArgs& A, u64 run, int lane, u16* set0, u
         __syncwarp();
 #endif
     }
-    if (lane == 0 && mx > 0) b2c_atomic_max_u32(&A.max_k[u], mx);
+    if (lane == 0 && mx > 0) {
+        b2c_atomic_max_u32(&A.max_k[u], mx);
+        b2c_atomic_add_u32(&A.sum_k[u], off);
+    }
 }
 
 template <class T>
