@@ -225,8 +225,9 @@ __global__ void __launch_bounds__(B2C_PREP_THREADS) b2c_tokens_kernel(const B2cP
     __shared__ B2cPrepShared sh;
     b2c_tokens_block<T>(A, static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x), &sh);
 }
-template <bool kFast>
-__global__ void __launch_bounds__(B2C_BEAM_THREADS, kFast ? 4 : 2) b2c_beam_kernel(const B2cBeamArgs A) {
+// kOcc: CTAs per SM the register allocation is bounded for (4: <= 128 registers, 2: <= 255)
+template <bool kFast, int kOcc>
+__global__ void __launch_bounds__(B2C_BEAM_THREADS, kOcc) b2c_beam_kernel(const B2cBeamArgs A) {
     extern __shared__ __align__(16) u8 b2c_smem[];
     b2c_beam_block<kFast>(A, static_cast<int>(blockIdx.x), b2c_smem);
 }
@@ -411,25 +412,28 @@ static int launch_prepare(b2c_decoder* d, const B2cPrepArgs& A, int n_utts, int 
     return 0;
 }
 
-static int launch_beam(b2c_decoder* d, const B2cBeamArgs& A, int slots, bool fast, cudaStream_t stream) {
+static int launch_beam(b2c_decoder* d, const B2cBeamArgs& A, int slots, bool fast, int per_sm, cudaStream_t stream) {
 #ifdef B2C_HOSTSIM
     (void)d;
     (void)stream;
+    (void)per_sm;
     std::vector<u8> smem(A.L.smem_bytes + 64);
     for (int s = 0; s < slots; ++s) {
         if (fast) b2c_beam_block<true>(A, s, smem.data());
         else b2c_beam_block<false>(A, s, smem.data());
     }
 #else
-    if (fast) {
-        if (A.L.smem_bytes > 48 * 1024)
-            CUDA_OK(cudaFuncSetAttribute(b2c_beam_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(A.L.smem_bytes)));
-        b2c_beam_kernel<true><<<slots, B2C_BEAM_THREADS, A.L.smem_bytes, stream>>>(A);
-    } else {
-        if (A.L.smem_bytes > 48 * 1024)
-            CUDA_OK(cudaFuncSetAttribute(b2c_beam_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(A.L.smem_bytes)));
-        b2c_beam_kernel<false><<<slots, B2C_BEAM_THREADS, A.L.smem_bytes, stream>>>(A);
-    }
+    const int smem = static_cast<int>(A.L.smem_bytes);
+#define B2C_LAUNCH_BEAM(FAST, OCC)                                                                                     \
+    do {                                                                                                               \
+        if (smem > 48 * 1024)                                                                                          \
+            CUDA_OK(cudaFuncSetAttribute(b2c_beam_kernel<FAST, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+        b2c_beam_kernel<FAST, OCC><<<slots, B2C_BEAM_THREADS, A.L.smem_bytes, stream>>>(A);                           \
+    } while (0)
+    if (fast && per_sm > 2) B2C_LAUNCH_BEAM(true, 4);
+    else if (fast) B2C_LAUNCH_BEAM(true, 2);
+    else B2C_LAUNCH_BEAM(false, 2);
+#undef B2C_LAUNCH_BEAM
     CUDA_OK(cudaGetLastError());
 #endif
     return 0;
@@ -865,17 +869,34 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     bool cap_ok[4];
     for (int c = 0; c < 4; ++c)
         cap_ok[c] = make_layout(opts->beam_width, V, 1, false, smem_budget, kCaps[c]).smem_bytes <= smem_budget;
-    std::vector<std::vector<int>> classes(5);   // 0..3 fast classes, 4 general
-    for (int q = 0; q < n_utts; ++q) {
-        const int u = order[q];                 // keeps longest-first order inside every class
-        const double mean_k = T[u] > 0 ? static_cast<double>(h_sumk[u]) / T[u] : 1.0;
-        const u32 typ_k = std::min<u32>(std::max<u32>(h_maxk[u], 1u), std::max<u32>(4u, static_cast<u32>(std::ceil(2.5 * mean_k))));
-        const u64 need = std::min<u64>(static_cast<u64>(opts->beam_width) * typ_k,
-                                       static_cast<u64>(opts->beam_width) * static_cast<u64>(V));
-        int cls = 4;
-        for (int c = 0; c < 4; ++c)
-            if (cap_ok[c] && need <= kCaps[c]) { cls = c; break; }
-        classes[cls].push_back(u);
+    std::vector<std::vector<int>> classes(5);   // 0..3 fast classes (only one is used per call), 4 general
+    auto per_sm_of = [&](u32 smem_bytes) {
+        const int by_smem = static_cast<int>(std::max<u64>(1, (220 * 1024) / std::max<u32>(smem_bytes + 1024, 2048)));
+        return std::min(by_smem, 4);
+    };
+    {
+        std::vector<int> cls_of(n_utts, 4);
+        int top = -1, n_fast = 0;
+        for (int u = 0; u < n_utts; ++u) {
+            const double mean_k = T[u] > 0 ? static_cast<double>(h_sumk[u]) / T[u] : 1.0;
+            const u32 typ_k = std::min<u32>(std::max<u32>(h_maxk[u], 1u), std::max<u32>(4u, static_cast<u32>(std::ceil(2.5 * mean_k))));
+            const u64 need = std::min<u64>(static_cast<u64>(opts->beam_width) * typ_k,
+                                           static_cast<u64>(opts->beam_width) * static_cast<u64>(V));
+            for (int c = 0; c < 4; ++c)
+                if (cap_ok[c] && need <= kCaps[c]) { cls_of[u] = c; break; }
+            if (cls_of[u] < 4) { top = std::max(top, cls_of[u]); ++n_fast; }
+        }
+        // one fast class for the whole call: the largest typical class, upgraded while every fast
+        // utterance stays resident (fewer frames then need the out-of-line HBM-tier step)
+        while (top >= 0 && top + 1 < 4 && cap_ok[top + 1]) {
+            const u32 sb = make_layout(opts->beam_width, V, 1, false, smem_budget, kCaps[top + 1]).smem_bytes;
+            if (static_cast<long long>(d->n_sm) * per_sm_of(sb) < n_fast) break;
+            ++top;
+        }
+        for (int q = 0; q < n_utts; ++q) {
+            const int u = order[q];             // keeps longest-first order inside every class
+            classes[cls_of[u] < 4 ? top : 4].push_back(u);
+        }
     }
     B2cBeamArgs BA;
     std::memset(&BA, 0, sizeof(BA));
@@ -901,7 +922,7 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     BA.phase_clk = d->d_clk.as<u64>();
 #endif
 
-    struct Launch { int cls; size_t ord_off; int count; B2cLayout L; int slots; };
+    struct Launch { int cls; size_t ord_off; int count; B2cLayout L; int slots; int per_sm; };
     auto plan = [&](const std::vector<int>& utts, int cls, bool full, size_t ord_off) {
         Launch ln;
         ln.cls = cls;
@@ -915,9 +936,8 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
         }
         const u64 worst_m = static_cast<u64>(opts->beam_width) * std::min<u32>(kmax, static_cast<u32>(V));
         ln.L = make_layout(opts->beam_width, V, tmax, full, smem_budget, cls < 4 ? kCaps[cls] : 0, worst_m);
-        const int by_smem = static_cast<int>(std::max<u64>(1, (220 * 1024) / std::max<u32>(ln.L.smem_bytes + 1024, 2048)));
-        const int per_sm = std::min(by_smem, 4);   // ~128 registers x 128 threads -> 4 CTAs per SM
-        ln.slots = std::min(ln.count, d->n_sm * per_sm);
+        ln.per_sm = per_sm_of(ln.L.smem_bytes);
+        ln.slots = std::min(ln.count, d->n_sm * ln.per_sm);
         const u64 budget = 16ull << 30;            // keep the HBM workspace bounded
         if (static_cast<u64>(ln.slots) * ln.L.gws_bytes > budget)
             ln.slots = static_cast<int>(std::max<u64>(1, budget / ln.L.gws_bytes));
@@ -955,7 +975,7 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
         BA.next = d_next + qi;
         BA.gws = d->d_ws.as<u8>() + ws_off[qi];
         ++qi;
-        rc = launch_beam(d, BA, ln.slots, ln.cls < 4, cs);
+        rc = launch_beam(d, BA, ln.slots, ln.cls < 4, ln.per_sm, cs);
         if (rc) return rc;
         d->tm.launches += 1;
         if (cs != st) {
@@ -988,7 +1008,7 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
         BA.order = d_ord + n_utts;
         BA.next = d_next + 15;
         BA.gws = d->d_ws.as<u8>();
-        rc = launch_beam(d, BA, ln.slots, false, st);
+        rc = launch_beam(d, BA, ln.slots, false, ln.per_sm, st);
         if (rc) return rc;
         d->tm.launches += 1;
         CUDA_OK(cudaMemcpyAsync(d->h_out_small.p, d->d_out_small.p, small_bytes, cudaMemcpyDeviceToHost, st));
