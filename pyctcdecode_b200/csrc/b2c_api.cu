@@ -225,9 +225,9 @@ __global__ void __launch_bounds__(B2C_PREP_THREADS) b2c_tokens_kernel(const B2cP
     __shared__ B2cPrepShared sh;
     b2c_tokens_block<T>(A, static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x), &sh);
 }
-// kOcc: CTAs per SM the register allocation is bounded for (4: <= 128 registers, 2: <= 255)
-template <bool kFast, int kOcc>
-__global__ void __launch_bounds__(B2C_BEAM_THREADS, kOcc) b2c_beam_kernel(const B2cBeamArgs A) {
+// kThreads x kOcc bound the register allocation: (128,4) and (256,2) -> <= 128 registers, (128,2) -> <= 255
+template <bool kFast, int kThreads, int kOcc>
+__global__ void __launch_bounds__(kThreads, kOcc) b2c_beam_kernel(const B2cBeamArgs A) {
     extern __shared__ __align__(16) u8 b2c_smem[];
     b2c_beam_block<kFast>(A, static_cast<int>(blockIdx.x), b2c_smem);
 }
@@ -412,11 +412,12 @@ static int launch_prepare(b2c_decoder* d, const B2cPrepArgs& A, int n_utts, int 
     return 0;
 }
 
-static int launch_beam(b2c_decoder* d, const B2cBeamArgs& A, int slots, bool fast, int per_sm, cudaStream_t stream) {
+static int launch_beam(b2c_decoder* d, const B2cBeamArgs& A, int slots, bool fast, int per_sm, int threads, cudaStream_t stream) {
 #ifdef B2C_HOSTSIM
     (void)d;
     (void)stream;
     (void)per_sm;
+    (void)threads;
     std::vector<u8> smem(A.L.smem_bytes + 64);
     for (int s = 0; s < slots; ++s) {
         if (fast) b2c_beam_block<true>(A, s, smem.data());
@@ -424,15 +425,17 @@ static int launch_beam(b2c_decoder* d, const B2cBeamArgs& A, int slots, bool fas
     }
 #else
     const int smem = static_cast<int>(A.L.smem_bytes);
-#define B2C_LAUNCH_BEAM(FAST, OCC)                                                                                     \
+#define B2C_LAUNCH_BEAM(FAST, THREADS, OCC)                                                                            \
     do {                                                                                                               \
         if (smem > 48 * 1024)                                                                                          \
-            CUDA_OK(cudaFuncSetAttribute(b2c_beam_kernel<FAST, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-        b2c_beam_kernel<FAST, OCC><<<slots, B2C_BEAM_THREADS, A.L.smem_bytes, stream>>>(A);                           \
+            CUDA_OK(cudaFuncSetAttribute(b2c_beam_kernel<FAST, THREADS, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+        b2c_beam_kernel<FAST, THREADS, OCC><<<slots, THREADS, A.L.smem_bytes, stream>>>(A);                           \
     } while (0)
-    if (fast && per_sm > 2) B2C_LAUNCH_BEAM(true, 4);
-    else if (fast) B2C_LAUNCH_BEAM(true, 2);
-    else B2C_LAUNCH_BEAM(false, 2);
+    if (fast && threads == 512) B2C_LAUNCH_BEAM(true, 512, 1);
+    else if (fast && threads == 256) B2C_LAUNCH_BEAM(true, 256, 2);
+    else if (fast && per_sm > 2) B2C_LAUNCH_BEAM(true, 128, 4);
+    else if (fast) B2C_LAUNCH_BEAM(true, 128, 2);
+    else B2C_LAUNCH_BEAM(false, 128, 2);
 #undef B2C_LAUNCH_BEAM
     CUDA_OK(cudaGetLastError());
 #endif
@@ -922,7 +925,7 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     BA.phase_clk = d->d_clk.as<u64>();
 #endif
 
-    struct Launch { int cls; size_t ord_off; int count; B2cLayout L; int slots; int per_sm; };
+    struct Launch { int cls; size_t ord_off; int count; B2cLayout L; int slots; int per_sm; int threads; };
     auto plan = [&](const std::vector<int>& utts, int cls, bool full, size_t ord_off) {
         Launch ln;
         ln.cls = cls;
@@ -937,6 +940,16 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
         const u64 worst_m = static_cast<u64>(opts->beam_width) * std::min<u32>(kmax, static_cast<u32>(V));
         ln.L = make_layout(opts->beam_width, V, tmax, full, smem_budget, cls < 4 ? kCaps[cls] : 0, worst_m);
         ln.per_sm = per_sm_of(ln.L.smem_bytes);
+        // few utterances per SM: spend 256 threads on each (every phase is then a single pass over
+        // the ~150 candidates of a typical frame instead of two)
+        // (the register file holds 512 threads x 128 registers per SM in every configuration)
+        ln.threads = 128;
+        if (cls < 4) {
+            if (ln.per_sm == 1 || ln.count <= d->n_sm) ln.threads = 512;
+            else if (ln.per_sm == 2 || ln.count <= d->n_sm * 2) ln.threads = 256;
+        }
+        if (ln.threads == 512) ln.per_sm = 1;
+        else if (ln.threads == 256) ln.per_sm = std::min(ln.per_sm, 2);
         ln.slots = std::min(ln.count, d->n_sm * ln.per_sm);
         const u64 budget = 16ull << 30;            // keep the HBM workspace bounded
         if (static_cast<u64>(ln.slots) * ln.L.gws_bytes > budget)
@@ -975,7 +988,7 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
         BA.next = d_next + qi;
         BA.gws = d->d_ws.as<u8>() + ws_off[qi];
         ++qi;
-        rc = launch_beam(d, BA, ln.slots, ln.cls < 4, ln.per_sm, cs);
+        rc = launch_beam(d, BA, ln.slots, ln.cls < 4, ln.per_sm, ln.threads, cs);
         if (rc) return rc;
         d->tm.launches += 1;
         if (cs != st) {
@@ -1008,7 +1021,7 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
         BA.order = d_ord + n_utts;
         BA.next = d_next + 15;
         BA.gws = d->d_ws.as<u8>();
-        rc = launch_beam(d, BA, ln.slots, false, ln.per_sm, st);
+        rc = launch_beam(d, BA, ln.slots, false, ln.per_sm, 128, st);
         if (rc) return rc;
         d->tm.launches += 1;
         CUDA_OK(cudaMemcpyAsync(d->h_out_small.p, d->d_out_small.p, small_bytes, cudaMemcpyDeviceToHost, st));

@@ -59,7 +59,7 @@ struct B2cScalars {
 enum { B2C_FL_BPE = 1, B2C_FL_PRUNE = 2, B2C_FL_LM = 4, B2C_FL_PSCORE = 8 };
 
 #define B2C_NBUCKET 256      // score buckets of the O(m) ranking (monotone in the score)
-#define B2C_MAXWARPS 4       // warps per CTA of the beam kernel
+#define B2C_MAXWARPS 16      // warps per CTA of the beam kernel (128-, 256- and 512-thread variants)
 
 struct B2cCandTier {     // per-frame candidate working set (shared memory tier or HBM tier)
     u32 cap;             // candidates
@@ -374,15 +374,20 @@ B2C_HD B2cCandTier b2c_pick_tier(const B2cWork& W, u32 M) {
     return c;
 }
 
-B2C_HD u32 b2c_ht_size(u32 M) {
+B2C_HD u32 b2c_ht_size(u32 M) {   // power of two >= max(16, 2*M)
+    if (M <= 8) return 16;
+#if defined(__CUDA_ARCH__)
+    return 1u << (32 - __clz(static_cast<int>(2 * M - 1)));
+#else
     u32 h = 16;
     while (h < 2 * M) h <<= 1;
     return h;
+#endif
 }
 
 B2C_HD void b2c_fence_block() {
 #if defined(__CUDA_ARCH__)
-    __threadfence_block();
+    asm volatile("fence.acq_rel.cta;" ::: "memory");   // release before / acquire after the slot CAS
 #endif
 }
 

@@ -74,9 +74,10 @@ B2C_HD u64 b2c_text_append(u64 text_hash, u64 word_hash) {
 }
 // merge key of a beam: (text, partial_word, last_char)  (reference decoder.py:215-216)
 B2C_HD u64 b2c_beam_key(u64 text_hash, u64 part_hash, u32 part_len, u32 last_tok) {
-    u64 k = b2c_mix64(text_hash ^ 0xD6E8FEB86659FD93ull);
-    k = b2c_mix64(k + part_hash * 0xA24BAED4963EE407ull + part_len);
-    k = b2c_mix64(k ^ (static_cast<u64>(last_tok) + 1) * 0x9FB21C651E98DF25ull);
+    // three independent multiplies, one avalanche round (the key is on the critical path of a frame)
+    u64 k = text_hash * 0xD6E8FEB86659FD93ull + part_hash * 0xA24BAED4963EE407ull +
+            (static_cast<u64>(part_len) | ((static_cast<u64>(last_tok) + 1) << 20)) * 0x9FB21C651E98DF25ull;
+    k = b2c_mix64(k);
     return k ? k : 1;
 }
 // n-gram chain: start from the predicted word, extend with context words (most recent first)
