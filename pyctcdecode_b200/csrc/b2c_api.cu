@@ -48,7 +48,7 @@ static int fail(int code, const std::string& msg) {
 // =========================================================================================
 static inline u64 al16(u64 x) { return (x + 15) & ~15ull; }
 static inline u64 tab_bytes(int W) { return 6 * al16(8ull * W) + 4 * al16(4ull * W) + 2 * al16(2ull * W) + 64; }
-static inline u64 sel_bytes(int W) { return al16(8ull * W) + 2 * al16(4ull * W) + 2 * al16(4ull * pt_cap_for(W)) + (2 + B2C_MAXWARPS) * al16(4ull * B2C_NBUCKET) + 64; }
+static inline u64 sel_bytes(int W, int n_warps) { return al16(8ull * W) + 2 * al16(4ull * W) + 2 * al16(4ull * pt_cap_for(W)) + (2 + n_warps) * al16(4ull * B2C_NBUCKET) + 64; }
 static inline u64 tier_bytes(u32 cap, u32 ht) { return al16(8ull * cap) * 4 + al16(4ull * cap) * 4 + al16(4ull * ht) * 4 + 64; }
 
 static u32 pow2_ge(u32 x) {
@@ -61,13 +61,14 @@ static u32 pow2_ge(u32 x) {
 // HBM tier, beam tables in shared memory (the caller checks smem_bytes against the budget).
 // cap_request == 0: general layout -- what fits in shared memory plus an HBM tier sized for the
 // worst case beam_width * V.
-static B2cLayout make_layout(int W, int V, int T_max, bool full_caps, u32 smem_budget, u32 cap_request, u64 worst_m = 0) {
+static B2cLayout make_layout(int W, int V, int T_max, bool full_caps, u32 smem_budget, u32 cap_request, u64 worst_m = 0, int n_warps = 4) {
     B2cLayout L;
     std::memset(&L, 0, sizeof(L));
     L.W = W;
     L.V = V;
+    L.n_warps = n_warps;
     const u64 worst = static_cast<u64>(W) * static_cast<u64>(V);
-    u64 fixed = 64 + sel_bytes(W);
+    u64 fixed = 128 + sel_bytes(W, n_warps);
     if (cap_request) {
         L.beams_in_smem = 1;
         fixed += 2 * tab_bytes(W);
@@ -93,12 +94,12 @@ static B2cLayout make_layout(int W, int V, int T_max, bool full_caps, u32 smem_b
     L.chain_cap = static_cast<u32>(std::min<u64>(wt + 16, 0x7FFFFFF0ull));
     L.text_cap = static_cast<u32>(std::min<u64>(full_caps ? wt + 16 : wt / 4 + 4096, 0x7FFFFFF0ull));
     u64 s = 0;
-    L.s_sc = static_cast<u32>(s); s += 64;
+    L.s_sc = static_cast<u32>(s); s += 128;
     if (L.beams_in_smem) {
         L.s_tab[0] = static_cast<u32>(s); s += tab_bytes(W);
         L.s_tab[1] = static_cast<u32>(s); s += tab_bytes(W);
     }
-    L.s_sel = static_cast<u32>(s); s += sel_bytes(W);
+    L.s_sel = static_cast<u32>(s); s += sel_bytes(W, n_warps);
     L.s_tier = static_cast<u32>(s); s += tier_bytes(L.cap_s, L.ht_s);
     L.smem_bytes = static_cast<u32>(s);
     u64 g = 0;
@@ -140,6 +141,7 @@ struct B2cBeamArgs {
     int* out_frames;
     B2cLmState* out_states;
     u64* phase_clk;            // [16] profiling builds only (-DB2C_PHASE_CLOCKS)
+    u32* m_stats;              // [8] frames over 128..4096 candidates, total frames (adaptive sizing)
 };
 
 // kFast: every frame of every utterance handed to this launch fits the shared-memory candidate
@@ -152,7 +154,11 @@ B2C_HD void b2c_beam_block(const B2cBeamArgs& A, int slot, u8* smem) {
     B2cWork W;
     b2c_make_work(L, smem, g, 0, kFast || L.beams_in_smem, W);
     int parity = 0;      // which beam table is current (the out-of-line step rebuilds its descriptor from it)
-    u32* s_cur = reinterpret_cast<u32*>(smem + L.s_sc + 56);  // queue ticket of this CTA
+    u32* s_cur = reinterpret_cast<u32*>(smem + L.s_sc + 120);  // queue ticket of this CTA
+    B2C_LEADER {
+        for (int q = 0; q < 6; ++q) W.sc->m_over[q] = 0;
+        W.sc->m_frames = 0;
+    }
 #if defined(B2C_PHASE_CLOCKS) && defined(__CUDA_ARCH__)
     for (int q = 0; q < 16; ++q) W.clk[q] = 0;
     W.clk_last = clock64();
@@ -203,6 +209,13 @@ B2C_HD void b2c_beam_block(const B2cBeamArgs& A, int slot, u8* smem) {
         O.states = A.out_states + static_cast<u64>(u) * ob;
         b2c_finalize(A.P, W, O);
         B2C_MARK(8);
+    }
+    B2C_LEADER {
+        if (A.m_stats) {
+            for (int q = 0; q < 6; ++q)
+                if (W.sc->m_over[q]) b2c_atomic_add_u32(A.m_stats + q, W.sc->m_over[q]);
+            b2c_atomic_add_u32(A.m_stats + 6, W.sc->m_frames);
+        }
     }
 #if defined(B2C_PHASE_CLOCKS) && defined(__CUDA_ARCH__)
     if (threadIdx.x == 0 && A.phase_clk)
@@ -293,7 +306,7 @@ struct b2c_decoder {
     int score_boundary = 1;
     int n_sm = 1;
     size_t smem_optin = 48 * 1024;
-    DevBuf d_sumk, d_clk, d_maxk, d_toks, d_logits, d_meta, d_tok_start, d_tok_ids, d_tok_lp, d_rowsum, d_set, d_isprob, d_ws, d_hot, d_states,
+    DevBuf d_mstats, d_sumk, d_clk, d_maxk, d_toks, d_logits, d_meta, d_tok_start, d_tok_ids, d_tok_lp, d_rowsum, d_set, d_isprob, d_ws, d_hot, d_states,
         d_out_small, d_out_toks, d_out_frames;
     PinBuf h_sumk, h_maxk, h_meta, h_out_small, h_out_toks, h_out_frames;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -301,6 +314,11 @@ struct b2c_decoder {
     cudaEvent_t cls_done[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t fork_ev = nullptr;
     b2c_timings_t tm;
+    // adaptive sizing: candidate-count histogram of the previous call with the same configuration
+    bool hint_valid = false;
+    int hint_beam = 0, hint_lm = 0, hint_hot = 0, hint_prune = 0;
+    u32 hint_over[6] = {0, 0, 0, 0, 0, 0};
+    u32 hint_frames = 0;
 };
 
 struct BeamRes {
@@ -431,10 +449,9 @@ static int launch_beam(b2c_decoder* d, const B2cBeamArgs& A, int slots, bool fas
             CUDA_OK(cudaFuncSetAttribute(b2c_beam_kernel<FAST, THREADS, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
         b2c_beam_kernel<FAST, THREADS, OCC><<<slots, THREADS, A.L.smem_bytes, stream>>>(A);                           \
     } while (0)
-    if (fast && threads == 512) B2C_LAUNCH_BEAM(true, 512, 1);
-    else if (fast && threads == 256) B2C_LAUNCH_BEAM(true, 256, 2);
-    else if (fast && per_sm > 2) B2C_LAUNCH_BEAM(true, 128, 4);
-    else if (fast) B2C_LAUNCH_BEAM(true, 128, 2);
+    (void)per_sm;
+    if (fast && threads == 64) B2C_LAUNCH_BEAM(true, 64, 4);     // 255 registers x 64 threads: 4 CTAs per SM
+    else if (fast) B2C_LAUNCH_BEAM(true, 128, 2);                 // 255 registers x 128 threads: 2 CTAs per SM
     else B2C_LAUNCH_BEAM(false, 128, 2);
 #undef B2C_LAUNCH_BEAM
     CUDA_OK(cudaGetLastError());
@@ -638,7 +655,7 @@ void b2c_decoder_destroy(b2c_decoder_t* d) {
     if (!d) return;
     cudaSetDevice(d->device);
     if (d->stream) cudaStreamSynchronize(d->stream);
-    DevBuf* bufs[] = {&d->d_sumk, &d->d_clk, &d->d_maxk, &d->d_toks, &d->d_logits, &d->d_meta, &d->d_tok_start, &d->d_tok_ids, &d->d_tok_lp, &d->d_rowsum, &d->d_set,
+    DevBuf* bufs[] = {&d->d_mstats, &d->d_sumk, &d->d_clk, &d->d_maxk, &d->d_toks, &d->d_logits, &d->d_meta, &d->d_tok_start, &d->d_tok_ids, &d->d_tok_lp, &d->d_rowsum, &d->d_set,
                       &d->d_isprob, &d->d_ws, &d->d_hot, &d->d_states, &d->d_out_small, &d->d_out_toks, &d->d_out_frames};
     for (DevBuf* b : bufs) b->release();
     PinBuf* pins[] = {&d->h_sumk, &d->h_maxk, &d->h_meta, &d->h_out_small, &d->h_out_toks, &d->h_out_frames};
@@ -864,41 +881,56 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     CUDA_OK(cudaStreamSynchronize(st));
     const u32* h_maxk = d->h_maxk.as<u32>();
     const u32* h_sumk = d->h_sumk.as<u32>();
-    // capacity classes of the shared-memory candidate tier, sized for the TYPICAL frame of the
-    // utterance (2.5 x its mean tokens per frame, at least 4): the few wider frames of such an
-    // utterance take the out-of-line HBM-tier step inside the same kernel.  Utterances whose typical
-    // frame does not fit any class go to the general kernel.
-    static const u32 kCaps[4] = {512, 1024, 2048, 4096};
-    bool cap_ok[4];
-    for (int c = 0; c < 4; ++c)
-        cap_ok[c] = make_layout(opts->beam_width, V, 1, false, smem_budget, kCaps[c]).smem_bytes <= smem_budget;
-    std::vector<std::vector<int>> classes(5);   // 0..3 fast classes (only one is used per call), 4 general
-    auto per_sm_of = [&](u32 smem_bytes) {
-        const int by_smem = static_cast<int>(std::max<u64>(1, (220 * 1024) / std::max<u32>(smem_bytes + 1024, 2048)));
-        return std::min(by_smem, 4);
+    // ---- capacity class of the shared-memory candidate tier (ONE fast class per call) -------------
+    // upper bound: sized for the TYPICAL frame of an utterance if all beam_width beams were alive
+    // (2.5 x its mean tokens per frame, at least 4); with a hint from the previous call of the same
+    // configuration (histogram of the per-frame candidate counts actually seen -- with an LM far fewer
+    // beams stay alive): the smallest class that covers all but 0.4% of the frames.  The few wider
+    // frames take the out-of-line HBM-tier step inside the same kernel, so every choice is exact.
+    // Small classes run 64-thread CTAs (255 registers x 64 threads: 4 CTAs per SM), the others 128.
+    static const int kNumCaps = 6;
+    static const u32 kCaps[kNumCaps] = {128, 256, 512, 1024, 2048, 4096};
+    auto threads_of = [&](int c) { return kCaps[c] <= 256 ? 64 : 128; };
+    auto layout_of = [&](int c, int tmax, bool full, u64 worst_m) {
+        return make_layout(opts->beam_width, V, tmax, full, smem_budget, kCaps[c], worst_m, threads_of(c) / 32);
     };
+    auto per_sm_of = [&](u32 smem_bytes, int threads) {
+        const int by_smem = static_cast<int>(std::max<u64>(1, (220 * 1024) / std::max<u32>(smem_bytes + 1024, 2048)));
+        return std::min(by_smem, threads == 64 ? 4 : 2);
+    };
+    bool cap_ok[kNumCaps];
+    for (int c = 0; c < kNumCaps; ++c) cap_ok[c] = layout_of(c, 1, false, 0).smem_bytes <= smem_budget;
+    std::vector<std::vector<int>> classes(kNumCaps + 1);   // fast classes (one used per call), last = general
+    const bool hint_ok = d->hint_valid && d->hint_beam == opts->beam_width && d->hint_lm == (P.lm.order > 0 ? 1 : 0) &&
+                         d->hint_hot == (P.n_hot > 0 ? 1 : 0) && d->hint_prune == P.prune_history && d->hint_frames > 0;
     {
-        std::vector<int> cls_of(n_utts, 4);
+        std::vector<int> cls_of(n_utts, kNumCaps);
         int top = -1, n_fast = 0;
         for (int u = 0; u < n_utts; ++u) {
             const double mean_k = T[u] > 0 ? static_cast<double>(h_sumk[u]) / T[u] : 1.0;
             const u32 typ_k = std::min<u32>(std::max<u32>(h_maxk[u], 1u), std::max<u32>(4u, static_cast<u32>(std::ceil(2.5 * mean_k))));
             const u64 need = std::min<u64>(static_cast<u64>(opts->beam_width) * typ_k,
                                            static_cast<u64>(opts->beam_width) * static_cast<u64>(V));
-            for (int c = 0; c < 4; ++c)
+            for (int c = 0; c < kNumCaps; ++c)
                 if (cap_ok[c] && need <= kCaps[c]) { cls_of[u] = c; break; }
-            if (cls_of[u] < 4) { top = std::max(top, cls_of[u]); ++n_fast; }
+            if (cls_of[u] < kNumCaps) { top = std::max(top, cls_of[u]); ++n_fast; }
         }
-        // one fast class for the whole call: the largest typical class, upgraded while every fast
-        // utterance stays resident (fewer frames then need the out-of-line HBM-tier step)
-        while (top >= 0 && top + 1 < 4 && cap_ok[top + 1]) {
-            const u32 sb = make_layout(opts->beam_width, V, 1, false, smem_budget, kCaps[top + 1]).smem_bytes;
-            if (static_cast<long long>(d->n_sm) * per_sm_of(sb) < n_fast) break;
+        if (top >= 0 && hint_ok) {
+            int c_hint = kNumCaps - 1;
+            for (int c = 0; c < kNumCaps; ++c)
+                if (static_cast<double>(d->hint_over[c]) <= 0.004 * d->hint_frames) { c_hint = c; break; }
+            while (c_hint < top && !cap_ok[c_hint]) ++c_hint;
+            top = std::min(top, c_hint);
+        }
+        // upgrade while every fast utterance stays resident (fewer frames need the out-of-line step)
+        while (top >= 0 && top + 1 < kNumCaps && cap_ok[top + 1]) {
+            const u32 sb = layout_of(top + 1, 1, false, 0).smem_bytes;
+            if (static_cast<long long>(d->n_sm) * per_sm_of(sb, threads_of(top + 1)) < n_fast) break;
             ++top;
         }
         for (int q = 0; q < n_utts; ++q) {
             const int u = order[q];             // keeps longest-first order inside every class
-            classes[cls_of[u] < 4 ? top : 4].push_back(u);
+            classes[cls_of[u] < kNumCaps ? top : kNumCaps].push_back(u);
         }
     }
     B2cBeamArgs BA;
@@ -919,6 +951,9 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     BA.out_states = reinterpret_cast<B2cLmState*>(ds + off_ls);
     BA.out_toks = d->d_out_toks.as<u32>();
     BA.out_frames = d->d_out_frames.as<int>();
+    if (d->d_mstats.ensure(32)) return B2C_E_NOMEM;
+    CUDA_OK(cudaMemsetAsync(d->d_mstats.p, 0, 32, st));
+    BA.m_stats = d->d_mstats.as<u32>();
 #if defined(B2C_PHASE_CLOCKS)
     if (d->d_clk.ensure(16 * 8)) return B2C_E_NOMEM;
     CUDA_OK(cudaMemsetAsync(d->d_clk.p, 0, 16 * 8, st));
@@ -938,18 +973,10 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
             kmax = std::max(kmax, h_maxk[u]);
         }
         const u64 worst_m = static_cast<u64>(opts->beam_width) * std::min<u32>(kmax, static_cast<u32>(V));
-        ln.L = make_layout(opts->beam_width, V, tmax, full, smem_budget, cls < 4 ? kCaps[cls] : 0, worst_m);
-        ln.per_sm = per_sm_of(ln.L.smem_bytes);
-        // few utterances per SM: spend 256 threads on each (every phase is then a single pass over
-        // the ~150 candidates of a typical frame instead of two)
-        // (the register file holds 512 threads x 128 registers per SM in every configuration)
-        ln.threads = 128;
-        if (cls < 4) {
-            if (ln.per_sm == 1 || ln.count <= d->n_sm) ln.threads = 512;
-            else if (ln.per_sm == 2 || ln.count <= d->n_sm * 2) ln.threads = 256;
-        }
-        if (ln.threads == 512) ln.per_sm = 1;
-        else if (ln.threads == 256) ln.per_sm = std::min(ln.per_sm, 2);
+        ln.threads = cls < kNumCaps ? threads_of(cls) : 128;
+        ln.L = cls < kNumCaps ? layout_of(cls, tmax, full, worst_m)
+                              : make_layout(opts->beam_width, V, tmax, full, smem_budget, 0, worst_m, 4);
+        ln.per_sm = per_sm_of(ln.L.smem_bytes, ln.threads);
         ln.slots = std::min(ln.count, d->n_sm * ln.per_sm);
         const u64 budget = 16ull << 30;            // keep the HBM workspace bounded
         if (static_cast<u64>(ln.slots) * ln.L.gws_bytes > budget)
@@ -958,7 +985,7 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     };
     std::vector<Launch> launches;
     size_t ord_used = 0;
-    for (int c = 0; c < 5; ++c) {
+    for (int c = 0; c <= kNumCaps; ++c) {
         if (classes[c].empty()) continue;
         launches.push_back(plan(classes[c], c, false, ord_used));
         for (int u : classes[c]) h_ord[ord_used++] = u;
@@ -980,7 +1007,7 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     CUDA_OK(cudaEventRecord(d->fork_ev, st));
     int qi = 0;
     for (const Launch& ln : launches) {
-        cudaStream_t cs = launches.size() > 1 ? d->cls_stream[ln.cls] : st;
+        cudaStream_t cs = launches.size() > 1 ? d->cls_stream[ln.cls < kNumCaps ? 0 : 1] : st;
         if (cs != st) CUDA_OK(cudaStreamWaitEvent(cs, d->fork_ev, 0));
         BA.L = ln.L;
         BA.n_utts = ln.count;
@@ -988,12 +1015,12 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
         BA.next = d_next + qi;
         BA.gws = d->d_ws.as<u8>() + ws_off[qi];
         ++qi;
-        rc = launch_beam(d, BA, ln.slots, ln.cls < 4, ln.per_sm, ln.threads, cs);
+        rc = launch_beam(d, BA, ln.slots, ln.cls < kNumCaps, ln.per_sm, ln.threads, cs);
         if (rc) return rc;
         d->tm.launches += 1;
         if (cs != st) {
-            CUDA_OK(cudaEventRecord(d->cls_done[ln.cls], cs));
-            CUDA_OK(cudaStreamWaitEvent(st, d->cls_done[ln.cls], 0));
+            CUDA_OK(cudaEventRecord(d->cls_done[ln.cls < kNumCaps ? 0 : 1], cs));
+            CUDA_OK(cudaStreamWaitEvent(st, d->cls_done[ln.cls < kNumCaps ? 0 : 1], 0));
         }
     }
     CUDA_OK(cudaEventRecord(d->ev[3], st));
@@ -1004,7 +1031,18 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     CUDA_OK(cudaMemcpyAsync(d->h_out_frames.p, d->d_out_frames.p, frm_bytes, cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaEventRecord(d->ev[4], st));
     CUDA_OK(cudaStreamSynchronize(st));
-    d->tm.d2h_bytes += static_cast<long long>(small_bytes + tok_bytes + frm_bytes + 4ull * n_utts);
+    d->tm.d2h_bytes += static_cast<long long>(small_bytes + tok_bytes + frm_bytes + 8ull * n_utts + 32);
+    {
+        u32 ms[8];
+        CUDA_OK(cudaMemcpy(ms, d->d_mstats.p, 32, cudaMemcpyDeviceToHost));
+        d->hint_valid = true;
+        d->hint_beam = opts->beam_width;
+        d->hint_lm = P.lm.order > 0 ? 1 : 0;
+        d->hint_hot = P.n_hot > 0 ? 1 : 0;
+        d->hint_prune = P.prune_history;
+        for (int q = 0; q < 6; ++q) d->hint_over[q] = ms[q];
+        d->hint_frames = ms[6];
+    }
 
     u8* hs = d->h_out_small.as<u8>();
     int* h_status = reinterpret_cast<int*>(hs + off_st);
@@ -1012,7 +1050,7 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     for (int i = 0; i < n_utts; ++i) if (h_status[i] != B2C_OK) failed.push_back(i);
     if (!failed.empty()) {
         // second pass for utterances whose arenas overflowed: general kernel, worst-case arenas
-        Launch ln = plan(failed, 4, true, static_cast<size_t>(n_utts));
+        Launch ln = plan(failed, kNumCaps, true, static_cast<size_t>(n_utts));
         if (d->d_ws.ensure(static_cast<u64>(ln.slots) * ln.L.gws_bytes)) return B2C_E_NOMEM;
         for (size_t i = 0; i < failed.size(); ++i) h_ord[n_utts + i] = failed[i];
         CUDA_OK(cudaMemcpyAsync(d_ord + n_utts, h_ord + n_utts, 4 * failed.size(), cudaMemcpyHostToDevice, st));

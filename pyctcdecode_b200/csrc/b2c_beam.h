@@ -55,11 +55,13 @@ struct B2cScalars {
     u32 n_beams, n_sel, n_new, chain_used, text_used, status, force_break;
     u32 flags;           // B2C_FL_*: mode bits re-read from shared memory every frame so that the compiler
                          // cannot unswitch (= replicate) the frame loop on them
+    u32 m_over[6];       // frames whose candidate count exceeded 128,256,512,1024,2048,4096 (adaptive sizing)
+    u32 m_frames;
 };
 enum { B2C_FL_BPE = 1, B2C_FL_PRUNE = 2, B2C_FL_LM = 4, B2C_FL_PSCORE = 8 };
 
 #define B2C_NBUCKET 256      // score buckets of the O(m) ranking (monotone in the score)
-#define B2C_MAXWARPS 16      // warps per CTA of the beam kernel (128-, 256- and 512-thread variants)
+#define B2C_MAXWARPS 4       // warps per CTA of the beam kernel
 
 struct B2cCandTier {     // per-frame candidate working set (shared memory tier or HBM tier)
     u32 cap;             // candidates
@@ -117,6 +119,7 @@ struct B2cLayout {
     u32 cap_s, ht_s;            // shared-memory candidate tier
     u32 cap_g, ht_g;            // HBM candidate tier (0: absent)
     int beams_in_smem;
+    int n_warps;                // warps per CTA of the launch (sizes the per-warp scratch)
     u32 chain_cap, text_cap;
     int V;
     u32 smem_bytes;
@@ -187,7 +190,7 @@ B2C_HD void b2c_make_work(const B2cLayout& L, u8* smem, u8* g, int parity, bool 
         W.pt_min = reinterpret_cast<u32*>(b2c_carve(p, 4ull * W.pt_cap));
         W.bcnt = reinterpret_cast<u32*>(b2c_carve(p, 4ull * B2C_NBUCKET));
         W.bhead = reinterpret_cast<u32*>(b2c_carve(p, 4ull * B2C_NBUCKET));
-        W.bpre = reinterpret_cast<u32*>(b2c_carve(p, 4ull * B2C_NBUCKET * B2C_MAXWARPS));
+        W.bpre = reinterpret_cast<u32*>(b2c_carve(p, 4ull * B2C_NBUCKET * L.n_warps));
     }
     b2c_carve_tier(smem + L.s_tier, L.cap_s, L.ht_s, W.tier_s);
     if (L.cap_g) b2c_carve_tier(g + L.g_tier, L.cap_g, L.ht_g, W.tier_g);
@@ -584,6 +587,11 @@ B2C_HD void b2c_frame_step(const B2cParams& P, B2cWork& W, int t, const u16* tk_
         return;
     }
     B2C_MARK(0);
+    B2C_LEADER {
+        ++sc->m_frames;
+        for (int q = 0; q < 6; ++q)
+            if (M > (128u << q)) ++sc->m_over[q];
+    }
     const u32 hmask = b2c_ht_size(M) - 1;
     const B2cBeamTab cur = W.cur;
     const B2cBeamTab nx = W.nxt;
