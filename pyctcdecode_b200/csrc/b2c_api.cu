@@ -450,7 +450,8 @@ static int launch_beam(b2c_decoder* d, const B2cBeamArgs& A, int slots, bool fas
         b2c_beam_kernel<FAST, THREADS, OCC><<<slots, THREADS, A.L.smem_bytes, stream>>>(A);                           \
     } while (0)
     (void)per_sm;
-    if (fast && threads == 64) B2C_LAUNCH_BEAM(true, 64, 4);     // 255 registers x 64 threads: 4 CTAs per SM
+    if (fast && threads == 256) B2C_LAUNCH_BEAM(true, 256, 1);         // 255 registers x 256 threads: the whole register file
+    else if (fast && threads == 64) B2C_LAUNCH_BEAM(true, 64, 4);     // 255 registers x 64 threads: 4 CTAs per SM
     else if (fast) B2C_LAUNCH_BEAM(true, 128, 2);                 // 255 registers x 128 threads: 2 CTAs per SM
     else B2C_LAUNCH_BEAM(false, 128, 2);
 #undef B2C_LAUNCH_BEAM
@@ -890,13 +891,14 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     // Small classes run 64-thread CTAs (255 registers x 64 threads: 4 CTAs per SM), the others 128.
     static const int kNumCaps = 6;
     static const u32 kCaps[kNumCaps] = {128, 256, 512, 1024, 2048, 4096};
-    auto threads_of = [&](int c) { return kCaps[c] <= 256 ? 64 : 128; };
+    // big classes leave room for one CTA per SM only: give that CTA 256 threads (a diffuse frame has ~650 candidates)
+    auto threads_of = [&](int c) { return kCaps[c] <= 256 ? 64 : (kCaps[c] >= 2048 ? 256 : 128); };
     auto layout_of = [&](int c, int tmax, bool full, u64 worst_m) {
         return make_layout(opts->beam_width, V, tmax, full, smem_budget, kCaps[c], worst_m, threads_of(c) / 32);
     };
     auto per_sm_of = [&](u32 smem_bytes, int threads) {
         const int by_smem = static_cast<int>(std::max<u64>(1, (220 * 1024) / std::max<u32>(smem_bytes + 1024, 2048)));
-        return std::min(by_smem, threads == 64 ? 4 : 2);
+        return std::min(by_smem, threads == 64 ? 4 : (threads == 256 ? 1 : 2));
     };
     bool cap_ok[kNumCaps];
     for (int c = 0; c < kNumCaps; ++c) cap_ok[c] = layout_of(c, 1, false, 0).smem_bytes <= smem_budget;

@@ -61,7 +61,7 @@ struct B2cScalars {
 enum { B2C_FL_BPE = 1, B2C_FL_PRUNE = 2, B2C_FL_LM = 4, B2C_FL_PSCORE = 8 };
 
 #define B2C_NBUCKET 256      // score buckets of the O(m) ranking (monotone in the score)
-#define B2C_MAXWARPS 4       // warps per CTA of the beam kernel
+#define B2C_MAXWARPS 8       // warps per CTA of the beam kernel (64-, 128- and 256-thread variants)
 
 struct B2cCandTier {     // per-frame candidate working set (shared memory tier or HBM tier)
     u32 cap;             // candidates
