@@ -175,6 +175,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout (ONE JSON line)
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         dist.barrier()
@@ -286,6 +287,8 @@ def main():
                 "ms_per_step": 1e3 * e2e_total / args.steps},
         "gpu_launches": int(sum(t["launches"] for t in tms)),
         "device_ms_per_step": statistics.mean(t["ms_total"] for t in tms),
+        "beam_kernel_config": {"cap_candidates": tms[-1]["cap_candidates"], "cta_threads": tms[-1]["cta_threads"],
+                               "resident_ctas": tms[-1]["cta_slots"], "oversize_frames_per_step": tms[-1]["oversize_frames"]},
         "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -128,6 +128,10 @@ typedef struct {
     long long h2d_bytes, d2h_bytes;
     long long frames;          /* sum of T                                                 */
     long long tokens;          /* selected (frame, token) pairs                            */
+    int cap_candidates;        /* shared-memory candidate capacity class chosen for the call */
+    int cta_threads;           /* threads per CTA of the beam kernel                        */
+    int cta_slots;             /* resident CTAs (utterances in flight)                      */
+    long long oversize_frames; /* frames that took the out-of-line HBM-tier step           */
 } b2c_timings_t;
 int b2c_decoder_last_timings(const b2c_decoder_t* dec, b2c_timings_t* out);
 

@@ -44,6 +44,10 @@ class Timings(C.Structure):
         ("d2h_bytes", C.c_longlong),
         ("frames", C.c_longlong),
         ("tokens", C.c_longlong),
+        ("cap_candidates", C.c_int),
+        ("cta_threads", C.c_int),
+        ("cta_slots", C.c_int),
+        ("oversize_frames", C.c_longlong),
     ]
 
 

@@ -450,7 +450,8 @@ static int launch_beam(b2c_decoder* d, const B2cBeamArgs& A, int slots, bool fas
         b2c_beam_kernel<FAST, THREADS, OCC><<<slots, THREADS, A.L.smem_bytes, stream>>>(A);                           \
     } while (0)
     (void)per_sm;
-    if (fast && threads == 256) B2C_LAUNCH_BEAM(true, 256, 1);         // 255 registers x 256 threads: the whole register file
+    if (fast && threads == 32) B2C_LAUNCH_BEAM(true, 32, 8);           // 255 registers x 32 threads: 8 one-warp CTAs per SM
+    else if (fast && threads == 256) B2C_LAUNCH_BEAM(true, 256, 1);    // 255 registers x 256 threads: the whole register file
     else if (fast && threads == 64) B2C_LAUNCH_BEAM(true, 64, 4);     // 255 registers x 64 threads: 4 CTAs per SM
     else if (fast) B2C_LAUNCH_BEAM(true, 128, 2);                 // 255 registers x 128 threads: 2 CTAs per SM
     else B2C_LAUNCH_BEAM(false, 128, 2);
@@ -892,13 +893,13 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     static const int kNumCaps = 6;
     static const u32 kCaps[kNumCaps] = {128, 256, 512, 1024, 2048, 4096};
     // big classes leave room for one CTA per SM only: give that CTA 256 threads (a diffuse frame has ~650 candidates)
-    auto threads_of = [&](int c) { return kCaps[c] <= 256 ? 64 : (kCaps[c] >= 2048 ? 256 : 128); };
+    auto threads_of = [&](int c) { return kCaps[c] <= 128 ? 32 : (kCaps[c] <= 256 ? 64 : (kCaps[c] >= 2048 ? 256 : 128)); };
     auto layout_of = [&](int c, int tmax, bool full, u64 worst_m) {
         return make_layout(opts->beam_width, V, tmax, full, smem_budget, kCaps[c], worst_m, threads_of(c) / 32);
     };
     auto per_sm_of = [&](u32 smem_bytes, int threads) {
-        const int by_smem = static_cast<int>(std::max<u64>(1, (220 * 1024) / std::max<u32>(smem_bytes + 1024, 2048)));
-        return std::min(by_smem, threads == 64 ? 4 : (threads == 256 ? 1 : 2));
+        const int by_smem = static_cast<int>(std::max<u64>(1, (224 * 1024) / std::max<u32>(smem_bytes + 1024, 2048)));
+        return std::min(by_smem, threads == 32 ? 8 : (threads == 64 ? 4 : (threads == 256 ? 1 : 2)));
     };
     bool cap_ok[kNumCaps];
     for (int c = 0; c < kNumCaps; ++c) cap_ok[c] = layout_of(c, 1, false, 0).smem_bytes <= smem_budget;
@@ -1020,6 +1021,11 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
         rc = launch_beam(d, BA, ln.slots, ln.cls < kNumCaps, ln.per_sm, ln.threads, cs);
         if (rc) return rc;
         d->tm.launches += 1;
+        if (ln.cls < kNumCaps || launches.size() == 1) {
+            d->tm.cap_candidates = static_cast<int>(ln.L.cap_s);
+            d->tm.cta_threads = ln.threads;
+            d->tm.cta_slots = ln.slots;
+        }
         if (cs != st) {
             CUDA_OK(cudaEventRecord(d->cls_done[ln.cls < kNumCaps ? 0 : 1], cs));
             CUDA_OK(cudaStreamWaitEvent(st, d->cls_done[ln.cls < kNumCaps ? 0 : 1], 0));
@@ -1044,6 +1050,9 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
         d->hint_prune = P.prune_history;
         for (int q = 0; q < 6; ++q) d->hint_over[q] = ms[q];
         d->hint_frames = ms[6];
+        d->tm.oversize_frames = 0;
+        for (int q = 0; q < 6; ++q)
+            if (static_cast<int>(128u << q) == d->tm.cap_candidates) d->tm.oversize_frames = ms[q];
     }
 
     u8* hs = d->h_out_small.as<u8>();
