@@ -132,6 +132,7 @@ typedef struct {
     int cta_threads;           /* threads per CTA of the beam kernel                        */
     int cta_slots;             /* resident CTAs (utterances in flight)                      */
     long long oversize_frames; /* frames that took the out-of-line HBM-tier step           */
+    int kernel_variant;        /* 0 general, 1 capacity-class fast kernel, 2 latency-first kernel (beam_width <= 128) */
 } b2c_timings_t;
 int b2c_decoder_last_timings(const b2c_decoder_t* dec, b2c_timings_t* out);
 

@@ -48,6 +48,7 @@ class Timings(C.Structure):
         ("cta_threads", C.c_int),
         ("cta_slots", C.c_int),
         ("oversize_frames", C.c_longlong),
+        ("kernel_variant", C.c_int),
     ]
 
 

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -223,7 +224,15 @@ B2C_HD void b2c_beam_block(const B2cBeamArgs& A, int slot, u8* smem) {
 #endif
 }
 
+#include "b2c_beam_fast.h"
+typedef B2cFastSmem<128, 1024> B2cFastSmemA;      // beam_width <= 128, <= 1024 candidates per frame: 2 CTAs per SM
+
 #ifndef B2C_HOSTSIM
+template <int WC, int CAP>
+__global__ void __launch_bounds__(B2C_FAST_NT, 2) b2c_beam_fast_kernel(const B2cBeamArgs A) {
+    extern __shared__ __align__(16) u8 b2c_smem[];
+    b2c_beam_block_fast<WC, CAP>(A, static_cast<int>(blockIdx.x), b2c_smem);
+}
 template <class T>
 __global__ void __launch_bounds__(B2C_PREP_THREADS) b2c_rowsum_kernel(const B2cPrepArgs A) {
     b2c_rowsum_block<T>(A, static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x));
@@ -430,7 +439,9 @@ static int launch_prepare(b2c_decoder* d, const B2cPrepArgs& A, int n_utts, int 
     return 0;
 }
 
-static int launch_beam(b2c_decoder* d, const B2cBeamArgs& A, int slots, bool fast, int per_sm, int threads, cudaStream_t stream) {
+// v5: the latency-first kernel (b2c_beam_fast.h); A.L.smem_bytes is sizeof(B2cFastSmemA) then
+static int launch_beam(b2c_decoder* d, const B2cBeamArgs& A, int slots, bool fast, int per_sm, int threads, cudaStream_t stream,
+                       bool v5 = false) {
 #ifdef B2C_HOSTSIM
     (void)d;
     (void)stream;
@@ -438,11 +449,18 @@ static int launch_beam(b2c_decoder* d, const B2cBeamArgs& A, int slots, bool fas
     (void)threads;
     std::vector<u8> smem(A.L.smem_bytes + 64);
     for (int s = 0; s < slots; ++s) {
-        if (fast) b2c_beam_block<true>(A, s, smem.data());
+        if (v5) b2c_beam_block_fast<128, 1024>(A, s, smem.data());
+        else if (fast) b2c_beam_block<true>(A, s, smem.data());
         else b2c_beam_block<false>(A, s, smem.data());
     }
 #else
     const int smem = static_cast<int>(A.L.smem_bytes);
+    if (v5) {
+        CUDA_OK(cudaFuncSetAttribute(b2c_beam_fast_kernel<128, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        b2c_beam_fast_kernel<128, 1024><<<slots, B2C_FAST_NT, A.L.smem_bytes, stream>>>(A);
+        CUDA_OK(cudaGetLastError());
+        return 0;
+    }
 #define B2C_LAUNCH_BEAM(FAST, THREADS, OCC)                                                                            \
     do {                                                                                                               \
         if (smem > 48 * 1024)                                                                                          \
@@ -904,6 +922,8 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     bool cap_ok[kNumCaps];
     for (int c = 0; c < kNumCaps; ++c) cap_ok[c] = layout_of(c, 1, false, 0).smem_bytes <= smem_budget;
     std::vector<std::vector<int>> classes(kNumCaps + 1);   // fast classes (one used per call), last = general
+    bool use_v5 = false;
+    int v5_top = -1;
     const bool hint_ok = d->hint_valid && d->hint_beam == opts->beam_width && d->hint_lm == (P.lm.order > 0 ? 1 : 0) &&
                          d->hint_hot == (P.n_hot > 0 ? 1 : 0) && d->hint_prune == P.prune_history && d->hint_frames > 0;
     {
@@ -925,12 +945,18 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
             while (c_hint < top && !cap_ok[c_hint]) ++c_hint;
             top = std::min(top, c_hint);
         }
+        v5_top = top;                            // the class the statistics ask for, before the residency upgrade
         // upgrade while every fast utterance stays resident (fewer frames need the out-of-line step)
         while (top >= 0 && top + 1 < kNumCaps && cap_ok[top + 1]) {
             const u32 sb = layout_of(top + 1, 1, false, 0).smem_bytes;
             if (static_cast<long long>(d->n_sm) * per_sm_of(sb, threads_of(top + 1)) < n_fast) break;
             ++top;
         }
+        // beam_width <= 128 and a typical frame within 1024 candidates: the latency-first kernel (v5) takes
+        // the whole fast list; wider frames inside it go through its out-of-line HBM-tier step
+        const bool force_v5 = std::getenv("B200CTC_FORCE_V5") != nullptr;      // tests: exercise the out-of-line step
+        use_v5 = top >= 0 && opts->beam_width <= 128 && (force_v5 || kCaps[v5_top >= 0 ? v5_top : top] <= 1024) &&
+                 sizeof(B2cFastSmemA) + 1024 <= d->smem_optin && std::getenv("B200CTC_NO_V5") == nullptr;
         for (int q = 0; q < n_utts; ++q) {
             const int u = order[q];             // keeps longest-first order inside every class
             classes[cls_of[u] < kNumCaps ? top : kNumCaps].push_back(u);
@@ -963,7 +989,7 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     BA.phase_clk = d->d_clk.as<u64>();
 #endif
 
-    struct Launch { int cls; size_t ord_off; int count; B2cLayout L; int slots; int per_sm; int threads; };
+    struct Launch { int cls; size_t ord_off; int count; B2cLayout L; int slots; int per_sm; int threads; bool v5; };
     auto plan = [&](const std::vector<int>& utts, int cls, bool full, size_t ord_off) {
         Launch ln;
         ln.cls = cls;
@@ -976,10 +1002,19 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
             kmax = std::max(kmax, h_maxk[u]);
         }
         const u64 worst_m = static_cast<u64>(opts->beam_width) * std::min<u32>(kmax, static_cast<u32>(V));
+        ln.v5 = use_v5 && cls < kNumCaps;
+        if (ln.v5) {
+            // beam tables of capacity 128; the HBM tier always exists (frames with > B2C_FAST_KS tokens use it too)
+            ln.threads = B2C_FAST_NT;
+            ln.L = make_layout(128, V, tmax, full, smem_budget, 1024, std::max<u64>(worst_m, 1025), B2C_FAST_NW);
+            ln.L.smem_bytes = static_cast<u32>(sizeof(B2cFastSmemA));
+            ln.per_sm = 2;
+        } else {
         ln.threads = cls < kNumCaps ? threads_of(cls) : 128;
         ln.L = cls < kNumCaps ? layout_of(cls, tmax, full, worst_m)
                               : make_layout(opts->beam_width, V, tmax, full, smem_budget, 0, worst_m, 4);
         ln.per_sm = per_sm_of(ln.L.smem_bytes, ln.threads);
+        }
         ln.slots = std::min(ln.count, d->n_sm * ln.per_sm);
         const u64 budget = 16ull << 30;            // keep the HBM workspace bounded
         if (static_cast<u64>(ln.slots) * ln.L.gws_bytes > budget)
@@ -1018,13 +1053,14 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
         BA.next = d_next + qi;
         BA.gws = d->d_ws.as<u8>() + ws_off[qi];
         ++qi;
-        rc = launch_beam(d, BA, ln.slots, ln.cls < kNumCaps, ln.per_sm, ln.threads, cs);
+        rc = launch_beam(d, BA, ln.slots, ln.cls < kNumCaps, ln.per_sm, ln.threads, cs, ln.v5);
         if (rc) return rc;
         d->tm.launches += 1;
         if (ln.cls < kNumCaps || launches.size() == 1) {
             d->tm.cap_candidates = static_cast<int>(ln.L.cap_s);
             d->tm.cta_threads = ln.threads;
             d->tm.cta_slots = ln.slots;
+            d->tm.kernel_variant = ln.v5 ? 2 : (ln.cls < kNumCaps ? 1 : 0);
         }
         if (cs != st) {
             CUDA_OK(cudaEventRecord(d->cls_done[ln.cls < kNumCaps ? 0 : 1], cs));

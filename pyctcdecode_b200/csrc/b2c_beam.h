@@ -326,8 +326,9 @@ B2C_HDN double b2c_sum_log_scores_ool(double s1, double s2) { return b2c_sum_log
 // BPE only: who consumes force_next_break (decoder.py:442,474-482); contains two block barriers
 B2C_HDN void b2c_bpe_force(const B2cTok* toks, const u16* tk_id, int K, const u16* last_tok, u32 n, u32* ffirst, u8* fall,
                            u32* force_break) {
+    // tk_id == nullptr: `toks` is already the frame's token list (staged records of the fast kernel)
     B2C_FOR(k, K) {
-        const B2cTok ti = toks[tk_id[k]];
+        const B2cTok ti = toks[tk_id ? tk_id[k] : k];
         u32 first = B2C_NONE_U32;
         if (!(ti.flags & B2C_TF_BLANK)) {
             for (u32 b = 0; b < n; ++b)
@@ -339,7 +340,7 @@ B2C_HDN void b2c_bpe_force(const B2cTok* toks, const u16* tk_id, int K, const u1
     B2C_LEADER {
         u32 F = *force_break;
         for (int k = 0; k < K; ++k) {
-            const u16 fl = toks[tk_id[k]].flags;
+            const u16 fl = toks[tk_id ? tk_id[k] : k].flags;
             const u32 first = ffirst[k];
             u8 all = 0;
             u32 one = B2C_NONE_U32;

@@ -1,0 +1,639 @@
+// b200ctc -- latency-first variant of the per-utterance prefix beam search for beam_width <= WC
+// (same algorithm and the same results as b2c_beam.h, which stays the general path).
+//
+// A C2-shaped batch (256 utterances x 1000 frames on 148 SMs) keeps every utterance resident, so the
+// batch takes exactly as long as ONE utterance: T dependent frames.  What bounds it is the latency
+// of a frame, not throughput.  Compared with the general kernel this variant therefore
+//   * uses a compile-time shared-memory layout (B2cFastSmem): every array address is
+//     base + constant, no descriptor of generic pointers lives in registers or local memory;
+//   * stages the token list of frame t+1 (ids, log-probs AND the per-label records) in shared
+//     memory while frame t runs (two-deep register pipeline), so no global load is on the
+//     critical path of a frame;
+//   * enumerates candidates as (token k outer, beam b = thread inner): no index division, the
+//     token record is a warp-uniform shared-memory broadcast;
+//   * stores each candidate's own logit sum and (beam, token) pair, so the fold / fusion / commit
+//     phases never re-derive them;
+//   * probes the grouping table with the low bits of the (already avalanche-mixed) merge key, over
+//     the full table (load <= 0.5 at capacity, ~0.06 typically);
+//   * clears grouping / history-prune slots by their owners instead of sweeping the tables.
+// Frames with more than CAP candidates (or more than B2C_FAST_KS tokens) are rare on ASR-like
+// posteriors; they take the general out-of-line step on the HBM candidate tier (b2c_fast_slow_step).
+//
+// Reference lines restated: decoder.py:443-554 (frame loop), :211-224 (merge), :346-424 (LM
+// fusion), :545-554 (threshold, top-N, history prune).  Order-dependence notes: b2c_beam.h.
+#pragma once
+#include "b2c_beam.h"
+
+#define B2C_FAST_KS 32          // staged tokens per frame
+#define B2C_FAST_NT 128         // threads per CTA
+#define B2C_FAST_NW (B2C_FAST_NT / 32)
+
+#if defined(__CUDA_ARCH__)
+#define B2C_LAST_THREAD if (threadIdx.x == blockDim.x - 1)
+#else
+#define B2C_LAST_THREAD if (true)
+#endif
+
+constexpr u32 b2c_pt_cap_c(int W) {
+    u32 p = 16;
+    while (p < 2u * static_cast<u32>(W)) p <<= 1;
+    return p;
+}
+
+template <int WC>
+struct B2cFastTab {          // one beam table (same fields as B2cBeamTab)
+    double logit[WC], lm_hw[WC], pscore[WC];
+    u64 text_hash[WC], part_hash[WC], hist_hash[WC];
+    u32 text_node[WC], chain[WC];
+    int pf_s[WC], pf_e[WC];
+    u16 last_tok[WC], part_len[WC];
+};
+
+template <int WC, int CAP>
+struct B2cFastSmem {
+    static constexpr u32 HT = 2u * CAP;               // grouping table slots
+    static constexpr u32 PT = b2c_pt_cap_c(WC);        // history-prune table slots
+    B2cScalars sc;
+    u32 ticket;                                       // work-queue ticket of this CTA
+    u32 pad_[(128 - sizeof(B2cScalars) - 4) / 4];
+    B2cFastTab<WC> tab[2];
+    // selection
+    u64 phk[WC];
+    u32 ord[WC], pslot[WC];
+    u32 pt_idx[PT], pt_min[PT];
+    u32 bcnt[B2C_NBUCKET], bhead[B2C_NBUCKET];
+    u32 bpre[B2C_FAST_NW][B2C_NBUCKET];
+    // candidates
+    u64 ckey[CAP];           // merge key; after phase B: order-preserving score key of group leaders, 0 otherwise
+    double cfold[CAP];       // phase A: own logit sum; after phase B (leaders): merged logit_score
+    u64 cph[CAP];            // partial-word hash | branch type << 61
+    u32 cmeta[CAP];          // partial length | canonical token << 16
+    u32 cslot[CAP], cnext[CAP], clast[CAP];
+    u32 cbk[CAP];            // beam | token index << 16
+    u32 ht_idx[HT], ht_min[HT], ht_max[HT], ht_cnt[HT];
+    // staged token lists of the current / next frame
+    B2cTok stok[2][B2C_FAST_KS];
+    double slp[2][B2C_FAST_KS];
+    u16 sid[2][B2C_FAST_KS];
+    u32 ffirst[B2C_FAST_KS];     // BPE force_next_break side arrays
+    u8 fall[B2C_FAST_KS];
+};
+
+template <int WC>
+B2C_HD void b2c_fast_tab_view(B2cFastTab<WC>& t, B2cBeamTab& v) {
+    v.logit = t.logit; v.lm_hw = t.lm_hw; v.pscore = t.pscore;
+    v.text_hash = t.text_hash; v.part_hash = t.part_hash; v.hist_hash = t.hist_hash;
+    v.text_node = t.text_node; v.chain = t.chain;
+    v.pf_s = t.pf_s; v.pf_e = t.pf_e;
+    v.last_tok = t.last_tok; v.part_len = t.part_len;
+}
+
+// descriptor for the general helpers (b2c_utt_begin, b2c_finalize, the out-of-line slow step);
+// `slow`: hide the shared-memory tier so that the general frame step works on the HBM tier
+template <int WC, int CAP>
+B2C_HD void b2c_fast_work(B2cFastSmem<WC, CAP>& S, const B2cLayout& L, u8* g, int par, bool slow, B2cWork& W) {
+    W.sc = &S.sc;
+    b2c_fast_tab_view(S.tab[par], W.cur);
+    b2c_fast_tab_view(S.tab[par ^ 1], W.nxt);
+    W.phk = S.phk; W.ord = S.ord; W.pslot = S.pslot;
+    W.pt_cap = B2cFastSmem<WC, CAP>::PT;
+    W.pt_idx = S.pt_idx; W.pt_min = S.pt_min;
+    W.bcnt = S.bcnt; W.bhead = S.bhead; W.bpre = &S.bpre[0][0];
+    B2cCandTier& c = W.tier_s;
+    c.cap = slow ? 0u : static_cast<u32>(CAP);
+    c.ht_cap = B2cFastSmem<WC, CAP>::HT;
+    c.ckey = S.ckey; c.cfold = S.cfold; c.cth = nullptr; c.cph = S.cph;
+    c.cmeta = S.cmeta; c.cslot = S.cslot; c.cnext = S.cnext; c.clast = S.clast;
+    c.ht_idx = S.ht_idx; c.ht_min = S.ht_min; c.ht_max = S.ht_max; c.ht_cnt = S.ht_cnt;
+    if (L.cap_g) b2c_carve_tier(g + L.g_tier, L.cap_g, L.ht_g, W.tier_g);
+    else W.tier_g = W.tier_s;
+    {
+        u8* p = g + L.g_tk;
+        W.tk_ffirst = reinterpret_cast<u32*>(b2c_carve(p, 4ull * L.V));
+        W.tk_fall = reinterpret_cast<u8*>(b2c_carve(p, static_cast<u64>(L.V)));
+    }
+    W.chain = reinterpret_cast<B2cChain*>(g + L.g_chain);
+    W.chain_cap = L.chain_cap;
+    W.text = reinterpret_cast<B2cText*>(g + L.g_text);
+    W.text_cap = L.text_cap;
+#if defined(B2C_PHASE_CLOCKS)
+    for (int q = 0; q < 16; ++q) W.clk[q] = 0;
+    W.clk_last = 0;
+#endif
+}
+
+B2C_HD void b2c_warp_max_u64_to(u64 v, u64* target) {
+#if defined(__CUDA_ARCH__)
+    const u32 hi = static_cast<u32>(v >> 32), lo = static_cast<u32>(v);
+    const u32 mhi = __reduce_max_sync(0xFFFFFFFFu, hi);
+    const u32 mlo = __reduce_max_sync(0xFFFFFFFFu, hi == mhi ? lo : 0u);
+    if ((threadIdx.x & 31) == 0) {
+        const u64 m = (static_cast<u64>(mhi) << 32) | mlo;
+        if (m) atomicMax(target, m);
+    }
+#else
+    if (v > *target) *target = v;
+#endif
+}
+B2C_HD void b2c_warp_max_u32_to(u32 v, u32* target) {
+#if defined(__CUDA_ARCH__)
+    const u32 m = __reduce_max_sync(0xFFFFFFFFu, v);
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(target, m);
+#else
+    if (v > *target) *target = v;
+#endif
+}
+
+#if defined(B2C_PHASE_CLOCKS) && defined(__CUDA_ARCH__)
+#define B2C_FMARK(idx) do { if (threadIdx.x == 0) { const long long _c = clock64(); clk[idx] += static_cast<u64>(_c - clk_last); clk_last = _c; } } while (0)
+#else
+#define B2C_FMARK(idx) ((void)0)
+#endif
+
+// one new beam: rank r of this frame becomes beam j of the next frame (decoder.py:452-534 metadata)
+template <int WC, int CAP>
+B2C_HD void b2c_fast_commit(const B2cParams& P, B2cFastSmem<WC, CAP>& S, const B2cFastTab<WC>& cur, B2cFastTab<WC>& nx,
+                            B2cChain* chain_arena, u32 chain_cap, B2cText* text_arena, u32 text_cap, int sb, int t, u32 j, u32 r,
+                            u32 flags) {
+    const u32 i = S.ord[r];
+    const u32 last = S.clast[i];
+    const u32 bk = S.cbk[last];
+    const u32 bl = bk & 0xFFFFu, k = bk >> 16;
+    const u64 cph = S.cph[last];
+    const u32 type = static_cast<u32>(cph >> 61);
+    const u64 part_hash = cph & B2C_PH_MASK;
+    const u32 meta = S.cmeta[last];
+    const u32 part_len = meta & 0xFFFFu;
+    const u32 word_len = (type == 1 || type == 2) ? static_cast<u32>(cur.part_len[bl]) : 0u;
+    u64 th = cur.text_hash[bl];
+    if (word_len > 0) th = b2c_text_append(th, cur.part_hash[bl]);
+    nx.logit[j] = S.cfold[i];
+    nx.text_hash[j] = th;
+    nx.part_hash[j] = part_hash;
+    nx.part_len[j] = static_cast<u16>(part_len);
+    nx.last_tok[j] = static_cast<u16>(meta >> 16);
+    // partial_frames (decoder.py:454-461,495,513,519-523)
+    const int ps0 = cur.pf_s[bl], pe0 = cur.pf_e[bl];
+    int pfs, pfe;
+    if (type == 0) { pfs = ps0; pfe = (S.stok[sb][k].flags & B2C_TF_BLANK) ? pe0 : t + 1; }
+    else if (type == 1) { pfs = t; pfe = t + 1; }
+    else if (type == 2) { pfs = -1; pfe = -1; }
+    else { pfs = ps0 < 0 ? t : ps0; pfe = t + 1; }
+    nx.pf_s[j] = pfs;
+    nx.pf_e[j] = pfe;
+    // backtrack chain
+    u32 chain = cur.chain[bl];
+    if (type != 0) {
+        const u32 id = b2c_atomic_add_u32(&S.sc.chain_used, 1u);
+        if (id < chain_cap) {
+            B2cChain c;
+            c.parent = chain;
+            c.tok = S.sid[sb][k];
+            c.kind = type == 3 ? B2C_CK_CONT : (type == 2 ? B2C_CK_SPACE : B2C_CK_BPE);
+            c.has_word = word_len > 0 ? 1 : 0;
+            c.ws = ps0;
+            c.we = pe0;
+            chain_arena[id] = c;
+            chain = id;
+        } else {
+            b2c_atomic_or_u32(&S.sc.status, B2C_ERR_CHAIN_FULL);
+        }
+    }
+    nx.chain[j] = chain;
+    // text level
+    u32 tnode = cur.text_node[bl];
+    double lm_hw = cur.lm_hw[bl];
+    u64 hh = cur.hist_hash[bl];
+    if (word_len > 0) {
+        B2cTextCommit tc;
+        b2c_commit_text(P, text_arena, text_cap, &S.sc.text_used, &S.sc.status, tnode, cur.part_hash[bl], word_len, &tc);
+        tnode = tc.node;
+        lm_hw = tc.lm_hw;
+        hh = tc.hist_hash;
+    }
+    nx.text_node[j] = tnode;
+    nx.lm_hw[j] = lm_hw;
+    nx.hist_hash[j] = hh;
+    double ps = 0.0;
+    if (type == 0) ps = cur.pscore[bl];
+    else if (part_len > 0) ps = b2c_partial_score_of(P, (flags & B2C_FL_PSCORE) != 0, part_hash, part_len);
+    nx.pscore[j] = ps;
+}
+
+// -----------------------------------------------------------------------------------------
+// one frame with at most CAP candidates and at most B2C_FAST_KS tokens, all in shared memory.
+// On entry: grouping table, score buckets and max_key are clear; the history-prune table holds
+// exactly the entries pslot[0 .. n_sel) of the previous frame.  The caller issues the final block
+// barrier (after it has staged the next frame's tokens).
+// -----------------------------------------------------------------------------------------
+template <int WC, int CAP>
+B2C_HD void b2c_fast_step(const B2cParams& P, B2cFastSmem<WC, CAP>& S, B2cChain* chain_arena, u32 chain_cap, B2cText* text_arena,
+                          u32 text_cap, int par, int t, int sb, int K
+#if defined(B2C_PHASE_CLOCKS)
+                          , u64* clk, long long& clk_last
+#endif
+) {
+    typedef B2cFastSmem<WC, CAP> SM;
+    const B2cFastTab<WC>& cur = S.tab[par];
+    B2cFastTab<WC>& nx = S.tab[par ^ 1];
+    const u32 n = S.sc.n_beams;
+    const u32 M = n * static_cast<u32>(K);
+    const u32 flags = S.sc.flags;
+    const bool is_bpe = (flags & B2C_FL_BPE) != 0, prune = (flags & B2C_FL_PRUNE) != 0;
+    const double ref = S.sc.prev_max;
+    const double bscale = P.bucket_scale;
+    constexpr u32 hmask = SM::HT - 1, ptmask = SM::PT - 1;
+    B2C_FMARK(0);
+
+    if (is_bpe) b2c_bpe_force(S.stok[sb], nullptr, K, cur.last_tok, n, S.ffirst, S.fall, &S.sc.force_break);
+
+    // ---- phase A: expand (decoder.py:447-534), merge key, grouping ---------------------------------
+    if (prune) {
+        B2C_FOR(r, S.sc.n_sel) {
+            const u32 s = S.pslot[r];
+            S.pt_idx[s] = B2C_NONE_U32;
+            S.pt_min[s] = B2C_NONE_U32;
+        }
+    }
+    for (int k = 0; k < K; ++k) {
+        const B2cTok ti = S.stok[sb][k];
+        const double lp = S.slp[sb][k];
+        const u32 f_all = is_bpe ? static_cast<u32>(S.fall[k]) : 0u;
+        const u32 f_one = is_bpe ? S.ffirst[k] : B2C_NONE_U32;
+        B2C_FOR(b, n) {
+            const u32 i = static_cast<u32>(k) * n + static_cast<u32>(b);
+            const u32 plen = cur.part_len[b];
+            const u64 ph = cur.part_hash[b];
+            u64 th = cur.text_hash[b];
+            u64 nph;
+            u32 nplen, type;
+            if ((ti.flags & B2C_TF_BLANK) || cur.last_tok[b] == ti.canon) {                                      // (i)
+                type = 0; nph = ph; nplen = plen;
+            } else if (is_bpe && ((ti.flags & B2C_TF_BPE_LEAD) || f_all || f_one == static_cast<u32>(b))) {      // (ii)
+                type = 1; nph = ti.clean_hash; nplen = ti.clean_nchars;
+                if (plen) th = b2c_text_append(th, ph);
+            } else if (!is_bpe && (ti.flags & B2C_TF_SPACE)) {                                                   // (iii)
+                type = 2; nph = 0; nplen = 0;
+                if (plen) th = b2c_text_append(th, ph);
+            } else {                                                                                             // (iv)
+                type = 3; nph = b2c_hash_append(ph, ti.raw_hash, ti.raw_pow); nplen = plen + ti.raw_nchars;
+            }
+            S.cph[i] = nph | (static_cast<u64>(type) << 61);
+            S.cmeta[i] = (nplen & 0xFFFFu) | (static_cast<u32>(ti.canon) << 16);
+            S.cbk[i] = static_cast<u32>(b) | (static_cast<u32>(k) << 16);
+            S.cfold[i] = cur.logit[b] + lp;
+            const u64 key = b2c_beam_key(th, nph, nplen, ti.canon);
+            S.ckey[i] = key;
+            b2c_fence_block();
+            // group equal keys: claim a slot or join the group that owns it (the key is already mixed)
+            u32 slot = static_cast<u32>(key) & hmask;
+            while (true) {
+                const u32 rep = b2c_atomic_cas_u32(&S.ht_idx[slot], B2C_NONE_U32, i);
+                if (rep == B2C_NONE_U32) break;
+                b2c_fence_block();
+                if (S.ckey[rep] == key) break;
+                slot = (slot + 1) & hmask;
+            }
+            S.cslot[i] = slot;
+            b2c_atomic_min_u32(&S.ht_min[slot], i);
+            b2c_atomic_max_u32(&S.ht_max[slot], i);
+            b2c_atomic_add_u32(&S.ht_cnt[slot], 1u);
+        }
+    }
+    B2C_SYNC();
+    B2C_FMARK(1);
+
+    // ---- phase B: fold each group (decoder.py:211-224), LM / hotword fusion (:346-424), bucket, max ---
+    B2C_LAST_THREAD { S.sc.n_sel = 0; }
+    {
+        u64 tmax = 0;
+        B2C_FOR(i, M) {
+            const u32 slot = S.cslot[i];
+            if (S.ht_min[slot] != static_cast<u32>(i)) { S.ckey[i] = 0; continue; }
+            const u32 last = S.ht_max[slot], cnt = S.ht_cnt[slot];
+            double s = S.cfold[i];
+            for (u32 j = (cnt == 2) ? last : static_cast<u32>(i) + 1; cnt > 1 && j <= last; ++j) {
+                if (S.cslot[j] != slot) continue;
+                s = b2c_sum_log_scores_ool(s, S.cfold[j]);
+            }
+            S.cfold[i] = s;
+            S.clast[i] = last;
+            const u64 cph = S.cph[last];
+            const u32 type = static_cast<u32>(cph >> 61);
+            const u32 part_len = S.cmeta[last] & 0xFFFFu;
+            const u32 bl = S.cbk[last] & 0xFFFFu;
+            double lm_hw = cur.lm_hw[bl];
+            if ((type == 1 || type == 2) && cur.part_len[bl] > 0) {
+                B2cTextNew tn;
+                b2c_text_extend(P, text_arena + cur.text_node[bl], cur.part_hash[bl], cur.part_len[bl], 0, &tn);
+                lm_hw = tn.lm_hw;
+            }
+            double ps = 0.0;
+            if (type == 0) ps = cur.pscore[bl];
+            else if (part_len > 0) ps = b2c_partial_score_of(P, (flags & B2C_FL_PSCORE) != 0, cph & B2C_PH_MASK, part_len);
+            const double sco = b2c_combine_score((flags & B2C_FL_LM) != 0, s, lm_hw, ps, part_len);
+            const u64 key = b2c_f64_key(sco);
+            S.ckey[i] = key;
+            const u32 bkt = b2c_bucket(ref, sco, bscale);
+            b2c_atomic_add_u32(&S.bcnt[bkt], 1u);
+#if defined(__CUDA_ARCH__)
+            S.cnext[i] = atomicExch(&S.bhead[bkt], static_cast<u32>(i));
+#else
+            S.cnext[i] = S.bhead[bkt];
+            S.bhead[bkt] = static_cast<u32>(i);
+#endif
+            if (key > tmax) tmax = key;
+        }
+        b2c_warp_max_u64_to(tmax, &S.sc.max_key);
+    }
+    B2C_SYNC();
+    B2C_FMARK(2);
+
+    // ---- phase C: threshold (:545-546), stable top-N (:548): rank = bucket prefix + order inside the
+    //      bucket; history keys of the selected go to the prune table; grouping slots are released ----
+    u32* const bpre = S.bpre[b2c_warp_id()];
+    b2c_bucket_scan_warp(S.bcnt, bpre);
+    const double max_score = b2c_key_f64(S.sc.max_key);
+    const double thr = max_score + P.prune_logp;
+    const u32 width = static_cast<u32>(P.beam_width);
+    {
+        u32 my_top = 0;
+        B2C_FOR(i, M) {
+            const u64 key = S.ckey[i];
+            {
+                const u32 slot = S.cslot[i];
+                S.ht_idx[slot] = B2C_NONE_U32;
+                S.ht_min[slot] = B2C_NONE_U32;
+                S.ht_max[slot] = 0;
+                S.ht_cnt[slot] = 0;
+            }
+            if (key == 0) continue;
+            const double sco = b2c_key_f64(key);
+            if (!(sco >= thr)) continue;
+            const u32 bkt = b2c_bucket(ref, sco, bscale);
+            u32 rank = bpre[bkt];
+            for (u32 j = S.bhead[bkt]; j != B2C_NONE_U32; j = S.cnext[j]) {
+                if (j == static_cast<u32>(i)) continue;
+                const u64 kj = S.ckey[j];
+                rank += (kj > key || (kj == key && j < static_cast<u32>(i))) ? 1u : 0u;
+            }
+            if (rank >= width) continue;
+            S.ord[rank] = static_cast<u32>(i);
+            if (rank + 1 > my_top) my_top = rank + 1;
+            if (prune) {
+                const u32 last = S.clast[i];
+                const u32 bl = S.cbk[last] & 0xFFFFu;
+                const u64 cph = S.cph[last];
+                const u32 type = static_cast<u32>(cph >> 61);
+                const u32 meta = S.cmeta[last];
+                u64 hh = cur.hist_hash[bl];
+                if ((type == 1 || type == 2) && cur.part_len[bl] > 0)
+                    hh = b2c_hist_extend(text_arena + cur.text_node[bl], P.hist_n, cur.part_hash[bl]);
+                const u64 hk = b2c_beam_key(hh, cph & B2C_PH_MASK, meta & 0xFFFFu, meta >> 16);
+                S.phk[rank] = hk;
+                b2c_fence_block();
+                u32 slot = static_cast<u32>(hk) & ptmask;
+                while (true) {
+                    const u32 rep = b2c_atomic_cas_u32(&S.pt_idx[slot], B2C_NONE_U32, rank);
+                    if (rep == B2C_NONE_U32) break;
+                    b2c_fence_block();
+                    if (S.phk[rep] == hk) break;
+                    slot = (slot + 1) & ptmask;
+                }
+                S.pslot[rank] = slot;
+                b2c_atomic_min_u32(&S.pt_min[slot], rank);
+            }
+        }
+        b2c_warp_max_u32_to(my_top, &S.sc.n_sel);      // the selected ranks are exactly 0 .. n_sel-1
+    }
+    B2C_SYNC();
+    B2C_FMARK(3);
+
+    // ---- phase D: history prune (:550-552) = keep the best rank of every key, compact, commit ------
+    const u32 nsel = S.sc.n_sel;
+    u32 n_new = 0;
+#if defined(__CUDA_ARCH__)
+    {
+        const u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        const u32 lt = (1u << lane) - 1u;
+        for (u32 blk = 0; blk * 32 < nsel; ++blk) {
+            const u32 r = blk * 32 + lane;
+            const bool kept = r < nsel && (!prune || S.pt_min[S.pslot[r]] == r);
+            const u32 mask = __ballot_sync(0xFFFFFFFFu, kept);
+            if (kept && (blk % B2C_FAST_NW) == w)
+                b2c_fast_commit(P, S, cur, nx, chain_arena, chain_cap, text_arena, text_cap, sb, t, n_new + __popc(mask & lt), r, flags);
+            n_new += __popc(mask);
+        }
+    }
+#else
+    for (u32 r = 0; r < nsel; ++r) {
+        const bool kept = !prune || S.pt_min[S.pslot[r]] == r;
+        if (kept) b2c_fast_commit(P, S, cur, nx, chain_arena, chain_cap, text_arena, text_cap, sb, t, n_new++, r, flags);
+    }
+#endif
+    B2C_FOR(s, B2C_NBUCKET) { S.bcnt[s] = 0; S.bhead[s] = B2C_NONE_U32; }
+    B2C_LAST_THREAD {
+        S.sc.n_beams = n_new;
+        S.sc.prev_max = max_score;
+        S.sc.max_key = 0;
+    }
+    B2C_FMARK(4);
+}
+
+// A frame that does not fit the shared-memory tier (or the token stage): the general step on the
+// HBM tier, out of line, with its own descriptor.  Restores the invariants of b2c_fast_step.
+template <int WC, int CAP>
+B2C_HDN void b2c_fast_slow_step(B2cParams P, B2cLayout L, u8* smem, u8* g, int par, int t, const u16* tk_id, const double* tk_lp,
+                                int K, int K_next) {
+    B2cFastSmem<WC, CAP>& S = *reinterpret_cast<B2cFastSmem<WC, CAP>*>(smem);
+    B2cWork W;
+    b2c_fast_work(S, L, g, par, true, W);
+    const u32 M = S.sc.n_beams * static_cast<u32>(K);
+    const B2cCandTier C = W.tier_g;
+    u32 H = b2c_ht_size(M);
+    if (H > C.ht_cap) H = C.ht_cap;
+    b2c_clear_tables(W, C, H);
+    B2C_SYNC();
+    b2c_frame_step<false>(P, W, t, tk_id, tk_lp, K, K_next);      // ends with a block barrier
+    B2C_LEADER { S.sc.max_key = 0; }
+}
+
+// -----------------------------------------------------------------------------------------
+// one CTA: utterances from the work queue, all frames, finalisation
+// -----------------------------------------------------------------------------------------
+template <int WC, int CAP>
+B2C_HD void b2c_beam_block_fast(const B2cBeamArgs& A, int slot, u8* smem) {
+    typedef B2cFastSmem<WC, CAP> SM;
+    SM& S = *reinterpret_cast<SM*>(smem);
+    const B2cLayout& L = A.L;
+    u8* g = A.gws + static_cast<u64>(slot) * L.gws_bytes;
+    B2cChain* const chain_arena = reinterpret_cast<B2cChain*>(g + L.g_chain);
+    B2cText* const text_arena = reinterpret_cast<B2cText*>(g + L.g_text);
+    const u32 chain_cap = L.chain_cap, text_cap = L.text_cap;
+    const int V = A.P.V;
+    u32 st_over[6] = {0, 0, 0, 0, 0, 0};    // candidate-count histogram of the fast frames (last thread's copy counts)
+    u32 st_frames = 0;
+    B2C_LEADER {
+        for (int q = 0; q < 6; ++q) S.sc.m_over[q] = 0;
+        S.sc.m_frames = 0;
+    }
+#if defined(B2C_PHASE_CLOCKS)
+    u64 clk[16];
+    for (int q = 0; q < 16; ++q) clk[q] = 0;
+    long long clk_last = 0;
+#if defined(__CUDA_ARCH__)
+    clk_last = clock64();
+#endif
+#endif
+
+    while (true) {
+        B2C_LEADER { S.ticket = b2c_atomic_add_u32(A.next, 1u); }
+        B2C_SYNC();
+        const u32 q = S.ticket;
+        if (q >= static_cast<u32>(A.n_utts)) break;
+        const int u = A.order[q];
+        const int Tn = A.T[u];
+        const u64 f0 = A.frame_off[u];
+        const B2cFrameRec* recs = A.tok_rec + f0;
+        B2cFrameRec rA, rB, rC;
+        rA.off = rB.off = rC.off = 0;
+        rA.cnt = rB.cnt = rC.cnt = 1;
+        if (Tn > 0) rA = recs[0];
+        if (Tn > 1) rB = recs[1];
+        if (Tn > 2) rC = recs[2];
+        {
+            B2cWork W;
+            b2c_fast_work(S, L, g, 0, false, W);
+            b2c_utt_begin(A.P, W, A.start_states ? A.start_states + u : nullptr, static_cast<int>(rA.cnt));
+        }
+        B2C_FOR(s, SM::HT) {
+            S.ht_idx[s] = B2C_NONE_U32;
+            S.ht_min[s] = B2C_NONE_U32;
+            S.ht_max[s] = 0;
+            S.ht_cnt[s] = 0;
+        }
+        B2C_FOR(s, SM::PT) { S.pt_idx[s] = B2C_NONE_U32; S.pt_min[s] = B2C_NONE_U32; }
+        B2C_FOR(s, B2C_NBUCKET) { S.bcnt[s] = 0; S.bhead[s] = B2C_NONE_U32; }
+        B2C_LEADER { S.sc.n_sel = 0; S.sc.max_key = 0; }
+        // stage the tokens of frame 0 (once per utterance, latency exposed)
+        if (Tn > 0) {
+            const u64 base0 = f0 * static_cast<u64>(V) + rA.off;
+            const u32 k0 = rA.cnt < B2C_FAST_KS ? rA.cnt : B2C_FAST_KS;
+            B2C_FOR(c, k0) {
+                const u16 id = A.tok_ids[base0 + c];
+                S.stok[0][c] = A.P.toks[id];
+                S.slp[0][c] = A.tok_lp[base0 + c];
+                S.sid[0][c] = id;
+            }
+        }
+#if defined(__CUDA_ARCH__)
+        // register pipeline: token `threadIdx.x` of frame t+1 (id, log-prob) is loaded one frame ahead of
+        // its label record, which is loaded one frame ahead of the shared-memory store
+        u16 pid_b = 0;
+        double plp_b = 0.0;
+        if (Tn > 1 && threadIdx.x < (rB.cnt < B2C_FAST_KS ? rB.cnt : B2C_FAST_KS)) {
+            const u64 base1 = (f0 + static_cast<u64>(1 & ~(B2C_RUN - 1))) * static_cast<u64>(V) + rB.off;
+            pid_b = A.tok_ids[base1 + threadIdx.x];
+            plp_b = A.tok_lp[base1 + threadIdx.x];
+        }
+#endif
+        B2C_SYNC();
+        int par = 0;
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+        for (int t = 0; t < Tn; ++t) {
+            B2cFrameRec rD;
+            rD.off = 0;
+            rD.cnt = 1;
+            if (t + 3 < Tn) rD = recs[t + 3];
+            const int K = static_cast<int>(rA.cnt);
+            const int sb = t & 1;
+            const u32 kb = (t + 1 < Tn) ? (rB.cnt < B2C_FAST_KS ? rB.cnt : B2C_FAST_KS) : 0u;
+            const u64 base_b = (f0 + static_cast<u64>((t + 1) & ~(B2C_RUN - 1))) * static_cast<u64>(V) + rB.off;
+#if defined(__CUDA_ARCH__)
+            B2cTok ptk;
+            const bool has_b = threadIdx.x < kb;
+            if (has_b) ptk = A.P.toks[pid_b];
+            u16 pid_c = 0;
+            double plp_c = 0.0;
+            if (t + 2 < Tn && threadIdx.x < (rC.cnt < B2C_FAST_KS ? rC.cnt : B2C_FAST_KS)) {
+                const u64 base_c = (f0 + static_cast<u64>((t + 2) & ~(B2C_RUN - 1))) * static_cast<u64>(V) + rC.off;
+                pid_c = A.tok_ids[base_c + threadIdx.x];
+                plp_c = A.tok_lp[base_c + threadIdx.x];
+            }
+#endif
+            const u32 Mq = S.sc.n_beams * static_cast<u32>(K);
+            if (Mq > static_cast<u32>(CAP) || K > B2C_FAST_KS) {
+                const u64 base_a = (f0 + static_cast<u64>(t & ~(B2C_RUN - 1))) * static_cast<u64>(V) + rA.off;
+                b2c_fast_slow_step<WC, CAP>(A.P, L, smem, g, par, t, A.tok_ids + base_a, A.tok_lp + base_a, K, static_cast<int>(rB.cnt));
+            } else {
+                B2C_LAST_THREAD {
+                    ++st_frames;
+                    for (int c = 0; c < 6; ++c) st_over[c] += (Mq > (128u << c)) ? 1u : 0u;
+                }
+#if defined(B2C_PHASE_CLOCKS)
+                b2c_fast_step<WC, CAP>(A.P, S, chain_arena, chain_cap, text_arena, text_cap, par, t, sb, K, clk, clk_last);
+#else
+                b2c_fast_step<WC, CAP>(A.P, S, chain_arena, chain_cap, text_arena, text_cap, par, t, sb, K);
+#endif
+            }
+            // stage the tokens of frame t+1
+#if defined(__CUDA_ARCH__)
+            if (has_b) {
+                S.stok[sb ^ 1][threadIdx.x] = ptk;
+                S.slp[sb ^ 1][threadIdx.x] = plp_b;
+                S.sid[sb ^ 1][threadIdx.x] = pid_b;
+            }
+            pid_b = pid_c;
+            plp_b = plp_c;
+#else
+            B2C_FOR(c, kb) {
+                const u16 id = A.tok_ids[base_b + c];
+                S.stok[sb ^ 1][c] = A.P.toks[id];
+                S.slp[sb ^ 1][c] = A.tok_lp[base_b + c];
+                S.sid[sb ^ 1][c] = id;
+            }
+#endif
+            (void)base_b;
+            B2C_SYNC();
+            par ^= 1;
+            rA = rB;
+            rB = rC;
+            rC = rD;
+        }
+        B2cOut O;
+        const u64 ob = static_cast<u64>(A.P.out_beams);
+        O.n_beams = A.out_nbeams + u;
+        O.status = A.out_status + u;
+        O.scores = A.out_scores + static_cast<u64>(u) * ob * 2;
+        O.n_tok = A.out_ntok + static_cast<u64>(u) * ob;
+        O.n_words = A.out_nwords + static_cast<u64>(u) * ob;
+        O.stride = static_cast<u32>(Tn) + 1;
+        O.toks = A.out_toks + ob * (f0 + static_cast<u64>(u));
+        O.frames = A.out_frames + 2 * ob * (f0 + static_cast<u64>(u));
+        O.states = A.out_states + static_cast<u64>(u) * ob;
+        {
+            B2cWork W;
+            b2c_fast_work(S, L, g, par, false, W);
+            b2c_finalize(A.P, W, O);
+        }
+        B2C_FMARK(8);
+    }
+    if (A.m_stats) {
+        B2C_LAST_THREAD {
+            for (int c = 0; c < 6; ++c)
+                if (st_over[c]) b2c_atomic_add_u32(A.m_stats + c, st_over[c]);
+            if (st_frames) b2c_atomic_add_u32(A.m_stats + 6, st_frames);
+        }
+        B2C_LEADER {   // frames that took the general step counted themselves in shared memory
+            for (int c = 0; c < 6; ++c)
+                if (S.sc.m_over[c]) b2c_atomic_add_u32(A.m_stats + c, S.sc.m_over[c]);
+            if (S.sc.m_frames) b2c_atomic_add_u32(A.m_stats + 6, S.sc.m_frames);
+        }
+    }
+#if defined(B2C_PHASE_CLOCKS) && defined(__CUDA_ARCH__)
+    if (threadIdx.x == 0 && A.phase_clk)
+        for (int c = 0; c < 16; ++c) atomicAdd(A.phase_clk + c, clk[c]);
+#endif
+}
