@@ -25,7 +25,9 @@
 #include "b2c_beam.h"
 
 #define B2C_FAST_KS 32          // staged tokens per frame
+#ifndef B2C_FAST_NT
 #define B2C_FAST_NT 128         // threads per CTA
+#endif
 #define B2C_FAST_NW (B2C_FAST_NT / 32)
 
 #if defined(__CUDA_ARCH__)
@@ -55,14 +57,16 @@ struct B2cFastSmem {
     static constexpr u32 PT = b2c_pt_cap_c(WC);        // history-prune table slots
     B2cScalars sc;
     u32 ticket;                                       // work-queue ticket of this CTA
-    u32 pad_[(128 - sizeof(B2cScalars) - 4) / 4];
-    B2cFastTab<WC> tab[2];
+    u32 wtop[B2C_FAST_NW];                            // per warp: 1 + best rank selected this frame
+    alignas(16) u64 wmax[B2C_FAST_NW];                // per warp: best score key of this frame
+    alignas(16) B2cFastTab<WC> tab[2];
     // selection
     u64 phk[WC];
     u32 ord[WC], pslot[WC];
     u32 pt_idx[PT], pt_min[PT];
-    u32 bcnt[B2C_NBUCKET], bhead[B2C_NBUCKET];
-    u32 bpre[B2C_FAST_NW][B2C_NBUCKET];
+    alignas(16) u32 bcnt[B2C_NBUCKET];
+    alignas(16) u32 bhead[B2C_NBUCKET];
+    alignas(16) u32 bpre[B2C_FAST_NW][B2C_NBUCKET];
     // candidates
     u64 ckey[CAP];           // merge key; after phase B: order-preserving score key of group leaders, 0 otherwise
     double cfold[CAP];       // phase A: own logit sum; after phase B (leaders): merged logit_score
@@ -122,25 +126,63 @@ B2C_HD void b2c_fast_work(B2cFastSmem<WC, CAP>& S, const B2cLayout& L, u8* g, in
 #endif
 }
 
-B2C_HD void b2c_warp_max_u64_to(u64 v, u64* target) {
+// per-warp maxima go to the warp's own slot (no atomics); readers combine the slots after the barrier
+B2C_HD void b2c_warp_max_u64_slot(u64 v, u64* slots) {
 #if defined(__CUDA_ARCH__)
     const u32 hi = static_cast<u32>(v >> 32), lo = static_cast<u32>(v);
     const u32 mhi = __reduce_max_sync(0xFFFFFFFFu, hi);
     const u32 mlo = __reduce_max_sync(0xFFFFFFFFu, hi == mhi ? lo : 0u);
-    if ((threadIdx.x & 31) == 0) {
-        const u64 m = (static_cast<u64>(mhi) << 32) | mlo;
-        if (m) atomicMax(target, m);
-    }
+    if ((threadIdx.x & 31) == 0) slots[threadIdx.x >> 5] = (static_cast<u64>(mhi) << 32) | mlo;
 #else
-    if (v > *target) *target = v;
+    slots[0] = v;
 #endif
 }
-B2C_HD void b2c_warp_max_u32_to(u32 v, u32* target) {
+B2C_HD void b2c_warp_max_u32_slot(u32 v, u32* slots) {
 #if defined(__CUDA_ARCH__)
     const u32 m = __reduce_max_sync(0xFFFFFFFFu, v);
-    if ((threadIdx.x & 31) == 0 && m) atomicMax(target, m);
+    if ((threadIdx.x & 31) == 0) slots[threadIdx.x >> 5] = m;
 #else
-    if (v > *target) *target = v;
+    slots[0] = v;
+#endif
+}
+template <class T>
+B2C_HD T b2c_max_slots(const T* s) {
+    T m = s[0];
+#pragma unroll
+    for (int c = 1; c < B2C_FAST_NW; ++c) m = s[c] > m ? s[c] : m;
+    return m;
+}
+
+// merge key without the avalanche round of b2c_beam_key: a multiply-add combination of the (already
+// well-mixed) hashes is collision-free unless a 64-bit linear relation holds; the high half is
+// folded into the low half so that the low bits, which index the tables, depend on every input bit
+B2C_HD u64 b2c_fast_key(u64 text_hash, u64 part_hash, u32 part_len, u32 last_tok) {
+    u64 k = text_hash * 0xD6E8FEB86659FD93ull + part_hash * 0xA24BAED4963EE407ull +
+            (static_cast<u64>(part_len) | ((static_cast<u64>(last_tok) + 1) << 20)) * 0x9FB21C651E98DF25ull;
+    k ^= k >> 32;
+    return k ? k : 1;
+}
+
+// conflict-free variant of b2c_bucket_scan_warp: every lane owns 8 consecutive buckets = two 16-byte words
+B2C_HD void b2c_bucket_scan_warp_v(const u32* bcnt, u32* pre) {
+#if defined(__CUDA_ARCH__)
+    const u32 lane = threadIdx.x & 31;
+    const uint4 a = reinterpret_cast<const uint4*>(bcnt)[2 * lane], b = reinterpret_cast<const uint4*>(bcnt)[2 * lane + 1];
+    const u32 sum = a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
+    u32 incl = sum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const u32 o = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+        if (lane >= static_cast<u32>(off)) incl += o;
+    }
+    uint4 pa, pb;
+    pa.x = incl - sum; pa.y = pa.x + a.x; pa.z = pa.y + a.y; pa.w = pa.z + a.z;
+    pb.x = pa.w + a.w; pb.y = pb.x + b.x; pb.z = pb.y + b.y; pb.w = pb.z + b.z;
+    reinterpret_cast<uint4*>(pre)[2 * lane] = pa;
+    reinterpret_cast<uint4*>(pre)[2 * lane + 1] = pb;
+    __syncwarp();
+#else
+    b2c_bucket_scan_warp(bcnt, pre);
 #endif
 }
 
@@ -154,7 +196,10 @@ B2C_HD void b2c_warp_max_u32_to(u32 v, u32* target) {
 template <int WC, int CAP>
 B2C_HD void b2c_fast_commit(const B2cParams& P, B2cFastSmem<WC, CAP>& S, const B2cFastTab<WC>& cur, B2cFastTab<WC>& nx,
                             B2cChain* chain_arena, u32 chain_cap, B2cText* text_arena, u32 text_cap, int sb, int t, u32 j, u32 r,
-                            u32 flags) {
+                            u32 flags, bool kept) {
+    // device: called by all 32 lanes of a warp (`kept` lanes commit; the others only take part in the
+    // warp-aggregated allocation of backtrack nodes)
+    if (!kept) r = 0;
     const u32 i = S.ord[r];
     const u32 last = S.clast[i];
     const u32 bk = S.cbk[last];
@@ -167,11 +212,6 @@ B2C_HD void b2c_fast_commit(const B2cParams& P, B2cFastSmem<WC, CAP>& S, const B
     const u32 word_len = (type == 1 || type == 2) ? static_cast<u32>(cur.part_len[bl]) : 0u;
     u64 th = cur.text_hash[bl];
     if (word_len > 0) th = b2c_text_append(th, cur.part_hash[bl]);
-    nx.logit[j] = S.cfold[i];
-    nx.text_hash[j] = th;
-    nx.part_hash[j] = part_hash;
-    nx.part_len[j] = static_cast<u16>(part_len);
-    nx.last_tok[j] = static_cast<u16>(meta >> 16);
     // partial_frames (decoder.py:454-461,495,513,519-523)
     const int ps0 = cur.pf_s[bl], pe0 = cur.pf_e[bl];
     int pfs, pfe;
@@ -179,12 +219,34 @@ B2C_HD void b2c_fast_commit(const B2cParams& P, B2cFastSmem<WC, CAP>& S, const B
     else if (type == 1) { pfs = t; pfe = t + 1; }
     else if (type == 2) { pfs = -1; pfe = -1; }
     else { pfs = ps0 < 0 ? t : ps0; pfe = t + 1; }
+    // backtrack chain: one shared-memory atomic per warp
+    u32 chain = cur.chain[bl];
+    const bool emits = kept && type != 0;
+    u32 id = 0;
+#if defined(__CUDA_ARCH__)
+    {
+        const u32 em = __ballot_sync(0xFFFFFFFFu, emits);
+        if (em) {
+            const u32 lane = threadIdx.x & 31;
+            const int leader = __ffs(em) - 1;
+            u32 base = 0;
+            if (static_cast<int>(lane) == leader) base = atomicAdd(&S.sc.chain_used, static_cast<u32>(__popc(em)));
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            id = base + __popc(em & ((1u << lane) - 1u));
+        }
+    }
+#else
+    if (emits) id = b2c_atomic_add_u32(&S.sc.chain_used, 1u);
+#endif
+    if (!kept) return;
+    nx.logit[j] = S.cfold[i];
+    nx.text_hash[j] = th;
+    nx.part_hash[j] = part_hash;
+    nx.part_len[j] = static_cast<u16>(part_len);
+    nx.last_tok[j] = static_cast<u16>(meta >> 16);
     nx.pf_s[j] = pfs;
     nx.pf_e[j] = pfe;
-    // backtrack chain
-    u32 chain = cur.chain[bl];
-    if (type != 0) {
-        const u32 id = b2c_atomic_add_u32(&S.sc.chain_used, 1u);
+    if (emits) {
         if (id < chain_cap) {
             B2cChain c;
             c.parent = chain;
@@ -282,7 +344,7 @@ B2C_HD void b2c_fast_step(const B2cParams& P, B2cFastSmem<WC, CAP>& S, B2cChain*
             S.cmeta[i] = (nplen & 0xFFFFu) | (static_cast<u32>(ti.canon) << 16);
             S.cbk[i] = static_cast<u32>(b) | (static_cast<u32>(k) << 16);
             S.cfold[i] = cur.logit[b] + lp;
-            const u64 key = b2c_beam_key(th, nph, nplen, ti.canon);
+            const u64 key = b2c_fast_key(th, nph, nplen, ti.canon);
             S.ckey[i] = key;
             b2c_fence_block();
             // group equal keys: claim a slot or join the group that owns it (the key is already mixed)
@@ -304,7 +366,6 @@ B2C_HD void b2c_fast_step(const B2cParams& P, B2cFastSmem<WC, CAP>& S, B2cChain*
     B2C_FMARK(1);
 
     // ---- phase B: fold each group (decoder.py:211-224), LM / hotword fusion (:346-424), bucket, max ---
-    B2C_LAST_THREAD { S.sc.n_sel = 0; }
     {
         u64 tmax = 0;
         B2C_FOR(i, M) {
@@ -344,7 +405,7 @@ B2C_HD void b2c_fast_step(const B2cParams& P, B2cFastSmem<WC, CAP>& S, B2cChain*
 #endif
             if (key > tmax) tmax = key;
         }
-        b2c_warp_max_u64_to(tmax, &S.sc.max_key);
+        b2c_warp_max_u64_slot(tmax, S.wmax);
     }
     B2C_SYNC();
     B2C_FMARK(2);
@@ -352,8 +413,8 @@ B2C_HD void b2c_fast_step(const B2cParams& P, B2cFastSmem<WC, CAP>& S, B2cChain*
     // ---- phase C: threshold (:545-546), stable top-N (:548): rank = bucket prefix + order inside the
     //      bucket; history keys of the selected go to the prune table; grouping slots are released ----
     u32* const bpre = S.bpre[b2c_warp_id()];
-    b2c_bucket_scan_warp(S.bcnt, bpre);
-    const double max_score = b2c_key_f64(S.sc.max_key);
+    b2c_bucket_scan_warp_v(S.bcnt, bpre);
+    const double max_score = b2c_key_f64(b2c_max_slots(S.wmax));
     const double thr = max_score + P.prune_logp;
     const u32 width = static_cast<u32>(P.beam_width);
     {
@@ -389,7 +450,7 @@ B2C_HD void b2c_fast_step(const B2cParams& P, B2cFastSmem<WC, CAP>& S, B2cChain*
                 u64 hh = cur.hist_hash[bl];
                 if ((type == 1 || type == 2) && cur.part_len[bl] > 0)
                     hh = b2c_hist_extend(text_arena + cur.text_node[bl], P.hist_n, cur.part_hash[bl]);
-                const u64 hk = b2c_beam_key(hh, cph & B2C_PH_MASK, meta & 0xFFFFu, meta >> 16);
+                const u64 hk = b2c_fast_key(hh, cph & B2C_PH_MASK, meta & 0xFFFFu, meta >> 16);
                 S.phk[rank] = hk;
                 b2c_fence_block();
                 u32 slot = static_cast<u32>(hk) & ptmask;
@@ -404,38 +465,48 @@ B2C_HD void b2c_fast_step(const B2cParams& P, B2cFastSmem<WC, CAP>& S, B2cChain*
                 b2c_atomic_min_u32(&S.pt_min[slot], rank);
             }
         }
-        b2c_warp_max_u32_to(my_top, &S.sc.n_sel);      // the selected ranks are exactly 0 .. n_sel-1
+        b2c_warp_max_u32_slot(my_top, S.wtop);         // the selected ranks are exactly 0 .. max(wtop)-1
     }
     B2C_SYNC();
     B2C_FMARK(3);
 
     // ---- phase D: history prune (:550-552) = keep the best rank of every key, compact, commit ------
-    const u32 nsel = S.sc.n_sel;
+    const u32 nsel = b2c_max_slots(S.wtop);
     u32 n_new = 0;
 #if defined(__CUDA_ARCH__)
     {
+        static_assert(WC <= 32 * B2C_FAST_NW, "one rank per thread");
+        constexpr u32 kBlocks = (WC + 31) / 32;                // rank blocks of 32; warp w commits block w
         const u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
         const u32 lt = (1u << lane) - 1u;
-        for (u32 blk = 0; blk * 32 < nsel; ++blk) {
+        u32 mask[kBlocks];
+#pragma unroll
+        for (u32 blk = 0; blk < kBlocks; ++blk) {              // the loads of the blocks are independent
             const u32 r = blk * 32 + lane;
             const bool kept = r < nsel && (!prune || S.pt_min[S.pslot[r]] == r);
-            const u32 mask = __ballot_sync(0xFFFFFFFFu, kept);
-            if (kept && (blk % B2C_FAST_NW) == w)
-                b2c_fast_commit(P, S, cur, nx, chain_arena, chain_cap, text_arena, text_cap, sb, t, n_new + __popc(mask & lt), r, flags);
-            n_new += __popc(mask);
+            mask[blk] = __ballot_sync(0xFFFFFFFFu, kept);
         }
+        u32 before = 0, mine = 0;
+#pragma unroll
+        for (u32 blk = 0; blk < kBlocks; ++blk) {
+            if (blk == w) { before = n_new; mine = mask[blk]; }
+            n_new += __popc(mask[blk]);
+        }
+        if (mine)
+            b2c_fast_commit(P, S, cur, nx, chain_arena, chain_cap, text_arena, text_cap, sb, t, before + __popc(mine & lt),
+                            w * 32 + lane, flags, ((mine >> lane) & 1u) != 0);
     }
 #else
     for (u32 r = 0; r < nsel; ++r) {
         const bool kept = !prune || S.pt_min[S.pslot[r]] == r;
-        if (kept) b2c_fast_commit(P, S, cur, nx, chain_arena, chain_cap, text_arena, text_cap, sb, t, n_new++, r, flags);
+        if (kept) b2c_fast_commit(P, S, cur, nx, chain_arena, chain_cap, text_arena, text_cap, sb, t, n_new++, r, flags, true);
     }
 #endif
     B2C_FOR(s, B2C_NBUCKET) { S.bcnt[s] = 0; S.bhead[s] = B2C_NONE_U32; }
     B2C_LAST_THREAD {
         S.sc.n_beams = n_new;
+        S.sc.n_sel = nsel;
         S.sc.prev_max = max_score;
-        S.sc.max_key = 0;
     }
     B2C_FMARK(4);
 }
@@ -455,7 +526,6 @@ B2C_HDN void b2c_fast_slow_step(B2cParams P, B2cLayout L, u8* smem, u8* g, int p
     b2c_clear_tables(W, C, H);
     B2C_SYNC();
     b2c_frame_step<false>(P, W, t, tk_id, tk_lp, K, K_next);      // ends with a block barrier
-    B2C_LEADER { S.sc.max_key = 0; }
 }
 
 // -----------------------------------------------------------------------------------------
@@ -514,7 +584,10 @@ B2C_HD void b2c_beam_block_fast(const B2cBeamArgs& A, int slot, u8* smem) {
         }
         B2C_FOR(s, SM::PT) { S.pt_idx[s] = B2C_NONE_U32; S.pt_min[s] = B2C_NONE_U32; }
         B2C_FOR(s, B2C_NBUCKET) { S.bcnt[s] = 0; S.bhead[s] = B2C_NONE_U32; }
-        B2C_LEADER { S.sc.n_sel = 0; S.sc.max_key = 0; }
+        B2C_LEADER {
+            S.sc.n_sel = 0;
+            for (int c = 0; c < B2C_FAST_NW; ++c) { S.wmax[c] = 0; S.wtop[c] = 0; }
+        }
         // stage the tokens of frame 0 (once per utterance, latency exposed)
         if (Tn > 0) {
             const u64 base0 = f0 * static_cast<u64>(V) + rA.off;
