@@ -288,7 +288,9 @@ def main():
         "gpu_launches": int(sum(t["launches"] for t in tms)),
         "device_ms_per_step": statistics.mean(t["ms_total"] for t in tms),
         "beam_kernel_config": {"cap_candidates": tms[-1]["cap_candidates"], "cta_threads": tms[-1]["cta_threads"],
-                               "resident_ctas": tms[-1]["cta_slots"], "oversize_frames_per_step": tms[-1]["oversize_frames"]},
+                               "resident_ctas": tms[-1]["cta_slots"], "oversize_frames_per_step": tms[-1]["oversize_frames"],
+                               "kernel_variant": tms[-1]["kernel_variant"],
+                               "frames_over_128_256_512_1024_2048_4096_total": tms[-1]["cand_hist"]},
         "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:

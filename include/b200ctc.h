@@ -133,6 +133,7 @@ typedef struct {
     int cta_slots;             /* resident CTAs (utterances in flight)                      */
     long long oversize_frames; /* frames that took the out-of-line HBM-tier step           */
     int kernel_variant;        /* 0 general, 1 capacity-class fast kernel, 2 latency-first kernel (beam_width <= 128) */
+    long long cand_hist[7];    /* frames with more than 128,256,...,4096 candidates; [6] = frames counted */
 } b2c_timings_t;
 int b2c_decoder_last_timings(const b2c_decoder_t* dec, b2c_timings_t* out);
 

@@ -49,6 +49,7 @@ class Timings(C.Structure):
         ("cta_slots", C.c_int),
         ("oversize_frames", C.c_longlong),
         ("kernel_variant", C.c_int),
+        ("cand_hist", C.c_longlong * 7),
     ]
 
 

@@ -225,11 +225,19 @@ B2C_HD void b2c_beam_block(const B2cBeamArgs& A, int slot, u8* smem) {
 }
 
 #include "b2c_beam_fast.h"
-typedef B2cFastSmem<128, 1024> B2cFastSmemA;      // beam_width <= 128, <= 1024 candidates per frame: 2 CTAs per SM
+// latency-first kernel variants (beam_width <= 128): candidate capacity x resident CTAs per SM.  A is the
+// latency choice (batch resident at once); B and C trade capacity for residency when the batch is larger
+// than the resident set and the candidate histogram of the previous call says the frames fit.
+typedef B2cFastSmem<128, 1024> B2cFastSmemA;      // 2 CTAs per SM
+typedef B2cFastSmem<128, 512> B2cFastSmemB;       // 3 CTAs per SM
+typedef B2cFastSmem<128, 256> B2cFastSmemC;       // 4 CTAs per SM
+static const u32 kV5Cap[3] = {1024, 512, 256};
+static const int kV5Occ[3] = {2, 3, 4};
+static const size_t kV5Smem[3] = {sizeof(B2cFastSmemA), sizeof(B2cFastSmemB), sizeof(B2cFastSmemC)};
 
 #ifndef B2C_HOSTSIM
-template <int WC, int CAP>
-__global__ void __launch_bounds__(B2C_FAST_NT, 2) b2c_beam_fast_kernel(const B2cBeamArgs A) {
+template <int WC, int CAP, int OCC>
+__global__ void __launch_bounds__(B2C_FAST_NT, OCC) b2c_beam_fast_kernel(const B2cBeamArgs A) {
     extern __shared__ __align__(16) u8 b2c_smem[];
     b2c_beam_block_fast<WC, CAP>(A, static_cast<int>(blockIdx.x), b2c_smem);
 }
@@ -439,9 +447,9 @@ static int launch_prepare(b2c_decoder* d, const B2cPrepArgs& A, int n_utts, int 
     return 0;
 }
 
-// v5: the latency-first kernel (b2c_beam_fast.h); A.L.smem_bytes is sizeof(B2cFastSmemA) then
+// v5 >= 0: variant of the latency-first kernel (b2c_beam_fast.h); A.L.smem_bytes is kV5Smem[v5] then
 static int launch_beam(b2c_decoder* d, const B2cBeamArgs& A, int slots, bool fast, int per_sm, int threads, cudaStream_t stream,
-                       bool v5 = false) {
+                       int v5 = -1) {
 #ifdef B2C_HOSTSIM
     (void)d;
     (void)stream;
@@ -449,18 +457,27 @@ static int launch_beam(b2c_decoder* d, const B2cBeamArgs& A, int slots, bool fas
     (void)threads;
     std::vector<u8> smem(A.L.smem_bytes + 64);
     for (int s = 0; s < slots; ++s) {
-        if (v5) b2c_beam_block_fast<128, 1024>(A, s, smem.data());
+        if (v5 == 0) b2c_beam_block_fast<128, 1024>(A, s, smem.data());
+        else if (v5 == 1) b2c_beam_block_fast<128, 512>(A, s, smem.data());
+        else if (v5 == 2) b2c_beam_block_fast<128, 256>(A, s, smem.data());
         else if (fast) b2c_beam_block<true>(A, s, smem.data());
         else b2c_beam_block<false>(A, s, smem.data());
     }
 #else
     const int smem = static_cast<int>(A.L.smem_bytes);
-    if (v5) {
-        CUDA_OK(cudaFuncSetAttribute(b2c_beam_fast_kernel<128, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        b2c_beam_fast_kernel<128, 1024><<<slots, B2C_FAST_NT, A.L.smem_bytes, stream>>>(A);
+#define B2C_LAUNCH_V5(CAP, OCC)                                                                                         \
+    do {                                                                                                               \
+        CUDA_OK(cudaFuncSetAttribute(b2c_beam_fast_kernel<128, CAP, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+        b2c_beam_fast_kernel<128, CAP, OCC><<<slots, B2C_FAST_NT, A.L.smem_bytes, stream>>>(A);                      \
+    } while (0)
+    if (v5 >= 0) {
+        if (v5 == 0) B2C_LAUNCH_V5(1024, 2);
+        else if (v5 == 1) B2C_LAUNCH_V5(512, 3);
+        else B2C_LAUNCH_V5(256, 4);
         CUDA_OK(cudaGetLastError());
         return 0;
     }
+#undef B2C_LAUNCH_V5
 #define B2C_LAUNCH_BEAM(FAST, THREADS, OCC)                                                                            \
     do {                                                                                                               \
         if (smem > 48 * 1024)                                                                                          \
@@ -923,7 +940,7 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     for (int c = 0; c < kNumCaps; ++c) cap_ok[c] = layout_of(c, 1, false, 0).smem_bytes <= smem_budget;
     std::vector<std::vector<int>> classes(kNumCaps + 1);   // fast classes (one used per call), last = general
     bool use_v5 = false;
-    int v5_top = -1;
+    int v5_top = -1, v5_variant = 0;
     const bool hint_ok = d->hint_valid && d->hint_beam == opts->beam_width && d->hint_lm == (P.lm.order > 0 ? 1 : 0) &&
                          d->hint_hot == (P.n_hot > 0 ? 1 : 0) && d->hint_prune == P.prune_history && d->hint_frames > 0;
     {
@@ -957,6 +974,15 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
         const bool force_v5 = std::getenv("B200CTC_FORCE_V5") != nullptr;      // tests: exercise the out-of-line step
         use_v5 = top >= 0 && opts->beam_width <= 128 && (force_v5 || kCaps[v5_top >= 0 ? v5_top : top] <= 1024) &&
                  sizeof(B2cFastSmemA) + 1024 <= d->smem_optin && std::getenv("B200CTC_NO_V5") == nullptr;
+        // more utterances than variant A keeps resident: trade capacity for residency if the previous call's
+        // histogram says that all but 0.4% of the frames fit (hint_over[q] = frames with > 128 << q candidates)
+        if (use_v5 && hint_ok && n_fast > d->n_sm * kV5Occ[0] && std::getenv("B200CTC_V5_VARIANT") == nullptr) {
+            for (int v = 2; v >= 1; --v) {
+                const int q = kV5Cap[v] == 256 ? 1 : 2;
+                if (static_cast<double>(d->hint_over[q]) <= 0.004 * d->hint_frames) { v5_variant = v; break; }
+            }
+        }
+        if (const char* e = std::getenv("B200CTC_V5_VARIANT")) v5_variant = std::max(0, std::min(2, std::atoi(e)));
         for (int q = 0; q < n_utts; ++q) {
             const int u = order[q];             // keeps longest-first order inside every class
             classes[cls_of[u] < kNumCaps ? top : kNumCaps].push_back(u);
@@ -989,7 +1015,7 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     BA.phase_clk = d->d_clk.as<u64>();
 #endif
 
-    struct Launch { int cls; size_t ord_off; int count; B2cLayout L; int slots; int per_sm; int threads; bool v5; };
+    struct Launch { int cls; size_t ord_off; int count; B2cLayout L; int slots; int per_sm; int threads; int v5; };
     auto plan = [&](const std::vector<int>& utts, int cls, bool full, size_t ord_off) {
         Launch ln;
         ln.cls = cls;
@@ -1002,13 +1028,14 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
             kmax = std::max(kmax, h_maxk[u]);
         }
         const u64 worst_m = static_cast<u64>(opts->beam_width) * std::min<u32>(kmax, static_cast<u32>(V));
-        ln.v5 = use_v5 && cls < kNumCaps;
-        if (ln.v5) {
+        ln.v5 = (use_v5 && cls < kNumCaps) ? v5_variant : -1;
+        if (ln.v5 >= 0) {
             // beam tables of capacity 128; the HBM tier always exists (frames with > B2C_FAST_KS tokens use it too)
+            const u32 cap5 = kV5Cap[ln.v5];
             ln.threads = B2C_FAST_NT;
-            ln.L = make_layout(128, V, tmax, full, smem_budget, 1024, std::max<u64>(worst_m, 1025), B2C_FAST_NW);
-            ln.L.smem_bytes = static_cast<u32>(sizeof(B2cFastSmemA));
-            ln.per_sm = 2;
+            ln.L = make_layout(128, V, tmax, full, smem_budget, cap5, std::max<u64>(worst_m, cap5 + 1), B2C_FAST_NW);
+            ln.L.smem_bytes = static_cast<u32>(kV5Smem[ln.v5]);
+            ln.per_sm = kV5Occ[ln.v5];
         } else {
         ln.threads = cls < kNumCaps ? threads_of(cls) : 128;
         ln.L = cls < kNumCaps ? layout_of(cls, tmax, full, worst_m)
@@ -1060,7 +1087,7 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
             d->tm.cap_candidates = static_cast<int>(ln.L.cap_s);
             d->tm.cta_threads = ln.threads;
             d->tm.cta_slots = ln.slots;
-            d->tm.kernel_variant = ln.v5 ? 2 : (ln.cls < kNumCaps ? 1 : 0);
+            d->tm.kernel_variant = ln.v5 >= 0 ? 2 : (ln.cls < kNumCaps ? 1 : 0);
         }
         if (cs != st) {
             CUDA_OK(cudaEventRecord(d->cls_done[ln.cls < kNumCaps ? 0 : 1], cs));
@@ -1086,6 +1113,7 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
         d->hint_prune = P.prune_history;
         for (int q = 0; q < 6; ++q) d->hint_over[q] = ms[q];
         d->hint_frames = ms[6];
+        for (int q = 0; q < 7; ++q) d->tm.cand_hist[q] = ms[q];
         d->tm.oversize_frames = 0;
         for (int q = 0; q < 6; ++q)
             if (static_cast<int>(128u << q) == d->tm.cap_candidates) d->tm.oversize_frames = ms[q];

@@ -288,7 +288,9 @@ class BeamSearchDecoderCTC:
         """Device-side timings of the last decode call (CUDA events on the decoder's stream)."""
         tm = _lib.Timings()
         _lib.check(_lib.lib().b2c_decoder_last_timings(self._handle(device), C.byref(tm)))
-        return {name: getattr(tm, name) for name, _ in _lib.Timings._fields_}
+        out = {name: getattr(tm, name) for name, _ in _lib.Timings._fields_}
+        out["cand_hist"] = list(out["cand_hist"])
+        return out
 
     # ---- public decoding API (signatures of reference decoder.py:730-945) ------------------
     def decode_beams(self, logits: Any, beam_width: int = DEFAULT_BEAM_WIDTH, beam_prune_logp: float = DEFAULT_PRUNE_LOGP,
