@@ -114,7 +114,26 @@ def cpu_arm(wl, spec, kw, xs, beam, hot, target_cpu_seconds=20.0):
                       "%d threads, %.1f s" % (n, spec["T"], cores, dt)}, texts, n
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """stdout carries exactly ONE JSON line: everything else a library writes to fd 1 (NCCL's version banner,
+    nvcc output of a rebuild, ...) is sent to stderr for the lifetime of the process."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(obj):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(obj) + "\n").encode())
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -156,7 +175,7 @@ def main():
                 vals.append(info["value"])
         v = statistics.mean(vals)
         info["value"] = v
-        print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus,
+        _emit(({"impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
                           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                           "config": {"workload": spec["name"], "regime": args.regime, "beam_width": beam},
@@ -175,7 +194,6 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout (ONE JSON line)
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         dist.barrier()
@@ -297,7 +315,7 @@ def main():
         info, cpu_texts, n = cpu_arm(wl, spec, kw, xs, beam, hot)
         out["cpu_baseline"] = info
         out["transcripts_identical_to_oracle"] = "%d/%d" % (sum(a == b for a, b in zip(cpu_texts, texts[:n])), n)
-    print(json.dumps(out))
+    _emit(out)
     if dist is not None:
         dist.destroy_process_group()
     return 0

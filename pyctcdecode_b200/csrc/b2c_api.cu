@@ -4,6 +4,7 @@
 // the CUDA runtime and runs the kernel bodies block by block on the CPU so that kernel logic
 // can be tested where there is no GPU; that build is never loaded by the product package.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
@@ -13,6 +14,10 @@
 #include <mutex>
 #include <numeric>
 #include <string>
+#include <thread>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
 #include <vector>
 
 #ifdef B2C_HOSTSIM
@@ -312,7 +317,82 @@ struct b2c_lm {
     std::mutex mu;
 };
 
+// a few persistent host threads for the per-utterance string building (spawning threads per call costs
+// tens of microseconds each and occasionally milliseconds)
+struct HostPool {
+    std::vector<std::thread> workers;
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    const std::function<void(int)>* fn = nullptr;
+    int n_tasks = 0, generation = 0, active = 0;
+    std::atomic<int> next{0}, done{0};
+    bool stop = false;
+    void start(int n) {
+        for (int i = 0; i < n; ++i) workers.emplace_back([this]() { loop(); });
+    }
+    void drain(const std::function<void(int)>& f, int n) {
+        while (true) {
+            const int i = next.fetch_add(1);
+            if (i >= n) break;
+            f(i);
+            done.fetch_add(1);
+        }
+    }
+    void loop() {
+        int seen = 0;
+        while (true) {
+            const std::function<void(int)>* f;
+            int n;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv_work.wait(lk, [&]() { return stop || generation != seen; });
+                if (stop) return;
+                seen = generation;
+                f = fn;
+                n = n_tasks;
+                ++active;
+            }
+            drain(*f, n);
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                --active;
+            }
+            cv_done.notify_all();
+        }
+    }
+    // runs f(0..tasks-1) on the workers and the calling thread; returns when every task has finished and no
+    // worker is still inside this generation (f may live on the caller's stack)
+    void run(int tasks, const std::function<void(int)>& f) {
+        if (workers.empty() || tasks <= 1) {
+            for (int i = 0; i < tasks; ++i) f(i);
+            return;
+        }
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            fn = &f;
+            n_tasks = tasks;
+            next.store(0);
+            done.store(0);
+            ++generation;
+        }
+        cv_work.notify_all();
+        drain(f, tasks);
+        std::unique_lock<std::mutex> lk(mu);
+        cv_done.wait(lk, [&]() { return done.load() >= tasks && active == 0; });
+        n_tasks = 0;          // a worker that wakes up late for this generation finds nothing to do
+    }
+    ~HostPool() {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            stop = true;
+        }
+        cv_work.notify_all();
+        for (auto& t : workers) t.join();
+    }
+};
+
 struct b2c_decoder {
+    std::unique_ptr<HostPool> pool;
     int device = 0;
     cudaStream_t stream = nullptr;
     int V = 0, is_bpe = 0;
@@ -735,6 +815,15 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     std::unique_ptr<b2c_result> res(new b2c_result());
     res->utts.resize(n_utts);
     res->has_lm = d->lm != nullptr;
+    // opt-in host-side section timing (B200CTC_HOST_PROFILE=1, stderr)
+    static const bool host_prof = std::getenv("B200CTC_HOST_PROFILE") != nullptr;
+    auto hp_t0 = std::chrono::steady_clock::now();
+    double hp_ms[6] = {0, 0, 0, 0, 0, 0};
+    auto hp_mark = [&](int k) {
+        const auto now = std::chrono::steady_clock::now();
+        hp_ms[k] += std::chrono::duration<double, std::milli>(now - hp_t0).count();
+        hp_t0 = now;
+    };
     if (n_utts == 0) { *out = res.release(); return 0; }
     CUDA_OK(cudaSetDevice(d->device));
     const int V = d->V;
@@ -915,7 +1004,9 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     // ---- size the beam kernel from the token statistics of this batch ---------------------------
     CUDA_OK(cudaMemcpyAsync(d->h_maxk.p, d->d_maxk.p, 4ull * n_utts, cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaMemcpyAsync(d->h_sumk.p, d->d_sumk.p, 4ull * n_utts, cudaMemcpyDeviceToHost, st));
+    hp_mark(0);                                   // argument checks, buffers, enqueue of H2D + prepare kernels
     CUDA_OK(cudaStreamSynchronize(st));
+    hp_mark(1);                                   // wait: H2D + prepare kernels
     const u32* h_maxk = d->h_maxk.as<u32>();
     const u32* h_sumk = d->h_sumk.as<u32>();
     // ---- capacity class of the shared-memory candidate tier (ONE fast class per call) -------------
@@ -1101,7 +1192,9 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     CUDA_OK(cudaMemcpyAsync(d->h_out_toks.p, d->d_out_toks.p, tok_bytes, cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaMemcpyAsync(d->h_out_frames.p, d->d_out_frames.p, frm_bytes, cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaEventRecord(d->ev[4], st));
+    hp_mark(2);                                   // launch planning + enqueue of the beam kernel and D2H
     CUDA_OK(cudaStreamSynchronize(st));
+    hp_mark(3);                                   // wait: beam kernel + D2H
     d->tm.d2h_bytes += static_cast<long long>(small_bytes + tok_bytes + frm_bytes + 8ull * n_utts + 32);
     {
         u32 ms[8];
@@ -1171,20 +1264,44 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     const B2cLmState* h_ls = reinterpret_cast<const B2cLmState*>(hs + off_ls);
     const u32* h_toks = d->h_out_toks.as<u32>();
     const int* h_frames = d->h_out_frames.as<int>();
-    for (int u = 0; u < n_utts; ++u) {
-        const int nb = h_nb[u];
-        res->utts[u].resize(nb);
-        const u64 base = static_cast<u64>(OB) * (frame_off[u] + static_cast<u64>(u));
-        const u64 stride = static_cast<u64>(T[u]) + 1;
-        for (int r = 0; r < nb; ++r) {
-            BeamRes& br = res->utts[u][r];
-            const u64 k = static_cast<u64>(u) * OB + r;
-            br.logit = h_sc[2 * k];
-            br.lm = h_sc[2 * k + 1];
-            br.st = h_ls[k];
-            assemble_beam(d, h_toks + base + r * stride, h_nt[k], h_frames + 2 * (base + r * stride), h_nw[k], br);
+    auto assemble_range = [&](int u0, int u1) {
+        for (int u = u0; u < u1; ++u) {
+            const int nb = h_nb[u];
+            res->utts[u].resize(nb);
+            const u64 base = static_cast<u64>(OB) * (frame_off[u] + static_cast<u64>(u));
+            const u64 stride = static_cast<u64>(T[u]) + 1;
+            for (int r = 0; r < nb; ++r) {
+                BeamRes& br = res->utts[u][r];
+                const u64 k = static_cast<u64>(u) * OB + r;
+                br.logit = h_sc[2 * k];
+                br.lm = h_sc[2 * k + 1];
+                br.st = h_ls[k];
+                assemble_beam(d, h_toks + base + r * stride, h_nt[k], h_frames + 2 * (base + r * stride), h_nw[k], br);
+            }
+        }
+    };
+    {
+        // string building is independent per utterance: a few persistent host threads for large batches
+        const u64 work = (total_frames + static_cast<u64>(n_utts)) * static_cast<u64>(OB);
+        int n_thr = static_cast<int>(std::min<u64>(std::min<u64>(8, std::max(1u, std::thread::hardware_concurrency())), work / 32768));
+        n_thr = std::min(n_thr, n_utts);
+        if (n_thr <= 1) {
+            assemble_range(0, n_utts);
+        } else {
+            if (!d->pool) {
+                d->pool.reset(new HostPool());
+                d->pool->start(static_cast<int>(std::min<u64>(8, std::max(1u, std::thread::hardware_concurrency()))) - 1);
+            }
+            const int chunks = n_thr * 4;
+            const int per = (n_utts + chunks - 1) / chunks;
+            const std::function<void(int)> task = [&](int c) { assemble_range(std::min(n_utts, c * per), std::min(n_utts, (c + 1) * per)); };
+            d->pool->run(chunks, task);
         }
     }
+    hp_mark(4);                                   // statistics read-back, result assembly
+    if (host_prof)
+        std::fprintf(stderr, "[b2c host ms] enqueue=%.3f wait_prepare=%.3f plan=%.3f wait_beam=%.3f assemble=%.3f\n", hp_ms[0],
+                     hp_ms[1], hp_ms[2], hp_ms[3], hp_ms[4]);
     *out = res.release();
     return 0;
 }

@@ -351,7 +351,8 @@ struct B2cPrepShared { u16 sets[B2C_PREP_WARPS][2][B2C_PREP_SMEM_SET]; };
 
 // row statistics: max, log-sum-exp, argmax of the clipped log-probs, and the selected set
 // fed in ascending order into `set`.  Warp-cooperative on the device, a plain loop in hostsim.
-template <class T>
+// kMaskOnly (V <= 32): the selected set is returned as a bit mask in nsel_out instead of being inserted
+template <class T, bool kMaskOnly>
 B2C_HD void b2c_prep_row(const T* row, int V, bool is_prob, double thr, int lane, B2cPySet& set, T& m_out,
                          double& ls_out, int& amax_out, u32& nsel_out) {
 #if defined(__CUDA_ARCH__)
@@ -378,7 +379,7 @@ B2C_HD void b2c_prep_row(const T* row, int V, bool is_prob, double thr, int lane
     double best = 0.0;
     int besti = -1;
     u32 nsel = 0;
-    if (lane == 0) b2c_pyset_init(set, set.buf[0], set.buf[1]);
+    if (!kMaskOnly && lane == 0) b2c_pyset_init(set, set.buf[0], set.buf[1]);
     for (int base = 0; base < V; base += 32) {
         const int v = base + lane;
         bool sel = false;
@@ -388,6 +389,7 @@ B2C_HD void b2c_prep_row(const T* row, int V, bool is_prob, double thr, int lane
             sel = lp >= thr;
         }
         unsigned mask = __ballot_sync(full, sel);
+        if (kMaskOnly) { nsel = mask; continue; }
         nsel += __popc(mask);
         if (lane == 0) {
             while (mask) {
@@ -428,13 +430,241 @@ B2C_HD void b2c_prep_row(const T* row, int V, bool is_prob, double thr, int lane
     double best = 0.0;
     int besti = -1;
     u32 nsel = 0;
-    b2c_pyset_init(set, set.buf[0], set.buf[1]);
+    if (!kMaskOnly) b2c_pyset_init(set, set.buf[0], set.buf[1]);
     for (int v = 0; v < V; ++v) {
         const double lp = b2c_lp<T>(row[v], is_prob, m, ls);
         if (besti < 0 || lp > best) { best = lp; besti = v; }
-        if (lp >= thr) { ++nsel; b2c_pyset_add(set, static_cast<u32>(v)); }
+        if (lp >= thr) {
+            if (kMaskOnly) nsel |= 1u << v;
+            else { ++nsel; b2c_pyset_add(set, static_cast<u32>(v)); }
+        }
     }
     m_out = m; ls_out = ls; amax_out = besti; nsel_out = nsel;
+#endif
+}
+
+// CPython iteration order of set(ascending ints of `mask`) | {amax} for at most 3 selected tokens < 32 with
+// amax among them (or none selected): the table keeps its initial 8 slots (no resize below 5 entries, the
+// linear-probe window i+9 <= mask is never open at mask 7), one byte per slot in a 64-bit register.
+// Returns the number of tokens written to out[0..2].
+B2C_HD u32 b2c_pyset_small_order(u32 mask, u32 amax, u32* out) {
+    if (mask == 0) { out[0] = amax; return 1; }
+    u64 tab = ~0ull;
+    u32 mm = mask;
+    while (mm) {
+#if defined(__CUDA_ARCH__)
+        const u32 key = static_cast<u32>(__ffs(static_cast<int>(mm)) - 1);
+#else
+        u32 key = 0;
+        while (!((mm >> key) & 1u)) ++key;
+#endif
+        mm &= mm - 1;
+        u32 perturb = key, i = key & 7u;
+        while (((tab >> (8 * i)) & 0xFFull) != 0xFFull) {
+            perturb >>= 5;
+            i = (i * 5 + 1 + perturb) & 7u;
+        }
+        tab = (tab & ~(0xFFull << (8 * i))) | (static_cast<u64>(key) << (8 * i));
+    }
+    u32 n = 0;
+    for (u32 i = 0; i < 8; ++i) {
+        const u32 e = static_cast<u32>((tab >> (8 * i)) & 0xFFull);
+        if (e != 0xFFu) out[n++] = e;
+    }
+    return n;
+}
+
+// V <= 32: one run (<= 8 frames) per warp.  Row statistics are warp-wide per frame and leave the frame's
+// selected set as a bit mask in lane f; the ordering of the (typically 1-3) tokens, the offsets inside the
+// run and the compact writes are then done by 8 lanes in parallel, one frame each.  Frames with more than
+// 3 selected tokens go through the general set emulation afterwards, at offsets that are already known.
+template <class T>
+B2C_HD void b2c_tokens_run_v32(const B2cPrepArgs& A, u64 run, int lane, u16* set0, u16* set1) {
+    int lo = 0, hi = A.n_utts - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (A.run_off[mid] <= run) lo = mid; else hi = mid - 1;
+    }
+    const int u = lo;
+    const int Tn = A.T[u];
+    const int t0 = static_cast<int>(run - A.run_off[u]) * B2C_RUN;
+    const int t1 = t0 + B2C_RUN < Tn ? t0 + B2C_RUN : Tn;
+    const int nf = t1 - t0;
+    const int V = A.V;
+    const u64 f0 = A.frame_off[u];
+    const bool is_prob = A.is_prob[u] != 0;
+    const T* x = static_cast<const T*>(A.logits) + f0 * static_cast<u64>(V);
+    const u64 base = (f0 + static_cast<u64>(t0)) * static_cast<u64>(V);
+    u16* ids = A.tok_ids + base;
+    double* lps = A.tok_lp + base;
+    B2cPySet set;
+    set.buf[0] = set0;
+    set.buf[1] = set1;
+#if defined(__CUDA_ARCH__)
+    const unsigned full = 0xFFFFFFFFu;
+    u32 my_mask = 0, my_amax = 0;
+    T my_m = static_cast<T>(0);
+    double my_ls = 0.0;
+    if (sizeof(T) == 4 && !is_prob) {
+        // float32 logits (the common case), same arithmetic as b2c_prep_row with far fewer instructions:
+        // row max and argmax through REDUX on order-preserving integer keys, log(sum) once per RUN (lane f
+        // takes frame f), the 8 rows of the run held in registers
+        const bool has = lane < V;
+        float d[B2C_RUN];
+        double my_S = 1.0;
+#pragma unroll
+        for (int f = 0; f < B2C_RUN; ++f) {
+            d[f] = 0.0f;
+            if (f < nf) {
+                const float xv = has ? static_cast<float>(x[static_cast<u64>(t0 + f) * V + lane]) : 0.0f;
+                // max over the row: int order == float order on these keys (NaN sorts above +inf -> non-finite -> 0)
+                const u32 xb = __float_as_uint(xv);
+                const u32 key = has ? ((xb & 0x80000000u) ? ~xb : (xb | 0x80000000u)) : 0u;
+                const u32 km = __reduce_max_sync(full, key);
+                float m = __uint_as_float((km & 0x80000000u) ? (km & 0x7FFFFFFFu) : ~km);
+                if (!(static_cast<double>(m) - static_cast<double>(m) == 0.0)) m = 0.0f;
+                d[f] = xv - m;
+                double part = has ? exp(static_cast<double>(d[f])) : 0.0;
+                for (int off = 16; off >= 1; off >>= 1) part = part + __shfl_xor_sync(full, part, off);
+                if (lane == f) { my_S = part; my_m = static_cast<T>(m); }
+            }
+        }
+        my_ls = log(my_S);
+#pragma unroll
+        for (int f = 0; f < B2C_RUN; ++f) {
+            if (f < nf) {
+                const double ls = __shfl_sync(full, my_ls, f);
+                double lp = static_cast<double>(static_cast<float>(static_cast<double>(d[f]) - ls));
+                if (lp < B2C_LOG_MIN_CLIP) lp = B2C_LOG_MIN_CLIP;
+                if (lp > 0.0) lp = 0.0;
+                const u32 mask = __ballot_sync(full, has && lp >= A.token_min_logp);
+                // argmax like the sequential scan: the first element wins if it is NaN, otherwise the largest
+                // non-NaN value, lowest index among equals
+                const float lpf = static_cast<float>(lp);
+                const u32 lb = __float_as_uint(lpf);
+                const u32 lkey = (has && lpf == lpf) ? ((lb & 0x80000000u) ? ~lb : (lb | 0x80000000u)) : 0u;
+                const u32 lmax = __reduce_max_sync(full, lkey);
+                const u32 eq = __ballot_sync(full, has && lkey == lmax);
+                const u32 first_nan = __ballot_sync(full, lane == 0 && !(lpf == lpf));
+                const u32 amax = (first_nan || eq == 0) ? 0u : static_cast<u32>(__ffs(static_cast<int>(eq)) - 1);
+                if (lane == f) { my_mask = mask; my_amax = amax; }
+            }
+        }
+    } else {
+        for (int f = 0; f < nf; ++f) {
+            T m;
+            double ls;
+            int amax;
+            u32 mask;
+            b2c_prep_row<T, true>(x + static_cast<u64>(t0 + f) * V, V, is_prob, A.token_min_logp, lane, set, m, ls, amax, mask);
+            amax = __shfl_sync(full, amax, 0);          // lane 0's view, like the general path
+            if (lane == f) { my_mask = mask; my_amax = static_cast<u32>(amax); my_m = m; my_ls = ls; }
+        }
+    }
+    const bool mine = lane < nf;
+    const u32 nsel = __popc(my_mask);
+    const bool small = nsel == 0 || (nsel <= 3 && ((my_mask >> my_amax) & 1u));
+    const u32 cnt = mine ? static_cast<u32>(__popc(my_mask | (1u << my_amax))) : 0u;
+    u32 incl = cnt;
+    for (int off = 1; off < B2C_RUN; off <<= 1) {
+        const u32 o = __shfl_up_sync(full, incl, off);
+        if (lane >= off) incl += o;
+    }
+    const u32 my_off = incl - cnt;
+    if (mine) {
+        B2cFrameRec rec;
+        rec.off = my_off;
+        rec.cnt = cnt;
+        A.tok_rec[f0 + static_cast<u64>(t0 + lane)] = rec;
+        if (small) {
+            const T* row = x + static_cast<u64>(t0 + lane) * V;
+            u32 toks[3];
+            const u32 n = b2c_pyset_small_order(my_mask, my_amax, toks);
+            for (u32 q = 0; q < n; ++q) {
+                ids[my_off + q] = static_cast<u16>(toks[q]);
+                lps[my_off + q] = b2c_lp<T>(row[toks[q]], is_prob, my_m, my_ls);
+            }
+        }
+    }
+    u32 big = __ballot_sync(full, mine && !small);
+    while (big) {
+        const int f = __ffs(static_cast<int>(big)) - 1;
+        big &= big - 1;
+        const T* row = x + static_cast<u64>(t0 + f) * V;
+        T m;
+        double ls;
+        int amax;
+        u32 ns;
+        b2c_prep_row<T, false>(row, V, is_prob, A.token_min_logp, lane, set, m, ls, amax, ns);
+        u32 off = __shfl_sync(full, my_off, f);
+        if (lane == 0) {
+            b2c_pyset_copy_or(set, static_cast<u32>(amax));
+            const u16* tab = set.buf[set.cur];
+            for (u32 s = 0; s <= set.mask; ++s) {
+                const u16 tok = tab[s];
+                if (tok == 0xFFFFu) continue;
+                ids[off] = tok;
+                lps[off] = b2c_lp<T>(row[tok], is_prob, m, ls);
+                ++off;
+            }
+        }
+        __syncwarp();
+    }
+    u32 mx = cnt;
+    for (int off = 1; off < B2C_RUN; off <<= 1) {
+        const u32 o = __shfl_xor_sync(full, mx, off);
+        mx = o > mx ? o : mx;
+    }
+    const u32 total = __shfl_sync(full, incl, B2C_RUN - 1);
+    if (lane == 0 && mx > 0) {
+        b2c_atomic_max_u32(&A.max_k[u], mx);
+        b2c_atomic_add_u32(&A.sum_k[u], total);
+    }
+#else
+    (void)lane;
+    u32 off = 0, mx = 0;
+    for (int f = 0; f < nf; ++f) {
+        const T* row = x + static_cast<u64>(t0 + f) * V;
+        T m;
+        double ls;
+        int amax;
+        u32 mask;
+        b2c_prep_row<T, true>(row, V, is_prob, A.token_min_logp, 0, set, m, ls, amax, mask);
+        u32 nsel = 0;
+        for (u32 b = 0; b < 32; ++b) nsel += (mask >> b) & 1u;
+        const bool small = nsel == 0 || (nsel <= 3 && ((mask >> amax) & 1u));
+        B2cFrameRec rec;
+        rec.off = off;
+        if (small) {
+            u32 toks[3];
+            const u32 n = b2c_pyset_small_order(mask, static_cast<u32>(amax), toks);
+            for (u32 q = 0; q < n; ++q) {
+                ids[off] = static_cast<u16>(toks[q]);
+                lps[off] = b2c_lp<T>(row[toks[q]], is_prob, m, ls);
+                ++off;
+            }
+            rec.cnt = n;
+        } else {
+            u32 ns;
+            b2c_prep_row<T, false>(row, V, is_prob, A.token_min_logp, 0, set, m, ls, amax, ns);
+            b2c_pyset_copy_or(set, static_cast<u32>(amax));
+            rec.cnt = set.fill;
+            const u16* tab = set.buf[set.cur];
+            for (u32 s2 = 0; s2 <= set.mask; ++s2) {
+                const u16 tok = tab[s2];
+                if (tok == 0xFFFFu) continue;
+                ids[off] = tok;
+                lps[off] = b2c_lp<T>(row[tok], is_prob, m, ls);
+                ++off;
+            }
+        }
+        A.tok_rec[f0 + static_cast<u64>(t0 + f)] = rec;
+        if (rec.cnt > mx) mx = rec.cnt;
+    }
+    if (mx > 0) {
+        b2c_atomic_max_u32(&A.max_k[u], mx);
+        b2c_atomic_add_u32(&A.sum_k[u], off);
+    }
 #endif
 }
 
@@ -468,7 +698,7 @@ B2C_HD void b2c_tokens_run(const B2cPrepArgs& A, u64 run, int lane, u16* set0, u
         double ls;
         int amax;
         u32 nsel;
-        b2c_prep_row<T>(row, V, is_prob, A.token_min_logp, lane, set, m, ls, amax, nsel);
+        b2c_prep_row<T, false>(row, V, is_prob, A.token_min_logp, lane, set, m, ls, amax, nsel);
         if (lane == 0) {
             b2c_pyset_copy_or(set, static_cast<u32>(amax));
             const u32 cnt = set.fill;
@@ -506,14 +736,18 @@ B2C_HD void b2c_tokens_block(const B2cPrepArgs& A, int block_idx, int n_blocks, 
     const u64 n_warps = static_cast<u64>(n_blocks) * B2C_PREP_WARPS;
     u16* b0 = small ? sh->sets[w][0] : A.set_scratch + (gw * 2 + 0) * A.set_cap;
     u16* b1 = small ? sh->sets[w][1] : A.set_scratch + (gw * 2 + 1) * A.set_cap;
-    for (u64 run = gw; run < total_runs; run += n_warps) b2c_tokens_run<T>(A, run, lane, b0, b1);
+    if (small) { for (u64 run = gw; run < total_runs; run += n_warps) b2c_tokens_run_v32<T>(A, run, lane, b0, b1); }
+    else { for (u64 run = gw; run < total_runs; run += n_warps) b2c_tokens_run<T>(A, run, lane, b0, b1); }
 #else
     for (int w = 0; w < B2C_PREP_WARPS; ++w) {
         const u64 gw = static_cast<u64>(block_idx) * B2C_PREP_WARPS + w;
         const u64 n_warps = static_cast<u64>(n_blocks) * B2C_PREP_WARPS;
         u16* b0 = small ? sh->sets[w][0] : A.set_scratch + (gw * 2 + 0) * A.set_cap;
         u16* b1 = small ? sh->sets[w][1] : A.set_scratch + (gw * 2 + 1) * A.set_cap;
-        for (u64 run = gw; run < total_runs; run += n_warps) b2c_tokens_run<T>(A, run, 0, b0, b1);
+        for (u64 run = gw; run < total_runs; run += n_warps) {
+            if (small) b2c_tokens_run_v32<T>(A, run, 0, b0, b1);
+            else b2c_tokens_run<T>(A, run, 0, b0, b1);
+        }
     }
 #endif
 }
