@@ -108,6 +108,9 @@ void b2c_result_free(b2c_result_t* res);
 int b2c_result_n_utts(const b2c_result_t* res);
 int b2c_result_n_beams(const b2c_result_t* res, int utt);
 const char* b2c_result_text(const b2c_result_t* res, int utt, int beam);          /* utf-8 */
+/* top-1 text of every utterance in one buffer, each text followed by a NUL byte (one call instead of
+ * n_utts; what decode_batch needs); the buffer lives as long as the result */
+int b2c_result_top_texts(b2c_result_t* res, const char** data, size_t* size);
 double b2c_result_logit_score(const b2c_result_t* res, int utt, int beam);
 double b2c_result_lm_score(const b2c_result_t* res, int utt, int beam);
 int b2c_result_n_words(const b2c_result_t* res, int utt, int beam);

@@ -89,6 +89,7 @@ def _declare(L):
     L.b2c_result_n_beams.argtypes = [vp, i32]
     L.b2c_result_text.argtypes = [vp, i32, i32]
     L.b2c_result_text.restype = cp
+    L.b2c_result_top_texts.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.b2c_result_logit_score.argtypes = [vp, i32, i32]
     L.b2c_result_logit_score.restype = f64
     L.b2c_result_lm_score.argtypes = [vp, i32, i32]

@@ -428,6 +428,8 @@ struct BeamRes {
 struct b2c_result {
     std::vector<std::vector<BeamRes>> utts;
     bool has_lm = false;
+    std::string joined;        // b2c_result_top_texts: top-1 texts, each followed by '\0'
+    bool joined_built = false;
 };
 
 // hotword table (language_model.py:152-189): every code-point prefix of every hotword unigram
@@ -1311,6 +1313,22 @@ void b2c_result_free(b2c_result_t* r) { delete r; }
 int b2c_result_n_utts(const b2c_result_t* r) { return r ? static_cast<int>(r->utts.size()) : 0; }
 int b2c_result_n_beams(const b2c_result_t* r, int u) { return static_cast<int>(r->utts[u].size()); }
 const char* b2c_result_text(const b2c_result_t* r, int u, int b) { return r->utts[u][b].text.c_str(); }
+int b2c_result_top_texts(b2c_result_t* r, const char** data, size_t* size) {
+    if (!r || !data || !size) return fail(B2C_E_ARG, "null argument");
+    if (!r->joined_built) {
+        size_t total = 0;
+        for (const auto& u : r->utts) total += (u.empty() ? 0 : u[0].text.size()) + 1;
+        r->joined.reserve(total);
+        for (const auto& u : r->utts) {
+            if (!u.empty()) r->joined += u[0].text;
+            r->joined.push_back('\0');
+        }
+        r->joined_built = true;
+    }
+    *data = r->joined.data();
+    *size = r->joined.size();
+    return 0;
+}
 double b2c_result_logit_score(const b2c_result_t* r, int u, int b) { return r->utts[u][b].logit; }
 double b2c_result_lm_score(const b2c_result_t* r, int u, int b) { return r->utts[u][b].lm; }
 int b2c_result_n_words(const b2c_result_t* r, int u, int b) { return static_cast<int>(r->utts[u][b].words.size()); }

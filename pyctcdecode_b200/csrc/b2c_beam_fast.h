@@ -13,8 +13,8 @@
 //     token record is a warp-uniform shared-memory broadcast;
 //   * stores each candidate's own logit sum and (beam, token) pair, so the fold / fusion / commit
 //     phases never re-derive them;
-//   * probes the grouping table with the low bits of the (already avalanche-mixed) merge key, over
-//     the full table (load <= 0.5 at capacity, ~0.06 typically);
+//   * merge keys without an avalanche round (b2c_fast_key), probing the full grouping table with their
+//     folded low bits (load <= 0.5 at capacity, ~0.06 typically);
 //   * clears grouping / history-prune slots by their owners instead of sweeping the tables.
 // Frames with more than CAP candidates (or more than B2C_FAST_KS tokens) are rare on ASR-like
 // posteriors; they take the general out-of-line step on the HBM candidate tier (b2c_fast_slow_step).
@@ -267,11 +267,17 @@ B2C_HD void b2c_fast_commit(const B2cParams& P, B2cFastSmem<WC, CAP>& S, const B
     double lm_hw = cur.lm_hw[bl];
     u64 hh = cur.hist_hash[bl];
     if (word_len > 0) {
-        B2cTextCommit tc;
-        b2c_commit_text(P, text_arena, text_cap, &S.sc.text_used, &S.sc.status, tnode, cur.part_hash[bl], word_len, &tc);
-        tnode = tc.node;
-        lm_hw = tc.lm_hw;
-        hh = tc.hist_hash;
+        if (flags & B2C_FL_PSCORE) {
+            B2cTextCommit tc;
+            b2c_commit_text(P, text_arena, text_cap, &S.sc.text_used, &S.sc.status, tnode, cur.part_hash[bl], word_len, &tc);
+            tnode = tc.node;
+            lm_hw = tc.lm_hw;
+            hh = tc.hist_hash;
+        } else {
+            // no LM, no hotwords: hist_n == 1, the text-level score stays hot_weight * 0 and nothing ever reads
+            // a text node other than the root -> no arena traffic on word boundaries
+            hh = b2c_hist_fold(B2C_HIST_SEED, cur.part_hash[bl]);
+        }
     }
     nx.text_node[j] = tnode;
     nx.lm_hw[j] = lm_hw;
@@ -384,7 +390,8 @@ B2C_HD void b2c_fast_step(const B2cParams& P, B2cFastSmem<WC, CAP>& S, B2cChain*
             const u32 part_len = S.cmeta[last] & 0xFFFFu;
             const u32 bl = S.cbk[last] & 0xFFFFu;
             double lm_hw = cur.lm_hw[bl];
-            if ((type == 1 || type == 2) && cur.part_len[bl] > 0) {
+            // without LM and hotwords the text-level score is the constant hot_weight * 0: no text node is read
+            if ((flags & B2C_FL_PSCORE) && (type == 1 || type == 2) && cur.part_len[bl] > 0) {
                 B2cTextNew tn;
                 b2c_text_extend(P, text_arena + cur.text_node[bl], cur.part_hash[bl], cur.part_len[bl], 0, &tn);
                 lm_hw = tn.lm_hw;
@@ -448,8 +455,9 @@ B2C_HD void b2c_fast_step(const B2cParams& P, B2cFastSmem<WC, CAP>& S, B2cChain*
                 const u32 type = static_cast<u32>(cph >> 61);
                 const u32 meta = S.cmeta[last];
                 u64 hh = cur.hist_hash[bl];
-                if ((type == 1 || type == 2) && cur.part_len[bl] > 0)
-                    hh = b2c_hist_extend(text_arena + cur.text_node[bl], P.hist_n, cur.part_hash[bl]);
+                if ((type == 1 || type == 2) && cur.part_len[bl] > 0)       // a one-word history does not depend on the parent
+                    hh = P.hist_n == 1 ? b2c_hist_fold(B2C_HIST_SEED, cur.part_hash[bl])
+                                       : b2c_hist_extend(text_arena + cur.text_node[bl], P.hist_n, cur.part_hash[bl]);
                 const u64 hk = b2c_fast_key(hh, cph & B2C_PH_MASK, meta & 0xFFFFu, meta >> 16);
                 S.phk[rank] = hk;
                 b2c_fence_block();

@@ -513,10 +513,12 @@ B2C_HD void b2c_tokens_run_v32(const B2cPrepArgs& A, u64 run, int lane, u16* set
         float d[B2C_RUN];
         double my_S = 1.0;
 #pragma unroll
+        for (int f = 0; f < B2C_RUN; ++f)      // all rows of the run in flight before the first reduction
+            d[f] = (has && f < nf) ? static_cast<float>(x[static_cast<u64>(t0 + f) * V + lane]) : 0.0f;
+#pragma unroll
         for (int f = 0; f < B2C_RUN; ++f) {
-            d[f] = 0.0f;
             if (f < nf) {
-                const float xv = has ? static_cast<float>(x[static_cast<u64>(t0 + f) * V + lane]) : 0.0f;
+                const float xv = d[f];
                 // max over the row: int order == float order on these keys (NaN sorts above +inf -> non-finite -> 0)
                 const u32 xb = __float_as_uint(xv);
                 const u32 key = has ? ((xb & 0x80000000u) ? ~xb : (xb | 0x80000000u)) : 0u;

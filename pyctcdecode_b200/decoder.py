@@ -265,7 +265,9 @@ class BeamSearchDecoderCTC:
         _lib.check(L.b2c_decode_batch(handle, ptrs, Ts, n, dtype_code, int(is_device), C.byref(opts), C.byref(res)))
         try:
             if texts_only:
-                return [L.b2c_result_text(res, u, 0).decode("utf-8") for u in range(n)]
+                data, size = C.c_void_p(), C.c_size_t()
+                _lib.check(L.b2c_result_top_texts(res, C.byref(data), C.byref(size)))
+                return C.string_at(data, size.value).decode("utf-8").split("\x00")[:n]
             out: List[List[OutputBeam]] = []
             st = _lib.LMState()
             for u in range(n):
