@@ -248,7 +248,8 @@ __global__ void __launch_bounds__(B2C_FAST_NT, OCC) b2c_beam_fast_kernel(const B
 }
 template <class T>
 __global__ void __launch_bounds__(B2C_PREP_THREADS) b2c_rowsum_kernel(const B2cPrepArgs A) {
-    b2c_rowsum_block<T>(A, static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x));
+    __shared__ double leaf_sums[B2C_PREP_WARPS * B2C_ROWSUM_MAX_LEAF];
+    b2c_rowsum_block<T>(A, static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x), leaf_sums);
 }
 template <class T>
 __global__ void __launch_bounds__(128) b2c_decide_kernel(const B2cPrepArgs A) {
@@ -515,7 +516,7 @@ template <class T>
 static int launch_prepare(b2c_decoder* d, const B2cPrepArgs& A, int n_utts, int grid_rows, int grid_tok) {
 #ifdef B2C_HOSTSIM
     (void)d;
-    for (int b = 0; b < grid_rows; ++b) b2c_rowsum_block<T>(A, b, grid_rows);
+    for (int b = 0; b < grid_rows; ++b) b2c_rowsum_block<T>(A, b, grid_rows, nullptr);
     std::unique_ptr<B2cDecideShared> dsh(new B2cDecideShared());
     for (int u = 0; u < n_utts; ++u) b2c_decide_block<T>(A, u, dsh.get());
     std::unique_ptr<B2cPrepShared> sh(new B2cPrepShared());
@@ -992,6 +993,29 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     PA.set_scratch = d->d_set.as<u16>();
     PA.set_cap = set_cap;
     PA.is_prob = d->d_isprob.as<int>();
+    if (V > 128) {   // leaves of numpy's pairwise recursion over a row of V elements, in visiting order
+        std::vector<std::pair<long, long>> st{{0, V}}, leaves;
+        while (!st.empty()) {
+            const auto f = st.back();
+            st.pop_back();
+            if (f.second <= 128) { leaves.push_back(f); continue; }
+            long n2 = f.second / 2;
+            n2 -= n2 % 8;
+            st.push_back({f.first + n2, f.second - n2});     // right half is visited after the left one
+            st.push_back({f.first, n2});
+        }
+        if (leaves.size() <= B2C_ROWSUM_MAX_LEAF) {
+            bool ok = true;
+            for (const auto& lf : leaves) ok = ok && lf.second >= 8;
+            if (ok) {
+                PA.n_leaf = static_cast<int>(leaves.size());
+                for (size_t i = 0; i < leaves.size(); ++i) {
+                    PA.leaf_off[i] = static_cast<u32>(leaves[i].first);
+                    PA.leaf_n[i] = static_cast<u32>(leaves[i].second);
+                }
+            }
+        }
+    }
     PA.max_k = d->d_maxk.as<u32>();
     PA.sum_k = d->d_sumk.as<u32>();
     CUDA_OK(cudaMemsetAsync(d->d_maxk.p, 0, 4ull * n_utts, st));

@@ -221,6 +221,7 @@ B2C_HD void b2c_pyset_copy_or(B2cPySet& s, u32 extra) {
 #define B2C_PREP_WARPS 8
 #define B2C_PREP_SMEM_SET 128       // entries per smem set buffer (enough for 32 selected tokens)
 #define B2C_PREP_LEAF_CAP 1024
+#define B2C_ROWSUM_MAX_LEAF 64      // rows up to 8192 elements take the coalesced warp-per-row sum
 
 struct B2cFrameRec { u32 off; u32 cnt; };   // token list of one frame: offset inside its run, length
 
@@ -239,6 +240,11 @@ struct B2cPrepArgs {
     void* rowsum;            // [total_frames] scratch, input dtype
     u16* set_scratch;        // [total warps][2][set_cap] spill space for large token sets
     u32 set_cap;             // power of two >= 8 * (V + 1)
+    // leaves (<= 128 elements) of numpy's pairwise recursion over one row, in visiting order; n_leaf == 0:
+    // not tabulated (V <= 128 needs no table, very long rows use the per-thread path)
+    int n_leaf;
+    u32 leaf_off[B2C_ROWSUM_MAX_LEAF];
+    u32 leaf_n[B2C_ROWSUM_MAX_LEAF];
     int* is_prob;            // [B]
     u32* max_k;              // [B] largest per-frame token count (zeroed before the launch)
     u32* sum_k;              // [B] total number of selected tokens (zeroed before the launch)
@@ -246,7 +252,14 @@ struct B2cPrepArgs {
 
 // ---- rowsum ---------------------------------------------------------------------------------
 template <class T>
-B2C_HD void b2c_rowsum_block(const B2cPrepArgs& A, int block_idx, int n_blocks) {
+struct B2cLeafShared {
+    const double* sums;
+    mutable int next;
+    B2C_HD T operator()(long, long) const { return static_cast<T>(sums[next++]); }
+};
+
+template <class T>
+B2C_HD void b2c_rowsum_block(const B2cPrepArgs& A, int block_idx, int n_blocks, double* leaf_sums) {
     const T* x = static_cast<const T*>(A.logits);
     T* rs = static_cast<T*>(A.rowsum);
     const int V = A.V;
@@ -273,24 +286,56 @@ B2C_HD void b2c_rowsum_block(const B2cPrepArgs& A, int block_idx, int n_blocks) 
         }
         return;
     }
+    if (A.n_leaf > 0) {
+        // long rows (V > 128): one warp per row, four leaves at a time (8 lanes = numpy's 8 accumulators of a
+        // leaf, 32-byte sectors fully used), then the recursion over the leaf sums by lane 0
+        const int wib = static_cast<int>(threadIdx.x >> 5);
+        for (u64 r = warp; r < A.total_frames; r += n_warps) {
+            const T* a = x + r * static_cast<u64>(V);
+            for (int l0 = 0; l0 < A.n_leaf; l0 += 4) {
+                const int lf = l0 + g;
+                const bool ok = lf < A.n_leaf;
+                const u32 off = ok ? A.leaf_off[lf] : 0u;
+                const int n = ok ? static_cast<int>(A.leaf_n[lf]) : 8;
+                T res;
+                if (n < 8) {
+                    res = static_cast<T>(-0.0);
+                    for (int i = 0; i < n; ++i) res = res + a[off + i];
+                } else {
+                    const int body = n - (n % 8);
+                    T acc = a[off + j];
+                    for (int i = 8; i < body; i += 8) acc = acc + a[off + i + j];
+                    acc = acc + __shfl_xor_sync(full, acc, 1);
+                    acc = acc + __shfl_xor_sync(full, acc, 2);
+                    acc = acc + __shfl_xor_sync(full, acc, 4);
+                    for (int i = body; i < n; ++i) acc = acc + a[off + i];
+                    res = acc;
+                }
+                if (ok && j == 0) leaf_sums[wib * B2C_ROWSUM_MAX_LEAF + lf] = static_cast<double>(res);
+            }
+            __syncwarp();
+            if (lane == 0) {
+                B2cLeafShared<T> lfn;
+                lfn.sums = leaf_sums + wib * B2C_ROWSUM_MAX_LEAF;
+                lfn.next = 0;
+                rs[r] = b2c_np_pairwise_generic<T>(V, lfn);
+            }
+            __syncwarp();
+        }
+        return;
+    }
     // generic: one thread per row, numpy's recursion evaluated sequentially
     for (u64 r = warp * 32 + lane; r < A.total_frames; r += n_warps * 32) rs[r] = b2c_np_pairwise<T>(x + r * static_cast<u64>(V), V);
 #else
     if (block_idx == 0)
         for (u64 r = 0; r < A.total_frames; ++r) rs[r] = b2c_np_pairwise<T>(x + r * static_cast<u64>(V), V);
     (void)n_blocks;
+    (void)leaf_sums;
 #endif
 }
 
 // ---- decide ---------------------------------------------------------------------------------
 struct B2cDecideShared { double leaf_sum[B2C_PREP_LEAF_CAP]; };
-
-template <class T>
-struct B2cLeafShared {
-    const double* sums;
-    mutable int next;
-    B2C_HD T operator()(long, long) const { return static_cast<T>(sums[next++]); }
-};
 
 B2C_HD int b2c_count_leaves(long n) {
     long st[48];
