@@ -246,6 +246,17 @@ __global__ void __launch_bounds__(B2C_FAST_NT, OCC) b2c_beam_fast_kernel(const B
     extern __shared__ __align__(16) u8 b2c_smem[];
     b2c_beam_block_fast<WC, CAP>(A, static_cast<int>(blockIdx.x), b2c_smem);
 }
+// device-resident utterances that are not adjacent in memory (a padded [B, T, V] batch with lengths, a list
+// of separate tensors): ONE launch packs their valid rows, instead of one cudaMemcpyAsync per utterance
+__global__ void __launch_bounds__(256) b2c_gather_kernel(const void* const* src, const u64* frame_off, const int* T, u64 row_words,
+                                                         u32* dst, int n_utts, int chunks) {
+    const int u = static_cast<int>(blockIdx.x) / chunks, c = static_cast<int>(blockIdx.x) % chunks;
+    if (u >= n_utts) return;
+    const u64 words = static_cast<u64>(T[u]) * row_words;
+    const u32* s = static_cast<const u32*>(src[u]);
+    u32* o = dst + frame_off[u] * row_words;
+    for (u64 i = static_cast<u64>(c) * blockDim.x + threadIdx.x; i < words; i += static_cast<u64>(chunks) * blockDim.x) o[i] = s[i];
+}
 template <class T>
 __global__ void __launch_bounds__(B2C_PREP_THREADS) b2c_rowsum_kernel(const B2cPrepArgs A) {
     __shared__ double leaf_sums[B2C_PREP_WARPS * B2C_ROWSUM_MAX_LEAF];
@@ -890,7 +901,7 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
         return T[0] > 0 || n_utts == 1;
     }();
     if (!contiguous_dev && d->d_logits.ensure(std::max<u64>(total_frames * V * esz, 16))) return B2C_E_NOMEM;
-    const size_t meta_bytes = al16(8ull * n_utts) + 3 * al16(4ull * n_utts) + 64 + al16(8ull * (n_utts + 1));
+    const size_t meta_bytes = al16(8ull * n_utts) + 3 * al16(4ull * n_utts) + 64 + al16(8ull * (n_utts + 1)) + al16(8ull * n_utts);
     if (d->d_meta.ensure(meta_bytes) || d->h_meta.ensure(meta_bytes)) return B2C_E_NOMEM;
     if (d->d_tok_start.ensure(8 * (total_frames + 1)) || d->d_tok_ids.ensure(2 * n_entries) ||
         d->d_tok_lp.ensure(8 * n_entries) || d->d_rowsum.ensure(std::max<u64>(8 * total_frames, 16)) ||
@@ -931,6 +942,7 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     const size_t off_run = al16(8ull * n_utts) + al16(4ull * n_utts);
     const size_t off_ord = off_run + al16(8ull * (n_utts + 1));
     const size_t off_next = off_ord + 2 * al16(4ull * n_utts);
+    const size_t off_ptr = off_next + 64;                        // [n_utts] source pointers (gather launch only)
     u64* h_run = reinterpret_cast<u64*>(hm + off_run);
     for (int i = 0; i <= n_utts; ++i) h_run[i] = run_off[i];
     int* h_ord = reinterpret_cast<int*>(hm + off_ord);           // [2 * n_utts]: class lists, then retry list
@@ -946,6 +958,18 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     const void* d_logits = nullptr;
     if (contiguous_dev) {
         d_logits = logits[0];
+#ifndef B2C_HOSTSIM
+    } else if (is_device && n_utts > 4) {
+        d_logits = d->d_logits.p;
+        const void** h_ptr = reinterpret_cast<const void**>(hm + off_ptr);
+        for (int i = 0; i < n_utts; ++i) h_ptr[i] = logits[i];
+        CUDA_OK(cudaMemcpyAsync(dm + off_ptr, h_ptr, 8ull * n_utts, cudaMemcpyHostToDevice, st));
+        const int chunks = std::max(1, std::min(64, (d->n_sm * 8 + n_utts - 1) / n_utts));
+        b2c_gather_kernel<<<n_utts * chunks, 256, 0, st>>>(reinterpret_cast<const void* const*>(dm + off_ptr), d_fo, d_T,
+                                                         static_cast<u64>(V) * (esz / 4), d->d_logits.as<u32>(), n_utts, chunks);
+        CUDA_OK(cudaGetLastError());
+        d->tm.launches += 1;
+#endif
     } else {
         d_logits = d->d_logits.p;
         // coalesce runs of utterances that are adjacent in the source into one copy

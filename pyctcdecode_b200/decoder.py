@@ -192,7 +192,11 @@ class BeamSearchDecoderCTC:
             import torch
 
             t = logits_list
-            if t.dim() != 3 or t.dtype not in (torch.float32, torch.float64):
+            if t.dim() != 3:
+                return None
+            if t.dtype in (torch.float16, torch.bfloat16):
+                t = t.float()           # widened on the device the tensor lives on (no host round trip)
+            if t.dtype not in (torch.float32, torch.float64):
                 return None
             if t.shape[2] != V:
                 raise ValueError("Input logits shape is %s, but vocabulary is size %s. Need logits of shape: "
@@ -211,15 +215,23 @@ class BeamSearchDecoderCTC:
     def _run(self, logits_list: Sequence[Any], beam_width: int, beam_prune_logp: float, token_min_logp: float,
              prune_history: bool, hotwords: Optional[Iterable[str]], hotword_weight: float, max_out_beams: int,
              lm_start_states: Optional[Sequence[Optional[AbstractLMState]]] = None, with_state: bool = True,
-             device: Optional[int] = None, texts_only: bool = False) -> Any:
+             device: Optional[int] = None, texts_only: bool = False, lengths: Optional[Sequence[int]] = None) -> Any:
         packed = self._as_packed_batch(logits_list)
+        if lengths is not None and packed is None:
+            raise ValueError("lengths= needs one padded [B, T, V] array or tensor")
         if packed is not None:
             # one [B, T, V] array / tensor: no per-utterance conversion, pointers by arithmetic
             owner, base, n, t_each, dtype_code, is_device = packed
             if n == 0:
                 return []
             step = t_each * len(self._idx2vocab) * (4 if dtype_code == 0 else 8)
-            mats = [(owner, base + i * step, t_each, dtype_code, is_device) for i in range(n)]
+            if lengths is None:
+                mats = [(owner, base + i * step, t_each, dtype_code, is_device) for i in range(n)]
+            else:
+                lens = [int(x) for x in lengths]
+                if len(lens) != n or any(x < 0 or x > t_each for x in lens):
+                    raise ValueError("lengths must hold one value in [0, T] per utterance of the padded batch")
+                mats = [(owner, base + i * step, lens[i], dtype_code, is_device) for i in range(n)]
         else:
             for logits in logits_list:
                 self._check_logits_dimension(logits)
@@ -305,10 +317,13 @@ class BeamSearchDecoderCTC:
     def decode_beams_batch(self, pool: Any, logits_list: Sequence[Any], beam_width: int = DEFAULT_BEAM_WIDTH,
                            beam_prune_logp: float = DEFAULT_PRUNE_LOGP, token_min_logp: float = DEFAULT_MIN_TOKEN_LOGP,
                            prune_history: bool = DEFAULT_PRUNE_BEAMS, hotwords: Optional[Iterable[str]] = None,
-                           hotword_weight: float = DEFAULT_HOTWORD_WEIGHT) -> List[List[OutputBeam]]:
+                           hotword_weight: float = DEFAULT_HOTWORD_WEIGHT,
+                           lengths: Optional[Sequence[int]] = None) -> List[List[OutputBeam]]:
+        """`lengths` (extension): valid frames per utterance when `logits_list` is ONE padded
+        [B, T, V] array or (CUDA) tensor -- the padding rows are never read."""
         # the reference strips the LM state for multiprocessing (decoder.py:797-799); keep that
         return self._run(logits_list, beam_width, beam_prune_logp, token_min_logp, prune_history, hotwords,
-                         hotword_weight, max_out_beams=beam_width, with_state=False)
+                         hotword_weight, max_out_beams=beam_width, with_state=False, lengths=lengths)
 
     def decode(self, logits: Any, beam_width: int = DEFAULT_BEAM_WIDTH, beam_prune_logp: float = DEFAULT_PRUNE_LOGP,
                token_min_logp: float = DEFAULT_MIN_TOKEN_LOGP, hotwords: Optional[Iterable[str]] = None,
@@ -319,9 +334,10 @@ class BeamSearchDecoderCTC:
 
     def decode_batch(self, pool: Any, logits_list: Sequence[Any], beam_width: int = DEFAULT_BEAM_WIDTH,
                      beam_prune_logp: float = DEFAULT_PRUNE_LOGP, token_min_logp: float = DEFAULT_MIN_TOKEN_LOGP,
-                     hotwords: Optional[Iterable[str]] = None, hotword_weight: float = DEFAULT_HOTWORD_WEIGHT) -> List[str]:
+                     hotwords: Optional[Iterable[str]] = None, hotword_weight: float = DEFAULT_HOTWORD_WEIGHT,
+                     lengths: Optional[Sequence[int]] = None) -> List[str]:
         return self._run(logits_list, beam_width, beam_prune_logp, token_min_logp, True, hotwords, hotword_weight,
-                         max_out_beams=1, with_state=False, texts_only=True)
+                         max_out_beams=1, with_state=False, texts_only=True, lengths=lengths)
 
     # ---- streaming: out of scope this round -------------------------------
     def get_starting_state(self) -> Any:

@@ -171,3 +171,59 @@ def test_gpu_ragged_and_empty(pkg, orc):
     assert dec.decode_batch(None, [], beam_width=25) == []
     with pytest.raises(ValueError):
         dec.decode(np.zeros((4, 7), np.float32))
+
+
+@pytest.mark.parametrize("variant", ["0", "1", "2", "general"])
+def test_gpu_kernel_variants_agree(pkg, orc, variant, monkeypatch):
+    """Every beam-kernel variant (latency-first 1024x2 / 512x3 / 256x4 CTAs per SM, and the general kernel with
+    the latency-first one disabled) must give the oracle's beams, including on frames that overflow the
+    shared-memory candidate tier (diffuse utterances force the out-of-line HBM-tier step)."""
+    if variant == "general":
+        monkeypatch.setenv("B200CTC_NO_V5", "1")
+    else:
+        monkeypatch.setenv("B200CTC_V5_VARIANT", variant)
+        monkeypatch.setenv("B200CTC_FORCE_V5", "1")
+    wl = synth.CharWorkload("B", n_words=2000, lm_order=3)
+    kw = dict(kenlm_model_path=wl.arpa, unigrams=wl.words, alpha=0.5, beta=1.0)
+    dec = pkg.build_ctcdecoder(wl.labels, **kw)
+    ora = orc.OracleDecoder(wl.labels, **kw)
+    xs = wl.batch(40_000, 10, 300, "peaky") + wl.batch(41_000, 6, 200, "diffuse")
+    threads = os.cpu_count() or 1
+    got = dec.decode_beams_batch(None, xs, beam_width=100, prune_history=True)
+    tm = dec.last_timings()
+    assert tm["kernel_variant"] == (2 if variant != "general" else tm["kernel_variant"])
+    want = ora.decode_beams_batch(xs, n_threads=threads, beam_width=100, prune_history=True)
+    for w, g in zip(want, got):
+        _compare(w, _beams(g))
+    dec2 = pkg.build_ctcdecoder(wl.labels)          # no LM: the text arena is bypassed in the latency-first kernel
+    ora2 = orc.OracleDecoder(wl.labels)
+    assert dec2.decode_batch(None, xs, beam_width=100) == ora2.decode_batch(xs, n_threads=threads, beam_width=100)
+
+
+def test_gpu_padded_batch_lengths_and_half_precision(pkg):
+    """one padded [B, T, V] CUDA tensor + lengths (the padding rows are never read), and
+    fp16 / bf16 tensors (widened to float32 on the device) decode like the per-utterance float32 arrays."""
+    import torch
+
+    wl = synth.CharWorkload("B", n_words=2000, lm_order=0)
+    dec = pkg.build_ctcdecoder(wl.labels)
+    Ts = [300, 120, 1, 0, 257, 300, 33, 64, 299]
+    xs = [wl.utterance(50_000 + i, T, "peaky") if T else np.zeros((0, wl.V), np.float32) for i, T in enumerate(Ts)]
+    want = dec.decode_batch(None, xs, beam_width=50)
+    pad = np.full((len(Ts), 300, wl.V), np.nan, np.float32)      # NaN padding: reading it would poison the result
+    for i, x in enumerate(xs):
+        pad[i, :len(x)] = x
+    dev = torch.from_numpy(pad).cuda()
+    assert dec.decode_batch(None, dev, beam_width=50, lengths=Ts) == want
+    assert dec.decode_batch(None, pad, beam_width=50, lengths=Ts) == want
+    beams = dec.decode_beams_batch(None, dev, beam_width=50, lengths=Ts)
+    assert [b[0].text for b in beams] == want
+    with pytest.raises(ValueError):
+        dec.decode_batch(None, dev, beam_width=50, lengths=Ts[:-1])
+    # half precision: the values are rounded by the caller; decoding the widened values must match
+    full = torch.from_numpy(np.stack([wl.utterance(51_000 + i, 200, "peaky") for i in range(6)]))
+    for dt in (torch.float16, torch.bfloat16):
+        h = full.to(dt).cuda()
+        ref = dec.decode_batch(None, h.float().cpu().numpy(), beam_width=50)
+        assert dec.decode_batch(None, h, beam_width=50) == ref
+        assert dec.decode(h[2], beam_width=50) == ref[2]
