@@ -331,8 +331,10 @@ B2C_HDN void b2c_bpe_force(const B2cTok* toks, const u16* tk_id, int K, const u1
         const B2cTok ti = toks[tk_id ? tk_id[k] : k];
         u32 first = B2C_NONE_U32;
         if (!(ti.flags & B2C_TF_BLANK)) {
-            for (u32 b = 0; b < n; ++b)
+            for (u32 b = 0; b < n; ++b) {
+                if (last_tok[b] == 0xFFFEu) continue;      // dead slot of the latency-first kernel (B2C_INVALID_TOK)
                 if (last_tok[b] != ti.canon) { first = b; break; }
+            }
         }
         ffirst[k] = first;
     }

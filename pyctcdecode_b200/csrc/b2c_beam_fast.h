@@ -57,6 +57,7 @@ struct B2cFastSmem {
     static constexpr u32 PT = b2c_pt_cap_c(WC);        // history-prune table slots
     B2cScalars sc;
     u32 ticket;                                       // work-queue ticket of this CTA
+    u32 holes;                                        // the current beam table has history-pruned slots (see b2c_fast_step)
     u32 wtop[B2C_FAST_NW];                            // per warp: 1 + best rank selected this frame
     alignas(16) u64 wmax[B2C_FAST_NW];                // per warp: best score key of this frame
     alignas(16) B2cFastTab<WC> tab[2];
@@ -192,16 +193,14 @@ B2C_HD void b2c_bucket_scan_warp_v(const u32* bcnt, u32* pre) {
 #define B2C_FMARK(idx) ((void)0)
 #endif
 
-// one new beam: rank r of this frame becomes beam j of the next frame (decoder.py:452-534 metadata)
+#define B2C_INVALID_TOK 0xFFFEu      // last_tok of a history-pruned slot (BPE force logic skips it)
+
+// candidate i (a group leader) becomes beam j of the next frame (decoder.py:452-534 metadata); called by the
+// thread that owns the candidate, inside the ranking loop
 template <int WC, int CAP>
 B2C_HD void b2c_fast_commit(const B2cParams& P, B2cFastSmem<WC, CAP>& S, const B2cFastTab<WC>& cur, B2cFastTab<WC>& nx,
-                            B2cChain* chain_arena, u32 chain_cap, B2cText* text_arena, u32 text_cap, int sb, int t, u32 j, u32 r,
-                            u32 flags, bool kept) {
-    // device: called by all 32 lanes of a warp (`kept` lanes commit; the others only take part in the
-    // warp-aggregated allocation of backtrack nodes)
-    if (!kept) r = 0;
-    const u32 i = S.ord[r];
-    const u32 last = S.clast[i];
+                            B2cChain* chain_arena, u32 chain_cap, B2cText* text_arena, u32 text_cap, int sb, int t, u32 j, u32 i,
+                            u32 last, u32 flags) {
     const u32 bk = S.cbk[last];
     const u32 bl = bk & 0xFFFFu, k = bk >> 16;
     const u64 cph = S.cph[last];
@@ -212,6 +211,11 @@ B2C_HD void b2c_fast_commit(const B2cParams& P, B2cFastSmem<WC, CAP>& S, const B
     const u32 word_len = (type == 1 || type == 2) ? static_cast<u32>(cur.part_len[bl]) : 0u;
     u64 th = cur.text_hash[bl];
     if (word_len > 0) th = b2c_text_append(th, cur.part_hash[bl]);
+    nx.logit[j] = S.cfold[i];
+    nx.text_hash[j] = th;
+    nx.part_hash[j] = part_hash;
+    nx.part_len[j] = static_cast<u16>(part_len);
+    nx.last_tok[j] = static_cast<u16>(meta >> 16);
     // partial_frames (decoder.py:454-461,495,513,519-523)
     const int ps0 = cur.pf_s[bl], pe0 = cur.pf_e[bl];
     int pfs, pfe;
@@ -219,34 +223,12 @@ B2C_HD void b2c_fast_commit(const B2cParams& P, B2cFastSmem<WC, CAP>& S, const B
     else if (type == 1) { pfs = t; pfe = t + 1; }
     else if (type == 2) { pfs = -1; pfe = -1; }
     else { pfs = ps0 < 0 ? t : ps0; pfe = t + 1; }
-    // backtrack chain: one shared-memory atomic per warp
-    u32 chain = cur.chain[bl];
-    const bool emits = kept && type != 0;
-    u32 id = 0;
-#if defined(__CUDA_ARCH__)
-    {
-        const u32 em = __ballot_sync(0xFFFFFFFFu, emits);
-        if (em) {
-            const u32 lane = threadIdx.x & 31;
-            const int leader = __ffs(em) - 1;
-            u32 base = 0;
-            if (static_cast<int>(lane) == leader) base = atomicAdd(&S.sc.chain_used, static_cast<u32>(__popc(em)));
-            base = __shfl_sync(0xFFFFFFFFu, base, leader);
-            id = base + __popc(em & ((1u << lane) - 1u));
-        }
-    }
-#else
-    if (emits) id = b2c_atomic_add_u32(&S.sc.chain_used, 1u);
-#endif
-    if (!kept) return;
-    nx.logit[j] = S.cfold[i];
-    nx.text_hash[j] = th;
-    nx.part_hash[j] = part_hash;
-    nx.part_len[j] = static_cast<u16>(part_len);
-    nx.last_tok[j] = static_cast<u16>(meta >> 16);
     nx.pf_s[j] = pfs;
     nx.pf_e[j] = pfe;
-    if (emits) {
+    // backtrack chain
+    u32 chain = cur.chain[bl];
+    if (type != 0) {
+        const u32 id = b2c_atomic_add_u32(&S.sc.chain_used, 1u);
         if (id < chain_cap) {
             B2cChain c;
             c.parent = chain;
@@ -289,10 +271,16 @@ B2C_HD void b2c_fast_commit(const B2cParams& P, B2cFastSmem<WC, CAP>& S, const B
 }
 
 // -----------------------------------------------------------------------------------------
-// one frame with at most CAP candidates and at most B2C_FAST_KS tokens, all in shared memory.
-// On entry: grouping table, score buckets and max_key are clear; the history-prune table holds
-// exactly the entries pslot[0 .. n_sel) of the previous frame.  The caller issues the final block
-// barrier (after it has staged the next frame's tokens).
+// one frame with at most CAP candidates and at most B2C_FAST_KS tokens, all in shared memory: three phases,
+// three block barriers (the third is issued by the caller after it has staged the next frame's tokens).
+//
+// Beam tables may have HOLES: the beam of rank r is written to slot r by the thread that ranked it, before the
+// history prune (decoder.py:550-552) is known; a slot is live iff it holds the best rank of its history key
+// (pt_min[pslot[r]] == r).  The next frame simply skips dead slots -- the relative order of the live beams,
+// which is all the reference's order dependence needs, is the rank order either way -- so there is no
+// compaction pass and no fourth phase.  S.holes says whether the current table is in that form; wtop / wmax
+// hold the number of slots and the best score key of the previous frame (per-warp maxima).
+// Invariants on entry: grouping table clear; prune table = entries pslot[0 .. n) iff S.holes.
 // -----------------------------------------------------------------------------------------
 template <int WC, int CAP>
 B2C_HD void b2c_fast_step(const B2cParams& P, B2cFastSmem<WC, CAP>& S, B2cChain* chain_arena, u32 chain_cap, B2cText* text_arena,
@@ -302,42 +290,47 @@ B2C_HD void b2c_fast_step(const B2cParams& P, B2cFastSmem<WC, CAP>& S, B2cChain*
 #endif
 ) {
     typedef B2cFastSmem<WC, CAP> SM;
-    const B2cFastTab<WC>& cur = S.tab[par];
+    B2cFastTab<WC>& cur = S.tab[par];
     B2cFastTab<WC>& nx = S.tab[par ^ 1];
-    const u32 n = S.sc.n_beams;
+    const u32 n = b2c_max_slots(S.wtop);                       // slots of the current table (live + dead)
     const u32 M = n * static_cast<u32>(K);
     const u32 flags = S.sc.flags;
     const bool is_bpe = (flags & B2C_FL_BPE) != 0, prune = (flags & B2C_FL_PRUNE) != 0;
-    const double ref = S.sc.prev_max;
+    const bool holes = S.holes != 0;
+    const double ref = b2c_key_f64(b2c_max_slots(S.wmax));     // best score of the previous frame
     const double bscale = P.bucket_scale;
     constexpr u32 hmask = SM::HT - 1, ptmask = SM::PT - 1;
     B2C_FMARK(0);
 
-    if (is_bpe) b2c_bpe_force(S.stok[sb], nullptr, K, cur.last_tok, n, S.ffirst, S.fall, &S.sc.force_break);
+    if (is_bpe) {
+        if (holes) {   // the force_next_break scan reads last_tok of every beam: mark the dead slots first
+            B2C_FOR(b, n) {
+                if (S.pt_min[S.pslot[b]] != static_cast<u32>(b)) cur.last_tok[b] = B2C_INVALID_TOK;
+            }
+            B2C_SYNC();
+        }
+        b2c_bpe_force(S.stok[sb], nullptr, K, cur.last_tok, n, S.ffirst, S.fall, &S.sc.force_break);
+    }
 
     // ---- phase A: expand (decoder.py:447-534), merge key, grouping ---------------------------------
-    if (prune) {
-        B2C_FOR(r, S.sc.n_sel) {
-            const u32 s = S.pslot[r];
-            S.pt_idx[s] = B2C_NONE_U32;
-            S.pt_min[s] = B2C_NONE_U32;
-        }
-    }
-    for (int k = 0; k < K; ++k) {
-        const B2cTok ti = S.stok[sb][k];
-        const double lp = S.slp[sb][k];
-        const u32 f_all = is_bpe ? static_cast<u32>(S.fall[k]) : 0u;
-        const u32 f_one = is_bpe ? S.ffirst[k] : B2C_NONE_U32;
-        B2C_FOR(b, n) {
+    B2C_FOR(s, B2C_NBUCKET) { S.bcnt[s] = 0; S.bhead[s] = B2C_NONE_U32; }
+    B2C_FOR(b, n) {
+        const bool live = !holes || S.pt_min[S.pslot[b]] == static_cast<u32>(b);
+        const u32 plen = cur.part_len[b];
+        const u64 ph = cur.part_hash[b];
+        const u64 th0 = cur.text_hash[b];
+        const u32 ltok = cur.last_tok[b];
+        const double lg = cur.logit[b];
+        for (int k = 0; k < K; ++k) {
             const u32 i = static_cast<u32>(k) * n + static_cast<u32>(b);
-            const u32 plen = cur.part_len[b];
-            const u64 ph = cur.part_hash[b];
-            u64 th = cur.text_hash[b];
+            if (!live) { S.cslot[i] = 0; continue; }           // never a group leader (phase B), key 0 in phase C
+            const B2cTok ti = S.stok[sb][k];
+            u64 th = th0;
             u64 nph;
             u32 nplen, type;
-            if ((ti.flags & B2C_TF_BLANK) || cur.last_tok[b] == ti.canon) {                                      // (i)
+            if ((ti.flags & B2C_TF_BLANK) || ltok == ti.canon) {                                                 // (i)
                 type = 0; nph = ph; nplen = plen;
-            } else if (is_bpe && ((ti.flags & B2C_TF_BPE_LEAD) || f_all || f_one == static_cast<u32>(b))) {      // (ii)
+            } else if (is_bpe && ((ti.flags & B2C_TF_BPE_LEAD) || S.fall[k] || S.ffirst[k] == static_cast<u32>(b))) {   // (ii)
                 type = 1; nph = ti.clean_hash; nplen = ti.clean_nchars;
                 if (plen) th = b2c_text_append(th, ph);
             } else if (!is_bpe && (ti.flags & B2C_TF_SPACE)) {                                                   // (iii)
@@ -349,11 +342,11 @@ B2C_HD void b2c_fast_step(const B2cParams& P, B2cFastSmem<WC, CAP>& S, B2cChain*
             S.cph[i] = nph | (static_cast<u64>(type) << 61);
             S.cmeta[i] = (nplen & 0xFFFFu) | (static_cast<u32>(ti.canon) << 16);
             S.cbk[i] = static_cast<u32>(b) | (static_cast<u32>(k) << 16);
-            S.cfold[i] = cur.logit[b] + lp;
+            S.cfold[i] = lg + S.slp[sb][k];
             const u64 key = b2c_fast_key(th, nph, nplen, ti.canon);
             S.ckey[i] = key;
             b2c_fence_block();
-            // group equal keys: claim a slot or join the group that owns it (the key is already mixed)
+            // group equal keys: claim a slot or join the group that owns it
             u32 slot = static_cast<u32>(key) & hmask;
             while (true) {
                 const u32 rep = b2c_atomic_cas_u32(&S.ht_idx[slot], B2C_NONE_U32, i);
@@ -372,6 +365,13 @@ B2C_HD void b2c_fast_step(const B2cParams& P, B2cFastSmem<WC, CAP>& S, B2cChain*
     B2C_FMARK(1);
 
     // ---- phase B: fold each group (decoder.py:211-224), LM / hotword fusion (:346-424), bucket, max ---
+    if (holes) {   // the validity tests of phase A are done: release the previous frame's prune entries
+        B2C_FOR(r, n) {
+            const u32 s = S.pslot[r];
+            S.pt_idx[s] = B2C_NONE_U32;
+            S.pt_min[s] = B2C_NONE_U32;
+        }
+    }
     {
         u64 tmax = 0;
         B2C_FOR(i, M) {
@@ -418,7 +418,8 @@ B2C_HD void b2c_fast_step(const B2cParams& P, B2cFastSmem<WC, CAP>& S, B2cChain*
     B2C_FMARK(2);
 
     // ---- phase C: threshold (:545-546), stable top-N (:548): rank = bucket prefix + order inside the
-    //      bucket; history keys of the selected go to the prune table; grouping slots are released ----
+    //      bucket; the owner of a selected candidate commits it as beam `rank` of the next frame and enters
+    //      its history key into the prune table (:550-552); grouping slots are released -------------------
     u32* const bpre = S.bpre[b2c_warp_id()];
     b2c_bucket_scan_warp_v(S.bcnt, bpre);
     const double max_score = b2c_key_f64(b2c_max_slots(S.wmax));
@@ -446,10 +447,9 @@ B2C_HD void b2c_fast_step(const B2cParams& P, B2cFastSmem<WC, CAP>& S, B2cChain*
                 rank += (kj > key || (kj == key && j < static_cast<u32>(i))) ? 1u : 0u;
             }
             if (rank >= width) continue;
-            S.ord[rank] = static_cast<u32>(i);
             if (rank + 1 > my_top) my_top = rank + 1;
+            const u32 last = S.clast[i];
             if (prune) {
-                const u32 last = S.clast[i];
                 const u32 bl = S.cbk[last] & 0xFFFFu;
                 const u64 cph = S.cph[last];
                 const u32 type = static_cast<u32>(cph >> 61);
@@ -472,51 +472,56 @@ B2C_HD void b2c_fast_step(const B2cParams& P, B2cFastSmem<WC, CAP>& S, B2cChain*
                 S.pslot[rank] = slot;
                 b2c_atomic_min_u32(&S.pt_min[slot], rank);
             }
+            b2c_fast_commit(P, S, cur, nx, chain_arena, chain_cap, text_arena, text_cap, sb, t, rank, static_cast<u32>(i), last, flags);
         }
         b2c_warp_max_u32_slot(my_top, S.wtop);         // the selected ranks are exactly 0 .. max(wtop)-1
     }
-    B2C_SYNC();
+    B2C_LAST_THREAD { S.holes = prune ? 1u : 0u; }
     B2C_FMARK(3);
-
-    // ---- phase D: history prune (:550-552) = keep the best rank of every key, compact, commit ------
-    const u32 nsel = b2c_max_slots(S.wtop);
-    u32 n_new = 0;
-#if defined(__CUDA_ARCH__)
-    {
-        static_assert(WC <= 32 * B2C_FAST_NW, "one rank per thread");
-        constexpr u32 kBlocks = (WC + 31) / 32;                // rank blocks of 32; warp w commits block w
-        const u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-        const u32 lt = (1u << lane) - 1u;
-        u32 mask[kBlocks];
-#pragma unroll
-        for (u32 blk = 0; blk < kBlocks; ++blk) {              // the loads of the blocks are independent
-            const u32 r = blk * 32 + lane;
-            const bool kept = r < nsel && (!prune || S.pt_min[S.pslot[r]] == r);
-            mask[blk] = __ballot_sync(0xFFFFFFFFu, kept);
-        }
-        u32 before = 0, mine = 0;
-#pragma unroll
-        for (u32 blk = 0; blk < kBlocks; ++blk) {
-            if (blk == w) { before = n_new; mine = mask[blk]; }
-            n_new += __popc(mask[blk]);
-        }
-        if (mine)
-            b2c_fast_commit(P, S, cur, nx, chain_arena, chain_cap, text_arena, text_cap, sb, t, before + __popc(mine & lt),
-                            w * 32 + lane, flags, ((mine >> lane) & 1u) != 0);
-    }
-#else
-    for (u32 r = 0; r < nsel; ++r) {
-        const bool kept = !prune || S.pt_min[S.pslot[r]] == r;
-        if (kept) b2c_fast_commit(P, S, cur, nx, chain_arena, chain_cap, text_arena, text_cap, sb, t, n_new++, r, flags, true);
-    }
-#endif
-    B2C_FOR(s, B2C_NBUCKET) { S.bcnt[s] = 0; S.bhead[s] = B2C_NONE_U32; }
-    B2C_LAST_THREAD {
-        S.sc.n_beams = n_new;
-        S.sc.n_sel = nsel;
-        S.sc.prev_max = max_score;
-    }
     B2C_FMARK(4);
+}
+
+// squeeze the dead slots out of the current table (into the other one: the caller flips its parity) and
+// leave the state the general helpers expect: sc.n_beams / sc.prev_max set, prune table clear
+template <int WC, int CAP>
+B2C_HDN void b2c_fast_compact(B2cFastSmem<WC, CAP>* Sp, int par) {
+    B2cFastSmem<WC, CAP>& S = *Sp;
+    const B2cFastTab<WC>& cur = S.tab[par];
+    B2cFastTab<WC>& nx = S.tab[par ^ 1];
+    const u32 n = b2c_max_slots(S.wtop);
+    const bool holes = S.holes != 0;
+    const double prev_max = b2c_key_f64(b2c_max_slots(S.wmax));
+    B2C_FOR(b, n) { S.ord[b] = (!holes || S.pt_min[S.pslot[b]] == static_cast<u32>(b)) ? 1u : 0u; }
+    B2C_SYNC();
+    B2C_FOR(b, n) {
+        if (!S.ord[b]) continue;
+        u32 j = 0;
+        for (int q = 0; q < b; ++q) j += S.ord[q];
+        nx.logit[j] = cur.logit[b]; nx.lm_hw[j] = cur.lm_hw[b]; nx.pscore[j] = cur.pscore[b];
+        nx.text_hash[j] = cur.text_hash[b]; nx.part_hash[j] = cur.part_hash[b]; nx.hist_hash[j] = cur.hist_hash[b];
+        nx.text_node[j] = cur.text_node[b]; nx.chain[j] = cur.chain[b];
+        nx.pf_s[j] = cur.pf_s[b]; nx.pf_e[j] = cur.pf_e[b];
+        nx.last_tok[j] = cur.last_tok[b]; nx.part_len[j] = cur.part_len[b];
+    }
+    B2C_SYNC();
+    if (holes) {
+        B2C_FOR(r, n) {
+            const u32 s = S.pslot[r];
+            S.pt_idx[s] = B2C_NONE_U32;
+            S.pt_min[s] = B2C_NONE_U32;
+        }
+    }
+    B2C_LEADER {
+        u32 live = 0;
+        for (u32 q = 0; q < n; ++q) live += S.ord[q];
+        S.sc.n_beams = live;
+        S.sc.n_sel = 0;
+        S.sc.prev_max = prev_max;
+        S.holes = 0;
+        S.wtop[0] = live;
+        for (int c = 1; c < B2C_FAST_NW; ++c) S.wtop[c] = 0;
+    }
+    B2C_SYNC();
 }
 
 // A frame that does not fit the shared-memory tier (or the token stage): the general step on the
@@ -534,6 +539,20 @@ B2C_HDN void b2c_fast_slow_step(B2cParams P, B2cLayout L, u8* smem, u8* g, int p
     b2c_clear_tables(W, C, H);
     B2C_SYNC();
     b2c_frame_step<false>(P, W, t, tk_id, tk_lp, K, K_next);      // ends with a block barrier
+    // the general step compacts its survivors and leaves their prune entries pslot[0 .. n_sel) behind
+    if (S.sc.flags & B2C_FL_PRUNE) {
+        B2C_FOR(r, S.sc.n_sel) {
+            const u32 s = S.pslot[r];
+            S.pt_idx[s] = B2C_NONE_U32;
+            S.pt_min[s] = B2C_NONE_U32;
+        }
+    }
+    B2C_LEADER {
+        S.holes = 0;
+        S.wtop[0] = S.sc.n_beams;
+        S.wmax[0] = b2c_f64_key(S.sc.prev_max);
+        for (int c = 1; c < B2C_FAST_NW; ++c) { S.wtop[c] = 0; S.wmax[c] = 0; }
+    }
 }
 
 // -----------------------------------------------------------------------------------------
@@ -592,9 +611,12 @@ B2C_HD void b2c_beam_block_fast(const B2cBeamArgs& A, int slot, u8* smem) {
         }
         B2C_FOR(s, SM::PT) { S.pt_idx[s] = B2C_NONE_U32; S.pt_min[s] = B2C_NONE_U32; }
         B2C_FOR(s, B2C_NBUCKET) { S.bcnt[s] = 0; S.bhead[s] = B2C_NONE_U32; }
-        B2C_LEADER {
+        B2C_LEADER {      // EMPTY_START_BEAM in the form b2c_fast_step expects: one slot, no holes, best score 0
             S.sc.n_sel = 0;
+            S.holes = 0;
             for (int c = 0; c < B2C_FAST_NW; ++c) { S.wmax[c] = 0; S.wtop[c] = 0; }
+            S.wtop[0] = 1;
+            S.wmax[0] = b2c_f64_key(0.0);
         }
         // stage the tokens of frame 0 (once per utterance, latency exposed)
         if (Tn > 0) {
@@ -644,9 +666,12 @@ B2C_HD void b2c_beam_block_fast(const B2cBeamArgs& A, int slot, u8* smem) {
                 plp_c = A.tok_lp[base_c + threadIdx.x];
             }
 #endif
-            const u32 Mq = S.sc.n_beams * static_cast<u32>(K);
+            const u32 Mq = b2c_max_slots(S.wtop) * static_cast<u32>(K);
             if (Mq > static_cast<u32>(CAP) || K > B2C_FAST_KS) {
                 const u64 base_a = (f0 + static_cast<u64>(t & ~(B2C_RUN - 1))) * static_cast<u64>(V) + rA.off;
+                // the general step wants a dense table: squeeze first (the squeezed table is the other one)
+                b2c_fast_compact<WC, CAP>(&S, par);
+                par ^= 1;
                 b2c_fast_slow_step<WC, CAP>(A.P, L, smem, g, par, t, A.tok_ids + base_a, A.tok_lp + base_a, K, static_cast<int>(rB.cnt));
             } else {
                 B2C_LAST_THREAD {
@@ -694,6 +719,8 @@ B2C_HD void b2c_beam_block_fast(const B2cBeamArgs& A, int slot, u8* smem) {
         O.toks = A.out_toks + ob * (f0 + static_cast<u64>(u));
         O.frames = A.out_frames + 2 * ob * (f0 + static_cast<u64>(u));
         O.states = A.out_states + static_cast<u64>(u) * ob;
+        b2c_fast_compact<WC, CAP>(&S, par);
+        par ^= 1;
         {
             B2cWork W;
             b2c_fast_work(S, L, g, par, false, W);
