@@ -49,18 +49,42 @@ def make_workload(spec):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons during the timed region (B200_PROFILING.md's clocks line), read through NVML
+    in this process every 20 ms.  (A polling `nvidia-smi -lms` child process was used first: its driver queries
+    delayed the decode calls of the timed loop by up to 2 ms per step.)  Falls back to nvidia-smi without pynvml."""
 
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
+    BITS = (("sw_power_cap", 0x4), ("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40))
 
     def __init__(self, index):
         self.index = index
-        self.samples = []
+        self.sm, self.mx, self.reasons = [], [], set()
         self.proc = None
+        self.nvml = None
+        self._stop = threading.Event()
+        self._thread = None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.index])
+                except (ValueError, IndexError):
+                    pass
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.mx.append(float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)))
+            self.nvml = pynvml
+            self._thread = threading.Thread(target=self._poll, daemon=True)
+            self._thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -69,29 +93,49 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def _poll(self):
+        nv = self.nvml
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                for name, bit in self.BITS:
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
     def _read(self):
         for line in self.proc.stdout:
-            parts = [p.strip() for p in line.split(",")]
-            if len(parts) >= 7:
-                self.samples.append(parts)
-
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for p in self.samples:
+            p = [q.strip() for q in line.split(",")]
+            if len(p) < 7:
+                continue
             try:
-                sm.append(float(p[0]))
-                mx.append(float(p[1]))
+                self.sm.append(float(p[0]))
+                self.mx.append(float(p[1]))
             except ValueError:
                 continue
             for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[3:7]):
                 if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                    self.reasons.add(name)
+
+    def stop(self):
+        if self.nvml is not None:
+            self._stop.set()
+            self._thread.join(timeout=1.0)
+            how = "nvml, 20 ms"
+        elif self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            how = "nvidia-smi -lms 100"
+        else:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML and no nvidia-smi"]}
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "how": how}
 
 
 def host_cores():
@@ -163,7 +207,7 @@ def main():
     _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
@@ -196,8 +240,10 @@ def main():
         n_gen = min(B, 8 * host_cores() + 8)
         xs = wl.batch(1, n_gen, T, args.regime)
         vals, info = [], None
+        # every step is a bounded sample; the whole run (warm-up + steps) is sized to about two minutes
+        per_step = min(8.0, 120.0 / max(1, args.warmup + args.steps))
         for i in range(args.warmup + args.steps):
-            info, _, _ = cpu_arm(wl, spec, kw, xs, beam, hot, target_cpu_seconds=8.0)
+            info, _, _ = cpu_arm(wl, spec, kw, xs, beam, hot, target_cpu_seconds=per_step)
             if i >= args.warmup:
                 vals.append(info["value"])
         v = statistics.mean(vals)
@@ -335,6 +381,7 @@ def main():
         "beam_kernel_config": {"cap_candidates": tms[-1]["cap_candidates"], "cta_threads": tms[-1]["cta_threads"],
                                "resident_ctas": tms[-1]["cta_slots"], "oversize_frames_per_step": tms[-1]["oversize_frames"],
                                "kernel_variant": tms[-1]["kernel_variant"],
+                               "inplace_single_token_frames_per_step": tms[-1]["inplace_frames"],
                                "frames_over_128_256_512_1024_2048_4096_total": tms[-1]["cand_hist"]},
         "clocks": clocks,
     }

@@ -50,6 +50,7 @@ class Timings(C.Structure):
         ("oversize_frames", C.c_longlong),
         ("kernel_variant", C.c_int),
         ("cand_hist", C.c_longlong * 7),
+        ("inplace_frames", C.c_longlong),
     ]
 
 

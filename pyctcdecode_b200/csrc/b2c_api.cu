@@ -147,7 +147,7 @@ struct B2cBeamArgs {
     int* out_frames;
     B2cLmState* out_states;
     u64* phase_clk;            // [16] profiling builds only (-DB2C_PHASE_CLOCKS)
-    u32* m_stats;              // [8] frames over 128..4096 candidates, total frames (adaptive sizing)
+    u32* m_stats;              // [8] frames over 128..4096 candidates, total frames (adaptive sizing), in-place frames
 };
 
 // kFast: every frame of every utterance handed to this launch fits the shared-memory candidate
@@ -1257,6 +1257,7 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
         for (int q = 0; q < 6; ++q) d->hint_over[q] = ms[q];
         d->hint_frames = ms[6];
         for (int q = 0; q < 7; ++q) d->tm.cand_hist[q] = ms[q];
+        d->tm.inplace_frames = ms[7];
         d->tm.oversize_frames = 0;
         for (int q = 0; q < 6; ++q)
             if (static_cast<int>(128u << q) == d->tm.cap_candidates) d->tm.oversize_frames = ms[q];

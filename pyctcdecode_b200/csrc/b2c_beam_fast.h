@@ -58,6 +58,7 @@ struct B2cFastSmem {
     B2cScalars sc;
     u32 ticket;                                       // work-queue ticket of this CTA
     u32 holes;                                        // the current beam table has history-pruned slots (see b2c_fast_step)
+    u32 cheap_bad;                                    // a thread's exactness check of b2c_fast_cheap_step failed (rare)
     u32 wtop[B2C_FAST_NW];                            // per warp: 1 + best rank selected this frame
     alignas(16) u64 wmax[B2C_FAST_NW];                // per warp: best score key of this frame
     alignas(16) B2cFastTab<WC> tab[2];
@@ -301,6 +302,9 @@ B2C_HD void b2c_fast_step(const B2cParams& P, B2cFastSmem<WC, CAP>& S, B2cChain*
     const double bscale = P.bucket_scale;
     constexpr u32 hmask = SM::HT - 1, ptmask = SM::PT - 1;
     B2C_FMARK(0);
+#ifdef B2C_DEBUG_CHEAP
+    fprintf(stderr, "general t=%d n=%u K=%d ref=%g par=%d logit0=%g last0=%u\n", t, n, K, ref, par, cur.logit[0], (unsigned)cur.last_tok[0]);
+#endif
 
     if (is_bpe) {
         if (holes) {   // the force_next_break scan reads last_tok of every beam: mark the dead slots first
@@ -481,6 +485,100 @@ B2C_HD void b2c_fast_step(const B2cParams& P, B2cFastSmem<WC, CAP>& S, B2cChain*
     B2C_FMARK(4);
 }
 
+// -----------------------------------------------------------------------------------------
+// single-token frames that cannot reorder, merge or prune anything.
+//
+// After a frame with ONE selected token c' every beam has last_char == c' (all four branches of
+// decoder.py:452-534 set last_char = char), and the beams' (text, partial_word) pairs are pairwise distinct.
+// If the next frame also selects one token c, every beam produces exactly one candidate and
+//   * c == c' or c is the blank: branch (i) for every beam -- nothing changes but logit_score += p, last_char
+//     and the end of partial_frames (decoder.py:454-461);
+//   * c is an ordinary character (not the space, regular alphabet) and there is neither an LM nor hotwords:
+//     branch (iv) for every beam -- the partial words grow by the same suffix, so keys (merge and history
+//     prune) stay pairwise distinct exactly as before, and lm_score == logit_score + 0.
+// In both cases the candidates are the old beams in the old order with the same number added to every
+// logit_score: no merge (decoder.py:211-224), the same history-prune survivors (:227-258), and -- unless
+// float64 rounding interferes -- the same order and the same threshold outcome (:545-548).  The rounding
+// caveat is CHECKED, not assumed: every slot recomputes its lm_score and the frame takes this path only if
+// the scores are still non-increasing in slot (= rank) order and all above max + beam_prune_logp; otherwise
+// the general step runs on the untouched state.  One vote barrier, no table swap, no grouping, no ranking.
+// -----------------------------------------------------------------------------------------
+enum { B2C_CHEAP_NO = 0, B2C_CHEAP_T0 = 1, B2C_CHEAP_T3 = 2 };
+B2C_HD int b2c_fast_cheap_kind(u32 flags, u32 prev_single, const B2cTok& ti) {
+    if (prev_single == B2C_NONE_U32) return B2C_CHEAP_NO;
+    if ((ti.flags & B2C_TF_BLANK) || prev_single == ti.canon) return B2C_CHEAP_T0;
+    if (!(flags & (B2C_FL_PSCORE | B2C_FL_BPE)) && !(ti.flags & B2C_TF_SPACE)) return B2C_CHEAP_T3;
+    return B2C_CHEAP_NO;
+}
+
+// returns false (state untouched) when the exactness check failed
+template <int WC, int CAP>
+B2C_HD bool b2c_fast_cheap_step(const B2cParams& P, B2cFastSmem<WC, CAP>& S, B2cChain* chain_arena, u32 chain_cap, int par, int t,
+                                int sb, int kind) {
+    B2cFastTab<WC>& cur = S.tab[par];
+    const u32 n = b2c_max_slots(S.wtop);
+    const u32 flags = S.sc.flags;
+    const bool has_lm = (flags & B2C_FL_LM) != 0;
+    const bool holes = S.holes != 0;
+    const B2cTok ti = S.stok[sb][0];
+    const double p = S.slp[sb][0];
+    // slot 0 holds rank 0 = the best score of the previous frame, and it is always live
+    const double top = b2c_combine_score(has_lm, cur.logit[0] + p, cur.lm_hw[0], cur.pscore[0], cur.part_len[0]);
+    const double thr = top + P.prune_logp;
+#ifdef B2C_DEBUG_CHEAP
+    fprintf(stderr, "cheap t=%d kind=%d n=%u top=%g thr=%g p=%g holes=%d\n", t, kind, n, top, thr, p, (int)holes);
+#endif
+    B2C_FOR(b, n) {
+        const double mine = b2c_combine_score(has_lm, cur.logit[b] + p, cur.lm_hw[b], cur.pscore[b], cur.part_len[b]);
+        bool ok = mine >= thr;
+        if (static_cast<u32>(b) + 1 < n) {
+            const double next = b2c_combine_score(has_lm, cur.logit[b + 1] + p, cur.lm_hw[b + 1], cur.pscore[b + 1], cur.part_len[b + 1]);
+            ok = ok && mine >= next;
+        }
+        if (!ok) S.cheap_bad = 1;
+    }
+    B2C_SYNC();
+    if (S.cheap_bad) {      // block-uniform
+        B2C_SYNC();
+        B2C_LEADER { S.cheap_bad = 0; }
+        return false;
+    }
+    const bool blank = (ti.flags & B2C_TF_BLANK) != 0;
+    B2C_FOR(b, n) {
+        // dead (history-pruned) slots keep their place in the score order: only their logit follows
+        cur.logit[b] = cur.logit[b] + p;
+        const bool live = !holes || S.pt_min[S.pslot[b]] == static_cast<u32>(b);
+        if (!live) continue;
+        cur.last_tok[b] = ti.canon;
+        if (kind == B2C_CHEAP_T0) {
+            if (!blank) cur.pf_e[b] = t + 1;
+        } else {
+            const int ps0 = cur.pf_s[b], pe0 = cur.pf_e[b];
+            cur.part_hash[b] = b2c_hash_append(cur.part_hash[b], ti.raw_hash, ti.raw_pow);
+            cur.part_len[b] = static_cast<u16>(cur.part_len[b] + ti.raw_nchars);
+            if (ps0 < 0) cur.pf_s[b] = t;
+            cur.pf_e[b] = t + 1;
+            const u32 id = b2c_atomic_add_u32(&S.sc.chain_used, 1u);
+            if (id < chain_cap) {
+                B2cChain c;
+                c.parent = cur.chain[b];
+                c.tok = S.sid[sb][0];
+                c.kind = B2C_CK_CONT;
+                c.has_word = 0;
+                c.ws = ps0;
+                c.we = pe0;
+                chain_arena[id] = c;
+                cur.chain[b] = id;
+            } else {
+                b2c_atomic_or_u32(&S.sc.status, B2C_ERR_CHAIN_FULL);
+            }
+        }
+    }
+    // best score of this frame = reference point of the next frame's score buckets
+    B2C_FOR(w, B2C_FAST_NW) { S.wmax[w] = w == 0 ? b2c_f64_key(top) : 0ull; }
+    return true;
+}
+
 // squeeze the dead slots out of the current table (into the other one: the caller flips its parity) and
 // leave the state the general helpers expect: sc.n_beams / sc.prev_max set, prune table clear
 template <int WC, int CAP>
@@ -569,7 +667,7 @@ B2C_HD void b2c_beam_block_fast(const B2cBeamArgs& A, int slot, u8* smem) {
     const u32 chain_cap = L.chain_cap, text_cap = L.text_cap;
     const int V = A.P.V;
     u32 st_over[6] = {0, 0, 0, 0, 0, 0};    // candidate-count histogram of the fast frames (last thread's copy counts)
-    u32 st_frames = 0;
+    u32 st_frames = 0, st_inplace = 0;
     B2C_LEADER {
         for (int q = 0; q < 6; ++q) S.sc.m_over[q] = 0;
         S.sc.m_frames = 0;
@@ -614,6 +712,7 @@ B2C_HD void b2c_beam_block_fast(const B2cBeamArgs& A, int slot, u8* smem) {
         B2C_LEADER {      // EMPTY_START_BEAM in the form b2c_fast_step expects: one slot, no holes, best score 0
             S.sc.n_sel = 0;
             S.holes = 0;
+            S.cheap_bad = 0;
             for (int c = 0; c < B2C_FAST_NW; ++c) { S.wmax[c] = 0; S.wtop[c] = 0; }
             S.wtop[0] = 1;
             S.wmax[0] = b2c_f64_key(0.0);
@@ -642,6 +741,7 @@ B2C_HD void b2c_beam_block_fast(const B2cBeamArgs& A, int slot, u8* smem) {
 #endif
         B2C_SYNC();
         int par = 0;
+        u32 prev_single = B2C_NONE_U32;   // canonical token of the previous frame if it selected exactly one
 #if defined(__CUDACC__)
 #pragma unroll 1
 #endif
@@ -667,6 +767,7 @@ B2C_HD void b2c_beam_block_fast(const B2cBeamArgs& A, int slot, u8* smem) {
             }
 #endif
             const u32 Mq = b2c_max_slots(S.wtop) * static_cast<u32>(K);
+            bool in_place = false;      // the frame updated the current table in place (no table swap)
             if (Mq > static_cast<u32>(CAP) || K > B2C_FAST_KS) {
                 const u64 base_a = (f0 + static_cast<u64>(t & ~(B2C_RUN - 1))) * static_cast<u64>(V) + rA.off;
                 // the general step wants a dense table: squeeze first (the squeezed table is the other one)
@@ -678,12 +779,21 @@ B2C_HD void b2c_beam_block_fast(const B2cBeamArgs& A, int slot, u8* smem) {
                     ++st_frames;
                     for (int c = 0; c < 6; ++c) st_over[c] += (Mq > (128u << c)) ? 1u : 0u;
                 }
+                if (K == 1 && prev_single != B2C_NONE_U32) {
+                    const int kind = b2c_fast_cheap_kind(S.sc.flags, prev_single, S.stok[sb][0]);
+                    if (kind != B2C_CHEAP_NO) in_place = b2c_fast_cheap_step<WC, CAP>(A.P, S, chain_arena, chain_cap, par, t, sb, kind);
+                    B2C_LAST_THREAD { st_inplace += in_place ? 1u : 0u; }
+                }
+                if (!in_place) {
 #if defined(B2C_PHASE_CLOCKS)
-                b2c_fast_step<WC, CAP>(A.P, S, chain_arena, chain_cap, text_arena, text_cap, par, t, sb, K, clk, clk_last);
+                    b2c_fast_step<WC, CAP>(A.P, S, chain_arena, chain_cap, text_arena, text_cap, par, t, sb, K, clk, clk_last);
 #else
-                b2c_fast_step<WC, CAP>(A.P, S, chain_arena, chain_cap, text_arena, text_cap, par, t, sb, K);
+                    b2c_fast_step<WC, CAP>(A.P, S, chain_arena, chain_cap, text_arena, text_cap, par, t, sb, K);
 #endif
+                }
             }
+            // after a single-token frame every beam ends in that token (precondition of b2c_fast_cheap_step)
+            prev_single = (K == 1) ? static_cast<u32>(S.stok[sb][0].canon) : B2C_NONE_U32;
             // stage the tokens of frame t+1
 #if defined(__CUDA_ARCH__)
             if (has_b) {
@@ -703,7 +813,7 @@ B2C_HD void b2c_beam_block_fast(const B2cBeamArgs& A, int slot, u8* smem) {
 #endif
             (void)base_b;
             B2C_SYNC();
-            par ^= 1;
+            if (!in_place) par ^= 1;
             rA = rB;
             rB = rC;
             rC = rD;
@@ -733,6 +843,7 @@ B2C_HD void b2c_beam_block_fast(const B2cBeamArgs& A, int slot, u8* smem) {
             for (int c = 0; c < 6; ++c)
                 if (st_over[c]) b2c_atomic_add_u32(A.m_stats + c, st_over[c]);
             if (st_frames) b2c_atomic_add_u32(A.m_stats + 6, st_frames);
+            if (st_inplace) b2c_atomic_add_u32(A.m_stats + 7, st_inplace);
         }
         B2C_LEADER {   // frames that took the general step counted themselves in shared memory
             for (int c = 0; c < 6; ++c)
