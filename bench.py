@@ -382,6 +382,7 @@ def main():
                                "resident_ctas": tms[-1]["cta_slots"], "oversize_frames_per_step": tms[-1]["oversize_frames"],
                                "kernel_variant": tms[-1]["kernel_variant"],
                                "inplace_single_token_frames_per_step": tms[-1]["inplace_frames"],
+                               "sorted_no_merge_frames_per_step": tms[-1]["sorted_frames"],
                                "frames_over_128_256_512_1024_2048_4096_total": tms[-1]["cand_hist"]},
         "clocks": clocks,
     }

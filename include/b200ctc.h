@@ -138,6 +138,7 @@ typedef struct {
     int kernel_variant;        /* 0 general, 1 capacity-class fast kernel, 2 latency-first kernel (beam_width <= 128) */
     long long cand_hist[7];    /* frames with more than 128,256,...,4096 candidates; [6] = frames counted */
     long long inplace_frames;  /* single-token frames that updated the beam table in place (b2c_fast_cheap_step) */
+    long long sorted_frames;   /* multi-token frames ranked by binary search, no grouping (b2c_fast_sorted_step) */
 } b2c_timings_t;
 int b2c_decoder_last_timings(const b2c_decoder_t* dec, b2c_timings_t* out);
 

@@ -51,6 +51,7 @@ class Timings(C.Structure):
         ("kernel_variant", C.c_int),
         ("cand_hist", C.c_longlong * 7),
         ("inplace_frames", C.c_longlong),
+        ("sorted_frames", C.c_longlong),
     ]
 
 

@@ -137,6 +137,13 @@ struct B2cBeamArgs {
     const double* tok_lp;
     u8* gws;                   // [slots][L.gws_bytes]
     const B2cLmState* start_states;  // optional [n_utts]
+    // streaming calls (general kernel only): input beams per utterance, what to do at the end of the call
+    const B2cStreamUtt* s_utts;      // optional [n_utts]
+    const B2cStreamBeam* s_beams;
+    const u64* s_word_hash;
+    const u32* s_word_len;
+    int fin_mode;                    // B2C_FIN_*
+    int* out_aux;                    // [n_utts][out_beams][4], streaming calls only
     // outputs
     int* out_nbeams;
     int* out_status;
@@ -147,7 +154,7 @@ struct B2cBeamArgs {
     int* out_frames;
     B2cLmState* out_states;
     u64* phase_clk;            // [16] profiling builds only (-DB2C_PHASE_CLOCKS)
-    u32* m_stats;              // [8] frames over 128..4096 candidates, total frames (adaptive sizing), in-place frames
+    u32* m_stats;              // [8] frames over 128..4096 candidates, total frames (adaptive sizing), in-place frames, sorted (no-merge) frames
 };
 
 // kFast: every frame of every utterance handed to this launch fits the shared-memory candidate
@@ -183,7 +190,17 @@ B2C_HD void b2c_beam_block(const B2cBeamArgs& A, int slot, u8* smem) {
         rec.off = 0;
         rec.cnt = 1;
         if (Tn > 0) rec = recs[0];
-        b2c_utt_begin(A.P, W, A.start_states ? A.start_states + u : nullptr, static_cast<int>(rec.cnt));
+        B2cStreamIn sin{nullptr, 0u, nullptr, nullptr};
+        int t0 = 0;
+        if (A.s_utts) {
+            const B2cStreamUtt su = A.s_utts[u];
+            sin.beams = A.s_beams + su.beam_off;
+            sin.n_beams = su.n_beams;
+            sin.word_hash = A.s_word_hash;
+            sin.word_len = A.s_word_len;
+            t0 = su.t0;
+        }
+        b2c_utt_begin(A.P, W, A.start_states ? A.start_states + u : nullptr, static_cast<int>(rec.cnt), sin);
 #if defined(__CUDACC__)
 #pragma unroll 1
 #endif
@@ -194,10 +211,10 @@ B2C_HD void b2c_beam_block(const B2cBeamArgs& A, int slot, u8* smem) {
             if (t + 1 < Tn) nxt = recs[t + 1];      // one frame ahead: hides the load latency
             const u64 base = (f0 + static_cast<u64>(t & ~(B2C_RUN - 1))) * static_cast<u64>(A.P.V) + rec.off;
             if (kFast && W.sc->n_beams * rec.cnt > L.cap_s) {
-                b2c_frame_step_slow(A.P, L, smem, g, parity, t, A.tok_ids + base, A.tok_lp + base, static_cast<int>(rec.cnt), static_cast<int>(nxt.cnt));
+                b2c_frame_step_slow(A.P, L, smem, g, parity, t + t0, A.tok_ids + base, A.tok_lp + base, static_cast<int>(rec.cnt), static_cast<int>(nxt.cnt));
                 b2c_swap_tabs(W.cur, W.nxt);   // the out-of-line step swapped its private descriptor
             } else {
-                b2c_frame_step<kFast>(A.P, W, t, A.tok_ids + base, A.tok_lp + base, static_cast<int>(rec.cnt), static_cast<int>(nxt.cnt));
+                b2c_frame_step<kFast>(A.P, W, t + t0, A.tok_ids + base, A.tok_lp + base, static_cast<int>(rec.cnt), static_cast<int>(nxt.cnt));
             }
             parity ^= 1;
             rec = nxt;
@@ -213,7 +230,8 @@ B2C_HD void b2c_beam_block(const B2cBeamArgs& A, int slot, u8* smem) {
         O.toks = A.out_toks + ob * (f0 + static_cast<u64>(u));
         O.frames = A.out_frames + 2 * ob * (f0 + static_cast<u64>(u));
         O.states = A.out_states + static_cast<u64>(u) * ob;
-        b2c_finalize(A.P, W, O);
+        O.aux = A.out_aux ? A.out_aux + 4 * static_cast<u64>(u) * ob : nullptr;
+        b2c_finalize(A.P, W, O, A.fin_mode);
         B2C_MARK(8);
     }
     B2C_LEADER {
@@ -407,7 +425,7 @@ struct b2c_decoder {
     std::unique_ptr<HostPool> pool;
     int device = 0;
     cudaStream_t stream = nullptr;
-    int V = 0, is_bpe = 0;
+    int V = 0, is_bpe = 0, has_dup_labels = 0;
     std::vector<std::string> labels, clean;
     std::vector<B2cTok> toks;
     b2c_lm* lm = nullptr;
@@ -753,7 +771,7 @@ int b2c_decoder_create(const char* const* labels, int n_labels, int is_bpe, b2c_
         t.clean_nchars = static_cast<u16>(b2c_utf8_len(clean.data(), clean.size()));
         t.canon = static_cast<u16>(i);
         for (int j = 0; j < i; ++j)
-            if (d->labels[j] == s) { t.canon = static_cast<u16>(j); break; }
+            if (d->labels[j] == s) { t.canon = static_cast<u16>(j); d->has_dup_labels = 1; break; }
         d->labels.push_back(s);
         d->clean.push_back(clean);
         d->toks.push_back(t);
@@ -865,6 +883,7 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     std::memset(&P, 0, sizeof(P));
     P.V = V;
     P.is_bpe = d->is_bpe;
+    P.has_dup_labels = d->has_dup_labels;
     P.beam_width = opts->beam_width;
     P.prune_history = opts->prune_history ? 1 : 0;
     P.out_beams = OB;
@@ -1147,12 +1166,12 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     BA.out_states = reinterpret_cast<B2cLmState*>(ds + off_ls);
     BA.out_toks = d->d_out_toks.as<u32>();
     BA.out_frames = d->d_out_frames.as<int>();
-    if (d->d_mstats.ensure(32)) return B2C_E_NOMEM;
-    CUDA_OK(cudaMemsetAsync(d->d_mstats.p, 0, 32, st));
+    if (d->d_mstats.ensure(64)) return B2C_E_NOMEM;
+    CUDA_OK(cudaMemsetAsync(d->d_mstats.p, 0, 64, st));
     BA.m_stats = d->d_mstats.as<u32>();
 #if defined(B2C_PHASE_CLOCKS)
-    if (d->d_clk.ensure(16 * 8)) return B2C_E_NOMEM;
-    CUDA_OK(cudaMemsetAsync(d->d_clk.p, 0, 16 * 8, st));
+    if (d->d_clk.ensure(32 * 8)) return B2C_E_NOMEM;
+    CUDA_OK(cudaMemsetAsync(d->d_clk.p, 0, 32 * 8, st));
     BA.phase_clk = d->d_clk.as<u64>();
 #endif
 
@@ -1247,8 +1266,8 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     hp_mark(3);                                   // wait: beam kernel + D2H
     d->tm.d2h_bytes += static_cast<long long>(small_bytes + tok_bytes + frm_bytes + 8ull * n_utts + 32);
     {
-        u32 ms[8];
-        CUDA_OK(cudaMemcpy(ms, d->d_mstats.p, 32, cudaMemcpyDeviceToHost));
+        u32 ms[16];
+        CUDA_OK(cudaMemcpy(ms, d->d_mstats.p, 64, cudaMemcpyDeviceToHost));
         d->hint_valid = true;
         d->hint_beam = opts->beam_width;
         d->hint_lm = P.lm.order > 0 ? 1 : 0;
@@ -1258,6 +1277,7 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
         d->hint_frames = ms[6];
         for (int q = 0; q < 7; ++q) d->tm.cand_hist[q] = ms[q];
         d->tm.inplace_frames = ms[7];
+        d->tm.sorted_frames = ms[8];
         d->tm.oversize_frames = 0;
         for (int q = 0; q < 6; ++q)
             if (static_cast<int>(128u << q) == d->tm.cap_candidates) d->tm.oversize_frames = ms[q];
@@ -1291,10 +1311,10 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     }
 #if defined(B2C_PHASE_CLOCKS)
     {
-        u64 hc[16];
+        u64 hc[32];
         CUDA_OK(cudaMemcpy(hc, d->d_clk.p, sizeof(hc), cudaMemcpyDeviceToHost));
         std::fprintf(stderr, "[b2c phase clocks, summed over CTAs, Mcycles]");
-        for (int q = 0; q < 9; ++q) std::fprintf(stderr, " p%d=%.2f", q, hc[q] / 1e6);
+        for (int q = 0; q < 24; ++q) std::fprintf(stderr, " p%d=%.3f", q, hc[q] / 1e6);
         std::fprintf(stderr, "  frames=%llu\n", static_cast<unsigned long long>(total_frames));
     }
 #endif

@@ -801,9 +801,15 @@ B2C_HDN void b2c_frame_step_slow(B2cParams P, B2cLayout L, u8* smem, u8* g, int 
 // -----------------------------------------------------------------------------------------
 // start of an utterance: EMPTY_START_BEAM (decoder.py:130,628) and the root text node
 // -----------------------------------------------------------------------------------------
-B2C_HDN void b2c_utt_begin(B2cParams P, B2cWork W, const B2cLmState* start_state, int K_first) {
+struct B2cStreamIn {           // streaming input of one utterance (n_beams == 0: start from EMPTY_START_BEAM)
+    const B2cStreamBeam* beams;
+    u32 n_beams;
+    const u64* word_hash;
+    const u32* word_len;
+};
+B2C_HDN void b2c_utt_begin(B2cParams P, B2cWork W, const B2cLmState* start_state, int K_first, B2cStreamIn in) {
     {
-        const u32 M0 = static_cast<u32>(K_first > 0 ? K_first : 1);
+        const u32 M0 = static_cast<u32>(K_first > 0 ? K_first : 1) * (in.n_beams > 0 ? in.n_beams : 1u);
         const B2cCandTier C0 = b2c_pick_tier(W, M0);
         b2c_clear_tables(W, C0, b2c_ht_size(M0));
     }
@@ -851,8 +857,53 @@ B2C_HDN void b2c_utt_begin(B2cParams P, B2cWork W, const B2cLmState* start_state
         c.pf_e[0] = -1;
         c.last_tok[0] = B2C_NO_TOK;
         c.part_len[0] = 0;
+        if (in.n_beams > 0) {
+            sc->n_beams = in.n_beams;
+            sc->chain_used = in.n_beams;     // chain nodes [0, n_beams) are the ROOT markers of the input beams
+        }
     }
     B2C_SYNC();
+    // streaming: the beams of the previous call, in their given (rank) order.  The words of each beam's text are
+    // replayed from the start state: text identity, LM state, raw LM score, hotword count and history window come
+    // out exactly as if the beam had been decoded in this call (reference: cached_lm_scores carried between calls)
+    B2C_FOR(b, in.n_beams) {
+        B2cScalars* sc = W.sc;
+        const B2cStreamBeam sb = in.beams[b];
+        u64 th = B2C_TEXT_SEED, hh = B2C_HIST_SEED;
+        u32 node = 0;
+        double lm_hw = P.lm.order > 0 ? 0.0 : P.hot_weight * 0;
+        for (u32 w = 0; w < sb.n_words; ++w) {
+            const u64 wh = in.word_hash[sb.word_off + w];
+            B2cTextCommit tc;
+            b2c_commit_text(P, W.text, W.text_cap, &sc->text_used, &sc->status, node, wh, in.word_len[sb.word_off + w], &tc);
+            node = tc.node;
+            lm_hw = tc.lm_hw;
+            hh = tc.hist_hash;
+            th = b2c_text_append(th, wh);
+        }
+        const B2cBeamTab& c = W.cur;
+        c.logit[b] = sb.logit;
+        c.lm_hw[b] = lm_hw;
+        c.pscore[b] = sb.part_len > 0 ? b2c_partial_score_of(P, P.n_hot > 0 || P.lm.order > 0, sb.part_hash, sb.part_len) : 0.0;
+        c.text_hash[b] = th;
+        c.part_hash[b] = sb.part_hash;
+        c.hist_hash[b] = hh;
+        c.text_node[b] = node;
+        c.chain[b] = static_cast<u32>(b);
+        c.pf_s[b] = sb.pf_s;
+        c.pf_e[b] = sb.pf_e;
+        c.last_tok[b] = static_cast<u16>(sb.last_tok);
+        c.part_len[b] = static_cast<u16>(sb.part_len);
+        B2cChain root;
+        root.parent = B2C_NONE_U32;
+        root.tok = static_cast<u16>(b);
+        root.kind = B2C_CK_ROOT;
+        root.has_word = 0;
+        root.ws = -1;
+        root.we = -1;
+        W.chain[b] = root;
+    }
+    if (in.n_beams > 0) B2C_SYNC();
 }
 
 // -----------------------------------------------------------------------------------------
@@ -868,10 +919,14 @@ struct B2cOut {              // per-utterance output views (HBM)
     u32* toks;               // [out_beams][stride]  token | kind << 16, last emission first
     int* frames;             // [out_beams][stride][2] word frames, last word first
     B2cLmState* states;      // [out_beams] LM state after the last word (last_lm_state)
+    int* aux;                // [out_beams][4] streaming: input beam the output descends from (-1: none), canonical
+                             // token of last_char (-1: None), partial_frames; nullptr outside streaming calls
     u32 stride;              // T + 1
 };
 
-B2C_HDN void b2c_finalize(B2cParams P, B2cWork W, B2cOut O) {
+B2C_HDN void b2c_finalize(B2cParams P, B2cWork W, B2cOut O, int fin_mode) {
+    const bool keep = fin_mode == B2C_FIN_KEEP;
+    const int is_eos = fin_mode == B2C_FIN_EOS ? 1 : 0;
     // on entry the grouping table is clear for ht_size(n_beams) slots (last phase D / utt_begin)
     B2cScalars* sc = W.sc;
     const u32 n = sc->n_beams;
@@ -879,8 +934,9 @@ B2C_HDN void b2c_finalize(B2cParams P, B2cWork W, B2cOut O) {
     const u32 hmask = b2c_ht_size(n) - 1;
     const B2cBeamTab cur = W.cur;
     B2C_FOR(b, n) {
+        // B2C_FIN_KEEP: new_beams = list(beams), nothing merges (decoder.py:592-593): one group per beam
         const u64 th = cur.part_len[b] ? b2c_text_append(cur.text_hash[b], cur.part_hash[b]) : cur.text_hash[b];
-        const u64 key = b2c_beam_key(th, 0, 0, B2C_NO_TOK);
+        const u64 key = keep ? b2c_beam_key(b2c_mix64(static_cast<u64>(b) + 1), 1, 0, B2C_NO_TOK) : b2c_beam_key(th, 0, 0, B2C_NO_TOK);
         C.ckey[b] = key;
         b2c_fence_block();
         b2c_group_insert(C, hmask, static_cast<u32>(b), key);
@@ -899,14 +955,18 @@ B2C_HDN void b2c_finalize(B2cParams P, B2cWork W, B2cOut O) {
         // the LAST duplicate decides the (text, next_word) split that gets scored with is_eos
         // (decoder.py:387-395: an empty next_word is scored as a word -> <unk>)
         double lm_hw;
-        if (P.lm.order > 0 || cur.part_len[last] > 0) {
+        if (keep) {
+            lm_hw = cur.lm_hw[last];        // next_word == "": cache hit on (text, False) (decoder.py:387-396)
+        } else if ((P.lm.order > 0 && (is_eos || cur.part_len[last] > 0)) || cur.part_len[last] > 0) {
+            // is_eos=False with an empty next_word is a cache hit on (text, False) as well
             B2cTextNew tn;
-            b2c_text_extend(P, W.text + cur.text_node[last], cur.part_hash[last], cur.part_len[last], 1, &tn);
+            b2c_text_extend(P, W.text + cur.text_node[last], cur.part_hash[last], cur.part_len[last], is_eos, &tn);
             lm_hw = tn.lm_hw;
         } else {
             lm_hw = cur.lm_hw[last];
         }
-        const u64 key = b2c_f64_key(b2c_combine_score(P.lm.order > 0, s, lm_hw, 0.0, 0));
+        const u64 key = keep ? b2c_f64_key(b2c_combine_score(P.lm.order > 0, s, lm_hw, cur.pscore[last], cur.part_len[last]))
+                             : b2c_f64_key(b2c_combine_score(P.lm.order > 0, s, lm_hw, 0.0, 0));
         C.ckey[b] = key;
         b2c_atomic_max_u64(&sc->max_key, key);
     }
@@ -945,22 +1005,28 @@ B2C_HDN void b2c_finalize(B2cParams P, B2cWork W, B2cOut O) {
         st.length = 0;
         for (int w = 0; w < B2C_MAX_HIST; ++w) { st.words[w] = 0; st.backoff[w] = 0.0f; }
         if (P.lm.order > 0) {
-            B2cTextNew tn;
-            b2c_text_extend(P, W.text + cur.text_node[last], cur.part_hash[last], cur.part_len[last], 1, &tn);
-            st = tn.st;
+            if (keep || (!is_eos && cur.part_len[last] == 0)) {
+                st = W.text[cur.text_node[last]].st;
+            } else {
+                B2cTextNew tn;
+                b2c_text_extend(P, W.text + cur.text_node[last], cur.part_hash[last], cur.part_len[last], is_eos, &tn);
+                st = tn.st;
+            }
         }
         O.states[r] = st;
         u32* toks = O.toks + static_cast<u64>(r) * O.stride;
         int* frames = O.frames + static_cast<u64>(r) * O.stride * 2;
         u32 nt = 0, nw = 0;
-        if (cur.part_len[last] > 0) {
+        if (!keep && cur.part_len[last] > 0) {
             frames[0] = cur.pf_s[last];
             frames[1] = cur.pf_e[last];
             nw = 1;
         }
+        int root = -1;
         u32 node = cur.chain[last];
         while (node != B2C_NONE_U32 && nt < O.stride) {
             const B2cChain c = W.chain[node];
+            if (c.kind == B2C_CK_ROOT) { root = static_cast<int>(c.tok); break; }
             toks[nt++] = static_cast<u32>(c.tok) | (static_cast<u32>(c.kind) << 16);
             if (c.kind != B2C_CK_CONT && c.has_word && nw < O.stride) {
                 frames[2 * nw] = c.ws;
@@ -971,6 +1037,13 @@ B2C_HDN void b2c_finalize(B2cParams P, B2cWork W, B2cOut O) {
         }
         O.n_tok[r] = static_cast<int>(nt);
         O.n_words[r] = static_cast<int>(nw);
+        if (O.aux) {
+            int* a = O.aux + 4 * static_cast<u64>(r);
+            a[0] = root;
+            a[1] = (keep && cur.last_tok[last] != B2C_NO_TOK) ? static_cast<int>(cur.last_tok[last]) : -1;
+            a[2] = keep ? cur.pf_s[last] : -1;
+            a[3] = keep ? cur.pf_e[last] : -1;
+        }
     }
     // leave the tables clear for the next utterance handled by this CTA (utt_begin clears again)
     B2C_SYNC();

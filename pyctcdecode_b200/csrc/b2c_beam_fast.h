@@ -59,6 +59,11 @@ struct B2cFastSmem {
     u32 ticket;                                       // work-queue ticket of this CTA
     u32 holes;                                        // the current beam table has history-pruned slots (see b2c_fast_step)
     u32 cheap_bad;                                    // a thread's exactness check of b2c_fast_cheap_step failed (rare)
+    u32 wmask[B2C_FAST_NW];                           // per warp: live slots of the current table (b2c_fast_sorted_step)
+#if defined(B2C_PHASE_CLOCKS)
+    u64 pclk[32];                                     // profiling builds: cycles between marks, thread 0
+    long long pclk_last;
+#endif
     u32 wtop[B2C_FAST_NW];                            // per warp: 1 + best rank selected this frame
     alignas(16) u64 wmax[B2C_FAST_NW];                // per warp: best score key of this frame
     alignas(16) B2cFastTab<WC> tab[2];
@@ -189,7 +194,7 @@ B2C_HD void b2c_bucket_scan_warp_v(const u32* bcnt, u32* pre) {
 }
 
 #if defined(B2C_PHASE_CLOCKS) && defined(__CUDA_ARCH__)
-#define B2C_FMARK(idx) do { if (threadIdx.x == 0) { const long long _c = clock64(); clk[idx] += static_cast<u64>(_c - clk_last); clk_last = _c; } } while (0)
+#define B2C_FMARK(idx) do { if (threadIdx.x == 0) { const long long _c = clock64(); S.pclk[idx] += static_cast<u64>(_c - S.pclk_last); S.pclk_last = _c; } } while (0)
 #else
 #define B2C_FMARK(idx) ((void)0)
 #endif
@@ -285,11 +290,7 @@ B2C_HD void b2c_fast_commit(const B2cParams& P, B2cFastSmem<WC, CAP>& S, const B
 // -----------------------------------------------------------------------------------------
 template <int WC, int CAP>
 B2C_HD void b2c_fast_step(const B2cParams& P, B2cFastSmem<WC, CAP>& S, B2cChain* chain_arena, u32 chain_cap, B2cText* text_arena,
-                          u32 text_cap, int par, int t, int sb, int K
-#if defined(B2C_PHASE_CLOCKS)
-                          , u64* clk, long long& clk_last
-#endif
-) {
+                          u32 text_cap, int par, int t, int sb, int K) {
     typedef B2cFastSmem<WC, CAP> SM;
     B2cFastTab<WC>& cur = S.tab[par];
     B2cFastTab<WC>& nx = S.tab[par ^ 1];
@@ -522,13 +523,21 @@ B2C_HD bool b2c_fast_cheap_step(const B2cParams& P, B2cFastSmem<WC, CAP>& S, B2c
     const bool holes = S.holes != 0;
     const B2cTok ti = S.stok[sb][0];
     const double p = S.slp[sb][0];
-    // slot 0 holds rank 0 = the best score of the previous frame, and it is always live
-    const double top = b2c_combine_score(has_lm, cur.logit[0] + p, cur.lm_hw[0], cur.pscore[0], cur.part_len[0]);
+    // slot 0 holds rank 0 = the best score of the previous frame, and it is always live.  Without LM and
+    // hotwords lm_score is logit_score + (+-0) + 0: adding the same p to every beam keeps the order (rounding is
+    // monotone, equal results keep their slot order), so only the threshold has to be re-checked.
+    const bool plain = (flags & B2C_FL_PSCORE) == 0;
+    const double top = plain ? (cur.logit[0] + p) + 0.0
+                             : b2c_combine_score(has_lm, cur.logit[0] + p, cur.lm_hw[0], cur.pscore[0], cur.part_len[0]);
     const double thr = top + P.prune_logp;
 #ifdef B2C_DEBUG_CHEAP
     fprintf(stderr, "cheap t=%d kind=%d n=%u top=%g thr=%g p=%g holes=%d\n", t, kind, n, top, thr, p, (int)holes);
 #endif
     B2C_FOR(b, n) {
+        if (plain) {
+            if (!((cur.logit[b] + p) + 0.0 >= thr)) S.cheap_bad = 1;
+            continue;
+        }
         const double mine = b2c_combine_score(has_lm, cur.logit[b] + p, cur.lm_hw[b], cur.pscore[b], cur.part_len[b]);
         bool ok = mine >= thr;
         if (static_cast<u32>(b) + 1 < n) {
@@ -537,7 +546,9 @@ B2C_HD bool b2c_fast_cheap_step(const B2cParams& P, B2cFastSmem<WC, CAP>& S, B2c
         }
         if (!ok) S.cheap_bad = 1;
     }
+    B2C_FMARK(17);
     B2C_SYNC();
+    B2C_FMARK(18);
     if (S.cheap_bad) {      // block-uniform
         B2C_SYNC();
         B2C_LEADER { S.cheap_bad = 0; }
@@ -576,6 +587,213 @@ B2C_HD bool b2c_fast_cheap_step(const B2cParams& P, B2cFastSmem<WC, CAP>& S, B2c
     }
     // best score of this frame = reference point of the next frame's score buckets
     B2C_FOR(w, B2C_FAST_NW) { S.wmax[w] = w == 0 ? b2c_f64_key(top) : 0ull; }
+    return true;
+}
+
+// -----------------------------------------------------------------------------------------
+// multi-token frames that cannot merge: ranking by binary search instead of grouping + buckets.
+//
+// Same precondition as b2c_fast_cheap_step: the previous frame selected ONE token c', so every beam ends in c'
+// and the (text, partial_word) pairs are pairwise distinct.  If now K >= 2 tokens with pairwise different label
+// strings are selected, none of them the space (regular alphabet) and there is neither an LM nor hotwords, then
+//   * a candidate's key is (text, partial_word [+ c], c): different tokens give different last_char, one token
+//     maps distinct beams to distinct keys -> no two candidates merge (decoder.py:211-224 is the identity);
+//   * lm_score == logit_score + 0, and inside one token the candidates are in beam (= score) order.
+// So the candidate scores form K non-increasing lists, and the position of a candidate in the stable sort of
+// decoder.py:548 is a sum of K - 1 binary searches plus its position in its own list.  No grouping table, no
+// fold, no score buckets.  Phases: liveness masks (and release of the previous prune entries) | ranks | commit
+// (one new beam per thread) -- the third barrier is the caller's.
+// -----------------------------------------------------------------------------------------
+#define B2C_SORTED_MAXK 8
+template <int WC, int CAP>
+B2C_HD bool b2c_fast_sorted_ok(const B2cParams& P, const B2cFastSmem<WC, CAP>& S, int sb, int K, u32 prev_single) {
+    if (prev_single == B2C_NONE_U32 || K < 2 || K > B2C_SORTED_MAXK || P.has_dup_labels) return false;
+    if (S.sc.flags & (B2C_FL_PSCORE | B2C_FL_BPE)) return false;
+    u32 fl = 0;
+    for (int k = 0; k < K; ++k) fl |= S.stok[sb][k].flags;
+    return (fl & B2C_TF_SPACE) == 0;
+}
+
+B2C_HD u32 b2c_live_before(const u32* wm, u32 pos) {   // live slots with index < pos (pos <= 32 * B2C_FAST_NW)
+    u32 c = 0;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (u32 w = 0; w < B2C_FAST_NW; ++w) {
+        const u32 lo = w * 32;
+        u32 m = wm[w];
+        if (pos < lo + 32) m = pos > lo ? (m & ((1u << (pos - lo)) - 1u)) : 0u;
+#if defined(__CUDA_ARCH__)
+        c += static_cast<u32>(__popc(m));
+#else
+        c += static_cast<u32>(__builtin_popcount(m));
+#endif
+    }
+    return c;
+}
+
+// number of leading slots p (of n, scores non-increasing) whose candidate for a token with log-prob lp2 sorts
+// before score s: (logit[p] + lp2) + 0 >= s (or > s when `ge` is false).  Three levels of independent probes
+// (3 x stride 32, 3 x stride 8, 7 x stride 1: 13 probes, 3 dependent rounds) instead of a 7-step dependent binary
+// search: the frame is bound by dependent-instruction latency.
+B2C_HD u32 b2c_sorted_probe(const double* logit, u32 n, u32 p, double lp2, double s, bool ge) {
+    if (p >= n) return 0u;
+    const double s2 = (logit[p] + lp2) + 0.0;
+    return (ge ? s2 >= s : s2 > s) ? 1u : 0u;
+}
+template <int WC>
+B2C_HD u32 b2c_sorted_count(const double* logit, u32 n, double lp2, double s, bool ge) {
+    static_assert(WC <= 128, "radix search covers 128 slots");
+    // invariant: slots < base sort before s, slot base + width does not (or is past the end)
+    u32 base = 32 * (b2c_sorted_probe(logit, n, 31, lp2, s, ge) + b2c_sorted_probe(logit, n, 63, lp2, s, ge) +
+                     b2c_sorted_probe(logit, n, 95, lp2, s, ge));
+    base += 8 * (b2c_sorted_probe(logit, n, base + 7, lp2, s, ge) + b2c_sorted_probe(logit, n, base + 15, lp2, s, ge) +
+                 b2c_sorted_probe(logit, n, base + 23, lp2, s, ge));
+    u32 cnt = 0;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (u32 q = 0; q < 7; ++q) cnt += b2c_sorted_probe(logit, n, base + q, lp2, s, ge);
+    return base + cnt;
+}
+
+// returns false (state untouched) when the best score is not finite
+template <int WC, int CAP>
+B2C_HD bool b2c_fast_sorted_step(const B2cParams& P, B2cFastSmem<WC, CAP>& S, B2cChain* chain_arena, u32 chain_cap, int par, int t,
+                                 int sb, int K, u32 prev_single) {
+    typedef B2cFastSmem<WC, CAP> SM;
+    B2cFastTab<WC>& cur = S.tab[par];
+    B2cFastTab<WC>& nx = S.tab[par ^ 1];
+    const u32 n = b2c_max_slots(S.wtop);
+    const bool prune = (S.sc.flags & B2C_FL_PRUNE) != 0;
+    const bool holes = S.holes != 0;
+    constexpr u32 ptmask = SM::PT - 1;
+    // best score of the frame (block-uniform): rank-0 beam + best token
+    double top = (cur.logit[0] + S.slp[sb][0]) + 0.0;
+    for (int k = 1; k < K; ++k) {
+        const double v = (cur.logit[0] + S.slp[sb][k]) + 0.0;
+        if (v > top || v != v) top = v;
+    }
+    if (!(top >= -1.7976931348623157e308)) return false;      // NaN / -inf (only from such input): general step
+    const double thr = top + P.prune_logp;
+    const u32 width = static_cast<u32>(P.beam_width);
+
+    // ---- phase 1: which slots are live; the live owner of a prune entry releases it ----------------
+#if !defined(__CUDA_ARCH__)
+    for (int w = 0; w < B2C_FAST_NW; ++w) S.wmask[w] = 0;
+#endif
+    B2C_FOR(b, WC) {
+        bool live = static_cast<u32>(b) < n;
+        if (live && holes) {
+            const u32 ps = S.pslot[b];
+            live = S.pt_min[ps] == static_cast<u32>(b);
+            if (live) { S.pt_idx[ps] = B2C_NONE_U32; S.pt_min[ps] = B2C_NONE_U32; }
+        }
+#if defined(__CUDA_ARCH__)
+        const u32 m = __ballot_sync(0xFFFFFFFFu, live);
+        if ((threadIdx.x & 31) == 0) S.wmask[threadIdx.x >> 5] = m;
+#else
+        if (live) S.wmask[b >> 5] |= 1u << (b & 31);
+#endif
+    }
+    B2C_SYNC();
+    B2C_FMARK(20);
+
+    // ---- phase 2: threshold (:545-546) and rank (:548) of every candidate ---------------------------
+    {
+        u32 wm[B2C_FAST_NW];
+        for (int w = 0; w < B2C_FAST_NW; ++w) wm[w] = S.wmask[w];
+        u32 my_top = 0;
+        B2C_FOR(b, n) {
+            if (!((S.wmask[b >> 5] >> (b & 31)) & 1u)) continue;
+            const u32 lb = b2c_live_before(wm, static_cast<u32>(b));
+            const double lg = cur.logit[b];
+            for (int k = 0; k < K; ++k) {
+                const double s = (lg + S.slp[sb][k]) + 0.0;
+                if (!(s >= thr)) continue;
+                u32 rank = lb;      // same token: the live beams before this one (equal scores keep beam order)
+                for (int k2 = 0; k2 < K && rank < width; ++k2) {
+                    if (k2 == k) continue;
+                    const double lp2 = S.slp[sb][k2];
+                    // candidates of token k2 that sort before (k, b): score greater, or equal and enumerated earlier
+                    rank += b2c_live_before(wm, b2c_sorted_count<WC>(cur.logit, n, lp2, s, k2 < k));
+                }
+                if (rank >= width) continue;
+                S.ord[rank] = static_cast<u32>(b) | (static_cast<u32>(k) << 16);
+                if (rank + 1 > my_top) my_top = rank + 1;
+            }
+        }
+        b2c_warp_max_u32_slot(my_top, S.wtop);         // the selected ranks are exactly 0 .. max(wtop)-1
+    }
+    B2C_FMARK(21);
+    B2C_SYNC();
+    B2C_FMARK(22);
+
+    // ---- phase 3: rank r becomes beam r (decoder.py:452-534 metadata), history key into the prune table ---
+    const u32 n_new = b2c_max_slots(S.wtop);
+    B2C_FOR(r, n_new) {
+        const u32 e = S.ord[r];
+        const u32 b = e & 0xFFFFu, k = e >> 16;
+        const B2cTok ti = S.stok[sb][k];
+        const bool blank = (ti.flags & B2C_TF_BLANK) != 0;
+        const bool same = blank || ti.canon == prev_single;                      // branch (i), else branch (iv)
+        const u64 ph = cur.part_hash[b];
+        const u32 plen = cur.part_len[b];
+        const int ps0 = cur.pf_s[b], pe0 = cur.pf_e[b];
+        u64 nph = ph;
+        u32 nplen = plen;
+        u32 chain = cur.chain[b];
+        int pfs = ps0, pfe = blank ? pe0 : t + 1;
+        if (!same) {
+            nph = b2c_hash_append(ph, ti.raw_hash, ti.raw_pow);
+            nplen = plen + ti.raw_nchars;
+            pfs = ps0 < 0 ? t : ps0;
+            const u32 id = b2c_atomic_add_u32(&S.sc.chain_used, 1u);
+            if (id < chain_cap) {
+                B2cChain c;
+                c.parent = chain;
+                c.tok = S.sid[sb][k];
+                c.kind = B2C_CK_CONT;
+                c.has_word = 0;
+                c.ws = ps0;
+                c.we = pe0;
+                chain_arena[id] = c;
+                chain = id;
+            } else {
+                b2c_atomic_or_u32(&S.sc.status, B2C_ERR_CHAIN_FULL);
+            }
+        }
+        const u64 hh = cur.hist_hash[b];
+        nx.logit[r] = cur.logit[b] + S.slp[sb][k];
+        nx.lm_hw[r] = cur.lm_hw[b];
+        nx.pscore[r] = same ? cur.pscore[b] : 0.0;
+        nx.text_hash[r] = cur.text_hash[b];
+        nx.part_hash[r] = nph;
+        nx.hist_hash[r] = hh;
+        nx.text_node[r] = cur.text_node[b];
+        nx.chain[r] = chain;
+        nx.pf_s[r] = pfs;
+        nx.pf_e[r] = pfe;
+        nx.last_tok[r] = ti.canon;
+        nx.part_len[r] = static_cast<u16>(nplen);
+        if (prune) {
+            const u64 hk = b2c_fast_key(hh, nph, nplen & 0xFFFFu, ti.canon);
+            S.phk[r] = hk;
+            b2c_fence_block();
+            u32 slot = static_cast<u32>(hk) & ptmask;
+            while (true) {
+                const u32 rep = b2c_atomic_cas_u32(&S.pt_idx[slot], B2C_NONE_U32, static_cast<u32>(r));
+                if (rep == B2C_NONE_U32) break;
+                b2c_fence_block();
+                if (S.phk[rep] == hk) break;
+                slot = (slot + 1) & ptmask;
+            }
+            S.pslot[r] = slot;
+            b2c_atomic_min_u32(&S.pt_min[slot], static_cast<u32>(r));
+        }
+    }
+    B2C_FOR(w, B2C_FAST_NW) { S.wmax[w] = w == 0 ? b2c_f64_key(top) : 0ull; }
+    B2C_LAST_THREAD { S.holes = prune ? 1u : 0u; }
     return true;
 }
 
@@ -667,18 +885,16 @@ B2C_HD void b2c_beam_block_fast(const B2cBeamArgs& A, int slot, u8* smem) {
     const u32 chain_cap = L.chain_cap, text_cap = L.text_cap;
     const int V = A.P.V;
     u32 st_over[6] = {0, 0, 0, 0, 0, 0};    // candidate-count histogram of the fast frames (last thread's copy counts)
-    u32 st_frames = 0, st_inplace = 0;
+    u32 st_frames = 0, st_inplace = 0, st_sorted = 0;
     B2C_LEADER {
         for (int q = 0; q < 6; ++q) S.sc.m_over[q] = 0;
         S.sc.m_frames = 0;
     }
-#if defined(B2C_PHASE_CLOCKS)
-    u64 clk[16];
-    for (int q = 0; q < 16; ++q) clk[q] = 0;
-    long long clk_last = 0;
-#if defined(__CUDA_ARCH__)
-    clk_last = clock64();
-#endif
+#if defined(B2C_PHASE_CLOCKS) && defined(__CUDA_ARCH__)
+    if (threadIdx.x == 0) {
+        for (int q = 0; q < 32; ++q) S.pclk[q] = 0;
+        S.pclk_last = clock64();
+    }
 #endif
 
     while (true) {
@@ -690,16 +906,25 @@ B2C_HD void b2c_beam_block_fast(const B2cBeamArgs& A, int slot, u8* smem) {
         const int Tn = A.T[u];
         const u64 f0 = A.frame_off[u];
         const B2cFrameRec* recs = A.tok_rec + f0;
-        B2cFrameRec rA, rB, rC;
-        rA.off = rB.off = rC.off = 0;
-        rA.cnt = rB.cnt = rC.cnt = 1;
-        if (Tn > 0) rA = recs[0];
-        if (Tn > 1) rB = recs[1];
-        if (Tn > 2) rC = recs[2];
+        // prefetch distances (frames): frame records RD ahead, token ids / log-probs ID ahead, label records 1 ahead.
+        // An in-place frame (b2c_fast_cheap_step) lasts a few hundred cycles, less than one trip to L2, so the
+        // resident-batch variant (register headroom) looks further ahead than the throughput variants.
+        constexpr int RD = CAP >= 1024 ? 6 : 3;
+        constexpr int ID = CAP >= 1024 ? 4 : 2;
+        (void)ID;
+        B2cFrameRec rq[RD];                       // rq[j]: record of frame t + j
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+        for (int j = 0; j < RD; ++j) {
+            rq[j].off = 0;
+            rq[j].cnt = 1;
+            if (j < Tn) rq[j] = recs[j];
+        }
         {
             B2cWork W;
             b2c_fast_work(S, L, g, 0, false, W);
-            b2c_utt_begin(A.P, W, A.start_states ? A.start_states + u : nullptr, static_cast<int>(rA.cnt));
+            b2c_utt_begin(A.P, W, A.start_states ? A.start_states + u : nullptr, static_cast<int>(rq[0].cnt), B2cStreamIn{nullptr, 0u, nullptr, nullptr});
         }
         B2C_FOR(s, SM::HT) {
             S.ht_idx[s] = B2C_NONE_U32;
@@ -719,8 +944,8 @@ B2C_HD void b2c_beam_block_fast(const B2cBeamArgs& A, int slot, u8* smem) {
         }
         // stage the tokens of frame 0 (once per utterance, latency exposed)
         if (Tn > 0) {
-            const u64 base0 = f0 * static_cast<u64>(V) + rA.off;
-            const u32 k0 = rA.cnt < B2C_FAST_KS ? rA.cnt : B2C_FAST_KS;
+            const u64 base0 = f0 * static_cast<u64>(V) + rq[0].off;
+            const u32 k0 = rq[0].cnt < B2C_FAST_KS ? rq[0].cnt : B2C_FAST_KS;
             B2C_FOR(c, k0) {
                 const u16 id = A.tok_ids[base0 + c];
                 S.stok[0][c] = A.P.toks[id];
@@ -729,14 +954,21 @@ B2C_HD void b2c_beam_block_fast(const B2cBeamArgs& A, int slot, u8* smem) {
             }
         }
 #if defined(__CUDA_ARCH__)
-        // register pipeline: token `threadIdx.x` of frame t+1 (id, log-prob) is loaded one frame ahead of
+        // register pipeline: token `threadIdx.x` of frame t+ID (id, log-prob) is loaded ID-1 frames ahead of
         // its label record, which is loaded one frame ahead of the shared-memory store
-        u16 pid_b = 0;
-        double plp_b = 0.0;
-        if (Tn > 1 && threadIdx.x < (rB.cnt < B2C_FAST_KS ? rB.cnt : B2C_FAST_KS)) {
-            const u64 base1 = (f0 + static_cast<u64>(1 & ~(B2C_RUN - 1))) * static_cast<u64>(V) + rB.off;
-            pid_b = A.tok_ids[base1 + threadIdx.x];
-            plp_b = A.tok_lp[base1 + threadIdx.x];
+        u32 pidq[ID - 1];                         // [j]: token `threadIdx.x` of frame t + 1 + j (u32: a u16 array gets
+                                                  // packed two to a register, and the packing consumes a load at once)
+        double plpq[ID - 1];
+#pragma unroll
+        for (int j = 0; j < ID - 1; ++j) {
+            pidq[j] = 0;
+            plpq[j] = 0.0;
+            const int f = j + 1;
+            if (f < Tn && threadIdx.x < (rq[f].cnt < B2C_FAST_KS ? rq[f].cnt : B2C_FAST_KS)) {
+                const u64 basef = (f0 + static_cast<u64>(f & ~(B2C_RUN - 1))) * static_cast<u64>(V) + rq[f].off;
+                pidq[j] = A.tok_ids[basef + threadIdx.x];
+                plpq[j] = A.tok_lp[basef + threadIdx.x];
+            }
         }
 #endif
         B2C_SYNC();
@@ -746,47 +978,54 @@ B2C_HD void b2c_beam_block_fast(const B2cBeamArgs& A, int slot, u8* smem) {
 #pragma unroll 1
 #endif
         for (int t = 0; t < Tn; ++t) {
-            B2cFrameRec rD;
-            rD.off = 0;
-            rD.cnt = 1;
-            if (t + 3 < Tn) rD = recs[t + 3];
-            const int K = static_cast<int>(rA.cnt);
+            const int K = static_cast<int>(rq[0].cnt);
             const int sb = t & 1;
-            const u32 kb = (t + 1 < Tn) ? (rB.cnt < B2C_FAST_KS ? rB.cnt : B2C_FAST_KS) : 0u;
-            const u64 base_b = (f0 + static_cast<u64>((t + 1) & ~(B2C_RUN - 1))) * static_cast<u64>(V) + rB.off;
+            const u32 kb = (t + 1 < Tn) ? (rq[1].cnt < B2C_FAST_KS ? rq[1].cnt : B2C_FAST_KS) : 0u;
+            const u64 base_b = (f0 + static_cast<u64>((t + 1) & ~(B2C_RUN - 1))) * static_cast<u64>(V) + rq[1].off;
 #if defined(__CUDA_ARCH__)
             B2cTok ptk;
             const bool has_b = threadIdx.x < kb;
-            if (has_b) ptk = A.P.toks[pid_b];
-            u16 pid_c = 0;
-            double plp_c = 0.0;
-            if (t + 2 < Tn && threadIdx.x < (rC.cnt < B2C_FAST_KS ? rC.cnt : B2C_FAST_KS)) {
-                const u64 base_c = (f0 + static_cast<u64>((t + 2) & ~(B2C_RUN - 1))) * static_cast<u64>(V) + rC.off;
-                pid_c = A.tok_ids[base_c + threadIdx.x];
-                plp_c = A.tok_lp[base_c + threadIdx.x];
-            }
+            if (has_b) ptk = A.P.toks[pidq[0]];
 #endif
             const u32 Mq = b2c_max_slots(S.wtop) * static_cast<u32>(K);
+            B2C_FMARK(16);
             bool in_place = false;      // the frame updated the current table in place (no table swap)
             if (Mq > static_cast<u32>(CAP) || K > B2C_FAST_KS) {
-                const u64 base_a = (f0 + static_cast<u64>(t & ~(B2C_RUN - 1))) * static_cast<u64>(V) + rA.off;
+                const u64 base_a = (f0 + static_cast<u64>(t & ~(B2C_RUN - 1))) * static_cast<u64>(V) + rq[0].off;
                 // the general step wants a dense table: squeeze first (the squeezed table is the other one)
                 b2c_fast_compact<WC, CAP>(&S, par);
                 par ^= 1;
-                b2c_fast_slow_step<WC, CAP>(A.P, L, smem, g, par, t, A.tok_ids + base_a, A.tok_lp + base_a, K, static_cast<int>(rB.cnt));
+                b2c_fast_slow_step<WC, CAP>(A.P, L, smem, g, par, t, A.tok_ids + base_a, A.tok_lp + base_a, K, static_cast<int>(rq[1].cnt));
             } else {
                 B2C_LAST_THREAD {
                     ++st_frames;
                     for (int c = 0; c < 6; ++c) st_over[c] += (Mq > (128u << c)) ? 1u : 0u;
                 }
+                bool done = false;          // the frame was handled by one of the two special steps
                 if (K == 1 && prev_single != B2C_NONE_U32) {
                     const int kind = b2c_fast_cheap_kind(S.sc.flags, prev_single, S.stok[sb][0]);
                     if (kind != B2C_CHEAP_NO) in_place = b2c_fast_cheap_step<WC, CAP>(A.P, S, chain_arena, chain_cap, par, t, sb, kind);
                     B2C_LAST_THREAD { st_inplace += in_place ? 1u : 0u; }
+                    done = in_place;
+                    if (in_place) B2C_FMARK(5);
+                } else if (b2c_fast_sorted_ok<WC, CAP>(A.P, S, sb, K, prev_single)) {
+                    done = b2c_fast_sorted_step<WC, CAP>(A.P, S, chain_arena, chain_cap, par, t, sb, K, prev_single);
+                    B2C_LAST_THREAD { st_sorted += done ? 1u : 0u; }
+                    if (done) B2C_FMARK(7);
                 }
-                if (!in_place) {
+                if (!done) {
 #if defined(B2C_PHASE_CLOCKS)
-                    b2c_fast_step<WC, CAP>(A.P, S, chain_arena, chain_cap, text_arena, text_cap, par, t, sb, K, clk, clk_last);
+#if defined(__CUDA_ARCH__)
+                    const long long c0 = clock64();
+#endif
+                    b2c_fast_step<WC, CAP>(A.P, S, chain_arena, chain_cap, text_arena, text_cap, par, t, sb, K);
+#if defined(__CUDA_ARCH__)
+                    if (threadIdx.x == 0) {      // general frames by token count: cycles in 9..11, frames in 12..14
+                        const int cls = K == 1 ? 0 : (K == 2 ? 1 : 2);
+                        S.pclk[9 + cls] += static_cast<u64>(clock64() - c0);
+                        S.pclk[12 + cls] += 1;
+                    }
+#endif
 #else
                     b2c_fast_step<WC, CAP>(A.P, S, chain_arena, chain_cap, text_arena, text_cap, par, t, sb, K);
 #endif
@@ -798,11 +1037,24 @@ B2C_HD void b2c_beam_block_fast(const B2cBeamArgs& A, int slot, u8* smem) {
 #if defined(__CUDA_ARCH__)
             if (has_b) {
                 S.stok[sb ^ 1][threadIdx.x] = ptk;
-                S.slp[sb ^ 1][threadIdx.x] = plp_b;
-                S.sid[sb ^ 1][threadIdx.x] = pid_b;
+                S.slp[sb ^ 1][threadIdx.x] = plpq[0];
+                S.sid[sb ^ 1][threadIdx.x] = static_cast<u16>(pidq[0]);
             }
-            pid_b = pid_c;
-            plp_b = plp_c;
+            // rotate FIRST (values loaded at least one frame ago), THEN issue the new loads into the freed
+            // registers: nothing touches them before the next rotation, a whole frame later.  (Loading at the top
+            // of the iteration and rotating here made every frame wait for the loads it had just issued.)
+#pragma unroll
+            for (int j = 0; j + 1 < ID - 1; ++j) {
+                pidq[j] = pidq[j + 1];
+                plpq[j] = plpq[j + 1];
+            }
+            pidq[ID - 2] = 0;
+            plpq[ID - 2] = 0.0;
+            if (t + ID < Tn && threadIdx.x < (rq[ID].cnt < B2C_FAST_KS ? rq[ID].cnt : B2C_FAST_KS)) {
+                const u64 base_n = (f0 + static_cast<u64>((t + ID) & ~(B2C_RUN - 1))) * static_cast<u64>(V) + rq[ID].off;
+                pidq[ID - 2] = A.tok_ids[base_n + threadIdx.x];
+                plpq[ID - 2] = A.tok_lp[base_n + threadIdx.x];
+            }
 #else
             B2C_FOR(c, kb) {
                 const u16 id = A.tok_ids[base_b + c];
@@ -812,11 +1064,17 @@ B2C_HD void b2c_beam_block_fast(const B2cBeamArgs& A, int slot, u8* smem) {
             }
 #endif
             (void)base_b;
+            B2C_FMARK(19);
             B2C_SYNC();
+            B2C_FMARK(6);
             if (!in_place) par ^= 1;
-            rA = rB;
-            rB = rC;
-            rC = rD;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+            for (int j = 0; j + 1 < RD; ++j) rq[j] = rq[j + 1];
+            rq[RD - 1].off = 0;
+            rq[RD - 1].cnt = 1;
+            if (t + RD < Tn) rq[RD - 1] = recs[t + RD];
         }
         B2cOut O;
         const u64 ob = static_cast<u64>(A.P.out_beams);
@@ -829,12 +1087,13 @@ B2C_HD void b2c_beam_block_fast(const B2cBeamArgs& A, int slot, u8* smem) {
         O.toks = A.out_toks + ob * (f0 + static_cast<u64>(u));
         O.frames = A.out_frames + 2 * ob * (f0 + static_cast<u64>(u));
         O.states = A.out_states + static_cast<u64>(u) * ob;
+        O.aux = nullptr;
         b2c_fast_compact<WC, CAP>(&S, par);
         par ^= 1;
         {
             B2cWork W;
             b2c_fast_work(S, L, g, par, false, W);
-            b2c_finalize(A.P, W, O);
+            b2c_finalize(A.P, W, O, B2C_FIN_EOS);
         }
         B2C_FMARK(8);
     }
@@ -844,6 +1103,7 @@ B2C_HD void b2c_beam_block_fast(const B2cBeamArgs& A, int slot, u8* smem) {
                 if (st_over[c]) b2c_atomic_add_u32(A.m_stats + c, st_over[c]);
             if (st_frames) b2c_atomic_add_u32(A.m_stats + 6, st_frames);
             if (st_inplace) b2c_atomic_add_u32(A.m_stats + 7, st_inplace);
+            if (st_sorted) b2c_atomic_add_u32(A.m_stats + 8, st_sorted);
         }
         B2C_LEADER {   // frames that took the general step counted themselves in shared memory
             for (int c = 0; c < 6; ++c)
@@ -853,6 +1113,6 @@ B2C_HD void b2c_beam_block_fast(const B2cBeamArgs& A, int slot, u8* smem) {
     }
 #if defined(B2C_PHASE_CLOCKS) && defined(__CUDA_ARCH__)
     if (threadIdx.x == 0 && A.phase_clk)
-        for (int c = 0; c < 16; ++c) atomicAdd(A.phase_clk + c, clk[c]);
+        for (int c = 0; c < 32; ++c) atomicAdd(A.phase_clk + c, S.pclk[c]);
 #endif
 }

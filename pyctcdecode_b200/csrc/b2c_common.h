@@ -151,6 +151,7 @@ struct B2cHot { u64 key; u32 min_len; u32 is_word; };                // hotword 
 struct B2cParams {
     int V;
     int is_bpe;
+    int has_dup_labels;        // two token ids share a label string (their candidates can merge across tokens)
     int beam_width;
     int prune_history;
     int hist_n;                // max(1, lm order - 1)   (reference decoder.py:244)
@@ -171,7 +172,7 @@ struct B2cParams {
 // ---------------------------------------------------------------------------------------
 // per-utterance prefix structures kept in HBM arenas
 // ---------------------------------------------------------------------------------------
-enum { B2C_CK_CONT = 0, B2C_CK_SPACE = 1, B2C_CK_BPE = 2 };
+enum { B2C_CK_CONT = 0, B2C_CK_SPACE = 1, B2C_CK_BPE = 2, B2C_CK_ROOT = 3 };   // ROOT: input beam `tok` of a streaming call
 struct B2cChain {              // 16 bytes: one emitted (non-blank, non-repeat) token of a beam
     u32 parent;
     u16 tok;
@@ -187,6 +188,23 @@ struct B2cText {               // one distinct "text" (sequence of finished word
     u32 hw_count;              // hotword unigram matches in the text
     u32 n_win;
 };
+
+// streaming (reference partial_decode_beams, decoder.py:669-728): the beams a call starts from, string-free.
+// The host hashes the words of every input beam; the kernel replays them through the LM / hotword scorer, which
+// reproduces what the reference keeps in cached_lm_scores (raw LM score, LM state) without carrying a cache.
+struct B2cStreamBeam {
+    u64 part_hash;             // partial_word
+    double logit;              // logit_score
+    u32 word_off, n_words;     // finished words of `text`: word_hash / word_len [word_off, word_off + n_words)
+    u32 part_len;              // python len(partial_word)
+    u32 last_tok;              // canonical token id of last_char, B2C_NO_TOK for None
+    int pf_s, pf_e;            // partial_frames
+};
+struct B2cStreamUtt { u32 beam_off, n_beams; int t0; u32 pad; };   // t0: processed_frames
+// what _finalize_beams does at the end of a call (decoder.py:558-602)
+enum { B2C_FIN_EOS = 0,        // force_next_word or is_end, scored with is_eos=True  (decode_beams; is_end=True)
+       B2C_FIN_FLUSH = 1,      // force_next_word=True, is_end=False: partial words become words, no </s>
+       B2C_FIN_KEEP = 2 };     // neither: beams keep their partial words (streaming continues)
 
 #define B2C_LOG_MIN_CLIP (-0x1.144f69ff9ffc4p+5)   // np.log(1e-15)
 #define B2C_AVG_TOKEN_LEN 6

@@ -316,3 +316,19 @@ def make_workload(spec):
     kw = dict(spec)
     kind = kw.pop("kind")
     return CharWorkload(**kw) if kind == "char" else BpeWorkload(**kw)
+
+
+def special_step_cases(wl, n_cases=60, seed=7):
+    """Seeded (logits, decode kwargs) pairs that drive the kernel's single-token special steps (in-place frames,
+    binary-search ranking of merge-free frames): peaky logits of varying sharpness, integer-valued logits (exact
+    score ties), small and large beams, all prune settings.  Shared by the hostsim and the GPU parity tests."""
+    rng = np.random.default_rng(seed)
+    for i in range(n_cases):
+        T = int(rng.integers(20, 300))
+        margin = float(rng.choice([5.0, 6.0, 7.0, 8.0, 10.0]))
+        x = (wl.utterance(9000 + i, T, "peaky") * (margin / 8.0)).astype(np.float32)
+        if i % 6 == 0:
+            x = np.round(x).astype(np.float32)
+        kw = dict(beam_width=int(rng.choice([2, 5, 17, 50, 100, 128])), prune_history=bool(i % 2),
+                  beam_prune_logp=float(rng.choice([-10.0, -3.0, -20.0])), token_min_logp=float(rng.choice([-5.0, -3.0, -7.0])))
+        yield x, kw

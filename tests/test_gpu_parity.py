@@ -227,3 +227,19 @@ def test_gpu_padded_batch_lengths_and_half_precision(pkg):
         ref = dec.decode_batch(None, h.float().cpu().numpy(), beam_width=50)
         assert dec.decode_batch(None, h, beam_width=50) == ref
         assert dec.decode(h[2], beam_width=50) == ref[2]
+
+
+def test_gpu_special_single_token_steps(pkg, orc):
+    """In-place single-token frames and merge-free sorted frames (b2c_fast_cheap_step / b2c_fast_sorted_step)
+    on the device against the oracle: varying sharpness, exact ties (integer logits), beams from 2 to 128."""
+    wl = synth.make_workload(dict(kind="char", vocab="B", n_words=400, lm_order=0))
+    dec = pkg.build_ctcdecoder(wl.labels)
+    ora = orc.OracleDecoder(wl.labels)
+    inplace = ranked = 0
+    for x, kw in synth.special_step_cases(wl):
+        got = _beams(dec.decode_beams(x, **kw))
+        tm = dec.last_timings()
+        inplace += tm["inplace_frames"]
+        ranked += tm["sorted_frames"]
+        _compare(ora.decode_beams(x, **kw), got)
+    assert inplace > 1000 and ranked > 100

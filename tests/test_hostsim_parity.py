@@ -134,3 +134,36 @@ def test_hostsim_errors(sim):
     with pytest.raises(ValueError):
         dec.decode(np.zeros((4,), np.float32))
     assert dec.decode(np.zeros((0, 29))) == ""
+
+
+def test_hostsim_special_single_token_steps(sim):
+    """The in-place single-token frames and the merge-free sorted frames of the latency-first kernel
+    (b2c_fast_cheap_step / b2c_fast_sorted_step) against the oracle, incl. exact ties and tiny beams."""
+    wl = synth.make_workload(FAMILIES["B_nolm"][0])
+    dec = sim.build_ctcdecoder(wl.labels)
+    ora = orc.OracleDecoder(wl.labels)
+    inplace = ranked = 0
+    for x, kw in synth.special_step_cases(wl):
+        got = _beams(dec.decode_beams(x, **kw))
+        tm = dec.last_timings()
+        inplace += tm["inplace_frames"]
+        ranked += tm["sorted_frames"]
+        _compare(ora.decode_beams(x, **kw), got)
+    assert inplace > 1000 and ranked > 100      # the special steps really ran
+    # with an LM only the branch-(i) in-place frames apply; hotwords and BPE likewise
+    for fam in ("B_3gram", "C_bpe"):
+        wkw, lmkw = FAMILIES[fam]
+        wl2 = synth.make_workload(wkw)
+        kw2 = dict(lmkw)
+        if wl2.arpa:
+            kw2.update(kenlm_model_path=wl2.arpa, unigrams=wl2.words)
+        dec2 = sim.build_ctcdecoder(wl2.labels, **kw2)
+        ora2 = orc.OracleDecoder(wl2.labels, **kw2)
+        n = 0
+        for i in range(4):
+            x = wl2.utterance(5000 + i, 200 if wl2.V <= 64 else 80, "peaky")
+            for hot in (None, [wl2.words[3], wl2.words[10]]):
+                for prune in (True, False):
+                    _compare(ora2.decode_beams(x, prune_history=prune, hotwords=hot), _beams(dec2.decode_beams(x, prune_history=prune, hotwords=hot)))
+                    n += dec2.last_timings()["inplace_frames"]
+        assert n > 0
