@@ -81,6 +81,28 @@ void b2c_decoder_destroy(b2c_decoder_t* dec);
 int b2c_decoder_set_params(b2c_decoder_t* dec, double alpha, double beta, double unk_score_offset,
                            int lm_score_boundary);
 
+#define B2C_FIN_EOS 0
+#define B2C_FIN_FLUSH 1
+#define B2C_FIN_KEEP 2
+/* One input beam of a streaming call, string-free (reference Beam, decoder.py:69-94): the finished words of
+ * `text` as (hash, code points) pairs from b2c_hash_utf8, the partial word likewise, last_char as a token id. */
+typedef struct {
+    uint64_t part_hash;        /* b2c_hash_utf8(partial_word) */
+    double logit_score;
+    uint32_t word_off, n_words;/* words of `text`: word_hashes / word_lens [word_off, word_off + n_words) of the state */
+    uint32_t part_len;         /* code points of partial_word */
+    uint32_t last_tok;         /* b2c_decoder_token_id(last_char); 0xFFFF for None */
+    int32_t pf_s, pf_e;        /* partial_frames */
+} b2c_stream_beam_t;
+typedef struct b2c_stream_state {
+    const b2c_stream_beam_t* beams;   /* in the order the previous call returned them */
+    int n_beams;
+    int processed_frames;             /* frame index of the first row of this call's logits */
+    const uint64_t* word_hashes;
+    const uint32_t* word_lens;
+    int n_words;
+} b2c_stream_state_t;
+
 typedef struct {
     int beam_width;            /* DEFAULT_BEAM_WIDTH 100          (constants.py:8)  */
     double beam_prune_logp;    /* DEFAULT_PRUNE_LOGP -10          (constants.py:10) */
@@ -91,6 +113,11 @@ typedef struct {
     double hotword_weight;     /* DEFAULT_HOTWORD_WEIGHT 10       (constants.py:9)  */
     int max_out_beams;         /* 1 for decode()/decode_batch(); beam_width for decode_beams*() */
     const b2c_lm_state_t* lm_start_states; /* NULL, or one start state per utterance (lm_start_state, decoder.py:612-625) */
+    /* streaming (partial_decode_beams, decoder.py:669-728): NULL, or one state per utterance = the beams the call
+     * starts from (NULL beams / n_beams == 0: EMPTY_START_BEAM) and processed_frames */
+    const struct b2c_stream_state* stream_states;
+    int finalize_mode;         /* B2C_FIN_EOS (default): decode_beams / is_end=True; B2C_FIN_FLUSH: force_next_word=True,
+                                  is_end=False; B2C_FIN_KEEP: neither -- beams keep their partial words (decoder.py:571-593) */
 } b2c_decode_opts_t;
 void b2c_decode_opts_default(b2c_decode_opts_t* opts);
 
@@ -119,6 +146,17 @@ const char* b2c_result_word(const b2c_result_t* res, int utt, int beam, int word
 const int32_t* b2c_result_frames(const b2c_result_t* res, int utt, int beam);
 /* LM state after the last word (OutputBeam.last_lm_state); returns 0 when there is no LM */
 int b2c_result_lm_state(const b2c_result_t* res, int utt, int beam, b2c_lm_state_t* out);
+/* streaming calls (opts->stream_states != NULL): what the call appended to an input beam instead of assembled
+ * strings.  aux = {input beam index (-1: none), token id of last_char (-1: None), partial_frames start, end};
+ * toks = the emitted tokens since the input beam, oldest first, token | kind << 16 with kind 0 = appended to the
+ * partial word, 1 = BPE piece that starts a word, 2 = space; b2c_result_frames / b2c_result_n_frames give the frames
+ * of the words finished during the call (LMBeam, decoder.py:97-100; the host replays them onto the input beam). */
+int b2c_result_stream_beam(const b2c_result_t* res, int utt, int beam, int32_t aux[4], const uint32_t** toks, int* n_toks);
+int b2c_result_n_frames(const b2c_result_t* res, int utt, int beam);
+/* string -> (hash, code points) as the kernels identify words and partial words; label -> canonical token id
+ * (-1 when the alphabet has no such label) */
+int b2c_hash_utf8(const char* s, uint64_t* hash, uint32_t* n_chars);
+int b2c_decoder_token_id(const b2c_decoder_t* dec, const char* label);
 
 /* ---- measurement hooks (bench.py) ---------------------------------------------------------
  * Device time of the kernels of the LAST decode call, measured with CUDA events on the

@@ -8,7 +8,7 @@ The per-frame beam update runs in hand-written sm_100a CUDA kernels behind a C A
 (include/b200ctc.h, pyctcdecode_b200/libb200ctc.so).  There is no CPU fallback.
 """
 from .alphabet import Alphabet  # noqa: F401
-from .decoder import BeamSearchDecoderCTC, OutputBeam, build_ctcdecoder  # noqa: F401
+from .decoder import Beam, BeamSearchDecoderCTC, LMBeam, OutputBeam, build_ctcdecoder  # noqa: F401
 from .language_model import HotwordScorer, LanguageModel, MultiLanguageModel, NgramModel  # noqa: F401
 
 __version__ = "0.1.0"

@@ -20,6 +20,19 @@ class LMState(C.Structure):
     _fields_ = [("words", C.c_uint32 * 5), ("backoff", C.c_float * 5), ("length", C.c_uint32)]
 
 
+class StreamBeam(C.Structure):
+    _fields_ = [("part_hash", C.c_uint64), ("logit_score", C.c_double), ("word_off", C.c_uint32), ("n_words", C.c_uint32),
+                ("part_len", C.c_uint32), ("last_tok", C.c_uint32), ("pf_s", C.c_int32), ("pf_e", C.c_int32)]
+
+
+class StreamState(C.Structure):
+    _fields_ = [("beams", C.POINTER(StreamBeam)), ("n_beams", C.c_int), ("processed_frames", C.c_int),
+                ("word_hashes", C.POINTER(C.c_uint64)), ("word_lens", C.POINTER(C.c_uint32)), ("n_words", C.c_int)]
+
+
+FIN_EOS, FIN_FLUSH, FIN_KEEP = 0, 1, 2
+
+
 class DecodeOpts(C.Structure):
     _fields_ = [
         ("beam_width", C.c_int),
@@ -31,6 +44,8 @@ class DecodeOpts(C.Structure):
         ("hotword_weight", C.c_double),
         ("max_out_beams", C.c_int),
         ("lm_start_states", C.POINTER(LMState)),
+        ("stream_states", C.POINTER(StreamState)),
+        ("finalize_mode", C.c_int),
     ]
 
 
@@ -103,6 +118,10 @@ def _declare(L):
     L.b2c_result_frames.restype = C.POINTER(C.c_int32)
     L.b2c_result_lm_state.argtypes = [vp, i32, i32, C.POINTER(LMState)]
     L.b2c_decoder_last_timings.argtypes = [vp, C.POINTER(Timings)]
+    L.b2c_result_stream_beam.argtypes = [vp, i32, i32, C.POINTER(C.c_int32 * 4), C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(i32)]
+    L.b2c_result_n_frames.argtypes = [vp, i32, i32]
+    L.b2c_hash_utf8.argtypes = [cp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
+    L.b2c_decoder_token_id.argtypes = [vp, cp]
     return L
 
 

@@ -67,7 +67,8 @@ static u32 pow2_ge(u32 x) {
 // HBM tier, beam tables in shared memory (the caller checks smem_bytes against the budget).
 // cap_request == 0: general layout -- what fits in shared memory plus an HBM tier sized for the
 // worst case beam_width * V.
-static B2cLayout make_layout(int W, int V, int T_max, bool full_caps, u32 smem_budget, u32 cap_request, u64 worst_m = 0, int n_warps = 4) {
+static B2cLayout make_layout(int W, int V, int T_max, bool full_caps, u32 smem_budget, u32 cap_request, u64 worst_m = 0, int n_warps = 4,
+                             u64 extra_chain = 0, u64 extra_text = 0) {
     B2cLayout L;
     std::memset(&L, 0, sizeof(L));
     L.W = W;
@@ -97,8 +98,8 @@ static B2cLayout make_layout(int W, int V, int T_max, bool full_caps, u32 smem_b
         }
     }
     const u64 wt = static_cast<u64>(W) * static_cast<u64>(std::max(T_max, 1));
-    L.chain_cap = static_cast<u32>(std::min<u64>(wt + 16, 0x7FFFFFF0ull));
-    L.text_cap = static_cast<u32>(std::min<u64>(full_caps ? wt + 16 : wt / 4 + 4096, 0x7FFFFFF0ull));
+    L.chain_cap = static_cast<u32>(std::min<u64>(wt + 16 + extra_chain, 0x7FFFFFF0ull));
+    L.text_cap = static_cast<u32>(std::min<u64>((full_caps ? wt + 16 : wt / 4 + 4096) + extra_text, 0x7FFFFFF0ull));
     u64 s = 0;
     L.s_sc = static_cast<u32>(s); s += 128;
     if (L.beams_in_smem) {
@@ -433,7 +434,7 @@ struct b2c_decoder {
     int score_boundary = 1;
     int n_sm = 1;
     size_t smem_optin = 48 * 1024;
-    DevBuf d_mstats, d_sumk, d_clk, d_maxk, d_toks, d_logits, d_meta, d_tok_start, d_tok_ids, d_tok_lp, d_rowsum, d_set, d_isprob, d_ws, d_hot, d_states,
+    DevBuf d_stream, d_mstats, d_sumk, d_clk, d_maxk, d_toks, d_logits, d_meta, d_tok_start, d_tok_ids, d_tok_lp, d_rowsum, d_set, d_isprob, d_ws, d_hot, d_states,
         d_out_small, d_out_toks, d_out_frames;
     PinBuf h_sumk, h_maxk, h_meta, h_out_small, h_out_toks, h_out_frames;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -454,6 +455,8 @@ struct BeamRes {
     std::vector<int32_t> frames;
     double logit = 0, lm = 0;
     B2cLmState st;
+    std::vector<u32> raw;      // streaming calls: emitted tokens since the input beam, oldest first
+    int aux[4] = {-1, -1, -1, -1};
 };
 struct b2c_result {
     std::vector<std::vector<BeamRes>> utts;
@@ -804,7 +807,7 @@ void b2c_decoder_destroy(b2c_decoder_t* d) {
     if (!d) return;
     cudaSetDevice(d->device);
     if (d->stream) cudaStreamSynchronize(d->stream);
-    DevBuf* bufs[] = {&d->d_mstats, &d->d_sumk, &d->d_clk, &d->d_maxk, &d->d_toks, &d->d_logits, &d->d_meta, &d->d_tok_start, &d->d_tok_ids, &d->d_tok_lp, &d->d_rowsum, &d->d_set,
+    DevBuf* bufs[] = {&d->d_stream, &d->d_mstats, &d->d_sumk, &d->d_clk, &d->d_maxk, &d->d_toks, &d->d_logits, &d->d_meta, &d->d_tok_start, &d->d_tok_ids, &d->d_tok_lp, &d->d_rowsum, &d->d_set,
                       &d->d_isprob, &d->d_ws, &d->d_hot, &d->d_states, &d->d_out_small, &d->d_out_toks, &d->d_out_frames};
     for (DevBuf* b : bufs) b->release();
     PinBuf* pins[] = {&d->h_sumk, &d->h_maxk, &d->h_meta, &d->h_out_small, &d->h_out_toks, &d->h_out_frames};
@@ -877,6 +880,51 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     std::iota(order.begin(), order.end(), 0);
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return T[a] > T[b]; });
     const int OB = std::max(1, std::min(opts->max_out_beams, opts->beam_width));
+    // ---- streaming input (partial_decode_beams): flatten the per-utterance beam / word lists -----------
+    if (opts->finalize_mode < B2C_FIN_EOS || opts->finalize_mode > B2C_FIN_KEEP) return fail(B2C_E_ARG, "bad finalize_mode");
+    const bool streaming = opts->stream_states != nullptr || opts->finalize_mode != B2C_FIN_EOS;
+    std::vector<B2cStreamUtt> s_utts;
+    std::vector<B2cStreamBeam> s_beams;
+    std::vector<u64> s_wh;
+    std::vector<u32> s_wl;
+    int s_max_beams = 0;
+    u64 s_max_words = 0;
+    if (opts->stream_states) {
+        s_utts.resize(n_utts);
+        for (int i = 0; i < n_utts; ++i) {
+            const b2c_stream_state_t& ss = opts->stream_states[i];
+            if (ss.n_beams < 0 || ss.n_beams > 65535 || (ss.n_beams > 0 && !ss.beams)) return fail(B2C_E_ARG, "bad stream state");
+            B2cStreamUtt su;
+            su.beam_off = static_cast<u32>(s_beams.size());
+            su.n_beams = static_cast<u32>(ss.n_beams);
+            su.t0 = ss.processed_frames;
+            su.pad = 0;
+            const u32 wbase = static_cast<u32>(s_wh.size());
+            u64 words = 0;
+            for (int b = 0; b < ss.n_beams; ++b) {
+                const b2c_stream_beam_t& ib = ss.beams[b];
+                if (static_cast<u64>(ib.word_off) + ib.n_words > static_cast<u64>(std::max(ss.n_words, 0)))
+                    return fail(B2C_E_ARG, "stream beam word range outside the state's word list");
+                if (ib.last_tok != B2C_NO_TOK && ib.last_tok >= static_cast<u32>(V)) return fail(B2C_E_ARG, "stream beam last_tok out of range");
+                B2cStreamBeam sb;
+                sb.part_hash = ib.part_hash;
+                sb.logit = ib.logit_score;
+                sb.word_off = wbase + ib.word_off;
+                sb.n_words = ib.n_words;
+                sb.part_len = ib.part_len;
+                sb.last_tok = ib.last_tok == B2C_NO_TOK ? B2C_NO_TOK : d->toks[ib.last_tok].canon;
+                sb.pf_s = ib.pf_s;
+                sb.pf_e = ib.pf_e;
+                s_beams.push_back(sb);
+                words += ib.n_words;
+            }
+            for (int w = 0; w < ss.n_words; ++w) { s_wh.push_back(ss.word_hashes[w]); s_wl.push_back(ss.word_lens[w]); }
+            s_utts[i] = su;
+            s_max_beams = std::max(s_max_beams, ss.n_beams);
+            s_max_words = std::max(s_max_words, words);
+        }
+    }
+    const int W_tab = std::max(opts->beam_width, s_max_beams);     // capacity of the beam tables
 
     // ---- parameters -----------------------------------------------------------------------
     B2cParams P;
@@ -943,7 +991,8 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     // outputs
     const u64 off_nb = 0, off_st = al16(4ull * n_utts), off_sc = off_st + al16(4ull * n_utts),
               off_nt = off_sc + al16(16ull * OB * n_utts), off_nw = off_nt + al16(4ull * OB * n_utts),
-              off_ls = off_nw + al16(4ull * OB * n_utts), small_bytes = off_ls + al16(sizeof(B2cLmState) * static_cast<u64>(OB) * n_utts);
+              off_ls = off_nw + al16(4ull * OB * n_utts), off_ax = off_ls + al16(sizeof(B2cLmState) * static_cast<u64>(OB) * n_utts),
+              small_bytes = off_ax + (streaming ? al16(16ull * OB * n_utts) : 0);
     const u64 tok_bytes = 4ull * OB * (total_frames + n_utts), frm_bytes = 2 * tok_bytes;
     if (d->d_out_small.ensure(small_bytes) || d->h_out_small.ensure(small_bytes) || d->d_out_toks.ensure(tok_bytes) ||
         d->h_out_toks.ensure(tok_bytes) || d->d_out_frames.ensure(frm_bytes) || d->h_out_frames.ensure(frm_bytes))
@@ -1016,6 +1065,28 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
         for (int i = 0; i < n_utts; ++i) to_internal(opts->lm_start_states + i, start_host[i]);
         CUDA_OK(cudaMemcpyAsync(d->d_states.p, start_host.data(), sizeof(B2cLmState) * n_utts, cudaMemcpyHostToDevice, st));
         d_start = d->d_states.as<B2cLmState>();
+    }
+
+    const B2cStreamUtt* d_sutt = nullptr;
+    const B2cStreamBeam* d_sbeam = nullptr;
+    const u64* d_swh = nullptr;
+    const u32* d_swl = nullptr;
+    if (!s_utts.empty()) {
+        const size_t b0 = al16(sizeof(B2cStreamUtt) * s_utts.size()), b1 = al16(sizeof(B2cStreamBeam) * std::max<size_t>(s_beams.size(), 1)),
+                     b2 = al16(8 * std::max<size_t>(s_wh.size(), 1)), b3 = al16(4 * std::max<size_t>(s_wl.size(), 1));
+        if (d->d_stream.ensure(b0 + b1 + b2 + b3)) return B2C_E_NOMEM;
+        u8* base = d->d_stream.as<u8>();
+        CUDA_OK(cudaMemcpyAsync(base, s_utts.data(), sizeof(B2cStreamUtt) * s_utts.size(), cudaMemcpyHostToDevice, st));
+        if (!s_beams.empty()) CUDA_OK(cudaMemcpyAsync(base + b0, s_beams.data(), sizeof(B2cStreamBeam) * s_beams.size(), cudaMemcpyHostToDevice, st));
+        if (!s_wh.empty()) {
+            CUDA_OK(cudaMemcpyAsync(base + b0 + b1, s_wh.data(), 8 * s_wh.size(), cudaMemcpyHostToDevice, st));
+            CUDA_OK(cudaMemcpyAsync(base + b0 + b1 + b2, s_wl.data(), 4 * s_wl.size(), cudaMemcpyHostToDevice, st));
+        }
+        d_sutt = reinterpret_cast<const B2cStreamUtt*>(base);
+        d_sbeam = reinterpret_cast<const B2cStreamBeam*>(base + b0);
+        d_swh = reinterpret_cast<const u64*>(base + b0 + b1);
+        d_swl = reinterpret_cast<const u32*>(base + b0 + b1 + b2);
+        d->tm.h2d_bytes += static_cast<long long>(b0 + b1 + b2 + b3);
     }
 
     // ---- prepare kernel ---------------------------------------------------------------------
@@ -1111,7 +1182,7 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
             const u32 typ_k = std::min<u32>(std::max<u32>(h_maxk[u], 1u), std::max<u32>(4u, static_cast<u32>(std::ceil(2.5 * mean_k))));
             const u64 need = std::min<u64>(static_cast<u64>(opts->beam_width) * typ_k,
                                            static_cast<u64>(opts->beam_width) * static_cast<u64>(V));
-            for (int c = 0; c < kNumCaps; ++c)
+            for (int c = 0; c < kNumCaps && !streaming; ++c)      // streaming calls take the general kernel
                 if (cap_ok[c] && need <= kCaps[c]) { cls_of[u] = c; break; }
             if (cls_of[u] < kNumCaps) { top = std::max(top, cls_of[u]); ++n_fast; }
         }
@@ -1157,6 +1228,11 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     BA.tok_ids = PA.tok_ids;
     BA.tok_lp = PA.tok_lp;
     BA.start_states = d_start;
+    BA.s_utts = d_sutt;
+    BA.s_beams = d_sbeam;
+    BA.s_word_hash = d_swh;
+    BA.s_word_len = d_swl;
+    BA.fin_mode = opts->finalize_mode;
     u8* ds = d->d_out_small.as<u8>();
     BA.out_nbeams = reinterpret_cast<int*>(ds + off_nb);
     BA.out_status = reinterpret_cast<int*>(ds + off_st);
@@ -1164,6 +1240,7 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     BA.out_ntok = reinterpret_cast<int*>(ds + off_nt);
     BA.out_nwords = reinterpret_cast<int*>(ds + off_nw);
     BA.out_states = reinterpret_cast<B2cLmState*>(ds + off_ls);
+    BA.out_aux = streaming ? reinterpret_cast<int*>(ds + off_ax) : nullptr;
     BA.out_toks = d->d_out_toks.as<u32>();
     BA.out_frames = d->d_out_frames.as<int>();
     if (d->d_mstats.ensure(64)) return B2C_E_NOMEM;
@@ -1187,7 +1264,7 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
             tmax = std::max(tmax, static_cast<int>(T[u]));
             kmax = std::max(kmax, h_maxk[u]);
         }
-        const u64 worst_m = static_cast<u64>(opts->beam_width) * std::min<u32>(kmax, static_cast<u32>(V));
+        const u64 worst_m = static_cast<u64>(W_tab) * std::min<u32>(kmax, static_cast<u32>(V));
         ln.v5 = (use_v5 && cls < kNumCaps) ? v5_variant : -1;
         if (ln.v5 >= 0) {
             // beam tables of capacity 128; the HBM tier always exists (frames with > B2C_FAST_KS tokens use it too)
@@ -1199,7 +1276,8 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
         } else {
         ln.threads = cls < kNumCaps ? threads_of(cls) : 128;
         ln.L = cls < kNumCaps ? layout_of(cls, tmax, full, worst_m)
-                              : make_layout(opts->beam_width, V, tmax, full, smem_budget, 0, worst_m, 4);
+                              : make_layout(W_tab, V, tmax, full, smem_budget, 0, worst_m, 4, static_cast<u64>(s_max_beams),
+                                            s_max_words + static_cast<u64>(s_max_beams));
         ln.per_sm = per_sm_of(ln.L.smem_bytes, ln.threads);
         }
         ln.slots = std::min(ln.count, d->n_sm * ln.per_sm);
@@ -1333,6 +1411,7 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     const int* h_nt = reinterpret_cast<const int*>(hs + off_nt);
     const int* h_nw = reinterpret_cast<const int*>(hs + off_nw);
     const B2cLmState* h_ls = reinterpret_cast<const B2cLmState*>(hs + off_ls);
+    const int* h_ax = streaming ? reinterpret_cast<const int*>(hs + off_ax) : nullptr;
     const u32* h_toks = d->h_out_toks.as<u32>();
     const int* h_frames = d->h_out_frames.as<int>();
     auto assemble_range = [&](int u0, int u1) {
@@ -1348,6 +1427,19 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
                 br.lm = h_sc[2 * k + 1];
                 br.st = h_ls[k];
                 assemble_beam(d, h_toks + base + r * stride, h_nt[k], h_frames + 2 * (base + r * stride), h_nw[k], br);
+                if (h_ax) {
+                    const u32* tk = h_toks + base + r * stride;
+                    br.raw.resize(static_cast<size_t>(h_nt[k]));
+                    for (int q = 0; q < h_nt[k]; ++q) br.raw[q] = tk[h_nt[k] - 1 - q];
+                    for (int q = 0; q < 4; ++q) br.aux[q] = h_ax[4 * k + q];
+                    // assemble_beam truncated the frame list to the words it could name; keep all of them here
+                    br.frames.resize(static_cast<size_t>(h_nw[k]) * 2);
+                    const int* fr = h_frames + 2 * (base + r * stride);
+                    for (int w = 0; w < h_nw[k]; ++w) {
+                        br.frames[2 * w] = fr[2 * (h_nw[k] - 1 - w)];
+                        br.frames[2 * w + 1] = fr[2 * (h_nw[k] - 1 - w) + 1];
+                    }
+                }
             }
         }
     };
@@ -1407,6 +1499,29 @@ int b2c_result_lm_state(const b2c_result_t* r, int u, int b, b2c_lm_state_t* out
     if (!r->has_lm) return 0;
     from_internal(r->utts[u][b].st, out);
     return 1;
+}
+int b2c_result_stream_beam(const b2c_result_t* r, int u, int b, int32_t aux[4], const uint32_t** toks, int* n_toks) {
+    if (!r || u < 0 || u >= static_cast<int>(r->utts.size()) || b < 0 || b >= static_cast<int>(r->utts[u].size()))
+        return fail(B2C_E_ARG, "no such beam");
+    const BeamRes& br = r->utts[u][b];
+    for (int q = 0; q < 4; ++q) aux[q] = br.aux[q];
+    *toks = br.raw.data();
+    *n_toks = static_cast<int>(br.raw.size());
+    return 0;
+}
+int b2c_result_n_frames(const b2c_result_t* r, int u, int b) { return static_cast<int>(r->utts[u][b].frames.size() / 2); }
+int b2c_hash_utf8(const char* s, uint64_t* hash, uint32_t* n_chars) {
+    if (!s || !hash || !n_chars) return fail(B2C_E_ARG, "null argument");
+    const size_t n = std::strlen(s);
+    *hash = b2c_hash_bytes(s, n);
+    *n_chars = b2c_utf8_len(s, n);
+    return 0;
+}
+int b2c_decoder_token_id(const b2c_decoder_t* d, const char* label) {
+    if (!d || !label) return -1;
+    for (size_t i = 0; i < d->labels.size(); ++i)
+        if (d->labels[i] == label) return static_cast<int>(d->toks[i].canon);
+    return -1;
 }
 int b2c_decoder_last_timings(const b2c_decoder_t* d, b2c_timings_t* out) {
     if (!d || !out) return fail(B2C_E_ARG, "null argument");

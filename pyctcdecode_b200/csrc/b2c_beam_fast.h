@@ -303,9 +303,6 @@ B2C_HD void b2c_fast_step(const B2cParams& P, B2cFastSmem<WC, CAP>& S, B2cChain*
     const double bscale = P.bucket_scale;
     constexpr u32 hmask = SM::HT - 1, ptmask = SM::PT - 1;
     B2C_FMARK(0);
-#ifdef B2C_DEBUG_CHEAP
-    fprintf(stderr, "general t=%d n=%u K=%d ref=%g par=%d logit0=%g last0=%u\n", t, n, K, ref, par, cur.logit[0], (unsigned)cur.last_tok[0]);
-#endif
 
     if (is_bpe) {
         if (holes) {   // the force_next_break scan reads last_tok of every beam: mark the dead slots first
@@ -530,9 +527,6 @@ B2C_HD bool b2c_fast_cheap_step(const B2cParams& P, B2cFastSmem<WC, CAP>& S, B2c
     const double top = plain ? (cur.logit[0] + p) + 0.0
                              : b2c_combine_score(has_lm, cur.logit[0] + p, cur.lm_hw[0], cur.pscore[0], cur.part_len[0]);
     const double thr = top + P.prune_logp;
-#ifdef B2C_DEBUG_CHEAP
-    fprintf(stderr, "cheap t=%d kind=%d n=%u top=%g thr=%g p=%g holes=%d\n", t, kind, n, top, thr, p, (int)holes);
-#endif
     B2C_FOR(b, n) {
         if (plain) {
             if (!((cur.logit[b] + p) + 0.0 >= thr)) S.cheap_bad = 1;

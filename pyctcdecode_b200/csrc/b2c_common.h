@@ -201,10 +201,12 @@ struct B2cStreamBeam {
     int pf_s, pf_e;            // partial_frames
 };
 struct B2cStreamUtt { u32 beam_off, n_beams; int t0; u32 pad; };   // t0: processed_frames
-// what _finalize_beams does at the end of a call (decoder.py:558-602)
-enum { B2C_FIN_EOS = 0,        // force_next_word or is_end, scored with is_eos=True  (decode_beams; is_end=True)
-       B2C_FIN_FLUSH = 1,      // force_next_word=True, is_end=False: partial words become words, no </s>
-       B2C_FIN_KEEP = 2 };     // neither: beams keep their partial words (streaming continues)
+// what _finalize_beams does at the end of a call (decoder.py:558-602); same values as include/b200ctc.h
+#ifndef B2C_FIN_EOS
+#define B2C_FIN_EOS 0          // force_next_word or is_end, scored with is_eos=True (decode_beams; is_end=True)
+#define B2C_FIN_FLUSH 1        // force_next_word=True, is_end=False: partial words become words, no </s>
+#define B2C_FIN_KEEP 2         // neither: beams keep their partial words (streaming continues)
+#endif
 
 #define B2C_LOG_MIN_CLIP (-0x1.144f69ff9ffc4p+5)   // np.log(1e-15)
 #define B2C_AVG_TOKEN_LEN 6

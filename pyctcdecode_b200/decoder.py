@@ -9,6 +9,7 @@ What moved to the GPU: input normalisation (:756-765), the per-frame loop of
 utterance on the device (and one rank per GPU above that), not ``multiprocessing``.
 """
 import ctypes as C
+import dataclasses
 import logging
 import os
 import threading
@@ -44,6 +45,45 @@ logger = logging.getLogger(__name__)
 
 Frames = Tuple[int, int]
 WordFrames = Tuple[str, Frames]
+
+
+@dataclasses.dataclass(frozen=True)
+class Beam:
+    """reference decoder.py:69-94 (what partial_decode_beams takes and, as LMBeam, returns)"""
+
+    text: str
+    next_word: str
+    partial_word: str
+    last_char: Optional[str]
+    text_frames: List[Frames]
+    partial_frames: Frames
+    logit_score: float
+
+    @classmethod
+    def from_lm_beam(cls, lm_beam: "LMBeam") -> "Beam":
+        return Beam(lm_beam.text, lm_beam.next_word, lm_beam.partial_word, lm_beam.last_char, lm_beam.text_frames,
+                    lm_beam.partial_frames, lm_beam.logit_score)
+
+
+@dataclasses.dataclass(frozen=True)
+class LMBeam(Beam):
+    """reference decoder.py:97-100"""
+
+    lm_score: float
+
+
+NULL_FRAMES: Frames = (-1, -1)
+EMPTY_START_BEAM = Beam("", "", "", None, [], NULL_FRAMES, 0.0)
+LMScoreCache = Dict[Tuple[str, bool], Tuple[float, float, AbstractLMState]]
+
+
+def _merge_tokens(token_1: str, token_2: str) -> str:
+    """reference decoder.py:200-208"""
+    if len(token_2) == 0:
+        return token_1
+    if len(token_1) == 0:
+        return token_2
+    return token_1 + " " + token_2
 
 
 class OutputBeam(NamedTuple):
@@ -215,7 +255,8 @@ class BeamSearchDecoderCTC:
     def _run(self, logits_list: Sequence[Any], beam_width: int, beam_prune_logp: float, token_min_logp: float,
              prune_history: bool, hotwords: Optional[Iterable[str]], hotword_weight: float, max_out_beams: int,
              lm_start_states: Optional[Sequence[Optional[AbstractLMState]]] = None, with_state: bool = True,
-             device: Optional[int] = None, texts_only: bool = False, lengths: Optional[Sequence[int]] = None) -> Any:
+             device: Optional[int] = None, texts_only: bool = False, lengths: Optional[Sequence[int]] = None,
+             stream: Optional[Sequence[Tuple[Sequence[Beam], int]]] = None, finalize_mode: int = _lib.FIN_EOS) -> Any:
         packed = self._as_packed_batch(logits_list)
         if lengths is not None and packed is None:
             raise ValueError("lengths= needs one padded [B, T, V] array or tensor")
@@ -271,6 +312,10 @@ class BeamSearchDecoderCTC:
                     raise AssertionError("Wrong input state type found. Expected B200LMState, got %s" % type(st))
                 states_arr[i] = st._to_c()
             opts.lm_start_states = C.cast(states_arr, C.POINTER(_lib.LMState))
+        keep_alive: List[Any] = []
+        if stream is not None:
+            opts.stream_states = C.cast(self._stream_states(handle, stream, keep_alive), C.POINTER(_lib.StreamState))
+        opts.finalize_mode = int(finalize_mode)
         ptrs = (C.c_void_p * n)(*[m[1] for m in mats])
         Ts = (C.c_int32 * n)(*[m[2] for m in mats])
         res = C.c_void_p()
@@ -280,6 +325,8 @@ class BeamSearchDecoderCTC:
                 data, size = C.c_void_p(), C.c_size_t()
                 _lib.check(L.b2c_result_top_texts(res, C.byref(data), C.byref(size)))
                 return C.string_at(data, size.value).decode("utf-8").split("\x00")[:n]
+            if stream is not None:
+                return [self._stream_results(res, u, stream[u][0], finalize_mode) for u in range(n)]
             out: List[List[OutputBeam]] = []
             st = _lib.LMState()
             for u in range(n):
@@ -339,13 +386,137 @@ class BeamSearchDecoderCTC:
         return self._run(logits_list, beam_width, beam_prune_logp, token_min_logp, True, hotwords, hotword_weight,
                          max_out_beams=1, with_state=False, texts_only=True, lengths=lengths)
 
-    # ---- streaming: out of scope this round -------------------------------
-    def get_starting_state(self) -> Any:
-        raise NotImplementedError("streaming decode (get_starting_state / partial_decode_beams) is not implemented "
-                                  "in pyctcdecode_b200 yet; use decode_beams(..., lm_start_state=...) per chunk")
+    # ---- streaming (reference decoder.py:669-728) ------------------------------------------------
+    def get_starting_state(self) -> Tuple[List[Beam], LMScoreCache, Dict[str, float]]:
+        """Starting beams and caches, same shape as the reference returns (decoder.py:669-680).  The caches are
+        accepted back by partial_decode_beams for signature compatibility; only the start state stored under
+        ("", False) is read -- the kernels recompute LM / hotword scores of the carried beams from their words."""
+        language_model = self._language_model
+        cached_lm_scores: LMScoreCache = {}
+        if language_model is not None:
+            cached_lm_scores[("", False)] = (0.0, 0.0, language_model.get_start_state())
+        return [EMPTY_START_BEAM], cached_lm_scores, {}
 
-    def partial_decode_beams(self, *args: Any, **kwargs: Any) -> Any:
-        raise NotImplementedError("streaming decode (partial_decode_beams) is not implemented in pyctcdecode_b200 yet")
+    def _token_id(self, handle: int, label: Optional[str]) -> int:
+        if label is None:
+            return 0xFFFF
+        tid = int(_lib.lib().b2c_decoder_token_id(handle, label.encode("utf-8")))
+        if tid < 0:
+            raise ValueError("beam.last_char %r is not a label of this decoder's alphabet" % (label,))
+        return tid
+
+    def _stream_states(self, handle: int, stream: Sequence[Tuple[Sequence[Beam], int]], keep_alive: List[Any]) -> Any:
+        """List of (beams, processed_frames) per utterance -> b2c_stream_state_t array (words and partial words
+        as hashes from b2c_hash_utf8, last_char as a token id)."""
+        L = _lib.lib()
+        hashes: Dict[str, Tuple[int, int]] = {}
+
+        def hash_of(word: str) -> Tuple[int, int]:
+            if word not in hashes:
+                h, n = C.c_uint64(), C.c_uint32()
+                _lib.check(L.b2c_hash_utf8(word.encode("utf-8"), C.byref(h), C.byref(n)))
+                hashes[word] = (h.value, n.value)
+            return hashes[word]
+
+        states = (_lib.StreamState * len(stream))()
+        for u, (beams, processed_frames) in enumerate(stream):
+            rows = (_lib.StreamBeam * max(1, len(beams)))()
+            wh: List[int] = []
+            wl: List[int] = []
+            for b, beam in enumerate(beams):
+                words = _merge_tokens(beam.text, beam.next_word).split()
+                row = rows[b]
+                row.word_off, row.n_words = len(wh), len(words)
+                for w in words:
+                    h, n = hash_of(w)
+                    wh.append(h)
+                    wl.append(n)
+                row.part_hash, row.part_len = hash_of(beam.partial_word) if beam.partial_word else (0, 0)
+                row.logit_score = float(beam.logit_score)
+                row.last_tok = self._token_id(handle, beam.last_char)
+                row.pf_s, row.pf_e = int(beam.partial_frames[0]), int(beam.partial_frames[1])
+            a_wh = (C.c_uint64 * max(1, len(wh)))(*wh)
+            a_wl = (C.c_uint32 * max(1, len(wl)))(*wl)
+            keep_alive.extend([rows, a_wh, a_wl])
+            states[u].beams = rows
+            states[u].n_beams = len(beams)
+            states[u].processed_frames = int(processed_frames)
+            states[u].word_hashes = a_wh
+            states[u].word_lens = a_wl
+            states[u].n_words = len(wh)
+        keep_alive.append(states)
+        return states
+
+    def _stream_results(self, res: Any, u: int, roots: Sequence[Beam], finalize_mode: int) -> List[LMBeam]:
+        """Replay what the call appended (token chain since the input beam, frames of the words finished during
+        the call) onto the input beams' strings -> LMBeam list (reference _finalize_beams output)."""
+        L = _lib.lib()
+        labels = self._alphabet.labels
+        out: List[LMBeam] = []
+        aux = (C.c_int32 * 4)()
+        toks = C.POINTER(C.c_uint32)()
+        n_toks = C.c_int()
+        for b in range(L.b2c_result_n_beams(res, u)):
+            _lib.check(L.b2c_result_stream_beam(res, u, b, C.byref(aux), C.byref(toks), C.byref(n_toks)))
+            root = roots[aux[0]] if aux[0] >= 0 else EMPTY_START_BEAM
+            text, partial = _merge_tokens(root.text, root.next_word), root.partial_word
+            for q in range(n_toks.value):
+                tok, kind = toks[q] & 0xFFFF, toks[q] >> 16
+                label = labels[tok]
+                if kind == 0:                       # branch (iv): the partial word grows
+                    partial += label
+                    continue
+                text = _merge_tokens(text, partial)  # branches (ii) / (iii): word boundary
+                partial = ""
+                if kind == 2:                       # BPE piece that starts a word (decoder.py:476-484)
+                    partial = label[1:] if label[:1] == "\u2581" else label
+                    if partial[-1:] == "\u2581":
+                        partial = partial[:-1]
+            fr = L.b2c_result_frames(res, u, b)
+            frames = list(root.text_frames) + [(fr[2 * w], fr[2 * w + 1]) for w in range(L.b2c_result_n_frames(res, u, b))]
+            logit, lm = L.b2c_result_logit_score(res, u, b), L.b2c_result_lm_score(res, u, b)
+            if finalize_mode == _lib.FIN_KEEP:
+                last_char = None if aux[1] < 0 else labels[aux[1]]
+                out.append(LMBeam(text, "", partial, last_char, frames, (int(aux[2]), int(aux[3])), logit, lm))
+            else:
+                out.append(LMBeam(_merge_tokens(text, partial), "", "", None, frames, NULL_FRAMES, logit, lm))
+        return out
+
+    def partial_decode_beams(self, logits: Any, cached_lm_scores: LMScoreCache, cached_p_lm_scores: Dict[str, float],
+                             beams: List[Beam], processed_frames: int, beam_width: int = DEFAULT_BEAM_WIDTH,
+                             beam_prune_logp: float = DEFAULT_PRUNE_LOGP, token_min_logp: float = DEFAULT_MIN_TOKEN_LOGP,
+                             prune_history: bool = DEFAULT_PRUNE_BEAMS, hotword_scorer: Optional[HotwordScorer] = None,
+                             force_next_word: bool = False, is_end: bool = False) -> List[LMBeam]:
+        """Decode one chunk of logits starting from `beams` (reference decoder.py:682-728).  The beam state
+        travels as the returned LMBeam list, exactly like in the reference; the chunk itself (input
+        normalisation, frame loop, _finalize_beams with force_next_word / is_end) runs on the device."""
+        return self.partial_decode_beams_batch([logits], [cached_lm_scores], [beams], [processed_frames], beam_width,
+                                               beam_prune_logp, token_min_logp, prune_history, hotword_scorer,
+                                               force_next_word, is_end)[0]
+
+    def partial_decode_beams_batch(self, logits_list: Sequence[Any], cached_lm_scores_list: Sequence[Optional[LMScoreCache]],
+                                   beams_list: Sequence[List[Beam]], processed_frames_list: Sequence[int],
+                                   beam_width: int = DEFAULT_BEAM_WIDTH, beam_prune_logp: float = DEFAULT_PRUNE_LOGP,
+                                   token_min_logp: float = DEFAULT_MIN_TOKEN_LOGP, prune_history: bool = DEFAULT_PRUNE_BEAMS,
+                                   hotword_scorer: Optional[HotwordScorer] = None, force_next_word: bool = False,
+                                   is_end: bool = False) -> List[List[LMBeam]]:
+        """Extension: many independent streams advance by one chunk each in ONE kernel launch."""
+        n = len(logits_list)
+        if not (len(beams_list) == len(processed_frames_list) == len(cached_lm_scores_list) == n):
+            raise ValueError("one beam list, cache and processed_frames value per stream")
+        lm = self._language_model
+        starts: Optional[List[Optional[AbstractLMState]]] = None
+        if lm is not None:
+            starts = []
+            for cache in cached_lm_scores_list:
+                entry = (cache or {}).get(("", False))
+                starts.append(entry[2] if entry is not None else None)
+        hot = hotword_scorer.unigrams if hotword_scorer is not None else None
+        weight = hotword_scorer.weight if hotword_scorer is not None else DEFAULT_HOTWORD_WEIGHT
+        mode = _lib.FIN_EOS if is_end else (_lib.FIN_FLUSH if force_next_word else _lib.FIN_KEEP)
+        return self._run(logits_list, beam_width, beam_prune_logp, token_min_logp, prune_history, hot, weight,
+                         max_out_beams=beam_width, lm_start_states=starts, with_state=False,
+                         stream=[(list(b), int(p)) for b, p in zip(beams_list, processed_frames_list)], finalize_mode=mode)
 
     # ---- serialisation (reference decoder.py:947-1005): file plumbing only ------------------
     def save_to_dir(self, filepath: str) -> None:

@@ -70,3 +70,65 @@ def build_product_decoder(pkg, labels, **kw):
                                score_boundary=kw.get("lm_score_boundary", True))
         return pkg.BeamSearchDecoderCTC(pkg.Alphabet.build_alphabet(labels), lm)
     return pkg.build_ctcdecoder(labels, **kw)
+
+
+def load_stream():
+    """tests/golden/stream_cases.json (oracle/gen_golden_stream.py: the reference's partial_decode_beams, call by call)."""
+    if "s" not in _cache:
+        with open(os.path.join(HERE, "golden", "stream_cases.json"), encoding="utf-8") as fh:
+            meta = json.load(fh)
+        arrays = dict(np.load(os.path.join(HERE, "golden", "stream_arrays.npz")))
+        _cache["s"] = {"meta": meta, "arrays": arrays}
+    return _cache["s"]
+
+
+def stream_case_names():
+    return [c["name"] for c in load_stream()["meta"]["cases"]]
+
+
+def run_stream_case(pkg, name, tol=2e-4):
+    """Drive the product's get_starting_state / partial_decode_beams through one recorded streaming case and
+    compare every call's LMBeam list with what the unmodified reference returned.  Returns '' or the first
+    difference.  Strings, frames and last_char must be identical; scores within `tol` (numpy's float32
+    log-softmax differs from the shared definition in the last bits)."""
+    g, s = load(), load_stream()
+    case = next(c for c in s["meta"]["cases"] if c["name"] == name)
+    x = s["arrays"][case["array"]] if case["array"] in s["arrays"] else g["arrays"][case["array"]]
+    dec = build_product_decoder(pkg, case["labels"], **lm_kwargs(g, case))
+    beams, cached_lm, cached_p = dec.get_starting_state()
+    for i, step in enumerate(case["steps"]):
+        call = step["call"]
+        scorer = None
+        if call.get("hotwords") is not None:
+            scorer = pkg.HotwordScorer.build_scorer(call["hotwords"], weight=call.get("hotword_weight", 10.0))
+        out = dec.partial_decode_beams(x[step["start"]:step["end"]], cached_lm, cached_p, beams, step["start"],
+                                       hotword_scorer=scorer, force_next_word=bool(call.get("force_next_word", False)),
+                                       is_end=step["is_end"], **case["common"])
+        exp = step["beams"]
+        if len(out) != len(exp):
+            return "call %d: %d beams != %d" % (i, len(out), len(exp))
+        # identical beams (strings, frames, last_char) with scores within tol; the ORDER must agree except between
+        # beams the reference itself separates by less than 1e-9 (last-bit rounding of float32 numpy log-softmax
+        # vs the shared definition decides such near-ties; DESIGN.md, "near-tie class")
+        def ident(text, nw, pw, lc, tf, pf):
+            return (text, nw, pw, lc, tuple(tuple(f) for f in tf), tuple(pf))
+        got = {}
+        for j, o in enumerate(out):
+            got[ident(o.text, o.next_word, o.partial_word, o.last_char, o.text_frames, o.partial_frames)] = (j, o)
+        pos = []
+        for j, e in enumerate(exp):
+            k = ident(e["text"], e["next_word"], e["partial_word"], e["last_char"], e["text_frames"], e["partial_frames"])
+            if k not in got:
+                return "call %d: reference beam %d %r missing (got rank %d: %r)" % (i, j, k[:4], j, (out[j].text, out[j].partial_word, out[j].last_char))
+            gj, o = got[k]
+            if abs(o.logit_score - e["logit_score"]) > tol + 1e-6 * abs(e["logit_score"]):
+                return "call %d beam %d logit %r != %r" % (i, j, o.logit_score, e["logit_score"])
+            if abs(o.lm_score - e["lm_score"]) > tol + 1e-6 * abs(e["lm_score"]):
+                return "call %d beam %d lm %r != %r" % (i, j, o.lm_score, e["lm_score"])
+            pos.append(gj)
+        for a in range(len(exp)):
+            for b in range(a + 1, len(exp)):
+                if exp[a]["lm_score"] - exp[b]["lm_score"] > 1e-9 and pos[a] > pos[b]:
+                    return "call %d: beams %d and %d swapped (scores %r, %r)" % (i, a, b, exp[a]["lm_score"], exp[b]["lm_score"])
+        beams = out
+    return ""

@@ -243,3 +243,29 @@ def test_gpu_special_single_token_steps(pkg, orc):
         ranked += tm["sorted_frames"]
         _compare(ora.decode_beams(x, **kw), got)
     assert inplace > 1000 and ranked > 100
+
+
+@pytest.mark.parametrize("name", goldens.stream_case_names())
+def test_gpu_streaming_matches_reference_golden(pkg, name):
+    """get_starting_state / partial_decode_beams on the device, call by call, against the outputs of the
+    unmodified reference (tests/golden/stream_cases.json, oracle/gen_golden_stream.py)."""
+    assert goldens.run_stream_case(pkg, name) == ""
+
+
+def test_gpu_streaming_batch_equals_whole(pkg):
+    wl = synth.make_workload(dict(kind="char", vocab="B", n_words=400, lm_order=3))
+    dec = pkg.build_ctcdecoder(wl.labels, kenlm_model_path=wl.arpa, unigrams=wl.words, alpha=0.5, beta=1.0)
+    T = 300
+    xs = [wl.utterance(8300 + i, T, ["peaky", "diffuse"][i % 2]) for i in range(12)]
+    whole = dec.decode_beams_batch(None, xs, beam_width=32)
+    states = [dec.get_starting_state() for _ in xs]
+    beams, caches = [s[0] for s in states], [s[1] for s in states]
+    for a in range(0, T, 64):
+        b = min(T, a + 64)
+        beams = dec.partial_decode_beams_batch([x[a:b] for x in xs], caches, beams, [a] * len(xs), beam_width=32, is_end=(b == T))
+    for w, got in zip(whole, beams):
+        assert [o.text for o in w] == [g.text for g in got]
+        assert [[f for _, f in o.text_frames] for o in w] == [[tuple(f) for f in g.text_frames] for g in got]
+        for o, g in zip(w, got):
+            assert abs(o.logit_score - g.logit_score) <= 1e-9 * max(1.0, abs(o.logit_score))
+            assert abs(o.lm_score - g.lm_score) <= 1e-9 * max(1.0, abs(o.lm_score))

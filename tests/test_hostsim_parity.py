@@ -167,3 +167,36 @@ def test_hostsim_special_single_token_steps(sim):
                     _compare(ora2.decode_beams(x, prune_history=prune, hotwords=hot), _beams(dec2.decode_beams(x, prune_history=prune, hotwords=hot)))
                     n += dec2.last_timings()["inplace_frames"]
         assert n > 0
+
+
+@pytest.mark.parametrize("name", goldens.stream_case_names())
+def test_hostsim_streaming_matches_reference_golden(sim, name):
+    """get_starting_state / partial_decode_beams, call by call, against the unmodified reference's outputs."""
+    assert goldens.run_stream_case(sim, name) == ""
+
+
+def test_hostsim_streaming_chunks_equal_whole(sim):
+    """Chunked partial_decode_beams (several streams per launch) ends in the beams decode_beams gives for the
+    whole utterance (reference tests/test_decoder.py:515-563 states this property for its own decoder)."""
+    for fam in ("B_nolm", "B_3gram", "C_bpe_4gram"):
+        wkw, lmkw = FAMILIES[fam]
+        wl = synth.make_workload(wkw)
+        kw = dict(lmkw)
+        if wl.arpa:
+            kw.update(kenlm_model_path=wl.arpa, unigrams=wl.words)
+        dec = sim.build_ctcdecoder(wl.labels, **kw)
+        T = 90 if wl.V <= 64 else 40
+        xs = [wl.utterance(8200 + i, T, ["peaky", "diffuse"][i % 2]) for i in range(3)]
+        whole = [dec.decode_beams(x, beam_width=16) for x in xs]
+        states = [dec.get_starting_state() for _ in xs]
+        beams = [s[0] for s in states]
+        caches = [s[1] for s in states]
+        bounds = [0, 17, 18, 50, T]
+        for a, b in zip(bounds[:-1], bounds[1:]):
+            beams = dec.partial_decode_beams_batch([x[a:b] for x in xs], caches, beams, [a] * len(xs), beam_width=16, is_end=(b == T))
+        for w, got in zip(whole, beams):
+            assert [o.text for o in w] == [g.text for g in got]
+            assert [[f for _, f in o.text_frames] for o in w] == [[tuple(f) for f in g.text_frames] for g in got]
+            for o, g in zip(w, got):
+                assert abs(o.logit_score - g.logit_score) <= 1e-9 * max(1.0, abs(o.logit_score))
+                assert abs(o.lm_score - g.lm_score) <= 1e-9 * max(1.0, abs(o.lm_score))
