@@ -390,6 +390,17 @@ def main():
         info, cpu_texts, n = cpu_arm(wl, spec, kw, xs, beam, hot)
         out["cpu_baseline"] = info
         out["transcripts_identical_to_oracle"] = "%d/%d" % (sum(a == b for a, b in zip(cpu_texts, texts[:n])), n)
+        # "WER parity" of the metric: both systems against the word sequence the synthetic alignment spells
+        from tests import synth
+        err = {"b200": [0, 0], "cpu_port": [0, 0]}
+        for i in range(n):
+            truth = wl.truth(1 + i, T)
+            for key, hyp in (("b200", texts[i]), ("cpu_port", cpu_texts[i])):
+                e, m = synth.word_errors(truth, hyp)
+                err[key][0] += e
+                err[key][1] += m
+        out["wer"] = {k: (v[0] / v[1] if v[1] else None) for k, v in err.items()}
+        out["wer"].update(utterances=n, against="ground-truth word sequence of the synthetic alignment (noisy logits, so not 0)")
     _emit(out)
     if dist is not None:
         dist.destroy_process_group()

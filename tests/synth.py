@@ -197,6 +197,29 @@ def ctc_alignment(rng, symbol_ids, blank_id, T):
     return np.asarray(frames, dtype=np.int64)
 
 
+def collapse_alignment(align, norm_labels, blank_id):
+    """CTC collapse of a frame alignment (repeats, then blanks) -> text with single spaces."""
+    out, prev = [], None
+    for a in align:
+        a = int(a)
+        if a != prev and a != blank_id:
+            out.append(norm_labels[a])
+        prev = a
+    return " ".join("".join(out).replace("\u2581", " ").split())
+
+
+def word_errors(ref, hyp):
+    """(word-level edit distance, reference length)"""
+    r, h = ref.split(), hyp.split()
+    row = list(range(len(h) + 1))
+    for i in range(1, len(r) + 1):
+        prev, row[0] = row[0], i
+        for j in range(1, len(h) + 1):
+            cur = min(row[j] + 1, row[j - 1] + 1, prev + (r[i - 1] != h[j - 1]))
+            prev, row[j] = row[j], cur
+    return row[len(h)], len(r)
+
+
 def logits_from_alignment(rng, align, V, margin, conf):
     T = len(align)
     x = rng.standard_normal((T, V), dtype=np.float32)
@@ -244,6 +267,17 @@ class CharWorkload:
 
     def batch(self, seed0, B, T, regime="peaky"):
         return [self.utterance(seed0 + i, T, regime) for i in range(B)]
+
+    def truth(self, seed, T):
+        """The text the alignment of utterance(seed, T, .) spells (ground truth for WER; the last word may be cut)."""
+        rng = np.random.default_rng(seed)
+        sent = sample_sentence(rng, self.words, self.probs, self.tables, max_words=max(2, T // 8))
+        syms = []
+        for wi, w in enumerate(sent):
+            if wi:
+                syms.append(self.space_id)
+            syms.extend(self.char_id[c] for c in w)
+        return collapse_alignment(ctc_alignment(rng, syms, self.blank_id, T), self.norm_labels, self.blank_id)
 
 
 class BpeWorkload:
@@ -305,6 +339,14 @@ class BpeWorkload:
 
     def batch(self, seed0, B, T, regime="peaky"):
         return [self.utterance(seed0 + i, T, regime) for i in range(B)]
+
+    def truth(self, seed, T):
+        rng = np.random.default_rng(seed)
+        sent = sample_sentence(rng, self.words, self.probs, self.tables, max_words=max(2, T // 5))
+        syms = []
+        for w in sent:
+            syms.extend(self.segment(w))
+        return collapse_alignment(ctc_alignment(rng, syms, self.blank_id, T), self.norm_labels, self.blank_id)
 
     def hotwords(self, n=16, seed=7):
         rng = np.random.default_rng(seed)
