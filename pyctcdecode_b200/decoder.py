@@ -560,8 +560,13 @@ def build_ctcdecoder(labels: List[str], kenlm_model_path: Optional[str] = None, 
                      lm_score_boundary: bool = DEFAULT_SCORE_LM_BOUNDARY, device: Optional[int] = None) -> BeamSearchDecoderCTC:
     """Same arguments and semantics as reference decoder.py:1051-1099; ``kenlm_model_path`` must be
     an ARPA file (KenLM binaries are not readable without the kenlm package)."""
-    ngram = None if kenlm_model_path is None else NgramModel(kenlm_model_path)
-    if unigrams is None and kenlm_model_path is not None:
+    from_blob = kenlm_model_path is not None and kenlm_model_path.endswith(NgramModel.BLOB_SUFFIX)
+    if from_blob:
+        # a flattened model written by NgramModel.save_blob: no ARPA parse; it carries its unigram / prefix sets
+        ngram = NgramModel.load_blob(kenlm_model_path)
+    else:
+        ngram = None if kenlm_model_path is None else NgramModel(kenlm_model_path)
+    if unigrams is None and kenlm_model_path is not None and not from_blob:
         if kenlm_model_path.endswith(".arpa"):
             unigrams = load_unigram_set_from_arpa(kenlm_model_path)
         else:

@@ -123,6 +123,8 @@ class NgramModel:
 
     def with_unigrams(self, unigrams: Optional[Collection[str]]) -> "NgramModel":
         """A model over the same ARPA file whose blob carries the unigram set / prefix set."""
+        if getattr(self, "_from_blob_file", False):
+            return self            # a saved blob already carries the unigram / prefix sets it was built with
         if unigrams is None and self._unigrams is None:
             return self
         return NgramModel(self.path.decode("utf-8"), unigrams)
@@ -168,6 +170,25 @@ class NgramModel:
         obj.path = os.path.abspath(path).encode("utf-8")
         obj._unigrams = None
         obj._handle = out.value
+        return obj
+
+    BLOB_SUFFIX = ".b2clm"
+
+    def save_blob(self, path: str) -> None:
+        """Write the flattened model (n-gram / vocabulary / unigram-prefix hash tables) to `path`.
+        Loading it back with :meth:`load_blob` skips the ARPA parse, which dominates start-up for large models."""
+        address, size = self.blob()
+        with open(path, "wb") as fh:
+            fh.write(C.string_at(address, size))
+
+    @classmethod
+    def load_blob(cls, path: str) -> "NgramModel":
+        """A model from a file written by :meth:`save_blob` (the blob is validated by magic and size)."""
+        with open(path, "rb") as fh:
+            data = fh.read()
+        buf = C.create_string_buffer(data, len(data))
+        obj = cls.from_blob(path, C.addressof(buf), len(data))
+        obj._from_blob_file = True
         return obj
 
     def __del__(self) -> None:

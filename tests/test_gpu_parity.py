@@ -229,9 +229,13 @@ def test_gpu_padded_batch_lengths_and_half_precision(pkg):
         assert dec.decode(h[2], beam_width=50) == ref[2]
 
 
-def test_gpu_special_single_token_steps(pkg, orc):
+@pytest.mark.parametrize("variant", ["0", "1", "2"])
+def test_gpu_special_single_token_steps(pkg, orc, variant, monkeypatch):
     """In-place single-token frames and merge-free sorted frames (b2c_fast_cheap_step / b2c_fast_sorted_step)
-    on the device against the oracle: varying sharpness, exact ties (integer logits), beams from 2 to 128."""
+    on the device against the oracle: varying sharpness, exact ties (integer logits), beams from 2 to 128, in
+    every capacity variant of the latency-first kernel."""
+    monkeypatch.setenv("B200CTC_V5_VARIANT", variant)
+    monkeypatch.setenv("B200CTC_FORCE_V5", "1")
     wl = synth.make_workload(dict(kind="char", vocab="B", n_words=400, lm_order=0))
     dec = pkg.build_ctcdecoder(wl.labels)
     ora = orc.OracleDecoder(wl.labels)

@@ -200,3 +200,21 @@ def test_hostsim_streaming_chunks_equal_whole(sim):
             for o, g in zip(w, got):
                 assert abs(o.logit_score - g.logit_score) <= 1e-9 * max(1.0, abs(o.logit_score))
                 assert abs(o.lm_score - g.lm_score) <= 1e-9 * max(1.0, abs(o.lm_score))
+
+
+def test_hostsim_lm_blob_file_roundtrip(sim, tmp_path):
+    """NgramModel.save_blob / build_ctcdecoder(kenlm_model_path="*.b2clm") (cached flattened LM):
+    the decoder built from the blob file decodes exactly like the one built from the ARPA file."""
+    wkw, lmkw = FAMILIES["B_3gram"]
+    wl = synth.make_workload(wkw)
+    dec = sim.build_ctcdecoder(wl.labels, kenlm_model_path=wl.arpa, unigrams=wl.words, **lmkw)
+    path = str(tmp_path / "lm.b2clm")
+    dec._language_model.ngram_model.save_blob(path)
+    dec2 = sim.build_ctcdecoder(wl.labels, kenlm_model_path=path, **lmkw)
+    for i in range(4):
+        x = wl.utterance(8400 + i, 80, ["peaky", "diffuse"][i % 2])
+        assert _beams(dec.decode_beams(x, beam_width=20, hotwords=[wl.words[5]])) == _beams(dec2.decode_beams(x, beam_width=20, hotwords=[wl.words[5]]))
+    with open(path, "r+b") as fh:       # a damaged file is rejected, not decoded with
+        fh.write(b"\x00\x00\x00\x00")
+    with pytest.raises(ValueError):
+        sim.build_ctcdecoder(wl.labels, kenlm_model_path=path)
