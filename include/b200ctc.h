@@ -103,6 +103,15 @@ typedef struct b2c_stream_state {
     int n_words;
 } b2c_stream_state_t;
 
+/* MultiLanguageModel (language_model.py:455-502, the mean of >= 2 models): the decoder is created with model 0,
+ * further models (at most 4 in total) are added here; every model keeps its own alpha / beta / unk offset /
+ * boundary flag (index 0 = the model given to b2c_decoder_create).  With more than one model
+ * opts->lm_start_states holds n_models consecutive states per utterance and b2c_result_lm_state_at returns the
+ * state of each model (MultiLanguageModelState.states). */
+int b2c_decoder_add_lm(b2c_decoder_t* dec, b2c_lm_t* lm);
+int b2c_decoder_set_params_lm(b2c_decoder_t* dec, int lm_index, double alpha, double beta, double unk_score_offset,
+                              int lm_score_boundary);
+
 typedef struct {
     int beam_width;            /* DEFAULT_BEAM_WIDTH 100          (constants.py:8)  */
     double beam_prune_logp;    /* DEFAULT_PRUNE_LOGP -10          (constants.py:10) */
@@ -146,6 +155,7 @@ const char* b2c_result_word(const b2c_result_t* res, int utt, int beam, int word
 const int32_t* b2c_result_frames(const b2c_result_t* res, int utt, int beam);
 /* LM state after the last word (OutputBeam.last_lm_state); returns 0 when there is no LM */
 int b2c_result_lm_state(const b2c_result_t* res, int utt, int beam, b2c_lm_state_t* out);
+int b2c_result_lm_state_at(const b2c_result_t* res, int utt, int beam, int lm_index, b2c_lm_state_t* out);
 /* streaming calls (opts->stream_states != NULL): what the call appended to an input beam instead of assembled
  * strings.  aux = {input beam index (-1: none), token id of last_char (-1: None), partial_frames start, end};
  * toks = the emitted tokens since the input beam, oldest first, token | kind << 16 with kind 0 = appended to the

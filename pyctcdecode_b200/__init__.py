@@ -9,6 +9,6 @@ The per-frame beam update runs in hand-written sm_100a CUDA kernels behind a C A
 """
 from .alphabet import Alphabet  # noqa: F401
 from .decoder import Beam, BeamSearchDecoderCTC, LMBeam, OutputBeam, build_ctcdecoder  # noqa: F401
-from .language_model import HotwordScorer, LanguageModel, MultiLanguageModel, NgramModel  # noqa: F401
+from .language_model import HotwordScorer, LanguageModel, MultiLanguageModel, MultiLanguageModelState, NgramModel  # noqa: F401
 
 __version__ = "0.1.0"

@@ -118,6 +118,9 @@ def _declare(L):
     L.b2c_result_frames.restype = C.POINTER(C.c_int32)
     L.b2c_result_lm_state.argtypes = [vp, i32, i32, C.POINTER(LMState)]
     L.b2c_decoder_last_timings.argtypes = [vp, C.POINTER(Timings)]
+    L.b2c_decoder_add_lm.argtypes = [vp, vp]
+    L.b2c_decoder_set_params_lm.argtypes = [vp, i32, f64, f64, f64, i32]
+    L.b2c_result_lm_state_at.argtypes = [vp, i32, i32, i32, C.POINTER(LMState)]
     L.b2c_result_stream_beam.argtypes = [vp, i32, i32, C.POINTER(C.c_int32 * 4), C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(i32)]
     L.b2c_result_n_frames.argtypes = [vp, i32, i32]
     L.b2c_hash_utf8.argtypes = [cp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]

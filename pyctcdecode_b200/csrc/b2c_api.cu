@@ -68,7 +68,7 @@ static u32 pow2_ge(u32 x) {
 // cap_request == 0: general layout -- what fits in shared memory plus an HBM tier sized for the
 // worst case beam_width * V.
 static B2cLayout make_layout(int W, int V, int T_max, bool full_caps, u32 smem_budget, u32 cap_request, u64 worst_m = 0, int n_warps = 4,
-                             u64 extra_chain = 0, u64 extra_text = 0) {
+                             u64 extra_chain = 0, u64 extra_text = 0, int n_lm = 1) {
     B2cLayout L;
     std::memset(&L, 0, sizeof(L));
     L.W = W;
@@ -117,7 +117,8 @@ static B2cLayout make_layout(int W, int V, int T_max, bool full_caps, u32 smem_b
     L.g_tier = g; if (L.cap_g) g += tier_bytes(L.cap_g, L.ht_g);
     L.g_tk = g; g += al16(4ull * V) + al16(static_cast<u64>(V)) + 64;
     L.g_chain = g; g += al16(sizeof(B2cChain) * static_cast<u64>(L.chain_cap));
-    L.g_text = g; g += al16(sizeof(B2cText) * static_cast<u64>(L.text_cap));
+    L.g_text = g; g += al16(sizeof(B2cText) * static_cast<u64>(L.text_cap)) +
+                      al16(sizeof(B2cLmState) * static_cast<u64>(L.text_cap) * static_cast<u64>(n_lm > 1 ? n_lm - 1 : 0));
     L.gws_bytes = (g + 255) & ~255ull;
     return L;
 }
@@ -145,6 +146,7 @@ struct B2cBeamArgs {
     const u32* s_word_len;
     int fin_mode;                    // B2C_FIN_*
     int* out_aux;                    // [n_utts][out_beams][4], streaming calls only
+    B2cLmState* out_states_x;        // [n_utts][out_beams][n_lm - 1], MultiLanguageModel only
     // outputs
     int* out_nbeams;
     int* out_status;
@@ -201,7 +203,8 @@ B2C_HD void b2c_beam_block(const B2cBeamArgs& A, int slot, u8* smem) {
             sin.word_len = A.s_word_len;
             t0 = su.t0;
         }
-        b2c_utt_begin(A.P, W, A.start_states ? A.start_states + u : nullptr, static_cast<int>(rec.cnt), sin);
+        b2c_utt_begin(A.P, W, A.start_states ? A.start_states + static_cast<u64>(u) * (A.P.n_lm > 1 ? A.P.n_lm : 1) : nullptr,
+                      static_cast<int>(rec.cnt), sin);
 #if defined(__CUDACC__)
 #pragma unroll 1
 #endif
@@ -232,6 +235,7 @@ B2C_HD void b2c_beam_block(const B2cBeamArgs& A, int slot, u8* smem) {
         O.frames = A.out_frames + 2 * ob * (f0 + static_cast<u64>(u));
         O.states = A.out_states + static_cast<u64>(u) * ob;
         O.aux = A.out_aux ? A.out_aux + 4 * static_cast<u64>(u) * ob : nullptr;
+        O.states_x = A.out_states_x ? A.out_states_x + static_cast<u64>(u) * ob * (A.P.n_lm - 1) : nullptr;
         b2c_finalize(A.P, W, O, A.fin_mode);
         B2C_MARK(8);
     }
@@ -432,9 +436,12 @@ struct b2c_decoder {
     b2c_lm* lm = nullptr;
     double alpha = 0.5, beta = 1.5, unk = -10.0;
     int score_boundary = 1;
+    // MultiLanguageModel: models 1.. (model 0 is `lm` with the scalars above)
+    struct ExtraLm { b2c_lm* lm; double alpha, beta, unk; int score_boundary; };
+    std::vector<ExtraLm> lmx;
     int n_sm = 1;
     size_t smem_optin = 48 * 1024;
-    DevBuf d_stream, d_mstats, d_sumk, d_clk, d_maxk, d_toks, d_logits, d_meta, d_tok_start, d_tok_ids, d_tok_lp, d_rowsum, d_set, d_isprob, d_ws, d_hot, d_states,
+    DevBuf d_lmx, d_stream, d_mstats, d_sumk, d_clk, d_maxk, d_toks, d_logits, d_meta, d_tok_start, d_tok_ids, d_tok_lp, d_rowsum, d_set, d_isprob, d_ws, d_hot, d_states,
         d_out_small, d_out_toks, d_out_frames;
     PinBuf h_sumk, h_maxk, h_meta, h_out_small, h_out_toks, h_out_frames;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -455,6 +462,7 @@ struct BeamRes {
     std::vector<int32_t> frames;
     double logit = 0, lm = 0;
     B2cLmState st;
+    std::vector<B2cLmState> stx;   // MultiLanguageModel: states of models 1..
     std::vector<u32> raw;      // streaming calls: emitted tokens since the input beam, oldest first
     int aux[4] = {-1, -1, -1, -1};
 };
@@ -803,11 +811,33 @@ int b2c_decoder_create(const char* const* labels, int n_labels, int is_bpe, b2c_
     return 0;
 }
 
+int b2c_decoder_add_lm(b2c_decoder_t* d, b2c_lm_t* lm) {
+    if (!d || !lm) return fail(B2C_E_ARG, "null argument");
+    if (!d->lm) return fail(B2C_E_ARG, "the decoder was created without a language model");
+    if (d->lmx.size() + 2 > B2C_MAX_LMS) return fail(B2C_E_ARG, "at most 4 language models");
+    if (lm->dev.find(d->device) == lm->dev.end()) {
+        const int rc = b2c_lm_upload(lm, d->device);
+        if (rc) return rc;
+    }
+    d->lmx.push_back(b2c_decoder::ExtraLm{lm, 0.5, 1.5, -10.0, 1});
+    return 0;
+}
+int b2c_decoder_set_params_lm(b2c_decoder_t* d, int index, double alpha, double beta, double unk, int boundary) {
+    if (!d) return fail(B2C_E_ARG, "null decoder");
+    if (index == 0) return b2c_decoder_set_params(d, alpha, beta, unk, boundary);
+    if (index < 0 || index > static_cast<int>(d->lmx.size())) return fail(B2C_E_ARG, "no such language model");
+    b2c_decoder::ExtraLm& x = d->lmx[index - 1];
+    x.alpha = alpha;
+    x.beta = beta;
+    x.unk = unk;
+    x.score_boundary = boundary ? 1 : 0;
+    return 0;
+}
 void b2c_decoder_destroy(b2c_decoder_t* d) {
     if (!d) return;
     cudaSetDevice(d->device);
     if (d->stream) cudaStreamSynchronize(d->stream);
-    DevBuf* bufs[] = {&d->d_stream, &d->d_mstats, &d->d_sumk, &d->d_clk, &d->d_maxk, &d->d_toks, &d->d_logits, &d->d_meta, &d->d_tok_start, &d->d_tok_ids, &d->d_tok_lp, &d->d_rowsum, &d->d_set,
+    DevBuf* bufs[] = {&d->d_lmx, &d->d_stream, &d->d_mstats, &d->d_sumk, &d->d_clk, &d->d_maxk, &d->d_toks, &d->d_logits, &d->d_meta, &d->d_tok_start, &d->d_tok_ids, &d->d_tok_lp, &d->d_rowsum, &d->d_set,
                       &d->d_isprob, &d->d_ws, &d->d_hot, &d->d_states, &d->d_out_small, &d->d_out_toks, &d->d_out_frames};
     for (DevBuf* b : bufs) b->release();
     PinBuf* pins[] = {&d->h_sumk, &d->h_maxk, &d->h_meta, &d->h_out_small, &d->h_out_toks, &d->h_out_frames};
@@ -948,8 +978,31 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
         if (it == d->lm->dev.end()) return fail(B2C_E_INTERNAL, "language model is not resident on this device");
         P.lm = d->lm->host.view(it->second);
         if (P.lm.order > B2C_MAX_ORDER) return fail(B2C_E_ARG, "n-gram order too large");
+        P.n_lm = 1 + static_cast<int>(d->lmx.size());
     }
-    P.hist_n = std::max(1, P.lm.order - 1);
+    int max_order = P.lm.order;     // MultiLanguageModel.order is the maximum (language_model.py:468-470)
+    std::vector<B2cLmExtra> lmx_host(d->lmx.size());
+    for (size_t j = 0; j < d->lmx.size(); ++j) {
+        const b2c_decoder::ExtraLm& x = d->lmx[j];
+        auto it = x.lm->dev.find(d->device);
+        if (it == x.lm->dev.end()) return fail(B2C_E_INTERNAL, "language model is not resident on this device");
+        B2cLmExtra& X = lmx_host[j];
+        std::memset(&X, 0, sizeof(X));
+        X.lm = x.lm->host.view(it->second);
+        if (X.lm.order > B2C_MAX_ORDER) return fail(B2C_E_ARG, "n-gram order too large");
+        X.alpha = x.alpha;
+        X.beta = x.beta;
+        X.unk_offset = x.unk;
+        X.score_boundary = x.score_boundary;
+        max_order = std::max(max_order, X.lm.order);
+    }
+    if (!lmx_host.empty()) {
+        if (d->d_lmx.ensure(sizeof(B2cLmExtra) * lmx_host.size())) return B2C_E_NOMEM;
+        CUDA_OK(cudaMemcpy(d->d_lmx.p, lmx_host.data(), sizeof(B2cLmExtra) * lmx_host.size(), cudaMemcpyHostToDevice));
+        P.lmx = d->d_lmx.as<B2cLmExtra>();
+    }
+    const int n_lm = std::max(1, P.n_lm);
+    P.hist_n = std::max(1, max_order - 1);
     std::vector<B2cHot> hot;
     build_hot(opts, hot, P.n_hot, P.hot_min_len_all);
     if (d->d_hot.ensure(hot.size() * sizeof(B2cHot))) return B2C_E_NOMEM;
@@ -992,13 +1045,14 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     const u64 off_nb = 0, off_st = al16(4ull * n_utts), off_sc = off_st + al16(4ull * n_utts),
               off_nt = off_sc + al16(16ull * OB * n_utts), off_nw = off_nt + al16(4ull * OB * n_utts),
               off_ls = off_nw + al16(4ull * OB * n_utts), off_ax = off_ls + al16(sizeof(B2cLmState) * static_cast<u64>(OB) * n_utts),
-              small_bytes = off_ax + (streaming ? al16(16ull * OB * n_utts) : 0);
+              off_lx = off_ax + (streaming ? al16(16ull * OB * n_utts) : 0),
+              small_bytes = off_lx + al16(sizeof(B2cLmState) * static_cast<u64>(OB) * n_utts * static_cast<u64>(n_lm - 1));
     const u64 tok_bytes = 4ull * OB * (total_frames + n_utts), frm_bytes = 2 * tok_bytes;
     if (d->d_out_small.ensure(small_bytes) || d->h_out_small.ensure(small_bytes) || d->d_out_toks.ensure(tok_bytes) ||
         d->h_out_toks.ensure(tok_bytes) || d->d_out_frames.ensure(frm_bytes) || d->h_out_frames.ensure(frm_bytes))
         return B2C_E_NOMEM;
     if (opts->lm_start_states) {
-        if (d->d_states.ensure(sizeof(B2cLmState) * static_cast<u64>(n_utts))) return B2C_E_NOMEM;
+        if (d->d_states.ensure(sizeof(B2cLmState) * static_cast<u64>(n_utts) * n_lm)) return B2C_E_NOMEM;
     }
 
     // ---- host -> device -------------------------------------------------------------------
@@ -1061,9 +1115,10 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     const B2cLmState* d_start = nullptr;
     std::vector<B2cLmState> start_host;
     if (opts->lm_start_states) {
-        start_host.resize(n_utts);
-        for (int i = 0; i < n_utts; ++i) to_internal(opts->lm_start_states + i, start_host[i]);
-        CUDA_OK(cudaMemcpyAsync(d->d_states.p, start_host.data(), sizeof(B2cLmState) * n_utts, cudaMemcpyHostToDevice, st));
+        // with a MultiLanguageModel: n_lm consecutive states per utterance (MultiLanguageModelState.states)
+        start_host.resize(static_cast<size_t>(n_utts) * n_lm);
+        for (size_t i = 0; i < start_host.size(); ++i) to_internal(opts->lm_start_states + i, start_host[i]);
+        CUDA_OK(cudaMemcpyAsync(d->d_states.p, start_host.data(), sizeof(B2cLmState) * start_host.size(), cudaMemcpyHostToDevice, st));
         d_start = d->d_states.as<B2cLmState>();
     }
 
@@ -1182,7 +1237,7 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
             const u32 typ_k = std::min<u32>(std::max<u32>(h_maxk[u], 1u), std::max<u32>(4u, static_cast<u32>(std::ceil(2.5 * mean_k))));
             const u64 need = std::min<u64>(static_cast<u64>(opts->beam_width) * typ_k,
                                            static_cast<u64>(opts->beam_width) * static_cast<u64>(V));
-            for (int c = 0; c < kNumCaps && !streaming; ++c)      // streaming calls take the general kernel
+            for (int c = 0; c < kNumCaps && !streaming && n_lm == 1; ++c)      // streaming / multi-LM calls take the general kernel
                 if (cap_ok[c] && need <= kCaps[c]) { cls_of[u] = c; break; }
             if (cls_of[u] < kNumCaps) { top = std::max(top, cls_of[u]); ++n_fast; }
         }
@@ -1241,6 +1296,7 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     BA.out_nwords = reinterpret_cast<int*>(ds + off_nw);
     BA.out_states = reinterpret_cast<B2cLmState*>(ds + off_ls);
     BA.out_aux = streaming ? reinterpret_cast<int*>(ds + off_ax) : nullptr;
+    BA.out_states_x = n_lm > 1 ? reinterpret_cast<B2cLmState*>(ds + off_lx) : nullptr;
     BA.out_toks = d->d_out_toks.as<u32>();
     BA.out_frames = d->d_out_frames.as<int>();
     if (d->d_mstats.ensure(64)) return B2C_E_NOMEM;
@@ -1277,7 +1333,7 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
         ln.threads = cls < kNumCaps ? threads_of(cls) : 128;
         ln.L = cls < kNumCaps ? layout_of(cls, tmax, full, worst_m)
                               : make_layout(W_tab, V, tmax, full, smem_budget, 0, worst_m, 4, static_cast<u64>(s_max_beams),
-                                            s_max_words + static_cast<u64>(s_max_beams));
+                                            s_max_words + static_cast<u64>(s_max_beams), n_lm);
         ln.per_sm = per_sm_of(ln.L.smem_bytes, ln.threads);
         }
         ln.slots = std::min(ln.count, d->n_sm * ln.per_sm);
@@ -1412,6 +1468,7 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     const int* h_nw = reinterpret_cast<const int*>(hs + off_nw);
     const B2cLmState* h_ls = reinterpret_cast<const B2cLmState*>(hs + off_ls);
     const int* h_ax = streaming ? reinterpret_cast<const int*>(hs + off_ax) : nullptr;
+    const B2cLmState* h_lx = n_lm > 1 ? reinterpret_cast<const B2cLmState*>(hs + off_lx) : nullptr;
     const u32* h_toks = d->h_out_toks.as<u32>();
     const int* h_frames = d->h_out_frames.as<int>();
     auto assemble_range = [&](int u0, int u1) {
@@ -1426,6 +1483,7 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
                 br.logit = h_sc[2 * k];
                 br.lm = h_sc[2 * k + 1];
                 br.st = h_ls[k];
+                if (h_lx) br.stx.assign(h_lx + k * (n_lm - 1), h_lx + (k + 1) * (n_lm - 1));
                 assemble_beam(d, h_toks + base + r * stride, h_nt[k], h_frames + 2 * (base + r * stride), h_nw[k], br);
                 if (h_ax) {
                     const u32* tk = h_toks + base + r * stride;
@@ -1498,6 +1556,14 @@ const int32_t* b2c_result_frames(const b2c_result_t* r, int u, int b) { return r
 int b2c_result_lm_state(const b2c_result_t* r, int u, int b, b2c_lm_state_t* out) {
     if (!r->has_lm) return 0;
     from_internal(r->utts[u][b].st, out);
+    return 1;
+}
+int b2c_result_lm_state_at(const b2c_result_t* r, int u, int b, int lm_index, b2c_lm_state_t* out) {
+    if (!r->has_lm) return 0;
+    const BeamRes& br = r->utts[u][b];
+    if (lm_index == 0) { from_internal(br.st, out); return 1; }
+    if (lm_index < 0 || lm_index > static_cast<int>(br.stx.size())) return 0;
+    from_internal(br.stx[lm_index - 1], out);
     return 1;
 }
 int b2c_result_stream_beam(const b2c_result_t* r, int u, int b, int32_t aux[4], const uint32_t** toks, int* n_toks) {

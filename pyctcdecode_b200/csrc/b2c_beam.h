@@ -229,9 +229,32 @@ struct B2cTextNew {
     u32 hw_count;
     B2cLmState st;
 };
-B2C_HDN void b2c_text_extend(B2cParams P, const B2cText* parent, u64 word_hash, u32 word_len, int is_eos, B2cTextNew* out) {
+// LM states of models 1.. of a text node live behind the node arena: [text_cap][n_lm - 1]
+B2C_HD B2cLmState* b2c_text_states_x(const B2cText* arena, u32 text_cap, int n_lm, u32 node) {
+    return reinterpret_cast<B2cLmState*>(const_cast<B2cText*>(arena) + text_cap) + static_cast<u64>(node) * static_cast<u64>(n_lm - 1);
+}
+// out_x: where the end states of models 1.. go (MultiLanguageModel; nullptr: not wanted)
+B2C_HDN void b2c_text_extend(B2cParams P, const B2cText* arena, u32 text_cap, u32 parent_id, u64 word_hash, u32 word_len, int is_eos,
+                             B2cTextNew* out, B2cLmState* out_x) {
+    const B2cText* parent = arena + parent_id;
     out->hw_count = parent->hw_count + b2c_hot_is_word(P, word_hash, word_len);
-    if (P.lm.order > 0) {
+    if (P.n_lm > 1) {
+        // MultiLanguageModel.score (language_model.py:485-502): sum of the models' scores, left to right, / N
+        const B2cLmState* px = b2c_text_states_x(arena, text_cap, P.n_lm, parent_id);
+        B2cLmState in = parent->st;
+        double sc = b2c_lm_score_word(P, in, word_hash, word_len, is_eos != 0, out->st);
+        for (int j = 1; j < P.n_lm; ++j) {
+            const B2cLmExtra X = P.lmx[j - 1];
+            in = px[j - 1];
+            B2cLmState end;
+            sc = sc + b2c_lm_score_word_v(X.lm, X.alpha, X.beta, X.unk_offset, X.score_boundary, P.log_base_change, in, word_hash,
+                                          word_len, is_eos != 0, end);
+            if (out_x) out_x[j - 1] = end;
+        }
+        sc = sc / static_cast<double>(P.n_lm);
+        out->raw_lm = parent->raw_lm + sc;
+        out->lm_hw = out->raw_lm + P.hot_weight * static_cast<double>(out->hw_count);
+    } else if (P.lm.order > 0) {
         B2cLmState in = parent->st;
         double sc = b2c_lm_score_word(P, in, word_hash, word_len, is_eos != 0, out->st);
         out->raw_lm = parent->raw_lm + sc;
@@ -275,8 +298,24 @@ B2C_HDN double b2c_partial_score_ool(int n_hot, const B2cHot* hot, u64 hot_mask,
     if (part_len > B2C_AVG_TOKEN_LEN) unk = unk * static_cast<double>(part_len) / B2C_AVG_TOKEN_LEN;
     return unk;
 }
+// MultiLanguageModel.score_partial_token (language_model.py:478-483): mean over the models; the hotword prefix
+// score takes precedence exactly as with one model (decoder.py:397-409)
+B2C_HDN double b2c_partial_score_multi(B2cParams P, u64 part_hash, u32 part_len) {
+    if (P.n_hot > 0) {
+        if (part_len == 0) return P.hot_weight * 0 / P.hot_min_len_all;
+        const B2cHot* h = b2c_hot_find(P, part_hash);
+        if (h) return P.hot_weight * static_cast<double>(part_len) / static_cast<double>(h->min_len);
+    }
+    double s = b2c_lm_partial_v(P.lm, P.unk_offset, part_hash, part_len);
+    for (int j = 1; j < P.n_lm; ++j) {
+        const B2cLmExtra X = P.lmx[j - 1];
+        s = s + b2c_lm_partial_v(X.lm, X.unk_offset, part_hash, part_len);
+    }
+    return s / static_cast<double>(P.n_lm);
+}
 B2C_HD double b2c_partial_score_of(const B2cParams& P, bool need, u64 part_hash, u32 part_len) {
     if (!need) return 0.0;
+    if (P.n_lm > 1) return b2c_partial_score_multi(P, part_hash, part_len);
     return b2c_partial_score_ool(P.n_hot, P.hot, P.hot_mask, P.hot_weight, P.hot_min_len_all, P.lm.order,
                                  P.lm.have_unigrams, P.lm.prefixes, P.lm.prefix_mask, P.unk_offset, part_hash, part_len);
 }
@@ -294,8 +333,11 @@ struct B2cTextCommit { u32 node; double lm_hw; u64 hist_hash; };
 B2C_HDN void b2c_commit_text(B2cParams P, B2cText* arena, u32 text_cap, u32* text_used, u32* status, u32 parent_id,
                              u64 word_hash, u32 word_len, B2cTextCommit* out) {
     const B2cText* par = arena + parent_id;
+    // the node is allocated first so that a MultiLanguageModel's other end states are written in place
+    const u32 id = b2c_atomic_add_u32(text_used, 1u);
     B2cTextNew tn;
-    b2c_text_extend(P, par, word_hash, word_len, 0, &tn);
+    b2c_text_extend(P, arena, text_cap, parent_id, word_hash, word_len, 0, &tn,
+                    (P.n_lm > 1 && id < text_cap) ? b2c_text_states_x(arena, text_cap, P.n_lm, id) : nullptr);
     out->lm_hw = tn.lm_hw;
     out->node = parent_id;
     const u32 keep = (par->n_win + 1 < static_cast<u32>(P.hist_n)) ? par->n_win : static_cast<u32>(P.hist_n) - 1;
@@ -311,7 +353,6 @@ B2C_HDN void b2c_commit_text(B2cParams P, B2cText* arena, u32 text_cap, u32* tex
     nt.raw_lm = tn.raw_lm;
     nt.st = tn.st;
     nt.hw_count = tn.hw_count;
-    const u32 id = b2c_atomic_add_u32(text_used, 1u);
     if (id < text_cap) {
         arena[id] = nt;
         out->node = id;
@@ -675,7 +716,7 @@ B2C_HD void b2c_frame_step(const B2cParams& P, B2cWork& W, int t, const u16* tk_
             double lm_hw = cur.lm_hw[bl];
             if ((type == 1 || type == 2) && cur.part_len[bl] > 0) {
                 B2cTextNew tn;
-                b2c_text_extend(P, W.text + cur.text_node[bl], cur.part_hash[bl], cur.part_len[bl], 0, &tn);
+                b2c_text_extend(P, W.text, W.text_cap, cur.text_node[bl], cur.part_hash[bl], cur.part_len[bl], 0, &tn, nullptr);
                 lm_hw = tn.lm_hw;
             }
             double ps = 0.0;
@@ -844,6 +885,22 @@ B2C_HDN void b2c_utt_begin(B2cParams P, B2cWork W, const B2cLmState* start_state
             }
         }
         W.text[0] = root;
+        if (P.n_lm > 1) {       // start states of models 1.. (start_state, if given, holds n_lm consecutive states)
+            B2cLmState* x = b2c_text_states_x(W.text, W.text_cap, P.n_lm, 0);
+            for (int j = 1; j < P.n_lm; ++j) {
+                B2cLmState st;
+                st.length = 0;
+                for (int w = 0; w < B2C_MAX_HIST; ++w) { st.words[w] = 0; st.backoff[w] = 0.0f; }
+                if (start_state) {
+                    st = start_state[j];
+                } else if (P.lmx[j - 1].score_boundary) {
+                    st.length = 1;
+                    st.words[0] = P.lmx[j - 1].lm.bos_id;
+                    st.backoff[0] = P.lmx[j - 1].lm.uni[P.lmx[j - 1].lm.bos_id].backoff;
+                }
+                x[j - 1] = st;
+            }
+        }
         const B2cBeamTab& c = W.cur;
         c.logit[0] = 0.0;
         c.lm_hw[0] = P.lm.order > 0 ? 0.0 : P.hot_weight * 0;
@@ -919,6 +976,7 @@ struct B2cOut {              // per-utterance output views (HBM)
     u32* toks;               // [out_beams][stride]  token | kind << 16, last emission first
     int* frames;             // [out_beams][stride][2] word frames, last word first
     B2cLmState* states;      // [out_beams] LM state after the last word (last_lm_state)
+    B2cLmState* states_x;    // [out_beams][n_lm - 1] MultiLanguageModel: the other models' states (nullptr otherwise)
     int* aux;                // [out_beams][4] streaming: input beam the output descends from (-1: none), canonical
                              // token of last_char (-1: None), partial_frames; nullptr outside streaming calls
     u32 stride;              // T + 1
@@ -960,7 +1018,7 @@ B2C_HDN void b2c_finalize(B2cParams P, B2cWork W, B2cOut O, int fin_mode) {
         } else if ((P.lm.order > 0 && (is_eos || cur.part_len[last] > 0)) || cur.part_len[last] > 0) {
             // is_eos=False with an empty next_word is a cache hit on (text, False) as well
             B2cTextNew tn;
-            b2c_text_extend(P, W.text + cur.text_node[last], cur.part_hash[last], cur.part_len[last], is_eos, &tn);
+            b2c_text_extend(P, W.text, W.text_cap, cur.text_node[last], cur.part_hash[last], cur.part_len[last], is_eos, &tn, nullptr);
             lm_hw = tn.lm_hw;
         } else {
             lm_hw = cur.lm_hw[last];
@@ -1007,9 +1065,14 @@ B2C_HDN void b2c_finalize(B2cParams P, B2cWork W, B2cOut O, int fin_mode) {
         if (P.lm.order > 0) {
             if (keep || (!is_eos && cur.part_len[last] == 0)) {
                 st = W.text[cur.text_node[last]].st;
+                if (P.n_lm > 1 && O.states_x) {
+                    const B2cLmState* x = b2c_text_states_x(W.text, W.text_cap, P.n_lm, cur.text_node[last]);
+                    for (int j = 1; j < P.n_lm; ++j) O.states_x[static_cast<u64>(r) * (P.n_lm - 1) + (j - 1)] = x[j - 1];
+                }
             } else {
                 B2cTextNew tn;
-                b2c_text_extend(P, W.text + cur.text_node[last], cur.part_hash[last], cur.part_len[last], is_eos, &tn);
+                b2c_text_extend(P, W.text, W.text_cap, cur.text_node[last], cur.part_hash[last], cur.part_len[last], is_eos, &tn,
+                                (P.n_lm > 1 && O.states_x) ? O.states_x + static_cast<u64>(r) * (P.n_lm - 1) : nullptr);
                 st = tn.st;
             }
         }

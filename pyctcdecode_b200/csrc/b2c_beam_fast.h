@@ -395,7 +395,7 @@ B2C_HD void b2c_fast_step(const B2cParams& P, B2cFastSmem<WC, CAP>& S, B2cChain*
             // without LM and hotwords the text-level score is the constant hot_weight * 0: no text node is read
             if ((flags & B2C_FL_PSCORE) && (type == 1 || type == 2) && cur.part_len[bl] > 0) {
                 B2cTextNew tn;
-                b2c_text_extend(P, text_arena + cur.text_node[bl], cur.part_hash[bl], cur.part_len[bl], 0, &tn);
+                b2c_text_extend(P, text_arena, text_cap, cur.text_node[bl], cur.part_hash[bl], cur.part_len[bl], 0, &tn, nullptr);
                 lm_hw = tn.lm_hw;
             }
             double ps = 0.0;
@@ -1082,6 +1082,7 @@ B2C_HD void b2c_beam_block_fast(const B2cBeamArgs& A, int slot, u8* smem) {
         O.frames = A.out_frames + 2 * ob * (f0 + static_cast<u64>(u));
         O.states = A.out_states + static_cast<u64>(u) * ob;
         O.aux = nullptr;
+        O.states_x = nullptr;
         b2c_fast_compact<WC, CAP>(&S, par);
         par ^= 1;
         {

@@ -145,6 +145,17 @@ struct B2cLmState {            // kenlm::ngram::State
 
 struct B2cHot { u64 key; u32 min_len; u32 is_word; };                // hotword prefix table
 
+// MultiLanguageModel (reference language_model.py:455-502): the mean of up to B2C_MAX_LMS n-gram models, each
+// with its own tables, vocabulary, unigram set and alpha / beta / unk offset / boundary flag.  Model 0 lives
+// in B2cParams::lm and the scalar parameters; models 1.. in lmx[].
+#define B2C_MAX_LMS 4
+struct B2cLmExtra {
+    B2cLmView lm;
+    double alpha, beta, unk_offset;
+    int score_boundary;
+    int pad;
+};
+
 // ---------------------------------------------------------------------------------------
 // decode parameters (one block per decode call, passed by value to the kernels)
 // ---------------------------------------------------------------------------------------
@@ -167,6 +178,10 @@ struct B2cParams {
     const B2cHot* hot; u64 hot_mask;
     const B2cTok* toks;
     B2cLmView lm;
+    int n_lm;                  // 0: none, 1: one model, > 1: MultiLanguageModel (general kernel only)
+    int pad_lm;
+    const B2cLmExtra* lmx;     // [n_lm - 1] models 1.. (device memory; the parameter block stays small: it is copied
+                               // into every out-of-line call of the hot kernels)
 };
 
 // ---------------------------------------------------------------------------------------

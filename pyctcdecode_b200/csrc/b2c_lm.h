@@ -90,24 +90,38 @@ B2C_HD float b2c_lm_base_score(const B2cLmView& lm, const B2cLmState& in, u32 w,
 }
 
 // LanguageModel.score(prev_state, word, is_last_word) -> alpha * ln10 * log10 score + beta
-B2C_HD double b2c_lm_score_word(const B2cParams& P, const B2cLmState& prev, u64 word_hash, u32 word_len,
-                                bool is_last, B2cLmState& end_state) {
+B2C_HD double b2c_lm_score_word_v(const B2cLmView& lm, double alpha, double beta, double unk_offset, int score_boundary,
+                                  double log_base_change, const B2cLmState& prev, u64 word_hash, u32 word_len, bool is_last,
+                                  B2cLmState& end_state) {
     u32 wid = 0, flags = 0;
     if (word_len) {
-        const B2cVocab* v = b2c_vocab_find(P.lm, word_hash);
+        const B2cVocab* v = b2c_vocab_find(lm, word_hash);
         if (v) { wid = v->id; flags = v->flags; }
     }
-    double s = static_cast<double>(b2c_lm_base_score(P.lm, prev, wid, end_state));
-    if ((P.lm.n_unigrams > 0 && !(flags & 1u)) || wid == 0) s += P.unk_offset;
+    double s = static_cast<double>(b2c_lm_base_score(lm, prev, wid, end_state));
+    if ((lm.n_unigrams > 0 && !(flags & 1u)) || wid == 0) s += unk_offset;
     if (is_last) {
         double e = 0.0;
-        if (P.score_boundary) {
+        if (score_boundary) {
             B2cLmState tmp;
-            e = static_cast<double>(b2c_lm_base_score(P.lm, end_state, P.lm.eos_id, tmp));
+            e = static_cast<double>(b2c_lm_base_score(lm, end_state, lm.eos_id, tmp));
         }
         s = s + e;
     }
-    return P.alpha * s * P.log_base_change + P.beta;
+    return alpha * s * log_base_change + beta;
+}
+B2C_HD double b2c_lm_score_word(const B2cParams& P, const B2cLmState& prev, u64 word_hash, u32 word_len,
+                                bool is_last, B2cLmState& end_state) {
+    return b2c_lm_score_word_v(P.lm, P.alpha, P.beta, P.unk_offset, P.score_boundary, P.log_base_change, prev, word_hash,
+                               word_len, is_last, end_state);
+}
+// LanguageModel.score_partial_token of one model (language_model.py:326-336)
+B2C_HD double b2c_lm_partial_v(const B2cLmView& lm, double unk_offset, u64 part_hash, u32 part_len) {
+    double is_oov = 1.0;
+    if (lm.have_unigrams) is_oov = b2c_prefix_contains(lm, part_hash) ? 0.0 : 1.0;
+    double unk = unk_offset * is_oov;
+    if (part_len > B2C_AVG_TOKEN_LEN) unk = unk * static_cast<double>(part_len) / B2C_AVG_TOKEN_LEN;
+    return unk;
 }
 
 // score of an unfinished word.  LM mode (reference decoder.py:397-409): hotword prefix score

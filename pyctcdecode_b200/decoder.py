@@ -37,6 +37,7 @@ from .language_model import (
     HotwordScorer,
     LanguageModel,
     MultiLanguageModel,
+    MultiLanguageModelState,
     NgramModel,
     load_unigram_set_from_arpa,
 )
@@ -203,17 +204,29 @@ class BeamSearchDecoderCTC:
             h = self._handles.get(dev)
             if h is None:
                 lm = self._language_model
-                if isinstance(lm, MultiLanguageModel):
-                    raise NotImplementedError("MultiLanguageModel is not supported by the B200 kernels yet")
-                if lm is not None and not isinstance(lm, LanguageModel):
-                    raise TypeError("language_model must be a pyctcdecode_b200 LanguageModel")
+                models = self._lm_list()
                 labels = self._alphabet.labels
                 out = C.c_void_p()
-                lm_handle = lm.ngram_model._h() if lm is not None else None
+                lm_handle = models[0].ngram_model._h() if models else None
                 _lib.check(_lib.lib().b2c_decoder_create(_lib.cstr_array(labels), len(labels), int(self._is_bpe),
                                                          lm_handle, dev, C.byref(out)))
+                for extra in models[1:]:          # MultiLanguageModel: models 1..
+                    _lib.check(_lib.lib().b2c_decoder_add_lm(out, extra.ngram_model._h()))
                 h = self._handles[dev] = out.value
         return h
+
+    def _lm_list(self) -> List[LanguageModel]:
+        """[] without a language model, [lm] for a LanguageModel, the member models of a MultiLanguageModel."""
+        lm = self._language_model
+        if lm is None:
+            return []
+        models = list(lm.language_models) if isinstance(lm, MultiLanguageModel) else [lm]
+        if len(models) > 4:
+            raise ValueError("pyctcdecode_b200 supports at most 4 models in a MultiLanguageModel")
+        for m in models:
+            if not isinstance(m, LanguageModel):
+                raise TypeError("language_model must be a pyctcdecode_b200 LanguageModel (or a MultiLanguageModel of them)")
+        return models
 
     def _check_logits_dimension(self, logits: Any) -> None:
         """reference decoder.py:330-344"""
@@ -288,9 +301,10 @@ class BeamSearchDecoderCTC:
         handle = self._handle(device)
         lm = self._language_model
         L = _lib.lib()
-        if lm is not None:
-            _lib.check(L.b2c_decoder_set_params(handle, float(lm.alpha), float(lm.beta), float(lm.unk_score_offset),
-                                                int(bool(lm.score_boundary))))
+        models = self._lm_list()
+        for idx, m in enumerate(models):
+            _lib.check(L.b2c_decoder_set_params_lm(handle, idx, float(m.alpha), float(m.beta), float(m.unk_score_offset),
+                                                   int(bool(m.score_boundary))))
         opts = _lib.DecodeOpts()
         L.b2c_decode_opts_default(C.byref(opts))
         opts.beam_width = int(beam_width)
@@ -304,13 +318,22 @@ class BeamSearchDecoderCTC:
         opts.hotword_weight = float(hotword_weight)
         opts.max_out_beams = int(max_out_beams)
         states_arr = None
+        n_lm = len(models)
         if lm is not None and lm_start_states is not None and any(s is not None for s in lm_start_states):
-            states_arr = (_lib.LMState * n)()
+            states_arr = (_lib.LMState * (n * n_lm))()      # n_lm consecutive states per utterance
             for i, s in enumerate(lm_start_states):
                 st = s if s is not None else lm.get_start_state()
-                if not isinstance(st, B200LMState):
-                    raise AssertionError("Wrong input state type found. Expected B200LMState, got %s" % type(st))
-                states_arr[i] = st._to_c()
+                if n_lm > 1:
+                    if not isinstance(st, MultiLanguageModelState) or len(st.states) != n_lm:
+                        raise AssertionError("Wrong input state type found. Expected MultiLanguageModelState with %d states, "
+                                             "got %s" % (n_lm, type(st)))
+                    parts = list(st.states)
+                else:
+                    parts = [st]
+                for j, part in enumerate(parts):
+                    if not isinstance(part, B200LMState):
+                        raise AssertionError("Wrong input state type found. Expected B200LMState, got %s" % type(part))
+                    states_arr[i * n_lm + j] = part._to_c()
             opts.lm_start_states = C.cast(states_arr, C.POINTER(_lib.LMState))
         keep_alive: List[Any] = []
         if stream is not None:
@@ -338,6 +361,12 @@ class BeamSearchDecoderCTC:
                     state = None
                     if with_state and L.b2c_result_lm_state(res, u, b, C.byref(st)):
                         state = B200LMState._from_c(st)
+                        if n_lm > 1:
+                            parts = [state]
+                            for j in range(1, n_lm):
+                                L.b2c_result_lm_state_at(res, u, b, j, C.byref(st))
+                                parts.append(B200LMState._from_c(st))
+                            state = MultiLanguageModelState(parts)
                     beams.append(OutputBeam(L.b2c_result_text(res, u, b).decode("utf-8"), state, frames,
                                             L.b2c_result_logit_score(res, u, b), L.b2c_result_lm_score(res, u, b)))
                 out.append(beams)

@@ -412,11 +412,25 @@ class LanguageModel(AbstractLanguageModel):
         return cls(NgramModel(names["kenlm"]), unigrams, **attrs)
 
 
-class MultiLanguageModel(AbstractLanguageModel):
-    """Mean of several language models (reference language_model.py:455-502).
+class MultiLanguageModelState(AbstractLMState):
+    """reference language_model.py:56-64"""
 
-    Out of scope for the CUDA path in this round: constructing it works like
-    in the reference (so the argument checks behave the same) but a decoder refuses to use it."""
+    def __init__(self, states: Sequence[AbstractLMState]) -> None:
+        self._states = states
+
+    @property
+    def states(self) -> Sequence[AbstractLMState]:
+        return self._states
+
+    def get_mp_safe_state(self) -> "MultiLanguageModelState":
+        return self
+
+
+class MultiLanguageModel(AbstractLanguageModel):
+    """Mean of several language models (reference language_model.py:455-502).  On the device every model keeps
+    its own tables, vocabulary, unigram set and alpha / beta / unk offset / boundary flag; a word's score is the
+    sum of the models' scores divided by their number, the state is the list of the models' states
+    (csrc/b2c_beam.h b2c_text_extend).  At most 4 models."""
 
     def __init__(self, language_models: Sequence[AbstractLanguageModel]) -> None:
         if len(language_models) < 2:
@@ -424,14 +438,29 @@ class MultiLanguageModel(AbstractLanguageModel):
         self._language_models = language_models
 
     @property
+    def language_models(self) -> Sequence[AbstractLanguageModel]:
+        return self._language_models
+
+    @property
     def order(self) -> int:
         return max(lm.order for lm in self._language_models)
 
-    def get_start_state(self) -> AbstractLMState:
-        raise NotImplementedError("MultiLanguageModel is not supported by the B200 kernels yet")
+    def get_start_state(self) -> MultiLanguageModelState:
+        return MultiLanguageModelState([lm.get_start_state() for lm in self._language_models])
 
     def score_partial_token(self, partial_token: str) -> float:
         return float(sum(lm.score_partial_token(partial_token) for lm in self._language_models) / len(self._language_models))
 
-    def score(self, prev_state: AbstractLMState, word: str, is_last_word: bool = False) -> Tuple[float, AbstractLMState]:
-        raise NotImplementedError("MultiLanguageModel is not supported by the B200 kernels yet")
+    def score(self, prev_state: AbstractLMState, word: str, is_last_word: bool = False) -> Tuple[float, MultiLanguageModelState]:
+        if not isinstance(prev_state, MultiLanguageModelState):
+            raise AssertionError("Wrong input state type found. Expected MultiLanguageModelState, got %s" % type(prev_state))
+        if len(prev_state.states) != len(self._language_models):
+            raise AssertionError("Number of states (%d) does not match number of language models (%d)."
+                                 % (len(prev_state.states), len(self._language_models)))
+        score = 0.0
+        end_state = []
+        for lm_prev_state, lm in zip(prev_state.states, self._language_models):
+            lm_score, lm_end_state = lm.score(lm_prev_state, word, is_last_word=is_last_word)
+            score += lm_score
+            end_state.append(lm_end_state)
+        return score / len(self._language_models), MultiLanguageModelState(end_state)

@@ -132,3 +132,86 @@ def run_stream_case(pkg, name, tol=2e-4):
                     return "call %d: beams %d and %d swapped (scores %r, %r)" % (i, a, b, exp[a]["lm_score"], exp[b]["lm_score"])
         beams = out
     return ""
+
+
+def load_multilm():
+    """tests/golden/multilm_cases.json (oracle/gen_golden_multilm.py: the reference's MultiLanguageModel)."""
+    if "m" not in _cache:
+        with open(os.path.join(HERE, "golden", "multilm_cases.json"), encoding="utf-8") as fh:
+            meta = json.load(fh)
+        _cache["m"] = {"meta": meta, "arrays": dict(np.load(os.path.join(HERE, "golden", "multilm_arrays.npz")))}
+    return _cache["m"]
+
+
+def multilm_case_names():
+    return [c["name"] for c in load_multilm()["meta"]["cases"]]
+
+
+def build_multilm_decoder(pkg, case):
+    g = load()
+    models = []
+    for m in case["models"]:
+        if m["arpa_kind"] == "toy":
+            path, words = g["toy_arpa"], None
+        else:
+            key = json.dumps(m["workload"], sort_keys=True)
+            if key not in g["workloads"]:
+                g["workloads"][key] = synth.make_workload(m["workload"])
+            path, words = g["workloads"][key].arpa, g["workloads"][key].words
+        unigrams = m.get("unigrams")
+        if unigrams is None and m.get("unigrams_first") is not None:
+            unigrams = words[: m["unigrams_first"]]
+        kw = {k: m[k] for k in ("alpha", "beta", "unk_score_offset", "score_boundary") if k in m}
+        models.append(pkg.LanguageModel(pkg.NgramModel(path), unigrams, **kw))
+    return pkg.BeamSearchDecoderCTC(pkg.Alphabet.build_alphabet(case["labels"]), pkg.MultiLanguageModel(models))
+
+
+def run_multilm_case(pkg, name, tol=2e-4):
+    """The product's decoder over a MultiLanguageModel against what the unmodified reference returned: all beams
+    (text, word frames, both scores), decode(), a second call started from the best beam's MultiLanguageModelState,
+    and chunked partial_decode_beams.  Returns '' or the first difference."""
+    g, m = load(), load_multilm()
+    case = next(c for c in m["meta"]["cases"] if c["name"] == name)
+    x = m["arrays"][case["array"]] if case["array"] in m["arrays"] else g["arrays"][case["array"]]
+    dec = build_multilm_decoder(pkg, case)
+    dkw = case["decode"]
+
+    def as_tuples(beams):
+        return [(b.text, b.text_frames, b.logit_score, b.lm_score) for b in beams]
+
+    out = dec.decode_beams(x, **dkw)
+    diff = beams_match(case["beams"], as_tuples(out), tol=tol)
+    if diff:
+        return "decode_beams: " + diff
+    if dec.decode(x, **{k: v for k, v in dkw.items() if k != "prune_history"}) != case["decode_text"]:
+        return "decode() text differs"
+    if "split" in case:
+        first = dec.decode_beams(x[:case["split"]], **dkw)
+        diff = beams_match(case["split_first"], as_tuples(first), tol=tol)
+        if diff:
+            return "first half: " + diff
+        state = first[0].last_lm_state
+        if state is None or len(state.states) != len(case["models"]):
+            return "last_lm_state is not a MultiLanguageModelState with %d states" % len(case["models"])
+        second = dec.decode_beams(x[case["split"]:], lm_start_state=state, **dkw)
+        diff = beams_match(case["split_second"], as_tuples(second), tol=tol)
+        if diff:
+            return "second half (from the carried state): " + diff
+    if "stream" in case:
+        beams, cached_lm, cached_p = dec.get_starting_state()
+        kw = {k: v for k, v in dkw.items() if k in ("beam_width", "prune_history")}
+        for i, step in enumerate(case["stream"]):
+            got = dec.partial_decode_beams(x[step["start"]:step["end"]], cached_lm, cached_p, beams, step["start"],
+                                           is_end=(i == len(case["stream"]) - 1), **kw)
+            exp = step["beams"]
+            if len(got) != len(exp):
+                return "stream call %d: %d beams != %d" % (i, len(got), len(exp))
+            for j, (o, e) in enumerate(zip(got, exp)):
+                a = (o.text, o.partial_word, o.last_char, [list(f) for f in o.text_frames], list(o.partial_frames))
+                b = (e["text"], e["partial_word"], e["last_char"], e["text_frames"], e["partial_frames"])
+                if a != b:
+                    return "stream call %d beam %d: %r != %r" % (i, j, a, b)
+                if abs(o.lm_score - e["lm_score"]) > tol + 1e-6 * abs(e["lm_score"]) or abs(o.logit_score - e["logit_score"]) > tol + 1e-6 * abs(e["logit_score"]):
+                    return "stream call %d beam %d scores (%r, %r) != (%r, %r)" % (i, j, o.logit_score, o.lm_score, e["logit_score"], e["lm_score"])
+            beams = got
+    return ""

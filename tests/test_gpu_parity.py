@@ -273,3 +273,9 @@ def test_gpu_streaming_batch_equals_whole(pkg):
         for o, g in zip(w, got):
             assert abs(o.logit_score - g.logit_score) <= 1e-9 * max(1.0, abs(o.logit_score))
             assert abs(o.lm_score - g.lm_score) <= 1e-9 * max(1.0, abs(o.lm_score))
+
+
+@pytest.mark.parametrize("name", goldens.multilm_case_names())
+def test_gpu_multi_language_model_matches_reference_golden(pkg, name):
+    """MultiLanguageModel on the device against the unmodified reference (tests/golden/multilm_cases.json)."""
+    assert goldens.run_multilm_case(pkg, name) == ""

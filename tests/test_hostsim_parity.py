@@ -218,3 +218,10 @@ def test_hostsim_lm_blob_file_roundtrip(sim, tmp_path):
         fh.write(b"\x00\x00\x00\x00")
     with pytest.raises(ValueError):
         sim.build_ctcdecoder(wl.labels, kenlm_model_path=path)
+
+
+@pytest.mark.parametrize("name", goldens.multilm_case_names())
+def test_hostsim_multi_language_model_matches_reference_golden(sim, name):
+    """MultiLanguageModel (mean of 2-3 n-gram models with their own parameters and unigram lists) against the
+    unmodified reference: all beams, decode(), carried MultiLanguageModelState, chunked streaming."""
+    assert goldens.run_multilm_case(sim, name) == ""
