@@ -127,6 +127,8 @@ typedef struct {
     const struct b2c_stream_state* stream_states;
     int finalize_mode;         /* B2C_FIN_EOS (default): decode_beams / is_end=True; B2C_FIN_FLUSH: force_next_word=True,
                                   is_end=False; B2C_FIN_KEEP: neither -- beams keep their partial words (decoder.py:571-593) */
+    int text_only;             /* decode() / decode_batch() (decoder.py:859-945 return beam.text only): word frames are
+                                  neither copied back nor assembled; b2c_result_n_words is 0 */
 } b2c_decode_opts_t;
 void b2c_decode_opts_default(b2c_decode_opts_t* opts);
 

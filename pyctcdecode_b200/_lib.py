@@ -46,6 +46,7 @@ class DecodeOpts(C.Structure):
         ("lm_start_states", C.POINTER(LMState)),
         ("stream_states", C.POINTER(StreamState)),
         ("finalize_mode", C.c_int),
+        ("text_only", C.c_int),
     ]
 
 

@@ -518,6 +518,27 @@ static void build_hot(const b2c_decode_opts_t* o, std::vector<B2cHot>& tab, int&
     }
 }
 
+// decode() / decode_batch() want the text only: no word vector, no frames
+static void assemble_text(const b2c_decoder* d, const u32* toks, int nt, BeamRes& br) {
+    br.text.clear();
+    br.words.clear();
+    br.frames.clear();
+    bool open_word = false;      // the current word has at least one character
+    bool need_space = false;     // a finished word precedes
+    for (int i = nt - 1; i >= 0; --i) {
+        const u32 tok = toks[i] & 0xFFFFu, kind = toks[i] >> 16;
+        if (kind != B2C_CK_CONT) {       // word boundary: space, or a BPE piece that starts the next word
+            if (open_word) need_space = true;
+            open_word = false;
+            if (kind != B2C_CK_BPE) continue;
+        }
+        const std::string& piece = kind == B2C_CK_CONT ? d->labels[tok] : d->clean[tok];
+        if (piece.empty()) continue;
+        if (!open_word && need_space) br.text += ' ';
+        br.text += piece;
+        open_word = true;
+    }
+}
 static void assemble_beam(const b2c_decoder* d, const u32* toks, int nt, const int* frames, int nw, BeamRes& br) {
     std::string word;
     br.words.clear();
@@ -1393,12 +1414,13 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     // ---- device -> host -------------------------------------------------------------------
     CUDA_OK(cudaMemcpyAsync(d->h_out_small.p, d->d_out_small.p, small_bytes, cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaMemcpyAsync(d->h_out_toks.p, d->d_out_toks.p, tok_bytes, cudaMemcpyDeviceToHost, st));
-    CUDA_OK(cudaMemcpyAsync(d->h_out_frames.p, d->d_out_frames.p, frm_bytes, cudaMemcpyDeviceToHost, st));
+    const bool text_only = opts->text_only != 0 && !streaming;
+    if (!text_only) CUDA_OK(cudaMemcpyAsync(d->h_out_frames.p, d->d_out_frames.p, frm_bytes, cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaEventRecord(d->ev[4], st));
     hp_mark(2);                                   // launch planning + enqueue of the beam kernel and D2H
     CUDA_OK(cudaStreamSynchronize(st));
     hp_mark(3);                                   // wait: beam kernel + D2H
-    d->tm.d2h_bytes += static_cast<long long>(small_bytes + tok_bytes + frm_bytes + 8ull * n_utts + 32);
+    d->tm.d2h_bytes += static_cast<long long>(small_bytes + tok_bytes + (text_only ? 0 : frm_bytes) + 8ull * n_utts + 32);
     {
         u32 ms[16];
         CUDA_OK(cudaMemcpy(ms, d->d_mstats.p, 64, cudaMemcpyDeviceToHost));
@@ -1484,7 +1506,8 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
                 br.lm = h_sc[2 * k + 1];
                 br.st = h_ls[k];
                 if (h_lx) br.stx.assign(h_lx + k * (n_lm - 1), h_lx + (k + 1) * (n_lm - 1));
-                assemble_beam(d, h_toks + base + r * stride, h_nt[k], h_frames + 2 * (base + r * stride), h_nw[k], br);
+                if (text_only) assemble_text(d, h_toks + base + r * stride, h_nt[k], br);
+                else assemble_beam(d, h_toks + base + r * stride, h_nt[k], h_frames + 2 * (base + r * stride), h_nw[k], br);
                 if (h_ax) {
                     const u32* tk = h_toks + base + r * stride;
                     br.raw.resize(static_cast<size_t>(h_nt[k]));

@@ -628,7 +628,7 @@ B2C_HD u32 b2c_live_before(const u32* wm, u32 pos) {   // live slots with index 
 
 // number of leading slots p (of n, scores non-increasing) whose candidate for a token with log-prob lp2 sorts
 // before score s: (logit[p] + lp2) + 0 >= s (or > s when `ge` is false).  Three levels of independent probes
-// (3 x stride 32, 3 x stride 8, 7 x stride 1: 13 probes, 3 dependent rounds) instead of a 7-step dependent binary
+// (3 x stride 32, 3 x stride 8, 8 x stride 1: 14 probes, 3 dependent rounds) instead of a 7-step dependent binary
 // search: the frame is bound by dependent-instruction latency.
 B2C_HD u32 b2c_sorted_probe(const double* logit, u32 n, u32 p, double lp2, double s, bool ge) {
     if (p >= n) return 0u;
@@ -647,8 +647,8 @@ B2C_HD u32 b2c_sorted_count(const double* logit, u32 n, double lp2, double s, bo
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
-    for (u32 q = 0; q < 7; ++q) cnt += b2c_sorted_probe(logit, n, base + q, lp2, s, ge);
-    return base + cnt;
+    for (u32 q = 0; q < 8; ++q) cnt += b2c_sorted_probe(logit, n, base + q, lp2, s, ge);   // 8: in the last block of 8
+    return base + cnt;                                                                      // slot base + 7 was never probed
 }
 
 // returns false (state untouched) when the best score is not finite

@@ -339,6 +339,7 @@ class BeamSearchDecoderCTC:
         if stream is not None:
             opts.stream_states = C.cast(self._stream_states(handle, stream, keep_alive), C.POINTER(_lib.StreamState))
         opts.finalize_mode = int(finalize_mode)
+        opts.text_only = int(bool(texts_only))
         ptrs = (C.c_void_p * n)(*[m[1] for m in mats])
         Ts = (C.c_int32 * n)(*[m[2] for m in mats])
         res = C.c_void_p()
