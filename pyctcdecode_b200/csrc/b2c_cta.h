@@ -13,6 +13,9 @@
 // must be block-uniform (it reads only kernel arguments and shared scalars).
 #pragma once
 #include "b2c_common.h"
+#if !defined(__CUDACC__)
+#include <cstdlib>
+#endif
 
 #if defined(__CUDACC__)
 #define B2C_NOINLINE __noinline__
@@ -27,7 +30,23 @@
 #define B2C_FOR_WARP(w, nw) for (int w = static_cast<int>(threadIdx.x >> 5), _once = 1; _once; _once = 0)
 #define B2C_NWARPS() (static_cast<int>(blockDim.x >> 5))
 #else
-#define B2C_FOR(i, n) for (int i = 0; i < static_cast<int>(n); ++i)
+// hostsim runs the work items of a phase one after another.  Any order is a legal interleaving of the CUDA
+// execution, so the results must not depend on it: B200CTC_HOSTSIM_ORDER=1 (reverse) / 2 (stride 7) / 3 (odd items
+// first) make tests/ replay every phase in another order -- a cheap detector for missing barriers and for code that
+// silently relies on thread order.
+inline int b2c_hostsim_order() {
+    static const int mode = [] { const char* e = std::getenv("B200CTC_HOSTSIM_ORDER"); return e ? std::atoi(e) : 0; }();
+    return mode;
+}
+inline int b2c_hostsim_item(int k, int n) {
+    switch (b2c_hostsim_order()) {
+        case 1: return n - 1 - k;
+        case 2: return n % 7 == 0 ? (n - 1 - k) : static_cast<int>((static_cast<long long>(k) * 7) % n);   // bijection iff gcd(7, n) == 1
+        case 3: { const int odd = n / 2; return k < odd ? 2 * k + 1 : 2 * (k - odd); }
+        default: return k;
+    }
+}
+#define B2C_FOR(i, n) for (int _k##i = 0, _n##i = static_cast<int>(n), i = 0; _k##i < _n##i && ((i = b2c_hostsim_item(_k##i, _n##i)), true); ++_k##i)
 #define B2C_SYNC() ((void)0)
 #define B2C_LEADER if (true)
 #define B2C_FOR_WARP(w, nw) for (int w = 0; w < static_cast<int>(nw); ++w)

@@ -225,3 +225,16 @@ def test_hostsim_multi_language_model_matches_reference_golden(sim, name):
     """MultiLanguageModel (mean of 2-3 n-gram models with their own parameters and unigram lists) against the
     unmodified reference: all beams, decode(), carried MultiLanguageModelState, chunked streaming."""
     assert goldens.run_multilm_case(sim, name) == ""
+
+
+@pytest.mark.parametrize("order", ["1", "3"])
+def test_hostsim_results_do_not_depend_on_work_item_order(order):
+    """hostsim replays the work items of every phase in another order (B200CTC_HOSTSIM_ORDER: 1 reverse, 3 odd items
+    first; csrc/b2c_cta.h).  Any order is a legal interleaving of the CUDA execution, so the parity tests must pass
+    unchanged -- this catches code that silently relies on thread order inside a phase."""
+    import sys
+    env = dict(os.environ, B200CTC_HOSTSIM_ORDER=order, B200CTC_FORCE_V5="1")
+    here = os.path.abspath(__file__)
+    r = subprocess.run([sys.executable, "-m", "pytest", here, "-x", "-q", "-k", "special or random or ragged or streaming_chunks"],
+                       env=env, cwd=os.path.dirname(os.path.dirname(here)), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout[-3000:]
