@@ -240,13 +240,21 @@ def test_gpu_special_single_token_steps(pkg, orc, variant, monkeypatch):
     dec = pkg.build_ctcdecoder(wl.labels)
     ora = orc.OracleDecoder(wl.labels)
     inplace = ranked = 0
-    for x, kw in synth.special_step_cases(wl):
+    for n, (x, kw) in enumerate(synth.special_step_cases(wl)):
         got = _beams(dec.decode_beams(x, **kw))
         tm = dec.last_timings()
         inplace += tm["inplace_frames"]
         ranked += tm["sorted_frames"]
-        _compare(ora.decode_beams(x, **kw), got)
-    assert inplace > 1000 and ranked > 100
+        want = ora.decode_beams(x, **kw)
+        try:
+            _compare(want, got)
+        except AssertionError as e:
+            first = next((j for j, (w, g) in enumerate(zip(want, got)) if w[0] != g[0] or abs(w[3] - g[3]) > 1e-9 * max(1.0, abs(w[3]))), -1)
+            raise AssertionError("case %d T=%d %r: %d vs %d beams, first difference at beam %d: want %r got %r; timings %r"
+                                 % (n, x.shape[0], kw, len(want), len(got), first, want[first] if first >= 0 else None,
+                                    got[first] if 0 <= first < len(got) else None,
+                                    {k: tm[k] for k in ("kernel_variant", "cap_candidates", "oversize_frames", "inplace_frames", "sorted_frames")})) from e
+    assert inplace > 1000 and ranked > 100, (inplace, ranked)
 
 
 @pytest.mark.parametrize("name", goldens.stream_case_names())

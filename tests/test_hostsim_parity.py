@@ -238,3 +238,20 @@ def test_hostsim_results_do_not_depend_on_work_item_order(order):
     r = subprocess.run([sys.executable, "-m", "pytest", here, "-x", "-q", "-k", "special or random or ragged or streaming_chunks"],
                        env=env, cwd=os.path.dirname(os.path.dirname(here)), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0, r.stdout[-3000:]
+
+
+def test_hostsim_text_only_results_equal_full_results(sim):
+    """decode_batch() asks the library for texts only (no frames, no word vectors: assemble_text); the texts must be
+    the top beams' texts of the full result path, for character and BPE alphabets."""
+    for fam in ("B_nolm", "B_3gram", "C_bpe", "C_bpe_4gram"):
+        wkw, lmkw = FAMILIES[fam]
+        wl = synth.make_workload(wkw)
+        kw = dict(lmkw)
+        if wl.arpa:
+            kw.update(kenlm_model_path=wl.arpa, unigrams=wl.words)
+        dec = sim.build_ctcdecoder(wl.labels, **kw)
+        T = 120 if wl.V <= 64 else 50
+        xs = [wl.utterance(8600 + i, T - 7 * i, ["peaky", "diffuse"][i % 2]) for i in range(6)] + [np.zeros((0, wl.V), np.float32)]
+        texts = dec.decode_batch(None, xs, beam_width=20)
+        full = [dec.decode_beams(x, beam_width=20, prune_history=True)[0].text for x in xs]
+        assert texts == full
