@@ -1,0 +1,34 @@
+// TEST INFRASTRUCTURE ONLY: exhaustive check of b2c_sorted_count (csrc/b2c_beam_fast.h, the three-level search of
+// the merge-free sorted step) against a linear scan, for every table size 1..128 and every answer 0..n.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include "cuda_shim.h"
+#include "b2c_beam.h"
+struct B2cFrameRec { u32 off; u32 cnt; };
+#define B2C_RUN 8
+struct B2cBeamArgs {
+    B2cParams P; B2cLayout L; int n_utts; const int* order; u32* next; const u64* frame_off; const int* T; const B2cFrameRec* tok_rec;
+    const u16* tok_ids; const double* tok_lp; u8* gws; const B2cLmState* start_states; int* out_nbeams; int* out_status; double* out_scores;
+    int* out_ntok; int* out_nwords; u32* out_toks; int* out_frames; B2cLmState* out_states; u64* phase_clk; u32* m_stats;
+};
+#include "b2c_beam_fast.h"
+int main() {
+    double logit[128];
+    int bad = 0;
+    for (int n = 1; n <= 128; ++n) {
+        for (int i = 0; i < n; ++i) logit[i] = -0.01 * (i / 2);          // non-increasing, with ties
+        for (int t = 0; t <= n; ++t) {
+            const double s = t == n ? -100.0 : logit[t] + 0.0;
+            for (int ge = 0; ge < 2; ++ge) {
+                int want = 0;
+                for (int i = 0; i < n; ++i) { const double s2 = (logit[i] + 0.0) + 0.0; want += ge ? (s2 >= s) : (s2 > s); }
+                const u32 got = b2c_sorted_count<128>(logit, static_cast<u32>(n), 0.0, s, ge != 0);
+                if (static_cast<int>(got) != want) { if (bad < 10) std::printf("n=%d t=%d ge=%d want %d got %u\n", n, t, ge, want, got); ++bad; }
+            }
+        }
+    }
+    std::printf("bad %d\n", bad);
+    return bad ? 1 : 0;
+}

@@ -135,3 +135,16 @@ def test_lm_host_queries_match_oracle(golden, tmp_path):
                     st, rst = out, rout
     finally:
         _lib._lib = None
+
+
+def test_sorted_step_search_matches_linear_scan(tmp_path):
+    """b2c_sorted_count (three-level search of the merge-free sorted step) against a linear scan for every table
+    size 1..128, every answer 0..n, ties included (tests/hostsim/t_sorted_count.cpp)."""
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    exe = str(tmp_path / "t_sorted_count")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-DB2C_HOSTSIM", "-I" + os.path.join(here, "hostsim"),
+                           "-I" + os.path.join(os.path.dirname(here), "pyctcdecode_b200", "csrc"),
+                           os.path.join(here, "hostsim", "t_sorted_count.cpp"), "-o", exe])
+    out = subprocess.run([exe], stdout=subprocess.PIPE, text=True)
+    assert out.returncode == 0, out.stdout
