@@ -174,6 +174,7 @@ B2C_HD void b2c_beam_block(const B2cBeamArgs& A, int slot, u8* smem) {
     B2C_LEADER {
         for (int q = 0; q < 6; ++q) W.sc->m_over[q] = 0;
         W.sc->m_frames = 0;
+        W.sc->m_inplace = 0;
     }
 #if defined(B2C_PHASE_CLOCKS) && defined(__CUDA_ARCH__)
     for (int q = 0; q < 16; ++q) W.clk[q] = 0;
@@ -194,33 +195,48 @@ B2C_HD void b2c_beam_block(const B2cBeamArgs& A, int slot, u8* smem) {
         rec.cnt = 1;
         if (Tn > 0) rec = recs[0];
         B2cStreamIn sin{nullptr, 0u, nullptr, nullptr};
-        int t0 = 0;
+        int t0_frames = 0;
         if (A.s_utts) {
             const B2cStreamUtt su = A.s_utts[u];
             sin.beams = A.s_beams + su.beam_off;
             sin.n_beams = su.n_beams;
             sin.word_hash = A.s_word_hash;
             sin.word_len = A.s_word_len;
-            t0 = su.t0;
+            t0_frames = su.t0;
         }
         b2c_utt_begin(A.P, W, A.start_states ? A.start_states + static_cast<u64>(u) * (A.P.n_lm > 1 ? A.P.n_lm : 1) : nullptr,
                       static_cast<int>(rec.cnt), sin);
 #if defined(__CUDACC__)
 #pragma unroll 1
 #endif
+        u32 prev_single = B2C_NONE_U32;   // canonical token of the previous frame if it selected exactly one token
         for (int t = 0; t < Tn; ++t) {
             B2cFrameRec nxt;
             nxt.off = 0;
             nxt.cnt = 1;
             if (t + 1 < Tn) nxt = recs[t + 1];      // one frame ahead: hides the load latency
             const u64 base = (f0 + static_cast<u64>(t & ~(B2C_RUN - 1))) * static_cast<u64>(A.P.V) + rec.off;
-            if (kFast && W.sc->n_beams * rec.cnt > L.cap_s) {
-                b2c_frame_step_slow(A.P, L, smem, g, parity, t + t0, A.tok_ids + base, A.tok_lp + base, static_cast<int>(rec.cnt), static_cast<int>(nxt.cnt));
-                b2c_swap_tabs(W.cur, W.nxt);   // the out-of-line step swapped its private descriptor
-            } else {
-                b2c_frame_step<kFast>(A.P, W, t + t0, A.tok_ids + base, A.tok_lp + base, static_cast<int>(rec.cnt), static_cast<int>(nxt.cnt));
+            bool in_place = false;
+            u32 single = B2C_NONE_U32;
+            if (rec.cnt == 1) {
+                const u16 id0 = A.tok_ids[base];
+                const B2cTok t0 = A.P.toks[id0];
+                single = t0.canon;
+                const int kind = b2c_inplace_kind(W.sc->flags, prev_single, t0.flags, t0.canon);
+                if (kind != B2C_INPLACE_NO)
+                    in_place = b2c_inplace_step(A.P, W, t + t0_frames, kind, id0, A.tok_lp[base], static_cast<int>(nxt.cnt));
             }
-            parity ^= 1;
+            prev_single = single;
+            if (in_place) {
+                // no table swap, no parity flip
+            } else if (kFast && W.sc->n_beams * rec.cnt > L.cap_s) {
+                b2c_frame_step_slow(A.P, L, smem, g, parity, t + t0_frames, A.tok_ids + base, A.tok_lp + base, static_cast<int>(rec.cnt), static_cast<int>(nxt.cnt));
+                b2c_swap_tabs(W.cur, W.nxt);   // the out-of-line step swapped its private descriptor
+                parity ^= 1;
+            } else {
+                b2c_frame_step<kFast>(A.P, W, t + t0_frames, A.tok_ids + base, A.tok_lp + base, static_cast<int>(rec.cnt), static_cast<int>(nxt.cnt));
+                parity ^= 1;
+            }
             rec = nxt;
         }
         B2cOut O;
@@ -244,6 +260,7 @@ B2C_HD void b2c_beam_block(const B2cBeamArgs& A, int slot, u8* smem) {
             for (int q = 0; q < 6; ++q)
                 if (W.sc->m_over[q]) b2c_atomic_add_u32(A.m_stats + q, W.sc->m_over[q]);
             b2c_atomic_add_u32(A.m_stats + 6, W.sc->m_frames);
+            if (W.sc->m_inplace) b2c_atomic_add_u32(A.m_stats + 7, W.sc->m_inplace);
         }
     }
 #if defined(B2C_PHASE_CLOCKS) && defined(__CUDA_ARCH__)

@@ -57,6 +57,8 @@ struct B2cScalars {
                          // cannot unswitch (= replicate) the frame loop on them
     u32 m_over[6];       // frames whose candidate count exceeded 128,256,512,1024,2048,4096 (adaptive sizing)
     u32 m_frames;
+    u32 inplace_bad;     // a thread's exactness check of b2c_inplace_step failed (rare)
+    u32 m_inplace;       // frames handled by b2c_inplace_step
 };
 enum { B2C_FL_BPE = 1, B2C_FL_PRUNE = 2, B2C_FL_LM = 4, B2C_FL_PSCORE = 8 };
 
@@ -828,6 +830,98 @@ B2C_HD void b2c_frame_step(const B2cParams& P, B2cWork& W, int t, const u16* tk_
     b2c_swap_tabs(W.cur, W.nxt);
 }
 
+// -----------------------------------------------------------------------------------------
+// single-token frame right after a single-token frame, updated IN PLACE (general kernel; the latency-first kernel
+// has its own copy working on its table with holes, b2c_fast_cheap_step in b2c_beam_fast.h, where the argument is
+// spelled out): every beam ends in the previous token c', so a frame that selects only c', only the blank, or (no
+// LM, no hotwords, regular alphabet) one ordinary character maps every beam to exactly one new beam in the same
+// order with the same log-prob added -- no merge, no reordering, no new history-prune victim.  What float64
+// rounding could change (order, threshold) is re-checked; on failure the state is untouched and the caller runs the
+// general step.  No table swap; leaves the tables clear for the next frame like phase D does.
+// -----------------------------------------------------------------------------------------
+enum { B2C_INPLACE_NO = 0, B2C_INPLACE_T0 = 1, B2C_INPLACE_T3 = 2 };
+B2C_HD int b2c_inplace_kind(u32 flags, u32 prev_single, u16 tok_flags, u16 tok_canon) {
+    if (prev_single == B2C_NONE_U32) return B2C_INPLACE_NO;
+    if ((tok_flags & B2C_TF_BLANK) || prev_single == tok_canon) return B2C_INPLACE_T0;
+    if (!(flags & (B2C_FL_PSCORE | B2C_FL_BPE)) && !(tok_flags & B2C_TF_SPACE)) return B2C_INPLACE_T3;
+    return B2C_INPLACE_NO;
+}
+B2C_HDN bool b2c_inplace_step(B2cParams P, B2cWork W, int t, int kind, u16 tok_id, double p, int K_next) {
+    B2cScalars* sc = W.sc;
+    const u32 n = sc->n_beams;
+    const u32 flags = sc->flags;
+    const bool has_lm = (flags & B2C_FL_LM) != 0, plain = (flags & B2C_FL_PSCORE) == 0;
+    const B2cBeamTab cur = W.cur;
+    const B2cTok ti = P.toks[tok_id];
+    const double top = plain ? (cur.logit[0] + p) + 0.0
+                             : b2c_combine_score(has_lm, cur.logit[0] + p, cur.lm_hw[0], cur.pscore[0], cur.part_len[0]);
+    const double thr = top + P.prune_logp;
+    B2C_FOR(b, n) {
+        if (plain) {      // order is preserved by monotone rounding; only the threshold needs the check
+            if (!((cur.logit[b] + p) + 0.0 >= thr)) sc->inplace_bad = 1;
+            continue;
+        }
+        const double mine = b2c_combine_score(has_lm, cur.logit[b] + p, cur.lm_hw[b], cur.pscore[b], cur.part_len[b]);
+        bool ok = mine >= thr;
+        if (static_cast<u32>(b) + 1 < n) {
+            const double next = b2c_combine_score(has_lm, cur.logit[b + 1] + p, cur.lm_hw[b + 1], cur.pscore[b + 1], cur.part_len[b + 1]);
+            ok = ok && mine >= next;
+        }
+        if (!ok) sc->inplace_bad = 1;
+    }
+    B2C_SYNC();
+    if (sc->inplace_bad) {      // block-uniform
+        B2C_SYNC();
+        B2C_LEADER { sc->inplace_bad = 0; }
+        B2C_SYNC();
+        return false;
+    }
+    const bool blank = (ti.flags & B2C_TF_BLANK) != 0;
+    B2C_FOR(b, n) {
+        cur.logit[b] = cur.logit[b] + p;
+        cur.last_tok[b] = ti.canon;
+        if (kind == B2C_INPLACE_T0) {
+            if (!blank) cur.pf_e[b] = t + 1;
+        } else {
+            const int ps0 = cur.pf_s[b], pe0 = cur.pf_e[b];
+            cur.part_hash[b] = b2c_hash_append(cur.part_hash[b], ti.raw_hash, ti.raw_pow);
+            cur.part_len[b] = static_cast<u16>(cur.part_len[b] + ti.raw_nchars);
+            if (ps0 < 0) cur.pf_s[b] = t;
+            cur.pf_e[b] = t + 1;
+            const u32 id = b2c_atomic_add_u32(&sc->chain_used, 1u);
+            if (id < W.chain_cap) {
+                B2cChain c;
+                c.parent = cur.chain[b];
+                c.tok = tok_id;
+                c.kind = B2C_CK_CONT;
+                c.has_word = 0;
+                c.ws = ps0;
+                c.we = pe0;
+                W.chain[id] = c;
+                cur.chain[b] = id;
+            } else {
+                b2c_atomic_or_u32(&sc->status, B2C_ERR_CHAIN_FULL);
+            }
+        }
+    }
+    {   // what phase D of the general step leaves behind: tables clear for the next frame
+        const u32 M_next = n * static_cast<u32>(K_next);
+        const B2cCandTier Cn = b2c_pick_tier(W, M_next);
+        u32 Hn = b2c_ht_size(M_next);
+        if (Hn > Cn.ht_cap) Hn = Cn.ht_cap;
+        b2c_clear_tables(W, Cn, Hn);
+    }
+    B2C_LEADER {
+        sc->prev_max = top;
+        ++sc->m_frames;
+        ++sc->m_inplace;
+        for (int q = 0; q < 6; ++q)
+            if (n > (128u << q)) ++sc->m_over[q];
+    }
+    B2C_SYNC();
+    return true;
+}
+
 // frames whose candidate count exceeds the shared-memory tier (a few very wide frames per
 // utterance, flat logits) take this out-of-line copy that works on the HBM tier through generic
 // pointers.  It operates on a COPY of the work descriptor so that the hot path's descriptor never
@@ -861,6 +955,7 @@ B2C_HDN void b2c_utt_begin(B2cParams P, B2cWork W, const B2cLmState* start_state
         sc->text_used = 1;
         sc->status = B2C_OK;
         sc->force_break = 0;
+        sc->inplace_bad = 0;
         sc->prev_max = 0.0;
         u32 fl = 0;
         if (P.is_bpe) fl |= B2C_FL_BPE;

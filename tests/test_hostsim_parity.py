@@ -255,3 +255,42 @@ def test_hostsim_text_only_results_equal_full_results(sim):
         texts = dec.decode_batch(None, xs, beam_width=20)
         full = [dec.decode_beams(x, beam_width=20, prune_history=True)[0].text for x in xs]
         assert texts == full
+
+
+def test_hostsim_general_kernel_in_place_frames():
+    """b2c_inplace_step (general kernel: beam_width > 128, streaming, MultiLanguageModel) against the oracle; run in
+    a subprocess with the latency-first kernel disabled so that beams <= 128 take the general kernels too."""
+    import sys
+    code = r'''
+import os, sys
+sys.path.insert(0, %r)
+import numpy as np
+from tests import synth
+from oracle import oracle as orc
+import pyctcdecode_b200 as sim
+from pyctcdecode_b200 import _lib
+_lib.use_library(%r)
+total = 0
+for wkw, lmkw in [(dict(kind="char", vocab="B", n_words=400, lm_order=0), {}), (dict(kind="char", vocab="B", n_words=400, lm_order=3), dict(alpha=0.5, beta=1.0))]:
+    wl = synth.make_workload(wkw)
+    kw = dict(lmkw)
+    if wl.arpa:
+        kw.update(kenlm_model_path=wl.arpa, unigrams=wl.words)
+    dec = sim.build_ctcdecoder(wl.labels, **kw)
+    ora = orc.OracleDecoder(wl.labels, **kw)
+    for i, (x, dkw) in enumerate(synth.special_step_cases(wl, n_cases=18)):
+        if i %% 3 == 0:
+            dkw = dict(dkw, beam_width=300)
+        got = dec.decode_beams(x, **dkw)
+        total += dec.last_timings()["inplace_frames"]
+        ref = ora.decode_beams(x, **dkw)
+        assert len(got) == len(ref)
+        for g, r in zip(got, ref):
+            assert g.text == r[0] and g.text_frames == r[1]
+            assert abs(g.logit_score - r[2]) <= 1e-9 * max(1.0, abs(r[2])) and abs(g.lm_score - r[3]) <= 1e-9 * max(1.0, abs(r[3]))
+assert total > 500, total
+''' % (os.path.dirname(HOSTSIM.rstrip("/")).rsplit("/tests", 1)[0], os.path.join(HOSTSIM, "libb200ctc_hostsim.so"))
+    subprocess.check_call(["make", "-s", "-C", HOSTSIM])
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, B200CTC_NO_V5="1"), stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout[-3000:]
