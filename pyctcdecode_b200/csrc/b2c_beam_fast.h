@@ -19,6 +19,16 @@
 // Frames with more than CAP candidates (or more than B2C_FAST_KS tokens) are rare on ASR-like
 // posteriors; they take the general out-of-line step on the HBM candidate tier (b2c_fast_slow_step).
 //
+// Three kinds of frame steps, chosen per frame from block-uniform facts (token count, the previous frame's
+// token, mode flags):
+//   b2c_fast_cheap_step   one token after a one-token frame (same token / blank / plain character without LM and
+//                         hotwords): nothing can merge, reorder or be pruned -> the table is updated in place
+//   b2c_fast_sorted_step  K >= 2 tokens after a one-token frame, no LM / hotwords / space: the candidates are K
+//                         sorted lists that cannot merge -> ranks by search, one commit per thread
+//   b2c_fast_step         everything else: expand + group | fold + fuse + bucket | threshold + rank + commit
+// Every special step re-checks what float64 rounding could change and falls back to b2c_fast_step on the untouched
+// state, so all three give the reference's result (tests: special_step_cases, hostsim work-item-order replay).
+//
 // Reference lines restated: decoder.py:443-554 (frame loop), :211-224 (merge), :346-424 (LM
 // fusion), :545-554 (threshold, top-N, history prune).  Order-dependence notes: b2c_beam.h.
 #pragma once
