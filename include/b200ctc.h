@@ -34,6 +34,8 @@ extern "C" {
 
 #define B2C_DTYPE_F32 0
 #define B2C_DTYPE_F64 1
+#define B2C_DTYPE_F16 2     /* IEEE half: copied as 2-byte elements, widened to float32 on the device (exact) */
+#define B2C_DTYPE_BF16 3    /* bfloat16: likewise */
 
 typedef struct b2c_lm b2c_lm_t;            /* flattened n-gram model (host blob + device copies) */
 typedef struct b2c_decoder b2c_decoder_t;  /* one decoder bound to one CUDA device */
@@ -134,7 +136,7 @@ void b2c_decode_opts_default(b2c_decode_opts_t* opts);
 
 /* Replaces decode_batch / decode_beams_batch (decoder.py:801-857, :895-945) and, with
  * n_utts == 1, decode / decode_beams (:730-775, :859-893).
- *   logits[i]  -> C-contiguous [T[i], V] matrix of dtype (B2C_DTYPE_*), host pointers when
+ *   logits[i]  -> C-contiguous [T[i], V] matrix of dtype (B2C_DTYPE_*; half types are computed as float32), host pointers when
  *                 is_device == 0 (copied host->device inside the call), device pointers on the
  *                 decoder's device when is_device != 0 (used in place when contiguous);
  *   ragged T and T == 0 are allowed.                                                      */

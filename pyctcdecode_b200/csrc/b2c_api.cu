@@ -280,7 +280,41 @@ static const u32 kV5Cap[3] = {1024, 512, 256};
 static const int kV5Occ[3] = {2, 3, 4};
 static const size_t kV5Smem[3] = {sizeof(B2cFastSmemA), sizeof(B2cFastSmemB), sizeof(B2cFastSmemC)};
 
+// half-precision logits (B2C_DTYPE_F16 / B2C_DTYPE_BF16) travel over PCIe as they are and are widened to float32 on the
+// device, exactly (every half / bfloat16 value is a float32 value); the path then computes as for float32 input
+B2C_HD float b2c_f16_bits_to_float(u16 h) {
+    const u32 sign = static_cast<u32>(h & 0x8000u) << 16;
+    u32 exp = (h >> 10) & 0x1Fu, man = h & 0x3FFu, out;
+    if (exp == 0) {
+        if (man == 0) {
+            out = sign;
+        } else {                                   // subnormal: normalise
+            int e = -1;
+            do { ++e; man <<= 1; } while (!(man & 0x400u));
+            out = sign | (static_cast<u32>(127 - 15 - e) << 23) | ((man & 0x3FFu) << 13);
+        }
+    } else if (exp == 31) {
+        out = sign | 0x7F800000u | (man << 13);
+    } else {
+        out = sign | ((exp + 127 - 15) << 23) | (man << 13);
+    }
+    union { u32 u; float f; } c;
+    c.u = out;
+    return c.f;
+}
+B2C_HD float b2c_bf16_bits_to_float(u16 h) {
+    union { u32 u; float f; } c;
+    c.u = static_cast<u32>(h) << 16;
+    return c.f;
+}
+B2C_HD void b2c_widen_range(const u16* src, float* dst, u64 begin, u64 end, u64 step, int bf16) {
+    for (u64 i = begin; i < end; i += step) dst[i] = bf16 ? b2c_bf16_bits_to_float(src[i]) : b2c_f16_bits_to_float(src[i]);
+}
+
 #ifndef B2C_HOSTSIM
+__global__ void __launch_bounds__(256) b2c_widen_kernel(const u16* src, float* dst, u64 n, int bf16) {
+    b2c_widen_range(src, dst, static_cast<u64>(blockIdx.x) * blockDim.x + threadIdx.x, n, static_cast<u64>(gridDim.x) * blockDim.x, bf16);
+}
 template <int WC, int CAP, int OCC>
 __global__ void __launch_bounds__(B2C_FAST_NT, OCC) b2c_beam_fast_kernel(const B2cBeamArgs A) {
     extern __shared__ __align__(16) u8 b2c_smem[];
@@ -458,7 +492,7 @@ struct b2c_decoder {
     std::vector<ExtraLm> lmx;
     int n_sm = 1;
     size_t smem_optin = 48 * 1024;
-    DevBuf d_lmx, d_stream, d_mstats, d_sumk, d_clk, d_maxk, d_toks, d_logits, d_meta, d_tok_start, d_tok_ids, d_tok_lp, d_rowsum, d_set, d_isprob, d_ws, d_hot, d_states,
+    DevBuf d_raw, d_lmx, d_stream, d_mstats, d_sumk, d_clk, d_maxk, d_toks, d_logits, d_meta, d_tok_start, d_tok_ids, d_tok_lp, d_rowsum, d_set, d_isprob, d_ws, d_hot, d_states,
         d_out_small, d_out_toks, d_out_frames;
     PinBuf h_sumk, h_maxk, h_meta, h_out_small, h_out_toks, h_out_frames;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -875,7 +909,7 @@ void b2c_decoder_destroy(b2c_decoder_t* d) {
     if (!d) return;
     cudaSetDevice(d->device);
     if (d->stream) cudaStreamSynchronize(d->stream);
-    DevBuf* bufs[] = {&d->d_lmx, &d->d_stream, &d->d_mstats, &d->d_sumk, &d->d_clk, &d->d_maxk, &d->d_toks, &d->d_logits, &d->d_meta, &d->d_tok_start, &d->d_tok_ids, &d->d_tok_lp, &d->d_rowsum, &d->d_set,
+    DevBuf* bufs[] = {&d->d_raw, &d->d_lmx, &d->d_stream, &d->d_mstats, &d->d_sumk, &d->d_clk, &d->d_maxk, &d->d_toks, &d->d_logits, &d->d_meta, &d->d_tok_start, &d->d_tok_ids, &d->d_tok_lp, &d->d_rowsum, &d->d_set,
                       &d->d_isprob, &d->d_ws, &d->d_hot, &d->d_states, &d->d_out_small, &d->d_out_toks, &d->d_out_frames};
     for (DevBuf* b : bufs) b->release();
     PinBuf* pins[] = {&d->h_sumk, &d->h_maxk, &d->h_meta, &d->h_out_small, &d->h_out_toks, &d->h_out_frames};
@@ -912,7 +946,11 @@ void b2c_decode_opts_default(b2c_decode_opts_t* o) {
 int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t* T, int n_utts, int dtype, int is_device,
                      const b2c_decode_opts_t* opts, b2c_result_t** out) {
     if (!d || !opts || !out || n_utts < 0 || (n_utts > 0 && (!logits || !T))) return fail(B2C_E_ARG, "null argument");
-    if (dtype != B2C_DTYPE_F32 && dtype != B2C_DTYPE_F64) return fail(B2C_E_ARG, "dtype must be B2C_DTYPE_F32 or B2C_DTYPE_F64");
+    if (dtype < B2C_DTYPE_F32 || dtype > B2C_DTYPE_BF16) return fail(B2C_E_ARG, "dtype must be one of B2C_DTYPE_F32 / F64 / F16 / BF16");
+    // half-precision input: copied as 2-byte elements, widened on the device, then the float32 path
+    const int dtype_in = dtype;
+    const bool half_in = dtype_in == B2C_DTYPE_F16 || dtype_in == B2C_DTYPE_BF16;
+    if (half_in) dtype = B2C_DTYPE_F32;
     if (opts->beam_width < 1) return fail(B2C_E_ARG, "beam_width must be >= 1");
     if (opts->beam_width > 65535) return fail(B2C_E_ARG, "beam_width above 65535 is not supported");
     std::unique_ptr<b2c_result> res(new b2c_result());
@@ -931,6 +969,7 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     CUDA_OK(cudaSetDevice(d->device));
     const int V = d->V;
     const size_t esz = dtype == B2C_DTYPE_F32 ? 4 : 8;
+    const size_t esz_in = half_in ? 2 : esz;         // element size of the caller's matrices
     std::memset(&d->tm, 0, sizeof(d->tm));
 
     // ---- batch geometry -------------------------------------------------------------------
@@ -1053,12 +1092,13 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
         if (!is_device) return false;
         for (int i = 0; i + 1 < n_utts; ++i) {
             if (T[i + 1] == 0) continue;
-            const char* expect = static_cast<const char*>(logits[0]) + frame_off[i + 1] * V * esz;
+            const char* expect = static_cast<const char*>(logits[0]) + frame_off[i + 1] * V * esz_in;
             if (static_cast<const char*>(logits[i + 1]) != expect) return false;
         }
         return T[0] > 0 || n_utts == 1;
     }();
-    if (!contiguous_dev && d->d_logits.ensure(std::max<u64>(total_frames * V * esz, 16))) return B2C_E_NOMEM;
+    if ((half_in || !contiguous_dev) && d->d_logits.ensure(std::max<u64>(total_frames * V * esz, 16))) return B2C_E_NOMEM;
+    if (half_in && !contiguous_dev && d->d_raw.ensure(std::max<u64>(total_frames * V * esz_in, 16))) return B2C_E_NOMEM;
     const size_t meta_bytes = al16(8ull * n_utts) + 3 * al16(4ull * n_utts) + 64 + al16(8ull * (n_utts + 1)) + al16(8ull * n_utts);
     if (d->d_meta.ensure(meta_bytes) || d->h_meta.ensure(meta_bytes)) return B2C_E_NOMEM;
     if (d->d_tok_start.ensure(8 * (total_frames + 1)) || d->d_tok_ids.ensure(2 * n_entries) ||
@@ -1116,10 +1156,10 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     u32* d_next = reinterpret_cast<u32*>(dm + off_next);
     d->tm.h2d_bytes += static_cast<long long>(meta_bytes);
     const void* d_logits = nullptr;
-    if (contiguous_dev) {
+    if (contiguous_dev && !half_in) {
         d_logits = logits[0];
 #ifndef B2C_HOSTSIM
-    } else if (is_device && n_utts > 4) {
+    } else if (is_device && n_utts > 4 && !half_in) {
         d_logits = d->d_logits.p;
         const void** h_ptr = reinterpret_cast<const void**>(hm + off_ptr);
         for (int i = 0; i < n_utts; ++i) h_ptr[i] = logits[i];
@@ -1132,21 +1172,35 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
 #endif
     } else {
         d_logits = d->d_logits.p;
+        const void* packed_half = contiguous_dev ? logits[0] : d->d_raw.p;      // half input only
+        char* dst = half_in ? d->d_raw.as<char>() : d->d_logits.as<char>();
         // coalesce runs of utterances that are adjacent in the source into one copy
         int i = 0;
-        while (i < n_utts) {
+        while (i < n_utts && !(half_in && contiguous_dev)) {
             if (T[i] == 0) { ++i; continue; }
             int j = i;
-            u64 bytes = static_cast<u64>(T[i]) * V * esz;
+            u64 bytes = static_cast<u64>(T[i]) * V * esz_in;
             while (j + 1 < n_utts && T[j + 1] > 0 &&
                    static_cast<const char*>(logits[j + 1]) == static_cast<const char*>(logits[i]) + bytes) {
                 ++j;
-                bytes += static_cast<u64>(T[j]) * V * esz;
+                bytes += static_cast<u64>(T[j]) * V * esz_in;
             }
-            CUDA_OK(cudaMemcpyAsync(d->d_logits.as<char>() + frame_off[i] * V * esz, logits[i], bytes,
+            CUDA_OK(cudaMemcpyAsync(dst + frame_off[i] * V * esz_in, logits[i], bytes,
                                     is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
             if (!is_device) d->tm.h2d_bytes += static_cast<long long>(bytes);
             i = j + 1;
+        }
+        if (half_in && total_frames > 0) {
+            const u64 n_el = total_frames * static_cast<u64>(V);
+#ifndef B2C_HOSTSIM
+            const int blocks = static_cast<int>(std::min<u64>((n_el + 255) / 256, static_cast<u64>(d->n_sm) * 16));
+            b2c_widen_kernel<<<blocks, 256, 0, st>>>(static_cast<const u16*>(packed_half), d->d_logits.as<float>(), n_el,
+                                                     dtype_in == B2C_DTYPE_BF16 ? 1 : 0);
+            CUDA_OK(cudaGetLastError());
+#else
+            b2c_widen_range(static_cast<const u16*>(packed_half), d->d_logits.as<float>(), 0, n_el, 1, dtype_in == B2C_DTYPE_BF16 ? 1 : 0);
+#endif
+            d->tm.launches += 1;
         }
     }
     CUDA_OK(cudaMemcpyAsync(d->d_hot.p, hot.data(), hot.size() * sizeof(B2cHot), cudaMemcpyHostToDevice, st));

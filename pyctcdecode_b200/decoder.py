@@ -110,20 +110,20 @@ def _default_device() -> int:
 
 
 def _as_matrix(logits: Any) -> Tuple[Any, int, int, int, bool]:
-    """-> (owner, address, T, dtype_code, is_device).  float32/float64 are passed through, integer
-    inputs are computed in float64 like numpy would, half precision is widened to float32."""
+    """-> (owner, address, T, dtype_code, is_device).  float32/float64 are passed through, integer inputs are
+    computed in float64 like numpy would, float16 / bfloat16 travel as they are (dtype codes 2 / 3) and are widened
+    to float32 on the device."""
     if hasattr(logits, "is_cuda") and hasattr(logits, "data_ptr"):  # torch tensor
         t = logits
         if t.dim() != 2:
             raise ValueError("Input logits have %s dimensions, but need 2: (time, vocabulary)" % t.dim())
         import torch
 
-        if t.dtype not in (torch.float32, torch.float64):
+        codes = {torch.float32: 0, torch.float64: 1, torch.float16: 2, torch.bfloat16: 3}
+        if t.dtype not in codes:
             t = t.to(torch.float64 if not t.dtype.is_floating_point else torch.float32)
         t = t.contiguous()
-        if t.is_cuda:
-            return t, t.data_ptr(), t.shape[0], 0 if t.dtype == torch.float32 else 1, True
-        return t, t.data_ptr(), t.shape[0], 0 if t.dtype == torch.float32 else 1, False
+        return t, t.data_ptr(), t.shape[0], codes[t.dtype], bool(t.is_cuda)
     arr = np.asarray(logits)
     if arr.ndim != 2:
         raise ValueError("Input logits have %s dimensions, but need 2: (time, vocabulary)" % arr.ndim)
@@ -131,8 +131,8 @@ def _as_matrix(logits: Any) -> Tuple[Any, int, int, int, bool]:
         arr = np.ascontiguousarray(arr)
         code = 0
     elif arr.dtype == np.float16:
-        arr = np.ascontiguousarray(arr, dtype=np.float32)
-        code = 0
+        arr = np.ascontiguousarray(arr)
+        code = 2
     else:
         arr = np.ascontiguousarray(arr, dtype=np.float64)
         code = 1
@@ -247,21 +247,20 @@ class BeamSearchDecoderCTC:
             t = logits_list
             if t.dim() != 3:
                 return None
-            if t.dtype in (torch.float16, torch.bfloat16):
-                t = t.float()           # widened on the device the tensor lives on (no host round trip)
-            if t.dtype not in (torch.float32, torch.float64):
+            codes = {torch.float32: 0, torch.float64: 1, torch.float16: 2, torch.bfloat16: 3}
+            if t.dtype not in codes:
                 return None
             if t.shape[2] != V:
                 raise ValueError("Input logits shape is %s, but vocabulary is size %s. Need logits of shape: "
                                  "(time, vocabulary)" % (tuple(t.shape[1:]), V))
             t = t.contiguous()
-            return t, t.data_ptr(), t.shape[0], t.shape[1], 0 if t.dtype == torch.float32 else 1, bool(t.is_cuda)
-        if isinstance(logits_list, np.ndarray) and logits_list.ndim == 3 and logits_list.dtype in (np.float32, np.float64):
+            return t, t.data_ptr(), t.shape[0], t.shape[1], codes[t.dtype], bool(t.is_cuda)
+        if isinstance(logits_list, np.ndarray) and logits_list.ndim == 3 and logits_list.dtype in (np.float32, np.float64, np.float16):
             if logits_list.shape[2] != V:
                 raise ValueError("Input logits shape is %s, but vocabulary is size %s. Need logits of shape: "
                                  "(time, vocabulary)" % (logits_list.shape[1:], V))
             a = np.ascontiguousarray(logits_list)
-            return a, a.ctypes.data, a.shape[0], a.shape[1], 0 if a.dtype == np.float32 else 1, False
+            return a, a.ctypes.data, a.shape[0], a.shape[1], {np.dtype(np.float32): 0, np.dtype(np.float64): 1, np.dtype(np.float16): 2}[a.dtype], False
         return None
 
     # ---- the one place that talks to the kernels ------------------------------------------
@@ -278,7 +277,7 @@ class BeamSearchDecoderCTC:
             owner, base, n, t_each, dtype_code, is_device = packed
             if n == 0:
                 return []
-            step = t_each * len(self._idx2vocab) * (4 if dtype_code == 0 else 8)
+            step = t_each * len(self._idx2vocab) * {0: 4, 1: 8, 2: 2, 3: 2}[dtype_code]
             if lengths is None:
                 mats = [(owner, base + i * step, t_each, dtype_code, is_device) for i in range(n)]
             else:
@@ -296,7 +295,8 @@ class BeamSearchDecoderCTC:
             codes = {m[3] for m in mats}
             devs = {m[4] for m in mats}
             if len(codes) > 1 or len(devs) > 1:  # mixed batch: bring everything to host float64
-                mats = [_as_matrix(np.asarray(x.cpu() if hasattr(x, "cpu") else x, dtype=np.float64)) for x in logits_list]
+                mats = [_as_matrix(x.detach().cpu().double().numpy() if hasattr(x, "cpu") else np.asarray(x, dtype=np.float64))
+                        for x in logits_list]
         dtype_code, is_device = mats[0][3], mats[0][4]
         handle = self._handle(device)
         lm = self._language_model

@@ -227,6 +227,11 @@ def test_gpu_padded_batch_lengths_and_half_precision(pkg):
         ref = dec.decode_batch(None, h.float().cpu().numpy(), beam_width=50)
         assert dec.decode_batch(None, h, beam_width=50) == ref
         assert dec.decode(h[2], beam_width=50) == ref[2]
+        assert dec.decode_batch(None, h, beam_width=50, lengths=[200, 150, 1, 0, 77, 200]) == \
+            dec.decode_batch(None, h.float(), beam_width=50, lengths=[200, 150, 1, 0, 77, 200])
+        assert dec.decode_batch(None, [t for t in h.cpu()], beam_width=50) == ref         # host tensors: 2-byte H2D
+    h16 = full.numpy().astype(np.float16)
+    assert dec.decode_batch(None, [x for x in h16], beam_width=50) == dec.decode_batch(None, h16.astype(np.float32), beam_width=50)
 
 
 @pytest.mark.parametrize("variant", ["0", "1", "2"])

@@ -294,3 +294,30 @@ assert total > 500, total
     r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, B200CTC_NO_V5="1"), stdout=subprocess.PIPE,
                        stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0, r.stdout[-3000:]
+
+
+def test_hostsim_half_precision_inputs(sim):
+    """float16 / bfloat16 logits travel as 2-byte elements (dtype codes 2 / 3) and are widened to float32 on the
+    device: the result must equal decoding the float32-widened matrix, for lists, one [B, T, V] array and torch
+    tensors; a mixed list falls back to float64 on the host."""
+    import torch
+    wl = synth.make_workload(FAMILIES["B_3gram"][0])
+    kw = dict(FAMILIES["B_3gram"][1], kenlm_model_path=wl.arpa, unigrams=wl.words)
+    dec = sim.build_ctcdecoder(wl.labels, **kw)
+    xs = [wl.utterance(8700 + i, 60, ["peaky", "diffuse"][i % 2]) for i in range(4)]
+    h16 = [x.astype(np.float16) for x in xs]
+    want16 = [_beams(dec.decode_beams(h.astype(np.float32), beam_width=16)) for h in h16]
+    assert [_beams(b) for b in dec.decode_beams_batch(None, h16, beam_width=16)] == want16
+    assert [_beams(b) for b in dec.decode_beams_batch(None, np.stack(h16), beam_width=16)] == want16
+    assert [_beams(b) for b in dec.decode_beams_batch(None, torch.from_numpy(np.stack(h16)), beam_width=16)] == want16
+    bf = [torch.from_numpy(x).to(torch.bfloat16) for x in xs]
+    wantbf = [_beams(dec.decode_beams(t.float().numpy(), beam_width=16)) for t in bf]
+    assert [_beams(b) for b in dec.decode_beams_batch(None, bf, beam_width=16)] == wantbf
+    assert [_beams(b) for b in dec.decode_beams_batch(None, torch.stack(bf), beam_width=16)] == wantbf
+    mixed = dec.decode_batch(None, [bf[0], xs[1]], beam_width=16)
+    assert mixed[1] == dec.decode(xs[1], beam_width=16)
+    # subnormal, zero, inf and NaN bit patterns convert like numpy does
+    special = np.array([[0.0, -0.0, 6e-8, -6.1e-5, 65504.0, np.inf, -np.inf, 1.0]] * 2, dtype=np.float16)
+    lab = ["a", "b", "c", "d", "e", "f", "g", ""]
+    d2 = sim.build_ctcdecoder(lab)
+    assert _beams(d2.decode_beams(special)) == _beams(d2.decode_beams(special.astype(np.float32)))
