@@ -215,6 +215,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="utterances per GPU (default: the workload's)")
     ap.add_argument("--beam", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--logits-dtype", default="f32", choices=["f32", "f16"],
+                    help="dtype of the model output handed to decode_batch (f16: 2-byte elements over PCIe, widened on the device)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -291,7 +293,12 @@ def main():
         dec = pkg.build_ctcdecoder(wl.labels, device=local_rank, **kw)
 
     xs = wl.batch(1 + rank * 100_000, B, T, args.regime)   # every rank its own utterances (weak scaling)
-    host = torch.from_numpy(np.stack(xs)).pin_memory()
+    if args.logits_dtype == "f16":                        # the model emitted half precision: both arms see those values
+        xs16 = [x.astype(np.float16) for x in xs]
+        xs = [x.astype(np.float32) for x in xs16]
+        host = torch.from_numpy(np.stack(xs16)).pin_memory()
+    else:
+        host = torch.from_numpy(np.stack(xs)).pin_memory()
     dev = host.cuda(non_blocking=False)
     frames_per_step = B * T
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
@@ -366,7 +373,7 @@ def main():
         "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": spec["name"], "regime": args.regime, "beam_width": beam, "batch_per_gpu": B, "T": T, "V": wl.V,
-                   "logits_dtype": "f32", "l2": "flushed between timed steps (512 MiB write)", "parallelism": "utterance-sharded x%d" % world},
+                   "logits_dtype": args.logits_dtype, "l2": "flushed between timed steps (512 MiB write)", "parallelism": "utterance-sharded x%d" % world},
         "roofline": {"bound": "hbm", "kernel": "b2c_beam_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                      "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6.65 TB/s (of fallback)",
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": ms_beam,
