@@ -358,7 +358,7 @@ def main():
     except OSError:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    esz = 4
+    esz = 2 if args.logits_dtype == "f16" else 4      # algorithmic bytes per logit: the dtype the rows arrive in
     alg_bytes = frames_per_step * wl.V * esz
     traffic = None
     try:
