@@ -839,12 +839,14 @@ B2C_HD void b2c_frame_step(const B2cParams& P, B2cWork& W, int t, const u16* tk_
 // rounding could change (order, threshold) is re-checked; on failure the state is untouched and the caller runs the
 // general step.  No table swap; leaves the tables clear for the next frame like phase D does.
 // -----------------------------------------------------------------------------------------
-enum { B2C_INPLACE_NO = 0, B2C_INPLACE_T0 = 1, B2C_INPLACE_T3 = 2 };
+enum { B2C_INPLACE_NO = 0, B2C_INPLACE_T0 = 1, B2C_INPLACE_T3 = 2, B2C_INPLACE_T3P = 3 };
 B2C_HD int b2c_inplace_kind(u32 flags, u32 prev_single, u16 tok_flags, u16 tok_canon) {
     if (prev_single == B2C_NONE_U32) return B2C_INPLACE_NO;
     if ((tok_flags & B2C_TF_BLANK) || prev_single == tok_canon) return B2C_INPLACE_T0;
-    if (!(flags & (B2C_FL_PSCORE | B2C_FL_BPE)) && !(tok_flags & B2C_TF_SPACE)) return B2C_INPLACE_T3;
-    return B2C_INPLACE_NO;
+    if ((flags & B2C_FL_BPE) || (tok_flags & B2C_TF_SPACE)) return B2C_INPLACE_NO;
+    // an ordinary character; with LM / hotwords (T3P) the new per-beam scores are computed first and the frame is
+    // in place only if they stay in order and above the threshold (same as b2c_fast_scored_step)
+    return (flags & B2C_FL_PSCORE) ? B2C_INPLACE_T3P : B2C_INPLACE_T3;
 }
 B2C_HDN bool b2c_inplace_step(B2cParams P, B2cWork W, int t, int kind, u16 tok_id, double p, int K_next) {
     B2cScalars* sc = W.sc;
@@ -853,10 +855,32 @@ B2C_HDN bool b2c_inplace_step(B2cParams P, B2cWork W, int t, int kind, u16 tok_i
     const bool has_lm = (flags & B2C_FL_LM) != 0, plain = (flags & B2C_FL_PSCORE) == 0;
     const B2cBeamTab cur = W.cur;
     const B2cTok ti = P.toks[tok_id];
-    const double top = plain ? (cur.logit[0] + p) + 0.0
-                             : b2c_combine_score(has_lm, cur.logit[0] + p, cur.lm_hw[0], cur.pscore[0], cur.part_len[0]);
+    const bool scored = kind == B2C_INPLACE_T3P;
+    const B2cCandTier Cs = b2c_pick_tier(W, n);        // scratch of the scored form: new lm_score, new partial score
+    if (scored) {
+        B2C_FOR(b, n) {
+            const u64 nph = b2c_hash_append(cur.part_hash[b], ti.raw_hash, ti.raw_pow);
+            const u32 nplen = (static_cast<u32>(cur.part_len[b]) + ti.raw_nchars) & 0xFFFFu;
+            const double ps = b2c_partial_score_of(P, true, nph, nplen);
+            union { double d; u64 u; } c;
+            c.d = ps;
+            Cs.ckey[b] = c.u;
+            Cs.cfold[b] = b2c_combine_score(has_lm, cur.logit[b] + p, cur.lm_hw[b], ps, nplen);
+        }
+        B2C_SYNC();
+    }
+    const double top = scored ? Cs.cfold[0]
+                              : (plain ? (cur.logit[0] + p) + 0.0
+                                       : b2c_combine_score(has_lm, cur.logit[0] + p, cur.lm_hw[0], cur.pscore[0], cur.part_len[0]));
     const double thr = top + P.prune_logp;
     B2C_FOR(b, n) {
+        if (scored) {
+            const double mine = Cs.cfold[b];
+            bool ok = mine >= thr;
+            if (static_cast<u32>(b) + 1 < n) ok = ok && mine >= Cs.cfold[b + 1];
+            if (!ok) sc->inplace_bad = 1;
+            continue;
+        }
         if (plain) {      // order is preserved by monotone rounding; only the threshold needs the check
             if (!((cur.logit[b] + p) + 0.0 >= thr)) sc->inplace_bad = 1;
             continue;
@@ -886,6 +910,11 @@ B2C_HDN bool b2c_inplace_step(B2cParams P, B2cWork W, int t, int kind, u16 tok_i
             const int ps0 = cur.pf_s[b], pe0 = cur.pf_e[b];
             cur.part_hash[b] = b2c_hash_append(cur.part_hash[b], ti.raw_hash, ti.raw_pow);
             cur.part_len[b] = static_cast<u16>(cur.part_len[b] + ti.raw_nchars);
+            if (scored) {
+                union { double d; u64 u; } c;
+                c.u = Cs.ckey[b];
+                cur.pscore[b] = c.d;
+            }
             if (ps0 < 0) cur.pf_s[b] = t;
             cur.pf_e[b] = t + 1;
             const u32 id = b2c_atomic_add_u32(&sc->chain_used, 1u);

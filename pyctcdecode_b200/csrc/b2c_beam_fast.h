@@ -511,12 +511,15 @@ B2C_HD void b2c_fast_step(const B2cParams& P, B2cFastSmem<WC, CAP>& S, B2cChain*
 // the scores are still non-increasing in slot (= rank) order and all above max + beam_prune_logp; otherwise
 // the general step runs on the untouched state.  One vote barrier, no table swap, no grouping, no ranking.
 // -----------------------------------------------------------------------------------------
-enum { B2C_CHEAP_NO = 0, B2C_CHEAP_T0 = 1, B2C_CHEAP_T3 = 2 };
+enum { B2C_CHEAP_NO = 0, B2C_CHEAP_T0 = 1, B2C_CHEAP_T3 = 2, B2C_CHEAP_T3P = 3 };
 B2C_HD int b2c_fast_cheap_kind(u32 flags, u32 prev_single, const B2cTok& ti) {
     if (prev_single == B2C_NONE_U32) return B2C_CHEAP_NO;
     if ((ti.flags & B2C_TF_BLANK) || prev_single == ti.canon) return B2C_CHEAP_T0;
-    if (!(flags & (B2C_FL_PSCORE | B2C_FL_BPE)) && !(ti.flags & B2C_TF_SPACE)) return B2C_CHEAP_T3;
-    return B2C_CHEAP_NO;
+    if ((flags & B2C_FL_BPE) || (ti.flags & B2C_TF_SPACE)) return B2C_CHEAP_NO;
+    // an ordinary character: without LM and hotwords the scores move together (T3); with them every beam's
+    // partial-word score changes, so the new scores are computed and the frame is in place only if they
+    // still come out in slot order and above the threshold (T3P, b2c_fast_scored_step)
+    return (flags & B2C_FL_PSCORE) ? B2C_CHEAP_T3P : B2C_CHEAP_T3;
 }
 
 // returns false (state untouched) when the exactness check failed
@@ -590,6 +593,82 @@ B2C_HD bool b2c_fast_cheap_step(const B2cParams& P, B2cFastSmem<WC, CAP>& S, B2c
         }
     }
     // best score of this frame = reference point of the next frame's score buckets
+    B2C_FOR(w, B2C_FAST_NW) { S.wmax[w] = w == 0 ? b2c_f64_key(top) : 0ull; }
+    return true;
+}
+
+// -----------------------------------------------------------------------------------------
+// One ordinary character after a one-token frame WITH a language model and / or hotwords: still no merge (same
+// argument as above) and the same history-prune survivors, but lm_score = logit_score + lm_hw(text) +
+// score(partial_word + c) changes per beam (decoder.py:397-420).  Every slot computes its new partial-word score
+// and lm_score; if the scores are still non-increasing in slot order (equal scores keep their order, as the stable
+// nlargest of decoder.py:548 would) and all reach max + beam_prune_logp, the reference's result is the old beams in
+// the old order with the new fields -> in-place update.  Otherwise the state is untouched and the general step runs.
+// Scratch: S.cfold[slot] (new lm_score), S.ckey[slot] (new partial score, as bits).
+// -----------------------------------------------------------------------------------------
+template <int WC, int CAP>
+B2C_HD bool b2c_fast_scored_step(const B2cParams& P, B2cFastSmem<WC, CAP>& S, B2cChain* chain_arena, u32 chain_cap, int par, int t,
+                                 int sb) {
+    B2cFastTab<WC>& cur = S.tab[par];
+    const u32 n = b2c_max_slots(S.wtop);
+    const u32 flags = S.sc.flags;
+    const bool has_lm = (flags & B2C_FL_LM) != 0;
+    const bool holes = S.holes != 0;
+    const B2cTok ti = S.stok[sb][0];
+    const double p = S.slp[sb][0];
+    B2C_FOR(b, n) {
+        const u64 nph = b2c_hash_append(cur.part_hash[b], ti.raw_hash, ti.raw_pow);
+        const u32 nplen = static_cast<u32>(cur.part_len[b]) + ti.raw_nchars;
+        const double ps = b2c_partial_score_of(P, true, nph, nplen & 0xFFFFu);
+        union { double d; u64 u; } c;
+        c.d = ps;
+        S.ckey[b] = c.u;
+        S.cfold[b] = b2c_combine_score(has_lm, cur.logit[b] + p, cur.lm_hw[b], ps, nplen & 0xFFFFu);
+    }
+    B2C_SYNC();
+    const double top = S.cfold[0];
+    const double thr = top + P.prune_logp;
+    B2C_FOR(b, n) {
+        const double mine = S.cfold[b];
+        bool ok = mine >= thr;
+        if (static_cast<u32>(b) + 1 < n) ok = ok && mine >= S.cfold[b + 1];
+        if (!ok) S.cheap_bad = 1;
+    }
+    B2C_SYNC();
+    if (S.cheap_bad) {      // block-uniform
+        B2C_SYNC();
+        B2C_LEADER { S.cheap_bad = 0; }
+        return false;
+    }
+    B2C_FOR(b, n) {
+        cur.logit[b] = cur.logit[b] + p;
+        union { double d; u64 u; } c;
+        c.u = S.ckey[b];
+        // dead slots keep their place in the score order: logit and partial-word fields follow, no backtrack node
+        const int ps0 = cur.pf_s[b], pe0 = cur.pf_e[b];
+        cur.part_hash[b] = b2c_hash_append(cur.part_hash[b], ti.raw_hash, ti.raw_pow);
+        cur.part_len[b] = static_cast<u16>(cur.part_len[b] + ti.raw_nchars);
+        cur.pscore[b] = c.d;
+        cur.last_tok[b] = ti.canon;
+        if (ps0 < 0) cur.pf_s[b] = t;
+        cur.pf_e[b] = t + 1;
+        const bool live = !holes || S.pt_min[S.pslot[b]] == static_cast<u32>(b);
+        if (!live) continue;
+        const u32 id = b2c_atomic_add_u32(&S.sc.chain_used, 1u);
+        if (id < chain_cap) {
+            B2cChain cn;
+            cn.parent = cur.chain[b];
+            cn.tok = S.sid[sb][0];
+            cn.kind = B2C_CK_CONT;
+            cn.has_word = 0;
+            cn.ws = ps0;
+            cn.we = pe0;
+            chain_arena[id] = cn;
+            cur.chain[b] = id;
+        } else {
+            b2c_atomic_or_u32(&S.sc.status, B2C_ERR_CHAIN_FULL);
+        }
+    }
     B2C_FOR(w, B2C_FAST_NW) { S.wmax[w] = w == 0 ? b2c_f64_key(top) : 0ull; }
     return true;
 }
@@ -1008,7 +1087,8 @@ B2C_HD void b2c_beam_block_fast(const B2cBeamArgs& A, int slot, u8* smem) {
                 bool done = false;          // the frame was handled by one of the two special steps
                 if (K == 1 && prev_single != B2C_NONE_U32) {
                     const int kind = b2c_fast_cheap_kind(S.sc.flags, prev_single, S.stok[sb][0]);
-                    if (kind != B2C_CHEAP_NO) in_place = b2c_fast_cheap_step<WC, CAP>(A.P, S, chain_arena, chain_cap, par, t, sb, kind);
+                    if (kind == B2C_CHEAP_T3P) in_place = b2c_fast_scored_step<WC, CAP>(A.P, S, chain_arena, chain_cap, par, t, sb);
+                    else if (kind != B2C_CHEAP_NO) in_place = b2c_fast_cheap_step<WC, CAP>(A.P, S, chain_arena, chain_cap, par, t, sb, kind);
                     B2C_LAST_THREAD { st_inplace += in_place ? 1u : 0u; }
                     done = in_place;
                     if (in_place) B2C_FMARK(5);

@@ -292,3 +292,26 @@ def test_gpu_streaming_batch_equals_whole(pkg):
 def test_gpu_multi_language_model_matches_reference_golden(pkg, name):
     """MultiLanguageModel on the device against the unmodified reference (tests/golden/multilm_cases.json)."""
     assert goldens.run_multilm_case(pkg, name) == ""
+
+
+@pytest.mark.parametrize("fam", ["3gram", "5gram"])
+def test_gpu_scored_in_place_frames_with_lm(pkg, orc, fam):
+    """b2c_fast_scored_step / the scored form of b2c_inplace_step on the device against the oracle (LM + hotwords)."""
+    wkw, lmkw = {"3gram": (dict(kind="char", vocab="B", n_words=400, lm_order=3), dict(alpha=0.5, beta=1.0)),
+                 "5gram": (dict(kind="char", vocab="B", n_words=150, lm_order=5), dict(alpha=0.9, beta=0.3, unk_score_offset=-4.0))}[fam]
+    wl = synth.make_workload(wkw)
+    kw = dict(lmkw, kenlm_model_path=wl.arpa, unigrams=wl.words)
+    dec = pkg.build_ctcdecoder(wl.labels, **kw)
+    ora = orc.OracleDecoder(wl.labels, **kw)
+    inplace = frames = 0
+    for i, (x, dkw) in enumerate(synth.special_step_cases(wl, n_cases=40, seed=11)):
+        if i % 4 == 1:
+            dkw = dict(dkw, hotwords=[wl.words[2], wl.words[7] + " " + wl.words[9]], hotword_weight=7.5)
+        if i % 5 == 3:
+            dkw = dict(dkw, beam_width=300)          # general kernel
+        got = _beams(dec.decode_beams(x, **dkw))
+        tm = dec.last_timings()
+        inplace += tm["inplace_frames"]
+        frames += tm["frames"]
+        _compare(ora.decode_beams(x, **dkw), got)
+    assert inplace > 0.4 * frames, (inplace, frames)

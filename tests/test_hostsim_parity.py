@@ -321,3 +321,24 @@ def test_hostsim_half_precision_inputs(sim):
     lab = ["a", "b", "c", "d", "e", "f", "g", ""]
     d2 = sim.build_ctcdecoder(lab)
     assert _beams(d2.decode_beams(special)) == _beams(d2.decode_beams(special.astype(np.float32)))
+
+
+@pytest.mark.parametrize("fam", ["B_3gram", "B_5gram", "A_2gram"])
+def test_hostsim_scored_in_place_frames_with_lm(sim, fam):
+    """b2c_fast_scored_step: one ordinary character after a one-token frame WITH an LM / hotwords (new partial-word
+    scores per beam; in place only if the new lm_scores keep slot order and threshold) against the oracle."""
+    wkw, lmkw = FAMILIES[fam]
+    wl = synth.make_workload(wkw)
+    kw = dict(lmkw, kenlm_model_path=wl.arpa, unigrams=wl.words)
+    dec = sim.build_ctcdecoder(wl.labels, **kw)
+    ora = orc.OracleDecoder(wl.labels, **kw)
+    inplace = frames = 0
+    for i, (x, dkw) in enumerate(synth.special_step_cases(wl, n_cases=24, seed=11)):
+        if i % 4 == 1:
+            dkw = dict(dkw, hotwords=[wl.words[2], wl.words[7] + " " + wl.words[9]], hotword_weight=7.5)
+        got = _beams(dec.decode_beams(x, **dkw))
+        tm = dec.last_timings()
+        inplace += tm["inplace_frames"]
+        frames += tm["frames"]
+        _compare(ora.decode_beams(x, **dkw), got)
+    assert inplace > 0.4 * frames, (inplace, frames)
