@@ -19,10 +19,12 @@
 // Frames with more than CAP candidates (or more than B2C_FAST_KS tokens) are rare on ASR-like
 // posteriors; they take the general out-of-line step on the HBM candidate tier (b2c_fast_slow_step).
 //
-// Three kinds of frame steps, chosen per frame from block-uniform facts (token count, the previous frame's
+// Four kinds of frame steps, chosen per frame from block-uniform facts (token count, the previous frame's
 // token, mode flags):
 //   b2c_fast_cheap_step   one token after a one-token frame (same token / blank / plain character without LM and
 //                         hotwords): nothing can merge, reorder or be pruned -> the table is updated in place
+//   b2c_fast_scored_step  the same with LM / hotwords and an ordinary character: new per-beam scores first, in place
+//                         only if they keep slot order and threshold
 //   b2c_fast_sorted_step  K >= 2 tokens after a one-token frame, no LM / hotwords / space: the candidates are K
 //                         sorted lists that cannot merge -> ranks by search, one commit per thread
 //   b2c_fast_step         everything else: expand + group | fold + fuse + bucket | threshold + rank + commit
