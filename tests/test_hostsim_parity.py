@@ -342,3 +342,13 @@ def test_hostsim_scored_in_place_frames_with_lm(sim, fam):
         frames += tm["frames"]
         _compare(ora.decode_beams(x, **dkw), got)
     assert inplace > 0.4 * frames, (inplace, frames)
+
+
+def test_hostsim_quickstart_example_runs(sim, capsys):
+    """examples/quickstart.py (the reference README's usage patterns) runs end to end on the simulated kernels."""
+    import runpy
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "quickstart.py")
+    mod = runpy.run_path(path)
+    assert isinstance(mod["main"](), str)
+    out = capsys.readouterr().out
+    assert "decode_batch" in out and "after frame" in out
