@@ -60,7 +60,8 @@ def main():
         regime = ["peaky", "peaky", "diffuse", "flat"][int(rng.integers(4))] if wl.V <= 64 else ["peaky", "diffuse"][int(rng.integers(2))]
         x = wl.utterance(int(rng.integers(1 << 30)), T, regime)
         x = (x * float(rng.choice([0.6, 0.8, 1.0, 1.0, 1.3]))).astype(np.float32)
-        if rng.random() < 0.15:
+        rounded = rng.random() < 0.15
+        if rounded:
             x = np.round(x).astype(np.float32)
         if rng.random() < 0.1:
             x = x.astype(np.float64)
@@ -79,7 +80,9 @@ def main():
         # chunked streaming must end in the same beams -- for regular alphabets; with BPE the reference itself resets its
         # force_next_break flag at every call, so its chunked and whole results differ (checked against the reference:
         # the product reproduces the reference's CHUNKED result, tests/golden/stream_cases.json)
-        if ok and T > 4 and wl.V <= 64 and rng.random() < 0.4:
+        # ... and not for integer-valued logits: the reference decides "probabilities or logits" per CALL from the mean of
+        # the row sums (decoder.py:702), which can be exactly 1 for a chunk of integer rows and not for the whole matrix
+        if ok and T > 4 and wl.V <= 64 and not rounded and rng.random() < 0.4:
             cuts = sorted(set(int(c) for c in rng.integers(1, T, size=int(rng.integers(1, 4)))))
             beams, cache, pcache = dec.get_starting_state()
             start = 0
@@ -91,7 +94,12 @@ def main():
             ok = len(beams) == len(ref) and all(b.text == r[0] and [tuple(f) for f in b.text_frames] == [tuple(f) for _, f in r[1]]
                                                 and abs(b.lm_score - r[3]) <= 1e-9 * max(1.0, abs(r[3])) for b, r in zip(beams, ref))
             if not ok:
-                print("STREAM", end=" ")
+                print("STREAM cuts %r" % (cuts,), end=" ")
+                if os.environ.get("FUZZ_DUMP"):
+                    import json
+                    np.save(os.path.join(os.environ["FUZZ_DUMP"], "case%d_seed%d.npy" % (case, seed)), x)
+                    with open(os.path.join(os.environ["FUZZ_DUMP"], "case%d_seed%d.json" % (case, seed)), "w") as fh:
+                        json.dump({"fam": fam, "kw": kw, "cuts": cuts}, fh)
         if not ok:
             bad += 1
             print("MISMATCH case %d fam %s T=%d regime %s %r variant %d" % (case, fam, T, regime, kw, tm["kernel_variant"]), flush=True)
