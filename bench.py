@@ -379,7 +379,14 @@ def main():
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": ms_beam,
                      "note": "the beam kernel is a T-step serial chain per utterance (latency bound); the streaming stage is reported under roofline_prepare"},
         "roofline_prepare": {"bound": "hbm", "kernel": "b2c_prepare_kernel", "achieved": ach_prep, "peak": peak, "unit": "GB/s",
-                             "frac": (ach_prep / peak) if ach_prep else None, "kernel_ms": ms_prep},
+                             "frac": (ach_prep / peak) if ach_prep else None, "kernel_ms": ms_prep,
+                             # what really bounds the streaming stage at V <= 32: instruction issue (float64 exp of every logit,
+                             # DESIGN.md section 4).  352 warp instructions per 32-element row is the ncu count of the C2 launch
+                             # (profiles/ncu_r01_c2_final_summary.json: 90 M per 256 000 rows); peak = SMs x 4 schedulers x clock
+                             "issue": ({"warp_instructions_per_row_ncu": 352, "sm_mhz": clocks.get("sm_mhz"),
+                                        "frac_of_issue_peak": (352.0 * frames_per_step / (ms_prep * 1e-3)) /
+                                                              (148 * 4 * clocks["sm_mhz"] * 1e6)}
+                                       if wl.V <= 32 and ms_prep > 0 and clocks and clocks.get("sm_mhz") else None)},
         "e2e": {"value": world * frames_per_step * args.steps / e2e_total, "unit": "frames/s",
                 "h2d_bytes_per_step": int(e2e_tms[-1]["h2d_bytes"]), "d2h_bytes_per_step": int(e2e_tms[-1]["d2h_bytes"]),
                 "ms_per_step": 1e3 * e2e_total / args.steps},
