@@ -11,9 +11,13 @@
  * negative B2C_E_* code (b2c_last_error() gives the message for the calling thread); the
  * library owns every object it returns until the matching *_free/_destroy; inputs stay
  * caller-owned and are never modified (reference decoder.py:762-765 allocates instead of
- * mutating); calls are synchronous and use the decoder's own CUDA stream; a decoder handle
- * may be used from one thread at a time.  There is no CPU fallback: without a CUDA device
- * b2c_decoder_create fails with B2C_E_CUDA.
+ * mutating); calls are synchronous and use the decoder's own CUDA stream; any number of threads
+ * may call b2c_decode_batch on one handle -- the calls are serialised by a mutex inside the handle
+ * (results are independent objects).  Parameter setters (b2c_decoder_set_params*) are plain stores:
+ * a caller that changes parameters between calls from several threads serialises setter + decode
+ * itself (the Python layer does).  Device-resident logits written on another stream than the
+ * legacy default stream: call b2c_decoder_wait_stream first.  There is no CPU fallback: without a
+ * CUDA device b2c_decoder_create fails with B2C_E_CUDA.
  */
 #ifndef B200CTC_H
 #define B200CTC_H
@@ -51,7 +55,8 @@ int b2c_device_count(void);
  * (decoder.py:1074-1096, language_model.py:87-103, :237-269).  `unigrams` NULL or
  * n_unigrams < 0 means "no unigram list" (LanguageModel(unigrams=None)). ARPA text only. */
 int b2c_lm_build_from_arpa(const char* arpa_path, const char* const* unigrams, long n_unigrams, b2c_lm_t** out);
-/* the relocatable blob (for a NCCL broadcast) and its reconstruction on another rank */
+/* the relocatable blob (for a NCCL broadcast) and its reconstruction on another rank; from_blob validates every
+ * offset, mask and id of the header against `size` before use */
 int b2c_lm_blob(const b2c_lm_t* lm, const void** data, size_t* size);
 int b2c_lm_from_blob(const void* data, size_t size, b2c_lm_t** out);
 /* make the model resident on `device` by cudaMemcpy, or adopt a device copy that already
@@ -65,6 +70,8 @@ int b2c_lm_order(const b2c_lm_t* lm);
 int b2c_lm_contains(const b2c_lm_t* lm, const char* word);
 int b2c_lm_in_unigrams(const b2c_lm_t* lm, const char* word);
 int b2c_lm_has_prefix(const b2c_lm_t* lm, const char* prefix);
+/* 1 when the model was built with a unigram list (LanguageModel(unigrams=...) not None) */
+int b2c_lm_have_unigrams(const b2c_lm_t* lm);
 /* state: `words` most recent first; BaseScore writes the out state and returns log10 p */
 typedef struct { uint32_t words[5]; float backoff[5]; uint32_t length; } b2c_lm_state_t;
 void b2c_lm_begin_sentence(const b2c_lm_t* lm, b2c_lm_state_t* st);
@@ -79,6 +86,11 @@ float b2c_lm_base_score(const b2c_lm_t* lm, const b2c_lm_state_t* in, const char
 int b2c_decoder_create(const char* const* labels, int n_labels, int is_bpe, b2c_lm_t* lm, int device,
                        b2c_decoder_t** out);
 void b2c_decoder_destroy(b2c_decoder_t* dec);
+/* the CUDA device the decoder was created on */
+int b2c_decoder_device(const b2c_decoder_t* dec);
+/* order the next decode call after everything `cuda_stream` (a cudaStream_t, e.g. torch's current stream) holds now:
+ * needed when device-resident logits were produced on a stream other than the legacy default stream */
+int b2c_decoder_wait_stream(b2c_decoder_t* dec, void* cuda_stream);
 /* LanguageModel.reset_params (language_model.py:271-301): plain scalars handed to the kernels */
 int b2c_decoder_set_params(b2c_decoder_t* dec, double alpha, double beta, double unk_score_offset,
                            int lm_score_boundary);
@@ -162,9 +174,12 @@ int b2c_result_lm_state(const b2c_result_t* res, int utt, int beam, b2c_lm_state
 int b2c_result_lm_state_at(const b2c_result_t* res, int utt, int beam, int lm_index, b2c_lm_state_t* out);
 /* streaming calls (opts->stream_states != NULL): what the call appended to an input beam instead of assembled
  * strings.  aux = {input beam index (-1: none), token id of last_char (-1: None), partial_frames start, end};
- * toks = the emitted tokens since the input beam, oldest first, token | kind << 16 with kind 0 = appended to the
- * partial word, 1 = BPE piece that starts a word, 2 = space; b2c_result_frames / b2c_result_n_frames give the frames
+ * toks = the emitted tokens since the input beam, oldest first, token | kind << 16 with kind B2C_KIND_CONT = appended
+ * to the partial word, B2C_KIND_SPACE = the word separator, B2C_KIND_BPE = BPE piece that starts a word; b2c_result_frames / b2c_result_n_frames give the frames
  * of the words finished during the call (LMBeam, decoder.py:97-100; the host replays them onto the input beam). */
+#define B2C_KIND_CONT 0
+#define B2C_KIND_SPACE 1
+#define B2C_KIND_BPE 2
 int b2c_result_stream_beam(const b2c_result_t* res, int utt, int beam, int32_t aux[4], const uint32_t** toks, int* n_toks);
 int b2c_result_n_frames(const b2c_result_t* res, int utt, int beam);
 /* string -> (hash, code points) as the kernels identify words and partial words; label -> canonical token id

@@ -3,8 +3,14 @@
 Differential check of the C++ oracle (oracle/ctc_oracle.cpp) against the UNMODIFIED reference
 imported from /root/reference with the stand-ins in oracle/refshim.  Run:
     python oracle/check_vs_reference.py [n_random]
-Prints one line per case family and exits non-zero on any transcript / frame mismatch that is
-not a documented near-tie.
+Prints one line per case family and exits non-zero on any mismatch that is neither
+  (a) a permutation inside a group of beams the reference itself separates by <= `tie` in lm_score
+      (tests/goldens.py beams_match_tie_aware: the same beams -- text and word frames -- with scores within
+      tolerance, same order between beams that are not tied; tie = 1e-9 for float64 input, 4e-6 for float32 input,
+      where numpy's float32 log-softmax adds ~1e-7 of noise per frame to mathematically equal scores), nor
+  (b) a case the UNMODIFIED REFERENCE ITSELF decides by rounding noise: re-run on the input perturbed by
+      1e-13 * N(0,1) it returns different outcomes, and the oracle's output lies inside that family (same beam
+      set, every beam's scores among those the family gives it, list sorted) -- oracle/gen_golden_unstable.py.
 """
 import json
 import os
@@ -25,12 +31,37 @@ logging.disable(logging.CRITICAL)
 from pyctcdecode import build_ctcdecoder  # noqa: E402  (the reference)
 
 from oracle import oracle as orc  # noqa: E402
-from tests import synth  # noqa: E402
+from tests import goldens, synth  # noqa: E402
 
 SCORE_TOL = 2e-4  # numpy evaluates log-softmax in float32 with its own SIMD exp/log; see DESIGN.md
 
 
-def compare(ref_beams, orc_beams, tag, stats):
+def reference_unstable(ref_dec, x, dkw, orc_beams, n=16, eps=1e-13):
+    """(b) of the module docstring -> (number of distinct outcomes of the reference, '' or why the oracle is outside)"""
+    if x.dtype == np.float32:
+        return 1, "float32 input: no sub-ulp perturbation"
+    x = x.astype(np.float64)        # integer / float64 input: the reference computes in float64
+    from oracle import gen_golden_unstable as gu
+    beams, n_out, same_set = gu.reference_family(ref_dec, x, dkw, n=n, eps=eps)
+    if n_out < 2:
+        return n_out, "the reference is stable under the perturbation"
+    if not same_set:
+        return n_out, "reference outcomes differ in their beam sets"
+    exp = {(b["text"], tuple((w, s, t) for w, s, t in b["frames"])): b["scores"] for b in beams}
+    if len(orc_beams) != len(exp):
+        return n_out, "beam count"
+    for i, b in enumerate(orc_beams):
+        key = (b[0], tuple((w, int(f[0]), int(f[1])) for w, f in b[1]))
+        if key not in exp:
+            return n_out, "beam %d not in the reference's set" % i
+        if not any(abs(p[0] - b[2]) <= SCORE_TOL and abs(p[1] - b[3]) <= SCORE_TOL for p in exp[key]):
+            return n_out, "beam %d score outside the family" % i
+        if i and orc_beams[i - 1][3] < b[3] - 1e-9:
+            return n_out, "not sorted"
+    return n_out, ""
+
+
+def compare(ref_beams, orc_beams, tag, stats, ref_dec=None, x=None, dkw=None):
     ok = True
     if len(ref_beams) != len(orc_beams):
         ok = False
@@ -45,13 +76,21 @@ def compare(ref_beams, orc_beams, tag, stats):
                 break
     stats["n"] += 1
     if not ok:
-        # near tie?  compare as sets of (text) with score tolerance
-        rset = {b.text: b.lm_score for b in ref_beams}
-        oset = {b[0]: b[3] for b in orc_beams}
-        common = set(rset) & set(oset)
-        worst = max([abs(rset[k] - oset[k]) for k in common], default=0.0)
+        # a permutation inside tie groups?  (same beams, same scores, order free only where the reference's own
+        # scores agree to 1e-9)
+        exp = [{"text": b.text, "frames": [(w, f[0], f[1]) for w, f in b.text_frames], "logit_score": b.logit_score,
+                "lm_score": b.lm_score} for b in ref_beams]
+        tie = 4e-6 if (x is not None and x.dtype == np.float32) else 1e-9
+        why = goldens.beams_match_tie_aware(exp, orc_beams, tol=SCORE_TOL, tie=tie)
+        verdict = "tie permutation (reference scores within %g)" % tie
+        if why and ref_dec is not None:
+            n_out, outside = reference_unstable(ref_dec, x, dkw, orc_beams)
+            verdict = ("reference-unstable: %d distinct reference outcomes under 1e-13 input noise, oracle inside the family" % n_out
+                       if not outside else "HARD: %s; %s" % (why, outside))
+        elif why:
+            verdict = "HARD: " + why
         top_same = bool(ref_beams) and bool(orc_beams) and ref_beams[0].text == orc_beams[0][0]
-        stats["mismatch"].append((tag, len(ref_beams), len(orc_beams), top_same, worst))
+        stats["mismatch"].append((tag, len(ref_beams), len(orc_beams), top_same, verdict))
     return ok
 
 
@@ -95,7 +134,8 @@ def main():
             ref = build_ctcdecoder(labels, **lmkw)
             mine = orc.OracleDecoder(labels, **lmkw)
             for di, dkw in enumerate(dec_variants):
-                compare(ref.decode_beams(logits, **dkw), mine.decode_beams(logits, **dkw), "%s/lm%d/d%d" % (name, li, di), stats)
+                compare(ref.decode_beams(logits, **dkw), mine.decode_beams(logits, **dkw), "%s/lm%d/d%d" % (name, li, di), stats,
+                        ref, np.asarray(logits), dkw)
     print("fixtures: %d cases, %d mismatches" % (stats["n"], len(stats["mismatch"])))
 
     # ---- random synthetic -----------------------------------------------------------
@@ -124,13 +164,14 @@ def main():
             dkw = dict(beam_width=[100, 8, 25][i % 3], prune_history=bool(i % 2))
             if i % 4 == 3:
                 dkw.update(hotwords=[wl.words[3], wl.words[10] + " " + wl.words[11]], hotword_weight=6.0)
-            compare(ref.decode_beams(x, **dkw), mine.decode_beams(x, **dkw), "%s/%d" % (fam, i), stats)
+            compare(ref.decode_beams(x, **dkw), mine.decode_beams(x, **dkw), "%s/%d" % (fam, i), stats, ref, x, dkw)
         print("%s: %d cases, %d mismatches" % (fam, stats["n"] - n0, len(stats["mismatch"]) - m0))
 
-    hard = [m for m in stats["mismatch"] if not m[3] or m[4] > 1e-3]
+    hard = [m for m in stats["mismatch"] if not m[3] or m[4].startswith("HARD")]
     for m in stats["mismatch"]:
-        print("MISMATCH", m)
-    print("total %d cases, %d mismatches (%d hard)" % (stats["n"], len(stats["mismatch"]), len(hard)))
+        print("NOT-IDENTICAL", m)
+    print("total %d cases, %d identical, %d explained (tie order / reference-unstable), %d hard" %
+          (stats["n"], stats["n"] - len(stats["mismatch"]), len(stats["mismatch"]) - len(hard), len(hard)))
     return 1 if hard else 0
 
 

@@ -88,6 +88,7 @@ def _declare(L):
     L.b2c_lm_contains.argtypes = [vp, cp]
     L.b2c_lm_in_unigrams.argtypes = [vp, cp]
     L.b2c_lm_has_prefix.argtypes = [vp, cp]
+    L.b2c_lm_have_unigrams.argtypes = [vp]
     L.b2c_lm_begin_sentence.argtypes = [vp, C.POINTER(LMState)]
     L.b2c_lm_begin_sentence.restype = None
     L.b2c_lm_null_context.argtypes = [vp, C.POINTER(LMState)]
@@ -98,6 +99,8 @@ def _declare(L):
     L.b2c_decoder_destroy.argtypes = [vp]
     L.b2c_decoder_destroy.restype = None
     L.b2c_decoder_set_params.argtypes = [vp, f64, f64, f64, i32]
+    L.b2c_decoder_device.argtypes = [vp]
+    L.b2c_decoder_wait_stream.argtypes = [vp, vp]
     L.b2c_decode_opts_default.argtypes = [C.POINTER(DecodeOpts)]
     L.b2c_decode_opts_default.restype = None
     L.b2c_decode_batch.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_int32), i32, i32, i32, C.POINTER(DecodeOpts), pp]

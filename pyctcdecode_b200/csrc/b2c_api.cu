@@ -499,6 +499,8 @@ struct b2c_decoder {
     cudaStream_t cls_stream[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // one per capacity class
     cudaEvent_t cls_done[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t fork_ev = nullptr;
+    cudaEvent_t caller_ev = nullptr;      // b2c_decoder_wait_stream: the caller's stream at the time of the call
+    std::mutex call_mu;                   // b2c_decode_batch is serialised per handle (scratch buffers are per handle)
     b2c_timings_t tm;
     // adaptive sizing: candidate-count histogram of the previous call with the same configuration
     bool hint_valid = false;
@@ -719,15 +721,41 @@ int b2c_lm_blob(const b2c_lm_t* lm, const void** data, size_t* size) {
     *size = lm->host.blob.size();
     return 0;
 }
+// every offset, mask and id of a blob is checked before anything dereferences it: blobs come from files and from
+// other ranks
+static const char* blob_defect(const B2cLmHeader* h, size_t size) {
+    if (h->magic != B2C_LM_MAGIC) return "bad magic";
+    if (h->total_bytes != size) return "size does not match the header";
+    if (h->order < 1 || h->order > B2C_MAX_ORDER) return "n-gram order out of range";
+    if (h->n_vocab < 1 || h->bos_id >= h->n_vocab || h->eos_id >= h->n_vocab) return "vocabulary ids out of range";
+    auto pow2m1 = [](u64 m) { return m >= 15 && ((m + 1) & m) == 0; };
+    if (!pow2m1(h->ngram_mask) || !pow2m1(h->vocab_mask) || !pow2m1(h->prefix_mask)) return "table mask is not 2^k - 1";
+    auto inside = [&](u64 off, u64 count, u64 elem) {
+        return off >= sizeof(B2cLmHeader) && (off & 7) == 0 && off <= size && count <= (size - off) / elem;
+    };
+    if (!inside(h->off_uni, h->n_vocab, sizeof(B2cUni))) return "unigram array outside the blob";
+    if (!inside(h->off_ngrams, h->ngram_mask + 1, sizeof(B2cNgram))) return "n-gram table outside the blob";
+    if (!inside(h->off_vocab, h->vocab_mask + 1, sizeof(B2cVocab))) return "vocabulary table outside the blob";
+    if (!inside(h->off_prefix, h->prefix_mask + 1, sizeof(u64))) return "prefix table outside the blob";
+    if (h->have_unigrams != 0 && h->have_unigrams != 1) return "bad unigram flag";
+    if (h->n_unigrams < 0 || static_cast<u64>(h->n_unigrams) > h->n_vocab) return "bad unigram count";
+    return nullptr;
+}
 int b2c_lm_from_blob(const void* data, size_t size, b2c_lm_t** out) {
     if (!data || !out || size < sizeof(B2cLmHeader)) return fail(B2C_E_ARG, "bad blob");
-    const B2cLmHeader* h = static_cast<const B2cLmHeader*>(data);
-    if (h->magic != B2C_LM_MAGIC || h->total_bytes != size) return fail(B2C_E_ARG, "not a b200ctc LM blob");
+    B2cLmHeader h;
+    std::memcpy(&h, data, sizeof(h));
+    if (const char* why = blob_defect(&h, size)) return fail(B2C_E_ARG, std::string("not a valid b200ctc LM blob: ") + why);
     std::unique_ptr<b2c_lm> lm(new b2c_lm());
     lm->host.blob.assign(static_cast<const unsigned char*>(data), static_cast<const unsigned char*>(data) + size);
+    // vocabulary ids stored in the table must index the unigram array
+    const B2cLmView v = lm->host.view(lm->host.blob.data());
+    for (u64 s = 0; s <= v.vocab_mask; ++s)
+        if (v.vocab[s].key != 0 && v.vocab[s].id >= v.n_vocab) return fail(B2C_E_ARG, "not a valid b200ctc LM blob: vocabulary id out of range");
     *out = lm.release();
     return 0;
 }
+int b2c_lm_have_unigrams(const b2c_lm_t* lm) { return lm ? lm->host.header()->have_unigrams : 0; }
 int b2c_lm_upload(b2c_lm_t* lm, int device) {
     if (!lm) return fail(B2C_E_ARG, "null lm");
     std::lock_guard<std::mutex> lk(lm->mu);
@@ -868,6 +896,7 @@ int b2c_decoder_create(const char* const* labels, int n_labels, int is_bpe, b2c_
         CUDA_OK(cudaEventCreate(&d->cls_done[i]));
     }
     CUDA_OK(cudaEventCreate(&d->fork_ev));
+    CUDA_OK(cudaEventCreateWithFlags(&d->caller_ev, cudaEventDisableTiming));
     int v = 0;
     CUDA_OK(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device));
     d->n_sm = v;
@@ -920,8 +949,22 @@ void b2c_decoder_destroy(b2c_decoder_t* d) {
         if (d->cls_done[i]) cudaEventDestroy(d->cls_done[i]);
     }
     if (d->fork_ev) cudaEventDestroy(d->fork_ev);
+    if (d->caller_ev) cudaEventDestroy(d->caller_ev);
     if (d->stream) cudaStreamDestroy(d->stream);
     delete d;
+}
+
+int b2c_decoder_device(const b2c_decoder_t* d) { return d ? d->device : -1; }
+
+// Device-resident logits produced on another stream (e.g. torch's current stream): everything the decoder enqueues
+// from now on waits for what that stream holds at this moment.
+int b2c_decoder_wait_stream(b2c_decoder_t* d, void* cuda_stream) {
+    if (!d) return fail(B2C_E_ARG, "null decoder");
+    std::lock_guard<std::mutex> lk(d->call_mu);
+    CUDA_OK(cudaSetDevice(d->device));
+    CUDA_OK(cudaEventRecord(d->caller_ev, static_cast<cudaStream_t>(cuda_stream)));
+    CUDA_OK(cudaStreamWaitEvent(d->stream, d->caller_ev, 0));
+    return 0;
 }
 
 int b2c_decoder_set_params(b2c_decoder_t* d, double alpha, double beta, double unk, int boundary) {
@@ -953,6 +996,7 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     if (half_in) dtype = B2C_DTYPE_F32;
     if (opts->beam_width < 1) return fail(B2C_E_ARG, "beam_width must be >= 1");
     if (opts->beam_width > 65535) return fail(B2C_E_ARG, "beam_width above 65535 is not supported");
+    std::lock_guard<std::mutex> call_lock(d->call_mu);      // one call at a time per handle (any number of threads may call)
     std::unique_ptr<b2c_result> res(new b2c_result());
     res->utts.resize(n_utts);
     res->has_lm = d->lm != nullptr;

@@ -109,6 +109,13 @@ def _default_device() -> int:
     return int(os.environ.get("LOCAL_RANK", "0"))
 
 
+def _cuda_index(t: Any) -> Optional[int]:
+    """CUDA device index of a torch tensor, None for host tensors / arrays."""
+    if getattr(t, "is_cuda", False):
+        return int(t.device.index if t.device.index is not None else 0)
+    return None
+
+
 def _as_matrix(logits: Any) -> Tuple[Any, int, int, int, bool]:
     """-> (owner, address, T, dtype_code, is_device).  float32/float64 are passed through, integer inputs are
     computed in float64 like numpy would, float16 / bfloat16 travel as they are (dtype codes 2 / 3) and are widened
@@ -157,6 +164,10 @@ class BeamSearchDecoderCTC:
         self._device = device
         self._handles: Dict[int, int] = {}   # device -> b2c_decoder_t*
         self._lock = threading.Lock()
+        # decode calls on one decoder object are serialised: parameters (alpha, beta, ...) are set on the handle right
+        # before the call, and the handle's scratch buffers are per handle.  Any number of threads may call
+        # decode()/decode_batch()/... concurrently, like with the reference; they run one after another on the GPU.
+        self._run_lock = threading.RLock()
 
     # ---- life cycle ---------------------------------------------------------------------
     def reset_params(self, alpha: Optional[float] = None, beta: Optional[float] = None,
@@ -298,9 +309,37 @@ class BeamSearchDecoderCTC:
                 mats = [_as_matrix(x.detach().cpu().double().numpy() if hasattr(x, "cpu") else np.asarray(x, dtype=np.float64))
                         for x in logits_list]
         dtype_code, is_device = mats[0][3], mats[0][4]
+        # device-resident input: the decoder that runs must live on the tensors' device (raw pointers cross the ABI)
+        torch_stream = None
+        if is_device:
+            owners = {id(m[0]): m[0] for m in mats}.values()
+            where = {_cuda_index(o) for o in owners}
+            if len(where) != 1:
+                raise ValueError("logits of one call live on different CUDA devices: %s" % sorted(where))
+            (tensor_dev,) = where
+            pinned = device if device is not None else self._device
+            if pinned is not None and pinned != tensor_dev:
+                raise ValueError("logits are on cuda:%d but this decoder is bound to cuda:%d" % (tensor_dev, pinned))
+            device = tensor_dev
+            import torch
+
+            torch_stream = torch.cuda.current_stream(tensor_dev).cuda_stream
+        with self._run_lock:
+            return self._run_locked(mats, n, dtype_code, is_device, device, torch_stream, beam_width, beam_prune_logp,
+                                    token_min_logp, prune_history, hotwords, hotword_weight, max_out_beams, lm_start_states,
+                                    with_state, texts_only, stream, finalize_mode)
+
+    def _run_locked(self, mats: List[Tuple[Any, int, int, int, bool]], n: int, dtype_code: int, is_device: bool,
+                    device: Optional[int], torch_stream: Optional[int], beam_width: int, beam_prune_logp: float,
+                    token_min_logp: float, prune_history: bool, hotwords: Optional[Iterable[str]], hotword_weight: float,
+                    max_out_beams: int, lm_start_states: Optional[Sequence[Optional[AbstractLMState]]], with_state: bool,
+                    texts_only: bool, stream: Optional[Sequence[Tuple[Sequence[Beam], int]]], finalize_mode: int) -> Any:
         handle = self._handle(device)
         lm = self._language_model
         L = _lib.lib()
+        if torch_stream is not None:
+            # the logits may still be in flight on torch's current stream: the decoder's stream waits for it
+            _lib.check(L.b2c_decoder_wait_stream(handle, C.c_void_p(torch_stream)))
         models = self._lm_list()
         for idx, m in enumerate(models):
             _lib.check(L.b2c_decoder_set_params_lm(handle, idx, float(m.alpha), float(m.beta), float(m.unk_score_offset),

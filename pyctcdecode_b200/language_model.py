@@ -142,6 +142,11 @@ class NgramModel:
     def has_prefix(self, prefix: str) -> bool:
         return bool(_lib.lib().b2c_lm_has_prefix(self._h(), prefix.encode("utf-8")))
 
+    @property
+    def have_unigrams(self) -> bool:
+        """The tables carry a unigram set / prefix set (the model was built with a unigram list)."""
+        return bool(_lib.lib().b2c_lm_have_unigrams(self._h()))
+
     def BeginSentenceWrite(self, state: B200LMState) -> None:  # noqa: N802 (kenlm naming)
         st = _lib.LMState()
         _lib.lib().b2c_lm_begin_sentence(self._h(), C.byref(st))
@@ -295,9 +300,13 @@ class LanguageModel(AbstractLanguageModel):
             kenlm_model = NgramModel(os.fsdecode(kenlm_model))
         if not isinstance(kenlm_model, NgramModel):
             raise TypeError("kenlm_model must be a pyctcdecode_b200 NgramModel or an ARPA path")
-        if unigrams is None:
-            logger.warning("No known unigrams provided, decoding results might be a lot worse.")
+        self._blob_unigrams = bool(getattr(kenlm_model, "_from_blob_file", False)) and unigrams is None and kenlm_model.have_unigrams
+        if self._blob_unigrams:
+            # a saved *.b2clm blob carries the unigram / prefix sets it was built with; the word list itself is not stored
             self._unigram_list: Optional[List[str]] = None
+        elif unigrams is None:
+            logger.warning("No known unigrams provided, decoding results might be a lot worse.")
+            self._unigram_list = None
         else:
             if len(unigrams) < 1000:
                 logger.warning("Only %s unigrams passed as vocabulary. Is this small or artificial data?", len(unigrams))
@@ -348,7 +357,9 @@ class LanguageModel(AbstractLanguageModel):
         return self._kenlm_model.BaseScore(start_state, "</s>", B200LMState())
 
     def score_partial_token(self, partial_token: str) -> float:
-        if self._unigram_list is None:
+        if self._blob_unigrams:
+            is_oov = int(not self._kenlm_model.has_prefix(partial_token))
+        elif self._unigram_list is None:
             is_oov = 1.0
         else:
             is_oov = int(not self._kenlm_model.has_prefix(partial_token)) if partial_token else int(len(self._unigram_set) == 0)
@@ -362,7 +373,8 @@ class LanguageModel(AbstractLanguageModel):
             raise AssertionError("Wrong input state type found. Expected B200LMState, got %s" % type(prev_state))
         end_state = B200LMState()
         lm_score = self._kenlm_model.BaseScore(prev_state, word, end_state)
-        have_unigrams = self._unigram_list is not None and len(self._unigram_set) > 0
+        have_unigrams = (self._unigram_list is not None and len(self._unigram_set) > 0) or \
+            (self._blob_unigrams and self._kenlm_model.has_prefix(""))
         if (have_unigrams and not self._kenlm_model.in_unigrams(word)) or word not in self._kenlm_model:
             lm_score += self.unk_score_offset
         if is_last_word:
@@ -392,7 +404,7 @@ class LanguageModel(AbstractLanguageModel):
             if needed not in contents:
                 raise ValueError("did not find %s in files: %s" % (needed, contents))
             contents.remove(needed)
-        if os.path.splitext(contents[0])[1] not in {".arpa", ".bin", ".binary"}:
+        if os.path.splitext(contents[0])[1] not in {".arpa", ".bin", ".binary", NgramModel.BLOB_SUFFIX}:
             raise ValueError("Explected kenlm file to end in `.arpa` or `.bin(ary)`. Found %s" % contents[0])
         return {
             "json_attrs": os.path.join(filepath, LanguageModel._ATTRS_SERIALIZED_FILENAME),
@@ -409,6 +421,9 @@ class LanguageModel(AbstractLanguageModel):
             raise ValueError("Expected json serialized attributes to be %s but found %s" % (cls.JSON_ATTRS, attrs.keys()))
         with open(names["unigrams"], encoding=unigram_encoding) as fh:
             unigrams = fh.read().splitlines()
+        if names["kenlm"].endswith(NgramModel.BLOB_SUFFIX):
+            # a flattened model: its unigram / prefix sets are inside the blob (unigrams.txt is empty for it)
+            return cls(NgramModel.load_blob(names["kenlm"]), unigrams or None, **attrs)
         return cls(NgramModel(names["kenlm"]), unigrams, **attrs)
 
 

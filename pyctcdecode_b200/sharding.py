@@ -96,6 +96,7 @@ def build_ctcdecoder_broadcast(labels: List[str], kenlm_model_path: Optional[str
     if ngram is not None:
         lm = LanguageModel.__new__(LanguageModel)
         lm._unigram_list = ulist
+        lm._blob_unigrams = False
         lm._kenlm_model = ngram
         lm.alpha, lm.beta, lm.unk_score_offset, lm.score_boundary = alpha, beta, unk_score_offset, lm_score_boundary
     return BeamSearchDecoderCTC(alphabet, lm, device=device)

@@ -32,6 +32,8 @@ inline cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = nullptr; return cuda
 inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = nullptr; return cudaSuccess; }
+enum { cudaEventDisableTiming = 2 };
+inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = nullptr; return cudaSuccess; }
 inline cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
 inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }

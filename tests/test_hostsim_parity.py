@@ -352,3 +352,87 @@ def test_hostsim_quickstart_example_runs(sim, capsys):
     assert isinstance(mod["main"](), str)
     out = capsys.readouterr().out
     assert "decode_batch" in out and "after frame" in out
+
+
+def test_hostsim_decoder_is_thread_safe(sim):
+    """One decoder object called from 8 threads at once (the reference decoder can be): the handle
+    serialises the calls, every thread gets the results a lone call gets."""
+    import threading
+
+    wkw, lmkw = FAMILIES["B_3gram"]
+    wl = synth.make_workload(wkw)
+    dec = sim.build_ctcdecoder(wl.labels, kenlm_model_path=wl.arpa, unigrams=wl.words, **lmkw)
+    xs = [wl.utterance(8600 + i, 40 + 7 * i, ["peaky", "diffuse"][i % 2]) for i in range(8)]
+    want = [(dec.decode(x, beam_width=16), _beams(dec.decode_beams(x, beam_width=16))) for x in xs]
+    got, errors = [None] * len(xs), []
+
+    def work(i):
+        try:
+            for _ in range(5):
+                got[i] = (dec.decode(xs[i], beam_width=16), _beams(dec.decode_beams(xs[i], beam_width=16)))
+        except Exception as exc:  # pragma: no cover
+            errors.append(exc)
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(xs))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors
+    assert got == want
+
+
+def test_hostsim_blob_decoder_save_load_roundtrip(sim, tmp_path):
+    """save_to_dir / load_from_dir of a decoder built from a *.b2clm blob (the round trip was broken)."""
+    wkw, lmkw = FAMILIES["B_3gram"]
+    wl = synth.make_workload(wkw)
+    dec = sim.build_ctcdecoder(wl.labels, kenlm_model_path=wl.arpa, unigrams=wl.words, **lmkw)
+    path = str(tmp_path / "lm.b2clm")
+    dec._language_model.ngram_model.save_blob(path)
+    dec2 = sim.build_ctcdecoder(wl.labels, kenlm_model_path=path, **lmkw)
+    out = tmp_path / "saved"
+    out.mkdir()
+    dec2.save_to_dir(str(out))
+    dec3 = sim.BeamSearchDecoderCTC.load_from_dir(str(out))
+    lm2, lm3 = dec2._language_model, dec3._language_model
+    assert (lm3.alpha, lm3.beta) == (lm2.alpha, lm2.beta)
+    for tok in ("", wl.words[3][:2], "zzzzqqq"):     # host mirror of the partial-word score agrees with the ARPA-built model
+        assert lm3.score_partial_token(tok) == dec._language_model.score_partial_token(tok)
+    for i in range(3):
+        x = wl.utterance(8700 + i, 60, "peaky")
+        assert _beams(dec3.decode_beams(x, beam_width=20)) == _beams(dec.decode_beams(x, beam_width=20))
+
+
+def test_hostsim_corrupt_blob_fields_are_rejected(sim, tmp_path):
+    """b2c_lm_from_blob checks offsets, masks and ids against the blob size, not just the magic."""
+    import struct
+
+    wkw, lmkw = FAMILIES["B_3gram"]
+    wl = synth.make_workload(wkw)
+    dec = sim.build_ctcdecoder(wl.labels, kenlm_model_path=wl.arpa, unigrams=wl.words, **lmkw)
+    path = str(tmp_path / "lm.b2clm")
+    dec._language_model.ngram_model.save_blob(path)
+    good = open(path, "rb").read()
+    # header: magic u64, total u64, order i32, bos u32, eos u32, n_vocab u32, have i32, n_uni i32, then u64 offsets / masks
+    for off, fmt, bad in ((16, "<i", 99), (20, "<I", 0x7FFFFFFF), (40, "<Q", len(good) + 4096), (56, "<Q", 12345),
+                          (48, "<Q", len(good) - 8)):
+        data = bytearray(good)
+        struct.pack_into(fmt, data, off, bad)
+        bad_path = str(tmp_path / ("bad_%d.b2clm" % off))
+        with open(bad_path, "wb") as fh:
+            fh.write(bytes(data))
+        with pytest.raises(ValueError):
+            sim.build_ctcdecoder(wl.labels, kenlm_model_path=bad_path)
+    with open(str(tmp_path / "short.b2clm"), "wb") as fh:
+        fh.write(good[: len(good) // 2])
+    with pytest.raises(ValueError):
+        sim.build_ctcdecoder(wl.labels, kenlm_model_path=str(tmp_path / "short.b2clm"))
+
+
+@pytest.mark.parametrize("name", goldens.unstable_case_names())
+def test_hostsim_on_reference_unstable_goldens(sim, name):
+    """Kernel logic on the cases the reference itself decides by rounding noise (tests/goldens.py run_unstable_case)."""
+    def run(labels, x, **kw):
+        return _beams(sim.build_ctcdecoder(labels).decode_beams(x, **kw))
+
+    assert goldens.run_unstable_case(run, name) == ""
