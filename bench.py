@@ -2,7 +2,8 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4] [--regime peaky|diffuse]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
-    python bench.py --impl reference ...        # CPU arm: the oracle port on the host cores
+    python bench.py --impl reference ...        # CPU arm: the unmodified Python reference over a fork pool
+                                                # (baseline/_ref; LM workloads: the oracle C++ port)
 
 A "step" is one decode_batch() pass over one batch of synthetic logits.  `value` is frames/s
 with the batch already resident in HBM (device pointers handed to the C ABI); `e2e` is the same
@@ -10,7 +11,12 @@ call with PINNED HOST buffers, host->device copies and result copies inside the 
 Between timed steps L2 is flushed by writing a 512 MiB buffer (inputs of the headline config are
 smaller than L2).  Multi-GPU: one rank per GPU, utterances sharded with no data-path
 collective (the only collective is the broadcast of the LM blob before timing) -> "weak".
-Prints ONE JSON line on rank 0.
+Prints ONE JSON line on rank 0.  Besides the headline (C2) the line carries
+  secondary        (1 GPU) the other BASELINE.json configurations -- C3, C4 shape in f32 and f16, the diffuse regime,
+                   the beam sweep {10, 50, 500, 2000}, decode_beams_batch -- each with value, e2e, kernel times, a CPU
+                   figure and transcript identity against the oracle;
+  strong_scaling   (N > 1) ONE 2048-utterance C3 list decoded through sharding.decode_batch_sharded after the NCCL
+                   broadcast of the LM blob, checked against rank 0's single-GPU decode of the same list.
 """
 import argparse
 import json
@@ -165,17 +171,40 @@ def host_cores():
     return n
 
 
-def cpu_arm(wl, spec, kw, xs, beam, hot, target_cpu_seconds=20.0):
+def workload_objects(spec):
+    """-> (workload, build_ctcdecoder keyword arguments, hotword list or None)"""
+    wl = make_workload(spec)
+    kw = dict(spec["lm"])
+    if wl.arpa:
+        kw.update(kenlm_model_path=wl.arpa, unigrams=wl.words)
+    hot = wl.hotwords(spec["hot"]) if spec["hot"] else None
+    return wl, kw, hot
+
+
+def config_of(spec, regime, beam, B, V, logits_dtype, world):
+    """the `config` object of a JSON line -- the SAME dict for the B200 arm and the reference arm"""
+    return {"workload": spec["name"], "regime": regime, "beam_width": beam, "batch_per_gpu": B, "T": spec["T"], "V": V,
+            "logits_dtype": logits_dtype, "l2": "flushed between timed steps (512 MiB write)",
+            "parallelism": "utterance-sharded x%d" % world}
+
+
+def port_arm(wl, spec, kw, xs, beam, hot, target_cpu_seconds=20.0, min_utts=0, wall_seconds=0.0):
     """The reference's CPU path restated (oracle/ctc_oracle.cpp, a C++ port -- the reference itself is
-    pure Python) on all host cores, over a bounded sample of the same workload."""
+    pure Python) on all host cores, over a bounded sample of the same workload: about `target_cpu_seconds` of CPU work,
+    or (wall_seconds > 0) about that much wall time on all cores; the list is cycled if the sample needs more
+    utterances than were generated."""
     from oracle import oracle as orc
     cores = host_cores()
     ora = orc.OracleDecoder(wl.labels, **kw)
     t0 = time.perf_counter()
     ora.decode_batch(xs[:2], n_threads=2, beam_width=beam, hotwords=hot)
     per_utt = max((time.perf_counter() - t0), 1e-3)  # two utterances on two threads ~ one utterance-time
-    n = int(max(min(len(xs), target_cpu_seconds / per_utt), min(len(xs), cores)))
-    sample = xs[:n]
+    if wall_seconds > 0:
+        n = int(max(wall_seconds * cores / per_utt, min_utts, cores))
+        sample = [xs[i % len(xs)] for i in range(n)]
+    else:
+        n = int(max(min(len(xs), target_cpu_seconds / per_utt), min(len(xs), max(cores, min_utts))))
+        sample = xs[:n]
     t0 = time.perf_counter()
     texts = ora.decode_batch(sample, n_threads=cores, beam_width=beam, hotwords=hot)
     dt = time.perf_counter() - t0
@@ -183,6 +212,279 @@ def cpu_arm(wl, spec, kw, xs, beam, hot, target_cpu_seconds=20.0):
     return {"value": frames / dt, "unit": "frames/s", "cores": cores, "kind": "port",
             "sample": "%d utterances x T=%d of the same workload, oracle C++ port of the reference's Python loop, "
                       "%d threads, %.1f s" % (n, spec["T"], cores, dt)}, texts, n
+
+
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+
+def pyref_available(spec):
+    """The unmodified reference (pip-installed from /root/reference into baseline/_ref, which travels to the GPU box)
+    can be timed for workloads without a language model: its only missing hard dependency is then pygtrie's import,
+    served by the stand-in under oracle/refshim.  LM workloads would run on the pure-Python kenlm stand-in, which
+    would handicap the reference -- they are timed on the C++ port instead."""
+    return spec["lm_order"] == 0 and os.path.isdir(os.path.join(REF_DIR, "pyctcdecode"))
+
+
+class PyRef:
+    """`with multiprocessing.get_context('fork').Pool(n) as pool: decoder.decode_batch(pool, logits_list, ...)`
+    (reference README.md:82-85, decoder.py:895-945); pool start-up and decoder construction outside the timing."""
+
+    def __init__(self, labels, cores):
+        import logging
+        import multiprocessing as mp
+        for p in (os.path.join(ROOT, "oracle", "refshim"), REF_DIR):
+            if p not in sys.path:
+                sys.path.insert(0, p)
+        logging.disable(logging.CRITICAL)
+        from pyctcdecode import build_ctcdecoder as ref_build
+        import pyctcdecode as ref_pkg
+        assert os.path.realpath(ref_pkg.__file__).startswith(os.path.realpath(REF_DIR)), ref_pkg.__file__
+        self.dec = ref_build(labels)
+        self.cores = cores
+        self.pool = mp.get_context("fork").Pool(cores)
+
+    def run(self, sample, beam, hot):
+        t0 = time.perf_counter()
+        texts = self.dec.decode_batch(self.pool, sample, beam_width=beam, hotwords=hot)
+        return time.perf_counter() - t0, texts
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def reference_main(args, spec, B, beam):
+    """--impl reference: CPU only.  Each step is a bounded sample (>= 4 utterances per thread, >= ~2 s) of the
+    configured workload; the whole run is sized to about two minutes."""
+    wl, kw, hot = workload_objects(spec)
+    cores = host_cores()
+    T = spec["T"]
+    use_py = pyref_available(spec) and not args.ref_port
+    n_steps = max(1, args.warmup + args.steps)
+    per_step = args.ref_seconds if args.ref_seconds > 0 else min(8.0, max(2.2, 120.0 / n_steps))
+    n0 = 4 * cores
+    xs = wl.batch(1, n0, T, args.regime)
+    if args.logits_dtype == "f16":
+        xs = [x.astype(np.float16).astype(np.float32) for x in xs]
+    texts = None
+    if use_py:
+        ref = PyRef(wl.labels, cores)
+        dt0, _ = ref.run(xs[:cores], beam, hot)                     # pool warm-up + calibration: one utterance per process
+        n = int(max(n0, min(64 * cores, per_step / max(dt0, 1e-3) * cores)))
+        if n > len(xs):
+            xs = wl.batch(1, n, T, args.regime)
+        sample = xs[:n]
+        vals = []
+        for i in range(n_steps):
+            dt, texts = ref.run(sample, beam, hot)
+            if i >= args.warmup:
+                vals.append(n * T / dt)
+        ref.close()
+        kind = "reference"
+        what = ("%d utterances x T=%d of the same workload, the UNMODIFIED Python reference (baseline/_ref, pyctcdecode 0.6.0) "
+                "through decode_batch over a fork Pool(%d), %.1f s per step" % (n, T, cores, n * T / vals[-1]))
+    else:
+        vals, info = [], None
+        if len(xs) < min(B, 16 * cores):
+            xs = wl.batch(1, min(B, 16 * cores), T, args.regime)
+            if args.logits_dtype == "f16":
+                xs = [x.astype(np.float16).astype(np.float32) for x in xs]
+        for i in range(n_steps):
+            info, texts, n = port_arm(wl, spec, kw, xs, beam, hot, min_utts=n0, wall_seconds=per_step)
+            if i >= args.warmup:
+                vals.append(info["value"])
+        kind = "port"
+        what = info["sample"] + ("" if pyref_available(spec) else
+                                 "; the Python reference is not timed for LM workloads (kenlm is not installed: its stand-in is pure Python)")
+    v = statistics.mean(vals)
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": config_of(spec, args.regime, beam, B, wl.V, args.logits_dtype, max(1, args.gpus)),
+           "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": kind, "sample": what},
+           "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if args.emit_texts:
+        out["texts"] = list(texts)
+    _emit(out)
+    return 0
+
+
+def pyref_subprocess(args_workload, regime, beam, seconds):
+    """cpu_baseline of the B200 arm, `kind: reference`: the reference arm in a child process (the fork pool must not
+    be forked from a process that holds a CUDA context and helper threads)."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0", "--workload",
+           args_workload, "--regime", regime, "--beam", str(beam), "--emit-texts", "--ref-seconds", str(seconds)]
+    try:
+        run = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=300)
+        line = [ln for ln in run.stdout.splitlines() if ln.startswith("{")][-1]
+        obj = json.loads(line)
+        return obj["cpu_baseline"], obj.get("texts", [])
+    except Exception as exc:  # the figure is a reported baseline, not a gate: say why it is missing
+        return {"value": None, "unit": "frames/s", "cores": host_cores(), "kind": "reference", "sample": "failed: %r" % (exc,)}, []
+
+
+class Stepper:
+    """one decoder + one batch resident in pinned host memory and in HBM; times the public call"""
+
+    def __init__(self, torch, dist, dec, xs, beam, hot, logits_dtype, call="decode_batch"):
+        self.torch, self.dist, self.dec, self.beam, self.hot, self.call = torch, dist, dec, beam, hot, call
+        if logits_dtype == "f16":                             # the model emitted half precision: both arms see those values
+            xs16 = [x.astype(np.float16) for x in xs]
+            self.xs = [x.astype(np.float32) for x in xs16]
+            self.host = torch.from_numpy(np.stack(xs16)).pin_memory()
+        else:
+            self.xs = xs
+            self.host = torch.from_numpy(np.stack(xs)).pin_memory()
+        self.dev = self.host.cuda(non_blocking=False)
+
+    def step_dev(self):
+        return getattr(self.dec, self.call)(None, self.dev, beam_width=self.beam, hotwords=self.hot)
+
+    def step_host(self):
+        return getattr(self.dec, self.call)(None, self.host, beam_width=self.beam, hotwords=self.hot)
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.dist is not None:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def timed(self, fn, steps, warmup, flush):
+        torch = self.torch
+        for _ in range(warmup):
+            fn()
+        self.barrier()
+        total, tms, out = 0.0, [], None
+        for _ in range(steps):
+            flush.fill_(1)                       # L2 flush, outside the timed bracket
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            out = fn()
+            torch.cuda.synchronize()
+            total += time.perf_counter() - t0
+            tms.append(self.dec.last_timings())
+        self.barrier()
+        if self.dist is not None:
+            t = torch.tensor([total], dtype=torch.float64, device="cuda")
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            total = float(t.item())
+        return total, tms, out
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return json.load(fh)
+    except OSError:
+        return {}
+
+
+def secondary_entry(torch, pkg, flush, name, spec, regime, beam, logits_dtype, call, steps, warmup, batch=0, cpu_seconds=4.0):
+    """one more BASELINE.json configuration on one GPU: value / e2e / kernel times / CPU figure / transcript identity"""
+    t_start = time.perf_counter()
+    wl, kw, hot = workload_objects(spec)
+    B, T = batch or spec["batch"], spec["T"]
+    dec = pkg.build_ctcdecoder(wl.labels, device=torch.cuda.current_device(), **kw)
+    st = Stepper(torch, None, dec, wl.batch(1, B, T, regime), beam, hot, logits_dtype, call)
+    total, tms, out = st.timed(st.step_dev, steps, warmup, flush)
+    e2e_total, e2e_tms, out_e2e = st.timed(st.step_host, steps, 1, flush)
+    same = out == out_e2e
+    frames = B * T
+    peak = float(load_peaks().get("hbm_gbs", 6650.0))
+    esz = 2 if logits_dtype == "f16" else 4
+    ms_beam = statistics.mean(t["ms_beam"] for t in tms)
+    ms_prep = statistics.mean(t["ms_prepare"] for t in tms)
+    texts = out if call == "decode_batch" else [beams[0].text if beams else "" for beams in out]
+    info, cpu_texts, n = port_arm(wl, spec, kw, st.xs, beam, hot, target_cpu_seconds=cpu_seconds)
+    ent = {"name": name, "config": config_of(spec, regime, beam, B, wl.V, logits_dtype, 1), "call": call,
+           "value": frames * steps / total, "unit": "frames/s", "ms_per_step": 1e3 * total / steps, "steps": steps, "warmup": warmup,
+           "e2e": {"value": frames * steps / e2e_total, "unit": "frames/s", "ms_per_step": 1e3 * e2e_total / steps,
+                   "h2d_bytes_per_step": int(e2e_tms[-1]["h2d_bytes"]), "d2h_bytes_per_step": int(e2e_tms[-1]["d2h_bytes"])},
+           "beam_kernel_ms": ms_beam, "prepare_ms": ms_prep,
+           "roofline_frac": frames * wl.V * esz / (ms_beam * 1e-3) / 1e9 / peak if ms_beam > 0 else None,
+           "roofline_prepare_frac": frames * wl.V * esz / (ms_prep * 1e-3) / 1e9 / peak if ms_prep > 0 else None,
+           "kernel_variant": tms[-1]["kernel_variant"], "resident_ctas": tms[-1]["cta_slots"], "cap_candidates": tms[-1]["cap_candidates"],
+           "inplace_frames_per_step": tms[-1]["inplace_frames"], "sorted_frames_per_step": tms[-1]["sorted_frames"],
+           "oversize_frames_per_step": tms[-1]["oversize_frames"],
+           "gpu_launches": int(sum(t["launches"] for t in tms)),
+           "host_equals_device_input": bool(same),
+           "cpu_baseline": info,
+           "transcripts_identical_to_oracle": "%d/%d" % (sum(a == b for a, b in zip(cpu_texts, texts[:n])), n),
+           "wall_s": None}
+    del st, dec
+    torch.cuda.empty_cache()
+    ent["wall_s"] = round(time.perf_counter() - t_start, 1)
+    return ent
+
+
+def strong_scaling(torch, dist, pkg, sharding, flush, rank, world, local_rank, steps, n_utts=2048):
+    """The north_star multi-GPU path: every rank holds the SAME list of utterances (C3: 3-gram LM), the decoder is
+    built with ONE NCCL broadcast of the flattened LM, decode_batch_sharded splits the list over the ranks (no
+    data-path collective), the transcripts are gathered, and rank 0 checks them against its own single-GPU decode."""
+    spec = dict(WORKLOADS["c3"])
+    wl, kw, hot = workload_objects(spec)
+    T, beam = spec["T"], spec["beam"]
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    dec = sharding.build_ctcdecoder_broadcast(wl.labels, device=local_rank, **kw)
+    torch.cuda.synchronize()
+    dist.barrier()
+    build_s = time.perf_counter() - t0
+    bc = dict(sharding.last_broadcast)
+    big = np.stack(wl.batch(1, n_utts, T, "peaky"))          # one allocation: a rank's utterances are adjacent where possible
+    xs = [big[i] for i in range(n_utts)]
+
+    def sharded():
+        return sharding.decode_batch_sharded(dec, xs, beam_width=beam, hotwords=hot)
+
+    def timed(fn, n):
+        tot, out = 0.0, None
+        for _ in range(n):
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            dist.barrier()
+            t1 = time.perf_counter()
+            out = fn()
+            torch.cuda.synchronize()
+            tot += time.perf_counter() - t1
+        t = torch.tensor([tot], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), out
+
+    sharded()
+    sharded()                                               # warm-up: buffers, kernel variant hint
+    t_sh, texts = timed(sharded, steps)
+    # the same list on ONE GPU through the same public call (rank 0 decodes, the others wait at the barrier)
+    single_texts, t_single = None, None
+    if rank == 0:
+        dec.decode_batch(None, xs, beam_width=beam, hotwords=hot)
+        dec.decode_batch(None, xs, beam_width=beam, hotwords=hot)
+    tot = 0.0
+    for _ in range(steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        dist.barrier()
+        if rank == 0:
+            t1 = time.perf_counter()
+            single_texts = dec.decode_batch(None, xs, beam_width=beam, hotwords=hot)
+            torch.cuda.synchronize()
+            tot += time.perf_counter() - t1
+    dist.barrier()
+    if rank != 0:
+        return None
+    t_single = tot
+    frames = n_utts * T
+    return {"workload": spec["name"].replace("batch=1024 per GPU", "ONE list of %d utterances" % n_utts), "n_utts": n_utts, "T": T,
+            "beam_width": beam, "path": "sharding.build_ctcdecoder_broadcast -> sharding.decode_batch_sharded (host numpy in, texts out, all_gather_object of the transcripts inside the timed region)",
+            "lm_broadcast": {"bytes": bc.get("bytes"), "ms": bc.get("ms"), "gb_per_s": bc.get("gb_per_s"), "backend": bc.get("backend"),
+                             "build_decoder_s_incl_arpa_parse_on_rank0": build_s},
+            "sharded": {"value": frames * steps / t_sh, "unit": "frames/s", "ms_per_step": 1e3 * t_sh / steps, "n_gpus": world},
+            "single_gpu_same_list": {"value": frames * steps / t_single, "unit": "frames/s", "ms_per_step": 1e3 * t_single / steps},
+            "speedup_vs_one_gpu": t_single / t_sh,
+            "sharded_equals_single": bool(texts == single_texts), "steps": steps,
+            "limit": "per-rank host work (Python list handling, per-utterance H2D copies) and the latency of one resident wave: "
+                     "%d utterances per GPU are %s the resident set" % (n_utts // world, "within" if n_utts // world <= 592 else "above")}
 
 
 _REAL_STDOUT = None
@@ -215,8 +517,15 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="utterances per GPU (default: the workload's)")
     ap.add_argument("--beam", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary configurations (1 GPU) / the strong-scaling section (N > 1)")
+    ap.add_argument("--secondary", default="", help="comma separated subset of: c3,c4,c4_f16,diffuse,beam10,beam50,beam500,beam2000,beams_batch")
+    ap.add_argument("--secondary-steps", type=int, default=5)
+    ap.add_argument("--call", default="decode_batch", choices=["decode_batch", "decode_beams_batch"])
     ap.add_argument("--logits-dtype", default="f32", choices=["f32", "f16"],
                     help="dtype of the model output handed to decode_batch (f16: 2-byte elements over PCIe, widened on the device)")
+    ap.add_argument("--ref-port", action="store_true", help="reference arm: time the oracle C++ port even where the Python reference can run")
+    ap.add_argument("--ref-seconds", type=float, default=0.0, help="reference arm: target seconds of one step (default: sized from --steps)")
+    ap.add_argument("--emit-texts", action="store_true", help="reference arm: add the transcripts of the last step to the JSON line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -234,29 +543,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        wl = make_workload(spec)
-        kw = dict(spec["lm"])
-        if wl.arpa:
-            kw.update(kenlm_model_path=wl.arpa, unigrams=wl.words)
-        hot = wl.hotwords(spec["hot"]) if spec["hot"] else None
-        n_gen = min(B, 8 * host_cores() + 8)
-        xs = wl.batch(1, n_gen, T, args.regime)
-        vals, info = [], None
-        # every step is a bounded sample; the whole run (warm-up + steps) is sized to about two minutes
-        per_step = min(8.0, 120.0 / max(1, args.warmup + args.steps))
-        for i in range(args.warmup + args.steps):
-            info, _, _ = cpu_arm(wl, spec, kw, xs, beam, hot, target_cpu_seconds=per_step)
-            if i >= args.warmup:
-                vals.append(info["value"])
-        v = statistics.mean(vals)
-        info["value"] = v
-        _emit(({"impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus,
-                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
-                          "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                          "config": {"workload": spec["name"], "regime": args.regime, "beam_width": beam},
-                          "cpu_baseline": info,
-                          "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
-        return 0
+        return reference_main(args, spec, B, beam)
 
     # ------------------------------------------------------------------------------------
     # B200 arm
@@ -281,67 +568,36 @@ def main():
         from pyctcdecode_b200 import _lib
         _lib.use_library(os.environ["B200CTC_PROFILING_LIB"])
 
-    wl = make_workload(spec)
-    kw = dict(spec["lm"])
-    if wl.arpa:
-        kw.update(kenlm_model_path=wl.arpa, unigrams=wl.words)
-    hot = wl.hotwords(spec["hot"]) if spec["hot"] else None
+    wl, kw, hot = workload_objects(spec)
+    lm_broadcast = None
     if world > 1 and wl.arpa:
         # rank 0 parses the ARPA file; every other rank receives the flattened LM over NCCL
         dec = sharding.build_ctcdecoder_broadcast(wl.labels, device=local_rank, **kw)
+        lm_broadcast = dict(sharding.last_broadcast)
     else:
         dec = pkg.build_ctcdecoder(wl.labels, device=local_rank, **kw)
 
     xs = wl.batch(1 + rank * 100_000, B, T, args.regime)   # every rank its own utterances (weak scaling)
-    if args.logits_dtype == "f16":                        # the model emitted half precision: both arms see those values
-        xs16 = [x.astype(np.float16) for x in xs]
-        xs = [x.astype(np.float32) for x in xs16]
-        host = torch.from_numpy(np.stack(xs16)).pin_memory()
-    else:
-        host = torch.from_numpy(np.stack(xs)).pin_memory()
-    dev = host.cuda(non_blocking=False)
-    frames_per_step = B * T
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
-
-    def step_dev():
-        return dec.decode_batch(None, dev, beam_width=beam, hotwords=hot)
-
-    def step_host():
-        return dec.decode_batch(None, host, beam_width=beam, hotwords=hot)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    def timed(fn, steps, warmup):
-        for _ in range(warmup):
-            fn()
-        barrier()
-        total, tms = 0.0, []
-        for _ in range(steps):
-            flush.fill_(1)                       # L2 flush, outside the timed bracket
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            out = fn()
-            torch.cuda.synchronize()
-            total += time.perf_counter() - t0
-            tms.append(dec.last_timings())
-        barrier()
-        if dist is not None:
-            t = torch.tensor([total], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            total = float(t.item())
-        return total, tms, out
+    st = Stepper(torch, dist, dec, xs, beam, hot, args.logits_dtype, args.call)
+    xs = st.xs
+    frames_per_step = B * T
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    total, tms, texts = timed(step_dev, args.steps, args.warmup)
+    total, tms, texts = st.timed(st.step_dev, args.steps, args.warmup, flush)
     clocks = sampler.stop() if rank == 0 else None
-    e2e_total, e2e_tms, texts_e2e = timed(step_host, args.steps, 1)
+    e2e_total, e2e_tms, texts_e2e = st.timed(st.step_host, args.steps, 1, flush)
     assert texts == texts_e2e
+    if args.call != "decode_batch":
+        texts = [beams[0].text if beams else "" for beams in texts]
+
+    strong = None
+    if world > 1 and not args.no_secondary:
+        del st
+        torch.cuda.empty_cache()
+        strong = strong_scaling(torch, dist, pkg, sharding, flush, rank, world, local_rank, steps=max(2, min(5, args.steps)))
 
     if rank != 0:
         if dist is not None:
@@ -351,12 +607,7 @@ def main():
     value = world * frames_per_step * args.steps / total
     ms_beam = statistics.mean(t["ms_beam"] for t in tms)
     ms_prep = statistics.mean(t["ms_prepare"] for t in tms)
-    peaks = {}
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
-            peaks = json.load(fh)
-    except OSError:
-        pass
+    peaks = load_peaks()
     peak = float(peaks.get("hbm_gbs", 6650.0))
     esz = 2 if args.logits_dtype == "f16" else 4      # algorithmic bytes per logit: the dtype the rows arrive in
     alg_bytes = frames_per_step * wl.V * esz
@@ -372,21 +623,13 @@ def main():
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": spec["name"], "regime": args.regime, "beam_width": beam, "batch_per_gpu": B, "T": T, "V": wl.V,
-                   "logits_dtype": args.logits_dtype, "l2": "flushed between timed steps (512 MiB write)", "parallelism": "utterance-sharded x%d" % world},
+        "config": config_of(spec, args.regime, beam, B, wl.V, args.logits_dtype, world),
         "roofline": {"bound": "hbm", "kernel": "b2c_beam_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                      "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6.65 TB/s (of fallback)",
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": ms_beam,
                      "note": "the beam kernel is a T-step serial chain per utterance (latency bound); the streaming stage is reported under roofline_prepare"},
         "roofline_prepare": {"bound": "hbm", "kernel": "b2c_prepare_kernel", "achieved": ach_prep, "peak": peak, "unit": "GB/s",
-                             "frac": (ach_prep / peak) if ach_prep else None, "kernel_ms": ms_prep,
-                             # what really bounds the streaming stage at V <= 32: instruction issue (float64 exp of every logit,
-                             # DESIGN.md section 4).  352 warp instructions per 32-element row is the ncu count of the C2 launch
-                             # (profiles/ncu_r01_c2_final_summary.json: 90 M per 256 000 rows); peak = SMs x 4 schedulers x clock
-                             "issue": ({"warp_instructions_per_row_ncu": 352, "sm_mhz": clocks.get("sm_mhz"),
-                                        "frac_of_issue_peak": (352.0 * frames_per_step / (ms_prep * 1e-3)) /
-                                                              (148 * 4 * clocks["sm_mhz"] * 1e6)}
-                                       if wl.V <= 32 and ms_prep > 0 and clocks and clocks.get("sm_mhz") else None)},
+                             "frac": (ach_prep / peak) if ach_prep else None, "kernel_ms": ms_prep},
         "e2e": {"value": world * frames_per_step * args.steps / e2e_total, "unit": "frames/s",
                 "h2d_bytes_per_step": int(e2e_tms[-1]["h2d_bytes"]), "d2h_bytes_per_step": int(e2e_tms[-1]["d2h_bytes"]),
                 "ms_per_step": 1e3 * e2e_total / args.steps},
@@ -400,9 +643,21 @@ def main():
                                "frames_over_128_256_512_1024_2048_4096_total": tms[-1]["cand_hist"]},
         "clocks": clocks,
     }
+    if lm_broadcast:
+        out["lm_broadcast"] = lm_broadcast
+    if strong is not None:
+        out["strong_scaling"] = strong
     if world == 1 and not args.no_cpu_baseline:
-        info, cpu_texts, n = cpu_arm(wl, spec, kw, xs, beam, hot)
-        out["cpu_baseline"] = info
+        # the reference's own CPU path: the unmodified Python package over a fork pool where it can run (no LM), in a
+        # child process; next to it the C++ port of the same loop, which also provides the transcripts to compare with
+        port, cpu_texts, n = port_arm(wl, spec, kw, xs, beam, hot, target_cpu_seconds=10.0 if pyref_available(spec) else 20.0)
+        if pyref_available(spec) and args.logits_dtype == "f32":
+            ref_info, ref_texts = pyref_subprocess(args.workload, args.regime, beam, 6.0)
+            out["cpu_baseline"] = dict(ref_info, port=port)
+            m = min(len(ref_texts), len(texts))
+            out["transcripts_identical_to_reference"] = "%d/%d" % (sum(a == b for a, b in zip(ref_texts[:m], texts[:m])), m)
+        else:
+            out["cpu_baseline"] = port
         out["transcripts_identical_to_oracle"] = "%d/%d" % (sum(a == b for a, b in zip(cpu_texts, texts[:n])), n)
         # "WER parity" of the metric: both systems against the word sequence the synthetic alignment spells
         from tests import synth
@@ -415,6 +670,28 @@ def main():
                 err[key][1] += m
         out["wer"] = {k: (v[0] / v[1] if v[1] else None) for k, v in err.items()}
         out["wer"].update(utterances=n, against="ground-truth word sequence of the synthetic alignment (noisy logits, so not 0)")
+    if world == 1 and not args.no_secondary and args.workload == "c2" and args.regime == "peaky" and not args.batch and not args.beam:
+        del st, dec
+        torch.cuda.empty_cache()
+        S, W = max(1, args.secondary_steps), 3
+        plan = [("c3", WORKLOADS["c3"], "peaky", 100, "f32", "decode_batch", 0),
+                ("c4", WORKLOADS["c4"], "peaky", 100, "f32", "decode_batch", 0),
+                ("c4_f16", WORKLOADS["c4"], "peaky", 100, "f16", "decode_batch", 0),
+                ("diffuse", WORKLOADS["c2"], "diffuse", 100, "f32", "decode_batch", 0),
+                ("beam10", WORKLOADS["c2"], "peaky", 10, "f32", "decode_batch", 0),
+                ("beam50", WORKLOADS["c2"], "peaky", 50, "f32", "decode_batch", 0),
+                ("beam500", WORKLOADS["c2"], "peaky", 500, "f32", "decode_batch", 0),
+                ("beam2000", WORKLOADS["c2"], "peaky", 2000, "f32", "decode_batch", 0),
+                ("beams_batch", WORKLOADS["c2"], "peaky", 100, "f32", "decode_beams_batch", 0)]
+        want = [w for w in args.secondary.split(",") if w]
+        out["secondary"] = []
+        for name, sp, regime, bm, dt, call, bsz in plan:
+            if want and name not in want:
+                continue
+            try:
+                out["secondary"].append(secondary_entry(torch, pkg, flush, name, dict(sp), regime, bm, dt, call, S, W, bsz))
+            except Exception as exc:  # one configuration must not take the headline down with it
+                out["secondary"].append({"name": name, "error": repr(exc)})
     _emit(out)
     if dist is not None:
         dist.destroy_process_group()

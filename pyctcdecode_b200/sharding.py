@@ -20,6 +20,10 @@ from .decoder import BeamSearchDecoderCTC
 from .language_model import LanguageModel, NgramModel, load_unigram_set_from_arpa
 
 
+# what the last broadcast_ngram_model call moved: {"bytes", "ms", "gb_per_s", "backend"} (bench.py reports it)
+last_broadcast: dict = {}
+
+
 def shard_utterances(lengths: Sequence[int], world_size: int) -> List[List[int]]:
     """Longest-processing-time-first partition of utterance indices over ``world_size`` ranks.
     Deterministic (ties broken by index) so that every rank computes the same partition."""
@@ -64,7 +68,22 @@ def broadcast_ngram_model(path: Optional[str], unigrams: Optional[Collection[str
         addr, _ = model.blob()
         host = np.ctypeslib.as_array((C.c_uint8 * size).from_address(addr))
         buf.copy_(torch.from_numpy(host))
-    dist.broadcast(buf, src=src, group=group)
+    import time
+
+    if use_cuda:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        dist.broadcast(buf, src=src, group=group)
+        ev1.record()
+        ev1.synchronize()
+        ms = float(ev0.elapsed_time(ev1))
+    else:
+        t0 = time.perf_counter()
+        dist.broadcast(buf, src=src, group=group)
+        ms = 1e3 * (time.perf_counter() - t0)
+    last_broadcast.clear()
+    last_broadcast.update(bytes=int(size), ms=ms, gb_per_s=(size / 1e9) / max(ms * 1e-3, 1e-9), backend=str(dist.get_backend(group)),
+                          world_size=int(dist.get_world_size(group)))
     if rank != src:
         host_copy = buf.cpu().numpy()
         model = NgramModel.from_blob(path_b, host_copy.ctypes.data, size)

@@ -326,3 +326,124 @@ def test_gpu_scored_in_place_frames_with_lm(pkg, orc, fam):
         frames += tm["frames"]
         _compare(ora.decode_beams(x, **dkw), got)
     assert inplace > 0.4 * frames, (inplace, frames)
+
+
+# ---- BASELINE.json configurations at FULL size against the oracle -----------------------------
+def _threads():
+    import bench
+    return bench.host_cores()
+
+
+def test_gpu_full_size_c3_vs_oracle(pkg, orc):
+    """C3: B=1024, T=1000, V=32, beam 100 + 3-gram (alpha 0.5, beta 1.0): every transcript identical to the oracle's."""
+    import bench
+    spec = bench.WORKLOADS["c3"]
+    wl, kw, hot = bench.workload_objects(spec)
+    dec = pkg.build_ctcdecoder(wl.labels, **kw)
+    ora = orc.OracleDecoder(wl.labels, **kw)
+    xs = wl.batch(1, spec["batch"], spec["T"], "peaky")
+    got = dec.decode_batch(None, xs, beam_width=100)
+    assert got == dec.decode_batch(None, np.stack(xs), beam_width=100)       # second call: the residency variant chosen from the hint
+    want = ora.decode_batch(xs, n_threads=_threads(), beam_width=100)
+    bad = [i for i, (a, b) in enumerate(zip(want, got)) if a != b]
+    assert not bad, "%d of %d transcripts differ, first: %r vs %r" % (len(bad), len(xs), want[bad[0]], got[bad[0]])
+
+
+@pytest.mark.parametrize("dtype", ["f32", "f16"])
+def test_gpu_full_size_c4_shape_vs_oracle(pkg, orc, dtype):
+    """C4 shape on one GPU: B=512, T=500, V=1024 BPE, beam 100 + 4-gram + 16 hotwords, float32 and float16 logits."""
+    import bench
+    spec = bench.WORKLOADS["c4"]
+    wl, kw, hot = bench.workload_objects(spec)
+    dec = pkg.build_ctcdecoder(wl.labels, **kw)
+    ora = orc.OracleDecoder(wl.labels, **kw)
+    xs = wl.batch(1, spec["batch"], spec["T"], "peaky")
+    if dtype == "f16":
+        xs16 = [x.astype(np.float16) for x in xs]
+        xs = [x.astype(np.float32) for x in xs16]
+        got = dec.decode_batch(None, np.stack(xs16), beam_width=100, hotwords=hot)
+    else:
+        got = dec.decode_batch(None, xs, beam_width=100, hotwords=hot)
+    want = ora.decode_batch(xs, n_threads=_threads(), beam_width=100, hotwords=hot)
+    bad = [i for i, (a, b) in enumerate(zip(want, got)) if a != b]
+    assert not bad, "%d of %d transcripts differ, first: %r vs %r" % (len(bad), len(xs), want[bad[0]], got[bad[0]])
+
+
+@pytest.mark.parametrize("beam,B", [(10, 256), (50, 256), (500, 64), (2000, 24)])
+def test_gpu_full_T_beam_sweep_vs_oracle(pkg, orc, beam, B):
+    """C5 shape (T=1000, V=32): the beam sweep against the oracle; the wide beams on as many utterances as the oracle
+    finishes in seconds on the box's host cores."""
+    wl = synth.CharWorkload("B", n_words=20000, lm_order=0)
+    dec = pkg.build_ctcdecoder(wl.labels)
+    ora = orc.OracleDecoder(wl.labels)
+    xs = wl.batch(1, B, 1000, "peaky")
+    got = dec.decode_batch(None, xs, beam_width=beam)
+    want = ora.decode_batch(xs, n_threads=_threads(), beam_width=beam)
+    bad = [i for i, (a, b) in enumerate(zip(want, got)) if a != b]
+    assert not bad, "%d of %d transcripts differ" % (len(bad), len(xs))
+    g = dec.decode_beams_batch(None, xs[:2], beam_width=beam)
+    w = ora.decode_beams_batch(xs[:2], n_threads=2, beam_width=beam)
+    for a, b in zip(w, g):
+        _compare(a, _beams(b))
+
+
+def test_gpu_differential_fuzz(pkg):
+    """tools/fuzz_hostsim.py through the CUDA library ('differential fuzzing never runs on the device'):
+    random vocabulary family / LM / hotwords / prune settings / beams 1-300 / sharpness / exact ties / chunked streaming."""
+    from tools import fuzz_hostsim
+    assert fuzz_hostsim.fuzz(220, 2027) == 0
+
+
+def test_gpu_decoder_is_thread_safe(pkg):
+    """8 threads on one decoder object: calls are serialised inside the handle, every thread gets the lone-call result."""
+    import threading
+
+    wl = synth.make_workload(dict(kind="char", vocab="B", n_words=400, lm_order=3))
+    dec = pkg.build_ctcdecoder(wl.labels, kenlm_model_path=wl.arpa, unigrams=wl.words, alpha=0.5, beta=1.0)
+    xs = [wl.utterance(8600 + i, 80 + 11 * i, ["peaky", "diffuse"][i % 2]) for i in range(8)]
+    want = [(dec.decode(x, beam_width=32), _beams(dec.decode_beams(x, beam_width=32))) for x in xs]
+    got, errors = [None] * len(xs), []
+
+    def work(i):
+        try:
+            for _ in range(10):
+                got[i] = (dec.decode(xs[i], beam_width=32), _beams(dec.decode_beams(xs[i], beam_width=32)))
+        except Exception as exc:  # pragma: no cover
+            errors.append(exc)
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(xs))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors
+    assert got == want
+
+
+def test_gpu_tensor_device_and_stream_order(pkg):
+    """CUDA tensors: the decoder of the tensors' device runs (a decoder bound to another device raises), and logits
+    still being written on a side stream are waited for (the decoder's stream waits on torch's current stream)."""
+    import torch
+
+    wl = synth.CharWorkload("B", n_words=2000, lm_order=0)
+    dec = pkg.build_ctcdecoder(wl.labels)
+    x = torch.from_numpy(np.stack(wl.batch(61_000, 16, 400, "peaky")))
+    want = dec.decode_batch(None, x.numpy(), beam_width=50)
+    side = torch.cuda.Stream()
+    for _ in range(3):
+        with torch.cuda.stream(side):
+            big = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+            for _ in range(20):
+                big.fill_(1)                                  # ~ms of queued work ahead of the producer of the logits
+            dev = torch.zeros_like(x, device="cuda")
+            dev.copy_(x.pin_memory(), non_blocking=True)
+            assert dec.decode_batch(None, dev, beam_width=50) == want
+    bound = pkg.build_ctcdecoder(wl.labels, device=0)
+    assert bound.decode_batch(None, dev, beam_width=50) == want
+    if torch.cuda.device_count() > 1:
+        other = x.to("cuda:1")
+        with pytest.raises(ValueError):
+            bound.decode_batch(None, other, beam_width=50)
+        assert dec.decode_batch(None, other, beam_width=50) == want          # unbound decoder: follows the tensor
+        with pytest.raises(ValueError):
+            dec.decode_batch(None, [dev[0], other[1]], beam_width=50)

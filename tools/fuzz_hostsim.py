@@ -1,7 +1,9 @@
-"""Differential fuzzing of the kernel LOGIC (tests/hostsim build) against the oracle: random vocabulary family, LM /
-hotwords / prune settings, beam widths from 1 to 300, logits of random sharpness (incl. integer-valued rows for exact
-ties), whole-utterance decode and chunked streaming.  TEST TOOL, CPU only.
-    python tools/fuzz_hostsim.py [n_cases] [seed]      (B200CTC_HOSTSIM_ORDER / B200CTC_NO_V5 / B200CTC_FORCE_V5 apply)
+"""Differential fuzzing against the oracle: random vocabulary family, LM / hotwords / prune settings, beam widths
+from 1 to 300, logits of random sharpness (incl. integer-valued rows for exact ties), whole-utterance decode and
+chunked streaming.  TEST TOOL.
+    python tools/fuzz_hostsim.py [n_cases] [seed]          kernel LOGIC on the CPU (tests/hostsim build)
+    python tools/fuzz_hostsim.py [n_cases] [seed] --cuda   the CUDA library on a GPU box (also: tests/test_gpu_parity.py)
+(B200CTC_HOSTSIM_ORDER / B200CTC_NO_V5 / B200CTC_FORCE_V5 apply)
 """
 import os
 import subprocess
@@ -11,13 +13,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
-subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "hostsim")])
 import pyctcdecode_b200 as pkg  # noqa: E402
 from oracle import oracle as orc  # noqa: E402
-from pyctcdecode_b200 import _lib  # noqa: E402
 from tests import synth  # noqa: E402
 
-_lib.use_library(os.path.join(ROOT, "tests", "hostsim", "libb200ctc_hostsim.so"))
 FAMS = {
     "B_nolm": (dict(kind="char", vocab="B", n_words=400, lm_order=0), {}),
     "B_3gram": (dict(kind="char", vocab="B", n_words=400, lm_order=3), dict(alpha=0.5, beta=1.0)),
@@ -40,8 +39,16 @@ def same(ref, got, tol=1e-9):
 
 
 def main():
-    n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 300
-    seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    argv = [a for a in sys.argv[1:] if not a.startswith("--")]
+    if "--cuda" not in sys.argv:
+        from pyctcdecode_b200 import _lib
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "hostsim")])
+        _lib.use_library(os.path.join(ROOT, "tests", "hostsim", "libb200ctc_hostsim.so"))
+    return fuzz(int(argv[0]) if len(argv) > 0 else 300, int(argv[1]) if len(argv) > 1 else 1)
+
+
+def fuzz(n_cases, seed):
+    """runs on whichever library pyctcdecode_b200._lib is bound to; returns the number of mismatches"""
     rng = np.random.default_rng(seed)
     decs = {}
     bad = 0
@@ -104,8 +111,8 @@ def main():
             bad += 1
             print("MISMATCH case %d fam %s T=%d regime %s %r variant %d" % (case, fam, T, regime, kw, tm["kernel_variant"]), flush=True)
     print("cases %d mismatches %d  (frames %d, in place %d, sorted %d)" % (n_cases, bad, stats["frames"], stats["inplace"], stats["sorted"]))
-    return 1 if bad else 0
+    return bad
 
 
 if __name__ == "__main__":
-    sys.exit(main())
+    sys.exit(1 if main() else 0)
