@@ -135,7 +135,7 @@ struct B2cBeamArgs {
     const u64* frame_off;
     const int* T;
     const B2cFrameRec* tok_rec;
-    const u16* tok_ids;
+    const u32* tok_ids;
     const double* tok_lp;
     u8* gws;                   // [slots][L.gws_bytes]
     const B2cLmState* start_states;  // optional [n_utts]
@@ -219,12 +219,12 @@ B2C_HD void b2c_beam_block(const B2cBeamArgs& A, int slot, u8* smem) {
             bool in_place = false;
             u32 single = B2C_NONE_U32;
             if (rec.cnt == 1) {
-                const u16 id0 = A.tok_ids[base];
+                const u16 id0 = rec.id0;
                 const B2cTok t0 = A.P.toks[id0];
                 single = t0.canon;
                 const int kind = b2c_inplace_kind(W.sc->flags, prev_single, t0.flags, t0.canon);
                 if (kind != B2C_INPLACE_NO)
-                    in_place = b2c_inplace_step(A.P, W, t + t0_frames, kind, id0, A.tok_lp[base], static_cast<int>(nxt.cnt));
+                    in_place = b2c_inplace_step(A.P, W, t + t0_frames, kind, id0, rec.lp0, static_cast<int>(nxt.cnt));
             }
             prev_single = single;
             if (in_place) {
@@ -273,12 +273,21 @@ B2C_HD void b2c_beam_block(const B2cBeamArgs& A, int slot, u8* smem) {
 // latency-first kernel variants (beam_width <= 128): candidate capacity x resident CTAs per SM.  A is the
 // latency choice (batch resident at once); B and C trade capacity for residency when the batch is larger
 // than the resident set and the candidate histogram of the previous call says the frames fit.
-typedef B2cFastSmem<128, 1024> B2cFastSmemA;      // 2 CTAs per SM
-typedef B2cFastSmem<128, 512> B2cFastSmemB;       // 3 CTAs per SM
-typedef B2cFastSmem<128, 256> B2cFastSmemC;       // 4 CTAs per SM
+// Each variant exists with the label table resident in shared memory (alphabets of up to B2C_FAST_LT labels: runs of
+// in-place frames enabled) and with per-frame label staging (larger alphabets).
+#define B2C_FAST_LT 64
+typedef B2cFastSmem<128, 1024, B2C_FAST_LT> B2cFastSmemA;      // 2 CTAs per SM
+typedef B2cFastSmem<128, 512, B2C_FAST_LT> B2cFastSmemB;       // 3 CTAs per SM
+typedef B2cFastSmem<128, 256, B2C_FAST_LT> B2cFastSmemC;       // 4 CTAs per SM
 static const u32 kV5Cap[3] = {1024, 512, 256};
 static const int kV5Occ[3] = {2, 3, 4};
-static const size_t kV5Smem[3] = {sizeof(B2cFastSmemA), sizeof(B2cFastSmemB), sizeof(B2cFastSmemC)};
+// [variant][0: staged labels, 1: resident table]
+static const size_t kV5Smem[3][2] = {{sizeof(B2cFastSmem<128, 1024, 0>), sizeof(B2cFastSmemA)},
+                                     {sizeof(B2cFastSmem<128, 512, 0>), sizeof(B2cFastSmemB)},
+                                     {sizeof(B2cFastSmem<128, 256, 0>), sizeof(B2cFastSmemC)}};
+static_assert(2 * (sizeof(B2cFastSmemA) + 1024) <= 228 * 1024, "variant A: 2 CTAs per SM");
+static_assert(3 * (sizeof(B2cFastSmemB) + 1024) <= 228 * 1024, "variant B: 3 CTAs per SM");
+static_assert(4 * (sizeof(B2cFastSmemC) + 1024) <= 228 * 1024, "variant C: 4 CTAs per SM");
 
 // half-precision logits (B2C_DTYPE_F16 / B2C_DTYPE_BF16) travel over PCIe as they are and are widened to float32 on the
 // device, exactly (every half / bfloat16 value is a float32 value); the path then computes as for float32 input
@@ -315,10 +324,10 @@ B2C_HD void b2c_widen_range(const u16* src, float* dst, u64 begin, u64 end, u64 
 __global__ void __launch_bounds__(256) b2c_widen_kernel(const u16* src, float* dst, u64 n, int bf16) {
     b2c_widen_range(src, dst, static_cast<u64>(blockIdx.x) * blockDim.x + threadIdx.x, n, static_cast<u64>(gridDim.x) * blockDim.x, bf16);
 }
-template <int WC, int CAP, int OCC>
+template <int WC, int CAP, int OCC, int LT>
 __global__ void __launch_bounds__(B2C_FAST_NT, OCC) b2c_beam_fast_kernel(const B2cBeamArgs A) {
     extern __shared__ __align__(16) u8 b2c_smem[];
-    b2c_beam_block_fast<WC, CAP>(A, static_cast<int>(blockIdx.x), b2c_smem);
+    b2c_beam_block_fast<WC, CAP, LT>(A, static_cast<int>(blockIdx.x), b2c_smem);
 }
 // device-resident utterances that are not adjacent in memory (a padded [B, T, V] batch with lengths, a list
 // of separate tensors): ONE launch packs their valid rows, instead of one cudaMemcpyAsync per utterance
@@ -653,24 +662,32 @@ static int launch_beam(b2c_decoder* d, const B2cBeamArgs& A, int slots, bool fas
     (void)per_sm;
     (void)threads;
     std::vector<u8> smem(A.L.smem_bytes + 64);
+    const bool table = A.P.V <= B2C_FAST_LT;
     for (int s = 0; s < slots; ++s) {
-        if (v5 == 0) b2c_beam_block_fast<128, 1024>(A, s, smem.data());
-        else if (v5 == 1) b2c_beam_block_fast<128, 512>(A, s, smem.data());
-        else if (v5 == 2) b2c_beam_block_fast<128, 256>(A, s, smem.data());
+        if (v5 == 0 && table) b2c_beam_block_fast<128, 1024, B2C_FAST_LT>(A, s, smem.data());
+        else if (v5 == 0) b2c_beam_block_fast<128, 1024, 0>(A, s, smem.data());
+        else if (v5 == 1 && table) b2c_beam_block_fast<128, 512, B2C_FAST_LT>(A, s, smem.data());
+        else if (v5 == 1) b2c_beam_block_fast<128, 512, 0>(A, s, smem.data());
+        else if (v5 == 2 && table) b2c_beam_block_fast<128, 256, B2C_FAST_LT>(A, s, smem.data());
+        else if (v5 == 2) b2c_beam_block_fast<128, 256, 0>(A, s, smem.data());
         else if (fast) b2c_beam_block<true>(A, s, smem.data());
         else b2c_beam_block<false>(A, s, smem.data());
     }
 #else
     const int smem = static_cast<int>(A.L.smem_bytes);
-#define B2C_LAUNCH_V5(CAP, OCC)                                                                                         \
+#define B2C_LAUNCH_V5(CAP, OCC, LT)                                                                                     \
     do {                                                                                                               \
-        CUDA_OK(cudaFuncSetAttribute(b2c_beam_fast_kernel<128, CAP, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-        b2c_beam_fast_kernel<128, CAP, OCC><<<slots, B2C_FAST_NT, A.L.smem_bytes, stream>>>(A);                      \
+        CUDA_OK(cudaFuncSetAttribute(b2c_beam_fast_kernel<128, CAP, OCC, LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+        b2c_beam_fast_kernel<128, CAP, OCC, LT><<<slots, B2C_FAST_NT, A.L.smem_bytes, stream>>>(A);                  \
     } while (0)
     if (v5 >= 0) {
-        if (v5 == 0) B2C_LAUNCH_V5(1024, 2);
-        else if (v5 == 1) B2C_LAUNCH_V5(512, 3);
-        else B2C_LAUNCH_V5(256, 4);
+        const bool table = A.P.V <= B2C_FAST_LT;
+        if (v5 == 0 && table) B2C_LAUNCH_V5(1024, 2, B2C_FAST_LT);
+        else if (v5 == 0) B2C_LAUNCH_V5(1024, 2, 0);
+        else if (v5 == 1 && table) B2C_LAUNCH_V5(512, 3, B2C_FAST_LT);
+        else if (v5 == 1) B2C_LAUNCH_V5(512, 3, 0);
+        else if (table) B2C_LAUNCH_V5(256, 4, B2C_FAST_LT);
+        else B2C_LAUNCH_V5(256, 4, 0);
         CUDA_OK(cudaGetLastError());
         return 0;
     }
@@ -1145,7 +1162,7 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     if (half_in && !contiguous_dev && d->d_raw.ensure(std::max<u64>(total_frames * V * esz_in, 16))) return B2C_E_NOMEM;
     const size_t meta_bytes = al16(8ull * n_utts) + 3 * al16(4ull * n_utts) + 64 + al16(8ull * (n_utts + 1)) + al16(8ull * n_utts);
     if (d->d_meta.ensure(meta_bytes) || d->h_meta.ensure(meta_bytes)) return B2C_E_NOMEM;
-    if (d->d_tok_start.ensure(8 * (total_frames + 1)) || d->d_tok_ids.ensure(2 * n_entries) ||
+    if (d->d_tok_start.ensure(sizeof(B2cFrameRec) * (total_frames + 1)) || d->d_tok_ids.ensure(4 * n_entries) ||
         d->d_tok_lp.ensure(8 * n_entries) || d->d_rowsum.ensure(std::max<u64>(8 * total_frames, 16)) ||
         d->d_isprob.ensure(4ull * n_utts))
         return B2C_E_NOMEM;
@@ -1292,7 +1309,7 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     PA.n_utts = n_utts;
     PA.total_frames = total_frames;
     PA.tok_rec = d->d_tok_start.as<B2cFrameRec>();
-    PA.tok_ids = d->d_tok_ids.as<u16>();
+    PA.tok_ids = d->d_tok_ids.as<u32>();
     PA.tok_lp = d->d_tok_lp.as<double>();
     PA.rowsum = d->d_rowsum.p;
     PA.set_scratch = d->d_set.as<u16>();
@@ -1395,7 +1412,7 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
         // the whole fast list; wider frames inside it go through its out-of-line HBM-tier step
         const bool force_v5 = std::getenv("B200CTC_FORCE_V5") != nullptr;      // tests: exercise the out-of-line step
         use_v5 = top >= 0 && opts->beam_width <= 128 && (force_v5 || kCaps[v5_top >= 0 ? v5_top : top] <= 1024) &&
-                 sizeof(B2cFastSmemA) + 1024 <= d->smem_optin && std::getenv("B200CTC_NO_V5") == nullptr;
+                 kV5Smem[0][1] + 1024 <= d->smem_optin && std::getenv("B200CTC_NO_V5") == nullptr;
         // more utterances than variant A keeps resident: trade capacity for residency if the previous call's
         // histogram says that all but 0.4% of the frames fit (hint_over[q] = frames with > 128 << q candidates)
         if (use_v5 && hint_ok && n_fast > d->n_sm * kV5Occ[0] && std::getenv("B200CTC_V5_VARIANT") == nullptr) {
@@ -1462,8 +1479,10 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
             // beam tables of capacity 128; the HBM tier always exists (frames with > B2C_FAST_KS tokens use it too)
             const u32 cap5 = kV5Cap[ln.v5];
             ln.threads = B2C_FAST_NT;
-            ln.L = make_layout(128, V, tmax, full, smem_budget, cap5, std::max<u64>(worst_m, cap5 + 1), B2C_FAST_NW);
-            ln.L.smem_bytes = static_cast<u32>(kV5Smem[ln.v5]);
+            // backtrack arena: fixed node ids of the frame steps below 128 * T, the out-of-line step allocates above
+            ln.L = make_layout(128, V, tmax, full, smem_budget, cap5, std::max<u64>(worst_m, cap5 + 1), B2C_FAST_NW,
+                               128ull * static_cast<u64>(std::max(tmax, 1)));
+            ln.L.smem_bytes = static_cast<u32>(kV5Smem[ln.v5][V <= B2C_FAST_LT ? 1 : 0]);
             ln.per_sm = kV5Occ[ln.v5];
         } else {
         ln.threads = cls < kNumCaps ? threads_of(cls) : 128;

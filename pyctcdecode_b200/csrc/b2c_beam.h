@@ -367,7 +367,7 @@ B2C_HDN void b2c_commit_text(B2cParams P, B2cText* arena, u32 text_cap, u32* tex
 B2C_HDN double b2c_sum_log_scores_ool(double s1, double s2) { return b2c_sum_log_scores(s1, s2); }
 
 // BPE only: who consumes force_next_break (decoder.py:442,474-482); contains two block barriers
-B2C_HDN void b2c_bpe_force(const B2cTok* toks, const u16* tk_id, int K, const u16* last_tok, u32 n, u32* ffirst, u8* fall,
+B2C_HDN void b2c_bpe_force(const B2cTok* toks, const u32* tk_id, int K, const u16* last_tok, u32 n, u32* ffirst, u8* fall,
                            u32* force_break) {
     // tk_id == nullptr: `toks` is already the frame's token list (staged records of the fast kernel)
     B2C_FOR(k, K) {
@@ -549,7 +549,7 @@ B2C_HD void b2c_block_add_u32(u32 v, u32* target) {
 // one new beam: rank r of this frame becomes beam j of the next frame
 template <class Tier>
 B2C_HD void b2c_commit_one(const B2cParams& P, const B2cWork& W, const Tier& C, const B2cBeamTab& cur, const B2cBeamTab& nx,
-                           const u16* tk_id, u32 n, float rcp_n, int t, u32 j, u32 r, u32 flags) {
+                           const u32* tk_id, u32 n, float rcp_n, int t, u32 j, u32 r, u32 flags) {
     B2cScalars* sc = W.sc;
     const u32 i = W.ord[r];
     const u32 last = C.clast[i];
@@ -582,7 +582,7 @@ B2C_HD void b2c_commit_one(const B2cParams& P, const B2cWork& W, const Tier& C, 
         if (id < W.chain_cap) {
             B2cChain c;
             c.parent = chain;
-            c.tok = tk_id[k];
+            c.tok = static_cast<u16>(tk_id[k]);
             c.kind = type == 3 ? B2C_CK_CONT : (type == 2 ? B2C_CK_SPACE : B2C_CK_BPE);
             c.has_word = word_len > 0 ? 1 : 0;
             c.ws = ps0;
@@ -621,7 +621,7 @@ B2C_HD void b2c_commit_one(const B2cParams& P, const B2cWork& W, const Tier& C, 
 // prune table are clear (previous frame's phase D / b2c_utt_begin).
 // -----------------------------------------------------------------------------------------
 template <bool kFast>
-B2C_HD void b2c_frame_step(const B2cParams& P, B2cWork& W, int t, const u16* tk_id, const double* tk_lp, int K, int K_next) {
+B2C_HD void b2c_frame_step(const B2cParams& P, B2cWork& W, int t, const u32* tk_id, const double* tk_lp, int K, int K_next) {
     B2cScalars* sc = W.sc;
     const u32 n = sc->n_beams;
     const u32 M = n * static_cast<u32>(K);
@@ -955,7 +955,7 @@ B2C_HDN bool b2c_inplace_step(B2cParams P, B2cWork W, int t, int kind, u16 tok_i
 // utterance, flat logits) take this out-of-line copy that works on the HBM tier through generic
 // pointers.  It operates on a COPY of the work descriptor so that the hot path's descriptor never
 // has its address taken (which would push it to local memory).
-B2C_HDN void b2c_frame_step_slow(B2cParams P, B2cLayout L, u8* smem, u8* g, int parity, int t, const u16* tk_id,
+B2C_HDN void b2c_frame_step_slow(B2cParams P, B2cLayout L, u8* smem, u8* g, int parity, int t, const u32* tk_id,
                                  const double* tk_lp, int K, int K_next) {
     B2cWork Wc;
     b2c_make_work(L, smem, g, parity, true, Wc);

@@ -6,9 +6,15 @@
 // of a frame, not throughput.  Compared with the general kernel this variant therefore
 //   * uses a compile-time shared-memory layout (B2cFastSmem): every array address is
 //     base + constant, no descriptor of generic pointers lives in registers or local memory;
-//   * stages the token list of frame t+1 (ids, log-probs AND the per-label records) in shared
-//     memory while frame t runs (two-deep register pipeline), so no global load is on the
-//     critical path of a frame;
+//   * keeps the token lists of the next frames in shared-memory RINGS filled by asynchronous copies
+//     (cp.async / LDGSTS, no register staging): 16-byte frame records (token count + first token inline) 18-32
+//     frames ahead, token ids / log-probs up to 7 frames ahead, issued at the top of an iteration and waited for
+//     just before its closing barrier -- no global load is on the critical path of a frame and no barrier has
+//     a register-destined load in flight; for small alphabets (V <= 64) the per-label records live in shared
+//     memory for the whole launch;
+//   * handles RUNS of single-token frames (blank / held symbol / plain characters) in one step: the records of
+//     the next frames are already in the ring, so R frames cost one round of bookkeeping, R dependent additions
+//     per beam and one vote (b2c_fast_run_step);
 //   * enumerates candidates as (token k outer, beam b = thread inner): no index division, the
 //     token record is a warp-uniform shared-memory broadcast;
 //   * stores each candidate's own logit sum and (beam, token) pair, so the fold / fusion / commit
@@ -36,7 +42,10 @@
 #pragma once
 #include "b2c_beam.h"
 
-#define B2C_FAST_KS 32          // staged tokens per frame
+#define B2C_FAST_KS 32          // most tokens of a frame any variant stages (larger frames: out-of-line step)
+#define B2C_FAST_HR 32          // frame-record ring (frames)
+#define B2C_FAST_TR 8           // token ring (frames)
+#define B2C_FAST_RMAX 6         // longest run of in-place frames handled by one step (<= B2C_FAST_TR - 2)
 #ifndef B2C_FAST_NT
 #define B2C_FAST_NT 128         // threads per CTA
 #endif
@@ -44,8 +53,14 @@
 
 #if defined(__CUDA_ARCH__)
 #define B2C_LAST_THREAD if (threadIdx.x == blockDim.x - 1)
+// work for ONE warp -- the last one, which holds the slots >= 96 and has the fewest live beams -- so that the other
+// warps walk straight into the frame step: items strided over its lanes
+#define B2C_IN_LAST_WARP if ((threadIdx.x >> 5) == B2C_FAST_NW - 1)
+#define B2C_FOR_LANES(i, n) for (int i = static_cast<int>(threadIdx.x & 31); i < static_cast<int>(n); i += 32)
 #else
 #define B2C_LAST_THREAD if (true)
+#define B2C_IN_LAST_WARP if (true)
+#define B2C_FOR_LANES(i, n) B2C_FOR(i, n)
 #endif
 
 constexpr u32 b2c_pt_cap_c(int W) {
@@ -63,14 +78,48 @@ struct B2cFastTab {          // one beam table (same fields as B2cBeamTab)
     u16 last_tok[WC], part_len[WC];
 };
 
-template <int WC, int CAP>
+// asynchronous global -> shared copies (LDGSTS); hostsim: plain copies
+B2C_HD void b2c_cp_async4(void* dst_smem, const void* src) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(static_cast<u32>(__cvta_generic_to_shared(dst_smem))), "l"(src) : "memory");
+#else
+    *static_cast<u32*>(dst_smem) = *static_cast<const u32*>(src);
+#endif
+}
+B2C_HD void b2c_cp_async8(void* dst_smem, const void* src) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(static_cast<u32>(__cvta_generic_to_shared(dst_smem))), "l"(src) : "memory");
+#else
+    *static_cast<u64*>(dst_smem) = *static_cast<const u64*>(src);
+#endif
+}
+B2C_HD void b2c_cp_async16(void* dst_smem, const void* src) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(static_cast<u32>(__cvta_generic_to_shared(dst_smem))), "l"(src) : "memory");
+#else
+    static_cast<u64*>(dst_smem)[0] = static_cast<const u64*>(src)[0];
+    static_cast<u64*>(dst_smem)[1] = static_cast<const u64*>(src)[1];
+#endif
+}
+B2C_HD void b2c_cp_async_wait_all() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+}
+
+// LT: entries of the shared-memory label table (V <= LT: the table is resident, runs of in-place frames are
+// enabled); 0: labels are staged per frame from global memory (large alphabets)
+template <int WC, int CAP, int LT>
 struct B2cFastSmem {
     static constexpr u32 HT = 2u * CAP;               // grouping table slots
     static constexpr u32 PT = b2c_pt_cap_c(WC);        // history-prune table slots
+    static constexpr int KR = CAP >= 1024 ? 32 : 16;   // tokens per frame the rings hold (wider frames: out-of-line step)
+    static constexpr int LTN = LT > 0 ? LT : 1;
     B2cScalars sc;
     u32 ticket;                                       // work-queue ticket of this CTA
     u32 holes;                                        // the current beam table has history-pruned slots (see b2c_fast_step)
-    u32 cheap_bad;                                    // a thread's exactness check of b2c_fast_cheap_step failed (rare)
+    u32 cheap_bad;                                    // a thread's exactness check of b2c_fast_scored_step failed (rare)
+    u32 run_fail;                                     // b2c_fast_run_step: first frame of the run whose exactness check failed
     u32 wmask[B2C_FAST_NW];                           // per warp: live slots of the current table (b2c_fast_sorted_step)
 #if defined(B2C_PHASE_CLOCKS)
     u64 pclk[32];                                     // profiling builds: cycles between marks, thread 0
@@ -94,12 +143,14 @@ struct B2cFastSmem {
     u32 cslot[CAP], cnext[CAP], clast[CAP];
     u32 cbk[CAP];            // beam | token index << 16
     u32 ht_idx[HT], ht_min[HT], ht_max[HT], ht_cnt[HT];
-    // staged token lists of the current / next frame
-    B2cTok stok[2][B2C_FAST_KS];
-    double slp[2][B2C_FAST_KS];
-    u16 sid[2][B2C_FAST_KS];
-    u32 ffirst[B2C_FAST_KS];     // BPE force_next_break side arrays
-    u8 fall[B2C_FAST_KS];
+    // token lists: label records of the current / next frame, rings of frame records and of (id, log-prob) lists
+    alignas(16) B2cTok stok[2][LT > 0 ? 1 : KR];   // staged label records (large alphabets only)
+    alignas(16) B2cFrameRec rh[B2C_FAST_HR];
+    alignas(16) double rlp[B2C_FAST_TR][KR];
+    alignas(16) u32 rid[B2C_FAST_TR][KR];
+    alignas(16) B2cTok ltab[LTN];
+    u32 ffirst[KR];              // BPE force_next_break side arrays
+    u8 fall[KR];
 };
 
 template <int WC>
@@ -113,18 +164,18 @@ B2C_HD void b2c_fast_tab_view(B2cFastTab<WC>& t, B2cBeamTab& v) {
 
 // descriptor for the general helpers (b2c_utt_begin, b2c_finalize, the out-of-line slow step);
 // `slow`: hide the shared-memory tier so that the general frame step works on the HBM tier
-template <int WC, int CAP>
-B2C_HD void b2c_fast_work(B2cFastSmem<WC, CAP>& S, const B2cLayout& L, u8* g, int par, bool slow, B2cWork& W) {
+template <int WC, int CAP, int LT>
+B2C_HD void b2c_fast_work(B2cFastSmem<WC, CAP, LT>& S, const B2cLayout& L, u8* g, int par, bool slow, B2cWork& W) {
     W.sc = &S.sc;
     b2c_fast_tab_view(S.tab[par], W.cur);
     b2c_fast_tab_view(S.tab[par ^ 1], W.nxt);
     W.phk = S.phk; W.ord = S.ord; W.pslot = S.pslot;
-    W.pt_cap = B2cFastSmem<WC, CAP>::PT;
+    W.pt_cap = B2cFastSmem<WC, CAP, LT>::PT;
     W.pt_idx = S.pt_idx; W.pt_min = S.pt_min;
     W.bcnt = S.bcnt; W.bhead = S.bhead; W.bpre = &S.bpre[0][0];
     B2cCandTier& c = W.tier_s;
     c.cap = slow ? 0u : static_cast<u32>(CAP);
-    c.ht_cap = B2cFastSmem<WC, CAP>::HT;
+    c.ht_cap = B2cFastSmem<WC, CAP, LT>::HT;
     c.ckey = S.ckey; c.cfold = S.cfold; c.cth = nullptr; c.cph = S.cph;
     c.cmeta = S.cmeta; c.cslot = S.cslot; c.cnext = S.cnext; c.clast = S.clast;
     c.ht_idx = S.ht_idx; c.ht_min = S.ht_min; c.ht_max = S.ht_max; c.ht_cnt = S.ht_cnt;
@@ -143,6 +194,14 @@ B2C_HD void b2c_fast_work(B2cFastSmem<WC, CAP>& S, const B2cLayout& L, u8* g, in
     for (int q = 0; q < 16; ++q) W.clk[q] = 0;
     W.clk_last = 0;
 #endif
+}
+
+// label record of token k of the current frame: straight from the resident table (small alphabets: one more
+// dependent shared-memory load, no per-frame staging), or from the staged copy (large alphabets)
+template <int WC, int CAP, int LT>
+B2C_HD const B2cTok& b2c_fast_tok(const B2cFastSmem<WC, CAP, LT>& S, int sb, int slot, int k) {
+    if (LT > 0) return S.ltab[S.rid[slot][k]];
+    return S.stok[sb][k];
 }
 
 // per-warp maxima go to the warp's own slot (no atomics); readers combine the slots after the barrier
@@ -215,9 +274,9 @@ B2C_HD void b2c_bucket_scan_warp_v(const u32* bcnt, u32* pre) {
 
 // candidate i (a group leader) becomes beam j of the next frame (decoder.py:452-534 metadata); called by the
 // thread that owns the candidate, inside the ranking loop
-template <int WC, int CAP>
-B2C_HD void b2c_fast_commit(const B2cParams& P, B2cFastSmem<WC, CAP>& S, const B2cFastTab<WC>& cur, B2cFastTab<WC>& nx,
-                            B2cChain* chain_arena, u32 chain_cap, B2cText* text_arena, u32 text_cap, int sb, int t, u32 j, u32 i,
+template <int WC, int CAP, int LT>
+B2C_HD void b2c_fast_commit(const B2cParams& P, B2cFastSmem<WC, CAP, LT>& S, const B2cFastTab<WC>& cur, B2cFastTab<WC>& nx,
+                            B2cChain* chain_arena, B2cText* text_arena, u32 text_cap, int sb, int slot, int t, u32 j, u32 i,
                             u32 last, u32 flags) {
     const u32 bk = S.cbk[last];
     const u32 bl = bk & 0xFFFFu, k = bk >> 16;
@@ -237,29 +296,25 @@ B2C_HD void b2c_fast_commit(const B2cParams& P, B2cFastSmem<WC, CAP>& S, const B
     // partial_frames (decoder.py:454-461,495,513,519-523)
     const int ps0 = cur.pf_s[bl], pe0 = cur.pf_e[bl];
     int pfs, pfe;
-    if (type == 0) { pfs = ps0; pfe = (S.stok[sb][k].flags & B2C_TF_BLANK) ? pe0 : t + 1; }
+    if (type == 0) { pfs = ps0; pfe = (b2c_fast_tok<WC, CAP, LT>(S, sb, slot, static_cast<int>(k)).flags & B2C_TF_BLANK) ? pe0 : t + 1; }
     else if (type == 1) { pfs = t; pfe = t + 1; }
     else if (type == 2) { pfs = -1; pfe = -1; }
     else { pfs = ps0 < 0 ? t : ps0; pfe = t + 1; }
     nx.pf_s[j] = pfs;
     nx.pf_e[j] = pfe;
-    // backtrack chain
+    // backtrack chain: the node of (frame t, new slot j) has the fixed id t * WC + j -- no allocation counter
     u32 chain = cur.chain[bl];
     if (type != 0) {
-        const u32 id = b2c_atomic_add_u32(&S.sc.chain_used, 1u);
-        if (id < chain_cap) {
-            B2cChain c;
-            c.parent = chain;
-            c.tok = S.sid[sb][k];
-            c.kind = type == 3 ? B2C_CK_CONT : (type == 2 ? B2C_CK_SPACE : B2C_CK_BPE);
-            c.has_word = word_len > 0 ? 1 : 0;
-            c.ws = ps0;
-            c.we = pe0;
-            chain_arena[id] = c;
-            chain = id;
-        } else {
-            b2c_atomic_or_u32(&S.sc.status, B2C_ERR_CHAIN_FULL);
-        }
+        const u32 id = static_cast<u32>(t) * static_cast<u32>(WC) + j;
+        B2cChain c;
+        c.parent = chain;
+        c.tok = static_cast<u16>(S.rid[slot][k]);
+        c.kind = type == 3 ? B2C_CK_CONT : (type == 2 ? B2C_CK_SPACE : B2C_CK_BPE);
+        c.has_word = word_len > 0 ? 1 : 0;
+        c.ws = ps0;
+        c.we = pe0;
+        chain_arena[id] = c;
+        chain = id;
     }
     nx.chain[j] = chain;
     // text level
@@ -300,10 +355,10 @@ B2C_HD void b2c_fast_commit(const B2cParams& P, B2cFastSmem<WC, CAP>& S, const B
 // hold the number of slots and the best score key of the previous frame (per-warp maxima).
 // Invariants on entry: grouping table clear; prune table = entries pslot[0 .. n) iff S.holes.
 // -----------------------------------------------------------------------------------------
-template <int WC, int CAP>
-B2C_HD void b2c_fast_step(const B2cParams& P, B2cFastSmem<WC, CAP>& S, B2cChain* chain_arena, u32 chain_cap, B2cText* text_arena,
-                          u32 text_cap, int par, int t, int sb, int K) {
-    typedef B2cFastSmem<WC, CAP> SM;
+template <int WC, int CAP, int LT>
+B2C_HD void b2c_fast_step(const B2cParams& P, B2cFastSmem<WC, CAP, LT>& S, B2cChain* chain_arena, B2cText* text_arena,
+                          u32 text_cap, int par, int t, int sb, int slot, int K) {
+    typedef B2cFastSmem<WC, CAP, LT> SM;
     B2cFastTab<WC>& cur = S.tab[par];
     B2cFastTab<WC>& nx = S.tab[par ^ 1];
     const u32 n = b2c_max_slots(S.wtop);                       // slots of the current table (live + dead)
@@ -323,7 +378,8 @@ B2C_HD void b2c_fast_step(const B2cParams& P, B2cFastSmem<WC, CAP>& S, B2cChain*
             }
             B2C_SYNC();
         }
-        b2c_bpe_force(S.stok[sb], nullptr, K, cur.last_tok, n, S.ffirst, S.fall, &S.sc.force_break);
+        if (LT > 0) b2c_bpe_force(S.ltab, S.rid[slot], K, cur.last_tok, n, S.ffirst, S.fall, &S.sc.force_break);
+        else b2c_bpe_force(S.stok[sb], nullptr, K, cur.last_tok, n, S.ffirst, S.fall, &S.sc.force_break);
     }
 
     // ---- phase A: expand (decoder.py:447-534), merge key, grouping ---------------------------------
@@ -338,7 +394,7 @@ B2C_HD void b2c_fast_step(const B2cParams& P, B2cFastSmem<WC, CAP>& S, B2cChain*
         for (int k = 0; k < K; ++k) {
             const u32 i = static_cast<u32>(k) * n + static_cast<u32>(b);
             if (!live) { S.cslot[i] = 0; continue; }           // never a group leader (phase B), key 0 in phase C
-            const B2cTok ti = S.stok[sb][k];
+            const B2cTok ti = b2c_fast_tok<WC, CAP, LT>(S, sb, slot, k);
             u64 th = th0;
             u64 nph;
             u32 nplen, type;
@@ -356,7 +412,7 @@ B2C_HD void b2c_fast_step(const B2cParams& P, B2cFastSmem<WC, CAP>& S, B2cChain*
             S.cph[i] = nph | (static_cast<u64>(type) << 61);
             S.cmeta[i] = (nplen & 0xFFFFu) | (static_cast<u32>(ti.canon) << 16);
             S.cbk[i] = static_cast<u32>(b) | (static_cast<u32>(k) << 16);
-            S.cfold[i] = lg + S.slp[sb][k];
+            S.cfold[i] = lg + S.rlp[slot][k];
             const u64 key = b2c_fast_key(th, nph, nplen, ti.canon);
             S.ckey[i] = key;
             b2c_fence_block();
@@ -486,7 +542,7 @@ B2C_HD void b2c_fast_step(const B2cParams& P, B2cFastSmem<WC, CAP>& S, B2cChain*
                 S.pslot[rank] = slot;
                 b2c_atomic_min_u32(&S.pt_min[slot], rank);
             }
-            b2c_fast_commit(P, S, cur, nx, chain_arena, chain_cap, text_arena, text_cap, sb, t, rank, static_cast<u32>(i), last, flags);
+            b2c_fast_commit(P, S, cur, nx, chain_arena, text_arena, text_cap, sb, slot, t, rank, static_cast<u32>(i), last, flags);
         }
         b2c_warp_max_u32_slot(my_top, S.wtop);         // the selected ranks are exactly 0 .. max(wtop)-1
     }
@@ -524,79 +580,137 @@ B2C_HD int b2c_fast_cheap_kind(u32 flags, u32 prev_single, const B2cTok& ti) {
     return (flags & B2C_FL_PSCORE) ? B2C_CHEAP_T3P : B2C_CHEAP_T3;
 }
 
-// returns false (state untouched) when the exactness check failed
-template <int WC, int CAP>
-B2C_HD bool b2c_fast_cheap_step(const B2cParams& P, B2cFastSmem<WC, CAP>& S, B2cChain* chain_arena, u32 chain_cap, int par, int t,
-                                int sb, int kind) {
+// label record of the first token of frame f (a frame whose record is in the ring): the resident table for small
+// alphabets; with per-frame staging (LT == 0) only the CURRENT frame's record is available (stok[sb][0])
+template <int WC, int CAP, int LT>
+B2C_HD const B2cTok& b2c_fast_tok0(const B2cParams& P, const B2cFastSmem<WC, CAP, LT>& S, int f, int sb) {
+    (void)P;
+    if (LT > 0) return S.ltab[S.rh[f & (B2C_FAST_HR - 1)].id0];
+    return S.stok[sb][0];
+}
+
+// A RUN of R >= 1 consecutive in-place frames t .. t+R-1 (each selects one token, kinds T0 / T3 as above; the caller
+// has established R from the frame records in the ring).  Per slot: R dependent additions, the exactness check of
+// every frame (threshold; with LM / hotwords also the order against the next slot), ONE vote, then the R updates
+// applied from registers.  Returns the number of frames done: R, or fewer when a check failed at frame t + r (the
+// frames before it are applied, frame t + r is left to the general step), 0 = state untouched.
+// With LM / hotwords only T0 frames are in a run: the text-level and partial-word scores of a slot are constants.
+template <int WC, int CAP, int LT>
+B2C_HD int b2c_fast_run_step(const B2cParams& P, B2cFastSmem<WC, CAP, LT>& S, B2cChain* chain_arena, int par, int t, int sb, int R) {
+    constexpr int HM = B2C_FAST_HR - 1;
     B2cFastTab<WC>& cur = S.tab[par];
     const u32 n = b2c_max_slots(S.wtop);
     const u32 flags = S.sc.flags;
     const bool has_lm = (flags & B2C_FL_LM) != 0;
     const bool holes = S.holes != 0;
-    const B2cTok ti = S.stok[sb][0];
-    const double p = S.slp[sb][0];
-    // slot 0 holds rank 0 = the best score of the previous frame, and it is always live.  Without LM and
-    // hotwords lm_score is logit_score + (+-0) + 0: adding the same p to every beam keeps the order (rounding is
-    // monotone, equal results keep their slot order), so only the threshold has to be re-checked.
     const bool plain = (flags & B2C_FL_PSCORE) == 0;
-    const double top = plain ? (cur.logit[0] + p) + 0.0
-                             : b2c_combine_score(has_lm, cur.logit[0] + p, cur.lm_hw[0], cur.pscore[0], cur.part_len[0]);
-    const double thr = top + P.prune_logp;
+    const double prune = P.prune_logp;
+    // slot 0 holds rank 0 = the best score of the previous frame, and it is always live.  Without LM and hotwords
+    // lm_score is logit_score + (+-0) + 0: adding the same p to every beam keeps the order (rounding is monotone,
+    // equal results keep their slot order), so only the threshold has to be re-checked.
+    const double lmhw0 = cur.lm_hw[0], ps0s = cur.pscore[0];
+    const u32 plen0 = cur.part_len[0];
     B2C_FOR(b, n) {
+        double l = cur.logit[b], l0 = cur.logit[0];
+        int fail = R;
         if (plain) {
-            if (!((cur.logit[b] + p) + 0.0 >= thr)) S.cheap_bad = 1;
-            continue;
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+            for (int j = 0; j < R; ++j) {
+                const double p = S.rh[(t + j) & HM].lp0;
+                l = l + p;
+                l0 = l0 + p;
+                const double thr = (l0 + 0.0) + prune;
+                if (!((l + 0.0) >= thr) && j < fail) fail = j;
+            }
+        } else {
+            const bool has_next = static_cast<u32>(b) + 1 < n;
+            const u32 bn = has_next ? static_cast<u32>(b) + 1 : static_cast<u32>(b);
+            double ln = cur.logit[bn];
+            const double lmhw = cur.lm_hw[b], ps = cur.pscore[b], lmhwn = cur.lm_hw[bn], psn = cur.pscore[bn];
+            const u32 plen = cur.part_len[b], plenn = cur.part_len[bn];
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+            for (int j = 0; j < R; ++j) {
+                const double p = S.rh[(t + j) & HM].lp0;
+                l = l + p;
+                l0 = l0 + p;
+                ln = ln + p;
+                const double top = b2c_combine_score(has_lm, l0, lmhw0, ps0s, plen0);
+                const double mine = b2c_combine_score(has_lm, l, lmhw, ps, plen);
+                bool ok = mine >= top + prune;
+                if (has_next) ok = ok && mine >= b2c_combine_score(has_lm, ln, lmhwn, psn, plenn);
+                if (!ok && j < fail) fail = j;
+            }
         }
-        const double mine = b2c_combine_score(has_lm, cur.logit[b] + p, cur.lm_hw[b], cur.pscore[b], cur.part_len[b]);
-        bool ok = mine >= thr;
-        if (static_cast<u32>(b) + 1 < n) {
-            const double next = b2c_combine_score(has_lm, cur.logit[b + 1] + p, cur.lm_hw[b + 1], cur.pscore[b + 1], cur.part_len[b + 1]);
-            ok = ok && mine >= next;
-        }
-        if (!ok) S.cheap_bad = 1;
+        if (fail < R) b2c_atomic_min_u32(&S.run_fail, static_cast<u32>(fail));
     }
     B2C_FMARK(17);
     B2C_SYNC();
     B2C_FMARK(18);
-    if (S.cheap_bad) {      // block-uniform
+    int Rok = R;
+    if (S.run_fail != B2C_NONE_U32) {      // block-uniform, rare
+        Rok = static_cast<int>(S.run_fail);
         B2C_SYNC();
-        B2C_LEADER { S.cheap_bad = 0; }
-        return false;
+        B2C_LEADER { S.run_fail = B2C_NONE_U32; }
+        if (Rok == 0) return 0;
     }
-    const bool blank = (ti.flags & B2C_TF_BLANK) != 0;
+    double top = 0.0;
     B2C_FOR(b, n) {
         // dead (history-pruned) slots keep their place in the score order: only their logit follows
-        cur.logit[b] = cur.logit[b] + p;
+        double l = cur.logit[b];
         const bool live = !holes || S.pt_min[S.pslot[b]] == static_cast<u32>(b);
-        if (!live) continue;
-        cur.last_tok[b] = ti.canon;
-        if (kind == B2C_CHEAP_T0) {
-            if (!blank) cur.pf_e[b] = t + 1;
-        } else {
-            const int ps0 = cur.pf_s[b], pe0 = cur.pf_e[b];
-            cur.part_hash[b] = b2c_hash_append(cur.part_hash[b], ti.raw_hash, ti.raw_pow);
-            cur.part_len[b] = static_cast<u16>(cur.part_len[b] + ti.raw_nchars);
-            if (ps0 < 0) cur.pf_s[b] = t;
-            cur.pf_e[b] = t + 1;
-            const u32 id = b2c_atomic_add_u32(&S.sc.chain_used, 1u);
-            if (id < chain_cap) {
+        u64 ph = cur.part_hash[b];
+        u32 plen = cur.part_len[b], chain = cur.chain[b], canon = cur.last_tok[b];
+        int pfs = cur.pf_s[b], pfe = cur.pf_e[b];
+        u32 prev = canon;                                  // every live beam ends in the previous frame's single token
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+        for (int j = 0; j < Rok; ++j) {
+            const B2cFrameRec h = S.rh[(t + j) & HM];
+            l = l + h.lp0;
+            if (!live) continue;
+            const B2cTok& ti = b2c_fast_tok0<WC, CAP, LT>(P, S, t + j, sb);
+            const bool blank = (ti.flags & B2C_TF_BLANK) != 0;
+            if (blank || prev == ti.canon) {               // branch (i)
+                if (!blank) pfe = t + j + 1;
+            } else {                                       // branch (iv): a plain character
+                const u32 id = static_cast<u32>(t + j) * static_cast<u32>(WC) + static_cast<u32>(b);
                 B2cChain c;
-                c.parent = cur.chain[b];
-                c.tok = S.sid[sb][0];
+                c.parent = chain;
+                c.tok = h.id0;
                 c.kind = B2C_CK_CONT;
                 c.has_word = 0;
-                c.ws = ps0;
-                c.we = pe0;
+                c.ws = pfs;
+                c.we = pfe;
                 chain_arena[id] = c;
-                cur.chain[b] = id;
-            } else {
-                b2c_atomic_or_u32(&S.sc.status, B2C_ERR_CHAIN_FULL);
+                chain = id;
+                ph = b2c_hash_append(ph, ti.raw_hash, ti.raw_pow);
+                plen += ti.raw_nchars;
+                if (pfs < 0) pfs = t + j;
+                pfe = t + j + 1;
             }
+            prev = ti.canon;
+        }
+        cur.logit[b] = l;
+        if (b == 0) top = plain ? l + 0.0 : b2c_combine_score(has_lm, l, lmhw0, ps0s, plen0);
+        if (!live) continue;
+        cur.last_tok[b] = static_cast<u16>(prev);
+        cur.part_hash[b] = ph;
+        cur.part_len[b] = static_cast<u16>(plen);
+        cur.chain[b] = chain;
+        cur.pf_s[b] = pfs;
+        cur.pf_e[b] = pfe;
+        // best score of the last frame = reference point of the next frame's score buckets (slot 0's thread)
+        if (b == 0) {
+            S.wmax[0] = b2c_f64_key(top);
+            for (int w = 1; w < B2C_FAST_NW; ++w) S.wmax[w] = 0ull;
         }
     }
-    // best score of this frame = reference point of the next frame's score buckets
-    B2C_FOR(w, B2C_FAST_NW) { S.wmax[w] = w == 0 ? b2c_f64_key(top) : 0ull; }
-    return true;
+    return Rok;
 }
 
 // -----------------------------------------------------------------------------------------
@@ -608,16 +722,16 @@ B2C_HD bool b2c_fast_cheap_step(const B2cParams& P, B2cFastSmem<WC, CAP>& S, B2c
 // the old order with the new fields -> in-place update.  Otherwise the state is untouched and the general step runs.
 // Scratch: S.cfold[slot] (new lm_score), S.ckey[slot] (new partial score, as bits).
 // -----------------------------------------------------------------------------------------
-template <int WC, int CAP>
-B2C_HD bool b2c_fast_scored_step(const B2cParams& P, B2cFastSmem<WC, CAP>& S, B2cChain* chain_arena, u32 chain_cap, int par, int t,
-                                 int sb) {
+template <int WC, int CAP, int LT>
+B2C_HD bool b2c_fast_scored_step(const B2cParams& P, B2cFastSmem<WC, CAP, LT>& S, B2cChain* chain_arena, int par, int t,
+                                 int sb, int slot) {
     B2cFastTab<WC>& cur = S.tab[par];
     const u32 n = b2c_max_slots(S.wtop);
     const u32 flags = S.sc.flags;
     const bool has_lm = (flags & B2C_FL_LM) != 0;
     const bool holes = S.holes != 0;
-    const B2cTok ti = S.stok[sb][0];
-    const double p = S.slp[sb][0];
+    const B2cTok ti = b2c_fast_tok<WC, CAP, LT>(S, sb, slot, 0);
+    const double p = S.rlp[slot][0];
     B2C_FOR(b, n) {
         const u64 nph = b2c_hash_append(cur.part_hash[b], ti.raw_hash, ti.raw_pow);
         const u32 nplen = static_cast<u32>(cur.part_len[b]) + ti.raw_nchars;
@@ -656,20 +770,16 @@ B2C_HD bool b2c_fast_scored_step(const B2cParams& P, B2cFastSmem<WC, CAP>& S, B2
         cur.pf_e[b] = t + 1;
         const bool live = !holes || S.pt_min[S.pslot[b]] == static_cast<u32>(b);
         if (!live) continue;
-        const u32 id = b2c_atomic_add_u32(&S.sc.chain_used, 1u);
-        if (id < chain_cap) {
-            B2cChain cn;
-            cn.parent = cur.chain[b];
-            cn.tok = S.sid[sb][0];
-            cn.kind = B2C_CK_CONT;
-            cn.has_word = 0;
-            cn.ws = ps0;
-            cn.we = pe0;
-            chain_arena[id] = cn;
-            cur.chain[b] = id;
-        } else {
-            b2c_atomic_or_u32(&S.sc.status, B2C_ERR_CHAIN_FULL);
-        }
+        const u32 id = static_cast<u32>(t) * static_cast<u32>(WC) + static_cast<u32>(b);
+        B2cChain cn;
+        cn.parent = cur.chain[b];
+        cn.tok = static_cast<u16>(S.rid[slot][0]);
+        cn.kind = B2C_CK_CONT;
+        cn.has_word = 0;
+        cn.ws = ps0;
+        cn.we = pe0;
+        chain_arena[id] = cn;
+        cur.chain[b] = id;
     }
     B2C_FOR(w, B2C_FAST_NW) { S.wmax[w] = w == 0 ? b2c_f64_key(top) : 0ull; }
     return true;
@@ -690,12 +800,12 @@ B2C_HD bool b2c_fast_scored_step(const B2cParams& P, B2cFastSmem<WC, CAP>& S, B2
 // (one new beam per thread) -- the third barrier is the caller's.
 // -----------------------------------------------------------------------------------------
 #define B2C_SORTED_MAXK 8
-template <int WC, int CAP>
-B2C_HD bool b2c_fast_sorted_ok(const B2cParams& P, const B2cFastSmem<WC, CAP>& S, int sb, int K, u32 prev_single) {
+template <int WC, int CAP, int LT>
+B2C_HD bool b2c_fast_sorted_ok(const B2cParams& P, const B2cFastSmem<WC, CAP, LT>& S, int sb, int slot, int K, u32 prev_single) {
     if (prev_single == B2C_NONE_U32 || K < 2 || K > B2C_SORTED_MAXK || P.has_dup_labels) return false;
     if (S.sc.flags & (B2C_FL_PSCORE | B2C_FL_BPE)) return false;
     u32 fl = 0;
-    for (int k = 0; k < K; ++k) fl |= S.stok[sb][k].flags;
+    for (int k = 0; k < K; ++k) fl |= b2c_fast_tok<WC, CAP, LT>(S, sb, slot, k).flags;
     return (fl & B2C_TF_SPACE) == 0;
 }
 
@@ -743,10 +853,10 @@ B2C_HD u32 b2c_sorted_count(const double* logit, u32 n, double lp2, double s, bo
 }
 
 // returns false (state untouched) when the best score is not finite
-template <int WC, int CAP>
-B2C_HD bool b2c_fast_sorted_step(const B2cParams& P, B2cFastSmem<WC, CAP>& S, B2cChain* chain_arena, u32 chain_cap, int par, int t,
-                                 int sb, int K, u32 prev_single) {
-    typedef B2cFastSmem<WC, CAP> SM;
+template <int WC, int CAP, int LT>
+B2C_HD bool b2c_fast_sorted_step(const B2cParams& P, B2cFastSmem<WC, CAP, LT>& S, B2cChain* chain_arena, int par, int t,
+                                 int sb, int slot, int K, u32 prev_single) {
+    typedef B2cFastSmem<WC, CAP, LT> SM;
     B2cFastTab<WC>& cur = S.tab[par];
     B2cFastTab<WC>& nx = S.tab[par ^ 1];
     const u32 n = b2c_max_slots(S.wtop);
@@ -754,9 +864,10 @@ B2C_HD bool b2c_fast_sorted_step(const B2cParams& P, B2cFastSmem<WC, CAP>& S, B2
     const bool holes = S.holes != 0;
     constexpr u32 ptmask = SM::PT - 1;
     // best score of the frame (block-uniform): rank-0 beam + best token
-    double top = (cur.logit[0] + S.slp[sb][0]) + 0.0;
+    const double* const slp = S.rlp[slot];
+    double top = (cur.logit[0] + slp[0]) + 0.0;
     for (int k = 1; k < K; ++k) {
-        const double v = (cur.logit[0] + S.slp[sb][k]) + 0.0;
+        const double v = (cur.logit[0] + slp[k]) + 0.0;
         if (v > top || v != v) top = v;
     }
     if (!(top >= -1.7976931348623157e308)) return false;      // NaN / -inf (only from such input): general step
@@ -794,12 +905,12 @@ B2C_HD bool b2c_fast_sorted_step(const B2cParams& P, B2cFastSmem<WC, CAP>& S, B2
             const u32 lb = b2c_live_before(wm, static_cast<u32>(b));
             const double lg = cur.logit[b];
             for (int k = 0; k < K; ++k) {
-                const double s = (lg + S.slp[sb][k]) + 0.0;
+                const double s = (lg + slp[k]) + 0.0;
                 if (!(s >= thr)) continue;
                 u32 rank = lb;      // same token: the live beams before this one (equal scores keep beam order)
                 for (int k2 = 0; k2 < K && rank < width; ++k2) {
                     if (k2 == k) continue;
-                    const double lp2 = S.slp[sb][k2];
+                    const double lp2 = slp[k2];
                     // candidates of token k2 that sort before (k, b): score greater, or equal and enumerated earlier
                     rank += b2c_live_before(wm, b2c_sorted_count<WC>(cur.logit, n, lp2, s, k2 < k));
                 }
@@ -819,7 +930,7 @@ B2C_HD bool b2c_fast_sorted_step(const B2cParams& P, B2cFastSmem<WC, CAP>& S, B2
     B2C_FOR(r, n_new) {
         const u32 e = S.ord[r];
         const u32 b = e & 0xFFFFu, k = e >> 16;
-        const B2cTok ti = S.stok[sb][k];
+        const B2cTok ti = b2c_fast_tok<WC, CAP, LT>(S, sb, slot, static_cast<int>(k));
         const bool blank = (ti.flags & B2C_TF_BLANK) != 0;
         const bool same = blank || ti.canon == prev_single;                      // branch (i), else branch (iv)
         const u64 ph = cur.part_hash[b];
@@ -833,23 +944,19 @@ B2C_HD bool b2c_fast_sorted_step(const B2cParams& P, B2cFastSmem<WC, CAP>& S, B2
             nph = b2c_hash_append(ph, ti.raw_hash, ti.raw_pow);
             nplen = plen + ti.raw_nchars;
             pfs = ps0 < 0 ? t : ps0;
-            const u32 id = b2c_atomic_add_u32(&S.sc.chain_used, 1u);
-            if (id < chain_cap) {
-                B2cChain c;
-                c.parent = chain;
-                c.tok = S.sid[sb][k];
-                c.kind = B2C_CK_CONT;
-                c.has_word = 0;
-                c.ws = ps0;
-                c.we = pe0;
-                chain_arena[id] = c;
-                chain = id;
-            } else {
-                b2c_atomic_or_u32(&S.sc.status, B2C_ERR_CHAIN_FULL);
-            }
+            const u32 id = static_cast<u32>(t) * static_cast<u32>(WC) + static_cast<u32>(r);
+            B2cChain c;
+            c.parent = chain;
+            c.tok = static_cast<u16>(S.rid[slot][k]);
+            c.kind = B2C_CK_CONT;
+            c.has_word = 0;
+            c.ws = ps0;
+            c.we = pe0;
+            chain_arena[id] = c;
+            chain = id;
         }
         const u64 hh = cur.hist_hash[b];
-        nx.logit[r] = cur.logit[b] + S.slp[sb][k];
+        nx.logit[r] = cur.logit[b] + slp[k];
         nx.lm_hw[r] = cur.lm_hw[b];
         nx.pscore[r] = same ? cur.pscore[b] : 0.0;
         nx.text_hash[r] = cur.text_hash[b];
@@ -884,9 +991,9 @@ B2C_HD bool b2c_fast_sorted_step(const B2cParams& P, B2cFastSmem<WC, CAP>& S, B2
 
 // squeeze the dead slots out of the current table (into the other one: the caller flips its parity) and
 // leave the state the general helpers expect: sc.n_beams / sc.prev_max set, prune table clear
-template <int WC, int CAP>
-B2C_HDN void b2c_fast_compact(B2cFastSmem<WC, CAP>* Sp, int par) {
-    B2cFastSmem<WC, CAP>& S = *Sp;
+template <int WC, int CAP, int LT>
+B2C_HDN void b2c_fast_compact(B2cFastSmem<WC, CAP, LT>* Sp, int par) {
+    B2cFastSmem<WC, CAP, LT>& S = *Sp;
     const B2cFastTab<WC>& cur = S.tab[par];
     B2cFastTab<WC>& nx = S.tab[par ^ 1];
     const u32 n = b2c_max_slots(S.wtop);
@@ -927,10 +1034,10 @@ B2C_HDN void b2c_fast_compact(B2cFastSmem<WC, CAP>* Sp, int par) {
 
 // A frame that does not fit the shared-memory tier (or the token stage): the general step on the
 // HBM tier, out of line, with its own descriptor.  Restores the invariants of b2c_fast_step.
-template <int WC, int CAP>
-B2C_HDN void b2c_fast_slow_step(B2cParams P, B2cLayout L, u8* smem, u8* g, int par, int t, const u16* tk_id, const double* tk_lp,
+template <int WC, int CAP, int LT>
+B2C_HDN void b2c_fast_slow_step(B2cParams P, B2cLayout L, u8* smem, u8* g, int par, int t, const u32* tk_id, const double* tk_lp,
                                 int K, int K_next) {
-    B2cFastSmem<WC, CAP>& S = *reinterpret_cast<B2cFastSmem<WC, CAP>*>(smem);
+    B2cFastSmem<WC, CAP, LT>& S = *reinterpret_cast<B2cFastSmem<WC, CAP, LT>*>(smem);
     B2cWork W;
     b2c_fast_work(S, L, g, par, true, W);
     const u32 M = S.sc.n_beams * static_cast<u32>(K);
@@ -958,22 +1065,37 @@ B2C_HDN void b2c_fast_slow_step(B2cParams P, B2cLayout L, u8* smem, u8* g, int p
 
 // -----------------------------------------------------------------------------------------
 // one CTA: utterances from the work queue, all frames, finalisation
+//
+// Token staging (per utterance).  K1 left, per frame, a 16-byte record {offset, count, first token id, its
+// log-prob} and compact (id, log-prob) lists.  Three shared-memory structures are kept ahead of the frame loop by
+// cp.async copies issued at the TOP of an iteration and completed (wait_all + the closing barrier) at its end:
+//   rh[32]       frame records; frames < hv are visible, hv - t >= 18 at the top of every iteration
+//   rid/rlp[8]   token lists of frames < tv (tv <= t + 8; a frame's slot is frame & 7)
+//   stok[2]      label records of the current frame's tokens (copied from the resident table, or loaded from the
+//                global table one frame ahead for large alphabets: register staged, stored before the barrier)
+// An iteration handles frame t, or a run of R in-place frames t .. t+R-1 with t + R < tv (the label records of
+// frame t + R are staged during the iteration, which needs its ids in the ring).
 // -----------------------------------------------------------------------------------------
-template <int WC, int CAP>
-B2C_HD void b2c_beam_block_fast(const B2cBeamArgs& A, int slot, u8* smem) {
-    typedef B2cFastSmem<WC, CAP> SM;
+template <int WC, int CAP, int LT>
+B2C_HD void b2c_beam_block_fast(const B2cBeamArgs& A, int slot_cta, u8* smem) {
+    typedef B2cFastSmem<WC, CAP, LT> SM;
+    constexpr int KR = SM::KR;
+    constexpr int HM = B2C_FAST_HR - 1, TM = B2C_FAST_TR - 1;
     SM& S = *reinterpret_cast<SM*>(smem);
     const B2cLayout& L = A.L;
-    u8* g = A.gws + static_cast<u64>(slot) * L.gws_bytes;
+    u8* g = A.gws + static_cast<u64>(slot_cta) * L.gws_bytes;
     B2cChain* const chain_arena = reinterpret_cast<B2cChain*>(g + L.g_chain);
     B2cText* const text_arena = reinterpret_cast<B2cText*>(g + L.g_text);
-    const u32 chain_cap = L.chain_cap, text_cap = L.text_cap;
+    const u32 text_cap = L.text_cap;
     const int V = A.P.V;
     u32 st_over[6] = {0, 0, 0, 0, 0, 0};    // candidate-count histogram of the fast frames (last thread's copy counts)
     u32 st_frames = 0, st_inplace = 0, st_sorted = 0;
     B2C_LEADER {
         for (int q = 0; q < 6; ++q) S.sc.m_over[q] = 0;
         S.sc.m_frames = 0;
+    }
+    if (LT > 0) {       // the label table stays resident for the whole launch
+        B2C_FOR(c, V < LT ? V : LT) { S.ltab[c] = A.P.toks[c]; }
     }
 #if defined(B2C_PHASE_CLOCKS) && defined(__CUDA_ARCH__)
     if (threadIdx.x == 0) {
@@ -991,25 +1113,14 @@ B2C_HD void b2c_beam_block_fast(const B2cBeamArgs& A, int slot, u8* smem) {
         const int Tn = A.T[u];
         const u64 f0 = A.frame_off[u];
         const B2cFrameRec* recs = A.tok_rec + f0;
-        // prefetch distances (frames): frame records RD ahead, token ids / log-probs ID ahead, label records 1 ahead.
-        // An in-place frame (b2c_fast_cheap_step) lasts a few hundred cycles, less than one trip to L2, so the
-        // resident-batch variant (register headroom) looks further ahead than the throughput variants.
-        constexpr int RD = CAP >= 1024 ? 6 : 3;
-        constexpr int ID = CAP >= 1024 ? 4 : 2;
-        (void)ID;
-        B2cFrameRec rq[RD];                       // rq[j]: record of frame t + j
-#if defined(__CUDACC__)
-#pragma unroll
-#endif
-        for (int j = 0; j < RD; ++j) {
-            rq[j].off = 0;
-            rq[j].cnt = 1;
-            if (j < Tn) rq[j] = recs[j];
-        }
+        // ---- fill the rings: records of the first frames, then the token lists of the first frames ----------------
+        int hv = Tn < B2C_FAST_HR ? Tn : B2C_FAST_HR;            // records of frames < hv are (being) fetched
+        B2C_FOR(c, hv) { b2c_cp_async16(&S.rh[c], recs + c); }
+        b2c_cp_async_wait_all();
         {
             B2cWork W;
             b2c_fast_work(S, L, g, 0, false, W);
-            b2c_utt_begin(A.P, W, A.start_states ? A.start_states + u : nullptr, static_cast<int>(rq[0].cnt), B2cStreamIn{nullptr, 0u, nullptr, nullptr});
+            b2c_utt_begin(A.P, W, A.start_states ? A.start_states + u : nullptr, 1, B2cStreamIn{nullptr, 0u, nullptr, nullptr});
         }
         B2C_FOR(s, SM::HT) {
             S.ht_idx[s] = B2C_NONE_U32;
@@ -1023,144 +1134,172 @@ B2C_HD void b2c_beam_block_fast(const B2cBeamArgs& A, int slot, u8* smem) {
             S.sc.n_sel = 0;
             S.holes = 0;
             S.cheap_bad = 0;
+            S.run_fail = B2C_NONE_U32;
             for (int c = 0; c < B2C_FAST_NW; ++c) { S.wmax[c] = 0; S.wtop[c] = 0; }
             S.wtop[0] = 1;
             S.wmax[0] = b2c_f64_key(0.0);
+            // backtrack nodes of the frame steps have fixed ids below WC * T; the out-of-line step allocates above
+            S.sc.chain_used = static_cast<u32>(WC) * static_cast<u32>(Tn);
         }
-        // stage the tokens of frame 0 (once per utterance, latency exposed)
-        if (Tn > 0) {
-            const u64 base0 = f0 * static_cast<u64>(V) + rq[0].off;
-            const u32 k0 = rq[0].cnt < B2C_FAST_KS ? rq[0].cnt : B2C_FAST_KS;
-            B2C_FOR(c, k0) {
-                const u16 id = A.tok_ids[base0 + c];
-                S.stok[0][c] = A.P.toks[id];
-                S.slp[0][c] = A.tok_lp[base0 + c];
-                S.sid[0][c] = id;
+        B2C_SYNC();                                             // records visible
+        int tv = Tn < B2C_FAST_TR ? Tn : B2C_FAST_TR;            // token lists of frames < tv are (being) fetched
+        for (int f = 0; f < tv; ++f) {
+            const B2cFrameRec hf = S.rh[f & HM];
+            const u64 base = (f0 + static_cast<u64>(f & ~(B2C_RUN - 1))) * static_cast<u64>(V) + hf.off;
+            const u32 kf = hf.cnt < static_cast<u32>(KR) ? hf.cnt : static_cast<u32>(KR);
+            B2C_FOR(c, kf) {
+                b2c_cp_async4(&S.rid[f & TM][c], A.tok_ids + base + c);
+                b2c_cp_async8(&S.rlp[f & TM][c], A.tok_lp + base + c);
             }
         }
-#if defined(__CUDA_ARCH__)
-        // register pipeline: token `threadIdx.x` of frame t+ID (id, log-prob) is loaded ID-1 frames ahead of
-        // its label record, which is loaded one frame ahead of the shared-memory store
-        u32 pidq[ID - 1];                         // [j]: token `threadIdx.x` of frame t + 1 + j (u32: a u16 array gets
-                                                  // packed two to a register, and the packing consumes a load at once)
-        double plpq[ID - 1];
-#pragma unroll
-        for (int j = 0; j < ID - 1; ++j) {
-            pidq[j] = 0;
-            plpq[j] = 0.0;
-            const int f = j + 1;
-            if (f < Tn && threadIdx.x < (rq[f].cnt < B2C_FAST_KS ? rq[f].cnt : B2C_FAST_KS)) {
-                const u64 basef = (f0 + static_cast<u64>(f & ~(B2C_RUN - 1))) * static_cast<u64>(V) + rq[f].off;
-                pidq[j] = A.tok_ids[basef + threadIdx.x];
-                plpq[j] = A.tok_lp[basef + threadIdx.x];
-            }
-        }
-#endif
+        b2c_cp_async_wait_all();
         B2C_SYNC();
-        int par = 0;
+        if (Tn > 0) {       // label records of frame 0 (once per utterance, latency exposed)
+            const u32 k0 = S.rh[0].cnt < static_cast<u32>(KR) ? S.rh[0].cnt : static_cast<u32>(KR);
+            if (LT == 0) { B2C_FOR(c, k0) { S.stok[0][c] = A.P.toks[S.rid[0][c]]; } }
+        }
+        B2C_SYNC();
+        int par = 0, sb = 0;
         u32 prev_single = B2C_NONE_U32;   // canonical token of the previous frame if it selected exactly one
+        int t = 0;
 #if defined(__CUDACC__)
 #pragma unroll 1
 #endif
-        for (int t = 0; t < Tn; ++t) {
-            const int K = static_cast<int>(rq[0].cnt);
-            const int sb = t & 1;
-            const u32 kb = (t + 1 < Tn) ? (rq[1].cnt < B2C_FAST_KS ? rq[1].cnt : B2C_FAST_KS) : 0u;
-            const u64 base_b = (f0 + static_cast<u64>((t + 1) & ~(B2C_RUN - 1))) * static_cast<u64>(V) + rq[1].off;
-#if defined(__CUDA_ARCH__)
-            B2cTok ptk;
-            const bool has_b = threadIdx.x < kb;
-            if (has_b) ptk = A.P.toks[pidq[0]];
-#endif
+        while (t < Tn) {
+            const B2cFrameRec h = S.rh[t & HM];
+            const int K = static_cast<int>(h.cnt);
+            const int slot = t & TM;
+            const u32 flags = S.sc.flags;
+            // ---- what kind of step, and how many frames it covers ------------------------------------------
             const u32 Mq = b2c_max_slots(S.wtop) * static_cast<u32>(K);
+            const bool oversize = Mq > static_cast<u32>(CAP) || K > KR;
+            int kind = B2C_CHEAP_NO;
+            int R = 1;
+            if (!oversize && K == 1 && prev_single != B2C_NONE_U32) {
+                kind = b2c_fast_cheap_kind(flags, prev_single, b2c_fast_tok0<WC, CAP, LT>(A.P, S, t, sb));
+                if (LT > 0 && (kind == B2C_CHEAP_T0 || kind == B2C_CHEAP_T3)) {
+                    // extend the run while the next frames are in-place frames too; frame t + R must have its token
+                    // list in the ring (its label records are staged during this iteration)
+                    int lim = Tn - t < B2C_FAST_RMAX ? Tn - t : B2C_FAST_RMAX;
+                    if (tv < Tn && tv - 1 - t < lim) lim = tv - 1 - t;
+                    u32 pc = b2c_fast_tok0<WC, CAP, LT>(A.P, S, t, sb).canon;
+                    while (R < lim) {
+                        const B2cFrameRec hn = S.rh[(t + R) & HM];
+                        if (hn.cnt != 1) break;
+                        const B2cTok& tn = S.ltab[hn.id0];
+                        const int kn = b2c_fast_cheap_kind(flags, pc, tn);
+                        if (kn != B2C_CHEAP_T0 && kn != B2C_CHEAP_T3) break;
+                        pc = tn.canon;
+                        ++R;
+                    }
+                }
+            }
+            // ---- prefetch: frame records, token lists (visible at the next iteration) -----------------------
+            {
+                const bool more_recs = hv < Tn && hv - t <= B2C_FAST_HR - 8;
+                const int tv_new = t + B2C_FAST_TR < Tn ? t + B2C_FAST_TR : Tn;
+                B2C_IN_LAST_WARP {
+                    if (more_recs) {
+                        B2C_FOR_LANES(c, 8) {
+                            if (hv + c < Tn) b2c_cp_async16(&S.rh[(hv + c) & HM], recs + hv + c);
+                        }
+                    }
+                    for (int f = tv; f < tv_new; ++f) {
+                        const B2cFrameRec hf = S.rh[f & HM];
+                        const u64 base = (f0 + static_cast<u64>(f & ~(B2C_RUN - 1))) * static_cast<u64>(V) + hf.off;
+                        const u32 kf = hf.cnt < static_cast<u32>(KR) ? hf.cnt : static_cast<u32>(KR);
+                        B2C_FOR_LANES(c, kf) {
+                            b2c_cp_async4(&S.rid[f & TM][c], A.tok_ids + base + c);
+                            b2c_cp_async8(&S.rlp[f & TM][c], A.tok_lp + base + c);
+                        }
+                    }
+                }
+                if (more_recs) hv = hv + 8 < Tn ? hv + 8 : Tn;
+                if (tv_new > tv) tv = tv_new;
+            }
+#if defined(__CUDA_ARCH__)
+            // large alphabets (no resident label table): the label records of frame t + 1 come from global memory --
+            // loaded here into a register, stored to shared memory just before the closing barrier
+            B2cTok ptk;
+            bool has_ptk = false;
+            if (LT == 0 && t + 1 < Tn) {
+                const u32 cn1 = S.rh[(t + 1) & HM].cnt;
+                has_ptk = threadIdx.x < (cn1 < static_cast<u32>(KR) ? cn1 : static_cast<u32>(KR));
+                if (has_ptk) ptk = A.P.toks[S.rid[(t + 1) & TM][threadIdx.x]];
+            }
+#endif
             B2C_FMARK(16);
-            bool in_place = false;      // the frame updated the current table in place (no table swap)
-            if (Mq > static_cast<u32>(CAP) || K > B2C_FAST_KS) {
-                const u64 base_a = (f0 + static_cast<u64>(t & ~(B2C_RUN - 1))) * static_cast<u64>(V) + rq[0].off;
+            bool in_place = false;      // the frame(s) updated the current table in place (no table swap)
+            int done_frames = 0;
+            if (oversize) {
+                const u64 base_a = (f0 + static_cast<u64>(t & ~(B2C_RUN - 1))) * static_cast<u64>(V) + h.off;
+                const int K_next = t + 1 < Tn ? static_cast<int>(S.rh[(t + 1) & HM].cnt) : 1;
                 // the general step wants a dense table: squeeze first (the squeezed table is the other one)
-                b2c_fast_compact<WC, CAP>(&S, par);
+                b2c_fast_compact<WC, CAP, LT>(&S, par);
                 par ^= 1;
-                b2c_fast_slow_step<WC, CAP>(A.P, L, smem, g, par, t, A.tok_ids + base_a, A.tok_lp + base_a, K, static_cast<int>(rq[1].cnt));
+                b2c_fast_slow_step<WC, CAP, LT>(A.P, L, smem, g, par, t, A.tok_ids + base_a, A.tok_lp + base_a, K, K_next);
+                done_frames = 1;
             } else {
                 B2C_LAST_THREAD {
-                    ++st_frames;
                     for (int c = 0; c < 6; ++c) st_over[c] += (Mq > (128u << c)) ? 1u : 0u;
                 }
-                bool done = false;          // the frame was handled by one of the two special steps
-                if (K == 1 && prev_single != B2C_NONE_U32) {
-                    const int kind = b2c_fast_cheap_kind(S.sc.flags, prev_single, S.stok[sb][0]);
-                    if (kind == B2C_CHEAP_T3P) in_place = b2c_fast_scored_step<WC, CAP>(A.P, S, chain_arena, chain_cap, par, t, sb);
-                    else if (kind != B2C_CHEAP_NO) in_place = b2c_fast_cheap_step<WC, CAP>(A.P, S, chain_arena, chain_cap, par, t, sb, kind);
-                    B2C_LAST_THREAD { st_inplace += in_place ? 1u : 0u; }
-                    done = in_place;
-                    if (in_place) B2C_FMARK(5);
-                } else if (b2c_fast_sorted_ok<WC, CAP>(A.P, S, sb, K, prev_single)) {
-                    done = b2c_fast_sorted_step<WC, CAP>(A.P, S, chain_arena, chain_cap, par, t, sb, K, prev_single);
-                    B2C_LAST_THREAD { st_sorted += done ? 1u : 0u; }
-                    if (done) B2C_FMARK(7);
+                if (kind == B2C_CHEAP_T3P) {
+                    in_place = b2c_fast_scored_step<WC, CAP, LT>(A.P, S, chain_arena, par, t, sb, slot);
+                    done_frames = in_place ? 1 : 0;
+                } else if (kind != B2C_CHEAP_NO) {
+                    done_frames = b2c_fast_run_step<WC, CAP, LT>(A.P, S, chain_arena, par, t, sb, R);
+                    in_place = done_frames > 0;
                 }
-                if (!done) {
-#if defined(B2C_PHASE_CLOCKS)
-#if defined(__CUDA_ARCH__)
+                if (in_place) {
+                    B2C_LAST_THREAD { st_inplace += static_cast<u32>(done_frames); }
+                    B2C_FMARK(5);
+                } else if (kind == B2C_CHEAP_NO && b2c_fast_sorted_ok<WC, CAP, LT>(A.P, S, sb, slot, K, prev_single)) {
+                    if (b2c_fast_sorted_step<WC, CAP, LT>(A.P, S, chain_arena, par, t, sb, slot, K, prev_single)) {
+                        done_frames = 1;
+                        B2C_LAST_THREAD { ++st_sorted; }
+                        B2C_FMARK(7);
+                    }
+                }
+                if (done_frames == 0) {
+#if defined(B2C_PHASE_CLOCKS) && defined(__CUDA_ARCH__)
                     const long long c0 = clock64();
 #endif
-                    b2c_fast_step<WC, CAP>(A.P, S, chain_arena, chain_cap, text_arena, text_cap, par, t, sb, K);
-#if defined(__CUDA_ARCH__)
+                    b2c_fast_step<WC, CAP, LT>(A.P, S, chain_arena, text_arena, text_cap, par, t, sb, slot, K);
+#if defined(B2C_PHASE_CLOCKS) && defined(__CUDA_ARCH__)
                     if (threadIdx.x == 0) {      // general frames by token count: cycles in 9..11, frames in 12..14
                         const int cls = K == 1 ? 0 : (K == 2 ? 1 : 2);
                         S.pclk[9 + cls] += static_cast<u64>(clock64() - c0);
                         S.pclk[12 + cls] += 1;
                     }
 #endif
-#else
-                    b2c_fast_step<WC, CAP>(A.P, S, chain_arena, chain_cap, text_arena, text_cap, par, t, sb, K);
-#endif
+                    done_frames = 1;
                 }
+                B2C_LAST_THREAD { st_frames += static_cast<u32>(done_frames); }
             }
-            // after a single-token frame every beam ends in that token (precondition of b2c_fast_cheap_step)
-            prev_single = (K == 1) ? static_cast<u32>(S.stok[sb][0].canon) : B2C_NONE_U32;
-            // stage the tokens of frame t+1
+            // after a single-token frame every beam ends in that token (precondition of the in-place steps)
+            const int t_last = t + done_frames - 1;
+            if (done_frames == 1) prev_single = (K == 1) ? static_cast<u32>(b2c_fast_tok0<WC, CAP, LT>(A.P, S, t, sb).canon) : B2C_NONE_U32;
+            else prev_single = static_cast<u32>(S.ltab[S.rh[t_last & HM].id0].canon);
+            // ---- label records of the next frame's tokens (its ids are in the ring: t + done_frames < tv) ------
+            const int tn = t + done_frames;
 #if defined(__CUDA_ARCH__)
-            if (has_b) {
-                S.stok[sb ^ 1][threadIdx.x] = ptk;
-                S.slp[sb ^ 1][threadIdx.x] = plpq[0];
-                S.sid[sb ^ 1][threadIdx.x] = static_cast<u16>(pidq[0]);
-            }
-            // rotate FIRST (values loaded at least one frame ago), THEN issue the new loads into the freed
-            // registers: nothing touches them before the next rotation, a whole frame later.  (Loading at the top
-            // of the iteration and rotating here made every frame wait for the loads it had just issued.)
-#pragma unroll
-            for (int j = 0; j + 1 < ID - 1; ++j) {
-                pidq[j] = pidq[j + 1];
-                plpq[j] = plpq[j + 1];
-            }
-            pidq[ID - 2] = 0;
-            plpq[ID - 2] = 0.0;
-            if (t + ID < Tn && threadIdx.x < (rq[ID].cnt < B2C_FAST_KS ? rq[ID].cnt : B2C_FAST_KS)) {
-                const u64 base_n = (f0 + static_cast<u64>((t + ID) & ~(B2C_RUN - 1))) * static_cast<u64>(V) + rq[ID].off;
-                pidq[ID - 2] = A.tok_ids[base_n + threadIdx.x];
-                plpq[ID - 2] = A.tok_lp[base_n + threadIdx.x];
+            if (LT == 0) {
+                if (has_ptk) S.stok[sb ^ 1][threadIdx.x] = ptk;        // tn == t + 1: without the table every step covers one frame
             }
 #else
-            B2C_FOR(c, kb) {
-                const u16 id = A.tok_ids[base_b + c];
-                S.stok[sb ^ 1][c] = A.P.toks[id];
-                S.slp[sb ^ 1][c] = A.tok_lp[base_b + c];
-                S.sid[sb ^ 1][c] = id;
+            if (LT == 0 && tn < Tn) {
+                const u32 cn = S.rh[tn & HM].cnt;
+                const u32 kb = cn < static_cast<u32>(KR) ? cn : static_cast<u32>(KR);
+                B2C_FOR(c, kb) { S.stok[sb ^ 1][c] = A.P.toks[S.rid[tn & TM][c]]; }
             }
 #endif
-            (void)base_b;
             B2C_FMARK(19);
+            b2c_cp_async_wait_all();
             B2C_SYNC();
             B2C_FMARK(6);
             if (!in_place) par ^= 1;
-#if defined(__CUDACC__)
-#pragma unroll
-#endif
-            for (int j = 0; j + 1 < RD; ++j) rq[j] = rq[j + 1];
-            rq[RD - 1].off = 0;
-            rq[RD - 1].cnt = 1;
-            if (t + RD < Tn) rq[RD - 1] = recs[t + RD];
+            sb ^= 1;
+            t = tn;
         }
         B2cOut O;
         const u64 ob = static_cast<u64>(A.P.out_beams);
@@ -1175,7 +1314,7 @@ B2C_HD void b2c_beam_block_fast(const B2cBeamArgs& A, int slot, u8* smem) {
         O.states = A.out_states + static_cast<u64>(u) * ob;
         O.aux = nullptr;
         O.states_x = nullptr;
-        b2c_fast_compact<WC, CAP>(&S, par);
+        b2c_fast_compact<WC, CAP, LT>(&S, par);
         par ^= 1;
         {
             B2cWork W;

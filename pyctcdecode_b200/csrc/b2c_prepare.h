@@ -223,7 +223,10 @@ B2C_HD void b2c_pyset_copy_or(B2cPySet& s, u32 extra) {
 #define B2C_PREP_LEAF_CAP 1024
 #define B2C_ROWSUM_MAX_LEAF 64      // rows up to 8192 elements take the coalesced warp-per-row sum
 
-struct B2cFrameRec { u32 off; u32 cnt; };   // token list of one frame: offset inside its run, length
+// token list of one frame: offset inside its run, length, and the FIRST token of the list inline (a single-token
+// frame -- most frames of ASR posteriors -- is fully described by its 16-byte record: the beam kernel's in-place
+// runs never touch the token arrays)
+struct B2cFrameRec { u32 off; u16 cnt; u16 id0; double lp0; };
 
 struct B2cPrepArgs {
     const void* logits;      // packed [total_frames, V]
@@ -235,7 +238,7 @@ struct B2cPrepArgs {
     int V;
     double token_min_logp;
     B2cFrameRec* tok_rec;    // [total_frames]
-    u16* tok_ids;            // [total_frames * V]
+    u32* tok_ids;            // [total_frames * V]  (32-bit: the beam kernel stages them with 4-byte cp.async)
     double* tok_lp;
     void* rowsum;            // [total_frames] scratch, input dtype
     u16* set_scratch;        // [total warps][2][set_cap] spill space for large token sets
@@ -540,7 +543,7 @@ B2C_HD void b2c_tokens_run_v32(const B2cPrepArgs& A, u64 run, int lane, u16* set
     const bool is_prob = A.is_prob[u] != 0;
     const T* x = static_cast<const T*>(A.logits) + f0 * static_cast<u64>(V);
     const u64 base = (f0 + static_cast<u64>(t0)) * static_cast<u64>(V);
-    u16* ids = A.tok_ids + base;
+    u32* ids = A.tok_ids + base;
     double* lps = A.tok_lp + base;
     B2cPySet set;
     set.buf[0] = set0;
@@ -621,17 +624,21 @@ B2C_HD void b2c_tokens_run_v32(const B2cPrepArgs& A, u64 run, int lane, u16* set
     if (mine) {
         B2cFrameRec rec;
         rec.off = my_off;
-        rec.cnt = cnt;
-        A.tok_rec[f0 + static_cast<u64>(t0 + lane)] = rec;
+        rec.cnt = static_cast<u16>(cnt);
+        rec.id0 = 0;
+        rec.lp0 = 0.0;
         if (small) {
             const T* row = x + static_cast<u64>(t0 + lane) * V;
             u32 toks[3];
             const u32 n = b2c_pyset_small_order(my_mask, my_amax, toks);
             for (u32 q = 0; q < n; ++q) {
-                ids[my_off + q] = static_cast<u16>(toks[q]);
-                lps[my_off + q] = b2c_lp<T>(row[toks[q]], is_prob, my_m, my_ls);
+                const double lp = b2c_lp<T>(row[toks[q]], is_prob, my_m, my_ls);
+                ids[my_off + q] = toks[q];
+                lps[my_off + q] = lp;
+                if (q == 0) { rec.id0 = static_cast<u16>(toks[0]); rec.lp0 = lp; }
             }
         }
+        A.tok_rec[f0 + static_cast<u64>(t0 + lane)] = rec;     // frames of the general set emulation: first token patched below
     }
     u32 big = __ballot_sync(full, mine && !small);
     while (big) {
@@ -647,11 +654,19 @@ B2C_HD void b2c_tokens_run_v32(const B2cPrepArgs& A, u64 run, int lane, u16* set
         if (lane == 0) {
             b2c_pyset_copy_or(set, static_cast<u32>(amax));
             const u16* tab = set.buf[set.cur];
+            bool first = true;
             for (u32 s = 0; s <= set.mask; ++s) {
                 const u16 tok = tab[s];
                 if (tok == 0xFFFFu) continue;
+                const double lp = b2c_lp<T>(row[tok], is_prob, m, ls);
                 ids[off] = tok;
-                lps[off] = b2c_lp<T>(row[tok], is_prob, m, ls);
+                lps[off] = lp;
+                if (first) {
+                    B2cFrameRec* r = A.tok_rec + f0 + static_cast<u64>(t0 + f);
+                    r->id0 = tok;
+                    r->lp0 = lp;
+                    first = false;
+                }
                 ++off;
             }
         }
@@ -682,26 +697,31 @@ B2C_HD void b2c_tokens_run_v32(const B2cPrepArgs& A, u64 run, int lane, u16* set
         const bool small = nsel == 0 || (nsel <= 3 && ((mask >> amax) & 1u));
         B2cFrameRec rec;
         rec.off = off;
+        rec.id0 = 0;
+        rec.lp0 = 0.0;
         if (small) {
             u32 toks[3];
             const u32 n = b2c_pyset_small_order(mask, static_cast<u32>(amax), toks);
             for (u32 q = 0; q < n; ++q) {
-                ids[off] = static_cast<u16>(toks[q]);
+                ids[off] = toks[q];
                 lps[off] = b2c_lp<T>(row[toks[q]], is_prob, m, ls);
+                if (q == 0) { rec.id0 = static_cast<u16>(toks[0]); rec.lp0 = lps[off]; }
                 ++off;
             }
-            rec.cnt = n;
+            rec.cnt = static_cast<u16>(n);
         } else {
             u32 ns;
             b2c_prep_row<T, false>(row, V, is_prob, A.token_min_logp, 0, set, m, ls, amax, ns);
             b2c_pyset_copy_or(set, static_cast<u32>(amax));
-            rec.cnt = set.fill;
+            rec.cnt = static_cast<u16>(set.fill);
             const u16* tab = set.buf[set.cur];
+            bool first = true;
             for (u32 s2 = 0; s2 <= set.mask; ++s2) {
                 const u16 tok = tab[s2];
                 if (tok == 0xFFFFu) continue;
                 ids[off] = tok;
                 lps[off] = b2c_lp<T>(row[tok], is_prob, m, ls);
+                if (first) { rec.id0 = tok; rec.lp0 = lps[off]; first = false; }
                 ++off;
             }
         }
@@ -733,7 +753,7 @@ B2C_HD void b2c_tokens_run(const B2cPrepArgs& A, u64 run, int lane, u16* set0, u
     const bool is_prob = A.is_prob[u] != 0;
     const T* x = static_cast<const T*>(A.logits) + f0 * static_cast<u64>(V);
     const u64 base = (f0 + static_cast<u64>(t0)) * static_cast<u64>(V);
-    u16* ids = A.tok_ids + base;
+    u32* ids = A.tok_ids + base;
     double* lps = A.tok_lp + base;
     u32 off = 0, mx = 0;
     for (int t = t0; t < t1; ++t) {
@@ -751,16 +771,20 @@ B2C_HD void b2c_tokens_run(const B2cPrepArgs& A, u64 run, int lane, u16* set0, u
             const u32 cnt = set.fill;
             B2cFrameRec rec;
             rec.off = off;
-            rec.cnt = cnt;
-            A.tok_rec[f0 + static_cast<u64>(t)] = rec;
+            rec.cnt = static_cast<u16>(cnt);
+            rec.id0 = 0;
+            rec.lp0 = 0.0;
             const u16* tab = set.buf[set.cur];
+            bool first = true;
             for (u32 s = 0; s <= set.mask; ++s) {
                 const u16 tok = tab[s];
                 if (tok == 0xFFFFu) continue;
                 ids[off] = tok;
                 lps[off] = b2c_lp<T>(row[tok], is_prob, m, ls);
+                if (first) { rec.id0 = tok; rec.lp0 = lps[off]; first = false; }
                 ++off;
             }
+            A.tok_rec[f0 + static_cast<u64>(t)] = rec;
             if (cnt > mx) mx = cnt;
         }
 #if defined(__CUDA_ARCH__)

@@ -6,11 +6,10 @@
 #include <cstring>
 #include "cuda_shim.h"
 #include "b2c_beam.h"
-struct B2cFrameRec { u32 off; u32 cnt; };
-#define B2C_RUN 8
+#include "b2c_prepare.h"      // B2cFrameRec, B2C_RUN
 struct B2cBeamArgs {
     B2cParams P; B2cLayout L; int n_utts; const int* order; u32* next; const u64* frame_off; const int* T; const B2cFrameRec* tok_rec;
-    const u16* tok_ids; const double* tok_lp; u8* gws; const B2cLmState* start_states; int* out_nbeams; int* out_status; double* out_scores;
+    const u32* tok_ids; const double* tok_lp; u8* gws; const B2cLmState* start_states; int* out_nbeams; int* out_status; double* out_scores;
     int* out_ntok; int* out_nwords; u32* out_toks; int* out_frames; B2cLmState* out_states; u64* phase_clk; u32* m_stats;
 };
 #include "b2c_beam_fast.h"
