@@ -53,8 +53,12 @@ int b2c_device_count(void);
 /* ---- n-gram model ------------------------------------------------------------------------
  * Replaces kenlm.Model(kenlm_model_path) + _prepare_unigram_set + CharTrie.fromkeys
  * (decoder.py:1074-1096, language_model.py:87-103, :237-269).  `unigrams` NULL or
- * n_unigrams < 0 means "no unigram list" (LanguageModel(unigrams=None)). ARPA text only. */
+ * n_unigrams < 0 means "no unigram list" (LanguageModel(unigrams=None)). */
 int b2c_lm_build_from_arpa(const char* arpa_path, const char* const* unigrams, long n_unigrams, b2c_lm_t** out);
+/* the same from whatever kenlm.Model(path) accepts (decoder.py:1074, language_model.py:422-426): ARPA text, or a KenLM
+ * BINARY file of the probing model type (what kenlm's build_binary writes by default) -- told apart by the first
+ * bytes.  Trie / quantised binaries are rejected with a message (B2C_E_IO). */
+int b2c_lm_build_from_file(const char* path, const char* const* unigrams, long n_unigrams, b2c_lm_t** out);
 /* the relocatable blob (for a NCCL broadcast) and its reconstruction on another rank; from_blob validates every
  * offset, mask and id of the header against `size` before use */
 int b2c_lm_blob(const b2c_lm_t* lm, const void** data, size_t* size);

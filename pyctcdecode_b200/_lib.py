@@ -78,6 +78,7 @@ def _declare(L):
     L.b2c_version.restype = i32
     L.b2c_device_count.restype = i32
     L.b2c_lm_build_from_arpa.argtypes = [cp, C.POINTER(cp), C.c_long, pp]
+    L.b2c_lm_build_from_file.argtypes = [cp, C.POINTER(cp), C.c_long, pp]
     L.b2c_lm_blob.argtypes = [vp, pp, C.POINTER(C.c_size_t)]
     L.b2c_lm_from_blob.argtypes = [vp, C.c_size_t, pp]
     L.b2c_lm_upload.argtypes = [vp, i32]

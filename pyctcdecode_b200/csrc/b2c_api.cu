@@ -732,6 +732,15 @@ int b2c_lm_build_from_arpa(const char* arpa_path, const char* const* unigrams, l
     *out = lm.release();
     return 0;
 }
+// ARPA text or a KenLM binary (probing model type), told apart by the file's first bytes
+int b2c_lm_build_from_file(const char* path, const char* const* unigrams, long n_unigrams, b2c_lm_t** out) {
+    if (!path || !out) return fail(B2C_E_ARG, "null argument");
+    if (!b2c_is_kenlm_binary(path)) return b2c_lm_build_from_arpa(path, unigrams, n_unigrams, out);
+    std::unique_ptr<b2c_lm> lm(new b2c_lm());
+    if (!b2c_lm_build_kenlm_binary(lm->host, path, unigrams, n_unigrams)) return fail(B2C_E_IO, lm->host.error);
+    *out = lm.release();
+    return 0;
+}
 int b2c_lm_blob(const b2c_lm_t* lm, const void** data, size_t* size) {
     if (!lm || !data || !size) return fail(B2C_E_ARG, "null argument");
     *data = lm->host.blob.data();
@@ -755,6 +764,7 @@ static const char* blob_defect(const B2cLmHeader* h, size_t size) {
     if (!inside(h->off_vocab, h->vocab_mask + 1, sizeof(B2cVocab))) return "vocabulary table outside the blob";
     if (!inside(h->off_prefix, h->prefix_mask + 1, sizeof(u64))) return "prefix table outside the blob";
     if (h->have_unigrams != 0 && h->have_unigrams != 1) return "bad unigram flag";
+    if (h->key_scheme != B2C_KEYS_B2C && h->key_scheme != B2C_KEYS_KENLM) return "unknown key scheme";
     if (h->n_unigrams < 0 || static_cast<u64>(h->n_unigrams) > h->n_vocab) return "bad unigram count";
     return nullptr;
 }

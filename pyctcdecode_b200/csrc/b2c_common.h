@@ -89,6 +89,14 @@ B2C_HD u64 b2c_ngram_extend(u64 h, u32 ctx_word) {
 }
 B2C_HD u64 b2c_hist_fold(u64 h, u64 word_hash) { return b2c_mix64(h * 0xC2B2AE3D27D4EB4Full + word_hash + 1); }
 #define B2C_HIST_SEED 0x3C6EF372FE94F82Bull
+// the same chain as KenLM's probing search computes it (lm/search_hashed.hh: the node of a unigram is its word index,
+// detail::CombineWordHash extends it by one context word): tables read from a KenLM binary keep KenLM's own keys --
+// they cannot be re-keyed, the file stores the combined hash only
+B2C_HD u64 b2c_kenlm_start(u32 word) { return static_cast<u64>(word); }
+B2C_HD u64 b2c_kenlm_extend(u64 h, u32 ctx_word) {
+    return (h * 8978948897894561157ull) ^ ((static_cast<u64>(ctx_word) + 1) * 17894857484156487943ull);
+}
+enum { B2C_KEYS_B2C = 0, B2C_KEYS_KENLM = 1 };
 
 // order-preserving map double -> u64 (larger double -> larger key); NaN sorts above +inf
 B2C_HD u64 b2c_f64_key(double d) {
@@ -131,6 +139,8 @@ struct B2cLmView {
     u32 n_vocab;
     int have_unigrams;         // unigrams were given (reference: char_trie is not None)
     int n_unigrams;            // size of the filtered unigram set
+    int key_scheme;            // B2C_KEYS_*: how the keys of the n-gram table chain word ids
+    int pad_view;
     const B2cUni* uni;
     const B2cNgram* ngrams; u64 ngram_mask;
     const B2cVocab* vocab; u64 vocab_mask;

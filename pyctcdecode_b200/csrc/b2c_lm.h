@@ -70,10 +70,12 @@ B2C_HD float b2c_lm_base_score(const B2cLmView& lm, const B2cLmState& in, u32 w,
     out.words[0] = w;
     u32 out_len = b2c_has_extension(u.backoff) ? 1u : 0u;
     u32 matched = 1;
-    u64 h = b2c_ngram_start(w);
+    const bool kenlm_keys = lm.key_scheme == B2C_KEYS_KENLM;
+    u64 h = kenlm_keys ? b2c_kenlm_start(w) : b2c_ngram_start(w);
     for (u32 k = 0; k < in.length; ++k) {
         if (static_cast<int>(k) + 2 > lm.order) break;
-        h = b2c_ngram_extend(h, in.words[k]);
+        h = kenlm_keys ? b2c_kenlm_extend(h, in.words[k]) : b2c_ngram_extend(h, in.words[k]);
+        if (h == 0) break;      // 0 marks an empty slot (KenLM's tables reserve it as well)
         const B2cNgram* e = b2c_ngram_find(lm, h);
         if (!e) break;
         prob = e->prob;

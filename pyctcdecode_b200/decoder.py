@@ -627,8 +627,8 @@ def build_ctcdecoder(labels: List[str], kenlm_model_path: Optional[str] = None, 
                      alpha: float = DEFAULT_ALPHA, beta: float = DEFAULT_BETA,
                      unk_score_offset: float = DEFAULT_UNK_LOGP_OFFSET,
                      lm_score_boundary: bool = DEFAULT_SCORE_LM_BOUNDARY, device: Optional[int] = None) -> BeamSearchDecoderCTC:
-    """Same arguments and semantics as reference decoder.py:1051-1099; ``kenlm_model_path`` must be
-    an ARPA file (KenLM binaries are not readable without the kenlm package)."""
+    """Same arguments and semantics as reference decoder.py:1051-1099; ``kenlm_model_path`` is an ARPA file, a KenLM
+    binary of the probing model type, or a ``*.b2clm`` blob written by ``NgramModel.save_blob``."""
     from_blob = kenlm_model_path is not None and kenlm_model_path.endswith(NgramModel.BLOB_SUFFIX)
     if from_blob:
         # a flattened model written by NgramModel.save_blob: no ARPA parse; it carries its unigram / prefix sets

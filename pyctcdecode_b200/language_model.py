@@ -95,7 +95,8 @@ def load_unigram_set_from_arpa(arpa_path: str) -> Set[str]:
 
 
 class NgramModel:
-    """``kenlm.Model`` look-alike over the library's flattened n-gram tables (ARPA files only).
+    """``kenlm.Model`` look-alike over the library's flattened n-gram tables: ARPA files and KenLM binaries of the
+    probing model type (what ``build_binary`` writes by default; trie / quantised binaries raise).
 
     Covers the calls the reference makes on a kenlm model: ``word in model``, ``.order``,
     ``.path``, ``BeginSentenceWrite``, ``NullContextWrite``, ``BaseScore``."""
@@ -104,8 +105,6 @@ class NgramModel:
         self.path = os.path.abspath(path).encode("utf-8")
         if not os.path.exists(path):
             raise OSError("Cannot read model '%s'" % path)
-        if os.path.splitext(path)[1].lower() in (".bin", ".binary"):
-            raise ValueError("KenLM binary files cannot be read by pyctcdecode_b200; pass the .arpa file.")
         self._unigrams = None if unigrams is None else list(unigrams)
         self._handle = _handle
 
@@ -113,10 +112,10 @@ class NgramModel:
         if self._handle is None:
             out = C.c_void_p()
             if self._unigrams is None:
-                rc = _lib.lib().b2c_lm_build_from_arpa(self.path, None, -1, C.byref(out))
+                rc = _lib.lib().b2c_lm_build_from_file(self.path, None, -1, C.byref(out))
             else:
                 arr = _lib.cstr_array(self._unigrams)
-                rc = _lib.lib().b2c_lm_build_from_arpa(self.path, arr, len(self._unigrams), C.byref(out))
+                rc = _lib.lib().b2c_lm_build_from_file(self.path, arr, len(self._unigrams), C.byref(out))
             _lib.check(rc)
             self._handle = out.value
         return self._handle

@@ -447,3 +447,21 @@ def test_gpu_tensor_device_and_stream_order(pkg):
         assert dec.decode_batch(None, other, beam_width=50) == want          # unbound decoder: follows the tensor
         with pytest.raises(ValueError):
             dec.decode_batch(None, [dev[0], other[1]], beam_width=50)
+
+
+def test_gpu_kenlm_binary_equals_arpa(pkg, tmp_path):
+    """A KenLM binary (probing layout, written by tests/kenlm_binary.py) decodes on the device exactly like the ARPA
+    text of the same model: the device tables keep KenLM's own n-gram keys (csrc/b2c_lm.h key_scheme)."""
+    from tests import kenlm_binary
+
+    wl = synth.make_workload(dict(kind="char", vocab="B", n_words=2000, lm_order=4))
+    path = str(tmp_path / "model.binary")
+    kenlm_binary.write_probing_binary(wl.arpa, path)
+    kw = dict(unigrams=wl.words, alpha=0.6, beta=1.2)
+    dec_a = pkg.build_ctcdecoder(wl.labels, kenlm_model_path=wl.arpa, **kw)
+    dec_b = pkg.build_ctcdecoder(wl.labels, kenlm_model_path=path, **kw)
+    xs = wl.batch(70_000, 24, 300, "peaky") + wl.batch(71_000, 8, 200, "diffuse")
+    assert dec_a.decode_batch(None, xs, beam_width=100) == dec_b.decode_batch(None, xs, beam_width=100)
+    a = dec_a.decode_beams_batch(None, xs[:6], beam_width=50, hotwords=[wl.words[3]])
+    b = dec_b.decode_beams_batch(None, xs[:6], beam_width=50, hotwords=[wl.words[3]])
+    assert [_beams(x) for x in a] == [_beams(x) for x in b]

@@ -413,9 +413,10 @@ def test_hostsim_corrupt_blob_fields_are_rejected(sim, tmp_path):
     path = str(tmp_path / "lm.b2clm")
     dec._language_model.ngram_model.save_blob(path)
     good = open(path, "rb").read()
-    # header: magic u64, total u64, order i32, bos u32, eos u32, n_vocab u32, have i32, n_uni i32, then u64 offsets / masks
-    for off, fmt, bad in ((16, "<i", 99), (20, "<I", 0x7FFFFFFF), (40, "<Q", len(good) + 4096), (56, "<Q", 12345),
-                          (48, "<Q", len(good) - 8)):
+    # header: magic u64, total u64, order i32, bos u32, eos u32, n_vocab u32, have i32, n_uni i32, key scheme i32,
+    # reserved i32, then u64 off_uni, off_ngrams, ngram_mask, ...
+    for off, fmt, bad in ((16, "<i", 99), (20, "<I", 0x7FFFFFFF), (40, "<i", 7), (48, "<Q", len(good) + 4096), (64, "<Q", 12345),
+                          (56, "<Q", len(good) - 8)):
         data = bytearray(good)
         struct.pack_into(fmt, data, off, bad)
         bad_path = str(tmp_path / ("bad_%d.b2clm" % off))
@@ -436,3 +437,61 @@ def test_hostsim_on_reference_unstable_goldens(sim, name):
         return _beams(sim.build_ctcdecoder(labels).decode_beams(x, **kw))
 
     assert goldens.run_unstable_case(run, name) == ""
+
+
+@pytest.mark.parametrize("fam", ["B_3gram", "B_5gram", "C_bpe_4gram"])
+def test_hostsim_kenlm_binary_equals_arpa(sim, tmp_path, fam):
+    """KenLM binary files of the probing model type (reference decoder.py:1074 takes what kenlm.Model takes).
+    The same model as ARPA text and in the binary layout (written by tests/kenlm_binary.py, an independent Python
+    restatement of the published layout -- no kenlm-built file exists here, see csrc/b2c_lm_host.h) must give identical
+    host queries and identical decodes; the binary's tables keep KenLM's own n-gram keys."""
+    from tests import kenlm_binary
+
+    wkw, lmkw = FAMILIES[fam]
+    wl = synth.make_workload(wkw)
+    path = str(tmp_path / "model.binary")
+    info = kenlm_binary.write_probing_binary(wl.arpa, path)
+    assert info["order"] == wkw["lm_order"]
+    a = sim.NgramModel(wl.arpa, wl.words)
+    b = sim.NgramModel(path, wl.words)
+    assert b.order == a.order
+    from pyctcdecode_b200.language_model import B200LMState as LMS
+    rng = np.random.default_rng(5)
+    st_a, st_b = LMS(), LMS()
+    a.BeginSentenceWrite(st_a)
+    b.BeginSentenceWrite(st_b)
+    for i in range(300):
+        w = wl.words[int(rng.integers(len(wl.words)))] if i % 7 else "zzzunknown"
+        assert (w in a) == (w in b)
+        na, nb = LMS(), LMS()
+        assert a.BaseScore(st_a, w, na) == b.BaseScore(st_b, w, nb)
+        assert na.backoffs == nb.backoffs and len(na.words) == len(nb.words)
+        st_a, st_b = (na, nb) if i % 11 else (LMS(), LMS())
+    dec_a = sim.build_ctcdecoder(wl.labels, kenlm_model_path=wl.arpa, unigrams=wl.words, **lmkw)
+    dec_b = sim.build_ctcdecoder(wl.labels, kenlm_model_path=path, unigrams=wl.words, **lmkw)
+    for i in range(4):
+        x = wl.utterance(8800 + i, 70 if wl.V <= 64 else 30, ["peaky", "diffuse"][i % 2])
+        assert _beams(dec_a.decode_beams(x, beam_width=24, hotwords=[wl.words[4]])) == _beams(dec_b.decode_beams(x, beam_width=24, hotwords=[wl.words[4]]))
+
+
+def test_hostsim_kenlm_binary_rejects_what_it_cannot_read(sim, tmp_path):
+    from tests import kenlm_binary
+
+    wl = synth.make_workload(FAMILIES["B_3gram"][0])
+    path = str(tmp_path / "model.bin")
+    kenlm_binary.write_probing_binary(wl.arpa, path)
+    good = bytearray(open(path, "rb").read())
+    cases = {"trie.bin": (88 + 8, b"\x02\x00\x00\x00"),           # model_type = TRIE
+             "novocab.bin": (88 + 12, b"\x00"),                  # has_vocabulary = false
+             "counts.bin": (88 + 20, b"\x07\x00\x00\x00"),       # unigram count changed: the sections no longer line up
+             "version.bin": (49, b"4")}                          # format version 4
+    for name, (off, patch) in cases.items():
+        data = bytearray(good)
+        data[off:off + len(patch)] = patch
+        p = str(tmp_path / name)
+        open(p, "wb").write(bytes(data))
+        with pytest.raises((ValueError, OSError, RuntimeError)):
+            sim.NgramModel(p, wl.words).order          # the file is parsed when the model is first used
+    open(str(tmp_path / "cut.bin"), "wb").write(bytes(good[: len(good) * 2 // 3]))
+    with pytest.raises((ValueError, OSError, RuntimeError)):
+        sim.NgramModel(str(tmp_path / "cut.bin"), wl.words).order
