@@ -340,10 +340,10 @@ __global__ void __launch_bounds__(256) b2c_gather_kernel(const void* const* src,
     u32* o = dst + frame_off[u] * row_words;
     for (u64 i = static_cast<u64>(c) * blockDim.x + threadIdx.x; i < words; i += static_cast<u64>(chunks) * blockDim.x) o[i] = s[i];
 }
-template <class T>
-__global__ void __launch_bounds__(B2C_PREP_THREADS) b2c_rowsum_kernel(const B2cPrepArgs A) {
-    __shared__ double leaf_sums[B2C_PREP_WARPS * B2C_ROWSUM_MAX_LEAF];
-    b2c_rowsum_block<T>(A, static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x), leaf_sums);
+// float32, V <= 32: one lane per row, tiles of 32 rows brought in by bulk asynchronous copies (b2c_prepare.h)
+__global__ void __launch_bounds__(B2C_TILE_WARPS * 32) b2c_tokens_tile_kernel(const B2cPrepArgs A) {
+    __shared__ B2cTileShared sh;
+    b2c_tokens_tiles_v32(A, static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x), &sh);
 }
 template <class T>
 __global__ void __launch_bounds__(128) b2c_decide_kernel(const B2cPrepArgs A) {
@@ -501,7 +501,7 @@ struct b2c_decoder {
     std::vector<ExtraLm> lmx;
     int n_sm = 1;
     size_t smem_optin = 48 * 1024;
-    DevBuf d_raw, d_lmx, d_stream, d_mstats, d_sumk, d_clk, d_maxk, d_toks, d_logits, d_meta, d_tok_start, d_tok_ids, d_tok_lp, d_rowsum, d_set, d_isprob, d_ws, d_hot, d_states,
+    DevBuf d_raw, d_lmx, d_stream, d_mstats, d_sumk, d_clk, d_maxk, d_toks, d_logits, d_meta, d_tok_start, d_tok_ids, d_tok_lp, d_rowsum, d_set, d_isprob, d_approx, d_ws, d_hot, d_states,
         d_out_small, d_out_toks, d_out_frames;
     PinBuf h_sumk, h_maxk, h_meta, h_out_small, h_out_toks, h_out_frames;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -635,19 +635,26 @@ struct MetaHost {   // one pinned staging block -> one H2D copy
     std::vector<int> T, order;
 };
 
+// streaming pass (every utterance as logits) -> decide (exact only where the approximate mean row sum is near 1) ->
+// second pass over the utterances that turned out to be probabilities (returns at once when there is none)
 template <class T>
-static int launch_prepare(b2c_decoder* d, const B2cPrepArgs& A, int n_utts, int grid_rows, int grid_tok) {
+static int launch_prepare(b2c_decoder* d, const B2cPrepArgs& A0, int n_utts, int grid_tile, int grid_tok) {
+    B2cPrepArgs A = A0, A1 = A0;
+    A.mode = 0;
+    A1.mode = 1;
 #ifdef B2C_HOSTSIM
     (void)d;
-    for (int b = 0; b < grid_rows; ++b) b2c_rowsum_block<T>(A, b, grid_rows, nullptr);
-    std::unique_ptr<B2cDecideShared> dsh(new B2cDecideShared());
-    for (int u = 0; u < n_utts; ++u) b2c_decide_block<T>(A, u, dsh.get());
+    (void)grid_tile;
     std::unique_ptr<B2cPrepShared> sh(new B2cPrepShared());
     for (int b = 0; b < grid_tok; ++b) b2c_tokens_block<T>(A, b, grid_tok, sh.get());
+    std::unique_ptr<B2cDecideShared> dsh(new B2cDecideShared());
+    for (int u = 0; u < n_utts; ++u) b2c_decide_block<T>(A, u, dsh.get());
+    for (int b = 0; b < grid_tok; ++b) b2c_tokens_block<T>(A1, b, grid_tok, sh.get());
 #else
-    b2c_rowsum_kernel<T><<<grid_rows, B2C_PREP_THREADS, 0, d->stream>>>(A);
+    if (sizeof(T) == 4 && A.V <= 32) b2c_tokens_tile_kernel<<<grid_tile, B2C_TILE_WARPS * 32, 0, d->stream>>>(A);
+    else b2c_tokens_kernel<T><<<grid_tok, B2C_PREP_THREADS, 0, d->stream>>>(A);
     b2c_decide_kernel<T><<<n_utts, 128, 0, d->stream>>>(A);
-    b2c_tokens_kernel<T><<<grid_tok, B2C_PREP_THREADS, 0, d->stream>>>(A);
+    b2c_tokens_kernel<T><<<grid_tok, B2C_PREP_THREADS, 0, d->stream>>>(A1);
     CUDA_OK(cudaGetLastError());
 #endif
     return 0;
@@ -966,7 +973,7 @@ void b2c_decoder_destroy(b2c_decoder_t* d) {
     cudaSetDevice(d->device);
     if (d->stream) cudaStreamSynchronize(d->stream);
     DevBuf* bufs[] = {&d->d_raw, &d->d_lmx, &d->d_stream, &d->d_mstats, &d->d_sumk, &d->d_clk, &d->d_maxk, &d->d_toks, &d->d_logits, &d->d_meta, &d->d_tok_start, &d->d_tok_ids, &d->d_tok_lp, &d->d_rowsum, &d->d_set,
-                      &d->d_isprob, &d->d_ws, &d->d_hot, &d->d_states, &d->d_out_small, &d->d_out_toks, &d->d_out_frames};
+                      &d->d_isprob, &d->d_approx, &d->d_ws, &d->d_hot, &d->d_states, &d->d_out_small, &d->d_out_toks, &d->d_out_frames};
     for (DevBuf* b : bufs) b->release();
     PinBuf* pins[] = {&d->h_sumk, &d->h_maxk, &d->h_meta, &d->h_out_small, &d->h_out_toks, &d->h_out_frames};
     for (PinBuf* b : pins) b->release();
@@ -1170,18 +1177,20 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     }();
     if ((half_in || !contiguous_dev) && d->d_logits.ensure(std::max<u64>(total_frames * V * esz, 16))) return B2C_E_NOMEM;
     if (half_in && !contiguous_dev && d->d_raw.ensure(std::max<u64>(total_frames * V * esz_in, 16))) return B2C_E_NOMEM;
-    const size_t meta_bytes = al16(8ull * n_utts) + 3 * al16(4ull * n_utts) + 64 + al16(8ull * (n_utts + 1)) + al16(8ull * n_utts);
+    const size_t meta_bytes = al16(8ull * n_utts) + 3 * al16(4ull * n_utts) + 64 + 2 * al16(8ull * (n_utts + 1)) + al16(8ull * n_utts);
     if (d->d_meta.ensure(meta_bytes) || d->h_meta.ensure(meta_bytes)) return B2C_E_NOMEM;
     if (d->d_tok_start.ensure(sizeof(B2cFrameRec) * (total_frames + 1)) || d->d_tok_ids.ensure(4 * n_entries) ||
         d->d_tok_lp.ensure(8 * n_entries) || d->d_rowsum.ensure(std::max<u64>(8 * total_frames, 16)) ||
-        d->d_isprob.ensure(4ull * n_utts))
+        d->d_isprob.ensure(4ull * n_utts) || d->d_approx.ensure(16ull * n_utts + 16))
         return B2C_E_NOMEM;
     u32 set_cap = 16;
     while (set_cap < 8u * (static_cast<u32>(V) + 1)) set_cap <<= 1;
     std::vector<u64> run_off(n_utts + 1, 0);
     for (int i = 0; i < n_utts; ++i) run_off[i + 1] = run_off[i] + (static_cast<u64>(T[i]) + B2C_RUN - 1) / B2C_RUN;
     const u64 total_runs = run_off[n_utts];
-    const int grid_rows = static_cast<int>(std::max<u64>(1, std::min<u64>((total_frames + 31) / 32, static_cast<u64>(d->n_sm) * 8)));
+    std::vector<u64> tile_off(n_utts + 1, 0);
+    for (int i = 0; i < n_utts; ++i) tile_off[i + 1] = tile_off[i] + (static_cast<u64>(T[i]) + B2C_TILE_ROWS - 1) / B2C_TILE_ROWS;
+    const int grid_tile = static_cast<int>(std::max<u64>(1, std::min<u64>((tile_off[n_utts] + B2C_TILE_WARPS - 1) / B2C_TILE_WARPS, static_cast<u64>(d->n_sm) * 8)));
     const int grid_tok = static_cast<int>(std::max<u64>(1, std::min<u64>((total_runs + B2C_PREP_WARPS - 1) / B2C_PREP_WARPS, static_cast<u64>(d->n_sm) * 8)));
     if (V > 32) {
         if (d->d_set.ensure(2ull * set_cap * 2 * B2C_PREP_WARPS * grid_tok)) return B2C_E_NOMEM;
@@ -1211,11 +1220,14 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     u64* h_fo = reinterpret_cast<u64*>(hm);
     int* h_T = reinterpret_cast<int*>(hm + al16(8ull * n_utts));
     const size_t off_run = al16(8ull * n_utts) + al16(4ull * n_utts);
-    const size_t off_ord = off_run + al16(8ull * (n_utts + 1));
+    const size_t off_tile = off_run + al16(8ull * (n_utts + 1));
+    const size_t off_ord = off_tile + al16(8ull * (n_utts + 1));
     const size_t off_next = off_ord + 2 * al16(4ull * n_utts);
     const size_t off_ptr = off_next + 64;                        // [n_utts] source pointers (gather launch only)
     u64* h_run = reinterpret_cast<u64*>(hm + off_run);
     for (int i = 0; i <= n_utts; ++i) h_run[i] = run_off[i];
+    u64* h_tile = reinterpret_cast<u64*>(hm + off_tile);
+    for (int i = 0; i <= n_utts; ++i) h_tile[i] = tile_off[i];
     int* h_ord = reinterpret_cast<int*>(hm + off_ord);           // [2 * n_utts]: class lists, then retry list
     u32* h_next = reinterpret_cast<u32*>(hm + off_next);         // [16] one queue head per launch
     for (int i = 0; i < n_utts; ++i) { h_fo[i] = frame_off[i]; h_T[i] = T[i]; }
@@ -1325,36 +1337,16 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     PA.set_scratch = d->d_set.as<u16>();
     PA.set_cap = set_cap;
     PA.is_prob = d->d_isprob.as<int>();
-    if (V > 128) {   // leaves of numpy's pairwise recursion over a row of V elements, in visiting order
-        std::vector<std::pair<long, long>> st{{0, V}}, leaves;
-        while (!st.empty()) {
-            const auto f = st.back();
-            st.pop_back();
-            if (f.second <= 128) { leaves.push_back(f); continue; }
-            long n2 = f.second / 2;
-            n2 -= n2 % 8;
-            st.push_back({f.first + n2, f.second - n2});     // right half is visited after the left one
-            st.push_back({f.first, n2});
-        }
-        if (leaves.size() <= B2C_ROWSUM_MAX_LEAF) {
-            bool ok = true;
-            for (const auto& lf : leaves) ok = ok && lf.second >= 8;
-            if (ok) {
-                PA.n_leaf = static_cast<int>(leaves.size());
-                for (size_t i = 0; i < leaves.size(); ++i) {
-                    PA.leaf_off[i] = static_cast<u32>(leaves[i].first);
-                    PA.leaf_n[i] = static_cast<u32>(leaves[i].second);
-                }
-            }
-        }
-    }
+    PA.tile_off = reinterpret_cast<const u64*>(dm + off_tile);
+    PA.approx = d->d_approx.as<double>();
+    CUDA_OK(cudaMemsetAsync(d->d_approx.p, 0, 16ull * n_utts + 16, st));
     PA.max_k = d->d_maxk.as<u32>();
     PA.sum_k = d->d_sumk.as<u32>();
     CUDA_OK(cudaMemsetAsync(d->d_maxk.p, 0, 4ull * n_utts, st));
     CUDA_OK(cudaMemsetAsync(d->d_sumk.p, 0, 4ull * n_utts, st));
     CUDA_OK(cudaEventRecord(d->ev[1], st));
-    int rc = dtype == B2C_DTYPE_F32 ? launch_prepare<float>(d, PA, n_utts, grid_rows, grid_tok)
-                                    : launch_prepare<double>(d, PA, n_utts, grid_rows, grid_tok);
+    int rc = dtype == B2C_DTYPE_F32 ? launch_prepare<float>(d, PA, n_utts, grid_tile, grid_tok)
+                                    : launch_prepare<double>(d, PA, n_utts, grid_tile, grid_tok);
     if (rc) return rc;
     CUDA_OK(cudaEventRecord(d->ev[2], st));
     d->tm.launches += 3;

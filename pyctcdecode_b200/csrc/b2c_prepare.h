@@ -9,14 +9,22 @@
 // a row hit L1/L2), algorithmic bytes per frame = V * sizeof(dtype).
 //
 // Numerical definition shared with the oracle (oracle/ctc_oracle.cpp normalise_rows):
-//   logits branch  d = fl_T(x - max), S = sum exp((double)d) in "warp order" (32 lane-strided
-//                  partial sums, then xor butterfly 16,8,4,2,1), lp = fl_T((double)d - log S),
-//                  clipped in float64 to [log(1e-15), 0];
+//   logits branch, float32 (computed IN float32 like the reference, decoder.py:180-197):
+//                  d = x - max;  e = b2c_sm_expf(d) (fixed sequence of IEEE operations, b2c_softmath.h);
+//                  S = fl32(sum rint(e * 2^32)) * 2^-32 -- an INTEGER sum: exact, independent of the order of
+//                  summation, so one lane per row, one warp per row or any other decomposition gives the same bits;
+//                  lp = d - b2c_sm_logf(S), clipped in float64 to [log(1e-15), 0];
+//   logits branch, float64: d = x - max, S = sum exp(d) in "warp order" (32 lane-strided partial sums, then xor
+//                  butterfly 16,8,4,2,1), lp = d - log S (libm / CUDA double exp and log);
 //   probs branch   lp = fl_T(log((double)clip(x, fl_T(1e-15), 1)));
-//   the branch decision is math.isclose(x.sum(axis=1).mean(), 1) evaluated bit-exactly like
-//   numpy does (pairwise summation in the input dtype).
+//   the branch decision is math.isclose(x.sum(axis=1).mean(), 1) evaluated bit-exactly like numpy does (pairwise
+//   summation in the input dtype) -- but only for utterances whose approximate mean row sum is anywhere near 1: the
+//   streaming pass accumulates sum(x) and sum(|x|) per utterance, and an utterance with |mean - 1| > 0.01 + 1e-4 *
+//   mean|x| cannot be "probabilities" whatever the order of summation (numpy's float32 pairwise error is below
+//   2e-6 * mean|x|), so the exact evaluation -- a second read of the utterance -- happens for probability inputs only.
 #pragma once
 #include "b2c_cta.h"
+#include "b2c_softmath.h"
 
 // ---------------------------------------------------------------------------------------
 // numpy pairwise summation (numpy/_core/src/umath/loops_utils.h.src, PW_BLOCKSIZE = 128)
@@ -96,10 +104,32 @@ B2C_HD bool b2c_isclose_one(double x) {
 template <class T>
 B2C_HD double b2c_lp_logit(T x, T m, double ls) {
     const T d = x - m;
-    double lp = static_cast<double>(static_cast<T>(static_cast<double>(d) - ls));
+    // float32 rows: `ls` holds a float32 value and the subtraction is the float32 one (one rounding); float64: as is
+    double lp = sizeof(T) == 4 ? static_cast<double>(B2C_SM_ADD(static_cast<float>(d), -static_cast<float>(ls)))
+                               : static_cast<double>(d) - ls;
     if (lp < B2C_LOG_MIN_CLIP) lp = B2C_LOG_MIN_CLIP;
     if (lp > 0.0) lp = 0.0;
     return lp;
+}
+// the integer addend of one element in the softmax denominator of a float32 row, and the flags of the special values
+B2C_HD u64 b2c_sm_quantum(float e, bool& any_nan, bool& any_inf) {
+    if (!(e == e)) { any_nan = true; return 0; }
+    if (e > 1.0f) { any_inf = true; return 0; }          // only exp(+inf): d <= 0 for finite rows
+#if defined(__CUDA_ARCH__)
+    return __float2ull_rn(B2C_SM_MUL(e, 4294967296.0f));
+#else
+    return static_cast<u64>(llrintf(e * 4294967296.0f));
+#endif
+}
+B2C_HD float b2c_sm_finish(u64 q, bool any_nan, bool any_inf) {
+    if (any_nan) return b2c_sm_from_bits(0x7FC00000u);
+    if (any_inf) return b2c_sm_from_bits(0x7F800000u);
+#if defined(__CUDA_ARCH__)
+    const float S = B2C_SM_MUL(__ull2float_rn(q), 2.3283064365386963e-10f);
+#else
+    const float S = static_cast<float>(q) * 2.3283064365386963e-10f;
+#endif
+    return b2c_sm_logf(S);
 }
 template <class T>
 B2C_HD double b2c_lp_prob(T x) {
@@ -240,14 +270,13 @@ struct B2cPrepArgs {
     B2cFrameRec* tok_rec;    // [total_frames]
     u32* tok_ids;            // [total_frames * V]  (32-bit: the beam kernel stages them with 4-byte cp.async)
     double* tok_lp;
-    void* rowsum;            // [total_frames] scratch, input dtype
+    void* rowsum;            // [total_frames] scratch, input dtype (exact numpy row sums, probability-like utterances only)
     u16* set_scratch;        // [total warps][2][set_cap] spill space for large token sets
     u32 set_cap;             // power of two >= 8 * (V + 1)
-    // leaves (<= 128 elements) of numpy's pairwise recursion over one row, in visiting order; n_leaf == 0:
-    // not tabulated (V <= 128 needs no table, very long rows use the per-thread path)
-    int n_leaf;
-    u32 leaf_off[B2C_ROWSUM_MAX_LEAF];
-    u32 leaf_n[B2C_ROWSUM_MAX_LEAF];
+    int mode;                // 0: streaming pass (every utterance as logits, approximate row sums accumulated);
+                             // 1: second pass over the utterances the decide kernel found to be probabilities
+    double* approx;          // [B][2] sum of all elements, sum of their absolute values (zeroed before the launch)
+    const u64* tile_off;     // [B+1] exclusive prefix of ceil(T/32): work items of the lane-per-row kernel (V <= 32)
     int* is_prob;            // [B]
     u32* max_k;              // [B] largest per-frame token count (zeroed before the launch)
     u32* sum_k;              // [B] total number of selected tokens (zeroed before the launch)
@@ -261,84 +290,41 @@ struct B2cLeafShared {
     B2C_HD T operator()(long, long) const { return static_cast<T>(sums[next++]); }
 };
 
-template <class T>
-B2C_HD void b2c_rowsum_block(const B2cPrepArgs& A, int block_idx, int n_blocks, double* leaf_sums) {
-    const T* x = static_cast<const T*>(A.logits);
-    T* rs = static_cast<T*>(A.rowsum);
-    const int V = A.V;
+B2C_HD void b2c_atomic_add_f64(double* p, double v) {
 #if defined(__CUDA_ARCH__)
-    const unsigned full = 0xFFFFFFFFu;
-    const int lane = threadIdx.x & 31, j = lane & 7, g = lane >> 3;
-    const u64 warp = static_cast<u64>(block_idx) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const u64 n_warps = static_cast<u64>(n_blocks) * (blockDim.x >> 5);
-    if (V >= 8 && V <= 128) {
-        // numpy's 8 accumulators are the 8 lanes of a group; xor-butterfly 1,2,4 reproduces
-        // ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)); the tail (n % 8) is added sequentially
-        const int body = V - (V % 8);
-        for (u64 r0 = warp * 4; r0 < A.total_frames; r0 += n_warps * 4) {
-            const u64 r = r0 + g;
-            const bool ok = r < A.total_frames;
-            const T* a = x + (ok ? r : 0) * static_cast<u64>(V);
-            T acc = a[j];
-            for (int i = 8; i < body; i += 8) acc = acc + a[i + j];
-            acc = acc + __shfl_xor_sync(full, acc, 1);
-            acc = acc + __shfl_xor_sync(full, acc, 2);
-            acc = acc + __shfl_xor_sync(full, acc, 4);
-            for (int i = body; i < V; ++i) acc = acc + a[i];
-            if (ok && j == 0) rs[r] = acc;
-        }
-        return;
-    }
-    if (A.n_leaf > 0) {
-        // long rows (V > 128): one warp per row, four leaves at a time (8 lanes = numpy's 8 accumulators of a
-        // leaf, 32-byte sectors fully used), then the recursion over the leaf sums by lane 0
-        const int wib = static_cast<int>(threadIdx.x >> 5);
-        for (u64 r = warp; r < A.total_frames; r += n_warps) {
-            const T* a = x + r * static_cast<u64>(V);
-            for (int l0 = 0; l0 < A.n_leaf; l0 += 4) {
-                const int lf = l0 + g;
-                const bool ok = lf < A.n_leaf;
-                const u32 off = ok ? A.leaf_off[lf] : 0u;
-                const int n = ok ? static_cast<int>(A.leaf_n[lf]) : 8;
-                T res;
-                if (n < 8) {
-                    res = static_cast<T>(-0.0);
-                    for (int i = 0; i < n; ++i) res = res + a[off + i];
-                } else {
-                    const int body = n - (n % 8);
-                    T acc = a[off + j];
-                    for (int i = 8; i < body; i += 8) acc = acc + a[off + i + j];
-                    acc = acc + __shfl_xor_sync(full, acc, 1);
-                    acc = acc + __shfl_xor_sync(full, acc, 2);
-                    acc = acc + __shfl_xor_sync(full, acc, 4);
-                    for (int i = body; i < n; ++i) acc = acc + a[off + i];
-                    res = acc;
-                }
-                if (ok && j == 0) leaf_sums[wib * B2C_ROWSUM_MAX_LEAF + lf] = static_cast<double>(res);
-            }
-            __syncwarp();
-            if (lane == 0) {
-                B2cLeafShared<T> lfn;
-                lfn.sums = leaf_sums + wib * B2C_ROWSUM_MAX_LEAF;
-                lfn.next = 0;
-                rs[r] = b2c_np_pairwise_generic<T>(V, lfn);
-            }
-            __syncwarp();
-        }
-        return;
-    }
-    // generic: one thread per row, numpy's recursion evaluated sequentially
-    for (u64 r = warp * 32 + lane; r < A.total_frames; r += n_warps * 32) rs[r] = b2c_np_pairwise<T>(x + r * static_cast<u64>(V), V);
+    atomicAdd(p, v);
 #else
-    if (block_idx == 0)
-        for (u64 r = 0; r < A.total_frames; ++r) rs[r] = b2c_np_pairwise<T>(x + r * static_cast<u64>(V), V);
-    (void)n_blocks;
-    (void)leaf_sums;
+    *p += v;
+#endif
+}
+
+// streaming pass: sum(x) and sum(|x|) of `n` consecutive elements (the rows of one run / tile are adjacent) added to
+// the utterance's accumulators; one warp, coalesced
+template <class T>
+B2C_HD void b2c_accum_approx(double* acc, const T* x, long n, int lane) {
+#if defined(__CUDA_ARCH__)
+    double sx = 0.0, sa = 0.0;
+    for (long i = lane; i < n; i += 32) {
+        const double v = static_cast<double>(x[i]);
+        sx += v;
+        sa += fabs(v);
+    }
+    for (int off = 16; off >= 1; off >>= 1) {
+        sx += __shfl_xor_sync(0xFFFFFFFFu, sx, off);
+        sa += __shfl_xor_sync(0xFFFFFFFFu, sa, off);
+    }
+    if (lane == 0) { atomicAdd(acc, sx); atomicAdd(acc + 1, sa); }
+#else
+    (void)lane;
+    double sx = 0.0, sa = 0.0;
+    for (long i = 0; i < n; ++i) { sx += static_cast<double>(x[i]); sa += fabs(static_cast<double>(x[i])); }
+    acc[0] += sx;
+    acc[1] += sa;
 #endif
 }
 
 // ---- decide ---------------------------------------------------------------------------------
-struct B2cDecideShared { double leaf_sum[B2C_PREP_LEAF_CAP]; };
+struct B2cDecideShared { double leaf_sum[B2C_PREP_LEAF_CAP]; int far; };
 
 B2C_HD int b2c_count_leaves(long n) {
     long st[48];
@@ -358,6 +344,21 @@ B2C_HD int b2c_count_leaves(long n) {
 template <class T>
 B2C_HD void b2c_decide_block(const B2cPrepArgs& A, int u, B2cDecideShared* sh) {
     const int Tn = A.T[u];
+    // far from 1 by a margin no order of summation can bridge -> logits, nothing else to do (see the file header)
+    B2C_LEADER {
+        const double mean = Tn > 0 ? A.approx[2 * u] / Tn : 0.0, mabs = Tn > 0 ? A.approx[2 * u + 1] / Tn : 0.0;
+        sh->far = (Tn == 0 || fabs(mean - 1.0) > 0.01 + 1e-4 * mabs) ? 1 : 0;
+        if (sh->far) A.is_prob[u] = 0;
+    }
+    B2C_SYNC();
+    if (sh->far) return;
+    // exact: numpy-order row sums of this utterance (one row per thread; probability-like input only)
+    {
+        const T* x = static_cast<const T*>(A.logits) + A.frame_off[u] * static_cast<u64>(A.V);
+        T* out = static_cast<T*>(A.rowsum) + A.frame_off[u];
+        B2C_FOR(r, Tn) { out[r] = b2c_np_pairwise<T>(x + static_cast<u64>(r) * A.V, A.V); }
+    }
+    B2C_SYNC();
     const T* rs = static_cast<const T*>(A.rowsum) + A.frame_off[u];
     const int n_leaf = b2c_count_leaves(Tn);
     const bool par_leaves = n_leaf <= B2C_PREP_LEAF_CAP && Tn > 128;
@@ -391,6 +392,11 @@ B2C_HD void b2c_decide_block(const B2cPrepArgs& A, int u, B2cDecideShared* sh) {
             isp = b2c_isclose_one(static_cast<double>(mean)) ? 1 : 0;
         }
         A.is_prob[u] = isp;
+        if (isp) {                                          // the second pass recounts this utterance's tokens
+            A.max_k[u] = 0;
+            A.sum_k[u] = 0;
+            b2c_atomic_or_u32(reinterpret_cast<u32*>(A.approx + 2 * A.n_utts), 1u);     // "some utterance is probabilities"
+        }
     }
 }
 
@@ -407,6 +413,65 @@ B2C_HD void b2c_prep_row(const T* row, int V, bool is_prob, double thr, int lane
     const unsigned full = 0xFFFFFFFFu;
     T m = static_cast<T>(0);
     double ls = 0.0;
+    if (sizeof(T) == 4 && !is_prob && !kMaskOnly && V > 32 && V <= 1024 && thr > B2C_LOG_MIN_CLIP) {
+        // float32 logits, wide rows (BPE vocabularies): the row is read ONCE into registers (32 elements per lane),
+        // everything is float32 (same definition, same bits as the general code below: the sum is an integer sum,
+        // the selection compares against thr rounded up to float32, the clip cannot move the arg-max); rows with a
+        // NaN or an infinity take the general code
+        const float* frow = reinterpret_cast<const float*>(row);
+        float r[32];
+        float sa = 0.0f, mx = -3.402823466e38f;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            const int v = c * 32 + lane;
+            r[c] = v < V ? frow[v] : -3.402823466e38f;
+            if (v < V) { sa += fabsf(r[c]); mx = fmaxf(mx, r[c]); }
+        }
+        for (int off = 16; off >= 1; off >>= 1) {
+            sa += __shfl_xor_sync(full, sa, off);
+            mx = fmaxf(mx, __shfl_xor_sync(full, mx, off));
+        }
+        if (sa < 3.0e38f) {                                     // warp-uniform: no NaN, no infinity
+            u64 q = 0;
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+                if (c * 32 + lane < V) q += __float2ull_rn(B2C_SM_MUL(b2c_sm_expf(r[c] - mx), 4294967296.0f));
+            for (int off = 16; off >= 1; off >>= 1) q += __shfl_xor_sync(full, q, off);
+            const float lsf = b2c_sm_finish(q, false, false);
+            const float thr_up = __double2float_ru(thr);
+            float bestf = -3.402823466e38f;
+            int bi = -1;
+            u32 nsel = 0;
+            if (lane == 0) b2c_pyset_init(set, set.buf[0], set.buf[1]);
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                if (c * 32 >= V) continue;                            // warp-uniform; r[] stays in registers (static indices)
+                const int v = c * 32 + lane;
+                const float lpf = B2C_SM_ADD(r[c] - mx, -lsf);
+                const bool in = v < V;
+                if (in && lpf > bestf) { bestf = lpf; bi = v; }       // ascending v per lane: the first of equals stays
+                unsigned mask = __ballot_sync(full, in && lpf >= thr_up);
+                if (mask) {                                          // warp-uniform
+                    nsel += __popc(mask);
+                    if (lane == 0) {
+                        while (mask) {
+                            const int bit = __ffs(mask) - 1;
+                            mask &= mask - 1;
+                            b2c_pyset_add(set, static_cast<u32>(c * 32 + bit));
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            for (int off = 16; off >= 1; off >>= 1) {
+                const float ob = __shfl_xor_sync(full, bestf, off);
+                const int oi = __shfl_xor_sync(full, bi, off);
+                if (oi >= 0 && (bi < 0 || ob > bestf || (ob == bestf && oi < bi))) { bestf = ob; bi = oi; }
+            }
+            m_out = static_cast<T>(mx); ls_out = static_cast<double>(lsf); amax_out = bi; nsel_out = nsel;
+            return;
+        }
+    }
     if (!is_prob) {
         bool have = false;
         for (int v = lane; v < V; v += 32) {
@@ -419,10 +484,18 @@ B2C_HD void b2c_prep_row(const T* row, int V, bool is_prob, double thr, int lane
             if (oh && (!have || o > m)) { m = o; have = true; }
         }
         if (!(static_cast<double>(m) - static_cast<double>(m) == 0.0)) m = static_cast<T>(0);
-        double part = 0.0;
-        for (int v = lane; v < V; v += 32) part += exp(static_cast<double>(static_cast<T>(row[v] - m)));
-        for (int off = 16; off >= 1; off >>= 1) part = part + __shfl_xor_sync(full, part, off);
-        ls = log(part);
+        if (sizeof(T) == 4) {
+            u64 q = 0;
+            bool nn = false, ni = false;
+            for (int v = lane; v < V; v += 32) q += b2c_sm_quantum(b2c_sm_expf(static_cast<float>(row[v] - m)), nn, ni);
+            for (int off = 16; off >= 1; off >>= 1) q += __shfl_xor_sync(full, q, off);
+            ls = static_cast<double>(b2c_sm_finish(q, __any_sync(full, nn), __any_sync(full, ni)));
+        } else {
+            double part = 0.0;
+            for (int v = lane; v < V; v += 32) part += exp(static_cast<double>(static_cast<T>(row[v] - m)));
+            for (int off = 16; off >= 1; off >>= 1) part = part + __shfl_xor_sync(full, part, off);
+            ls = log(part);
+        }
     }
     double best = 0.0;
     int besti = -1;
@@ -462,18 +535,25 @@ B2C_HD void b2c_prep_row(const T* row, int V, bool is_prob, double thr, int lane
         m = row[0];
         for (int v = 1; v < V; ++v) if (row[v] > m) m = row[v];
         if (!(static_cast<double>(m) - static_cast<double>(m) == 0.0)) m = static_cast<T>(0);
-        double part[32];
-        for (int l = 0; l < 32; ++l) {
-            double s = 0.0;
-            for (int v = l; v < V; v += 32) s += exp(static_cast<double>(static_cast<T>(row[v] - m)));
-            part[l] = s;
+        if (sizeof(T) == 4) {
+            u64 q = 0;
+            bool nn = false, ni = false;
+            for (int v = 0; v < V; ++v) q += b2c_sm_quantum(b2c_sm_expf(static_cast<float>(row[v] - m)), nn, ni);
+            ls = static_cast<double>(b2c_sm_finish(q, nn, ni));
+        } else {
+            double part[32];
+            for (int l = 0; l < 32; ++l) {
+                double s = 0.0;
+                for (int v = l; v < V; v += 32) s += exp(static_cast<double>(static_cast<T>(row[v] - m)));
+                part[l] = s;
+            }
+            for (int off = 16; off >= 1; off >>= 1) {
+                double nxt[32];
+                for (int l = 0; l < 32; ++l) nxt[l] = part[l] + part[l ^ off];
+                for (int l = 0; l < 32; ++l) part[l] = nxt[l];
+            }
+            ls = log(part[0]);
         }
-        for (int off = 16; off >= 1; off >>= 1) {
-            double nxt[32];
-            for (int l = 0; l < 32; ++l) nxt[l] = part[l] + part[l ^ off];
-            for (int l = 0; l < 32; ++l) part[l] = nxt[l];
-        }
-        ls = log(part[0]);
     }
     double best = 0.0;
     int besti = -1;
@@ -540,9 +620,11 @@ B2C_HD void b2c_tokens_run_v32(const B2cPrepArgs& A, u64 run, int lane, u16* set
     const int nf = t1 - t0;
     const int V = A.V;
     const u64 f0 = A.frame_off[u];
-    const bool is_prob = A.is_prob[u] != 0;
+    if (A.mode == 1 && A.is_prob[u] == 0) return;          // second pass: probability utterances only
+    const bool is_prob = A.mode == 1;
     const T* x = static_cast<const T*>(A.logits) + f0 * static_cast<u64>(V);
     const u64 base = (f0 + static_cast<u64>(t0)) * static_cast<u64>(V);
+    if (A.mode == 0) b2c_accum_approx<T>(A.approx + 2 * u, x + static_cast<u64>(t0) * V, static_cast<long>(nf) * V, lane);
     u32* ids = A.tok_ids + base;
     double* lps = A.tok_lp + base;
     B2cPySet set;
@@ -553,54 +635,7 @@ B2C_HD void b2c_tokens_run_v32(const B2cPrepArgs& A, u64 run, int lane, u16* set
     u32 my_mask = 0, my_amax = 0;
     T my_m = static_cast<T>(0);
     double my_ls = 0.0;
-    if (sizeof(T) == 4 && !is_prob) {
-        // float32 logits (the common case), same arithmetic as b2c_prep_row with far fewer instructions:
-        // row max and argmax through REDUX on order-preserving integer keys, log(sum) once per RUN (lane f
-        // takes frame f), the 8 rows of the run held in registers
-        const bool has = lane < V;
-        float d[B2C_RUN];
-        double my_S = 1.0;
-#pragma unroll
-        for (int f = 0; f < B2C_RUN; ++f)      // all rows of the run in flight before the first reduction
-            d[f] = (has && f < nf) ? static_cast<float>(x[static_cast<u64>(t0 + f) * V + lane]) : 0.0f;
-#pragma unroll
-        for (int f = 0; f < B2C_RUN; ++f) {
-            if (f < nf) {
-                const float xv = d[f];
-                // max over the row: int order == float order on these keys (NaN sorts above +inf -> non-finite -> 0)
-                const u32 xb = __float_as_uint(xv);
-                const u32 key = has ? ((xb & 0x80000000u) ? ~xb : (xb | 0x80000000u)) : 0u;
-                const u32 km = __reduce_max_sync(full, key);
-                float m = __uint_as_float((km & 0x80000000u) ? (km & 0x7FFFFFFFu) : ~km);
-                if (!(static_cast<double>(m) - static_cast<double>(m) == 0.0)) m = 0.0f;
-                d[f] = xv - m;
-                double part = has ? exp(static_cast<double>(d[f])) : 0.0;
-                for (int off = 16; off >= 1; off >>= 1) part = part + __shfl_xor_sync(full, part, off);
-                if (lane == f) { my_S = part; my_m = static_cast<T>(m); }
-            }
-        }
-        my_ls = log(my_S);
-#pragma unroll
-        for (int f = 0; f < B2C_RUN; ++f) {
-            if (f < nf) {
-                const double ls = __shfl_sync(full, my_ls, f);
-                double lp = static_cast<double>(static_cast<float>(static_cast<double>(d[f]) - ls));
-                if (lp < B2C_LOG_MIN_CLIP) lp = B2C_LOG_MIN_CLIP;
-                if (lp > 0.0) lp = 0.0;
-                const u32 mask = __ballot_sync(full, has && lp >= A.token_min_logp);
-                // argmax like the sequential scan: the first element wins if it is NaN, otherwise the largest
-                // non-NaN value, lowest index among equals
-                const float lpf = static_cast<float>(lp);
-                const u32 lb = __float_as_uint(lpf);
-                const u32 lkey = (has && lpf == lpf) ? ((lb & 0x80000000u) ? ~lb : (lb | 0x80000000u)) : 0u;
-                const u32 lmax = __reduce_max_sync(full, lkey);
-                const u32 eq = __ballot_sync(full, has && lkey == lmax);
-                const u32 first_nan = __ballot_sync(full, lane == 0 && !(lpf == lpf));
-                const u32 amax = (first_nan || eq == 0) ? 0u : static_cast<u32>(__ffs(static_cast<int>(eq)) - 1);
-                if (lane == f) { my_mask = mask; my_amax = amax; }
-            }
-        }
-    } else {
+    {
         for (int f = 0; f < nf; ++f) {
             T m;
             double ls;
@@ -750,9 +785,11 @@ B2C_HD void b2c_tokens_run(const B2cPrepArgs& A, u64 run, int lane, u16* set0, u
     const int t1 = t0 + B2C_RUN < Tn ? t0 + B2C_RUN : Tn;
     const int V = A.V;
     const u64 f0 = A.frame_off[u];
-    const bool is_prob = A.is_prob[u] != 0;
+    if (A.mode == 1 && A.is_prob[u] == 0) return;          // second pass: probability utterances only
+    const bool is_prob = A.mode == 1;
     const T* x = static_cast<const T*>(A.logits) + f0 * static_cast<u64>(V);
     const u64 base = (f0 + static_cast<u64>(t0)) * static_cast<u64>(V);
+    if (A.mode == 0) b2c_accum_approx<T>(A.approx + 2 * u, x + static_cast<u64>(t0) * V, static_cast<long>(t1 - t0) * V, lane);
     u32* ids = A.tok_ids + base;
     double* lps = A.tok_lp + base;
     u32 off = 0, mx = 0;
@@ -801,6 +838,7 @@ template <class T>
 B2C_HD void b2c_tokens_block(const B2cPrepArgs& A, int block_idx, int n_blocks, B2cPrepShared* sh) {
     const u64 total_runs = A.run_off[A.n_utts];
     const bool small = A.V <= 32;
+    if (A.mode == 1 && *reinterpret_cast<const u32*>(A.approx + 2 * A.n_utts) == 0) return;   // no probability input
 #if defined(__CUDA_ARCH__)
     const int w = static_cast<int>(threadIdx.x >> 5), lane = static_cast<int>(threadIdx.x & 31);
     const u64 gw = static_cast<u64>(block_idx) * B2C_PREP_WARPS + w;
@@ -822,3 +860,315 @@ B2C_HD void b2c_tokens_block(const B2cPrepArgs& A, int block_idx, int n_blocks, 
     }
 #endif
 }
+
+// ---------------------------------------------------------------------------------------
+// float32 logits, V <= 32: ONE LANE PER ROW.  A warp takes a tile of 32 consecutive frames of one utterance (4 runs);
+// the tile (<= 4 KB) is brought into shared memory by ONE bulk asynchronous copy (cp.async.bulk + mbarrier, the next
+// tile in flight while the current one is processed; rows that are not 16-byte aligned take a coalesced load
+// instead) and every lane walks its own row three times out of shared memory, in an order rotated by its lane index
+// so that the 32 lanes hit 32 different banks: maximum, sum of exponentials (an integer sum: the order of the walk
+// does not matter, see the file header), log-probabilities / selection mask / arg-max.  No shuffle, no ballot and
+// no float64 transcendental per element: ~35 warp instructions per row instead of ~350.  The (typically 1-3)
+// selected tokens are ordered like CPython's set iteration and written by the row's lane; frames with more than
+// three selected tokens fall back to the warp-cooperative set emulation at offsets that are already known.
+// Streaming pass only (mode 0); hostsim and the second pass use b2c_tokens_run_v32.
+// ---------------------------------------------------------------------------------------
+#define B2C_TILE_WARPS 4
+#define B2C_TILE_ROWS 32
+#if defined(__CUDACC__)
+struct B2cTileShared {
+    alignas(128) float tile[B2C_TILE_WARPS][2][B2C_TILE_ROWS * 32];
+    alignas(8) u64 mbar[B2C_TILE_WARPS][2];
+    u16 sets[B2C_TILE_WARPS][2][B2C_PREP_SMEM_SET];
+};
+
+struct B2cTileInfo { int u, t0, nrows; const float* src; u32 bytes; bool bulk; };
+
+__device__ __forceinline__ B2cTileInfo b2c_tile_locate(const B2cPrepArgs& A, u64 tile) {
+    int lo = 0, hi = A.n_utts - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (A.tile_off[mid] <= tile) lo = mid; else hi = mid - 1;
+    }
+    B2cTileInfo ti;
+    ti.u = lo;
+    const int Tn = A.T[lo];
+    ti.t0 = static_cast<int>(tile - A.tile_off[lo]) * B2C_TILE_ROWS;
+    ti.nrows = Tn - ti.t0 < B2C_TILE_ROWS ? Tn - ti.t0 : B2C_TILE_ROWS;
+    ti.src = static_cast<const float*>(A.logits) + (A.frame_off[lo] + static_cast<u64>(ti.t0)) * static_cast<u64>(A.V);
+    ti.bytes = static_cast<u32>(ti.nrows) * static_cast<u32>(A.V) * 4u;
+    ti.bulk = (reinterpret_cast<u64>(ti.src) & 15ull) == 0 && (ti.bytes & 15u) == 0;
+    return ti;
+}
+
+__device__ __forceinline__ void b2c_tile_issue(const B2cTileInfo& ti, float* dst, u64* mbar, int lane) {
+    if (ti.bulk && lane == 0) {
+        const u32 bar = static_cast<u32>(__cvta_generic_to_shared(mbar));
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(ti.bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         static_cast<u32>(__cvta_generic_to_shared(dst))),
+                     "l"(ti.src), "r"(ti.bytes), "r"(bar)
+                     : "memory");
+    }
+}
+__device__ __forceinline__ void b2c_tile_wait(u64* mbar, u32 parity) {
+    const u32 bar = static_cast<u32>(__cvta_generic_to_shared(mbar));
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "B2C_TILE_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra B2C_TILE_DONE;\n"
+        "bra B2C_TILE_WAIT;\n"
+        "B2C_TILE_DONE:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+
+__device__ inline void b2c_tokens_tiles_v32(const B2cPrepArgs& A, int block_idx, int n_blocks, B2cTileShared* sh) {
+    const unsigned full = 0xFFFFFFFFu;
+    const int w = static_cast<int>(threadIdx.x >> 5), lane = static_cast<int>(threadIdx.x & 31);
+    const u64 total = A.tile_off[A.n_utts];
+    const u64 gw = static_cast<u64>(block_idx) * B2C_TILE_WARPS + w, n_warps = static_cast<u64>(n_blocks) * B2C_TILE_WARPS;
+    const int V = A.V;
+    if (lane == 0) {
+        for (int b = 0; b < 2; ++b) {
+            const u32 bar = static_cast<u32>(__cvta_generic_to_shared(&sh->mbar[w][b]));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    u32 parity[2] = {0u, 0u};
+    int buf = 0;
+    if (gw >= total) return;
+    B2cTileInfo cur = b2c_tile_locate(A, gw);
+    b2c_tile_issue(cur, sh->tile[w][0], &sh->mbar[w][0], lane);
+    const int lr = lane % V;                 // rotation of this lane's walk over its row
+    const double thr = A.token_min_logp;
+    for (u64 tile = gw; tile < total; tile += n_warps) {
+        B2cTileInfo nxt;
+        nxt.nrows = 0;
+        const bool has_next = tile + n_warps < total;
+        if (has_next) {
+            nxt = b2c_tile_locate(A, tile + n_warps);
+            b2c_tile_issue(nxt, sh->tile[w][buf ^ 1], &sh->mbar[w][buf ^ 1], lane);
+        }
+        float* T0 = sh->tile[w][buf];
+        if (cur.bulk) {
+            b2c_tile_wait(&sh->mbar[w][buf], parity[buf]);
+            parity[buf] ^= 1u;
+        } else {
+            const int n = cur.nrows * V;
+            for (int i = lane; i < n; i += 32) T0[i] = cur.src[i];
+            __syncwarp();
+        }
+        // ---- one row per lane ----------------------------------------------------------------------------------
+        const bool mine = lane < cur.nrows;
+        const float* row = T0 + lane * V;
+        u32 mask = 0, amax = 0;
+        float m = 0.0f, lsf = 0.0f, sx = 0.0f, sa = 0.0f;
+        bool odd_row = false;       // a NaN / infinity in the row: the warp-cooperative general path decides everything
+        if (mine) {
+            if (V == 32) {
+                // rows of exactly 32 float32: four elements per shared-memory access (LDS.128), quads rotated by the
+                // lane index (8 lanes of a quarter warp -> 8 different quads -> no bank conflict)
+                // pass 1: maximum, sums
+                float mx = -3.402823466e38f;
+#pragma unroll
+                for (int qq = 0; qq < 8; ++qq) {
+                    const float4 v = *reinterpret_cast<const float4*>(row + 4 * ((qq + lane) & 7));
+                    sx += (v.x + v.y) + (v.z + v.w);
+                    sa += (fabsf(v.x) + fabsf(v.y)) + (fabsf(v.z) + fabsf(v.w));
+                    mx = fmaxf(fmaxf(mx, v.x), fmaxf(v.y, fmaxf(v.z, v.w)));
+                }
+                odd_row = !(sa < 3.0e38f);                          // NaN or infinity somewhere (or a sum that overflows)
+                m = mx;
+                // pass 2: softmax denominator, integer sum (order free)
+                u64 qs = 0;
+#pragma unroll
+                for (int qq = 0; qq < 8; ++qq) {
+                    const float4 v = *reinterpret_cast<const float4*>(row + 4 * ((qq + lane) & 7));
+                    qs += __float2ull_rn(B2C_SM_MUL(b2c_sm_expf(v.x - m), 4294967296.0f));
+                    qs += __float2ull_rn(B2C_SM_MUL(b2c_sm_expf(v.y - m), 4294967296.0f));
+                    qs += __float2ull_rn(B2C_SM_MUL(b2c_sm_expf(v.z - m), 4294967296.0f));
+                    qs += __float2ull_rn(B2C_SM_MUL(b2c_sm_expf(v.w - m), 4294967296.0f));
+                }
+                lsf = b2c_sm_finish(qs, false, false);
+                // pass 3 in float32: (double)lp >= thr  <=>  lp >= thr rounded up to float32; the clip at log(1e-15)
+                // cannot move the arg-max and matters for the mask only when thr is below it (thr_all)
+                const float thr_up = __double2float_ru(thr);
+                const bool thr_all = thr <= B2C_LOG_MIN_CLIP;
+                float best = -3.402823466e38f;
+                u32 bi = 32;
+#pragma unroll
+                for (int qq = 0; qq < 8; ++qq) {
+                    const u32 j0 = 4u * ((qq + lane) & 7);
+                    const float4 v = *reinterpret_cast<const float4*>(row + j0);
+                    const float l0 = B2C_SM_ADD(v.x - m, -lsf), l1 = B2C_SM_ADD(v.y - m, -lsf), l2 = B2C_SM_ADD(v.z - m, -lsf),
+                                l3 = B2C_SM_ADD(v.w - m, -lsf);
+                    const u32 bits = (l0 >= thr_up ? 1u : 0u) | (l1 >= thr_up ? 2u : 0u) | (l2 >= thr_up ? 4u : 0u) | (l3 >= thr_up ? 8u : 0u);
+                    mask |= (thr_all ? 15u : bits) << j0;
+                    // largest value, lowest index among equals (the quads are visited in a rotated order)
+                    if (l0 > best || (l0 == best && j0 < bi)) { best = l0; bi = j0; }
+                    if (l1 > best || (l1 == best && j0 + 1 < bi)) { best = l1; bi = j0 + 1; }
+                    if (l2 > best || (l2 == best && j0 + 2 < bi)) { best = l2; bi = j0 + 2; }
+                    if (l3 > best || (l3 == best && j0 + 3 < bi)) { best = l3; bi = j0 + 3; }
+                }
+                amax = bi & 31u;
+            } else {
+            // pass 1: maximum (a NaN in column 0 makes the reference's running maximum NaN -> "not finite" -> 0)
+            float mx = -3.402823466e38f;
+            bool seen = false;
+            for (int q = 0; q < V; ++q) {
+                int j = q + lr;
+                if (j >= V) j -= V;
+                const float x = row[j];
+                sx += x;
+                sa += fabsf(x);
+                if (x == x) { mx = seen ? fmaxf(mx, x) : x; seen = true; }
+            }
+            const float x0 = row[0];
+            m = (x0 == x0 && seen) ? mx : x0;                   // NaN first element: NaN (falls to 0 below)
+            if (!(m - m == 0.0f)) m = 0.0f;                     // inf / NaN
+            // pass 2: softmax denominator, integer sum (order free)
+            u64 qs = 0;
+            bool nn = false, ni = false;
+            for (int q = 0; q < V; ++q) {
+                int j = q + lr;
+                if (j >= V) j -= V;
+                qs += b2c_sm_quantum(b2c_sm_expf(row[j] - m), nn, ni);
+            }
+            lsf = b2c_sm_finish(qs, nn, ni);
+            // pass 3: log-probabilities, selection mask, arg-max (largest value, lowest index; NaN never wins, a NaN
+            // in column 0 keeps index 0 like the reference's sequential scan)
+            double best = 0.0;
+            int bi = -1;
+            bool nan0 = false;
+            for (int q = 0; q < V; ++q) {
+                int j = q + lr;
+                if (j >= V) j -= V;
+                double lp = static_cast<double>(B2C_SM_ADD(row[j] - m, -lsf));
+                if (lp < B2C_LOG_MIN_CLIP) lp = B2C_LOG_MIN_CLIP;
+                if (lp > 0.0) lp = 0.0;
+                if (lp >= thr) mask |= 1u << j;
+                if (j == 0 && !(lp == lp)) nan0 = true;
+                if (lp == lp && (bi < 0 || lp > best || (lp == best && j < bi))) { best = lp; bi = j; }
+            }
+            amax = (nan0 || bi < 0) ? 0u : static_cast<u32>(bi);
+            }
+        }
+        // ---- approximate row sums of the tile (decide kernel) -------------------------------------------------------
+        {
+            double dx = static_cast<double>(sx), da = static_cast<double>(sa);
+            for (int off = 16; off >= 1; off >>= 1) {
+                dx += __shfl_xor_sync(full, dx, off);
+                da += __shfl_xor_sync(full, da, off);
+            }
+            if (lane == 0) { atomicAdd(A.approx + 2 * cur.u, dx); atomicAdd(A.approx + 2 * cur.u + 1, da); }
+        }
+        // ---- offsets inside each run of 8 frames, records, small token lists ---------------------------------------
+        // a row with special values: its statistics come from the warp-cooperative general routine (same definition)
+        {
+            u32 odd = __ballot_sync(full, mine && odd_row);
+            while (odd) {
+                const int f = __ffs(static_cast<int>(odd)) - 1;
+                odd &= odd - 1;
+                B2cPySet tmp;
+                tmp.buf[0] = sh->sets[w][0];
+                tmp.buf[1] = sh->sets[w][1];
+                float gm;
+                double gls;
+                int gamax;
+                u32 gmask;
+                b2c_prep_row<float, true>(cur.src + static_cast<u64>(f) * V, V, false, thr, lane, tmp, gm, gls, gamax, gmask);
+                gamax = __shfl_sync(full, gamax, 0);
+                if (lane == f) { mask = gmask; amax = static_cast<u32>(gamax); m = gm; lsf = static_cast<float>(gls); }
+            }
+        }
+        const u32 nsel = __popc(mask);
+        const bool small = nsel == 0 || (nsel <= 3 && ((mask >> amax) & 1u));
+        const u32 cnt = mine ? static_cast<u32>(__popc(mask | (1u << amax))) : 0u;
+        u32 incl = cnt;
+        for (int off = 1; off < B2C_RUN; off <<= 1) {
+            const u32 o = __shfl_up_sync(full, incl, off, B2C_RUN);
+            if ((lane & (B2C_RUN - 1)) >= off) incl += o;
+        }
+        const u32 my_off = incl - cnt;
+        const u64 f0 = A.frame_off[cur.u];
+        const u64 run_base = (f0 + static_cast<u64>(cur.t0 + (lane & ~(B2C_RUN - 1)))) * static_cast<u64>(V);
+        if (mine) {
+            B2cFrameRec rec;
+            rec.off = my_off;
+            rec.cnt = static_cast<u16>(cnt);
+            rec.id0 = 0;
+            rec.lp0 = 0.0;
+            if (small) {
+                u32 toks[3];
+                const u32 n = b2c_pyset_small_order(mask, amax, toks);
+                for (u32 q = 0; q < n; ++q) {
+                    const double lp = b2c_lp_logit<float>(row[toks[q]], m, static_cast<double>(lsf));
+                    A.tok_ids[run_base + my_off + q] = toks[q];
+                    A.tok_lp[run_base + my_off + q] = lp;
+                    if (q == 0) { rec.id0 = static_cast<u16>(toks[0]); rec.lp0 = lp; }
+                }
+            }
+            A.tok_rec[f0 + static_cast<u64>(cur.t0 + lane)] = rec;       // big frames: first token patched below
+        }
+        // ---- frames with more than three selected tokens: the general set emulation ---------------------------------
+        u32 big = __ballot_sync(full, mine && !small);
+        while (big) {
+            const int f = __ffs(static_cast<int>(big)) - 1;
+            big &= big - 1;
+            const float* grow = cur.src + static_cast<u64>(f) * V;
+            B2cPySet set;
+            set.buf[0] = sh->sets[w][0];
+            set.buf[1] = sh->sets[w][1];
+            float gm;
+            double gls;
+            int gamax;
+            u32 ns;
+            b2c_prep_row<float, false>(grow, V, false, thr, lane, set, gm, gls, gamax, ns);
+            u32 off = __shfl_sync(full, my_off, f);
+            const u64 rb = (f0 + static_cast<u64>(cur.t0 + (f & ~(B2C_RUN - 1)))) * static_cast<u64>(V);
+            if (lane == 0) {
+                b2c_pyset_copy_or(set, static_cast<u32>(gamax));
+                const u16* tab = set.buf[set.cur];
+                bool first = true;
+                for (u32 s = 0; s <= set.mask; ++s) {
+                    const u16 tok = tab[s];
+                    if (tok == 0xFFFFu) continue;
+                    const double lp = b2c_lp_logit<float>(grow[tok], gm, gls);
+                    A.tok_ids[rb + off] = tok;
+                    A.tok_lp[rb + off] = lp;
+                    if (first) {
+                        B2cFrameRec* r = A.tok_rec + f0 + static_cast<u64>(cur.t0 + f);
+                        r->id0 = tok;
+                        r->lp0 = lp;
+                        first = false;
+                    }
+                    ++off;
+                }
+            }
+            __syncwarp();
+        }
+        // ---- token statistics of the utterance (launch planning) -----------------------------------------------------
+        {
+            u32 mx = cnt, tot = cnt;
+            for (int off = 16; off >= 1; off >>= 1) {
+                const u32 o = __shfl_xor_sync(full, mx, off);
+                mx = o > mx ? o : mx;
+                tot += __shfl_xor_sync(full, tot, off);
+            }
+            if (lane == 0 && mx > 0) {
+                atomicMax(&A.max_k[cur.u], mx);
+                atomicAdd(&A.sum_k[cur.u], tot);
+            }
+        }
+        __syncwarp();          // every lane is done with this buffer before the copy after next overwrites it
+        cur = nxt;
+        buf ^= 1;
+    }
+}
+#endif
