@@ -156,6 +156,11 @@ struct B2cBeamArgs {
     u32* out_toks;
     int* out_frames;
     B2cLmState* out_states;
+    // chunked launches of the latency-first kernel (chunk_t1 > 0): frames [chunk_t0, chunk_t1) of every utterance, CTA i
+    // bound to utterance order[i], state parked in `state` between launches
+    int chunk_t0, chunk_t1, chunk_last, pad_chunk;
+    u8* state;
+    u64 state_stride;
     u64* phase_clk;            // [16] profiling builds only (-DB2C_PHASE_CLOCKS)
     u32* m_stats;              // [8] frames over 128..4096 candidates, total frames (adaptive sizing), in-place frames, sorted (no-merge) frames
 };
@@ -285,6 +290,15 @@ static const int kV5Occ[3] = {2, 3, 4};
 static const size_t kV5Smem[3][2] = {{sizeof(B2cFastSmem<128, 1024, 0>), sizeof(B2cFastSmemA)},
                                      {sizeof(B2cFastSmem<128, 512, 0>), sizeof(B2cFastSmemB)},
                                      {sizeof(B2cFastSmem<128, 256, 0>), sizeof(B2cFastSmemC)}};
+// bytes a CTA parks between two chunked launches: everything in front of the per-frame candidate scratch
+typedef B2cFastSmem<128, 1024, 0> B2cFastSmemA0;
+typedef B2cFastSmem<128, 512, 0> B2cFastSmemB0;
+typedef B2cFastSmem<128, 256, 0> B2cFastSmemC0;
+static const size_t kV5Save[3][2] = {{offsetof(B2cFastSmemA0, ckey), offsetof(B2cFastSmemA, ckey)},
+                                     {offsetof(B2cFastSmemB0, ckey), offsetof(B2cFastSmemB, ckey)},
+                                     {offsetof(B2cFastSmemC0, ckey), offsetof(B2cFastSmemC, ckey)}};
+#define B2C_PIPE_CHUNKS 4
+#define B2C_E_RETRY_PLAIN (-1000)     // internal: the pipelined attempt must be redone as a plain call
 static_assert(2 * (sizeof(B2cFastSmemA) + 1024) <= 228 * 1024, "variant A: 2 CTAs per SM");
 static_assert(3 * (sizeof(B2cFastSmemB) + 1024) <= 228 * 1024, "variant B: 3 CTAs per SM");
 static_assert(4 * (sizeof(B2cFastSmemC) + 1024) <= 228 * 1024, "variant C: 4 CTAs per SM");
@@ -509,6 +523,12 @@ struct b2c_decoder {
     cudaEvent_t cls_done[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t fork_ev = nullptr;
     cudaEvent_t caller_ev = nullptr;      // b2c_decoder_wait_stream: the caller's stream at the time of the call
+    // pipelined calls (host input): chunks along T are copied on copy_stream while earlier chunks are decoded
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t copied[B2C_PIPE_CHUNKS] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t chunk_ev[3 * B2C_PIPE_CHUNKS] = {};
+    DevBuf d_state;
+    bool pipe_refused = false;            // the last pipelined attempt of this configuration could not be planned
     std::mutex call_mu;                   // b2c_decode_batch is serialised per handle (scratch buffers are per handle)
     b2c_timings_t tm;
     // adaptive sizing: candidate-count histogram of the previous call with the same configuration
@@ -931,6 +951,9 @@ int b2c_decoder_create(const char* const* labels, int n_labels, int is_bpe, b2c_
     }
     CUDA_OK(cudaEventCreate(&d->fork_ev));
     CUDA_OK(cudaEventCreateWithFlags(&d->caller_ev, cudaEventDisableTiming));
+    CUDA_OK(cudaStreamCreate(&d->copy_stream));
+    for (int i = 0; i < B2C_PIPE_CHUNKS; ++i) CUDA_OK(cudaEventCreateWithFlags(&d->copied[i], cudaEventDisableTiming));
+    for (int i = 0; i < 3 * B2C_PIPE_CHUNKS; ++i) CUDA_OK(cudaEventCreate(&d->chunk_ev[i]));
     int v = 0;
     CUDA_OK(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device));
     d->n_sm = v;
@@ -984,6 +1007,10 @@ void b2c_decoder_destroy(b2c_decoder_t* d) {
     }
     if (d->fork_ev) cudaEventDestroy(d->fork_ev);
     if (d->caller_ev) cudaEventDestroy(d->caller_ev);
+    if (d->copy_stream) cudaStreamDestroy(d->copy_stream);
+    for (int i = 0; i < B2C_PIPE_CHUNKS; ++i) if (d->copied[i]) cudaEventDestroy(d->copied[i]);
+    for (int i = 0; i < 3 * B2C_PIPE_CHUNKS; ++i) if (d->chunk_ev[i]) cudaEventDestroy(d->chunk_ev[i]);
+    d->d_state.release();
     if (d->stream) cudaStreamDestroy(d->stream);
     delete d;
 }
@@ -1020,9 +1047,21 @@ void b2c_decode_opts_default(b2c_decode_opts_t* o) {
     o->max_out_beams = 1;
 }
 
+static int decode_batch_locked(b2c_decoder_t* d, const void* const* logits, const int32_t* T, int n_utts, int dtype, int is_device,
+                               const b2c_decode_opts_t* opts, b2c_result_t** out, bool allow_pipe);
+
 int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t* T, int n_utts, int dtype, int is_device,
                      const b2c_decode_opts_t* opts, b2c_result_t** out) {
     if (!d || !opts || !out || n_utts < 0 || (n_utts > 0 && (!logits || !T))) return fail(B2C_E_ARG, "null argument");
+    std::lock_guard<std::mutex> call_lock(d->call_mu);      // one call at a time per handle (any number of threads may call)
+    int rc = decode_batch_locked(d, logits, T, n_utts, dtype, is_device, opts, out, true);
+    // a pipelined attempt that could not be planned, or that met probability input (decided after the fact): plain call
+    if (rc == B2C_E_RETRY_PLAIN) rc = decode_batch_locked(d, logits, T, n_utts, dtype, is_device, opts, out, false);
+    return rc;
+}
+
+static int decode_batch_locked(b2c_decoder_t* d, const void* const* logits, const int32_t* T, int n_utts, int dtype, int is_device,
+                               const b2c_decode_opts_t* opts, b2c_result_t** out, bool allow_pipe) {
     if (dtype < B2C_DTYPE_F32 || dtype > B2C_DTYPE_BF16) return fail(B2C_E_ARG, "dtype must be one of B2C_DTYPE_F32 / F64 / F16 / BF16");
     // half-precision input: copied as 2-byte elements, widened on the device, then the float32 path
     const int dtype_in = dtype;
@@ -1030,7 +1069,6 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     if (half_in) dtype = B2C_DTYPE_F32;
     if (opts->beam_width < 1) return fail(B2C_E_ARG, "beam_width must be >= 1");
     if (opts->beam_width > 65535) return fail(B2C_E_ARG, "beam_width above 65535 is not supported");
-    std::lock_guard<std::mutex> call_lock(d->call_mu);      // one call at a time per handle (any number of threads may call)
     std::unique_ptr<b2c_result> res(new b2c_result());
     res->utts.resize(n_utts);
     res->has_lm = d->lm != nullptr;
@@ -1177,7 +1215,7 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     }();
     if ((half_in || !contiguous_dev) && d->d_logits.ensure(std::max<u64>(total_frames * V * esz, 16))) return B2C_E_NOMEM;
     if (half_in && !contiguous_dev && d->d_raw.ensure(std::max<u64>(total_frames * V * esz_in, 16))) return B2C_E_NOMEM;
-    const size_t meta_bytes = al16(8ull * n_utts) + 3 * al16(4ull * n_utts) + 64 + 2 * al16(8ull * (n_utts + 1)) + al16(8ull * n_utts);
+    const size_t meta_bytes = al16(8ull * n_utts) + 3 * al16(4ull * n_utts) + 64 + al16(8ull * (n_utts + 1)) + al16(8ull * n_utts);
     if (d->d_meta.ensure(meta_bytes) || d->h_meta.ensure(meta_bytes)) return B2C_E_NOMEM;
     if (d->d_tok_start.ensure(sizeof(B2cFrameRec) * (total_frames + 1)) || d->d_tok_ids.ensure(4 * n_entries) ||
         d->d_tok_lp.ensure(8 * n_entries) || d->d_rowsum.ensure(std::max<u64>(8 * total_frames, 16)) ||
@@ -1188,9 +1226,8 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     std::vector<u64> run_off(n_utts + 1, 0);
     for (int i = 0; i < n_utts; ++i) run_off[i + 1] = run_off[i] + (static_cast<u64>(T[i]) + B2C_RUN - 1) / B2C_RUN;
     const u64 total_runs = run_off[n_utts];
-    std::vector<u64> tile_off(n_utts + 1, 0);
-    for (int i = 0; i < n_utts; ++i) tile_off[i + 1] = tile_off[i] + (static_cast<u64>(T[i]) + B2C_TILE_ROWS - 1) / B2C_TILE_ROWS;
-    const int grid_tile = static_cast<int>(std::max<u64>(1, std::min<u64>((tile_off[n_utts] + B2C_TILE_WARPS - 1) / B2C_TILE_WARPS, static_cast<u64>(d->n_sm) * 8)));
+    const int tiles_per_utt = std::max(1, (T_max + B2C_TILE_ROWS - 1) / B2C_TILE_ROWS);
+    const int grid_tile = static_cast<int>(std::max<u64>(1, std::min<u64>((static_cast<u64>(n_utts) * tiles_per_utt + B2C_TILE_WARPS - 1) / B2C_TILE_WARPS, static_cast<u64>(d->n_sm) * 8)));
     const int grid_tok = static_cast<int>(std::max<u64>(1, std::min<u64>((total_runs + B2C_PREP_WARPS - 1) / B2C_PREP_WARPS, static_cast<u64>(d->n_sm) * 8)));
     if (V > 32) {
         if (d->d_set.ensure(2ull * set_cap * 2 * B2C_PREP_WARPS * grid_tok)) return B2C_E_NOMEM;
@@ -1213,6 +1250,24 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
         if (d->d_states.ensure(sizeof(B2cLmState) * static_cast<u64>(n_utts) * n_lm)) return B2C_E_NOMEM;
     }
 
+    // ---- pipelined call? ---------------------------------------------------------------------
+    // Host input in one [B, T, V] float32 block, alphabet of the lane-per-row streaming kernel, every utterance
+    // resident in the latency-first beam kernel (known from the previous call of the same configuration): the batch
+    // is cut into chunks along T; chunk c+1 crosses PCIe while chunk c goes through the streaming stage and the beam
+    // kernel (chunked launches, state parked in HBM in between).  The launch plan cannot wait for this call's token
+    // statistics then: it is made from the hint alone.  Probabilities-vs-logits is decided after the last chunk; a
+    // call that turns out to hold probabilities is redone as a plain call (B2C_E_RETRY_PLAIN).
+    const bool hint_ok = d->hint_valid && d->hint_beam == opts->beam_width && d->hint_lm == (P.lm.order > 0 ? 1 : 0) &&
+                         d->hint_hot == (P.n_hot > 0 ? 1 : 0) && d->hint_prune == P.prune_history && d->hint_frames > 0;
+    static const bool no_pipe = std::getenv("B200CTC_NO_PIPELINE") != nullptr;
+    bool pipe_candidate = allow_pipe && !no_pipe && !is_device && !half_in && dtype == B2C_DTYPE_F32 && V <= 32 && T_max >= 8 * B2C_TILE_ROWS &&
+                          !streaming && n_lm == 1 && opts->beam_width <= 128 && hint_ok && !d->pipe_refused;
+    for (int i = 0; i < n_utts && pipe_candidate; ++i)
+        pipe_candidate = T[i] == T_max && static_cast<const char*>(logits[i]) == static_cast<const char*>(logits[0]) + static_cast<u64>(i) * T_max * V * esz_in;
+    if (!hint_ok) d->pipe_refused = false;                       // another configuration: a new attempt may be planned
+    if (pipe_candidate && d->d_logits.ensure(std::max<u64>(total_frames * V * esz, 16))) return B2C_E_NOMEM;
+    const int chunk_len = ((T_max + B2C_PIPE_CHUNKS * B2C_TILE_ROWS - 1) / (B2C_PIPE_CHUNKS * B2C_TILE_ROWS)) * B2C_TILE_ROWS;
+
     // ---- host -> device -------------------------------------------------------------------
     cudaStream_t st = d->stream;
     CUDA_OK(cudaEventRecord(d->ev[0], st));
@@ -1220,14 +1275,11 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     u64* h_fo = reinterpret_cast<u64*>(hm);
     int* h_T = reinterpret_cast<int*>(hm + al16(8ull * n_utts));
     const size_t off_run = al16(8ull * n_utts) + al16(4ull * n_utts);
-    const size_t off_tile = off_run + al16(8ull * (n_utts + 1));
-    const size_t off_ord = off_tile + al16(8ull * (n_utts + 1));
+    const size_t off_ord = off_run + al16(8ull * (n_utts + 1));
     const size_t off_next = off_ord + 2 * al16(4ull * n_utts);
     const size_t off_ptr = off_next + 64;                        // [n_utts] source pointers (gather launch only)
     u64* h_run = reinterpret_cast<u64*>(hm + off_run);
     for (int i = 0; i <= n_utts; ++i) h_run[i] = run_off[i];
-    u64* h_tile = reinterpret_cast<u64*>(hm + off_tile);
-    for (int i = 0; i <= n_utts; ++i) h_tile[i] = tile_off[i];
     int* h_ord = reinterpret_cast<int*>(hm + off_ord);           // [2 * n_utts]: class lists, then retry list
     u32* h_next = reinterpret_cast<u32*>(hm + off_next);         // [16] one queue head per launch
     for (int i = 0; i < n_utts; ++i) { h_fo[i] = frame_off[i]; h_T[i] = T[i]; }
@@ -1239,7 +1291,9 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     u32* d_next = reinterpret_cast<u32*>(dm + off_next);
     d->tm.h2d_bytes += static_cast<long long>(meta_bytes);
     const void* d_logits = nullptr;
-    if (contiguous_dev && !half_in) {
+    if (pipe_candidate) {
+        d_logits = d->d_logits.p;                    // copied chunk by chunk further down
+    } else if (contiguous_dev && !half_in) {
         d_logits = logits[0];
 #ifndef B2C_HOSTSIM
     } else if (is_device && n_utts > 4 && !half_in) {
@@ -1337,26 +1391,36 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     PA.set_scratch = d->d_set.as<u16>();
     PA.set_cap = set_cap;
     PA.is_prob = d->d_isprob.as<int>();
-    PA.tile_off = reinterpret_cast<const u64*>(dm + off_tile);
+    PA.tile_lo = 0;
+    PA.tile_hi = tiles_per_utt;
     PA.approx = d->d_approx.as<double>();
     CUDA_OK(cudaMemsetAsync(d->d_approx.p, 0, 16ull * n_utts + 16, st));
     PA.max_k = d->d_maxk.as<u32>();
     PA.sum_k = d->d_sumk.as<u32>();
     CUDA_OK(cudaMemsetAsync(d->d_maxk.p, 0, 4ull * n_utts, st));
     CUDA_OK(cudaMemsetAsync(d->d_sumk.p, 0, 4ull * n_utts, st));
-    CUDA_OK(cudaEventRecord(d->ev[1], st));
-    int rc = dtype == B2C_DTYPE_F32 ? launch_prepare<float>(d, PA, n_utts, grid_tile, grid_tok)
+    int rc = 0;
+    if (!pipe_candidate) {
+        CUDA_OK(cudaEventRecord(d->ev[1], st));
+        rc = dtype == B2C_DTYPE_F32 ? launch_prepare<float>(d, PA, n_utts, grid_tile, grid_tok)
                                     : launch_prepare<double>(d, PA, n_utts, grid_tile, grid_tok);
-    if (rc) return rc;
-    CUDA_OK(cudaEventRecord(d->ev[2], st));
-    d->tm.launches += 3;
+        if (rc) return rc;
+        CUDA_OK(cudaEventRecord(d->ev[2], st));
+        d->tm.launches += 3;
 
-    // ---- size the beam kernel from the token statistics of this batch ---------------------------
-    CUDA_OK(cudaMemcpyAsync(d->h_maxk.p, d->d_maxk.p, 4ull * n_utts, cudaMemcpyDeviceToHost, st));
-    CUDA_OK(cudaMemcpyAsync(d->h_sumk.p, d->d_sumk.p, 4ull * n_utts, cudaMemcpyDeviceToHost, st));
-    hp_mark(0);                                   // argument checks, buffers, enqueue of H2D + prepare kernels
-    CUDA_OK(cudaStreamSynchronize(st));
-    hp_mark(1);                                   // wait: H2D + prepare kernels
+        // ---- size the beam kernel from the token statistics of this batch ---------------------------
+        CUDA_OK(cudaMemcpyAsync(d->h_maxk.p, d->d_maxk.p, 4ull * n_utts, cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaMemcpyAsync(d->h_sumk.p, d->d_sumk.p, 4ull * n_utts, cudaMemcpyDeviceToHost, st));
+        hp_mark(0);                                   // argument checks, buffers, enqueue of H2D + prepare kernels
+        CUDA_OK(cudaStreamSynchronize(st));
+        hp_mark(1);                                   // wait: H2D + prepare kernels
+    } else {
+        // no statistics yet: the worst case for the workspace, the hint for the kernel variant
+        for (int i = 0; i < n_utts; ++i) {
+            d->h_maxk.as<u32>()[i] = static_cast<u32>(V);
+            d->h_sumk.as<u32>()[i] = static_cast<u32>(std::min<u64>(static_cast<u64>(T[i]) * V, 0xFFFFFFFFull));
+        }
+    }
     const u32* h_maxk = d->h_maxk.as<u32>();
     const u32* h_sumk = d->h_sumk.as<u32>();
     // ---- capacity class of the shared-memory candidate tier (ONE fast class per call) -------------
@@ -1382,8 +1446,6 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     std::vector<std::vector<int>> classes(kNumCaps + 1);   // fast classes (one used per call), last = general
     bool use_v5 = false;
     int v5_top = -1, v5_variant = 0;
-    const bool hint_ok = d->hint_valid && d->hint_beam == opts->beam_width && d->hint_lm == (P.lm.order > 0 ? 1 : 0) &&
-                         d->hint_hot == (P.n_hot > 0 ? 1 : 0) && d->hint_prune == P.prune_history && d->hint_frames > 0;
     {
         std::vector<int> cls_of(n_utts, kNumCaps);
         int top = -1, n_fast = 0;
@@ -1519,10 +1581,104 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
         ws_need += static_cast<u64>(ln.slots) * ln.L.gws_bytes;
     }
     if (d->d_ws.ensure(ws_need)) return B2C_E_NOMEM;
-    CUDA_OK(cudaEventRecord(d->ev[5], st));
+    // chunked launches need ONE launch of the latency-first kernel with every utterance resident
+    const bool can_chunk = launches.size() == 1 && launches[0].v5 >= 0 && launches[0].count <= launches[0].slots && !streaming;
+    if (pipe_candidate && !can_chunk) {
+        d->pipe_refused = true;                       // until the configuration (hint) changes
+        return B2C_E_RETRY_PLAIN;
+    }
+    static const int force_chunks = std::getenv("B200CTC_FORCE_CHUNKS") ? std::atoi(std::getenv("B200CTC_FORCE_CHUNKS")) : 0;   // tests
+    int n_chunks = 1, clen = T_max > 0 ? T_max : 1;
+    if (pipe_candidate) { n_chunks = (T_max + chunk_len - 1) / chunk_len; clen = chunk_len; }
+    else if (can_chunk && force_chunks > 1 && T_max >= 2) { n_chunks = std::min(force_chunks, T_max); clen = (T_max + n_chunks - 1) / n_chunks; n_chunks = (T_max + clen - 1) / clen; }
+    bool chunk_timing = false;
+    if (n_chunks > 1) {
+        const Launch& ln = launches[0];
+        const u64 stride = (kV5Save[ln.v5][V <= B2C_FAST_LT ? 1 : 0] + 16 + 255) & ~255ull;
+        if (d->d_state.ensure(stride * static_cast<u64>(ln.slots))) return B2C_E_NOMEM;
+        BA.L = ln.L;
+        BA.n_utts = ln.count;
+        BA.order = d_ord + ln.ord_off;
+        BA.next = d_next;
+        BA.gws = d->d_ws.as<u8>();
+        BA.state = d->d_state.as<u8>();
+        BA.state_stride = stride;
+        chunk_timing = pipe_candidate && n_chunks <= B2C_PIPE_CHUNKS;
+        if (pipe_candidate) {
+            // every chunk's copy is queued at once on the copy stream; the compute stream waits chunk by chunk
+            const size_t pitch = static_cast<size_t>(T_max) * V * esz;
+            for (int c = 0; c < n_chunks; ++c) {
+                const int t0 = c * clen, t1 = std::min(T_max, (c + 1) * clen);
+                CUDA_OK(cudaMemcpy2DAsync(d->d_logits.as<char>() + static_cast<size_t>(t0) * V * esz, pitch,
+                                          static_cast<const char*>(logits[0]) + static_cast<size_t>(t0) * V * esz, pitch,
+                                          static_cast<size_t>(t1 - t0) * V * esz, static_cast<size_t>(n_utts), cudaMemcpyHostToDevice, d->copy_stream));
+                CUDA_OK(cudaEventRecord(d->copied[c % B2C_PIPE_CHUNKS], d->copy_stream));
+                if (n_chunks > B2C_PIPE_CHUNKS) CUDA_OK(cudaStreamSynchronize(d->copy_stream));   // never: n_chunks <= B2C_PIPE_CHUNKS by construction
+                d->tm.h2d_bytes += static_cast<long long>(t1 - t0) * V * static_cast<long long>(esz) * n_utts;
+            }
+        }
+        CUDA_OK(cudaEventRecord(d->ev[5], st));
+        for (int c = 0; c < n_chunks; ++c) {
+            const int t0 = c * clen, t1 = std::min(T_max, (c + 1) * clen);
+            if (pipe_candidate) {
+                CUDA_OK(cudaStreamWaitEvent(st, d->copied[c % B2C_PIPE_CHUNKS], 0));
+                if (chunk_timing) CUDA_OK(cudaEventRecord(d->chunk_ev[3 * c], st));
+                B2cPrepArgs PC = PA;
+                PC.mode = 0;
+                PC.tile_lo = t0 / B2C_TILE_ROWS;
+                PC.tile_hi = (t1 + B2C_TILE_ROWS - 1) / B2C_TILE_ROWS;
+#ifdef B2C_HOSTSIM
+                {
+                    // hostsim has no lane-per-row kernel: the run-based routine over the runs of this chunk
+                    std::unique_ptr<B2cPrepShared> sh(new B2cPrepShared());
+                    for (int u = 0; u < n_utts; ++u)
+                        for (u64 r = run_off[u] + static_cast<u64>(t0 / B2C_RUN); r < run_off[u] + static_cast<u64>((t1 + B2C_RUN - 1) / B2C_RUN); ++r)
+                            b2c_tokens_run_v32<float>(PC, r, 0, sh->sets[0][0], sh->sets[0][1]);
+                }
+#else
+                {
+                    const u64 items = static_cast<u64>(n_utts) * static_cast<u64>(PC.tile_hi - PC.tile_lo);
+                    const int grid = static_cast<int>(std::max<u64>(1, std::min<u64>((items + B2C_TILE_WARPS - 1) / B2C_TILE_WARPS, static_cast<u64>(d->n_sm) * 8)));
+                    b2c_tokens_tile_kernel<<<grid, B2C_TILE_WARPS * 32, 0, st>>>(PC);
+                    CUDA_OK(cudaGetLastError());
+                }
+#endif
+                d->tm.launches += 1;
+                if (chunk_timing) CUDA_OK(cudaEventRecord(d->chunk_ev[3 * c + 1], st));
+            }
+            BA.chunk_t0 = t0;
+            BA.chunk_t1 = t1;
+            BA.chunk_last = c == n_chunks - 1 ? 1 : 0;
+            rc = launch_beam(d, BA, ln.slots, true, ln.per_sm, ln.threads, st, ln.v5);
+            if (rc) return rc;
+            d->tm.launches += 1;
+            if (chunk_timing) CUDA_OK(cudaEventRecord(d->chunk_ev[3 * c + 2], st));
+        }
+        BA.chunk_t1 = 0;
+        if (pipe_candidate) {
+            // probabilities or logits: decided now that every row has been seen; a probability utterance voids the call
+#ifdef B2C_HOSTSIM
+            {
+                std::unique_ptr<B2cDecideShared> dsh(new B2cDecideShared());
+                for (int u = 0; u < n_utts; ++u) b2c_decide_block<float>(PA, u, dsh.get());
+            }
+#else
+            b2c_decide_kernel<float><<<n_utts, 128, 0, st>>>(PA);
+            CUDA_OK(cudaGetLastError());
+#endif
+            d->tm.launches += 1;
+            CUDA_OK(cudaMemcpyAsync(d->h_maxk.p, d->d_approx.as<double>() + 2 * n_utts, 4, cudaMemcpyDeviceToHost, st));
+        }
+        d->tm.cap_candidates = static_cast<int>(ln.L.cap_s);
+        d->tm.cta_threads = ln.threads;
+        d->tm.cta_slots = ln.slots;
+        d->tm.kernel_variant = 2;
+    }
+    if (n_chunks == 1) CUDA_OK(cudaEventRecord(d->ev[5], st));
     CUDA_OK(cudaEventRecord(d->fork_ev, st));
     int qi = 0;
     for (const Launch& ln : launches) {
+        if (n_chunks > 1) break;
         cudaStream_t cs = launches.size() > 1 ? d->cls_stream[ln.cls < kNumCaps ? 0 : 1] : st;
         if (cs != st) CUDA_OK(cudaStreamWaitEvent(cs, d->fork_ev, 0));
         BA.L = ln.L;
@@ -1556,6 +1712,7 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     hp_mark(2);                                   // launch planning + enqueue of the beam kernel and D2H
     CUDA_OK(cudaStreamSynchronize(st));
     hp_mark(3);                                   // wait: beam kernel + D2H
+    if (pipe_candidate && d->h_maxk.as<u32>()[0] != 0) return B2C_E_RETRY_PLAIN;   // some utterance holds probabilities
     d->tm.d2h_bytes += static_cast<long long>(small_bytes + tok_bytes + (text_only ? 0 : frm_bytes) + 8ull * n_utts + 32);
     {
         u32 ms[16];
@@ -1611,8 +1768,18 @@ int b2c_decode_batch(b2c_decoder_t* d, const void* const* logits, const int32_t*
     }
 #endif
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, d->ev[1], d->ev[2]) == cudaSuccess) d->tm.ms_prepare = ms;
-    if (cudaEventElapsedTime(&ms, d->ev[5], d->ev[3]) == cudaSuccess) d->tm.ms_beam = ms;
+    if (chunk_timing) {        // pipelined: kernels of the chunks interleave with waits for the copies -- sum them up
+        float mp = 0.f, mb = 0.f;
+        for (int c = 0; c < n_chunks; ++c) {
+            if (cudaEventElapsedTime(&ms, d->chunk_ev[3 * c], d->chunk_ev[3 * c + 1]) == cudaSuccess) mp += ms;
+            if (cudaEventElapsedTime(&ms, d->chunk_ev[3 * c + 1], d->chunk_ev[3 * c + 2]) == cudaSuccess) mb += ms;
+        }
+        d->tm.ms_prepare = mp;
+        d->tm.ms_beam = mb;
+    } else {
+        if (!pipe_candidate && cudaEventElapsedTime(&ms, d->ev[1], d->ev[2]) == cudaSuccess) d->tm.ms_prepare = ms;
+        if (cudaEventElapsedTime(&ms, d->ev[5], d->ev[3]) == cudaSuccess) d->tm.ms_beam = ms;
+    }
     if (cudaEventElapsedTime(&ms, d->ev[0], d->ev[4]) == cudaSuccess) d->tm.ms_total = ms;
     d->tm.frames = static_cast<long long>(total_frames);
     // total selected tokens = last tok_start of the last utterance ... summed per utterance is not

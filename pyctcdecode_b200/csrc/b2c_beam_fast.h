@@ -40,6 +40,7 @@
 // Reference lines restated: decoder.py:443-554 (frame loop), :211-224 (merge), :346-424 (LM
 // fusion), :545-554 (threshold, top-N, history prune).  Order-dependence notes: b2c_beam.h.
 #pragma once
+#include <cstddef>
 #include "b2c_beam.h"
 
 #define B2C_FAST_KS 32          // most tokens of a frame any variant stages (larger frames: out-of-line step)
@@ -1104,20 +1105,50 @@ B2C_HD void b2c_beam_block_fast(const B2cBeamArgs& A, int slot_cta, u8* smem) {
     }
 #endif
 
+    // Chunked launches (A.chunk_t1 > 0; the host pipelines copy / streaming stage / beam search along T): CTA i keeps
+    // utterance order[i] over all launches of a call, processes frames [chunk_t0, chunk_t1) and parks its state --
+    // everything in front of the per-frame candidate scratch -- in HBM between two launches.
+    const bool chunked = A.chunk_t1 > 0;
+    constexpr u32 SAVE_WORDS = static_cast<u32>(offsetof(SM, ckey) / 4);
+    u32* const parked = chunked ? reinterpret_cast<u32*>(A.state + static_cast<u64>(slot_cta) * A.state_stride) : nullptr;
+    bool chunk_done = false;
     while (true) {
-        B2C_LEADER { S.ticket = b2c_atomic_add_u32(A.next, 1u); }
-        B2C_SYNC();
-        const u32 q = S.ticket;
-        if (q >= static_cast<u32>(A.n_utts)) break;
+        u32 q;
+        if (chunked) {
+            if (chunk_done || slot_cta >= A.n_utts) break;
+            chunk_done = true;
+            q = static_cast<u32>(slot_cta);
+        } else {
+            B2C_LEADER { S.ticket = b2c_atomic_add_u32(A.next, 1u); }
+            B2C_SYNC();
+            q = S.ticket;
+            if (q >= static_cast<u32>(A.n_utts)) break;
+        }
         const int u = A.order[q];
         const int Tn = A.T[u];
         const u64 f0 = A.frame_off[u];
         const B2cFrameRec* recs = A.tok_rec + f0;
+        const int ts = chunked ? A.chunk_t0 : 0;                                     // first frame of this launch
+        const int te = (chunked && !A.chunk_last && A.chunk_t1 < Tn) ? A.chunk_t1 : Tn;   // one past its last frame
+        const bool resume = chunked && ts > 0;
+        if (resume && Tn <= ts) continue;                        // finished (and finalised) in an earlier launch
         // ---- fill the rings: records of the first frames, then the token lists of the first frames ----------------
-        int hv = Tn < B2C_FAST_HR ? Tn : B2C_FAST_HR;            // records of frames < hv are (being) fetched
-        B2C_FOR(c, hv) { b2c_cp_async16(&S.rh[c], recs + c); }
+        int hv = te - ts < B2C_FAST_HR ? te : ts + B2C_FAST_HR;  // records of frames < hv are (being) fetched
+        B2C_FOR(c, hv - ts) { b2c_cp_async16(&S.rh[(ts + c) & HM], recs + ts + c); }
         b2c_cp_async_wait_all();
-        {
+        int par = 0, sb = 0;
+        u32 prev_single = B2C_NONE_U32;   // canonical token of the previous frame if it selected exactly one
+        if (resume) {
+            u32* const sw = reinterpret_cast<u32*>(smem);
+            // the frame records just fetched live behind the parked region, the label table in front of ckey is
+            // reloaded by every launch: only [0, ckey) is state
+            B2C_FOR(i, SAVE_WORDS) {
+                sw[i] = parked[i];
+            }
+            par = static_cast<int>(parked[SAVE_WORDS]);
+            sb = static_cast<int>(parked[SAVE_WORDS + 1]);
+            prev_single = parked[SAVE_WORDS + 2];
+        } else {
             B2cWork W;
             b2c_fast_work(S, L, g, 0, false, W);
             b2c_utt_begin(A.P, W, A.start_states ? A.start_states + u : nullptr, 1, B2cStreamIn{nullptr, 0u, nullptr, nullptr});
@@ -1128,6 +1159,7 @@ B2C_HD void b2c_beam_block_fast(const B2cBeamArgs& A, int slot_cta, u8* smem) {
             S.ht_max[s] = 0;
             S.ht_cnt[s] = 0;
         }
+        if (!resume) {
         B2C_FOR(s, SM::PT) { S.pt_idx[s] = B2C_NONE_U32; S.pt_min[s] = B2C_NONE_U32; }
         B2C_FOR(s, B2C_NBUCKET) { S.bcnt[s] = 0; S.bhead[s] = B2C_NONE_U32; }
         B2C_LEADER {      // EMPTY_START_BEAM in the form b2c_fast_step expects: one slot, no holes, best score 0
@@ -1141,9 +1173,10 @@ B2C_HD void b2c_beam_block_fast(const B2cBeamArgs& A, int slot_cta, u8* smem) {
             // backtrack nodes of the frame steps have fixed ids below WC * T; the out-of-line step allocates above
             S.sc.chain_used = static_cast<u32>(WC) * static_cast<u32>(Tn);
         }
+        }
         B2C_SYNC();                                             // records visible
-        int tv = Tn < B2C_FAST_TR ? Tn : B2C_FAST_TR;            // token lists of frames < tv are (being) fetched
-        for (int f = 0; f < tv; ++f) {
+        int tv = te - ts < B2C_FAST_TR ? te : ts + B2C_FAST_TR;  // token lists of frames < tv are (being) fetched
+        for (int f = ts; f < tv; ++f) {
             const B2cFrameRec hf = S.rh[f & HM];
             const u64 base = (f0 + static_cast<u64>(f & ~(B2C_RUN - 1))) * static_cast<u64>(V) + hf.off;
             const u32 kf = hf.cnt < static_cast<u32>(KR) ? hf.cnt : static_cast<u32>(KR);
@@ -1154,18 +1187,17 @@ B2C_HD void b2c_beam_block_fast(const B2cBeamArgs& A, int slot_cta, u8* smem) {
         }
         b2c_cp_async_wait_all();
         B2C_SYNC();
-        if (Tn > 0) {       // label records of frame 0 (once per utterance, latency exposed)
-            const u32 k0 = S.rh[0].cnt < static_cast<u32>(KR) ? S.rh[0].cnt : static_cast<u32>(KR);
-            if (LT == 0) { B2C_FOR(c, k0) { S.stok[0][c] = A.P.toks[S.rid[0][c]]; } }
+        if (te > ts) {      // label records of the first frame (once per launch, latency exposed)
+            const u32 c0 = S.rh[ts & HM].cnt;
+            const u32 k0 = c0 < static_cast<u32>(KR) ? c0 : static_cast<u32>(KR);
+            if (LT == 0) { B2C_FOR(c, k0) { S.stok[sb][c] = A.P.toks[S.rid[ts & TM][c]]; } }
         }
         B2C_SYNC();
-        int par = 0, sb = 0;
-        u32 prev_single = B2C_NONE_U32;   // canonical token of the previous frame if it selected exactly one
-        int t = 0;
+        int t = ts;
 #if defined(__CUDACC__)
 #pragma unroll 1
 #endif
-        while (t < Tn) {
+        while (t < te) {
             const B2cFrameRec h = S.rh[t & HM];
             const int K = static_cast<int>(h.cnt);
             const int slot = t & TM;
@@ -1180,8 +1212,8 @@ B2C_HD void b2c_beam_block_fast(const B2cBeamArgs& A, int slot_cta, u8* smem) {
                 if (LT > 0 && (kind == B2C_CHEAP_T0 || kind == B2C_CHEAP_T3)) {
                     // extend the run while the next frames are in-place frames too; frame t + R must have its token
                     // list in the ring (its label records are staged during this iteration)
-                    int lim = Tn - t < B2C_FAST_RMAX ? Tn - t : B2C_FAST_RMAX;
-                    if (tv < Tn && tv - 1 - t < lim) lim = tv - 1 - t;
+                    int lim = te - t < B2C_FAST_RMAX ? te - t : B2C_FAST_RMAX;
+                    if (tv < te && tv - 1 - t < lim) lim = tv - 1 - t;
                     u32 pc = b2c_fast_tok0<WC, CAP, LT>(A.P, S, t, sb).canon;
                     while (R < lim) {
                         const B2cFrameRec hn = S.rh[(t + R) & HM];
@@ -1196,12 +1228,12 @@ B2C_HD void b2c_beam_block_fast(const B2cBeamArgs& A, int slot_cta, u8* smem) {
             }
             // ---- prefetch: frame records, token lists (visible at the next iteration) -----------------------
             {
-                const bool more_recs = hv < Tn && hv - t <= B2C_FAST_HR - 8;
-                const int tv_new = t + B2C_FAST_TR < Tn ? t + B2C_FAST_TR : Tn;
+                const bool more_recs = hv < te && hv - t <= B2C_FAST_HR - 8;
+                const int tv_new = t + B2C_FAST_TR < te ? t + B2C_FAST_TR : te;
                 B2C_IN_LAST_WARP {
                     if (more_recs) {
                         B2C_FOR_LANES(c, 8) {
-                            if (hv + c < Tn) b2c_cp_async16(&S.rh[(hv + c) & HM], recs + hv + c);
+                            if (hv + c < te) b2c_cp_async16(&S.rh[(hv + c) & HM], recs + hv + c);
                         }
                     }
                     for (int f = tv; f < tv_new; ++f) {
@@ -1214,7 +1246,7 @@ B2C_HD void b2c_beam_block_fast(const B2cBeamArgs& A, int slot_cta, u8* smem) {
                         }
                     }
                 }
-                if (more_recs) hv = hv + 8 < Tn ? hv + 8 : Tn;
+                if (more_recs) hv = hv + 8 < te ? hv + 8 : te;
                 if (tv_new > tv) tv = tv_new;
             }
 #if defined(__CUDA_ARCH__)
@@ -1222,7 +1254,7 @@ B2C_HD void b2c_beam_block_fast(const B2cBeamArgs& A, int slot_cta, u8* smem) {
             // loaded here into a register, stored to shared memory just before the closing barrier
             B2cTok ptk;
             bool has_ptk = false;
-            if (LT == 0 && t + 1 < Tn) {
+            if (LT == 0 && t + 1 < te) {
                 const u32 cn1 = S.rh[(t + 1) & HM].cnt;
                 has_ptk = threadIdx.x < (cn1 < static_cast<u32>(KR) ? cn1 : static_cast<u32>(KR));
                 if (has_ptk) ptk = A.P.toks[S.rid[(t + 1) & TM][threadIdx.x]];
@@ -1233,7 +1265,7 @@ B2C_HD void b2c_beam_block_fast(const B2cBeamArgs& A, int slot_cta, u8* smem) {
             int done_frames = 0;
             if (oversize) {
                 const u64 base_a = (f0 + static_cast<u64>(t & ~(B2C_RUN - 1))) * static_cast<u64>(V) + h.off;
-                const int K_next = t + 1 < Tn ? static_cast<int>(S.rh[(t + 1) & HM].cnt) : 1;
+                const int K_next = t + 1 < te ? static_cast<int>(S.rh[(t + 1) & HM].cnt) : 1;
                 // the general step wants a dense table: squeeze first (the squeezed table is the other one)
                 b2c_fast_compact<WC, CAP, LT>(&S, par);
                 par ^= 1;
@@ -1287,7 +1319,7 @@ B2C_HD void b2c_beam_block_fast(const B2cBeamArgs& A, int slot_cta, u8* smem) {
                 if (has_ptk) S.stok[sb ^ 1][threadIdx.x] = ptk;        // tn == t + 1: without the table every step covers one frame
             }
 #else
-            if (LT == 0 && tn < Tn) {
+            if (LT == 0 && tn < te) {
                 const u32 cn = S.rh[tn & HM].cnt;
                 const u32 kb = cn < static_cast<u32>(KR) ? cn : static_cast<u32>(KR);
                 B2C_FOR(c, kb) { S.stok[sb ^ 1][c] = A.P.toks[S.rid[tn & TM][c]]; }
@@ -1300,6 +1332,16 @@ B2C_HD void b2c_beam_block_fast(const B2cBeamArgs& A, int slot_cta, u8* smem) {
             if (!in_place) par ^= 1;
             sb ^= 1;
             t = tn;
+        }
+        if (te < Tn) {      // more frames in a later launch: park the state
+            const u32* const sw = reinterpret_cast<const u32*>(smem);
+            B2C_FOR(i, SAVE_WORDS) { parked[i] = sw[i]; }
+            B2C_LEADER {
+                parked[SAVE_WORDS] = static_cast<u32>(par);
+                parked[SAVE_WORDS + 1] = static_cast<u32>(sb);
+                parked[SAVE_WORDS + 2] = prev_single;
+            }
+            continue;
         }
         B2cOut O;
         const u64 ob = static_cast<u64>(A.P.out_beams);

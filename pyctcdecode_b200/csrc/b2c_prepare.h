@@ -276,7 +276,8 @@ struct B2cPrepArgs {
     int mode;                // 0: streaming pass (every utterance as logits, approximate row sums accumulated);
                              // 1: second pass over the utterances the decide kernel found to be probabilities
     double* approx;          // [B][2] sum of all elements, sum of their absolute values (zeroed before the launch)
-    const u64* tile_off;     // [B+1] exclusive prefix of ceil(T/32): work items of the lane-per-row kernel (V <= 32)
+    int tile_lo, tile_hi;    // lane-per-row kernel (V <= 32): tiles [tile_lo, tile_hi) of 32 frames of EVERY utterance are the
+                             // work items (utterance = item / (tile_hi - tile_lo); tiles past an utterance's end are skipped)
     int* is_prob;            // [B]
     u32* max_k;              // [B] largest per-frame token count (zeroed before the launch)
     u32* sum_k;              // [B] total number of selected tokens (zeroed before the launch)
@@ -884,20 +885,17 @@ struct B2cTileShared {
 
 struct B2cTileInfo { int u, t0, nrows; const float* src; u32 bytes; bool bulk; };
 
-__device__ __forceinline__ B2cTileInfo b2c_tile_locate(const B2cPrepArgs& A, u64 tile) {
-    int lo = 0, hi = A.n_utts - 1;
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (A.tile_off[mid] <= tile) lo = mid; else hi = mid - 1;
-    }
+__device__ __forceinline__ B2cTileInfo b2c_tile_locate(const B2cPrepArgs& A, u64 item) {
+    const u32 per = static_cast<u32>(A.tile_hi - A.tile_lo);
     B2cTileInfo ti;
-    ti.u = lo;
-    const int Tn = A.T[lo];
-    ti.t0 = static_cast<int>(tile - A.tile_off[lo]) * B2C_TILE_ROWS;
-    ti.nrows = Tn - ti.t0 < B2C_TILE_ROWS ? Tn - ti.t0 : B2C_TILE_ROWS;
-    ti.src = static_cast<const float*>(A.logits) + (A.frame_off[lo] + static_cast<u64>(ti.t0)) * static_cast<u64>(A.V);
+    ti.u = static_cast<int>(item / per);
+    const int Tn = A.T[ti.u];
+    ti.t0 = (A.tile_lo + static_cast<int>(item % per)) * B2C_TILE_ROWS;
+    ti.nrows = Tn - ti.t0 < B2C_TILE_ROWS ? Tn - ti.t0 : B2C_TILE_ROWS;          // <= 0: past the end of this utterance
+    if (ti.nrows < 0) ti.nrows = 0;
+    ti.src = static_cast<const float*>(A.logits) + (A.frame_off[ti.u] + static_cast<u64>(ti.t0)) * static_cast<u64>(A.V);
     ti.bytes = static_cast<u32>(ti.nrows) * static_cast<u32>(A.V) * 4u;
-    ti.bulk = (reinterpret_cast<u64>(ti.src) & 15ull) == 0 && (ti.bytes & 15u) == 0;
+    ti.bulk = ti.nrows > 0 && (reinterpret_cast<u64>(ti.src) & 15ull) == 0 && (ti.bytes & 15u) == 0;
     return ti;
 }
 
@@ -929,7 +927,7 @@ __device__ __forceinline__ void b2c_tile_wait(u64* mbar, u32 parity) {
 __device__ inline void b2c_tokens_tiles_v32(const B2cPrepArgs& A, int block_idx, int n_blocks, B2cTileShared* sh) {
     const unsigned full = 0xFFFFFFFFu;
     const int w = static_cast<int>(threadIdx.x >> 5), lane = static_cast<int>(threadIdx.x & 31);
-    const u64 total = A.tile_off[A.n_utts];
+    const u64 total = static_cast<u64>(A.n_utts) * static_cast<u64>(A.tile_hi - A.tile_lo);
     const u64 gw = static_cast<u64>(block_idx) * B2C_TILE_WARPS + w, n_warps = static_cast<u64>(n_blocks) * B2C_TILE_WARPS;
     const int V = A.V;
     if (lane == 0) {
@@ -956,6 +954,11 @@ __device__ inline void b2c_tokens_tiles_v32(const B2cPrepArgs& A, int block_idx,
             b2c_tile_issue(nxt, sh->tile[w][buf ^ 1], &sh->mbar[w][buf ^ 1], lane);
         }
         float* T0 = sh->tile[w][buf];
+        if (cur.nrows <= 0) {                 // a tile past the end of a short utterance of a ragged batch
+            cur = nxt;
+            buf ^= 1;
+            continue;
+        }
         if (cur.bulk) {
             b2c_tile_wait(&sh->mbar[w][buf], parity[buf]);
             parity[buf] ^= 1u;

@@ -465,3 +465,45 @@ def test_gpu_kenlm_binary_equals_arpa(pkg, tmp_path):
     a = dec_a.decode_beams_batch(None, xs[:6], beam_width=50, hotwords=[wl.words[3]])
     b = dec_b.decode_beams_batch(None, xs[:6], beam_width=50, hotwords=[wl.words[3]])
     assert [_beams(x) for x in a] == [_beams(x) for x in b]
+
+
+def test_gpu_pipelined_host_batches(pkg, orc):
+    """Pipelined calls on the device: a [B, T, V] float32 host block is cut into chunks along T, chunk c+1 crosses PCIe
+    while chunk c runs through the lane-per-row streaming kernel and a chunked launch of the beam kernel (state parked
+    in HBM between launches).  Second call of a configuration onwards; same results as the plain call (first call),
+    with and without an LM; probability input falls back to a plain call."""
+    for lm_order in (0, 3):
+        wl = synth.CharWorkload("B", n_words=5000, lm_order=lm_order)
+        kw = dict(kenlm_model_path=wl.arpa, unigrams=wl.words, alpha=0.5, beta=1.0) if lm_order else {}
+        dec = pkg.build_ctcdecoder(wl.labels, **kw)
+        ora = orc.OracleDecoder(wl.labels, **kw)
+        xs = np.stack(wl.batch(81_000, 40, 1000, "peaky"))
+        want = ora.decode_batch(list(xs), n_threads=_threads(), beam_width=100)
+        assert dec.decode_batch(None, xs, beam_width=100) == want
+        plain = dec.last_timings()["launches"]
+        for _ in range(3):
+            assert dec.decode_batch(None, xs, beam_width=100) == want
+        assert dec.last_timings()["launches"] > plain
+        got = dec.decode_beams_batch(None, xs[:6], beam_width=100)
+        got = dec.decode_beams_batch(None, xs[:6], beam_width=100)
+        ref = ora.decode_beams_batch(list(xs[:6]), n_threads=6, beam_width=100)
+        for w, g in zip(ref, got):
+            _compare(w, _beams(g))
+    e = np.exp(xs[:8] - xs[:8].max(2, keepdims=True))
+    probs = (e / e.sum(2, keepdims=True)).astype(np.float32)
+    want_p = ora.decode_batch(list(probs), n_threads=8, beam_width=100)
+    assert dec.decode_batch(None, probs, beam_width=100) == want_p
+    assert dec.decode_batch(None, probs, beam_width=100) == want_p
+
+
+@pytest.mark.parametrize("chunks", ["3"])
+def test_gpu_chunked_launches_give_the_same_results(chunks):
+    """B200CTC_FORCE_CHUNKS on the device: chunked launches of the latency-first kernel for every call of a child
+    pytest run over the special-step and ragged cases."""
+    import subprocess
+    import sys
+    env = dict(os.environ, B200CTC_FORCE_CHUNKS=chunks, B200CTC_FORCE_V5="1")
+    here = os.path.abspath(__file__)
+    r = subprocess.run([sys.executable, "-m", "pytest", here, "-x", "-q", "-m", "gpu", "-k", "special_single or ragged or headline_shape"],
+                       env=env, cwd=os.path.dirname(os.path.dirname(here)), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout[-3000:]

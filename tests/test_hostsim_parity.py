@@ -495,3 +495,43 @@ def test_hostsim_kenlm_binary_rejects_what_it_cannot_read(sim, tmp_path):
     open(str(tmp_path / "cut.bin"), "wb").write(bytes(good[: len(good) * 2 // 3]))
     with pytest.raises((ValueError, OSError, RuntimeError)):
         sim.NgramModel(str(tmp_path / "cut.bin"), wl.words).order
+
+
+@pytest.mark.parametrize("chunks", ["2", "5"])
+def test_hostsim_chunked_launches_give_the_same_results(chunks):
+    """Chunked launches of the latency-first kernel (frames [t0, t1) per launch, state parked in HBM in between -- what
+    the pipelined host path runs) forced for every call (B200CTC_FORCE_CHUNKS): the parity tests must pass unchanged."""
+    import sys
+    env = dict(os.environ, B200CTC_FORCE_CHUNKS=chunks, B200CTC_FORCE_V5="1")
+    here = os.path.abspath(__file__)
+    r = subprocess.run([sys.executable, "-m", "pytest", here, "-x", "-q", "-k", "golden or special or random or ragged or text_only"],
+                       env=env, cwd=os.path.dirname(os.path.dirname(here)), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout[-3000:]
+
+
+def test_hostsim_pipelined_host_batches(sim):
+    """The pipelined call (one [B, T, V] float32 host block, V <= 32, second call of a configuration onwards): chunks
+    along T are copied / prepared / decoded in turn.  Same transcripts and beams as the plain call; probability
+    input -- found out only after the last chunk -- makes the call redo itself as a plain call."""
+    wkw, lmkw = FAMILIES["B_3gram"]
+    wl = synth.make_workload(wkw)
+    kw = dict(lmkw, kenlm_model_path=wl.arpa, unigrams=wl.words)
+    dec = sim.build_ctcdecoder(wl.labels, **kw)
+    ora = orc.OracleDecoder(wl.labels, **kw)
+    T = 300
+    xs = np.stack([wl.utterance(9100 + i, T, ["peaky", "diffuse"][i % 2]) for i in range(5)])
+    want = ora.decode_batch(list(xs), beam_width=24)
+    assert dec.decode_batch(None, xs, beam_width=24) == want            # first call: plain (no hint yet)
+    launches_plain = dec.last_timings()["launches"]
+    assert dec.decode_batch(None, xs, beam_width=24) == want            # second call: pipelined
+    assert dec.last_timings()["launches"] > launches_plain               # one streaming + one beam launch per chunk
+    got = dec.decode_beams_batch(None, xs, beam_width=24)
+    ref = ora.decode_beams_batch(list(xs), beam_width=24)
+    for w, g in zip(ref, got):
+        _compare(w, _beams(g))
+    # probabilities in one utterance of the block: the pipelined attempt notices at the end and the call is redone
+    e = np.exp(xs - xs.max(2, keepdims=True))
+    probs = (e / e.sum(2, keepdims=True)).astype(np.float32)
+    want_p = ora.decode_batch(list(probs), beam_width=24)
+    assert dec.decode_batch(None, probs, beam_width=24) == want_p
+    assert dec.decode_batch(None, probs, beam_width=24) == want_p
