@@ -1225,7 +1225,8 @@ static int decode_batch_locked(b2c_decoder_t* d, const void* const* logits, cons
     while (set_cap < 8u * (static_cast<u32>(V) + 1)) set_cap <<= 1;
     std::vector<u64> run_off(n_utts + 1, 0);
     for (int i = 0; i < n_utts; ++i) run_off[i + 1] = run_off[i] + (static_cast<u64>(T[i]) + B2C_RUN - 1) / B2C_RUN;
-    const u64 total_runs = run_off[n_utts];
+    const int runs_per_utt = std::max(1, (T_max + B2C_RUN - 1) / B2C_RUN);
+    const u64 total_runs = static_cast<u64>(n_utts) * runs_per_utt;
     const int tiles_per_utt = std::max(1, (T_max + B2C_TILE_ROWS - 1) / B2C_TILE_ROWS);
     const int grid_tile = static_cast<int>(std::max<u64>(1, std::min<u64>((static_cast<u64>(n_utts) * tiles_per_utt + B2C_TILE_WARPS - 1) / B2C_TILE_WARPS, static_cast<u64>(d->n_sm) * 8)));
     const int grid_tok = static_cast<int>(std::max<u64>(1, std::min<u64>((total_runs + B2C_PREP_WARPS - 1) / B2C_PREP_WARPS, static_cast<u64>(d->n_sm) * 8)));
@@ -1260,7 +1261,7 @@ static int decode_batch_locked(b2c_decoder_t* d, const void* const* logits, cons
     const bool hint_ok = d->hint_valid && d->hint_beam == opts->beam_width && d->hint_lm == (P.lm.order > 0 ? 1 : 0) &&
                          d->hint_hot == (P.n_hot > 0 ? 1 : 0) && d->hint_prune == P.prune_history && d->hint_frames > 0;
     static const bool no_pipe = std::getenv("B200CTC_NO_PIPELINE") != nullptr;
-    bool pipe_candidate = allow_pipe && !no_pipe && !is_device && !half_in && dtype == B2C_DTYPE_F32 && V <= 32 && T_max >= 8 * B2C_TILE_ROWS &&
+    bool pipe_candidate = allow_pipe && !no_pipe && !is_device && !half_in && T_max >= 8 * B2C_TILE_ROWS &&
                           !streaming && n_lm == 1 && opts->beam_width <= 128 && hint_ok && !d->pipe_refused;
     for (int i = 0; i < n_utts && pipe_candidate; ++i)
         pipe_candidate = T[i] == T_max && static_cast<const char*>(logits[i]) == static_cast<const char*>(logits[0]) + static_cast<u64>(i) * T_max * V * esz_in;
@@ -1393,6 +1394,8 @@ static int decode_batch_locked(b2c_decoder_t* d, const void* const* logits, cons
     PA.is_prob = d->d_isprob.as<int>();
     PA.tile_lo = 0;
     PA.tile_hi = tiles_per_utt;
+    PA.run_lo = 0;
+    PA.run_hi = runs_per_utt;
     PA.approx = d->d_approx.as<double>();
     CUDA_OK(cudaMemsetAsync(d->d_approx.p, 0, 16ull * n_utts + 16, st));
     PA.max_k = d->d_maxk.as<u32>();
@@ -1627,21 +1630,29 @@ static int decode_batch_locked(b2c_decoder_t* d, const void* const* logits, cons
                 PC.mode = 0;
                 PC.tile_lo = t0 / B2C_TILE_ROWS;
                 PC.tile_hi = (t1 + B2C_TILE_ROWS - 1) / B2C_TILE_ROWS;
+                PC.run_lo = t0 / B2C_RUN;
+                PC.run_hi = (t1 + B2C_RUN - 1) / B2C_RUN;
+                const u64 run_items = static_cast<u64>(n_utts) * static_cast<u64>(PC.run_hi - PC.run_lo);
+                const int grid_runs = static_cast<int>(std::max<u64>(1, std::min<u64>((run_items + B2C_PREP_WARPS - 1) / B2C_PREP_WARPS, static_cast<u64>(grid_tok))));
 #ifdef B2C_HOSTSIM
                 {
-                    // hostsim has no lane-per-row kernel: the run-based routine over the runs of this chunk
                     std::unique_ptr<B2cPrepShared> sh(new B2cPrepShared());
-                    for (int u = 0; u < n_utts; ++u)
-                        for (u64 r = run_off[u] + static_cast<u64>(t0 / B2C_RUN); r < run_off[u] + static_cast<u64>((t1 + B2C_RUN - 1) / B2C_RUN); ++r)
-                            b2c_tokens_run_v32<float>(PC, r, 0, sh->sets[0][0], sh->sets[0][1]);
+                    for (int b = 0; b < grid_runs; ++b) {
+                        if (dtype == B2C_DTYPE_F32) b2c_tokens_block<float>(PC, b, grid_runs, sh.get());
+                        else b2c_tokens_block<double>(PC, b, grid_runs, sh.get());
+                    }
                 }
 #else
-                {
+                if (dtype == B2C_DTYPE_F32 && V <= 32) {
                     const u64 items = static_cast<u64>(n_utts) * static_cast<u64>(PC.tile_hi - PC.tile_lo);
                     const int grid = static_cast<int>(std::max<u64>(1, std::min<u64>((items + B2C_TILE_WARPS - 1) / B2C_TILE_WARPS, static_cast<u64>(d->n_sm) * 8)));
                     b2c_tokens_tile_kernel<<<grid, B2C_TILE_WARPS * 32, 0, st>>>(PC);
-                    CUDA_OK(cudaGetLastError());
+                } else if (dtype == B2C_DTYPE_F32) {
+                    b2c_tokens_kernel<float><<<grid_runs, B2C_PREP_THREADS, 0, st>>>(PC);
+                } else {
+                    b2c_tokens_kernel<double><<<grid_runs, B2C_PREP_THREADS, 0, st>>>(PC);
                 }
+                CUDA_OK(cudaGetLastError());
 #endif
                 d->tm.launches += 1;
                 if (chunk_timing) CUDA_OK(cudaEventRecord(d->chunk_ev[3 * c + 1], st));
@@ -1660,10 +1671,14 @@ static int decode_batch_locked(b2c_decoder_t* d, const void* const* logits, cons
 #ifdef B2C_HOSTSIM
             {
                 std::unique_ptr<B2cDecideShared> dsh(new B2cDecideShared());
-                for (int u = 0; u < n_utts; ++u) b2c_decide_block<float>(PA, u, dsh.get());
+                for (int u = 0; u < n_utts; ++u) {
+                    if (dtype == B2C_DTYPE_F32) b2c_decide_block<float>(PA, u, dsh.get());
+                    else b2c_decide_block<double>(PA, u, dsh.get());
+                }
             }
 #else
-            b2c_decide_kernel<float><<<n_utts, 128, 0, st>>>(PA);
+            if (dtype == B2C_DTYPE_F32) b2c_decide_kernel<float><<<n_utts, 128, 0, st>>>(PA);
+            else b2c_decide_kernel<double><<<n_utts, 128, 0, st>>>(PA);
             CUDA_OK(cudaGetLastError());
 #endif
             d->tm.launches += 1;

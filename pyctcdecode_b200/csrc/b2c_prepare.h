@@ -276,6 +276,8 @@ struct B2cPrepArgs {
     int mode;                // 0: streaming pass (every utterance as logits, approximate row sums accumulated);
                              // 1: second pass over the utterances the decide kernel found to be probabilities
     double* approx;          // [B][2] sum of all elements, sum of their absolute values (zeroed before the launch)
+    int run_lo, run_hi;      // run-based kernels: runs [run_lo, run_hi) of 8 frames of EVERY utterance are the work items
+                             // (utterance = item / (run_hi - run_lo); runs past an utterance's end are skipped)
     int tile_lo, tile_hi;    // lane-per-row kernel (V <= 32): tiles [tile_lo, tile_hi) of 32 frames of EVERY utterance are the
                              // work items (utterance = item / (tile_hi - tile_lo); tiles past an utterance's end are skipped)
     int* is_prob;            // [B]
@@ -609,14 +611,11 @@ B2C_HD u32 b2c_pyset_small_order(u32 mask, u32 amax, u32* out) {
 // 3 selected tokens go through the general set emulation afterwards, at offsets that are already known.
 template <class T>
 B2C_HD void b2c_tokens_run_v32(const B2cPrepArgs& A, u64 run, int lane, u16* set0, u16* set1) {
-    int lo = 0, hi = A.n_utts - 1;
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (A.run_off[mid] <= run) lo = mid; else hi = mid - 1;
-    }
-    const int u = lo;
+    const u32 per = static_cast<u32>(A.run_hi - A.run_lo);
+    const int u = static_cast<int>(run / per);
     const int Tn = A.T[u];
-    const int t0 = static_cast<int>(run - A.run_off[u]) * B2C_RUN;
+    const int t0 = (A.run_lo + static_cast<int>(run % per)) * B2C_RUN;
+    if (t0 >= Tn) return;                                   // a run past the end of a short utterance of a ragged batch
     const int t1 = t0 + B2C_RUN < Tn ? t0 + B2C_RUN : Tn;
     const int nf = t1 - t0;
     const int V = A.V;
@@ -775,14 +774,11 @@ B2C_HD void b2c_tokens_run_v32(const B2cPrepArgs& A, u64 run, int lane, u16* set
 template <class T>
 B2C_HD void b2c_tokens_run(const B2cPrepArgs& A, u64 run, int lane, u16* set0, u16* set1) {
     // locate the utterance of this run (binary search over the prefix of runs per utterance)
-    int lo = 0, hi = A.n_utts - 1;
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (A.run_off[mid] <= run) lo = mid; else hi = mid - 1;
-    }
-    const int u = lo;
+    const u32 per = static_cast<u32>(A.run_hi - A.run_lo);
+    const int u = static_cast<int>(run / per);
     const int Tn = A.T[u];
-    const int t0 = static_cast<int>(run - A.run_off[u]) * B2C_RUN;
+    const int t0 = (A.run_lo + static_cast<int>(run % per)) * B2C_RUN;
+    if (t0 >= Tn) return;                                   // a run past the end of a short utterance of a ragged batch
     const int t1 = t0 + B2C_RUN < Tn ? t0 + B2C_RUN : Tn;
     const int V = A.V;
     const u64 f0 = A.frame_off[u];
@@ -837,7 +833,7 @@ B2C_HD void b2c_tokens_run(const B2cPrepArgs& A, u64 run, int lane, u16* set0, u
 
 template <class T>
 B2C_HD void b2c_tokens_block(const B2cPrepArgs& A, int block_idx, int n_blocks, B2cPrepShared* sh) {
-    const u64 total_runs = A.run_off[A.n_utts];
+    const u64 total_runs = static_cast<u64>(A.n_utts) * static_cast<u64>(A.run_hi - A.run_lo);
     const bool small = A.V <= 32;
     if (A.mode == 1 && *reinterpret_cast<const u32*>(A.approx + 2 * A.n_utts) == 0) return;   // no probability input
 #if defined(__CUDA_ARCH__)

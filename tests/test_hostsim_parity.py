@@ -509,17 +509,20 @@ def test_hostsim_chunked_launches_give_the_same_results(chunks):
     assert r.returncode == 0, r.stdout[-3000:]
 
 
-def test_hostsim_pipelined_host_batches(sim):
-    """The pipelined call (one [B, T, V] float32 host block, V <= 32, second call of a configuration onwards): chunks
-    along T are copied / prepared / decoded in turn.  Same transcripts and beams as the plain call; probability
-    input -- found out only after the last chunk -- makes the call redo itself as a plain call."""
-    wkw, lmkw = FAMILIES["B_3gram"]
+@pytest.mark.parametrize("fam,dtype", [("B_3gram", np.float32), ("C_bpe_4gram", np.float32), ("B_nolm", np.float64)])
+def test_hostsim_pipelined_host_batches(sim, fam, dtype):
+    """The pipelined call (one [B, T, V] host block, second call of a configuration onwards): chunks along T are
+    copied / prepared / decoded in turn.  Same transcripts and beams as the plain call; probability input -- found
+    out only after the last chunk -- makes the call redo itself as a plain call."""
+    wkw, lmkw = FAMILIES[fam]
     wl = synth.make_workload(wkw)
-    kw = dict(lmkw, kenlm_model_path=wl.arpa, unigrams=wl.words)
+    kw = dict(lmkw)
+    if wl.arpa:
+        kw.update(kenlm_model_path=wl.arpa, unigrams=wl.words)
     dec = sim.build_ctcdecoder(wl.labels, **kw)
     ora = orc.OracleDecoder(wl.labels, **kw)
     T = 300
-    xs = np.stack([wl.utterance(9100 + i, T, ["peaky", "diffuse"][i % 2]) for i in range(5)])
+    xs = np.stack([wl.utterance(9100 + i, T, ["peaky", "diffuse"][i % 2] if wl.V <= 64 else "peaky") for i in range(5)]).astype(dtype)
     want = ora.decode_batch(list(xs), beam_width=24)
     assert dec.decode_batch(None, xs, beam_width=24) == want            # first call: plain (no hint yet)
     launches_plain = dec.last_timings()["launches"]
@@ -531,7 +534,7 @@ def test_hostsim_pipelined_host_batches(sim):
         _compare(w, _beams(g))
     # probabilities in one utterance of the block: the pipelined attempt notices at the end and the call is redone
     e = np.exp(xs - xs.max(2, keepdims=True))
-    probs = (e / e.sum(2, keepdims=True)).astype(np.float32)
+    probs = (e / e.sum(2, keepdims=True)).astype(dtype)
     want_p = ora.decode_batch(list(probs), beam_width=24)
     assert dec.decode_batch(None, probs, beam_width=24) == want_p
     assert dec.decode_batch(None, probs, beam_width=24) == want_p
