@@ -1418,10 +1418,11 @@ static int decode_batch_locked(b2c_decoder_t* d, const void* const* logits, cons
         CUDA_OK(cudaStreamSynchronize(st));
         hp_mark(1);                                   // wait: H2D + prepare kernels
     } else {
-        // no statistics yet: the worst case for the workspace, the hint for the kernel variant
+        // no statistics yet: the worst case (V tokens in a frame) sizes the workspace; the capacity class comes from
+        // the hint (one token per frame "on average" keeps the statistics-based bound out of its way)
         for (int i = 0; i < n_utts; ++i) {
             d->h_maxk.as<u32>()[i] = static_cast<u32>(V);
-            d->h_sumk.as<u32>()[i] = static_cast<u32>(std::min<u64>(static_cast<u64>(T[i]) * V, 0xFFFFFFFFull));
+            d->h_sumk.as<u32>()[i] = static_cast<u32>(T[i]);
         }
     }
     const u32* h_maxk = d->h_maxk.as<u32>();
