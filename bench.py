@@ -188,7 +188,7 @@ def config_of(spec, regime, beam, B, V, logits_dtype, world):
             "parallelism": "utterance-sharded x%d" % world}
 
 
-def port_arm(wl, spec, kw, xs, beam, hot, target_cpu_seconds=20.0, min_utts=0, wall_seconds=0.0):
+def port_arm(wl, spec, kw, xs, beam, hot, target_cpu_seconds=20.0, min_utts=0, wall_seconds=0.0, call="decode_batch"):
     """The reference's CPU path restated (oracle/ctc_oracle.cpp, a C++ port -- the reference itself is
     pure Python) on all host cores, over a bounded sample of the same workload: about `target_cpu_seconds` of CPU work,
     or (wall_seconds > 0) about that much wall time on all cores; the list is cycled if the sample needs more
@@ -206,7 +206,10 @@ def port_arm(wl, spec, kw, xs, beam, hot, target_cpu_seconds=20.0, min_utts=0, w
         n = int(max(min(len(xs), target_cpu_seconds / per_utt), min(len(xs), max(cores, min_utts))))
         sample = xs[:n]
     t0 = time.perf_counter()
-    texts = ora.decode_batch(sample, n_threads=cores, beam_width=beam, hotwords=hot)
+    if call == "decode_beams_batch":        # all beams, prune_history off (decoder.py:801-857); top-1 text for the comparison
+        texts = [(b[0][0] if b else "") for b in ora.decode_beams_batch(sample, n_threads=cores, beam_width=beam, hotwords=hot)]
+    else:
+        texts = ora.decode_batch(sample, n_threads=cores, beam_width=beam, hotwords=hot)
     dt = time.perf_counter() - t0
     frames = sum(x.shape[0] for x in sample)
     return {"value": frames / dt, "unit": "frames/s", "cores": cores, "kind": "port",
@@ -395,7 +398,7 @@ def secondary_entry(torch, pkg, flush, name, spec, regime, beam, logits_dtype, c
     ms_beam = statistics.mean(t["ms_beam"] for t in tms)
     ms_prep = statistics.mean(t["ms_prepare"] for t in tms)
     texts = out if call == "decode_batch" else [beams[0].text if beams else "" for beams in out]
-    info, cpu_texts, n = port_arm(wl, spec, kw, st.xs, beam, hot, target_cpu_seconds=cpu_seconds)
+    info, cpu_texts, n = port_arm(wl, spec, kw, st.xs, beam, hot, target_cpu_seconds=cpu_seconds, call=call)
     ent = {"name": name, "config": config_of(spec, regime, beam, B, wl.V, logits_dtype, 1), "call": call,
            "value": frames * steps / total, "unit": "frames/s", "ms_per_step": 1e3 * total / steps, "steps": steps, "warmup": warmup,
            "e2e": {"value": frames * steps / e2e_total, "unit": "frames/s", "ms_per_step": 1e3 * e2e_total / steps,

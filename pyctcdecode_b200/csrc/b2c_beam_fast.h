@@ -47,16 +47,13 @@
 #define B2C_FAST_HR 32          // frame-record ring (frames)
 #define B2C_FAST_TR 8           // token ring (frames)
 #define B2C_FAST_RMAX 6         // longest run of in-place frames handled by one step (<= B2C_FAST_TR - 2)
-#ifndef B2C_FAST_NT
-#define B2C_FAST_NT 128         // threads per CTA
-#endif
-#define B2C_FAST_NW (B2C_FAST_NT / 32)
+#define B2C_FAST_NW 4           // most warps per CTA (a CTA has WC threads: one per beam slot; per-warp slot arrays have 4 entries)
 
 #if defined(__CUDA_ARCH__)
 #define B2C_LAST_THREAD if (threadIdx.x == blockDim.x - 1)
 // work for ONE warp -- the last one, which holds the slots >= 96 and has the fewest live beams -- so that the other
 // warps walk straight into the frame step: items strided over its lanes
-#define B2C_IN_LAST_WARP if ((threadIdx.x >> 5) == B2C_FAST_NW - 1)
+#define B2C_IN_LAST_WARP if ((threadIdx.x >> 5) == (blockDim.x >> 5) - 1)
 #define B2C_FOR_LANES(i, n) for (int i = static_cast<int>(threadIdx.x & 31); i < static_cast<int>(n); i += 32)
 #else
 #define B2C_LAST_THREAD if (true)
@@ -135,7 +132,7 @@ struct B2cFastSmem {
     u32 pt_idx[PT], pt_min[PT];
     alignas(16) u32 bcnt[B2C_NBUCKET];
     alignas(16) u32 bhead[B2C_NBUCKET];
-    alignas(16) u32 bpre[B2C_FAST_NW][B2C_NBUCKET];
+    alignas(16) u32 bpre[WC / 32][B2C_NBUCKET];
     // candidates
     u64 ckey[CAP];           // merge key; after phase B: order-preserving score key of group leaders, 0 otherwise
     double cfold[CAP];       // phase A: own logit sum; after phase B (leaders): merged logit_score
@@ -518,6 +515,10 @@ B2C_HD void b2c_fast_step(const B2cParams& P, B2cFastSmem<WC, CAP, LT>& S, B2cCh
                 rank += (kj > key || (kj == key && j < static_cast<u32>(i))) ? 1u : 0u;
             }
             if (rank >= width) continue;
+            if (WC < 128 && rank >= static_cast<u32>(WC)) {        // lean variant: more survivors than slots
+                b2c_atomic_or_u32(&S.sc.status, B2C_ERR_SLOTS);
+                continue;
+            }
             if (rank + 1 > my_top) my_top = rank + 1;
             const u32 last = S.clast[i];
             if (prune) {
@@ -916,6 +917,10 @@ B2C_HD bool b2c_fast_sorted_step(const B2cParams& P, B2cFastSmem<WC, CAP, LT>& S
                     rank += b2c_live_before(wm, b2c_sorted_count<WC>(cur.logit, n, lp2, s, k2 < k));
                 }
                 if (rank >= width) continue;
+                if (WC < 128 && rank >= static_cast<u32>(WC)) {    // lean variant: more survivors than slots
+                    b2c_atomic_or_u32(&S.sc.status, B2C_ERR_SLOTS);
+                    continue;
+                }
                 S.ord[rank] = static_cast<u32>(b) | (static_cast<u32>(k) << 16);
                 if (rank + 1 > my_top) my_top = rank + 1;
             }
@@ -1091,6 +1096,7 @@ B2C_HD void b2c_beam_block_fast(const B2cBeamArgs& A, int slot_cta, u8* smem) {
     const int V = A.P.V;
     u32 st_over[6] = {0, 0, 0, 0, 0, 0};    // candidate-count histogram of the fast frames (last thread's copy counts)
     u32 st_frames = 0, st_inplace = 0, st_sorted = 0;
+    u32 st_wide_utts = 0, st_utts = 0;      // utterances a one-warp CTA (32 slots, 128 candidates, 16 tokens) could NOT hold
     B2C_LEADER {
         for (int q = 0; q < 6; ++q) S.sc.m_over[q] = 0;
         S.sc.m_frames = 0;
@@ -1167,7 +1173,7 @@ B2C_HD void b2c_beam_block_fast(const B2cBeamArgs& A, int slot_cta, u8* smem) {
             S.holes = 0;
             S.cheap_bad = 0;
             S.run_fail = B2C_NONE_U32;
-            for (int c = 0; c < B2C_FAST_NW; ++c) { S.wmax[c] = 0; S.wtop[c] = 0; }
+            for (int c = 0; c < B2C_FAST_NW; ++c) { S.wmax[c] = 0; S.wtop[c] = 0; S.wmask[c] = 0; }
             S.wtop[0] = 1;
             S.wmax[0] = b2c_f64_key(0.0);
             // backtrack nodes of the frame steps have fixed ids below WC * T; the out-of-line step allocates above
@@ -1194,6 +1200,7 @@ B2C_HD void b2c_beam_block_fast(const B2cBeamArgs& A, int slot_cta, u8* smem) {
         }
         B2C_SYNC();
         int t = ts;
+        bool wide_utt = false;
 #if defined(__CUDACC__)
 #pragma unroll 1
 #endif
@@ -1205,6 +1212,15 @@ B2C_HD void b2c_beam_block_fast(const B2cBeamArgs& A, int slot_cta, u8* smem) {
             // ---- what kind of step, and how many frames it covers ------------------------------------------
             const u32 Mq = b2c_max_slots(S.wtop) * static_cast<u32>(K);
             const bool oversize = Mq > static_cast<u32>(CAP) || K > KR;
+            wide_utt = wide_utt || Mq > 128u || K > 16 || Mq > 32u * static_cast<u32>(K);
+            if (WC < 128 && (oversize || S.sc.status != B2C_OK)) {
+                // lean variant (one warp, WC slots): no out-of-line tier and no room for more survivors -- the
+                // utterance is handed back with an error status and decoded again by the full variant (host retry pass)
+                B2C_SYNC();
+                B2C_LEADER { S.sc.status |= B2C_ERR_SLOTS; }
+                B2C_SYNC();
+                break;
+            }
             int kind = B2C_CHEAP_NO;
             int R = 1;
             if (!oversize && K == 1 && prev_single != B2C_NONE_U32) {
@@ -1333,6 +1349,10 @@ B2C_HD void b2c_beam_block_fast(const B2cBeamArgs& A, int slot_cta, u8* smem) {
             sb ^= 1;
             t = tn;
         }
+        B2C_LAST_THREAD {
+            ++st_utts;
+            st_wide_utts += wide_utt ? 1u : 0u;
+        }
         if (te < Tn) {      // more frames in a later launch: park the state
             const u32* const sw = reinterpret_cast<const u32*>(smem);
             B2C_FOR(i, SAVE_WORDS) { parked[i] = sw[i]; }
@@ -1372,6 +1392,8 @@ B2C_HD void b2c_beam_block_fast(const B2cBeamArgs& A, int slot_cta, u8* smem) {
             if (st_frames) b2c_atomic_add_u32(A.m_stats + 6, st_frames);
             if (st_inplace) b2c_atomic_add_u32(A.m_stats + 7, st_inplace);
             if (st_sorted) b2c_atomic_add_u32(A.m_stats + 8, st_sorted);
+            if (st_wide_utts) b2c_atomic_add_u32(A.m_stats + 9, st_wide_utts);
+            if (st_utts) b2c_atomic_add_u32(A.m_stats + 10, st_utts);
         }
         B2C_LEADER {   // frames that took the general step counted themselves in shared memory
             for (int c = 0; c < 6; ++c)

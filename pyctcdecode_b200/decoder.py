@@ -396,8 +396,13 @@ class BeamSearchDecoderCTC:
                 beams = []
                 for b in range(L.b2c_result_n_beams(res, u)):
                     nw = L.b2c_result_n_words(res, u, b)
-                    fr = L.b2c_result_frames(res, u, b)
-                    frames = [(L.b2c_result_word(res, u, b, w).decode("utf-8"), (fr[2 * w], fr[2 * w + 1])) for w in range(nw)]
+                    text = L.b2c_result_text(res, u, b).decode("utf-8")
+                    if nw:
+                        # words = the text's words (labels never contain a space inside a word), frames in one array
+                        fr = np.ctypeslib.as_array(L.b2c_result_frames(res, u, b), shape=(2 * nw,)).tolist()
+                        frames = list(zip(text.split(" "), zip(fr[0::2], fr[1::2])))
+                    else:
+                        frames = []
                     state = None
                     if with_state and L.b2c_result_lm_state(res, u, b, C.byref(st)):
                         state = B200LMState._from_c(st)
@@ -407,8 +412,7 @@ class BeamSearchDecoderCTC:
                                 L.b2c_result_lm_state_at(res, u, b, j, C.byref(st))
                                 parts.append(B200LMState._from_c(st))
                             state = MultiLanguageModelState(parts)
-                    beams.append(OutputBeam(L.b2c_result_text(res, u, b).decode("utf-8"), state, frames,
-                                            L.b2c_result_logit_score(res, u, b), L.b2c_result_lm_score(res, u, b)))
+                    beams.append(OutputBeam(text, state, frames, L.b2c_result_logit_score(res, u, b), L.b2c_result_lm_score(res, u, b)))
                 out.append(beams)
         finally:
             L.b2c_result_free(res)
