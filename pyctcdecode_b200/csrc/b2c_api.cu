@@ -306,6 +306,19 @@ static const size_t kV5Save[4][2] = {{offsetof(B2cFastSmemA0, ckey), offsetof(B2
                                      {offsetof(B2cFastSmemC0, ckey), offsetof(B2cFastSmemC, ckey)},
                                      {offsetof(B2cFastSmemL0, ckey), offsetof(B2cFastSmemL, ckey)}};
 #define B2C_PIPE_CHUNKS 4
+// Features that are ON by default only once a GPU run has validated them (the environment overrides either way:
+// B200CTC_PIPELINE=0/1, B200CTC_LEAN=0/1; read at every call so that tests can switch them).
+#ifndef B2C_DEFAULT_PIPELINE
+#define B2C_DEFAULT_PIPELINE 0
+#endif
+#ifndef B2C_DEFAULT_LEAN
+#define B2C_DEFAULT_LEAN 0
+#endif
+static bool env_switch(const char* name, bool dflt) {
+    const char* e = std::getenv(name);
+    if (!e || !*e) return dflt;
+    return !(e[0] == '0' && e[1] == 0);
+}
 #define B2C_E_RETRY_PLAIN (-1000)     // internal: the pipelined attempt must be redone as a plain call
 static_assert(2 * (sizeof(B2cFastSmemA) + 1024) <= 228 * 1024, "variant A: 2 CTAs per SM");
 static_assert(3 * (sizeof(B2cFastSmemB) + 1024) <= 228 * 1024, "variant B: 3 CTAs per SM");
@@ -1274,7 +1287,7 @@ static int decode_batch_locked(b2c_decoder_t* d, const void* const* logits, cons
     // call that turns out to hold probabilities is redone as a plain call (B2C_E_RETRY_PLAIN).
     const bool hint_ok = d->hint_valid && d->hint_beam == opts->beam_width && d->hint_lm == (P.lm.order > 0 ? 1 : 0) &&
                          d->hint_hot == (P.n_hot > 0 ? 1 : 0) && d->hint_prune == P.prune_history && d->hint_frames > 0;
-    static const bool no_pipe = std::getenv("B200CTC_NO_PIPELINE") != nullptr;
+    const bool no_pipe = std::getenv("B200CTC_NO_PIPELINE") != nullptr || !env_switch("B200CTC_PIPELINE", B2C_DEFAULT_PIPELINE != 0);
     bool pipe_candidate = allow_pipe && !no_pipe && !is_device && !half_in && T_max >= 8 * B2C_TILE_ROWS &&
                           !streaming && n_lm == 1 && opts->beam_width <= 128 && hint_ok && !d->pipe_refused;
     for (int i = 0; i < n_utts && pipe_candidate; ++i)
@@ -1506,10 +1519,11 @@ static int decode_batch_locked(b2c_decoder_t* d, const void* const* logits, cons
         if (const char* e = std::getenv("B200CTC_V5_VARIANT")) v5_variant = std::max(0, std::min(2, std::atoi(e)));
         // the lean one-warp variant: more utterances than the chosen variant keeps resident, and the previous call of
         // this configuration says that (nearly) every utterance fits 32 slots / 128 candidates / 16 tokens per frame
-        static const bool no_lean = std::getenv("B200CTC_NO_LEAN") != nullptr, force_lean = std::getenv("B200CTC_FORCE_LEAN") != nullptr;
-        use_lean = use_v5 && opts->beam_width <= 128 && !no_lean &&
-                   (force_lean || (hint_ok && !d->lean_bad && d->hint_utts > 0 && 20ull * d->hint_wide_utts <= d->hint_utts &&
-                                   n_fast > d->n_sm * kV5Occ[v5_variant]));
+        const bool no_lean = std::getenv("B200CTC_NO_LEAN") != nullptr || !env_switch("B200CTC_LEAN", B2C_DEFAULT_LEAN != 0);
+        const bool force_lean = std::getenv("B200CTC_FORCE_LEAN") != nullptr;
+        use_lean = use_v5 && opts->beam_width <= 128 &&
+                   (force_lean || (!no_lean && (hint_ok && !d->lean_bad && d->hint_utts > 0 && 20ull * d->hint_wide_utts <= d->hint_utts &&
+                                   n_fast > d->n_sm * kV5Occ[v5_variant])));
         for (int q = 0; q < n_utts; ++q) {
             const int u = order[q];             // keeps longest-first order inside every class
             classes[cls_of[u] < kNumCaps ? top : kNumCaps].push_back(u);
