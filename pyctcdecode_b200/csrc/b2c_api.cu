@@ -309,7 +309,7 @@ static const size_t kV5Save[4][2] = {{offsetof(B2cFastSmemA0, ckey), offsetof(B2
 // Features that are ON by default only once a GPU run has validated them (the environment overrides either way:
 // B200CTC_PIPELINE=0/1, B200CTC_LEAN=0/1; read at every call so that tests can switch them).
 #ifndef B2C_DEFAULT_PIPELINE
-#define B2C_DEFAULT_PIPELINE 0
+#define B2C_DEFAULT_PIPELINE 1
 #endif
 #ifndef B2C_DEFAULT_LEAN
 #define B2C_DEFAULT_LEAN 0
@@ -550,6 +550,7 @@ struct b2c_decoder {
     cudaEvent_t chunk_ev[3 * B2C_PIPE_CHUNKS] = {};
     DevBuf d_state;
     bool pipe_refused = false;            // the last pipelined attempt of this configuration could not be planned
+    double last_device_ms = 0.0;          // streaming stage + beam kernel of the previous call (chunk sizing of pipelined calls)
     std::mutex call_mu;                   // b2c_decode_batch is serialised per handle (scratch buffers are per handle)
     b2c_timings_t tm;
     // adaptive sizing: candidate-count histogram of the previous call with the same configuration
@@ -1632,9 +1633,32 @@ static int decode_batch_locked(b2c_decoder_t* d, const void* const* logits, cons
         return B2C_E_RETRY_PLAIN;
     }
     static const int force_chunks = std::getenv("B200CTC_FORCE_CHUNKS") ? std::atoi(std::getenv("B200CTC_FORCE_CHUNKS")) : 0;   // tests
-    int n_chunks = 1, clen = T_max > 0 ? T_max : 1;
-    if (pipe_candidate) { n_chunks = (T_max + chunk_len - 1) / chunk_len; clen = chunk_len; }
-    else if (can_chunk && force_chunks > 1 && T_max >= 2) { n_chunks = std::min(force_chunks, T_max); clen = (T_max + n_chunks - 1) / n_chunks; n_chunks = (T_max + clen - 1) / clen; }
+    // Chunk boundaries.  A chunked launch ends when its SLOWEST utterance has finished the chunk, so every boundary
+    // costs the spread of the per-chunk times (measured: 4 equal chunks at C2 take 4.8 ms of beam kernel instead of
+    // 3.75).  Compute-bound calls (the copy is shorter than the decode) therefore use TWO chunks: a short first one whose
+    // decode covers the copy of the rest; copy-bound calls (large alphabets) use equal chunks.
+    std::vector<int> bounds{0, std::max(T_max, 0)};
+    if (pipe_candidate) {
+        const double copy_ms = static_cast<double>(total_frames) * V * esz / 50.0e6;             // ~50 GB/s pinned H2D
+        const double comp_ms = d->last_device_ms > 0 ? d->last_device_ms : copy_ms;            // previous call of the configuration
+        const double r = copy_ms / std::max(comp_ms, 1e-3);
+        bounds.clear();
+        bounds.push_back(0);
+        if (r < 0.6) {
+            int f = static_cast<int>(1.15 * T_max * r / (1.0 + r));
+            f = std::max(2 * B2C_TILE_ROWS, ((f + B2C_TILE_ROWS - 1) / B2C_TILE_ROWS) * B2C_TILE_ROWS);
+            if (f < T_max) bounds.push_back(f);
+        } else {
+            for (int c = 1; c < B2C_PIPE_CHUNKS; ++c) if (c * chunk_len < T_max) bounds.push_back(c * chunk_len);
+        }
+        bounds.push_back(T_max);
+    } else if (can_chunk && force_chunks > 1 && T_max >= 2) {
+        const int nc = std::min(force_chunks, T_max), cl = (T_max + nc - 1) / nc;
+        bounds.clear();
+        for (int t0 = 0; t0 < T_max; t0 += cl) bounds.push_back(t0);
+        bounds.push_back(T_max);
+    }
+    const int n_chunks = static_cast<int>(bounds.size()) - 1;
     bool chunk_timing = false;
     if (n_chunks > 1) {
         const Launch& ln = launches[0];
@@ -1652,7 +1676,7 @@ static int decode_batch_locked(b2c_decoder_t* d, const void* const* logits, cons
             // every chunk's copy is queued at once on the copy stream; the compute stream waits chunk by chunk
             const size_t pitch = static_cast<size_t>(T_max) * V * esz;
             for (int c = 0; c < n_chunks; ++c) {
-                const int t0 = c * clen, t1 = std::min(T_max, (c + 1) * clen);
+                const int t0 = bounds[c], t1 = bounds[c + 1];
                 CUDA_OK(cudaMemcpy2DAsync(d->d_logits.as<char>() + static_cast<size_t>(t0) * V * esz, pitch,
                                           static_cast<const char*>(logits[0]) + static_cast<size_t>(t0) * V * esz, pitch,
                                           static_cast<size_t>(t1 - t0) * V * esz, static_cast<size_t>(n_utts), cudaMemcpyHostToDevice, d->copy_stream));
@@ -1663,7 +1687,7 @@ static int decode_batch_locked(b2c_decoder_t* d, const void* const* logits, cons
         }
         CUDA_OK(cudaEventRecord(d->ev[5], st));
         for (int c = 0; c < n_chunks; ++c) {
-            const int t0 = c * clen, t1 = std::min(T_max, (c + 1) * clen);
+            const int t0 = bounds[c], t1 = bounds[c + 1];
             if (pipe_candidate) {
                 CUDA_OK(cudaStreamWaitEvent(st, d->copied[c % B2C_PIPE_CHUNKS], 0));
                 if (chunk_timing) CUDA_OK(cudaEventRecord(d->chunk_ev[3 * c], st));
@@ -1852,12 +1876,26 @@ static int decode_batch_locked(b2c_decoder_t* d, const void* const* logits, cons
         }
         d->tm.ms_prepare = mp;
         d->tm.ms_beam = mb;
+        if (host_prof) {
+            std::fprintf(stderr, "[b2c pipeline, ms after the call's first event]");
+            for (int c = 0; c < n_chunks; ++c) {
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+                cudaEventElapsedTime(&a0, d->ev[0], d->chunk_ev[3 * c]);
+                cudaEventElapsedTime(&a1, d->ev[0], d->chunk_ev[3 * c + 1]);
+                cudaEventElapsedTime(&a2, d->ev[0], d->chunk_ev[3 * c + 2]);
+                std::fprintf(stderr, "  chunk %d: copied %.3f streamed %.3f decoded %.3f", c, a0, a1, a2);
+            }
+            float a4 = 0.f;
+            cudaEventElapsedTime(&a4, d->ev[0], d->ev[4]);
+            std::fprintf(stderr, "  d2h done %.3f\n", a4);
+        }
     } else {
         if (!pipe_candidate && cudaEventElapsedTime(&ms, d->ev[1], d->ev[2]) == cudaSuccess) d->tm.ms_prepare = ms;
         if (cudaEventElapsedTime(&ms, d->ev[5], d->ev[3]) == cudaSuccess) d->tm.ms_beam = ms;
     }
     if (cudaEventElapsedTime(&ms, d->ev[0], d->ev[4]) == cudaSuccess) d->tm.ms_total = ms;
     d->tm.frames = static_cast<long long>(total_frames);
+    d->last_device_ms = static_cast<double>(d->tm.ms_prepare) + static_cast<double>(d->tm.ms_beam);
     // total selected tokens = last tok_start of the last utterance ... summed per utterance is not
     // available without a reduction; report the last utterance's end offset only when B == 1
     d->tm.tokens = 0;

@@ -416,65 +416,6 @@ B2C_HD void b2c_prep_row(const T* row, int V, bool is_prob, double thr, int lane
     const unsigned full = 0xFFFFFFFFu;
     T m = static_cast<T>(0);
     double ls = 0.0;
-    if (sizeof(T) == 4 && !is_prob && !kMaskOnly && V > 32 && V <= 1024 && thr > B2C_LOG_MIN_CLIP) {
-        // float32 logits, wide rows (BPE vocabularies): the row is read ONCE into registers (32 elements per lane),
-        // everything is float32 (same definition, same bits as the general code below: the sum is an integer sum,
-        // the selection compares against thr rounded up to float32, the clip cannot move the arg-max); rows with a
-        // NaN or an infinity take the general code
-        const float* frow = reinterpret_cast<const float*>(row);
-        float r[32];
-        float sa = 0.0f, mx = -3.402823466e38f;
-#pragma unroll
-        for (int c = 0; c < 32; ++c) {
-            const int v = c * 32 + lane;
-            r[c] = v < V ? frow[v] : -3.402823466e38f;
-            if (v < V) { sa += fabsf(r[c]); mx = fmaxf(mx, r[c]); }
-        }
-        for (int off = 16; off >= 1; off >>= 1) {
-            sa += __shfl_xor_sync(full, sa, off);
-            mx = fmaxf(mx, __shfl_xor_sync(full, mx, off));
-        }
-        if (sa < 3.0e38f) {                                     // warp-uniform: no NaN, no infinity
-            u64 q = 0;
-#pragma unroll
-            for (int c = 0; c < 32; ++c)
-                if (c * 32 + lane < V) q += __float2ull_rn(B2C_SM_MUL(b2c_sm_expf(r[c] - mx), 4294967296.0f));
-            for (int off = 16; off >= 1; off >>= 1) q += __shfl_xor_sync(full, q, off);
-            const float lsf = b2c_sm_finish(q, false, false);
-            const float thr_up = __double2float_ru(thr);
-            float bestf = -3.402823466e38f;
-            int bi = -1;
-            u32 nsel = 0;
-            if (lane == 0) b2c_pyset_init(set, set.buf[0], set.buf[1]);
-#pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                if (c * 32 >= V) continue;                            // warp-uniform; r[] stays in registers (static indices)
-                const int v = c * 32 + lane;
-                const float lpf = B2C_SM_ADD(r[c] - mx, -lsf);
-                const bool in = v < V;
-                if (in && lpf > bestf) { bestf = lpf; bi = v; }       // ascending v per lane: the first of equals stays
-                unsigned mask = __ballot_sync(full, in && lpf >= thr_up);
-                if (mask) {                                          // warp-uniform
-                    nsel += __popc(mask);
-                    if (lane == 0) {
-                        while (mask) {
-                            const int bit = __ffs(mask) - 1;
-                            mask &= mask - 1;
-                            b2c_pyset_add(set, static_cast<u32>(c * 32 + bit));
-                        }
-                    }
-                    __syncwarp();
-                }
-            }
-            for (int off = 16; off >= 1; off >>= 1) {
-                const float ob = __shfl_xor_sync(full, bestf, off);
-                const int oi = __shfl_xor_sync(full, bi, off);
-                if (oi >= 0 && (bi < 0 || ob > bestf || (ob == bestf && oi < bi))) { bestf = ob; bi = oi; }
-            }
-            m_out = static_cast<T>(mx); ls_out = static_cast<double>(lsf); amax_out = bi; nsel_out = nsel;
-            return;
-        }
-    }
     if (!is_prob) {
         bool have = false;
         for (int v = lane; v < V; v += 32) {
