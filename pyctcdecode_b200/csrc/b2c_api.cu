@@ -1293,6 +1293,14 @@ static int decode_batch_locked(b2c_decoder_t* d, const void* const* logits, cons
                           !streaming && n_lm == 1 && opts->beam_width <= 128 && hint_ok && !d->pipe_refused;
     for (int i = 0; i < n_utts && pipe_candidate; ++i)
         pipe_candidate = T[i] == T_max && static_cast<const char*>(logits[i]) == static_cast<const char*>(logits[0]) + static_cast<u64>(i) * T_max * V * esz_in;
+    // Only COPY-BOUND calls are pipelined.  A chunked launch ends when its slowest utterance has finished the chunk, so
+    // every chunk boundary costs the spread of the per-chunk times: measured on B200, the C2 call (copy 0.6 ms, decode
+    // 3.9 ms) gains nothing from two chunks (4.6 vs 4.9 ms of device time, lost again in the wall clock) and the diffuse
+    // regime loses 30 %, while the C4 shape (copy 20 ms, decode 7 ms) goes from 25.7 to 20.8 ms.
+    if (pipe_candidate) {
+        const double copy_ms = static_cast<double>(total_frames) * V * esz / 50.0e6;             // ~50 GB/s pinned H2D
+        pipe_candidate = std::getenv("B200CTC_PIPELINE_ALL") != nullptr || (d->last_device_ms > 0 && copy_ms >= 0.6 * d->last_device_ms);
+    }
     if (!hint_ok) d->pipe_refused = false;                       // another configuration: a new attempt may be planned
     if (pipe_candidate && d->d_logits.ensure(std::max<u64>(total_frames * V * esz, 16))) return B2C_E_NOMEM;
     const int chunk_len = ((T_max + B2C_PIPE_CHUNKS * B2C_TILE_ROWS - 1) / (B2C_PIPE_CHUNKS * B2C_TILE_ROWS)) * B2C_TILE_ROWS;
@@ -1644,7 +1652,7 @@ static int decode_batch_locked(b2c_decoder_t* d, const void* const* logits, cons
         const double r = copy_ms / std::max(comp_ms, 1e-3);
         bounds.clear();
         bounds.push_back(0);
-        if (r < 0.6) {
+        if (r < 0.6) {          // (not reached since compute-bound calls are not pipelined; kept for B200CTC_PIPELINE_ALL)
             int f = static_cast<int>(1.15 * T_max * r / (1.0 + r));
             f = std::max(2 * B2C_TILE_ROWS, ((f + B2C_TILE_ROWS - 1) / B2C_TILE_ROWS) * B2C_TILE_ROWS);
             if (f < T_max) bounds.push_back(f);

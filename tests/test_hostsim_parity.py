@@ -512,6 +512,7 @@ def test_hostsim_chunked_launches_give_the_same_results(chunks):
 @pytest.mark.parametrize("fam,dtype", [("B_3gram", np.float32), ("C_bpe_4gram", np.float32), ("B_nolm", np.float64)])
 def test_hostsim_pipelined_host_batches(sim, fam, dtype, monkeypatch):
     monkeypatch.setenv("B200CTC_PIPELINE", "1")
+    monkeypatch.setenv("B200CTC_PIPELINE_ALL", "1")        # also compute-bound calls (by default only copy-bound ones)
     """The pipelined call (one [B, T, V] host block, second call of a configuration onwards): chunks along T are
     copied / prepared / decoded in turn.  Same transcripts and beams as the plain call; probability input -- found
     out only after the last chunk -- makes the call redo itself as a plain call."""
