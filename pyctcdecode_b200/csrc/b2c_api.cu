@@ -161,6 +161,11 @@ struct B2cBeamArgs {
     int chunk_t0, chunk_t1, chunk_last, pad_chunk;
     u8* state;
     u64 state_stride;
+    // gated launch (gate != nullptr): ONE launch whose CTAs wait, at the boundaries gate_bounds[1..gate_n-1], for the
+    // flag gate[c] that the host sets (stream-ordered) once the streaming stage has written chunk c's token lists
+    const u32* gate;
+    int gate_n;
+    int gate_bounds[5];
     u64* phase_clk;            // [16] profiling builds only (-DB2C_PHASE_CLOCKS)
     u32* m_stats;              // [8] frames over 128..4096 candidates, total frames (adaptive sizing), in-place frames, sorted (no-merge) frames
 };
@@ -548,9 +553,12 @@ struct b2c_decoder {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t copied[B2C_PIPE_CHUNKS] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t chunk_ev[3 * B2C_PIPE_CHUNKS] = {};
-    DevBuf d_state;
+    DevBuf d_state, d_gate;
+    cudaStream_t prep_stream = nullptr;   // gated pipelined calls: streaming stage of the later chunks, concurrent with the beam kernel
+    cudaEvent_t prep_ev[3] = {nullptr, nullptr, nullptr};    // inputs ready / first chunk streamed / all streamed and decided
     bool pipe_refused = false;            // the last pipelined attempt of this configuration could not be planned
     double last_device_ms = 0.0;          // streaming stage + beam kernel of the previous call (chunk sizing of pipelined calls)
+    int plain_v5 = -2, plain_cap = 0;     // kernel variant / capacity class of the last PLAIN call (pipelined calls must plan the same)
     std::mutex call_mu;                   // b2c_decode_batch is serialised per handle (scratch buffers are per handle)
     b2c_timings_t tm;
     // adaptive sizing: candidate-count histogram of the previous call with the same configuration
@@ -980,6 +988,8 @@ int b2c_decoder_create(const char* const* labels, int n_labels, int is_bpe, b2c_
     CUDA_OK(cudaEventCreate(&d->fork_ev));
     CUDA_OK(cudaEventCreateWithFlags(&d->caller_ev, cudaEventDisableTiming));
     CUDA_OK(cudaStreamCreate(&d->copy_stream));
+    CUDA_OK(cudaStreamCreate(&d->prep_stream));
+    for (int i = 0; i < 3; ++i) CUDA_OK(cudaEventCreateWithFlags(&d->prep_ev[i], cudaEventDisableTiming));
     for (int i = 0; i < B2C_PIPE_CHUNKS; ++i) CUDA_OK(cudaEventCreateWithFlags(&d->copied[i], cudaEventDisableTiming));
     for (int i = 0; i < 3 * B2C_PIPE_CHUNKS; ++i) CUDA_OK(cudaEventCreate(&d->chunk_ev[i]));
     int v = 0;
@@ -1036,6 +1046,9 @@ void b2c_decoder_destroy(b2c_decoder_t* d) {
     if (d->fork_ev) cudaEventDestroy(d->fork_ev);
     if (d->caller_ev) cudaEventDestroy(d->caller_ev);
     if (d->copy_stream) cudaStreamDestroy(d->copy_stream);
+    if (d->prep_stream) cudaStreamDestroy(d->prep_stream);
+    for (int i = 0; i < 3; ++i) if (d->prep_ev[i]) cudaEventDestroy(d->prep_ev[i]);
+    d->d_gate.release();
     for (int i = 0; i < B2C_PIPE_CHUNKS; ++i) if (d->copied[i]) cudaEventDestroy(d->copied[i]);
     for (int i = 0; i < 3 * B2C_PIPE_CHUNKS; ++i) if (d->chunk_ev[i]) cudaEventDestroy(d->chunk_ev[i]);
     d->d_state.release();
@@ -1293,14 +1306,6 @@ static int decode_batch_locked(b2c_decoder_t* d, const void* const* logits, cons
                           !streaming && n_lm == 1 && opts->beam_width <= 128 && hint_ok && !d->pipe_refused;
     for (int i = 0; i < n_utts && pipe_candidate; ++i)
         pipe_candidate = T[i] == T_max && static_cast<const char*>(logits[i]) == static_cast<const char*>(logits[0]) + static_cast<u64>(i) * T_max * V * esz_in;
-    // Only COPY-BOUND calls are pipelined.  A chunked launch ends when its slowest utterance has finished the chunk, so
-    // every chunk boundary costs the spread of the per-chunk times: measured on B200, the C2 call (copy 0.6 ms, decode
-    // 3.9 ms) gains nothing from two chunks (4.6 vs 4.9 ms of device time, lost again in the wall clock) and the diffuse
-    // regime loses 30 %, while the C4 shape (copy 20 ms, decode 7 ms) goes from 25.7 to 20.8 ms.
-    if (pipe_candidate) {
-        const double copy_ms = static_cast<double>(total_frames) * V * esz / 50.0e6;             // ~50 GB/s pinned H2D
-        pipe_candidate = std::getenv("B200CTC_PIPELINE_ALL") != nullptr || (d->last_device_ms > 0 && copy_ms >= 0.6 * d->last_device_ms);
-    }
     if (!hint_ok) d->pipe_refused = false;                       // another configuration: a new attempt may be planned
     if (pipe_candidate && d->d_logits.ensure(std::max<u64>(total_frames * V * esz, 16))) return B2C_E_NOMEM;
     const int chunk_len = ((T_max + B2C_PIPE_CHUNKS * B2C_TILE_ROWS - 1) / (B2C_PIPE_CHUNKS * B2C_TILE_ROWS)) * B2C_TILE_ROWS;
@@ -1646,13 +1651,35 @@ static int decode_batch_locked(b2c_decoder_t* d, const void* const* logits, cons
     // 3.75).  Compute-bound calls (the copy is shorter than the decode) therefore use TWO chunks: a short first one whose
     // decode covers the copy of the rest; copy-bound calls (large alphabets) use equal chunks.
     std::vector<int> bounds{0, std::max(T_max, 0)};
+    // GATED launch (preferred for pipelined calls): ONE beam launch that starts after the first chunk and waits, on the
+    // device, for the flag of each later chunk -- no launch boundary, so no chunk pays for its slowest utterance.  The
+    // streaming stage of the later chunks runs CONCURRENTLY with the beam kernel on another stream, which needs free SM
+    // resources: only taken when the beam kernel leaves at least n_sm/8 CTA slots empty; a CTA that waits longer than
+    // ~40 ms gives up with B2C_ERR_GATE and the call is redone as a plain call.
+    // Which form of pipelining (measured on B200, profiles/pipeline_r02.txt):
+    //   compute-bound calls (copy < 0.6 x decode; C2: copy 0.6 ms, decode 3.9 ms) -> the gated launch: 5.05 -> 4.42 ms of
+    //     device time; chunked launches gain nothing there -- a chunked launch ends when its slowest utterance has finished
+    //     the chunk, so every boundary costs the spread of the per-chunk times;
+    //   copy-bound calls (C4 shape: copy 20 ms, decode 7 ms) -> chunked launches, equal chunks: 25.9 -> 20.8 ms (the gated
+    //     form is slower there, 22.8 ms: the streaming stage of a 1 GB batch crawls on the SM slots the beam kernel leaves free).
+    // The plan of a pipelined call comes from the hint alone; it must be the plan the previous plain call of this
+    // configuration ran (another kernel variant would change the speed, not the result: diffuse batches decode 35 % slower
+    // on the latency-first kernel the hint-only plan picks than on the capacity-class kernel their statistics pick).
+    const double copy_ms_est = static_cast<double>(total_frames) * V * esz / 50.0e6;            // ~50 GB/s pinned H2D
+    const double pipe_r = copy_ms_est / std::max(d->last_device_ms > 0 ? d->last_device_ms : copy_ms_est, 1e-3);
+    const bool pipe_all = std::getenv("B200CTC_PIPELINE_ALL") != nullptr;
+    const bool gated = pipe_candidate && can_chunk && std::getenv("B200CTC_NO_GATE") == nullptr && (pipe_r < 0.6 || pipe_all) &&
+                       launches[0].count + d->n_sm / 8 <= d->n_sm * launches[0].per_sm;
     if (pipe_candidate) {
-        const double copy_ms = static_cast<double>(total_frames) * V * esz / 50.0e6;             // ~50 GB/s pinned H2D
-        const double comp_ms = d->last_device_ms > 0 ? d->last_device_ms : copy_ms;            // previous call of the configuration
-        const double r = copy_ms / std::max(comp_ms, 1e-3);
+        const double r = pipe_r;
+        const bool same_plan = launches[0].v5 == d->plain_v5 && static_cast<int>(launches[0].L.cap_s) == d->plain_cap;
+        if ((!gated && r < 0.6 && !pipe_all) || (!same_plan && !pipe_all)) {
+            d->pipe_refused = true;
+            return B2C_E_RETRY_PLAIN;
+        }
         bounds.clear();
         bounds.push_back(0);
-        if (r < 0.6) {          // (not reached since compute-bound calls are not pipelined; kept for B200CTC_PIPELINE_ALL)
+        if (!gated && r < 0.6) {
             int f = static_cast<int>(1.15 * T_max * r / (1.0 + r));
             f = std::max(2 * B2C_TILE_ROWS, ((f + B2C_TILE_ROWS - 1) / B2C_TILE_ROWS) * B2C_TILE_ROWS);
             if (f < T_max) bounds.push_back(f);
@@ -1667,7 +1694,7 @@ static int decode_batch_locked(b2c_decoder_t* d, const void* const* logits, cons
         bounds.push_back(T_max);
     }
     const int n_chunks = static_cast<int>(bounds.size()) - 1;
-    bool chunk_timing = false;
+    bool chunk_timing = false, gated_call = false;
     if (n_chunks > 1) {
         const Launch& ln = launches[0];
         const u64 stride = (kV5Save[ln.v5][V <= B2C_FAST_LT ? 1 : 0] + 16 + 255) & ~255ull;
@@ -1680,6 +1707,16 @@ static int decode_batch_locked(b2c_decoder_t* d, const void* const* logits, cons
         BA.state = d->d_state.as<u8>();
         BA.state_stride = stride;
         chunk_timing = pipe_candidate && n_chunks <= B2C_PIPE_CHUNKS;
+        cudaStream_t ps = gated ? d->prep_stream : st;
+        if (gated) {
+            if (d->d_gate.ensure(64)) return B2C_E_NOMEM;
+            CUDA_OK(cudaMemsetAsync(d->d_gate.p, 0, 64, st));
+            CUDA_OK(cudaEventRecord(d->prep_ev[0], st));              // meta, memsets, hot table, LM states: uploaded
+            CUDA_OK(cudaStreamWaitEvent(ps, d->prep_ev[0], 0));
+            BA.gate = d->d_gate.as<u32>();
+            BA.gate_n = n_chunks;
+            for (int c = 0; c <= n_chunks; ++c) BA.gate_bounds[c] = bounds[c];
+        }
         if (pipe_candidate) {
             // every chunk's copy is queued at once on the copy stream; the compute stream waits chunk by chunk
             const size_t pitch = static_cast<size_t>(T_max) * V * esz;
@@ -1689,16 +1726,15 @@ static int decode_batch_locked(b2c_decoder_t* d, const void* const* logits, cons
                                           static_cast<const char*>(logits[0]) + static_cast<size_t>(t0) * V * esz, pitch,
                                           static_cast<size_t>(t1 - t0) * V * esz, static_cast<size_t>(n_utts), cudaMemcpyHostToDevice, d->copy_stream));
                 CUDA_OK(cudaEventRecord(d->copied[c % B2C_PIPE_CHUNKS], d->copy_stream));
-                if (n_chunks > B2C_PIPE_CHUNKS) CUDA_OK(cudaStreamSynchronize(d->copy_stream));   // never: n_chunks <= B2C_PIPE_CHUNKS by construction
                 d->tm.h2d_bytes += static_cast<long long>(t1 - t0) * V * static_cast<long long>(esz) * n_utts;
             }
         }
-        CUDA_OK(cudaEventRecord(d->ev[5], st));
+        if (!gated) CUDA_OK(cudaEventRecord(d->ev[5], st));
         for (int c = 0; c < n_chunks; ++c) {
             const int t0 = bounds[c], t1 = bounds[c + 1];
             if (pipe_candidate) {
-                CUDA_OK(cudaStreamWaitEvent(st, d->copied[c % B2C_PIPE_CHUNKS], 0));
-                if (chunk_timing) CUDA_OK(cudaEventRecord(d->chunk_ev[3 * c], st));
+                CUDA_OK(cudaStreamWaitEvent(ps, d->copied[c % B2C_PIPE_CHUNKS], 0));
+                if (chunk_timing) CUDA_OK(cudaEventRecord(d->chunk_ev[3 * c], ps));
                 B2cPrepArgs PC = PA;
                 PC.mode = 0;
                 PC.tile_lo = t0 / B2C_TILE_ROWS;
@@ -1719,16 +1755,37 @@ static int decode_batch_locked(b2c_decoder_t* d, const void* const* logits, cons
                 if (dtype == B2C_DTYPE_F32 && V <= 32) {
                     const u64 items = static_cast<u64>(n_utts) * static_cast<u64>(PC.tile_hi - PC.tile_lo);
                     const int grid = static_cast<int>(std::max<u64>(1, std::min<u64>((items + B2C_TILE_WARPS - 1) / B2C_TILE_WARPS, static_cast<u64>(d->n_sm) * 8)));
-                    b2c_tokens_tile_kernel<<<grid, B2C_TILE_WARPS * 32, 0, st>>>(PC);
+                    b2c_tokens_tile_kernel<<<grid, B2C_TILE_WARPS * 32, 0, ps>>>(PC);
                 } else if (dtype == B2C_DTYPE_F32) {
-                    b2c_tokens_kernel<float><<<grid_runs, B2C_PREP_THREADS, 0, st>>>(PC);
+                    b2c_tokens_kernel<float><<<grid_runs, B2C_PREP_THREADS, 0, ps>>>(PC);
                 } else {
-                    b2c_tokens_kernel<double><<<grid_runs, B2C_PREP_THREADS, 0, st>>>(PC);
+                    b2c_tokens_kernel<double><<<grid_runs, B2C_PREP_THREADS, 0, ps>>>(PC);
                 }
                 CUDA_OK(cudaGetLastError());
 #endif
                 d->tm.launches += 1;
-                if (chunk_timing) CUDA_OK(cudaEventRecord(d->chunk_ev[3 * c + 1], st));
+                if (chunk_timing) CUDA_OK(cudaEventRecord(d->chunk_ev[3 * c + 1], ps));
+            }
+            if (gated) {
+                CUDA_OK(cudaMemsetAsync(d->d_gate.as<u32>() + c, 1, 4, ps));       // chunk c's token lists are in HBM
+#ifdef B2C_HOSTSIM
+                // hostsim runs a launch to completion at once: after the last chunk -- or, to test the give-up path
+                // (the later chunks "never arrive"), right after the first one
+                if (c == (std::getenv("B200CTC_HOSTSIM_GATE_EARLY") ? 0 : n_chunks - 1)) {
+#else
+                if (c == 0) {
+#endif
+                    // the beam kernel: ONE launch, behind the first chunk only
+                    CUDA_OK(cudaEventRecord(d->prep_ev[1], ps));
+                    CUDA_OK(cudaStreamWaitEvent(st, d->prep_ev[1], 0));
+                    CUDA_OK(cudaEventRecord(d->ev[5], st));
+                    BA.chunk_t0 = 0;
+                    BA.chunk_t1 = 0;
+                    rc = launch_beam(d, BA, ln.slots, true, ln.per_sm, ln.threads, st, ln.v5);
+                    if (rc) return rc;
+                    d->tm.launches += 1;
+                }
+                continue;
             }
             BA.chunk_t0 = t0;
             BA.chunk_t1 = t1;
@@ -1739,6 +1796,7 @@ static int decode_batch_locked(b2c_decoder_t* d, const void* const* logits, cons
             if (chunk_timing) CUDA_OK(cudaEventRecord(d->chunk_ev[3 * c + 2], st));
         }
         BA.chunk_t1 = 0;
+        BA.gate = nullptr;
         if (pipe_candidate) {
             // probabilities or logits: decided now that every row has been seen; a probability utterance voids the call
 #ifdef B2C_HOSTSIM
@@ -1750,13 +1808,18 @@ static int decode_batch_locked(b2c_decoder_t* d, const void* const* logits, cons
                 }
             }
 #else
-            if (dtype == B2C_DTYPE_F32) b2c_decide_kernel<float><<<n_utts, 128, 0, st>>>(PA);
-            else b2c_decide_kernel<double><<<n_utts, 128, 0, st>>>(PA);
+            if (dtype == B2C_DTYPE_F32) b2c_decide_kernel<float><<<n_utts, 128, 0, ps>>>(PA);
+            else b2c_decide_kernel<double><<<n_utts, 128, 0, ps>>>(PA);
             CUDA_OK(cudaGetLastError());
 #endif
             d->tm.launches += 1;
+            if (gated) {
+                CUDA_OK(cudaEventRecord(d->prep_ev[2], ps));
+                CUDA_OK(cudaStreamWaitEvent(st, d->prep_ev[2], 0));
+            }
             CUDA_OK(cudaMemcpyAsync(d->h_maxk.p, d->d_approx.as<double>() + 2 * n_utts, 4, cudaMemcpyDeviceToHost, st));
         }
+        gated_call = gated;
         d->tm.cap_candidates = static_cast<int>(ln.L.cap_s);
         d->tm.cta_threads = ln.threads;
         d->tm.cta_slots = ln.slots;
@@ -1783,6 +1846,7 @@ static int decode_batch_locked(b2c_decoder_t* d, const void* const* logits, cons
             d->tm.cta_threads = ln.threads;
             d->tm.cta_slots = ln.slots;
             d->tm.kernel_variant = ln.v5 >= 0 ? 2 : (ln.cls < kNumCaps ? 1 : 0);
+            if (!pipe_candidate && launches.size() == 1) { d->plain_v5 = ln.v5; d->plain_cap = static_cast<int>(ln.L.cap_s); }
         }
         if (cs != st) {
             CUDA_OK(cudaEventRecord(d->cls_done[ln.cls < kNumCaps ? 0 : 1], cs));
@@ -1801,6 +1865,14 @@ static int decode_batch_locked(b2c_decoder_t* d, const void* const* logits, cons
     CUDA_OK(cudaStreamSynchronize(st));
     hp_mark(3);                                   // wait: beam kernel + D2H
     if (pipe_candidate && d->h_maxk.as<u32>()[0] != 0) return B2C_E_RETRY_PLAIN;   // some utterance holds probabilities
+    if (gated_call) {
+        const int* hst = reinterpret_cast<const int*>(d->h_out_small.as<u8>() + off_st);
+        for (int i = 0; i < n_utts; ++i)
+            if (hst[i] & B2C_ERR_GATE) {           // the streaming stage of a later chunk never got to run beside the beam kernel
+                d->pipe_refused = true;
+                return B2C_E_RETRY_PLAIN;
+            }
+    }
     d->tm.d2h_bytes += static_cast<long long>(small_bytes + tok_bytes + (text_only ? 0 : frm_bytes) + 8ull * n_utts + 32);
     {
         u32 ms[16];
@@ -1880,8 +1952,9 @@ static int decode_batch_locked(b2c_decoder_t* d, const void* const* logits, cons
         float mp = 0.f, mb = 0.f;
         for (int c = 0; c < n_chunks; ++c) {
             if (cudaEventElapsedTime(&ms, d->chunk_ev[3 * c], d->chunk_ev[3 * c + 1]) == cudaSuccess) mp += ms;
-            if (cudaEventElapsedTime(&ms, d->chunk_ev[3 * c + 1], d->chunk_ev[3 * c + 2]) == cudaSuccess) mb += ms;
+            if (!gated_call && cudaEventElapsedTime(&ms, d->chunk_ev[3 * c + 1], d->chunk_ev[3 * c + 2]) == cudaSuccess) mb += ms;
         }
+        if (gated_call && cudaEventElapsedTime(&ms, d->ev[5], d->ev[3]) == cudaSuccess) mb = ms;     // one launch, waits included
         d->tm.ms_prepare = mp;
         d->tm.ms_beam = mb;
         if (host_prof) {
@@ -1890,7 +1963,7 @@ static int decode_batch_locked(b2c_decoder_t* d, const void* const* logits, cons
                 float a0 = 0.f, a1 = 0.f, a2 = 0.f;
                 cudaEventElapsedTime(&a0, d->ev[0], d->chunk_ev[3 * c]);
                 cudaEventElapsedTime(&a1, d->ev[0], d->chunk_ev[3 * c + 1]);
-                cudaEventElapsedTime(&a2, d->ev[0], d->chunk_ev[3 * c + 2]);
+                if (!gated_call) cudaEventElapsedTime(&a2, d->ev[0], d->chunk_ev[3 * c + 2]);
                 std::fprintf(stderr, "  chunk %d: copied %.3f streamed %.3f decoded %.3f", c, a0, a1, a2);
             }
             float a4 = 0.f;

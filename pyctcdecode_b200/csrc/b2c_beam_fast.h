@@ -1135,7 +1135,11 @@ B2C_HD void b2c_beam_block_fast(const B2cBeamArgs& A, int slot_cta, u8* smem) {
         const u64 f0 = A.frame_off[u];
         const B2cFrameRec* recs = A.tok_rec + f0;
         const int ts = chunked ? A.chunk_t0 : 0;                                     // first frame of this launch
-        const int te = (chunked && !A.chunk_last && A.chunk_t1 < Tn) ? A.chunk_t1 : Tn;   // one past its last frame
+        int te = (chunked && !A.chunk_last && A.chunk_t1 < Tn) ? A.chunk_t1 : Tn;   // one past its last frame
+        // gated launch: frames up to the first boundary are ready when the kernel starts; the later chunks are waited for
+        const bool gated = !chunked && A.gate != nullptr && A.gate_n > 1;
+        int gate_c = 0;
+        if (gated && A.gate_bounds[1] < Tn) te = A.gate_bounds[1];
         const bool resume = chunked && ts > 0;
         if (resume && Tn <= ts) continue;                        // finished (and finalised) in an earlier launch
         // ---- fill the rings: records of the first frames, then the token lists of the first frames ----------------
@@ -1348,12 +1352,55 @@ B2C_HD void b2c_beam_block_fast(const B2cBeamArgs& A, int slot_cta, u8* smem) {
             if (!in_place) par ^= 1;
             sb ^= 1;
             t = tn;
+            if (gated && t >= te && te < Tn) {
+                // ---- the next chunk of frames: wait until the streaming stage has written its token lists ------------
+                B2C_LEADER {
+#if defined(__CUDA_ARCH__)
+                    const volatile u32* flag = A.gate + gate_c + 1;
+                    const long long c0 = clock64();
+                    while (*flag == 0u) {
+                        __nanosleep(200);
+                        if (clock64() - c0 > 80000000ll) { S.sc.status |= B2C_ERR_GATE; break; }      // ~40 ms: give up
+                    }
+                    __threadfence();
+#else
+                    if (A.gate[gate_c + 1] == 0u) S.sc.status |= B2C_ERR_GATE;
+#endif
+                }
+                B2C_SYNC();
+                if (S.sc.status & B2C_ERR_GATE) break;           // block-uniform
+                ++gate_c;
+                te = (gate_c + 1 < A.gate_n && A.gate_bounds[gate_c + 1] < Tn) ? A.gate_bounds[gate_c + 1] : Tn;
+                // refill the rings from frame t
+                hv = te - t < B2C_FAST_HR ? te : t + B2C_FAST_HR;
+                B2C_FOR(c, hv - t) { b2c_cp_async16(&S.rh[(t + c) & HM], recs + t + c); }
+                b2c_cp_async_wait_all();
+                B2C_SYNC();
+                tv = te - t < B2C_FAST_TR ? te : t + B2C_FAST_TR;
+                for (int f = t; f < tv; ++f) {
+                    const B2cFrameRec hf = S.rh[f & HM];
+                    const u64 base = (f0 + static_cast<u64>(f & ~(B2C_RUN - 1))) * static_cast<u64>(V) + hf.off;
+                    const u32 kf = hf.cnt < static_cast<u32>(KR) ? hf.cnt : static_cast<u32>(KR);
+                    B2C_FOR(c, kf) {
+                        b2c_cp_async4(&S.rid[f & TM][c], A.tok_ids + base + c);
+                        b2c_cp_async8(&S.rlp[f & TM][c], A.tok_lp + base + c);
+                    }
+                }
+                b2c_cp_async_wait_all();
+                B2C_SYNC();
+                if (LT == 0) {
+                    const u32 c0n = S.rh[t & HM].cnt;
+                    const u32 k0 = c0n < static_cast<u32>(KR) ? c0n : static_cast<u32>(KR);
+                    B2C_FOR(c, k0) { S.stok[sb][c] = A.P.toks[S.rid[t & TM][c]]; }
+                    B2C_SYNC();
+                }
+            }
         }
         B2C_LAST_THREAD {
             ++st_utts;
             st_wide_utts += wide_utt ? 1u : 0u;
         }
-        if (te < Tn) {      // more frames in a later launch: park the state
+        if (chunked && te < Tn) {      // more frames in a later launch: park the state
             const u32* const sw = reinterpret_cast<const u32*>(smem);
             B2C_FOR(i, SAVE_WORDS) { parked[i] = sw[i]; }
             B2C_LEADER {

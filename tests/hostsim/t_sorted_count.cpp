@@ -11,7 +11,7 @@ struct B2cBeamArgs {
     B2cParams P; B2cLayout L; int n_utts; const int* order; u32* next; const u64* frame_off; const int* T; const B2cFrameRec* tok_rec;
     const u32* tok_ids; const double* tok_lp; u8* gws; const B2cLmState* start_states; int* out_nbeams; int* out_status; double* out_scores;
     int* out_ntok; int* out_nwords; u32* out_toks; int* out_frames; B2cLmState* out_states; int chunk_t0, chunk_t1, chunk_last, pad_chunk;
-    u8* state; u64 state_stride; u64* phase_clk; u32* m_stats;
+    u8* state; u64 state_stride; const u32* gate; int gate_n; int gate_bounds[5]; u64* phase_clk; u32* m_stats;
 };
 #include "b2c_beam_fast.h"
 int main() {

@@ -552,3 +552,20 @@ def test_hostsim_lean_variant_with_hand_back():
     r = subprocess.run([sys.executable, "-m", "pytest", here, "-x", "-q", "-k", "golden or special or random or ragged or text_only or scored"],
                        env=env, cwd=os.path.dirname(os.path.dirname(here)), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0, r.stdout[-3000:]
+
+
+def test_hostsim_gated_launch_gives_up_cleanly(sim, monkeypatch):
+    """A gated launch whose later chunks never become ready (here: hostsim launches the beam kernel right after the
+    first chunk) must give up with B2C_ERR_GATE -- no hang, no garbage -- and the call is redone as a plain call."""
+    monkeypatch.setenv("B200CTC_PIPELINE", "1")
+    monkeypatch.setenv("B200CTC_PIPELINE_ALL", "1")
+    monkeypatch.setenv("B200CTC_HOSTSIM_GATE_EARLY", "1")
+    wkw, lmkw = FAMILIES["B_3gram"]
+    wl = synth.make_workload(wkw)
+    kw = dict(lmkw, kenlm_model_path=wl.arpa, unigrams=wl.words)
+    dec = sim.build_ctcdecoder(wl.labels, **kw)
+    ora = orc.OracleDecoder(wl.labels, **kw)
+    xs = np.stack([wl.utterance(9300 + i, 300, "peaky") for i in range(4)])
+    want = ora.decode_batch(list(xs), beam_width=24)
+    for _ in range(3):
+        assert dec.decode_batch(None, xs, beam_width=24) == want
