@@ -420,6 +420,60 @@ def secondary_entry(torch, pkg, flush, name, spec, regime, beam, logits_dtype, c
     return ent
 
 
+def _stream_run(dec, xs, chunk, beam):
+    """get_starting_state / partial_decode_beams(_batch) over `xs` in chunks of `chunk` frames (reference decoder.py:669-728,
+    the streaming form of the same frame loop) -> (seconds per call, final top-1 texts)"""
+    n, T = len(xs), len(xs[0])
+    starts = [dec.get_starting_state() for _ in range(n)]
+    beams, caches, pcaches = [s[0] for s in starts], [s[1] for s in starts], [s[2] for s in starts]
+    lat = []
+    for t0 in range(0, T, chunk):
+        t1 = min(T, t0 + chunk)
+        t = time.perf_counter()
+        if n == 1 or not hasattr(dec, "partial_decode_beams_batch"):
+            beams = [dec.partial_decode_beams(xs[i][t0:t1], caches[i], pcaches[i], beams[i], t0, beam_width=beam, is_end=t1 >= T)
+                     for i in range(n)]
+        else:
+            beams = dec.partial_decode_beams_batch([x[t0:t1] for x in xs], caches, beams, [t0] * n, beam_width=beam, is_end=t1 >= T)
+        lat.append(time.perf_counter() - t)
+    return lat, [b[0].text if b else "" for b in beams]
+
+
+def streaming_entry(torch, pkg, name, spec, n_streams, chunk=50, beam=100):
+    """Per-call latency of the streaming form of the path: `n_streams` independent streams advance by `chunk` frames per
+    call (host logits, beams carried as LMBeam lists exactly like in the reference).  The final transcripts must equal the
+    one-shot decode_batch of the same logits.  CPU figure: the unmodified Python reference's own partial_decode_beams on
+    one stream (workloads without a language model, when baseline/_ref is present)."""
+    t_start = time.perf_counter()
+    wl, kw, _ = workload_objects(spec)
+    T = spec["T"]
+    dec = pkg.build_ctcdecoder(wl.labels, device=torch.cuda.current_device(), **kw)
+    xs = wl.batch(1, n_streams, T, "peaky")
+    one_shot = dec.decode_batch(None, xs, beam_width=beam)
+    _stream_run(dec, xs, chunk, beam)                                    # warm-up pass
+    lat, texts = _stream_run(dec, xs, chunk, beam)
+    ent = {"name": name, "call": "partial_decode_beams" + ("_batch" if n_streams > 1 else ""), "streams": n_streams,
+           "chunk_frames": chunk, "beam": beam, "config": config_of(spec, "peaky", beam, n_streams, wl.V, "f32", 1),
+           "ms_per_call": {"median": 1e3 * statistics.median(lat), "first": 1e3 * lat[0], "last": 1e3 * lat[-1], "max": 1e3 * max(lat)},
+           "value": n_streams * T / sum(lat), "unit": "frames/s", "calls": len(lat),
+           "final_text_equals_one_shot": "%d/%d" % (sum(a == b for a, b in zip(texts, one_shot)), n_streams),
+           "cpu_baseline": None}
+    if pyref_available(spec):
+        try:
+            ref = PyRef(wl.labels, 1)
+            rlat, rtexts = _stream_run(ref.dec, xs[:1], chunk, beam)
+            ref.close()
+            ent["cpu_baseline"] = {"kind": "reference", "cores": 1, "streams": 1, "ms_per_call_median": 1e3 * statistics.median(rlat),
+                                   "value": T / sum(rlat), "unit": "frames/s",
+                                   "final_text_equals_b200": bool(rtexts[0] == texts[0]),
+                                   "sample": "the unmodified Python reference's partial_decode_beams, one stream, same chunks"}
+        except Exception as exc:
+            ent["cpu_baseline"] = {"kind": "reference", "value": None, "sample": "failed: %r" % (exc,)}
+    del dec
+    ent["wall_s"] = round(time.perf_counter() - t_start, 1)
+    return ent
+
+
 def strong_scaling(torch, dist, pkg, sharding, flush, rank, world, local_rank, steps, n_utts=2048):
     """The north_star multi-GPU path: every rank holds the SAME list of utterances (C3: 3-gram LM), the decoder is
     built with ONE NCCL broadcast of the flattened LM, decode_batch_sharded splits the list over the ranks (no
@@ -521,7 +575,7 @@ def main():
     ap.add_argument("--beam", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary configurations (1 GPU) / the strong-scaling section (N > 1)")
-    ap.add_argument("--secondary", default="", help="comma separated subset of: c3,c4,c4_f16,diffuse,beam10,beam50,beam500,beam2000,beams_batch")
+    ap.add_argument("--secondary", default="", help="comma separated subset of: c3,c4,c4_f16,diffuse,beam10,beam50,beam500,beam2000,beams_batch,stream1,stream64,stream64_lm")
     ap.add_argument("--secondary-steps", type=int, default=5)
     ap.add_argument("--call", default="decode_batch", choices=["decode_batch", "decode_beams_batch"])
     ap.add_argument("--logits-dtype", default="f32", choices=["f32", "f16"],
@@ -694,6 +748,13 @@ def main():
             try:
                 out["secondary"].append(secondary_entry(torch, pkg, flush, name, dict(sp), regime, bm, dt, call, S, W, bsz))
             except Exception as exc:  # one configuration must not take the headline down with it
+                out["secondary"].append({"name": name, "error": repr(exc)})
+        for name, sp, n_streams in (("stream1", WORKLOADS["c2"], 1), ("stream64", WORKLOADS["c2"], 64), ("stream64_lm", WORKLOADS["c3"], 64)):
+            if want and name not in want:
+                continue
+            try:
+                out["secondary"].append(streaming_entry(torch, pkg, name, dict(sp), n_streams))
+            except Exception as exc:
                 out["secondary"].append({"name": name, "error": repr(exc)})
     _emit(out)
     if dist is not None:

@@ -176,6 +176,23 @@ const int32_t* b2c_result_frames(const b2c_result_t* res, int utt, int beam);
 /* LM state after the last word (OutputBeam.last_lm_state); returns 0 when there is no LM */
 int b2c_result_lm_state(const b2c_result_t* res, int utt, int beam, b2c_lm_state_t* out);
 int b2c_result_lm_state_at(const b2c_result_t* res, int utt, int beam, int lm_index, b2c_lm_state_t* out);
+/* Every beam of every utterance in flat arrays (one call instead of ~6 per beam; what decode_beams_batch needs to
+ * build its OutputBeam lists, decoder.py:653-667).  Beams are numbered utterance by utterance in rank order.  All
+ * pointers live as long as the result. */
+typedef struct {
+    int32_t n_utts;
+    int32_t n_models;             /* LM states per beam (0: no language model, states == NULL) */
+    int64_t n_beams_total;
+    int64_t n_words_total;
+    const int32_t* n_beams;       /* [n_utts] */
+    const double* scores;         /* [n_beams_total][2]: logit_score, lm_score */
+    const int32_t* n_words;       /* [n_beams_total] */
+    const int32_t* frames;        /* [n_words_total][2]: (start_frame, end_frame) per word, beam after beam */
+    const char* texts;            /* utf-8, every beam's text followed by a NUL byte */
+    size_t texts_size;
+    const b2c_lm_state_t* states; /* [n_beams_total][n_models] */
+} b2c_packed_t;
+int b2c_result_packed(b2c_result_t* res, b2c_packed_t* out);
 /* streaming calls (opts->stream_states != NULL): what the call appended to an input beam instead of assembled
  * strings.  aux = {input beam index (-1: none), token id of last_char (-1: None), partial_frames start, end};
  * toks = the emitted tokens since the input beam, oldest first, token | kind << 16 with kind B2C_KIND_CONT = appended

@@ -50,6 +50,13 @@ class DecodeOpts(C.Structure):
     ]
 
 
+class Packed(C.Structure):
+    _fields_ = [("n_utts", C.c_int32), ("n_models", C.c_int32), ("n_beams_total", C.c_int64), ("n_words_total", C.c_int64),
+                ("n_beams", C.POINTER(C.c_int32)), ("scores", C.POINTER(C.c_double)), ("n_words", C.POINTER(C.c_int32)),
+                ("frames", C.POINTER(C.c_int32)), ("texts", C.c_void_p), ("texts_size", C.c_size_t),
+                ("states", C.POINTER(LMState))]
+
+
 class Timings(C.Structure):
     _fields_ = [
         ("ms_prepare", C.c_float),
@@ -119,6 +126,7 @@ def _declare(L):
     L.b2c_result_n_words.argtypes = [vp, i32, i32]
     L.b2c_result_word.argtypes = [vp, i32, i32, i32]
     L.b2c_result_word.restype = cp
+    L.b2c_result_packed.argtypes = [vp, C.POINTER(Packed)]
     L.b2c_result_frames.argtypes = [vp, i32, i32]
     L.b2c_result_frames.restype = C.POINTER(C.c_int32)
     L.b2c_result_lm_state.argtypes = [vp, i32, i32, C.POINTER(LMState)]

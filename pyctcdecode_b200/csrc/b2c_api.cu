@@ -585,6 +585,13 @@ struct b2c_result {
     bool has_lm = false;
     std::string joined;        // b2c_result_top_texts: top-1 texts, each followed by '\0'
     bool joined_built = false;
+    // b2c_result_packed
+    bool packed_built = false;
+    int n_models = 1;
+    std::vector<int32_t> pk_nb, pk_nw, pk_frames;
+    std::vector<double> pk_scores;
+    std::vector<b2c_lm_state_t> pk_states;
+    std::string pk_texts;
 };
 
 // hotword table (language_model.py:152-189): every code-point prefix of every hotword unigram
@@ -1236,6 +1243,7 @@ static int decode_batch_locked(b2c_decoder_t* d, const void* const* logits, cons
         P.lmx = d->d_lmx.as<B2cLmExtra>();
     }
     const int n_lm = std::max(1, P.n_lm);
+    res->n_models = n_lm;
     P.hist_n = std::max(1, max_order - 1);
     std::vector<B2cHot> hot;
     build_hot(opts, hot, P.n_hot, P.hot_min_len_all);
@@ -2067,6 +2075,50 @@ int b2c_result_top_texts(b2c_result_t* r, const char** data, size_t* size) {
     }
     *data = r->joined.data();
     *size = r->joined.size();
+    return 0;
+}
+int b2c_result_packed(b2c_result_t* r, b2c_packed_t* out) {
+    if (!r || !out) return fail(B2C_E_ARG, "null argument");
+    if (!r->packed_built) {
+        size_t nb = 0, nw = 0, nt = 0;
+        for (const auto& u : r->utts)
+            for (const auto& b : u) { ++nb; nw += b.frames.size() / 2; nt += b.text.size() + 1; }
+        const int nm = r->has_lm ? std::max(1, r->n_models) : 0;
+        r->pk_nb.reserve(r->utts.size());
+        r->pk_nw.reserve(nb);
+        r->pk_scores.reserve(2 * nb);
+        r->pk_frames.reserve(2 * nw);
+        r->pk_texts.reserve(nt);
+        r->pk_states.reserve(nb * static_cast<size_t>(nm));
+        for (const auto& u : r->utts) {
+            r->pk_nb.push_back(static_cast<int32_t>(u.size()));
+            for (const auto& b : u) {
+                r->pk_nw.push_back(static_cast<int32_t>(b.frames.size() / 2));
+                r->pk_scores.push_back(b.logit);
+                r->pk_scores.push_back(b.lm);
+                r->pk_frames.insert(r->pk_frames.end(), b.frames.begin(), b.frames.end());
+                r->pk_texts += b.text;
+                r->pk_texts.push_back('\0');
+                for (int j = 0; j < nm; ++j) {
+                    b2c_lm_state_t st;
+                    from_internal(j == 0 ? b.st : b.stx[static_cast<size_t>(j) - 1], &st);
+                    r->pk_states.push_back(st);
+                }
+            }
+        }
+        r->packed_built = true;
+    }
+    out->n_utts = static_cast<int32_t>(r->utts.size());
+    out->n_models = r->has_lm ? std::max(1, r->n_models) : 0;
+    out->n_beams_total = static_cast<int64_t>(r->pk_nw.size());
+    out->n_words_total = static_cast<int64_t>(r->pk_frames.size() / 2);
+    out->n_beams = r->pk_nb.data();
+    out->scores = r->pk_scores.data();
+    out->n_words = r->pk_nw.data();
+    out->frames = r->pk_frames.data();
+    out->texts = r->pk_texts.data();
+    out->texts_size = r->pk_texts.size();
+    out->states = r->pk_states.empty() ? nullptr : r->pk_states.data();
     return 0;
 }
 double b2c_result_logit_score(const b2c_result_t* r, int u, int b) { return r->utts[u][b].logit; }

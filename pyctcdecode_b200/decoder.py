@@ -390,32 +390,54 @@ class BeamSearchDecoderCTC:
                 return C.string_at(data, size.value).decode("utf-8").split("\x00")[:n]
             if stream is not None:
                 return [self._stream_results(res, u, stream[u][0], finalize_mode) for u in range(n)]
-            out: List[List[OutputBeam]] = []
-            st = _lib.LMState()
-            for u in range(n):
-                beams = []
-                for b in range(L.b2c_result_n_beams(res, u)):
-                    nw = L.b2c_result_n_words(res, u, b)
-                    text = L.b2c_result_text(res, u, b).decode("utf-8")
-                    if nw:
-                        # words = the text's words (labels never contain a space inside a word), frames in one array
-                        fr = np.ctypeslib.as_array(L.b2c_result_frames(res, u, b), shape=(2 * nw,)).tolist()
-                        frames = list(zip(text.split(" "), zip(fr[0::2], fr[1::2])))
-                    else:
-                        frames = []
-                    state = None
-                    if with_state and L.b2c_result_lm_state(res, u, b, C.byref(st)):
-                        state = B200LMState._from_c(st)
-                        if n_lm > 1:
-                            parts = [state]
-                            for j in range(1, n_lm):
-                                L.b2c_result_lm_state_at(res, u, b, j, C.byref(st))
-                                parts.append(B200LMState._from_c(st))
-                            state = MultiLanguageModelState(parts)
-                    beams.append(OutputBeam(text, state, frames, L.b2c_result_logit_score(res, u, b), L.b2c_result_lm_score(res, u, b)))
-                out.append(beams)
+            out = self._output_beams(L, res, with_state, n_lm)
         finally:
             L.b2c_result_free(res)
+        return out
+
+    _STATE_DTYPE = np.dtype([("w", "<u4", (5,)), ("b", "<f4", (5,)), ("n", "<u4")])
+
+    @classmethod
+    def _output_beams(cls, L: Any, res: Any, with_state: bool, n_lm: int) -> List[List[OutputBeam]]:
+        """OutputBeam lists (reference decoder.py:653-667) from the flat arrays of b2c_result_packed: one library call
+        per decode call, list slicing and C-level zip per beam."""
+        pk = _lib.Packed()
+        _lib.check(L.b2c_result_packed(res, C.byref(pk)))
+        nb_total, nw_total = int(pk.n_beams_total), int(pk.n_words_total)
+        counts = np.ctypeslib.as_array(pk.n_beams, shape=(pk.n_utts,)).tolist() if pk.n_utts else []
+        if nb_total == 0:
+            return [[] for _ in counts]
+        scores = np.ctypeslib.as_array(pk.scores, shape=(2 * nb_total,)).tolist()
+        n_words = np.ctypeslib.as_array(pk.n_words, shape=(nb_total,)).tolist()
+        if nw_total:
+            fr = np.ctypeslib.as_array(pk.frames, shape=(2 * nw_total,)).tolist()
+            pairs = list(zip(fr[0::2], fr[1::2]))
+        else:
+            pairs = []
+        texts = C.string_at(pk.texts, pk.texts_size).decode("utf-8").split("\x00")
+        states: List[Any] = []
+        if with_state and pk.n_models > 0 and bool(pk.states):
+            nm = int(pk.n_models)
+            raw = np.frombuffer(C.string_at(pk.states, C.sizeof(_lib.LMState) * nb_total * nm), dtype=cls._STATE_DTYPE)
+            lens, ws, bs = raw["n"].tolist(), raw["w"].tolist(), raw["b"].tolist()
+            flat = [B200LMState._from_tuples(tuple(w[:k]), tuple(b[:k])) for k, w, b in zip(lens, ws, bs)]
+            states = flat if nm == 1 else [MultiLanguageModelState(flat[i:i + nm]) for i in range(0, len(flat), nm)]
+        out: List[List[OutputBeam]] = []
+        k = wi = 0
+        for nb in counts:
+            beams = []
+            for _ in range(nb):
+                nw = n_words[k]
+                text = texts[k]
+                if nw:
+                    # words = the text's words (labels never contain a space inside a word)
+                    frames = list(zip(text.split(" "), pairs[wi:wi + nw]))
+                    wi += nw
+                else:
+                    frames = []
+                beams.append(OutputBeam(text, states[k] if states else None, frames, scores[2 * k], scores[2 * k + 1]))
+                k += 1
+            out.append(beams)
         return out
 
     def last_timings(self, device: Optional[int] = None) -> Dict[str, float]:

@@ -48,6 +48,13 @@ class B200LMState(AbstractLMState):
         n = st.length
         return cls(st.words[:n], st.backoff[:n])
 
+    @classmethod
+    def _from_tuples(cls, words: Tuple[int, ...], backoffs: Tuple[float, ...]) -> "B200LMState":
+        st = cls.__new__(cls)
+        st.words = words
+        st.backoffs = backoffs
+        return st
+
     def _to_c(self) -> _lib.LMState:
         st = _lib.LMState()
         st.length = len(self.words)
