@@ -441,8 +441,10 @@ def _stream_run(dec, xs, chunk, beam):
 
 def streaming_entry(torch, pkg, name, spec, n_streams, chunk=50, beam=100):
     """Per-call latency of the streaming form of the path: `n_streams` independent streams advance by `chunk` frames per
-    call (host logits, beams carried as LMBeam lists exactly like in the reference).  The final transcripts must equal the
-    one-shot decode_batch of the same logits.  CPU figure: the unmodified Python reference's own partial_decode_beams on
+    call (host logits, beams carried as LMBeam lists exactly like in the reference).  `final_text_equals_one_shot` is
+    informational: every chunk ends with _finalize_beams (sort, trim, prune), so the reference's own streaming result
+    differs from its one-shot decode on a few percent of the utterances too; parity of the streaming path is what the
+    22 reference-generated streaming goldens and `cpu_baseline.final_text_equals_b200` check.  CPU figure: the unmodified Python reference's own partial_decode_beams on
     one stream (workloads without a language model, when baseline/_ref is present)."""
     t_start = time.perf_counter()
     wl, kw, _ = workload_objects(spec)

@@ -54,7 +54,9 @@ static int fail(int code, const std::string& msg) {
 // =========================================================================================
 static inline u64 al16(u64 x) { return (x + 15) & ~15ull; }
 static inline u64 tab_bytes(int W) { return 6 * al16(8ull * W) + 4 * al16(4ull * W) + 2 * al16(2ull * W) + 64; }
-static inline u64 sel_bytes(int W, int n_warps) { return al16(8ull * W) + 2 * al16(4ull * W) + 2 * al16(4ull * pt_cap_for(W)) + (2 + n_warps) * al16(4ull * B2C_NBUCKET) + 64; }
+static inline u64 sel_bytes(int W, int n_warps, int nb) { return al16(8ull * W) + 2 * al16(4ull * W) + 2 * al16(4ull * pt_cap_for(W)) + 2 * al16(4ull * nb) +
+           (nb == B2C_NBUCKET ? al16(4ull * B2C_NBUCKET * n_warps) : al16(4ull * (nb + 8))) +
+           al16(sizeof(B2cTok) * B2C_STAGE_K) + al16(8ull * B2C_STAGE_K) + al16(4ull * B2C_STAGE_K) + 64; }
 static inline u64 tier_bytes(u32 cap, u32 ht) { return al16(8ull * cap) * 4 + al16(4ull * cap) * 4 + al16(4ull * ht) * 4 + 64; }
 
 static u32 pow2_ge(u32 x) {
@@ -68,14 +70,15 @@ static u32 pow2_ge(u32 x) {
 // cap_request == 0: general layout -- what fits in shared memory plus an HBM tier sized for the
 // worst case beam_width * V.
 static B2cLayout make_layout(int W, int V, int T_max, bool full_caps, u32 smem_budget, u32 cap_request, u64 worst_m = 0, int n_warps = 4,
-                             u64 extra_chain = 0, u64 extra_text = 0, int n_lm = 1) {
+                             u64 extra_chain = 0, u64 extra_text = 0, int n_lm = 1, int n_bucket = B2C_NBUCKET, u32 cap_max = 512) {
     B2cLayout L;
     std::memset(&L, 0, sizeof(L));
     L.W = W;
     L.V = V;
     L.n_warps = n_warps;
+    L.n_bucket = n_bucket;
     const u64 worst = static_cast<u64>(W) * static_cast<u64>(V);
-    u64 fixed = 128 + sel_bytes(W, n_warps);
+    u64 fixed = 128 + sel_bytes(W, n_warps, n_bucket);
     if (cap_request) {
         L.beams_in_smem = 1;
         fixed += 2 * tab_bytes(W);
@@ -88,7 +91,7 @@ static B2cLayout make_layout(int W, int V, int T_max, bool full_caps, u32 smem_b
     } else {
         L.beams_in_smem = (fixed + 2 * tab_bytes(W) + tier_bytes(256, 512) <= smem_budget) ? 1 : 0;
         if (L.beams_in_smem) fixed += 2 * tab_bytes(W);
-        u32 cap = 512;
+        u32 cap = cap_max;
         while (cap > 64 && fixed + tier_bytes(cap, pow2_ge(2 * cap)) > smem_budget) cap >>= 1;
         L.cap_s = cap;
         L.ht_s = pow2_ge(2 * cap);
@@ -106,7 +109,7 @@ static B2cLayout make_layout(int W, int V, int T_max, bool full_caps, u32 smem_b
         L.s_tab[0] = static_cast<u32>(s); s += tab_bytes(W);
         L.s_tab[1] = static_cast<u32>(s); s += tab_bytes(W);
     }
-    L.s_sel = static_cast<u32>(s); s += sel_bytes(W, n_warps);
+    L.s_sel = static_cast<u32>(s); s += sel_bytes(W, n_warps, n_bucket);
     L.s_tier = static_cast<u32>(s); s += tier_bytes(L.cap_s, L.ht_s);
     L.smem_bytes = static_cast<u32>(s);
     u64 g = 0;
@@ -234,7 +237,8 @@ B2C_HD void b2c_beam_block(const B2cBeamArgs& A, int slot, u8* smem) {
                 single = t0.canon;
                 const int kind = b2c_inplace_kind(W.sc->flags, prev_single, t0.flags, t0.canon);
                 if (kind != B2C_INPLACE_NO)
-                    in_place = b2c_inplace_step(A.P, W, t + t0_frames, kind, id0, rec.lp0, static_cast<int>(nxt.cnt));
+                    in_place = b2c_inplace_step(A.P, W, t + t0_frames, kind, id0, t0, rec.lp0, static_cast<int>(nxt.cnt));
+                B2C_MARK(5);
             }
             prev_single = single;
             if (in_place) {
@@ -773,6 +777,7 @@ static int launch_beam(b2c_decoder* d, const B2cBeamArgs& A, int slots, bool fas
     else if (fast && threads == 256) B2C_LAUNCH_BEAM(true, 256, 1);    // 255 registers x 256 threads: the whole register file
     else if (fast && threads == 64) B2C_LAUNCH_BEAM(true, 64, 4);     // 255 registers x 64 threads: 4 CTAs per SM
     else if (fast) B2C_LAUNCH_BEAM(true, 128, 2);                 // 255 registers x 128 threads: 2 CTAs per SM
+    else if (threads == 256) B2C_LAUNCH_BEAM(false, 256, 1);
     else B2C_LAUNCH_BEAM(false, 128, 2);
 #undef B2C_LAUNCH_BEAM
     CUDA_OK(cudaGetLastError());
@@ -1488,7 +1493,9 @@ static int decode_batch_locked(b2c_decoder_t* d, const void* const* logits, cons
     // big classes leave room for one CTA per SM only: give that CTA 256 threads (a diffuse frame has ~650 candidates)
     auto threads_of = [&](int c) { return kCaps[c] <= 128 ? 32 : (kCaps[c] <= 256 ? 64 : (kCaps[c] >= 2048 ? 256 : 128)); };
     auto layout_of = [&](int c, int tmax, bool full, u64 worst_m) {
-        return make_layout(opts->beam_width, V, tmax, full, smem_budget, kCaps[c], worst_m, threads_of(c) / 32);
+        // the 2048 / 4096-candidate classes own an SM anyway: they rank over the wide bucket array
+        return make_layout(opts->beam_width, V, tmax, full, smem_budget, kCaps[c], worst_m, threads_of(c) / 32, 0, 0, 1,
+                           kCaps[c] >= 2048 ? B2C_NBUCKET_WIDE : B2C_NBUCKET);
     };
     auto per_sm_of = [&](u32 smem_bytes, int threads) {
         const int by_smem = static_cast<int>(std::max<u64>(1, (224 * 1024) / std::max<u32>(smem_bytes + 1024, 2048)));
@@ -1616,9 +1623,24 @@ static int decode_batch_locked(b2c_decoder_t* d, const void* const* logits, cons
             ln.per_sm = kV5Occ[ln.v5];
         } else {
         ln.threads = cls < kNumCaps ? threads_of(cls) : 128;
-        ln.L = cls < kNumCaps ? layout_of(cls, tmax, full, worst_m)
-                              : make_layout(W_tab, V, tmax, full, smem_budget, 0, worst_m, 4, static_cast<u64>(s_max_beams),
-                                            s_max_words + static_cast<u64>(s_max_beams), n_lm);
+        if (cls < kNumCaps) {
+            ln.L = layout_of(cls, tmax, full, worst_m);
+        } else {
+            // general kernel: the largest shared-memory candidate tier that fits (frames beyond it work on the HBM tier at
+            // L2 latency) -- unless the launch has more utterances than SMs and the small tier keeps two CTAs per SM
+            auto general = [&](u32 cap_max) {
+                return make_layout(W_tab, V, tmax, full, smem_budget, 0, worst_m, B2C_MAXWARPS, static_cast<u64>(s_max_beams),
+                                   s_max_words + static_cast<u64>(s_max_beams), n_lm, B2C_NBUCKET_WIDE, cap_max);
+            };
+            ln.L = general(2048);
+            if (per_sm_of(ln.L.smem_bytes, 128) == 1 && ln.count > d->n_sm) {
+                const B2cLayout small = general(512);
+                if (per_sm_of(small.smem_bytes, 128) >= 2) ln.L = small;
+            }
+        }
+        // the general kernel with room for one CTA per SM only (wide beams): that CTA gets the whole register file --
+        // its phases are loops over hundreds to thousands of candidates, each a chain of dependent memory accesses
+        if (cls == kNumCaps && per_sm_of(ln.L.smem_bytes, 128) == 1) ln.threads = 256;
         ln.per_sm = per_sm_of(ln.L.smem_bytes, ln.threads);
         }
         ln.slots = std::min(ln.count, d->n_sm * ln.per_sm);

@@ -59,11 +59,15 @@ struct B2cScalars {
     u32 m_frames;
     u32 inplace_bad;     // a thread's exactness check of b2c_inplace_step failed (rare)
     u32 m_inplace;       // frames handled by b2c_inplace_step
+    u32 clean_s, clean_g; // leading slots of the shared-memory / HBM tier's grouping table that are known to be clear
 };
 enum { B2C_FL_BPE = 1, B2C_FL_PRUNE = 2, B2C_FL_LM = 4, B2C_FL_PSCORE = 8 };
 
 #define B2C_NBUCKET 256      // score buckets of the O(m) ranking (monotone in the score)
+#define B2C_NBUCKET_WIDE 2048 // the same for launches that rank hundreds to thousands of candidates per frame (general kernel,
+                              // the 2048 / 4096-candidate classes): a bucket then holds ~1 candidate instead of ~10
 #define B2C_MAXWARPS 8       // warps per CTA of the beam kernel (64-, 128- and 256-thread variants)
+#define B2C_STAGE_K 64       // most tokens of a frame whose label records are staged in shared memory (general kernels)
 
 struct B2cCandTier {     // per-frame candidate working set (shared memory tier or HBM tier)
     u32 cap;             // candidates
@@ -93,9 +97,15 @@ struct B2cWork {
     u32* pt_idx;         // history-prune table: slot -> representative rank
     u32* pt_min;         //                      slot -> best rank with that key
     u32 pt_cap;          // power of two >= 2 * beam_width
-    u32* bcnt;           // [B2C_NBUCKET] leaders per score bucket
-    u32* bhead;          // [B2C_NBUCKET] list heads
-    u32* bpre;           // [B2C_MAXWARPS][B2C_NBUCKET] exclusive prefix, one private copy per warp
+    u32 n_bucket;        // B2C_NBUCKET or B2C_NBUCKET_WIDE
+    u32* bcnt;           // [n_bucket] leaders per score bucket
+    u32* bhead;          // [n_bucket] list heads
+    u32* bpre;           // exclusive prefix: [n_warps][B2C_NBUCKET], one private copy per warp, or ONE [B2C_NBUCKET_WIDE + 8]
+    // label records / log-probs / ids of the current frame's tokens, staged once per frame (frames of up to
+    // B2C_STAGE_K tokens; nullptr: no staging area, e.g. the out-of-line step of the latency-first kernel)
+    B2cTok* stok;
+    double* slp;
+    u32* sid;
     // per-frame token side arrays for BPE force_next_break (capacity V, HBM)
     u32* tk_ffirst;
     u8* tk_fall;
@@ -122,6 +132,7 @@ struct B2cLayout {
     u32 cap_g, ht_g;            // HBM candidate tier (0: absent)
     int beams_in_smem;
     int n_warps;                // warps per CTA of the launch (sizes the per-warp scratch)
+    int n_bucket;               // score buckets (B2C_NBUCKET / B2C_NBUCKET_WIDE)
     u32 chain_cap, text_cap;
     int V;
     u32 smem_bytes;
@@ -190,9 +201,13 @@ B2C_HD void b2c_make_work(const B2cLayout& L, u8* smem, u8* g, int parity, bool 
         W.pt_cap = pt_cap_for(L.W);
         W.pt_idx = reinterpret_cast<u32*>(b2c_carve(p, 4ull * W.pt_cap));
         W.pt_min = reinterpret_cast<u32*>(b2c_carve(p, 4ull * W.pt_cap));
-        W.bcnt = reinterpret_cast<u32*>(b2c_carve(p, 4ull * B2C_NBUCKET));
-        W.bhead = reinterpret_cast<u32*>(b2c_carve(p, 4ull * B2C_NBUCKET));
-        W.bpre = reinterpret_cast<u32*>(b2c_carve(p, 4ull * B2C_NBUCKET * L.n_warps));
+        W.n_bucket = static_cast<u32>(L.n_bucket);
+        W.bcnt = reinterpret_cast<u32*>(b2c_carve(p, 4ull * L.n_bucket));
+        W.bhead = reinterpret_cast<u32*>(b2c_carve(p, 4ull * L.n_bucket));
+        W.bpre = reinterpret_cast<u32*>(b2c_carve(p, L.n_bucket == B2C_NBUCKET ? 4ull * B2C_NBUCKET * L.n_warps : 4ull * (L.n_bucket + 8)));
+        W.stok = reinterpret_cast<B2cTok*>(b2c_carve(p, sizeof(B2cTok) * B2C_STAGE_K));
+        W.slp = reinterpret_cast<double*>(b2c_carve(p, 8ull * B2C_STAGE_K));
+        W.sid = reinterpret_cast<u32*>(b2c_carve(p, 4ull * B2C_STAGE_K));
     }
     b2c_carve_tier(smem + L.s_tier, L.cap_s, L.ht_s, W.tier_s);
     if (L.cap_g) b2c_carve_tier(g + L.g_tier, L.cap_g, L.ht_g, W.tier_g);
@@ -468,7 +483,34 @@ B2C_HD void b2c_clear_tables(const B2cWork& W, const B2cCandTier& C, u32 H) {
         C.ht_max[s] = 0;
         C.ht_cnt[s] = 0;
     }
-    B2C_FOR(s, B2C_NBUCKET) { W.bcnt[s] = 0; W.bhead[s] = B2C_NONE_U32; }
+    B2C_FOR(s, W.n_bucket) { W.bcnt[s] = 0; W.bhead[s] = B2C_NONE_U32; }
+}
+// The same with bookkeeping: sc->clean_s / clean_g say how many leading slots of each tier's table are known to be
+// clear, so that frames which never touch the table (in-place steps) do not sweep it again.  `used_g` / `H_used`: the
+// tier and extent the calling step has dirtied (H_used == 0: none).  Every thread computes the same values from the
+// scalars it read BEFORE the closing barrier of the step; the leader stores them (block-uniform control flow).
+B2C_HD void b2c_prepare_tables(const B2cWork& W, u32 M_next, bool used_g, u32 H_used, bool buckets) {
+    B2cScalars* sc = W.sc;
+    const bool next_g = M_next > W.tier_s.cap && W.tier_g.cap > W.tier_s.cap;
+    const B2cCandTier Cn = next_g ? W.tier_g : W.tier_s;
+    u32 Hn = b2c_ht_size(M_next);
+    if (Hn > Cn.ht_cap) Hn = Cn.ht_cap;
+    u32 cs = sc->clean_s, cg = sc->clean_g;
+    if (H_used) { if (used_g) cg = 0; else cs = 0; }
+    const u32 have = next_g ? cg : cs;
+    if (have < Hn) {
+        B2C_FOR(q, Hn - have) {
+            const u32 s = have + static_cast<u32>(q);
+            Cn.ht_idx[s] = B2C_NONE_U32;
+            Cn.ht_min[s] = B2C_NONE_U32;
+            Cn.ht_max[s] = 0;
+            Cn.ht_cnt[s] = 0;
+        }
+        if (next_g) cg = Hn; else cs = Hn;
+    }
+    if (buckets) { B2C_FOR(s, W.n_bucket) { W.bcnt[s] = 0; W.bhead[s] = B2C_NONE_U32; } }
+    B2C_SYNC();         // everybody has read the old extents
+    B2C_LEADER { sc->clean_s = cs; sc->clean_g = cg; }
 }
 
 // i -> (i / n, i % n) without an integer division (float reciprocal + exact correction)
@@ -482,11 +524,12 @@ B2C_HD void b2c_divmod(u32 i, u32 n, float rcp, u32& q, u32& r) {
 
 // score bucket relative to a reference score, monotone non-increasing in the score: a larger score
 // never gets a larger bucket (scores above the reference share bucket 0, far-away ones the last)
-B2C_HD u32 b2c_bucket(double ref, double score, double scale) {
+B2C_HD u32 b2c_bucket_n(double ref, double score, double scale, u32 nb) {
     const double d = (ref - score) * scale;
     if (!(d > 0.0)) return 0;
-    return d >= static_cast<double>(B2C_NBUCKET - 1) ? static_cast<u32>(B2C_NBUCKET - 1) : static_cast<u32>(d);
+    return d >= static_cast<double>(nb - 1) ? nb - 1 : static_cast<u32>(d);
 }
+B2C_HD u32 b2c_bucket(double ref, double score, double scale) { return b2c_bucket_n(ref, score, scale, B2C_NBUCKET); }
 B2C_HD double b2c_bucket_scale(double prune_logp) {
     double range = -prune_logp + 2.0;      // the reference point is the previous frame's best score
     if (!(range >= 1.0)) range = 1.0;      // also catches NaN
@@ -515,6 +558,39 @@ B2C_HD void b2c_bucket_scan_warp(const u32* bcnt, u32* pre) {
 #else
     u32 run = 0;
     for (u32 b = 0; b < B2C_NBUCKET; ++b) { pre[b] = run; run += bcnt[b]; }
+#endif
+}
+
+// the same for B2C_NBUCKET_WIDE buckets: ONE copy computed by the whole CTA (two block barriers inside; nb is a multiple
+// of 4 * blockDim.x); pre[nb .. nb + 8) is scratch for the warp totals
+B2C_HD void b2c_bucket_scan_block(const u32* bcnt, u32* pre, u32 nb) {
+#if defined(__CUDA_ARCH__)
+    const u32 tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const u32 per4 = nb / (4 * blockDim.x);
+    const uint4* src = reinterpret_cast<const uint4*>(bcnt) + tid * per4;
+    u32 sum = 0;
+    for (u32 q = 0; q < per4; ++q) { const uint4 a = src[q]; sum += a.x + a.y + a.z + a.w; }
+    u32 incl = sum;
+    for (int off = 1; off < 32; off <<= 1) {
+        const u32 o = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+        if (lane >= static_cast<u32>(off)) incl += o;
+    }
+    if (lane == 31) pre[nb + w] = incl;
+    __syncthreads();
+    u32 run = incl - sum;
+    for (u32 q = 0; q < w; ++q) run += pre[nb + q];
+    uint4* dst = reinterpret_cast<uint4*>(pre) + tid * per4;
+    for (u32 q = 0; q < per4; ++q) {
+        const uint4 a = src[q];
+        uint4 o;
+        o.x = run; o.y = o.x + a.x; o.z = o.y + a.y; o.w = o.z + a.z;
+        run = o.w + a.w;
+        dst[q] = o;
+    }
+    __syncthreads();
+#else
+    u32 run = 0;
+    for (u32 b = 0; b < nb; ++b) { pre[b] = run; run += bcnt[b]; }
 #endif
 }
 
@@ -549,7 +625,7 @@ B2C_HD void b2c_block_add_u32(u32 v, u32* target) {
 // one new beam: rank r of this frame becomes beam j of the next frame
 template <class Tier>
 B2C_HD void b2c_commit_one(const B2cParams& P, const B2cWork& W, const Tier& C, const B2cBeamTab& cur, const B2cBeamTab& nx,
-                           const u32* tk_id, u32 n, float rcp_n, int t, u32 j, u32 r, u32 flags) {
+                           const u32* tk_id, const B2cTok* toks_s, u32 n, float rcp_n, int t, u32 j, u32 r, u32 flags) {
     B2cScalars* sc = W.sc;
     const u32 i = W.ord[r];
     const u32 last = C.clast[i];
@@ -568,7 +644,7 @@ B2C_HD void b2c_commit_one(const B2cParams& P, const B2cWork& W, const Tier& C, 
     // partial_frames (decoder.py:454-461,495,513,519-523)
     const int ps0 = cur.pf_s[bl], pe0 = cur.pf_e[bl];
     int pfs, pfe;
-    if (type == 0) { pfs = ps0; pfe = (P.toks[tk_id[k]].flags & B2C_TF_BLANK) ? pe0 : t + 1; }
+    if (type == 0) { pfs = ps0; pfe = ((toks_s ? toks_s[k].flags : P.toks[tk_id[k]].flags) & B2C_TF_BLANK) ? pe0 : t + 1; }
     else if (type == 1) { pfs = t; pfe = t + 1; }
     else if (type == 2) { pfs = -1; pfe = -1; }
     else { pfs = ps0 < 0 ? t : ps0; pfe = t + 1; }
@@ -578,7 +654,7 @@ B2C_HD void b2c_commit_one(const B2cParams& P, const B2cWork& W, const Tier& C, 
     // backtrack chain
     u32 chain = cur.chain[bl];
     if (type != 0) {
-        const u32 id = b2c_atomic_add_u32(&sc->chain_used, 1u);
+        const u32 id = b2c_alloc_one(&sc->chain_used);
         if (id < W.chain_cap) {
             B2cChain c;
             c.parent = chain;
@@ -621,7 +697,7 @@ B2C_HD void b2c_commit_one(const B2cParams& P, const B2cWork& W, const Tier& C, 
 // prune table are clear (previous frame's phase D / b2c_utt_begin).
 // -----------------------------------------------------------------------------------------
 template <bool kFast>
-B2C_HD void b2c_frame_step(const B2cParams& P, B2cWork& W, int t, const u32* tk_id, const double* tk_lp, int K, int K_next) {
+B2C_HD void b2c_frame_step(const B2cParams& P, B2cWork& W, int t, const u32* tk_id_g, const double* tk_lp_g, int K, int K_next) {
     B2cScalars* sc = W.sc;
     const u32 n = sc->n_beams;
     const u32 M = n * static_cast<u32>(K);
@@ -646,23 +722,40 @@ B2C_HD void b2c_frame_step(const B2cParams& P, B2cWork& W, int t, const u32* tk_
     u32* const pslot = W.pslot;
     u32* const bcnt = W.bcnt;
     u32* const bhead = W.bhead;
-    u32* const bpre = W.bpre + static_cast<u32>(b2c_warp_id()) * B2C_NBUCKET;
+    const u32 nb = W.n_bucket;
+    u32* const bpre = nb == B2C_NBUCKET ? W.bpre + static_cast<u32>(b2c_warp_id()) * B2C_NBUCKET : W.bpre;
     u32* const pt_idx = W.pt_idx;
     u32* const pt_min = W.pt_min;
     const u32 ptmask = W.pt_cap - 1;
     const double ref = sc->prev_max;
-    const double bscale = P.bucket_scale;
+    const double bscale = P.bucket_scale * static_cast<double>(nb / B2C_NBUCKET);
     const u32 flags = sc->flags;
     const bool is_bpe = (flags & B2C_FL_BPE) != 0, prune = (flags & B2C_FL_PRUNE) != 0;
 
-    if (is_bpe) b2c_bpe_force(P.toks, tk_id, K, cur.last_tok, n, W.tk_ffirst, W.tk_fall, &sc->force_break);
+    // label records / log-probs of this frame's tokens: once into shared memory instead of two dependent global
+    // loads per candidate (frames of up to B2C_STAGE_K tokens)
+    const bool staged = W.stok != nullptr && K <= B2C_STAGE_K;
+    const B2cTok* const toks_s = staged ? W.stok : nullptr;
+    if (staged) {
+        B2C_FOR(k, K) {
+            const u32 id = tk_id_g[k];
+            W.sid[k] = id;
+            W.stok[k] = P.toks[id];
+            W.slp[k] = tk_lp_g[k];
+        }
+    }
+    const u32* const tk_id = staged ? W.sid : tk_id_g;
+    const double* const tk_lp = staged ? W.slp : tk_lp_g;
+    if (prune) { B2C_FOR(s, W.pt_cap) { pt_idx[s] = B2C_NONE_U32; pt_min[s] = B2C_NONE_U32; } }
+    if (staged) B2C_SYNC();
+
+    if (is_bpe) b2c_bpe_force(toks_s ? toks_s : P.toks, toks_s ? nullptr : tk_id, K, cur.last_tok, n, W.tk_ffirst, W.tk_fall, &sc->force_break);
 
     // ---- phase A: expand once, cache, merge key, grouping (publish key, fence, claim slot) -----
-    if (prune) { B2C_FOR(s, W.pt_cap) { pt_idx[s] = B2C_NONE_U32; pt_min[s] = B2C_NONE_U32; } }
     B2C_FOR(i, M) {
         u32 k, b;
         b2c_divmod(static_cast<u32>(i), n, rcp_n, k, b);
-        const B2cTok ti = P.toks[tk_id[k]];
+        const B2cTok ti = toks_s ? toks_s[k] : P.toks[tk_id[k]];
         const u32 plen = cur.part_len[b];
         const u64 ph = cur.part_hash[b];
         u64 th = cur.text_hash[b];
@@ -727,7 +820,7 @@ B2C_HD void b2c_frame_step(const B2cParams& P, B2cWork& W, int t, const u32* tk_
             const double sco = b2c_combine_score((flags & B2C_FL_LM) != 0, s, lm_hw, ps, part_len);
             const u64 key = b2c_f64_key(sco);
             C.ckey[i] = key;
-            const u32 bkt = b2c_bucket(ref, sco, bscale);
+            const u32 bkt = b2c_bucket_n(ref, sco, bscale, nb);
             b2c_atomic_add_u32(&bcnt[bkt], 1u);
 #if defined(__CUDA_ARCH__)
             C.cnext[i] = atomicExch(&bhead[bkt], static_cast<u32>(i));
@@ -744,7 +837,8 @@ B2C_HD void b2c_frame_step(const B2cParams& P, B2cWork& W, int t, const u32* tk_
 
     // ---- phase C: threshold (decoder.py:545-546), stable top-N (decoder.py:548): rank = bucket
     //      prefix + exact order inside the bucket; history keys of the selected go to the prune table
-    b2c_bucket_scan_warp(bcnt, bpre);
+    if (nb == B2C_NBUCKET) b2c_bucket_scan_warp(bcnt, bpre);
+    else b2c_bucket_scan_block(bcnt, bpre, nb);
     const double max_score = b2c_key_f64(sc->max_key);
     const double thr = max_score + P.prune_logp;
     const u32 width = static_cast<u32>(P.beam_width);
@@ -755,8 +849,9 @@ B2C_HD void b2c_frame_step(const B2cParams& P, B2cWork& W, int t, const u32* tk_
             if (key == 0) continue;
             const double sco = b2c_key_f64(key);
             if (!(sco >= thr)) continue;
-            const u32 bkt = b2c_bucket(ref, sco, bscale);
+            const u32 bkt = b2c_bucket_n(ref, sco, bscale, nb);
             u32 rank = bpre[bkt];
+            if (rank >= width) continue;          // every candidate of a better bucket outranks it: no need to walk its own
             for (u32 j = bhead[bkt]; j != B2C_NONE_U32; j = C.cnext[j]) {
                 if (j == static_cast<u32>(i)) continue;
                 const u64 kj = C.ckey[j];
@@ -807,23 +902,18 @@ B2C_HD void b2c_frame_step(const B2cParams& P, B2cWork& W, int t, const u32* tk_
             const u32 r = blk * 32 + lane;
             const bool kept = r < nsel && (!prune || pt_min[pslot[r]] == r);
             const u32 mask = __ballot_sync(0xFFFFFFFFu, kept);
-            if (kept && (blk % nw) == w) b2c_commit_one(P, W, C, cur, nx, tk_id, n, rcp_n, t, n_new + __popc(mask & lt), r, flags);
+            if (kept && (blk % nw) == w) b2c_commit_one(P, W, C, cur, nx, tk_id, toks_s, n, rcp_n, t, n_new + __popc(mask & lt), r, flags);
             n_new += __popc(mask);
         }
     }
 #else
     for (u32 r = 0; r < nsel; ++r) {
         const bool kept = !prune || pt_min[pslot[r]] == r;
-        if (kept) b2c_commit_one(P, W, C, cur, nx, tk_id, n, rcp_n, t, n_new++, r, flags);
+        if (kept) b2c_commit_one(P, W, C, cur, nx, tk_id, toks_s, n, rcp_n, t, n_new++, r, flags);
     }
 #endif
-    {
-        const u32 M_next = n_new * static_cast<u32>(K_next);
-        const B2cCandTier Cn = b2c_pick_tier(W, M_next);   // the next frame may take the other tier
-        u32 Hn = b2c_ht_size(M_next);
-        if (Hn > Cn.ht_cap) Hn = Cn.ht_cap;
-        b2c_clear_tables(W, Cn, Hn);
-    }
+    // the next frame may take the other tier; this frame dirtied the first hmask + 1 slots of its own
+    b2c_prepare_tables(W, n_new * static_cast<u32>(K_next), !kFast && M > W.tier_s.cap && W.tier_g.cap > W.tier_s.cap, hmask + 1, true);
     B2C_LEADER { sc->n_beams = n_new; sc->prev_max = max_score; }
     B2C_SYNC();
     B2C_MARK(4);
@@ -848,13 +938,14 @@ B2C_HD int b2c_inplace_kind(u32 flags, u32 prev_single, u16 tok_flags, u16 tok_c
     // in place only if they stay in order and above the threshold (same as b2c_fast_scored_step)
     return (flags & B2C_FL_PSCORE) ? B2C_INPLACE_T3P : B2C_INPLACE_T3;
 }
-B2C_HDN bool b2c_inplace_step(B2cParams P, B2cWork W, int t, int kind, u16 tok_id, double p, int K_next) {
+// Inline, by reference: an out-of-line copy would take the parameter block and the work descriptor by value (~1 KB of
+// local-memory traffic per frame) or force the descriptor into local memory for the whole kernel.
+B2C_HD bool b2c_inplace_step(const B2cParams& P, const B2cWork& W, int t, int kind, u16 tok_id, const B2cTok& ti, double p, int K_next) {
     B2cScalars* sc = W.sc;
     const u32 n = sc->n_beams;
     const u32 flags = sc->flags;
     const bool has_lm = (flags & B2C_FL_LM) != 0, plain = (flags & B2C_FL_PSCORE) == 0;
     const B2cBeamTab cur = W.cur;
-    const B2cTok ti = P.toks[tok_id];
     const bool scored = kind == B2C_INPLACE_T3P;
     const B2cCandTier Cs = b2c_pick_tier(W, n);        // scratch of the scored form: new lm_score, new partial score
     if (scored) {
@@ -901,6 +992,7 @@ B2C_HDN bool b2c_inplace_step(B2cParams P, B2cWork W, int t, int kind, u16 tok_i
         return false;
     }
     const bool blank = (ti.flags & B2C_TF_BLANK) != 0;
+    const u32 chain_base = sc->chain_used;        // branch (iv): beam b takes node chain_base + b (no per-beam atomic)
     B2C_FOR(b, n) {
         cur.logit[b] = cur.logit[b] + p;
         cur.last_tok[b] = ti.canon;
@@ -917,7 +1009,7 @@ B2C_HDN bool b2c_inplace_step(B2cParams P, B2cWork W, int t, int kind, u16 tok_i
             }
             if (ps0 < 0) cur.pf_s[b] = t;
             cur.pf_e[b] = t + 1;
-            const u32 id = b2c_atomic_add_u32(&sc->chain_used, 1u);
+            const u32 id = chain_base + static_cast<u32>(b);
             if (id < W.chain_cap) {
                 B2cChain c;
                 c.parent = cur.chain[b];
@@ -933,14 +1025,11 @@ B2C_HDN bool b2c_inplace_step(B2cParams P, B2cWork W, int t, int kind, u16 tok_i
             }
         }
     }
-    {   // what phase D of the general step leaves behind: tables clear for the next frame
-        const u32 M_next = n * static_cast<u32>(K_next);
-        const B2cCandTier Cn = b2c_pick_tier(W, M_next);
-        u32 Hn = b2c_ht_size(M_next);
-        if (Hn > Cn.ht_cap) Hn = Cn.ht_cap;
-        b2c_clear_tables(W, Cn, Hn);
-    }
+    // what phase D of the general step leaves behind: tables clear for the next frame (this step touched neither
+    // the grouping table nor the buckets: only what a wider next frame needs beyond the clear extent is swept)
+    b2c_prepare_tables(W, n * static_cast<u32>(K_next), false, 0, false);
     B2C_LEADER {
+        if (kind != B2C_INPLACE_T0) sc->chain_used = chain_base + n;
         sc->prev_max = top;
         ++sc->m_frames;
         ++sc->m_inplace;
@@ -972,13 +1061,18 @@ struct B2cStreamIn {           // streaming input of one utterance (n_beams == 0
     const u32* word_len;
 };
 B2C_HDN void b2c_utt_begin(B2cParams P, B2cWork W, const B2cLmState* start_state, int K_first, B2cStreamIn in) {
+    const u32 M0 = static_cast<u32>(K_first > 0 ? K_first : 1) * (in.n_beams > 0 ? in.n_beams : 1u);
     {
-        const u32 M0 = static_cast<u32>(K_first > 0 ? K_first : 1) * (in.n_beams > 0 ? in.n_beams : 1u);
         const B2cCandTier C0 = b2c_pick_tier(W, M0);
         b2c_clear_tables(W, C0, b2c_ht_size(M0));
     }
     B2C_LEADER {
         B2cScalars* sc = W.sc;
+        {   // clear extents of the two grouping tables (b2c_prepare_tables)
+            const bool g0 = M0 > W.tier_s.cap && W.tier_g.cap > W.tier_s.cap;
+            sc->clean_s = g0 ? 0u : b2c_ht_size(M0);
+            sc->clean_g = g0 ? b2c_ht_size(M0) : 0u;
+        }
         sc->n_beams = 1;
         sc->chain_used = 0;
         sc->text_used = 1;

@@ -170,7 +170,9 @@ B2C_HD void b2c_fast_work(B2cFastSmem<WC, CAP, LT>& S, const B2cLayout& L, u8* g
     W.phk = S.phk; W.ord = S.ord; W.pslot = S.pslot;
     W.pt_cap = B2cFastSmem<WC, CAP, LT>::PT;
     W.pt_idx = S.pt_idx; W.pt_min = S.pt_min;
+    W.n_bucket = B2C_NBUCKET;
     W.bcnt = S.bcnt; W.bhead = S.bhead; W.bpre = &S.bpre[0][0];
+    W.stok = nullptr; W.slp = nullptr; W.sid = nullptr;
     B2cCandTier& c = W.tier_s;
     c.cap = slow ? 0u : static_cast<u32>(CAP);
     c.ht_cap = B2cFastSmem<WC, CAP, LT>::HT;
@@ -509,6 +511,7 @@ B2C_HD void b2c_fast_step(const B2cParams& P, B2cFastSmem<WC, CAP, LT>& S, B2cCh
             if (!(sco >= thr)) continue;
             const u32 bkt = b2c_bucket(ref, sco, bscale);
             u32 rank = bpre[bkt];
+            if (rank >= width) continue;          // every candidate of a better bucket outranks it: no need to walk its own
             for (u32 j = S.bhead[bkt]; j != B2C_NONE_U32; j = S.cnext[j]) {
                 if (j == static_cast<u32>(i)) continue;
                 const u64 kj = S.ckey[j];

@@ -72,6 +72,21 @@ B2C_HD u32 b2c_atomic_add_u32(u32* p, u32 v) {
     return old;
 #endif
 }
+// one item from a bump counter per calling thread: the threads of a warp that arrive together share ONE atomic
+// (hundreds of beams allocating a backtrack node each would otherwise serialise on one shared-memory word)
+B2C_HD u32 b2c_alloc_one(u32* counter) {
+#if defined(__CUDA_ARCH__)
+    const unsigned m = __activemask();
+    const unsigned lane = threadIdx.x & 31u;
+    const int first = __ffs(static_cast<int>(m)) - 1;
+    u32 base = 0;
+    if (static_cast<int>(lane) == first) base = atomicAdd(counter, static_cast<u32>(__popc(m)));
+    base = __shfl_sync(m, base, first);
+    return base + static_cast<u32>(__popc(m & ((1u << lane) - 1u)));
+#else
+    return b2c_atomic_add_u32(counter, 1u);
+#endif
+}
 B2C_HD void b2c_atomic_min_u32(u32* p, u32 v) {
 #if defined(__CUDA_ARCH__)
     atomicMin(p, v);

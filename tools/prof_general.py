@@ -1,6 +1,7 @@
 """Profiling helper (GPU box): phase clocks of the wide-beam / diffuse regimes and a host profile of decode_beams_batch.
 Run with the phase-clock build in place of the product library for the first part:
     python tools/prof_general.py clocks   (stderr carries one phase-clock line per call)
+    python tools/prof_general.py one beam500   (two calls of one configuration, e.g. under ncu -k regex:b2c_beam_kernel -s 1 -c 1)
     python tools/prof_general.py beams    (cProfile of decode_beams_batch at the C2 shape)
 """
 import cProfile
@@ -23,9 +24,9 @@ def main():
     spec = bench.WORKLOADS["c2"]
     wl, kw, hot = bench.workload_objects(spec)
     dec = pkg.build_ctcdecoder(wl.labels, device=0, **kw)
-    if what == "clocks":
-        for name, regime, beam, B in (("beam500", "peaky", 500, 256), ("beam2000", "peaky", 2000, 256), ("diffuse", "diffuse", 100, 256),
-                                      ("beam200", "peaky", 200, 256)):
+    cfgs = (("beam500", "peaky", 500, 256), ("beam2000", "peaky", 2000, 256), ("diffuse", "diffuse", 100, 256), ("beam200", "peaky", 200, 256))
+    if what in ("clocks", "one"):
+        for name, regime, beam, B in [c for c in cfgs if what == "clocks" or c[0] == sys.argv[2]]:
             xs = wl.batch(1, B, spec["T"], regime)
             dev = torch.from_numpy(np.stack(xs)).cuda()
             for it in range(2):
