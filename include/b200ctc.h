@@ -191,6 +191,19 @@ typedef struct {
     const char* texts;            /* utf-8, every beam's text followed by a NUL byte */
     size_t texts_size;
     const b2c_lm_state_t* states; /* [n_beams_total][n_models] */
+    /* streaming calls only (NULL otherwise): what b2c_result_stream_beam returns, for every beam at once; `frames` /
+     * `n_words` then describe the words finished during the call */
+    const int32_t* stream_aux;    /* [n_beams_total][4] */
+    const int32_t* n_stream_toks; /* [n_beams_total] */
+    const uint32_t* stream_toks;  /* emitted tokens (token | kind << 16), oldest first, beam after beam */
+    int64_t n_stream_toks_total;
+    /* the same token chains replayed into strings, three per beam, each followed by a NUL byte: what the chain appends
+     * to the input beam's partial word before the first word boundary; the words finished after that boundary, joined
+     * by single spaces; the partial word after the last boundary.  stream_boundary[beam] says whether the chain
+     * contains a word boundary at all (0: everything went to the first string). */
+    const char* stream_pieces;
+    size_t stream_pieces_size;
+    const int32_t* stream_boundary; /* [n_beams_total] */
 } b2c_packed_t;
 int b2c_result_packed(b2c_result_t* res, b2c_packed_t* out);
 /* streaming calls (opts->stream_states != NULL): what the call appended to an input beam instead of assembled
@@ -206,6 +219,8 @@ int b2c_result_n_frames(const b2c_result_t* res, int utt, int beam);
 /* string -> (hash, code points) as the kernels identify words and partial words; label -> canonical token id
  * (-1 when the alphabet has no such label) */
 int b2c_hash_utf8(const char* s, uint64_t* hash, uint32_t* n_chars);
+/* the same for `count` strings stored back to back, each followed by a NUL byte */
+int b2c_hash_utf8_batch(const char* data, size_t size, int64_t count, uint64_t* hashes, uint32_t* n_chars);
 int b2c_decoder_token_id(const b2c_decoder_t* dec, const char* label);
 
 /* ---- measurement hooks (bench.py) ---------------------------------------------------------

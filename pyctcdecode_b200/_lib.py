@@ -54,7 +54,9 @@ class Packed(C.Structure):
     _fields_ = [("n_utts", C.c_int32), ("n_models", C.c_int32), ("n_beams_total", C.c_int64), ("n_words_total", C.c_int64),
                 ("n_beams", C.POINTER(C.c_int32)), ("scores", C.POINTER(C.c_double)), ("n_words", C.POINTER(C.c_int32)),
                 ("frames", C.POINTER(C.c_int32)), ("texts", C.c_void_p), ("texts_size", C.c_size_t),
-                ("states", C.POINTER(LMState))]
+                ("states", C.POINTER(LMState)), ("stream_aux", C.POINTER(C.c_int32)), ("n_stream_toks", C.POINTER(C.c_int32)),
+                ("stream_toks", C.POINTER(C.c_uint32)), ("n_stream_toks_total", C.c_int64),
+                ("stream_pieces", C.c_void_p), ("stream_pieces_size", C.c_size_t), ("stream_boundary", C.POINTER(C.c_int32))]
 
 
 class Timings(C.Structure):
@@ -127,6 +129,7 @@ def _declare(L):
     L.b2c_result_word.argtypes = [vp, i32, i32, i32]
     L.b2c_result_word.restype = cp
     L.b2c_result_packed.argtypes = [vp, C.POINTER(Packed)]
+    L.b2c_hash_utf8_batch.argtypes = [C.c_char_p, C.c_size_t, C.c_int64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
     L.b2c_result_frames.argtypes = [vp, i32, i32]
     L.b2c_result_frames.restype = C.POINTER(C.c_int32)
     L.b2c_result_lm_state.argtypes = [vp, i32, i32, C.POINTER(LMState)]

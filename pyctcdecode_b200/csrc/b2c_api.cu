@@ -582,6 +582,8 @@ struct BeamRes {
     B2cLmState st;
     std::vector<B2cLmState> stx;   // MultiLanguageModel: states of models 1..
     std::vector<u32> raw;      // streaming calls: emitted tokens since the input beam, oldest first
+    std::string s_first, s_mid, s_last;   // ... and replayed into strings (b2c_packed_t.stream_pieces)
+    bool s_boundary = false;
     int aux[4] = {-1, -1, -1, -1};
 };
 struct b2c_result {
@@ -596,6 +598,10 @@ struct b2c_result {
     std::vector<double> pk_scores;
     std::vector<b2c_lm_state_t> pk_states;
     std::string pk_texts;
+    bool streaming = false;
+    std::vector<int32_t> pk_aux, pk_ntok, pk_boundary;
+    std::vector<u32> pk_toks;
+    std::string pk_pieces;
 };
 
 // hotword table (language_model.py:152-189): every code-point prefix of every hotword unigram
@@ -1249,6 +1255,7 @@ static int decode_batch_locked(b2c_decoder_t* d, const void* const* logits, cons
     }
     const int n_lm = std::max(1, P.n_lm);
     res->n_models = n_lm;
+    res->streaming = streaming;
     P.hist_n = std::max(1, max_order - 1);
     std::vector<B2cHot> hot;
     build_hot(opts, hot, P.n_hot, P.hot_min_len_all);
@@ -2041,6 +2048,18 @@ static int decode_batch_locked(b2c_decoder_t* d, const void* const* logits, cons
                     br.raw.resize(static_cast<size_t>(h_nt[k]));
                     for (int q = 0; q < h_nt[k]; ++q) br.raw[q] = tk[h_nt[k] - 1 - q];
                     for (int q = 0; q < 4; ++q) br.aux[q] = h_ax[4 * k + q];
+                    {   // the chain as strings (the host replays it onto the input beam's text / partial word)
+                        std::string cur;
+                        br.s_boundary = false;
+                        for (const u32 v : br.raw) {
+                            const u32 tok = v & 0xFFFFu, kind = v >> 16;
+                            if (kind == B2C_CK_CONT) { cur += d->labels[tok]; continue; }
+                            if (!br.s_boundary) { br.s_first = cur; br.s_boundary = true; }
+                            else if (!cur.empty()) { if (!br.s_mid.empty()) br.s_mid += ' '; br.s_mid += cur; }
+                            cur = kind == B2C_CK_BPE ? d->clean[tok] : std::string();
+                        }
+                        if (br.s_boundary) br.s_last = cur; else br.s_first = cur;
+                    }
                     // assemble_beam truncated the frame list to the words it could name; keep all of them here
                     br.frames.resize(static_cast<size_t>(h_nw[k]) * 2);
                     const int* fr = h_frames + 2 * (base + r * stride);
@@ -2126,6 +2145,15 @@ int b2c_result_packed(b2c_result_t* r, b2c_packed_t* out) {
                     from_internal(j == 0 ? b.st : b.stx[static_cast<size_t>(j) - 1], &st);
                     r->pk_states.push_back(st);
                 }
+                if (r->streaming) {
+                    r->pk_aux.insert(r->pk_aux.end(), b.aux, b.aux + 4);
+                    r->pk_ntok.push_back(static_cast<int32_t>(b.raw.size()));
+                    r->pk_toks.insert(r->pk_toks.end(), b.raw.begin(), b.raw.end());
+                    r->pk_boundary.push_back(b.s_boundary ? 1 : 0);
+                    r->pk_pieces += b.s_first; r->pk_pieces.push_back('\0');
+                    r->pk_pieces += b.s_mid; r->pk_pieces.push_back('\0');
+                    r->pk_pieces += b.s_last; r->pk_pieces.push_back('\0');
+                }
             }
         }
         r->packed_built = true;
@@ -2141,6 +2169,13 @@ int b2c_result_packed(b2c_result_t* r, b2c_packed_t* out) {
     out->texts = r->pk_texts.data();
     out->texts_size = r->pk_texts.size();
     out->states = r->pk_states.empty() ? nullptr : r->pk_states.data();
+    out->stream_aux = r->streaming ? r->pk_aux.data() : nullptr;
+    out->n_stream_toks = r->streaming ? r->pk_ntok.data() : nullptr;
+    out->stream_toks = r->streaming ? r->pk_toks.data() : nullptr;
+    out->n_stream_toks_total = static_cast<int64_t>(r->pk_toks.size());
+    out->stream_pieces = r->streaming ? r->pk_pieces.data() : nullptr;
+    out->stream_pieces_size = r->pk_pieces.size();
+    out->stream_boundary = r->streaming ? r->pk_boundary.data() : nullptr;
     return 0;
 }
 double b2c_result_logit_score(const b2c_result_t* r, int u, int b) { return r->utts[u][b].logit; }
@@ -2176,6 +2211,19 @@ int b2c_hash_utf8(const char* s, uint64_t* hash, uint32_t* n_chars) {
     const size_t n = std::strlen(s);
     *hash = b2c_hash_bytes(s, n);
     *n_chars = b2c_utf8_len(s, n);
+    return 0;
+}
+int b2c_hash_utf8_batch(const char* data, size_t size, int64_t count, uint64_t* hashes, uint32_t* n_chars) {
+    if (count < 0 || (count > 0 && (!data || !hashes || !n_chars))) return fail(B2C_E_ARG, "null argument");
+    size_t p = 0;
+    for (int64_t i = 0; i < count; ++i) {
+        size_t q = p;
+        while (q < size && data[q] != '\0') ++q;
+        if (q >= size) return fail(B2C_E_ARG, "b2c_hash_utf8_batch: fewer NUL-terminated strings than `count`");
+        hashes[i] = b2c_hash_bytes(data + p, q - p);
+        n_chars[i] = b2c_utf8_len(data + p, q - p);
+        p = q + 1;
+    }
     return 0;
 }
 int b2c_decoder_token_id(const b2c_decoder_t* d, const char* label) {

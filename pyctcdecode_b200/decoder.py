@@ -168,6 +168,10 @@ class BeamSearchDecoderCTC:
         # before the call, and the handle's scratch buffers are per handle.  Any number of threads may call
         # decode()/decode_batch()/... concurrently, like with the reference; they run one after another on the GPU.
         self._run_lock = threading.RLock()
+        self._label_ids: Dict[str, int] = {}                              # last_char -> canonical token id
+        self._word_hash: Dict[str, Tuple[bytes, bytes, int, int]] = {}    # streaming host path, see _stream_states
+        self._text_cache: List[Dict[str, Tuple[bytes, bytes, int]]] = [{}, {}]
+        self._labels_with_space = any(len(lbl) > 1 and len(lbl.split()) != 1 for lbl in alphabet.labels)
 
     # ---- life cycle ---------------------------------------------------------------------
     def reset_params(self, alpha: Optional[float] = None, beta: Optional[float] = None,
@@ -389,7 +393,7 @@ class BeamSearchDecoderCTC:
                 _lib.check(L.b2c_result_top_texts(res, C.byref(data), C.byref(size)))
                 return C.string_at(data, size.value).decode("utf-8").split("\x00")[:n]
             if stream is not None:
-                return [self._stream_results(res, u, stream[u][0], finalize_mode) for u in range(n)]
+                return self._stream_results(res, stream, finalize_mode)
             out = self._output_beams(L, res, with_state, n_lm)
         finally:
             L.b2c_result_free(res)
@@ -495,86 +499,227 @@ class BeamSearchDecoderCTC:
     def _token_id(self, handle: int, label: Optional[str]) -> int:
         if label is None:
             return 0xFFFF
-        tid = int(_lib.lib().b2c_decoder_token_id(handle, label.encode("utf-8")))
-        if tid < 0:
-            raise ValueError("beam.last_char %r is not a label of this decoder's alphabet" % (label,))
+        ids = self._label_ids
+        tid = ids.get(label)
+        if tid is None:
+            tid = int(_lib.lib().b2c_decoder_token_id(handle, label.encode("utf-8")))
+            if tid < 0:
+                raise ValueError("beam.last_char %r is not a label of this decoder's alphabet" % (label,))
+            ids[label] = tid
         return tid
+
+    # ---- streaming host path ---------------------------------------------------------------------------------
+    # The beam state travels as Python strings (the reference's API).  The kernels identify words by hashes, so every
+    # call has to hand over the word hashes of every carried beam's text.  Two caches keep that linear in what is NEW:
+    #   _word_hash    word -> (hash as 8 bytes, code points as 4 bytes, hash, code points), filled by ONE library call
+    #                 per decode call for all the words not seen before
+    #   _text_cache   text -> (hashes of its words as bytes, their lengths as bytes, word count) for the beams the last
+    #                 two calls returned (a call's output texts are the next call's input texts); misses re-split the text
+    _SB_DTYPE = np.dtype([("part_hash", "<u8"), ("logit", "<f8"), ("word_off", "<u4"), ("n_words", "<u4"), ("part_len", "<u4"),
+                          ("last_tok", "<u4"), ("pf_s", "<i4"), ("pf_e", "<i4")])
+
+    def _hash_words(self, words: Sequence[str]) -> None:
+        if not words:
+            return
+        n = len(words)
+        data = b"".join([w.encode("utf-8") + b"\x00" for w in words])
+        hs, ls = np.empty(n, dtype=np.uint64), np.empty(n, dtype=np.uint32)
+        _lib.check(_lib.lib().b2c_hash_utf8_batch(data, len(data), n, hs.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                                  ls.ctypes.data_as(C.POINTER(C.c_uint32))))
+        table = self._word_hash
+        if len(table) > 1000000:
+            table.clear()
+        hb, lb, hl, ll = hs.tobytes(), ls.tobytes(), hs.tolist(), ls.tolist()
+        for i, w in enumerate(words):
+            table[w] = (hb[8 * i:8 * i + 8], lb[4 * i:4 * i + 4], hl[i], ll[i])
+
+    def _text_entry(self, text: str) -> Optional[Tuple[bytes, bytes, int]]:
+        ent = self._text_cache[0].get(text)
+        if ent is None:
+            ent = self._text_cache[1].get(text)
+        return ent
 
     def _stream_states(self, handle: int, stream: Sequence[Tuple[Sequence[Beam], int]], keep_alive: List[Any]) -> Any:
         """List of (beams, processed_frames) per utterance -> b2c_stream_state_t array (words and partial words
-        as hashes from b2c_hash_utf8, last_char as a token id)."""
-        L = _lib.lib()
-        hashes: Dict[str, Tuple[int, int]] = {}
-
-        def hash_of(word: str) -> Tuple[int, int]:
-            if word not in hashes:
-                h, n = C.c_uint64(), C.c_uint32()
-                _lib.check(L.b2c_hash_utf8(word.encode("utf-8"), C.byref(h), C.byref(n)))
-                hashes[word] = (h.value, n.value)
-            return hashes[word]
-
+        as hashes, last_char as a token id)."""
+        table = self._word_hash
+        c0, c1 = self._text_cache
+        # pass 1: the cached entry of every beam's text; which strings need hashing
+        missing: Dict[str, None] = {}
+        found: List[Any] = []            # per beam: cache entry, or the text itself on a miss
+        for beams, _ in stream:
+            for beam in beams:
+                text = beam.text if not beam.next_word else _merge_tokens(beam.text, beam.next_word)
+                ent = c0.get(text)
+                if ent is None:
+                    ent = c1.get(text)
+                if ent is None:
+                    ent = text
+                    for w in text.split():
+                        if w not in table:
+                            missing[w] = None
+                found.append(ent)
+                pw = beam.partial_word
+                if pw and pw not in table:
+                    missing[pw] = None
+        self._hash_words(list(missing))
+        # pass 2: columns of the beam rows and the word arrays (one allocation each for the whole call)
+        n_rows = len(found)
+        col_ph, col_lg, col_off, col_nw, col_pl, col_lt, col_s, col_e = [], [], [], [], [], [], [], []
+        hparts: List[bytes] = []
+        lparts: List[bytes] = []
+        starts: List[Tuple[int, int, int, int]] = []        # per utterance: first row, rows, first word, words
+        n_words_total = r = 0
+        ids = self._label_ids
+        for beams, _ in stream:
+            row0, off = r, 0
+            for beam in beams:
+                ent = found[r]
+                r += 1
+                if ent.__class__ is str:
+                    words = ent.split()
+                    ent = c0[ent] = (b"".join([table[w][0] for w in words]), b"".join([table[w][1] for w in words]), len(words))
+                hparts.append(ent[0])
+                lparts.append(ent[1])
+                pw = beam.partial_word
+                if pw:
+                    e = table[pw]
+                    col_ph.append(e[2])
+                    col_pl.append(e[3])
+                else:
+                    col_ph.append(0)
+                    col_pl.append(0)
+                col_lg.append(beam.logit_score)
+                col_off.append(off)
+                col_nw.append(ent[2])
+                lc = beam.last_char
+                col_lt.append(0xFFFF if lc is None else (ids[lc] if lc in ids else self._token_id(handle, lc)))
+                pf = beam.partial_frames
+                col_s.append(pf[0])
+                col_e.append(pf[1])
+                off += ent[2]
+            starts.append((row0, r - row0, n_words_total, off))
+            n_words_total += off
+        a_rows = np.zeros(max(1, n_rows), dtype=self._SB_DTYPE)
+        if n_rows:
+            for name, col in (("part_hash", col_ph), ("logit", col_lg), ("word_off", col_off), ("n_words", col_nw), ("part_len", col_pl),
+                              ("last_tok", col_lt), ("pf_s", col_s), ("pf_e", col_e)):
+                a_rows[name] = col
+        a_wh = np.frombuffer(b"".join(hparts) or b"\x00" * 8, dtype=np.uint64)
+        a_wl = np.frombuffer(b"".join(lparts) or b"\x00" * 4, dtype=np.uint32)
+        assert a_rows.itemsize == C.sizeof(_lib.StreamBeam)
         states = (_lib.StreamState * len(stream))()
-        for u, (beams, processed_frames) in enumerate(stream):
-            rows = (_lib.StreamBeam * max(1, len(beams)))()
-            wh: List[int] = []
-            wl: List[int] = []
-            for b, beam in enumerate(beams):
-                words = _merge_tokens(beam.text, beam.next_word).split()
-                row = rows[b]
-                row.word_off, row.n_words = len(wh), len(words)
-                for w in words:
-                    h, n = hash_of(w)
-                    wh.append(h)
-                    wl.append(n)
-                row.part_hash, row.part_len = hash_of(beam.partial_word) if beam.partial_word else (0, 0)
-                row.logit_score = float(beam.logit_score)
-                row.last_tok = self._token_id(handle, beam.last_char)
-                row.pf_s, row.pf_e = int(beam.partial_frames[0]), int(beam.partial_frames[1])
-            a_wh = (C.c_uint64 * max(1, len(wh)))(*wh)
-            a_wl = (C.c_uint32 * max(1, len(wl)))(*wl)
-            keep_alive.extend([rows, a_wh, a_wl])
-            states[u].beams = rows
-            states[u].n_beams = len(beams)
-            states[u].processed_frames = int(processed_frames)
-            states[u].word_hashes = a_wh
-            states[u].word_lens = a_wl
-            states[u].n_words = len(wh)
-        keep_alive.append(states)
+        p_rows, p_wh, p_wl = a_rows.ctypes.data, a_wh.ctypes.data, a_wl.ctypes.data
+        for u, ((_, processed_frames), (row0, n_beams, word0, n_words)) in enumerate(zip(stream, starts)):
+            st = states[u]
+            st.beams = C.cast(p_rows + row0 * a_rows.itemsize, C.POINTER(_lib.StreamBeam))
+            st.n_beams = n_beams
+            st.processed_frames = int(processed_frames)
+            st.word_hashes = C.cast(p_wh + 8 * word0, C.POINTER(C.c_uint64))
+            st.word_lens = C.cast(p_wl + 4 * word0, C.POINTER(C.c_uint32))
+            st.n_words = n_words
+        keep_alive.extend([a_rows, a_wh, a_wl, states])
         return states
 
-    def _stream_results(self, res: Any, u: int, roots: Sequence[Beam], finalize_mode: int) -> List[LMBeam]:
-        """Replay what the call appended (token chain since the input beam, frames of the words finished during
-        the call) onto the input beams' strings -> LMBeam list (reference _finalize_beams output)."""
+    @staticmethod
+    def _new_lm_beam(text: str, partial: str, last_char: Optional[str], frames: List[Frames], pframes: Frames, logit: float,
+                     lm: float) -> LMBeam:
+        # LMBeam(text, "", partial, last_char, frames, pframes, logit, lm) without the eight object.__setattr__ calls of
+        # a frozen dataclass's __init__ (a streaming call returns thousands of beams)
+        beam = LMBeam.__new__(LMBeam)
+        beam.__dict__.update(text=text, next_word="", partial_word=partial, last_char=last_char, text_frames=frames,
+                             partial_frames=pframes, logit_score=logit, lm_score=lm)
+        return beam
+
+    def _stream_results(self, res: Any, stream: Sequence[Tuple[Sequence[Beam], int]], finalize_mode: int) -> List[List[LMBeam]]:
+        """What the call appended (the token chain since the input beam, replayed into strings by the library; frames of
+        the words finished during the call) on top of the input beams' strings -> LMBeam lists (reference
+        _finalize_beams output)."""
         L = _lib.lib()
+        pk = _lib.Packed()
+        _lib.check(L.b2c_result_packed(res, C.byref(pk)))
+        nb_total, nw_total = int(pk.n_beams_total), int(pk.n_words_total)
+        counts = np.ctypeslib.as_array(pk.n_beams, shape=(pk.n_utts,)).tolist() if pk.n_utts else []
+        if nb_total == 0:
+            return [[] for _ in counts]
+        scores = np.ctypeslib.as_array(pk.scores, shape=(2 * nb_total,)).tolist()
+        n_frames = np.ctypeslib.as_array(pk.n_words, shape=(nb_total,)).tolist()
+        aux = np.ctypeslib.as_array(pk.stream_aux, shape=(4 * nb_total,)).tolist()
+        boundary = np.ctypeslib.as_array(pk.stream_boundary, shape=(nb_total,)).tolist()
+        pieces = C.string_at(pk.stream_pieces, pk.stream_pieces_size).decode("utf-8").split("\x00")
+        if nw_total:
+            fr = np.ctypeslib.as_array(pk.frames, shape=(2 * nw_total,)).tolist()
+            pairs = list(zip(fr[0::2], fr[1::2]))
+        else:
+            pairs = []
         labels = self._alphabet.labels
-        out: List[LMBeam] = []
-        aux = (C.c_int32 * 4)()
-        toks = C.POINTER(C.c_uint32)()
-        n_toks = C.c_int()
-        for b in range(L.b2c_result_n_beams(res, u)):
-            _lib.check(L.b2c_result_stream_beam(res, u, b, C.byref(aux), C.byref(toks), C.byref(n_toks)))
-            root = roots[aux[0]] if aux[0] >= 0 else EMPTY_START_BEAM
-            text, partial = _merge_tokens(root.text, root.next_word), root.partial_word
-            for q in range(n_toks.value):
-                tok, kind = toks[q] & 0xFFFF, toks[q] >> 16
-                label = labels[tok]
-                if kind == 0:                       # branch (iv): the partial word grows
-                    partial += label
-                    continue
-                text = _merge_tokens(text, partial)  # branches (ii) / (iii): word boundary
-                partial = ""
-                if kind == 2:                       # BPE piece that starts a word (decoder.py:476-484)
-                    partial = label[1:] if label[:1] == "\u2581" else label
-                    if partial[-1:] == "\u2581":
-                        partial = partial[:-1]
-            fr = L.b2c_result_frames(res, u, b)
-            frames = list(root.text_frames) + [(fr[2 * w], fr[2 * w + 1]) for w in range(L.b2c_result_n_frames(res, u, b))]
-            logit, lm = L.b2c_result_logit_score(res, u, b), L.b2c_result_lm_score(res, u, b)
-            if finalize_mode == _lib.FIN_KEEP:
-                last_char = None if aux[1] < 0 else labels[aux[1]]
-                out.append(LMBeam(text, "", partial, last_char, frames, (int(aux[2]), int(aux[3])), logit, lm))
+        keep = finalize_mode == _lib.FIN_KEEP
+        table = self._word_hash
+        c0, c1 = self._text_cache
+        spaced = self._labels_with_space
+        new_beam = self._new_lm_beam
+        pending: Dict[str, Tuple[Tuple[bytes, bytes, int], List[str]]] = {}     # new text -> (entry of the root text, appended words)
+        missing: Dict[str, None] = {}
+        out: List[List[LMBeam]] = []
+        k = wi = 0
+        for u, nb in enumerate(counts):
+            roots = stream[u][0]
+            beams = []
+            for _ in range(nb):
+                a0 = aux[4 * k]
+                root = roots[a0] if a0 >= 0 else EMPTY_START_BEAM
+                root_text = root.text if not root.next_word else _merge_tokens(root.text, root.next_word)
+                first, mid, last = pieces[3 * k], pieces[3 * k + 1], pieces[3 * k + 2]
+                if boundary[k]:
+                    word0 = root.partial_word + first
+                    text = root_text
+                    if word0:                           # branches (ii) / (iii): a word boundary finishes the partial word
+                        text = text + " " + word0 if text else word0
+                    if mid:
+                        text = text + " " + mid if text else mid
+                    partial = last
+                else:                                   # branch (iv) only: the partial word grew
+                    text, partial = root_text, root.partial_word + first
+                nf = n_frames[k]
+                frames = list(root.text_frames) + pairs[wi:wi + nf] if nf else list(root.text_frames)
+                wi += nf
+                if keep:
+                    a1 = aux[4 * k + 1]
+                    beams.append(new_beam(text, partial, None if a1 < 0 else labels[a1], frames, (aux[4 * k + 2], aux[4 * k + 3]),
+                                          scores[2 * k], scores[2 * k + 1]))
+                    if text not in pending:
+                        ent = c0.get(root_text)
+                        if ent is None:
+                            ent = c1.get(root_text)
+                        if ent is None and not root_text:
+                            ent = (b"", b"", 0)
+                        if ent is not None:
+                            added: List[str] = []
+                            if boundary[k]:
+                                if word0:
+                                    added.append(word0)
+                                if mid:
+                                    added.extend(mid.split(" "))
+                            # labels with white space inside would make text.split() disagree with the word list
+                            if not spaced or all(len(w.split()) == 1 for w in added):
+                                pending[text] = (ent, added)
+                                for w in added:
+                                    if w not in table:
+                                        missing[w] = None
+                else:
+                    beams.append(new_beam(_merge_tokens(text, partial), "", None, frames, NULL_FRAMES, scores[2 * k], scores[2 * k + 1]))
+                k += 1
+            out.append(beams)
+        # the texts this call returned are the texts the next call brings back: their word hashes, incrementally
+        self._hash_words(list(missing))
+        fresh: Dict[str, Tuple[bytes, bytes, int]] = {}
+        for text, (ent, added) in pending.items():
+            if added:
+                fresh[text] = (ent[0] + b"".join([table[w][0] for w in added]), ent[1] + b"".join([table[w][1] for w in added]),
+                               ent[2] + len(added))
             else:
-                out.append(LMBeam(_merge_tokens(text, partial), "", "", None, frames, NULL_FRAMES, logit, lm))
+                fresh[text] = ent
+        self._text_cache = [fresh, c0]
         return out
 
     def partial_decode_beams(self, logits: Any, cached_lm_scores: LMScoreCache, cached_p_lm_scores: Dict[str, float],
