@@ -55,7 +55,7 @@ static int fail(int code, const std::string& msg) {
 static inline u64 al16(u64 x) { return (x + 15) & ~15ull; }
 static inline u64 tab_bytes(int W) { return 6 * al16(8ull * W) + 4 * al16(4ull * W) + 2 * al16(2ull * W) + 64; }
 static inline u64 sel_bytes(int W, int n_warps, int nb) { return al16(8ull * W) + 2 * al16(4ull * W) + 2 * al16(4ull * pt_cap_for(W)) + 2 * al16(4ull * nb) +
-           (nb == B2C_NBUCKET ? al16(4ull * B2C_NBUCKET * n_warps) : al16(4ull * (nb + 8))) +
+           (nb == B2C_NBUCKET ? al16(4ull * B2C_NBUCKET * n_warps) : al16(4ull * (nb + 32))) +
            al16(sizeof(B2cTok) * B2C_STAGE_K) + al16(8ull * B2C_STAGE_K) + al16(4ull * B2C_STAGE_K) + 64; }
 static inline u64 tier_bytes(u32 cap, u32 ht) { return al16(8ull * cap) * 4 + al16(4ull * cap) * 4 + al16(4ull * ht) * 4 + 64; }
 
@@ -783,6 +783,7 @@ static int launch_beam(b2c_decoder* d, const B2cBeamArgs& A, int slots, bool fas
     else if (fast && threads == 256) B2C_LAUNCH_BEAM(true, 256, 1);    // 255 registers x 256 threads: the whole register file
     else if (fast && threads == 64) B2C_LAUNCH_BEAM(true, 64, 4);     // 255 registers x 64 threads: 4 CTAs per SM
     else if (fast) B2C_LAUNCH_BEAM(true, 128, 2);                 // 255 registers x 128 threads: 2 CTAs per SM
+    else if (threads == 512) B2C_LAUNCH_BEAM(false, 512, 1);      // 128 registers x 512 threads (beam tables in HBM: latency-bound)
     else if (threads == 256) B2C_LAUNCH_BEAM(false, 256, 1);
     else B2C_LAUNCH_BEAM(false, 128, 2);
 #undef B2C_LAUNCH_BEAM
@@ -1506,7 +1507,7 @@ static int decode_batch_locked(b2c_decoder_t* d, const void* const* logits, cons
     };
     auto per_sm_of = [&](u32 smem_bytes, int threads) {
         const int by_smem = static_cast<int>(std::max<u64>(1, (224 * 1024) / std::max<u32>(smem_bytes + 1024, 2048)));
-        return std::min(by_smem, threads == 32 ? 8 : (threads == 64 ? 4 : (threads == 256 ? 1 : 2)));
+        return std::min(by_smem, threads == 32 ? 8 : (threads == 64 ? 4 : (threads >= 256 ? 1 : 2)));
     };
     bool cap_ok[kNumCaps];
     for (int c = 0; c < kNumCaps; ++c) cap_ok[c] = layout_of(c, 1, false, 0).smem_bytes <= smem_budget;
@@ -1648,6 +1649,10 @@ static int decode_batch_locked(b2c_decoder_t* d, const void* const* logits, cons
         // the general kernel with room for one CTA per SM only (wide beams): that CTA gets the whole register file --
         // its phases are loops over hundreds to thousands of candidates, each a chain of dependent memory accesses
         if (cls == kNumCaps && per_sm_of(ln.L.smem_bytes, 128) == 1) ln.threads = 256;
+        // beam tables that do not fit shared memory (beam_width in the thousands) live in HBM: every phase is a chain of L2
+        // round trips, and twice the threads at half the registers hide more of them (measured at beam 2000 on the C2
+        // shape: 56 -> 49 ms; with the tables in shared memory, beam 500, the spills cost more than they hide: 19 -> 22 ms)
+        if (cls == kNumCaps && ln.threads == 256 && !ln.L.beams_in_smem) ln.threads = 512;
         ln.per_sm = per_sm_of(ln.L.smem_bytes, ln.threads);
         }
         ln.slots = std::min(ln.count, d->n_sm * ln.per_sm);

@@ -100,7 +100,7 @@ struct B2cWork {
     u32 n_bucket;        // B2C_NBUCKET or B2C_NBUCKET_WIDE
     u32* bcnt;           // [n_bucket] leaders per score bucket
     u32* bhead;          // [n_bucket] list heads
-    u32* bpre;           // exclusive prefix: [n_warps][B2C_NBUCKET], one private copy per warp, or ONE [B2C_NBUCKET_WIDE + 8]
+    u32* bpre;           // exclusive prefix: [n_warps][B2C_NBUCKET], one private copy per warp, or ONE [B2C_NBUCKET_WIDE + 32]
     // label records / log-probs / ids of the current frame's tokens, staged once per frame (frames of up to
     // B2C_STAGE_K tokens; nullptr: no staging area, e.g. the out-of-line step of the latency-first kernel)
     B2cTok* stok;
@@ -204,7 +204,7 @@ B2C_HD void b2c_make_work(const B2cLayout& L, u8* smem, u8* g, int parity, bool 
         W.n_bucket = static_cast<u32>(L.n_bucket);
         W.bcnt = reinterpret_cast<u32*>(b2c_carve(p, 4ull * L.n_bucket));
         W.bhead = reinterpret_cast<u32*>(b2c_carve(p, 4ull * L.n_bucket));
-        W.bpre = reinterpret_cast<u32*>(b2c_carve(p, L.n_bucket == B2C_NBUCKET ? 4ull * B2C_NBUCKET * L.n_warps : 4ull * (L.n_bucket + 8)));
+        W.bpre = reinterpret_cast<u32*>(b2c_carve(p, L.n_bucket == B2C_NBUCKET ? 4ull * B2C_NBUCKET * L.n_warps : 4ull * (L.n_bucket + 32)));
         W.stok = reinterpret_cast<B2cTok*>(b2c_carve(p, sizeof(B2cTok) * B2C_STAGE_K));
         W.slp = reinterpret_cast<double*>(b2c_carve(p, 8ull * B2C_STAGE_K));
         W.sid = reinterpret_cast<u32*>(b2c_carve(p, 4ull * B2C_STAGE_K));
@@ -460,17 +460,34 @@ B2C_HD void b2c_fence_block() {
 // (store, fence) before its CAS.
 B2C_HD void b2c_group_insert(const B2cCandTier& C, u32 hmask, u32 i, u64 key) {
     u32 slot = static_cast<u32>(b2c_mix64(key)) & hmask;
+    bool claimed = false;
     while (true) {
         const u32 rep = b2c_atomic_cas_u32(&C.ht_idx[slot], B2C_NONE_U32, i);
-        if (rep == B2C_NONE_U32) break;
+        if (rep == B2C_NONE_U32) { claimed = true; break; }
         b2c_fence_block();
         if (C.ckey[rep] == key) break;
         slot = (slot + 1) & hmask;
     }
     C.cslot[i] = slot;
-    b2c_atomic_min_u32(&C.ht_min[slot], i);
-    b2c_atomic_max_u32(&C.ht_max[slot], i);
-    b2c_atomic_add_u32(&C.ht_cnt[slot], 1u);
+    // the member that claimed the slot is known from ht_idx; only JOINERS (merges: a few percent of the candidates) pay
+    // for the three atomics that track the group's extent
+    if (!claimed) {
+        b2c_atomic_min_u32(&C.ht_min[slot], i);
+        b2c_atomic_max_u32(&C.ht_max[slot], i);
+        b2c_atomic_add_u32(&C.ht_cnt[slot], 1u);
+    }
+}
+// first / last member and size of the group in `slot` (after the barrier that ends the insert phase)
+B2C_HD void b2c_group_extent(const B2cCandTier& C, u32 slot, u32& first, u32& last, u32& cnt) {
+    const u32 rep = C.ht_idx[slot], joined = C.ht_cnt[slot];
+    first = rep;
+    last = rep;
+    cnt = joined + 1;
+    if (joined) {
+        const u32 lo = C.ht_min[slot], hi = C.ht_max[slot];
+        if (lo < first) first = lo;
+        if (hi > last) last = hi;
+    }
 }
 
 // clear the grouping table (first H slots) and the score buckets for the next frame; called in
@@ -562,7 +579,7 @@ B2C_HD void b2c_bucket_scan_warp(const u32* bcnt, u32* pre) {
 }
 
 // the same for B2C_NBUCKET_WIDE buckets: ONE copy computed by the whole CTA (two block barriers inside; nb is a multiple
-// of 4 * blockDim.x); pre[nb .. nb + 8) is scratch for the warp totals
+// of 4 * blockDim.x); pre[nb .. nb + 32) is scratch for the warp totals
 B2C_HD void b2c_bucket_scan_block(const u32* bcnt, u32* pre, u32 nb) {
 #if defined(__CUDA_ARCH__)
     const u32 tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -789,8 +806,9 @@ B2C_HD void b2c_frame_step(const B2cParams& P, B2cWork& W, int t, const u32* tk_
         u64 tmax = 0;
         B2C_FOR(i, M) {
             const u32 slot = C.cslot[i];
-            if (C.ht_min[slot] != static_cast<u32>(i)) { C.ckey[i] = 0; continue; }
-            const u32 last = C.ht_max[slot], cnt = C.ht_cnt[slot];
+            u32 first, last, cnt;
+            b2c_group_extent(C, slot, first, last, cnt);
+            if (first != static_cast<u32>(i)) { C.ckey[i] = 0; continue; }
             // members of a group normally share the token; tokens with identical label strings
             // (string compare in the reference) may merge across tokens, so decode every index
             u32 k0, b0, kl, bl;
@@ -1221,8 +1239,9 @@ B2C_HDN void b2c_finalize(B2cParams P, B2cWork W, B2cOut O, int fin_mode) {
     B2C_SYNC();
     B2C_FOR(b, n) {
         const u32 slot = C.cslot[b];
-        if (C.ht_min[slot] != static_cast<u32>(b)) { C.ckey[b] = 0; continue; }
-        const u32 last = C.ht_max[slot];
+        u32 first, last, cnt;
+        b2c_group_extent(C, slot, first, last, cnt);
+        if (first != static_cast<u32>(b)) { C.ckey[b] = 0; continue; }
         double s = cur.logit[b];
         for (u32 j = static_cast<u32>(b) + 1; j <= last; ++j)
             if (C.cslot[j] == slot) s = b2c_sum_log_scores(s, cur.logit[j]);

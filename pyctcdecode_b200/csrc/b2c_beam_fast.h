@@ -418,17 +418,20 @@ B2C_HD void b2c_fast_step(const B2cParams& P, B2cFastSmem<WC, CAP, LT>& S, B2cCh
             b2c_fence_block();
             // group equal keys: claim a slot or join the group that owns it
             u32 slot = static_cast<u32>(key) & hmask;
+            bool claimed = false;
             while (true) {
                 const u32 rep = b2c_atomic_cas_u32(&S.ht_idx[slot], B2C_NONE_U32, i);
-                if (rep == B2C_NONE_U32) break;
+                if (rep == B2C_NONE_U32) { claimed = true; break; }
                 b2c_fence_block();
                 if (S.ckey[rep] == key) break;
                 slot = (slot + 1) & hmask;
             }
             S.cslot[i] = slot;
-            b2c_atomic_min_u32(&S.ht_min[slot], i);
-            b2c_atomic_max_u32(&S.ht_max[slot], i);
-            b2c_atomic_add_u32(&S.ht_cnt[slot], 1u);
+            if (!claimed) {      // the claimer is known from ht_idx: only joiners (merges) track the group's extent
+                b2c_atomic_min_u32(&S.ht_min[slot], i);
+                b2c_atomic_max_u32(&S.ht_max[slot], i);
+                b2c_atomic_add_u32(&S.ht_cnt[slot], 1u);
+            }
         }
     }
     B2C_SYNC();
@@ -446,8 +449,14 @@ B2C_HD void b2c_fast_step(const B2cParams& P, B2cFastSmem<WC, CAP, LT>& S, B2cCh
         u64 tmax = 0;
         B2C_FOR(i, M) {
             const u32 slot = S.cslot[i];
-            if (S.ht_min[slot] != static_cast<u32>(i)) { S.ckey[i] = 0; continue; }
-            const u32 last = S.ht_max[slot], cnt = S.ht_cnt[slot];
+            u32 first = S.ht_idx[slot], last = first;
+            const u32 cnt = S.ht_cnt[slot] + 1;
+            if (cnt > 1) {
+                const u32 lo = S.ht_min[slot], hi = S.ht_max[slot];
+                first = lo < first ? lo : first;
+                last = hi > last ? hi : last;
+            }
+            if (first != static_cast<u32>(i)) { S.ckey[i] = 0; continue; }
             double s = S.cfold[i];
             for (u32 j = (cnt == 2) ? last : static_cast<u32>(i) + 1; cnt > 1 && j <= last; ++j) {
                 if (S.cslot[j] != slot) continue;
