@@ -390,7 +390,7 @@ def secondary_entry(torch, pkg, flush, name, spec, regime, beam, logits_dtype, c
     dec = pkg.build_ctcdecoder(wl.labels, device=torch.cuda.current_device(), **kw)
     st = Stepper(torch, None, dec, wl.batch(1, B, T, regime), beam, hot, logits_dtype, call)
     total, tms, out = st.timed(st.step_dev, steps, warmup, flush)
-    e2e_total, e2e_tms, out_e2e = st.timed(st.step_host, steps, 1, flush)
+    e2e_total, e2e_tms, out_e2e = st.timed(st.step_host, steps, warmup, flush)
     same = out == out_e2e
     frames = B * T
     peak = float(load_peaks().get("hbm_gbs", 6650.0))
@@ -647,7 +647,7 @@ def main():
         sampler.start()
     total, tms, texts = st.timed(st.step_dev, args.steps, args.warmup, flush)
     clocks = sampler.stop() if rank == 0 else None
-    e2e_total, e2e_tms, texts_e2e = st.timed(st.step_host, args.steps, 1, flush)
+    e2e_total, e2e_tms, texts_e2e = st.timed(st.step_host, args.steps, args.warmup, flush)   # the same W warm-up steps as the device-resident arm
     assert texts == texts_e2e
     if args.call != "decode_batch":
         texts = [beams[0].text if beams else "" for beams in texts]
