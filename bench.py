@@ -42,6 +42,10 @@ WORKLOADS = {
     "c3": dict(kind="char", vocab="B", n_words=20000, lm_order=3, T=1000, batch=1024, beam=100,
                lm=dict(alpha=0.5, beta=1.0), hot=0,
                name="Wav2Vec2-base V=32, T=1000, beam=100 + synthetic 3-gram (alpha=0.5,beta=1.0), batch=1024 per GPU"),
+    # opt-in (--secondary c3_biglm): the C3 shape with a ~10^7 n-gram model, i.e. tables several times the 126 MB L2
+    "c3_biglm": dict(kind="char", vocab="B", n_words=420000, lm_order=3, T=1000, batch=1024, beam=100,
+                     lm=dict(alpha=0.5, beta=1.0), hot=0,
+                     name="C3 shape + synthetic 3-gram over 420k words (~10^7 n-grams: tables several times the L2), batch=1024 per GPU"),
     "c4": dict(kind="bpe", n_words=50000, lm_order=4, T=500, batch=512, beam=100, lm=dict(alpha=0.5, beta=1.0), hot=16,
                name="Conformer-CTC BPE V=1024, T=500, beam=100 + synthetic 4-gram + 16 hotwords, batch=512 per GPU"),
 }
@@ -386,8 +390,11 @@ def secondary_entry(torch, pkg, flush, name, spec, regime, beam, logits_dtype, c
     """one more BASELINE.json configuration on one GPU: value / e2e / kernel times / CPU figure / transcript identity"""
     t_start = time.perf_counter()
     wl, kw, hot = workload_objects(spec)
+    t_gen = time.perf_counter() - t_start
     B, T = batch or spec["batch"], spec["T"]
+    t_b = time.perf_counter()
     dec = pkg.build_ctcdecoder(wl.labels, device=torch.cuda.current_device(), **kw)
+    t_build = time.perf_counter() - t_b
     st = Stepper(torch, None, dec, wl.batch(1, B, T, regime), beam, hot, logits_dtype, call)
     total, tms, out = st.timed(st.step_dev, steps, warmup, flush)
     e2e_total, e2e_tms, out_e2e = st.timed(st.step_host, steps, warmup, flush)
@@ -414,6 +421,15 @@ def secondary_entry(torch, pkg, flush, name, spec, regime, beam, logits_dtype, c
            "cpu_baseline": info,
            "transcripts_identical_to_oracle": "%d/%d" % (sum(a == b for a, b in zip(cpu_texts, texts[:n])), n),
            "wall_s": None}
+    if spec["lm_order"]:
+        try:        # how big the flattened model is (what one NCCL broadcast ships) and how long building it took
+            with open(wl.arpa, encoding="utf-8") as fh:
+                counts = [int(ln.split("=")[1]) for ln in (fh.readline() for _ in range(12)) if ln.startswith("ngram ")]
+            ent["lm"] = {"ngrams": counts, "arpa_mb": round(os.path.getsize(wl.arpa) / 1e6, 1),
+                         "blob_mb": round(dec._language_model._kenlm_model.blob()[1] / 1e6, 1),
+                         "build_decoder_s": round(t_build, 2), "generate_arpa_s": round(t_gen, 1)}
+        except Exception as exc:
+            ent["lm"] = {"error": repr(exc)}
     del st, dec
     torch.cuda.empty_cache()
     ent["wall_s"] = round(time.perf_counter() - t_start, 1)
@@ -577,7 +593,7 @@ def main():
     ap.add_argument("--beam", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary configurations (1 GPU) / the strong-scaling section (N > 1)")
-    ap.add_argument("--secondary", default="", help="comma separated subset of: c3,c4,c4_f16,diffuse,beam10,beam50,beam500,beam2000,beams_batch,stream1,stream64,stream64_lm")
+    ap.add_argument("--secondary", default="", help="comma separated subset of: c3,c4,c4_f16,diffuse,beam10,beam50,beam500,beam2000,beams_batch,stream1,stream64,stream64_lm; opt-in: c3_biglm")
     ap.add_argument("--secondary-steps", type=int, default=5)
     ap.add_argument("--call", default="decode_batch", choices=["decode_batch", "decode_beams_batch"])
     ap.add_argument("--logits-dtype", default="f32", choices=["f32", "f16"],
@@ -743,6 +759,8 @@ def main():
                 ("beam2000", WORKLOADS["c2"], "peaky", 2000, "f32", "decode_batch", 0),
                 ("beams_batch", WORKLOADS["c2"], "peaky", 100, "f32", "decode_beams_batch", 0)]
         want = [w for w in args.secondary.split(",") if w]
+        if "c3_biglm" in want:     # opt-in only: generating and loading the 10^7 n-gram model takes minutes
+            plan.append(("c3_biglm", WORKLOADS["c3_biglm"], "peaky", 100, "f32", "decode_batch", 0))
         out["secondary"] = []
         for name, sp, regime, bm, dt, call, bsz in plan:
             if want and name not in want:

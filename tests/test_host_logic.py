@@ -84,6 +84,22 @@ def test_cuda_library_exports_every_declared_symbol():
     assert "sm_100a" in out
 
 
+def test_batched_string_hash_equals_the_single_call():
+    """b2c_hash_utf8_batch (one call for all the new words of a streaming call) == b2c_hash_utf8 per string."""
+    import ctypes as C
+    from pyctcdecode_b200 import _lib
+    L = _lib.lib()
+    words = ["a", "hello", "", "\u2581na\u00efve", "\u4e16\u754c", "x" * 300]
+    data = b"".join(w.encode("utf-8") + b"\x00" for w in words)
+    hs, ns = (C.c_uint64 * len(words))(), (C.c_uint32 * len(words))()
+    assert L.b2c_hash_utf8_batch(data, len(data), len(words), hs, ns) == 0
+    for i, w in enumerate(words):
+        h, n = C.c_uint64(), C.c_uint32()
+        assert L.b2c_hash_utf8(w.encode("utf-8"), C.byref(h), C.byref(n)) == 0
+        assert (hs[i], ns[i]) == (h.value, n.value) and n.value == len(w)
+    assert L.b2c_hash_utf8_batch(data[:-1], len(data) - 1, len(words), hs, ns) != 0      # the last string is not terminated
+
+
 def test_product_fails_loudly_without_gpu_or_library(monkeypatch):
     """No CPU fallback: in this container (no CUDA device) creating a decoder handle must raise."""
     import pyctcdecode_b200 as pkg

@@ -202,6 +202,52 @@ def test_hostsim_streaming_chunks_equal_whole(sim):
                 assert abs(o.lm_score - g.lm_score) <= 1e-9 * max(1.0, abs(o.lm_score))
 
 
+def test_hostsim_streaming_host_caches_are_transparent(sim):
+    """The streaming host path keeps word hashes per word and per returned text (decoder.py, _stream_states): the
+    results must not depend on what the caches hold -- two streams interleaved on one decoder, beams re-wrapped as new
+    Beam objects, and a decoder that receives another decoder's beams mid-stream (every text misses its cache) all
+    give the beams of an undisturbed run, call by call."""
+    from pyctcdecode_b200.decoder import Beam
+    for fam in ("B_nolm", "B_3gram", "C_bpe_4gram"):
+        wkw, lmkw = FAMILIES[fam]
+        wl = synth.make_workload(wkw)
+        kw = dict(lmkw)
+        if wl.arpa:
+            kw.update(kenlm_model_path=wl.arpa, unigrams=wl.words)
+        T = 120 if wl.V <= 64 else 60
+        bounds = list(range(0, T, 20)) + [T]
+        xs = [wl.utterance(9300 + i, T, "peaky") for i in range(2)]
+
+        def run(dec_for_call, rewrap):
+            outs = []
+            for i, x in enumerate(xs):
+                beams, cache, pcache = dec_for_call(0, i).get_starting_state()
+                calls = []
+                for c, (a, b) in enumerate(zip(bounds[:-1], bounds[1:])):
+                    got = dec_for_call(c, i).partial_decode_beams(x[a:b], cache, pcache, beams, a, beam_width=24, is_end=(b == T))
+                    calls.append(got)
+                    beams = [Beam.from_lm_beam(g) for g in got] if rewrap else got
+                outs.append(calls)
+            return outs
+
+        plain = sim.build_ctcdecoder(wl.labels, **kw)
+        want = run(lambda c, i: plain, False)
+        # (a) re-wrapped beams, (b) a different decoder every other call: its caches have never seen the texts
+        a, b = sim.build_ctcdecoder(wl.labels, **kw), sim.build_ctcdecoder(wl.labels, **kw)
+        assert run(lambda c, i: a, True) == want
+        assert run(lambda c, i: (a, b)[c % 2], False) == want
+        # (c) the two streams interleaved call by call on ONE decoder (each call evicts half of the other stream's texts)
+        dec = sim.build_ctcdecoder(wl.labels, **kw)
+        st = [dec.get_starting_state() for _ in xs]
+        beams = [s_[0] for s_ in st]
+        got = [[] for _ in xs]
+        for a_, b_ in zip(bounds[:-1], bounds[1:]):
+            for i, x in enumerate(xs):
+                beams[i] = dec.partial_decode_beams(x[a_:b_], st[i][1], st[i][2], beams[i], a_, beam_width=24, is_end=(b_ == T))
+                got[i].append(beams[i])
+        assert got == want
+
+
 def test_hostsim_lm_blob_file_roundtrip(sim, tmp_path):
     """NgramModel.save_blob / build_ctcdecoder(kenlm_model_path="*.b2clm") (cached flattened LM):
     the decoder built from the blob file decodes exactly like the one built from the ARPA file."""
