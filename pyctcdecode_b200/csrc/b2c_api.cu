@@ -1218,6 +1218,7 @@ static int decode_batch_locked(b2c_decoder_t* d, const void* const* logits, cons
     P.beam_width = opts->beam_width;
     P.prune_history = opts->prune_history ? 1 : 0;
     P.out_beams = OB;
+    P.narrow_chain = (opts->text_only != 0 && !streaming) ? 1 : 0;
     P.prune_logp = opts->beam_prune_logp;
     P.token_min_logp = opts->token_min_logp;
     P.alpha = d->alpha; P.beta = d->beta; P.unk_offset = d->unk;

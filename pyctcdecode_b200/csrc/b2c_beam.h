@@ -680,7 +680,7 @@ B2C_HD void b2c_commit_one(const B2cParams& P, const B2cWork& W, const Tier& C, 
             c.has_word = word_len > 0 ? 1 : 0;
             c.ws = ps0;
             c.we = pe0;
-            W.chain[id] = c;
+            b2c_chain_store(W.chain, id, c, P.narrow_chain != 0);
             chain = id;
         } else {
             b2c_atomic_or_u32(&sc->status, B2C_ERR_CHAIN_FULL);
@@ -1036,7 +1036,7 @@ B2C_HD bool b2c_inplace_step(const B2cParams& P, const B2cWork& W, int t, int ki
                 c.has_word = 0;
                 c.ws = ps0;
                 c.we = pe0;
-                W.chain[id] = c;
+                b2c_chain_store(W.chain, id, c, P.narrow_chain != 0);
                 cur.chain[b] = id;
             } else {
                 b2c_atomic_or_u32(&sc->status, B2C_ERR_CHAIN_FULL);
@@ -1194,7 +1194,7 @@ B2C_HDN void b2c_utt_begin(B2cParams P, B2cWork W, const B2cLmState* start_state
         root.has_word = 0;
         root.ws = -1;
         root.we = -1;
-        W.chain[b] = root;
+        b2c_chain_store(W.chain, static_cast<u32>(b), root, P.narrow_chain != 0);
     }
     if (in.n_beams > 0) B2C_SYNC();
 }
@@ -1325,7 +1325,7 @@ B2C_HDN void b2c_finalize(B2cParams P, B2cWork W, B2cOut O, int fin_mode) {
         int root = -1;
         u32 node = cur.chain[last];
         while (node != B2C_NONE_U32 && nt < O.stride) {
-            const B2cChain c = W.chain[node];
+            const B2cChain c = b2c_chain_load(W.chain, node, P.narrow_chain != 0);
             if (c.kind == B2C_CK_ROOT) { root = static_cast<int>(c.tok); break; }
             toks[nt++] = static_cast<u32>(c.tok) | (static_cast<u32>(c.kind) << 16);
             if (c.kind != B2C_CK_CONT && c.has_word && nw < O.stride) {

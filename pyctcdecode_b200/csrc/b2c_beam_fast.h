@@ -313,7 +313,7 @@ B2C_HD void b2c_fast_commit(const B2cParams& P, B2cFastSmem<WC, CAP, LT>& S, con
         c.has_word = word_len > 0 ? 1 : 0;
         c.ws = ps0;
         c.we = pe0;
-        chain_arena[id] = c;
+        b2c_chain_store(chain_arena, id, c, P.narrow_chain != 0);
         chain = id;
     }
     nx.chain[j] = chain;
@@ -700,7 +700,7 @@ B2C_HD int b2c_fast_run_step(const B2cParams& P, B2cFastSmem<WC, CAP, LT>& S, B2
                 c.has_word = 0;
                 c.ws = pfs;
                 c.we = pfe;
-                chain_arena[id] = c;
+                b2c_chain_store(chain_arena, id, c, P.narrow_chain != 0);
                 chain = id;
                 ph = b2c_hash_append(ph, ti.raw_hash, ti.raw_pow);
                 plen += ti.raw_nchars;
@@ -792,7 +792,7 @@ B2C_HD bool b2c_fast_scored_step(const B2cParams& P, B2cFastSmem<WC, CAP, LT>& S
         cn.has_word = 0;
         cn.ws = ps0;
         cn.we = pe0;
-        chain_arena[id] = cn;
+        b2c_chain_store(chain_arena, id, cn, P.narrow_chain != 0);
         cur.chain[b] = id;
     }
     B2C_FOR(w, B2C_FAST_NW) { S.wmax[w] = w == 0 ? b2c_f64_key(top) : 0ull; }
@@ -970,7 +970,7 @@ B2C_HD bool b2c_fast_sorted_step(const B2cParams& P, B2cFastSmem<WC, CAP, LT>& S
             c.has_word = 0;
             c.ws = ps0;
             c.we = pe0;
-            chain_arena[id] = c;
+            b2c_chain_store(chain_arena, id, c, P.narrow_chain != 0);
             chain = id;
         }
         const u64 hh = cur.hist_hash[b];

@@ -177,6 +177,7 @@ struct B2cParams {
     int prune_history;
     int hist_n;                // max(1, lm order - 1)   (reference decoder.py:244)
     int out_beams;             // beams returned per utterance (1 for decode_batch)
+    int narrow_chain;          // text-only calls: 8-byte backtrack nodes (no word frames), b2c_chain_store / _load
     double prune_logp;
     double token_min_logp;
     double alpha, beta, unk_offset, log_base_change;
@@ -205,6 +206,29 @@ struct B2cChain {              // 16 bytes: one emitted (non-blank, non-repeat) 
     u8 has_word;               // boundary kinds: a finished word was flushed, frames valid
     int ws, we;                // frames of the flushed word
 };
+// Text-only calls (decode / decode_batch) never read the word frames: their nodes are the first 8 bytes only, packed
+// parent | tok << 32 | kind << 48 | has_word << 56, at index `id` of a u64 view of the same arena -- half the HBM
+// write traffic of the beam kernel (one node per emitted token of every surviving beam).
+B2C_HD void b2c_chain_store(B2cChain* arena, u32 id, const B2cChain& c, bool narrow) {
+    if (narrow) {
+        reinterpret_cast<u64*>(arena)[id] = static_cast<u64>(c.parent) | (static_cast<u64>(c.tok) << 32) |
+                                            (static_cast<u64>(c.kind) << 48) | (static_cast<u64>(c.has_word) << 56);
+    } else {
+        arena[id] = c;
+    }
+}
+B2C_HD B2cChain b2c_chain_load(const B2cChain* arena, u32 id, bool narrow) {
+    if (!narrow) return arena[id];
+    const u64 v = reinterpret_cast<const u64*>(arena)[id];
+    B2cChain c;
+    c.parent = static_cast<u32>(v);
+    c.tok = static_cast<u16>(v >> 32);
+    c.kind = static_cast<u8>(v >> 48);
+    c.has_word = static_cast<u8>(v >> 56);
+    c.ws = -1;
+    c.we = -1;
+    return c;
+}
 struct B2cText {               // one distinct "text" (sequence of finished words)
     u64 win[B2C_MAX_HIST];     // hashes of the last hist_n words, most recent first
     u64 hist_hash;

@@ -84,6 +84,12 @@ def fuzz(n_cases, seed):
         stats["sorted"] += tm["sorted_frames"]
         stats["frames"] += tm["frames"]
         ok = same(ref, got)
+        # the text-only call (decode: 8-byte backtrack nodes, no word frames) must give the top beam's text
+        if ok and rng.random() < 0.5:
+            dkw = {k: v for k, v in kw.items() if k != "prune_history"}
+            ok = dec.decode(x, **dkw) == (got[0].text if got and kw["prune_history"] else ora.decode(x, **dkw))
+            if not ok:
+                print("TEXT-ONLY", end=" ")
         # chunked streaming must end in the same beams -- for regular alphabets; with BPE the reference itself resets its
         # force_next_break flag at every call, so its chunked and whole results differ (checked against the reference:
         # the product reproduces the reference's CHUNKED result, tests/golden/stream_cases.json)
