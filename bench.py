@@ -713,6 +713,7 @@ def main():
         "beam_kernel_config": {"cap_candidates": tms[-1]["cap_candidates"], "cta_threads": tms[-1]["cta_threads"],
                                "resident_ctas": tms[-1]["cta_slots"], "oversize_frames_per_step": tms[-1]["oversize_frames"],
                                "kernel_variant": tms[-1]["kernel_variant"],
+                               "planned_from_previous_call_statistics": int(tms[-1].get("hinted", 0)),
                                "inplace_single_token_frames_per_step": tms[-1]["inplace_frames"],
                                "sorted_no_merge_frames_per_step": tms[-1]["sorted_frames"],
                                "frames_over_128_256_512_1024_2048_4096_total": tms[-1]["cand_hist"]},

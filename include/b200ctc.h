@@ -242,6 +242,8 @@ typedef struct {
     long long cand_hist[7];    /* frames with more than 128,256,...,4096 candidates; [6] = frames counted */
     long long inplace_frames;  /* single-token frames that updated the beam table in place (b2c_fast_cheap_step) */
     long long sorted_frames;   /* multi-token frames ranked by binary search, no grouping (b2c_fast_sorted_step) */
+    int hinted;                /* 1: the beam kernel was planned from the previous call's statistics and launched without
+                                  waiting for this call's (no mid-call synchronisation); same results either way */
 } b2c_timings_t;
 int b2c_decoder_last_timings(const b2c_decoder_t* dec, b2c_timings_t* out);
 

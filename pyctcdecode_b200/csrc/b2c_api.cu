@@ -547,7 +547,7 @@ struct b2c_decoder {
     size_t smem_optin = 48 * 1024;
     DevBuf d_raw, d_lmx, d_stream, d_mstats, d_sumk, d_clk, d_maxk, d_toks, d_logits, d_meta, d_tok_start, d_tok_ids, d_tok_lp, d_rowsum, d_set, d_isprob, d_approx, d_ws, d_hot, d_states,
         d_out_small, d_out_toks, d_out_frames;
-    PinBuf h_sumk, h_maxk, h_meta, h_out_small, h_out_toks, h_out_frames;
+    PinBuf h_sumk, h_maxk, h_meta, h_out_small, h_out_toks, h_out_frames, h_mstats;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaStream_t cls_stream[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // one per capacity class
     cudaEvent_t cls_done[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -563,6 +563,11 @@ struct b2c_decoder {
     bool pipe_refused = false;            // the last pipelined attempt of this configuration could not be planned
     double last_device_ms = 0.0;          // streaming stage + beam kernel of the previous call (chunk sizing of pipelined calls)
     int plain_v5 = -2, plain_cap = 0;     // kernel variant / capacity class of the last PLAIN call (pipelined calls must plan the same)
+    // hinted plain calls: the beam kernel is planned from the hint alone and launched right behind the streaming stage
+    // (no wait for this call's token statistics in the middle of the call) when that plan is the one the last
+    // statistics-based call of the configuration ran
+    bool hinted_refused = false;          // the hint-only plan differed: plan from the statistics until the next refresh
+    u32 hinted_calls = 0;                 // every 32nd call of a configuration plans from its statistics again (data may drift)
     std::mutex call_mu;                   // b2c_decode_batch is serialised per handle (scratch buffers are per handle)
     b2c_timings_t tm;
     // adaptive sizing: candidate-count histogram of the previous call with the same configuration
@@ -1055,7 +1060,7 @@ void b2c_decoder_destroy(b2c_decoder_t* d) {
     DevBuf* bufs[] = {&d->d_raw, &d->d_lmx, &d->d_stream, &d->d_mstats, &d->d_sumk, &d->d_clk, &d->d_maxk, &d->d_toks, &d->d_logits, &d->d_meta, &d->d_tok_start, &d->d_tok_ids, &d->d_tok_lp, &d->d_rowsum, &d->d_set,
                       &d->d_isprob, &d->d_approx, &d->d_ws, &d->d_hot, &d->d_states, &d->d_out_small, &d->d_out_toks, &d->d_out_frames};
     for (DevBuf* b : bufs) b->release();
-    PinBuf* pins[] = {&d->h_sumk, &d->h_maxk, &d->h_meta, &d->h_out_small, &d->h_out_toks, &d->h_out_frames};
+    PinBuf* pins[] = {&d->h_sumk, &d->h_maxk, &d->h_meta, &d->h_out_small, &d->h_out_toks, &d->h_out_frames, &d->h_mstats};
     for (PinBuf* b : pins) b->release();
     for (int i = 0; i < 6; ++i) if (d->ev[i]) cudaEventDestroy(d->ev[i]);
     for (int i = 0; i < 5; ++i) {
@@ -1329,6 +1334,8 @@ static int decode_batch_locked(b2c_decoder_t* d, const void* const* logits, cons
     for (int i = 0; i < n_utts && pipe_candidate; ++i)
         pipe_candidate = T[i] == T_max && static_cast<const char*>(logits[i]) == static_cast<const char*>(logits[0]) + static_cast<u64>(i) * T_max * V * esz_in;
     if (!hint_ok) d->pipe_refused = false;                       // another configuration: a new attempt may be planned
+    if (!hint_ok) { d->hinted_refused = false; d->hinted_calls = 0; }
+    static const bool no_hinted = std::getenv("B200CTC_NO_HINTED") != nullptr;
     if (pipe_candidate && d->d_logits.ensure(std::max<u64>(total_frames * V * esz, 16))) return B2C_E_NOMEM;
     const int chunk_len = ((T_max + B2C_PIPE_CHUNKS * B2C_TILE_ROWS - 1) / (B2C_PIPE_CHUNKS * B2C_TILE_ROWS)) * B2C_TILE_ROWS;
 
@@ -1466,6 +1473,7 @@ static int decode_batch_locked(b2c_decoder_t* d, const void* const* logits, cons
     CUDA_OK(cudaMemsetAsync(d->d_maxk.p, 0, 4ull * n_utts, st));
     CUDA_OK(cudaMemsetAsync(d->d_sumk.p, 0, 4ull * n_utts, st));
     int rc = 0;
+    bool hinted = false;
     if (!pipe_candidate) {
         CUDA_OK(cudaEventRecord(d->ev[1], st));
         rc = dtype == B2C_DTYPE_F32 ? launch_prepare<float>(d, PA, n_utts, grid_tile, grid_tok)
@@ -1478,18 +1486,27 @@ static int decode_batch_locked(b2c_decoder_t* d, const void* const* logits, cons
         CUDA_OK(cudaMemcpyAsync(d->h_maxk.p, d->d_maxk.p, 4ull * n_utts, cudaMemcpyDeviceToHost, st));
         CUDA_OK(cudaMemcpyAsync(d->h_sumk.p, d->d_sumk.p, 4ull * n_utts, cudaMemcpyDeviceToHost, st));
         hp_mark(0);                                   // argument checks, buffers, enqueue of H2D + prepare kernels
-        CUDA_OK(cudaStreamSynchronize(st));
-        hp_mark(1);                                   // wait: H2D + prepare kernels
-    } else {
-        // no statistics yet: the worst case (V tokens in a frame) sizes the workspace; the capacity class comes from
-        // the hint (one token per frame "on average" keeps the statistics-based bound out of its way)
-        for (int i = 0; i < n_utts; ++i) {
-            d->h_maxk.as<u32>()[i] = static_cast<u32>(V);
-            d->h_sumk.as<u32>()[i] = static_cast<u32>(T[i]);
+        // hinted plain call: plan now, from the hint alone, and launch the beam kernel right behind the streaming stage;
+        // if the plan is not the one the last statistics-based call ran, wait for the statistics after all (below)
+        hinted = allow_pipe && !no_hinted && hint_ok && !streaming && n_lm == 1 && opts->beam_width <= 128 && d->plain_v5 >= 0 &&
+                 (d->hinted_calls++ % 32u) != 31u && !d->hinted_refused;
+        if ((d->hinted_calls % 32u) == 0u) d->hinted_refused = false;       // the refresh call ran: try the hint again
+        if (!hinted) {
+            CUDA_OK(cudaStreamSynchronize(st));
+            hp_mark(1);                               // wait: H2D + prepare kernels
         }
     }
-    const u32* h_maxk = d->h_maxk.as<u32>();
-    const u32* h_sumk = d->h_sumk.as<u32>();
+    // without this call's statistics (pipelined and hinted calls): the worst case (V tokens in a frame) sizes the
+    // workspace; the capacity class comes from the hint (one token per frame "on average" keeps the statistics-based
+    // bound out of its way)
+    std::vector<u32> nostat_maxk, nostat_sumk;
+    if (pipe_candidate || hinted) {
+        nostat_maxk.assign(n_utts, static_cast<u32>(V));
+        nostat_sumk.resize(n_utts);
+        for (int i = 0; i < n_utts; ++i) nostat_sumk[i] = static_cast<u32>(T[i]);
+    }
+    const u32* h_maxk = nullptr;
+    const u32* h_sumk = nullptr;
     // ---- capacity class of the shared-memory candidate tier (ONE fast class per call) -------------
     // upper bound: sized for the TYPICAL frame of an utterance if all beam_width beams were alive
     // (2.5 x its mean tokens per frame, at least 4); with a hint from the previous call of the same
@@ -1512,10 +1529,13 @@ static int decode_batch_locked(b2c_decoder_t* d, const void* const* logits, cons
     };
     bool cap_ok[kNumCaps];
     for (int c = 0; c < kNumCaps; ++c) cap_ok[c] = layout_of(c, 1, false, 0).smem_bytes <= smem_budget;
-    std::vector<std::vector<int>> classes(kNumCaps + 1);   // fast classes (one used per call), last = general
+    std::vector<std::vector<int>> classes;                 // fast classes (one used per call), last = general
     bool use_v5 = false, use_lean = false;
     int v5_top = -1, v5_variant = 0;
-    {
+    auto classify = [&]() {
+        classes.assign(kNumCaps + 1, std::vector<int>());
+        use_v5 = false; use_lean = false;
+        v5_top = -1; v5_variant = 0;
         std::vector<int> cls_of(n_utts, kNumCaps);
         int top = -1, n_fast = 0;
         for (int u = 0; u < n_utts; ++u) {
@@ -1566,7 +1586,7 @@ static int decode_batch_locked(b2c_decoder_t* d, const void* const* logits, cons
             const int u = order[q];             // keeps longest-first order inside every class
             classes[cls_of[u] < kNumCaps ? top : kNumCaps].push_back(u);
         }
-    }
+    };
     B2cBeamArgs BA;
     std::memset(&BA, 0, sizeof(BA));
     BA.P = P;
@@ -1664,11 +1684,28 @@ static int decode_batch_locked(b2c_decoder_t* d, const void* const* logits, cons
     };
     std::vector<Launch> launches;
     size_t ord_used = 0;
-    for (int c = 0; c <= kNumCaps; ++c) {
-        if (classes[c].empty()) continue;
-        launches.push_back(plan(classes[c], c, false, ord_used));
-        for (int u : classes[c]) h_ord[ord_used++] = u;
+    auto plan_launches = [&](bool with_stats) {
+        h_maxk = with_stats ? d->h_maxk.as<u32>() : nostat_maxk.data();
+        h_sumk = with_stats ? d->h_sumk.as<u32>() : nostat_sumk.data();
+        classify();
+        launches.clear();
+        ord_used = 0;
+        for (int c = 0; c <= kNumCaps; ++c) {
+            if (classes[c].empty()) continue;
+            launches.push_back(plan(classes[c], c, false, ord_used));
+            for (int u : classes[c]) h_ord[ord_used++] = u;
+        }
+    };
+    plan_launches(!(pipe_candidate || hinted));
+    if (hinted && !(launches.size() == 1 && launches[0].v5 == d->plain_v5 && static_cast<int>(launches[0].L.cap_s) == d->plain_cap)) {
+        // not the plan the last statistics-based call ran: wait for this call's statistics and plan from them
+        hinted = false;
+        d->hinted_refused = true;
+        CUDA_OK(cudaStreamSynchronize(st));
+        hp_mark(1);
+        plan_launches(true);
     }
+    d->tm.hinted = hinted ? 1 : 0;
     for (size_t i = 0; i < 16; ++i) h_next[i] = 0;
     CUDA_OK(cudaMemcpyAsync(d_ord, h_ord, 4 * ord_used, cudaMemcpyHostToDevice, st));
     CUDA_OK(cudaMemcpyAsync(d_next, h_next, 64, cudaMemcpyHostToDevice, st));
@@ -1889,7 +1926,7 @@ static int decode_batch_locked(b2c_decoder_t* d, const void* const* logits, cons
             d->tm.cta_threads = ln.threads;
             d->tm.cta_slots = ln.slots;
             d->tm.kernel_variant = ln.v5 >= 0 ? 2 : (ln.cls < kNumCaps ? 1 : 0);
-            if (!pipe_candidate && launches.size() == 1) { d->plain_v5 = ln.v5; d->plain_cap = static_cast<int>(ln.L.cap_s); }
+            if (!pipe_candidate && !hinted && launches.size() == 1) { d->plain_v5 = ln.v5; d->plain_cap = static_cast<int>(ln.L.cap_s); }
         }
         if (cs != st) {
             CUDA_OK(cudaEventRecord(d->cls_done[ln.cls < kNumCaps ? 0 : 1], cs));
@@ -1903,6 +1940,8 @@ static int decode_batch_locked(b2c_decoder_t* d, const void* const* logits, cons
     CUDA_OK(cudaMemcpyAsync(d->h_out_toks.p, d->d_out_toks.p, tok_bytes, cudaMemcpyDeviceToHost, st));
     const bool text_only = opts->text_only != 0 && !streaming;
     if (!text_only) CUDA_OK(cudaMemcpyAsync(d->h_out_frames.p, d->d_out_frames.p, frm_bytes, cudaMemcpyDeviceToHost, st));
+    if (d->h_mstats.ensure(64)) return B2C_E_NOMEM;
+    CUDA_OK(cudaMemcpyAsync(d->h_mstats.p, d->d_mstats.p, 64, cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaEventRecord(d->ev[4], st));
     hp_mark(2);                                   // launch planning + enqueue of the beam kernel and D2H
     CUDA_OK(cudaStreamSynchronize(st));
@@ -1918,8 +1957,7 @@ static int decode_batch_locked(b2c_decoder_t* d, const void* const* logits, cons
     }
     d->tm.d2h_bytes += static_cast<long long>(small_bytes + tok_bytes + (text_only ? 0 : frm_bytes) + 8ull * n_utts + 32);
     {
-        u32 ms[16];
-        CUDA_OK(cudaMemcpy(ms, d->d_mstats.p, 64, cudaMemcpyDeviceToHost));
+        const u32* ms = d->h_mstats.as<u32>();
         d->hint_valid = true;
         d->hint_beam = opts->beam_width;
         d->hint_lm = P.lm.order > 0 ? 1 : 0;

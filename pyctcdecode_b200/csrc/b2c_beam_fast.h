@@ -841,29 +841,60 @@ B2C_HD u32 b2c_live_before(const u32* wm, u32 pos) {   // live slots with index 
     return c;
 }
 
-// number of leading slots p (of n, scores non-increasing) whose candidate for a token with log-prob lp2 sorts
-// before score s: (logit[p] + lp2) + 0 >= s (or > s when `ge` is false).  Three levels of independent probes
-// (3 x stride 32, 3 x stride 8, 8 x stride 1: 14 probes, 3 dependent rounds) instead of a 7-step dependent binary
-// search: the frame is bound by dependent-instruction latency.
-B2C_HD u32 b2c_sorted_probe(const double* logit, u32 n, u32 p, double lp2, double s, bool ge) {
-    if (p >= n) return 0u;
-    const double s2 = (logit[p] + lp2) + 0.0;
-    return (ge ? s2 >= s : s2 > s) ? 1u : 0u;
+// The candidate scores of token k2 form the list cf[k2 * n + p] = (logit[p] + lp[k2]) + 0.0, p < n, non-increasing in p
+// (written once per frame by the slots' owners, phase 1 of b2c_fast_sorted_step).  b2c_sorted_counts answers NS
+// questions at once: how many leading entries of list q sort before the score s[q] -- entry >= s (ge) or > s.
+// "> s" is asked as ">= the next double above s" (scores are finite and never -0.0: x + 0.0), so a probe is ONE
+// shared-memory load and ONE comparison.  Three levels of independent probes per question (3 x stride 32, 3 x stride 8,
+// 8 x stride 1: 14 probes, 3 dependent rounds) and the NS questions interleaved: the frame is bound by
+// dependent-instruction latency, so the rounds of different questions overlap.
+B2C_HD double b2c_next_up(double s) {        // smallest double > s, for finite s that is not -0.0
+    union { double d; u64 u; } c;
+    c.d = s;
+    c.u = (c.u >> 63) ? c.u - 1 : c.u + 1;
+    return c.d;
 }
-template <int WC>
-B2C_HD u32 b2c_sorted_count(const double* logit, u32 n, double lp2, double s, bool ge) {
-    static_assert(WC <= 128, "radix search covers 128 slots");
-    // invariant: slots < base sort before s, slot base + width does not (or is past the end)
-    u32 base = 32 * (b2c_sorted_probe(logit, n, 31, lp2, s, ge) + b2c_sorted_probe(logit, n, 63, lp2, s, ge) +
-                     b2c_sorted_probe(logit, n, 95, lp2, s, ge));
-    base += 8 * (b2c_sorted_probe(logit, n, base + 7, lp2, s, ge) + b2c_sorted_probe(logit, n, base + 15, lp2, s, ge) +
-                 b2c_sorted_probe(logit, n, base + 23, lp2, s, ge));
-    u32 cnt = 0;
+B2C_HD u32 b2c_list_probe(const double* list, u32 n, u32 p, double s) {
+    const u32 q = p < n ? p : n - 1;        // clamped: the load is unconditional (no branch), the answer is masked
+    return (p < n && list[q] >= s) ? 1u : 0u;
+}
+template <int NS>
+B2C_HD void b2c_sorted_counts(const double* const (&list)[NS], u32 n, const double (&s)[NS], u32 (&cnt)[NS]) {
+    u32 base[NS];
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
-    for (u32 q = 0; q < 8; ++q) cnt += b2c_sorted_probe(logit, n, base + q, lp2, s, ge);   // 8: in the last block of 8
-    return base + cnt;                                                                      // slot base + 7 was never probed
+    for (int q = 0; q < NS; ++q)
+        base[q] = 32 * (b2c_list_probe(list[q], n, 31, s[q]) + b2c_list_probe(list[q], n, 63, s[q]) + b2c_list_probe(list[q], n, 95, s[q]));
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int q = 0; q < NS; ++q)
+        base[q] += 8 * (b2c_list_probe(list[q], n, base[q] + 7, s[q]) + b2c_list_probe(list[q], n, base[q] + 15, s[q]) +
+                        b2c_list_probe(list[q], n, base[q] + 23, s[q]));
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int q = 0; q < NS; ++q) {
+        u32 c = 0;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+        for (u32 r = 0; r < 8; ++r) c += b2c_list_probe(list[q], n, base[q] + r, s[q]);    // 8: in the last block of 8
+        cnt[q] = base[q] + c;                                                               // entry base + 7 was never probed
+    }
+}
+// one question against the list logit[p] + lp2 computed on the fly (unit test: tests/hostsim/t_sorted_count.cpp)
+template <int WC>
+B2C_HD u32 b2c_sorted_count(const double* logit, u32 n, double lp2, double s, bool ge) {
+    static_assert(WC <= 128, "radix search covers 128 slots");
+    double tmp[WC];
+    for (u32 p = 0; p < n; ++p) tmp[p] = (logit[p] + lp2) + 0.0;
+    const double* const l1[1] = {tmp};
+    const double s1[1] = {ge ? s : b2c_next_up(s)};
+    u32 c1[1];
+    b2c_sorted_counts<1>(l1, n, s1, c1);
+    return c1[0];
 }
 
 // returns false (state untouched) when the best score is not finite
@@ -905,6 +936,11 @@ B2C_HD bool b2c_fast_sorted_step(const B2cParams& P, B2cFastSmem<WC, CAP, LT>& S
 #else
         if (live) S.wmask[b >> 5] |= 1u << (b & 31);
 #endif
+        // the K candidate lists (dead slots keep their place in the score order): cf[k * n + b]
+        if (static_cast<u32>(b) < n) {
+            const double lg = cur.logit[b];
+            for (int k = 0; k < K; ++k) S.cfold[static_cast<u32>(k) * n + static_cast<u32>(b)] = (lg + slp[k]) + 0.0;
+        }
     }
     B2C_SYNC();
     B2C_FMARK(20);
@@ -914,27 +950,71 @@ B2C_HD bool b2c_fast_sorted_step(const B2cParams& P, B2cFastSmem<WC, CAP, LT>& S
         u32 wm[B2C_FAST_NW];
         for (int w = 0; w < B2C_FAST_NW; ++w) wm[w] = S.wmask[w];
         u32 my_top = 0;
+        const double* const cf = S.cfold;
+        // candidate (b, k) takes rank `rank` (if it is inside the beam width)
+        auto place = [&](u32 b, u32 k, u32 rank) {
+            if (rank >= width) return;
+            if (WC < 128 && rank >= static_cast<u32>(WC)) {        // lean variant: more survivors than slots
+                b2c_atomic_or_u32(&S.sc.status, B2C_ERR_SLOTS);
+                return;
+            }
+            S.ord[rank] = b | (k << 16);
+            if (rank + 1 > my_top) my_top = rank + 1;
+        };
         B2C_FOR(b, n) {
             if (!((S.wmask[b >> 5] >> (b & 31)) & 1u)) continue;
+            // same token: the live beams before this one (equal scores keep beam order).  Another token k2: its
+            // candidates that sort before (k, b) -- score greater, or equal and enumerated earlier (k2 < k).
             const u32 lb = b2c_live_before(wm, static_cast<u32>(b));
-            const double lg = cur.logit[b];
-            for (int k = 0; k < K; ++k) {
-                const double s = (lg + slp[k]) + 0.0;
-                if (!(s >= thr)) continue;
-                u32 rank = lb;      // same token: the live beams before this one (equal scores keep beam order)
-                for (int k2 = 0; k2 < K && rank < width; ++k2) {
-                    if (k2 == k) continue;
-                    const double lp2 = slp[k2];
-                    // candidates of token k2 that sort before (k, b): score greater, or equal and enumerated earlier
-                    rank += b2c_live_before(wm, b2c_sorted_count<WC>(cur.logit, n, lp2, s, k2 < k));
+            const u32 ub = static_cast<u32>(b);
+            if (K == 2) {                       // both candidates of the beam at once
+                const double s0 = cf[ub], s1 = cf[n + ub];
+                const double* const l2[2] = {cf + n, cf};
+                const double q2[2] = {b2c_next_up(s0), s1};
+                u32 c2[2];
+                b2c_sorted_counts<2>(l2, n, q2, c2);
+                if (s0 >= thr) place(ub, 0u, lb + b2c_live_before(wm, c2[0]));
+                if (s1 >= thr) place(ub, 1u, lb + b2c_live_before(wm, c2[1]));
+            } else if (K == 3) {                // all six questions at once
+                const double s0 = cf[ub], s1 = cf[n + ub], s2 = cf[2 * n + ub];
+                const double u0 = b2c_next_up(s0), u1 = b2c_next_up(s1);
+                const double* const l6[6] = {cf + n, cf + 2 * n, cf, cf + 2 * n, cf, cf + n};
+                const double q6[6] = {u0, u0, s1, u1, s2, s2};
+                u32 c6[6];
+                b2c_sorted_counts<6>(l6, n, q6, c6);
+                if (s0 >= thr) place(ub, 0u, lb + b2c_live_before(wm, c6[0]) + b2c_live_before(wm, c6[1]));
+                if (s1 >= thr) place(ub, 1u, lb + b2c_live_before(wm, c6[2]) + b2c_live_before(wm, c6[3]));
+                if (s2 >= thr) place(ub, 2u, lb + b2c_live_before(wm, c6[4]) + b2c_live_before(wm, c6[5]));
+            } else {                            // K >= 4: per candidate, the other tokens three at a time
+                for (int k = 0; k < K; ++k) {
+                    const double s = cf[static_cast<u32>(k) * n + ub];
+                    if (!(s >= thr)) continue;
+                    const double su = b2c_next_up(s);
+                    u32 rank = lb;
+                    for (int k0 = 0; k0 < K && rank < width; k0 += 3) {
+                        const double* l3[3];
+                        double q3[3];
+                        bool on[3];
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+                        for (int j = 0; j < 3; ++j) {
+                            const int k2 = k0 + j;
+                            on[j] = k2 < K && k2 != k;
+                            l3[j] = cf + static_cast<u32>(on[j] ? k2 : k) * n;
+                            q3[j] = k2 < k ? s : su;
+                        }
+                        const double* const l3c[3] = {l3[0], l3[1], l3[2]};
+                        u32 c3[3];
+                        b2c_sorted_counts<3>(l3c, n, q3, c3);
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+                        for (int j = 0; j < 3; ++j)
+                            if (on[j]) rank += b2c_live_before(wm, c3[j]);
+                    }
+                    place(ub, static_cast<u32>(k), rank);
                 }
-                if (rank >= width) continue;
-                if (WC < 128 && rank >= static_cast<u32>(WC)) {    // lean variant: more survivors than slots
-                    b2c_atomic_or_u32(&S.sc.status, B2C_ERR_SLOTS);
-                    continue;
-                }
-                S.ord[rank] = static_cast<u32>(b) | (static_cast<u32>(k) << 16);
-                if (rank + 1 > my_top) my_top = rank + 1;
             }
         }
         b2c_warp_max_u32_slot(my_top, S.wtop);         // the selected ranks are exactly 0 .. max(wtop)-1

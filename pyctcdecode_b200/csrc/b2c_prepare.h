@@ -515,6 +515,73 @@ B2C_HD void b2c_prep_row(const T* row, int V, bool is_prob, double thr, int lane
 #endif
 }
 
+#if defined(__CUDA_ARCH__)
+// float32 logits, rows WITHOUT NaN / infinity (the common case), one warp per row: the same definition as
+// b2c_prep_row -- same maximum, same integer softmax denominator, same float32 log-probabilities, same selected set in
+// the same insertion order, same arg-max -- evaluated without the special-value branches and without float64 per element:
+//   pass 1  maximum, and sum(x) / sum(|x|) for the probabilities-or-logits decision (a separate read of the run before);
+//           a NaN or an infinity makes sum(|x|) non-finite -> return false, the general routine redoes the row
+//   pass 2  denominator through b2c_sm_quantum_fast (bit-identical to the definition on this domain)
+//   pass 3  float32 comparison against the threshold rounded UP to float32 ((double)lp >= thr <=> lp >= thr_up; the clip
+//           at log 1e-15 cannot move the arg-max and matters for the set only when thr is below it: thr_all)
+// ~40 warp instructions per 32 elements instead of ~64 (the streaming stage is instruction-bound at V = 1024).
+__device__ __forceinline__ bool b2c_prep_row_f32_fast(const float* row, int V, double thr, int lane, B2cPySet& set, float& m_out,
+                                                      double& ls_out, int& amax_out, u32& nsel_out, float& sx_out, float& sa_out) {
+    const unsigned full = 0xFFFFFFFFu;
+    float mx = -3.402823466e38f, sx = 0.0f, sa = 0.0f;
+    for (int v = lane; v < V; v += 32) {
+        const float x = row[v];
+        sx += x;
+        sa += fabsf(x);
+        mx = fmaxf(mx, x);
+    }
+    sx_out = sx;
+    sa_out = sa;
+    if (__any_sync(full, !(sa < 3.0e38f))) return false;
+    for (int off = 16; off >= 1; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(full, mx, off));
+    const float m = mx;
+    u64 q = 0;
+    for (int v = lane; v < V; v += 32) q += b2c_sm_quantum_fast(row[v] - m);
+    for (int off = 16; off >= 1; off >>= 1) q += __shfl_xor_sync(full, q, off);
+    const float lsf = b2c_sm_finish(q, false, false);
+    const float thr_up = __double2float_ru(thr);
+    const bool thr_all = thr <= B2C_LOG_MIN_CLIP;
+    float best = -3.402823466e38f;
+    int besti = -1;
+    u32 nsel = 0;
+    if (lane == 0) b2c_pyset_init(set, set.buf[0], set.buf[1]);
+    for (int base = 0; base < V; base += 32) {
+        const int v = base + lane;
+        bool sel = false;
+        if (v < V) {
+            const float lp = B2C_SM_ADD(row[v] - m, -lsf);
+            if (lp > best || besti < 0) { best = lp; besti = v; }
+            sel = thr_all || lp >= thr_up;
+        }
+        unsigned mask = __ballot_sync(full, sel);
+        nsel += __popc(mask);
+        if (lane == 0) {
+            while (mask) {
+                const int bit = __ffs(mask) - 1;
+                mask &= mask - 1;
+                b2c_pyset_add(set, static_cast<u32>(base + bit));
+            }
+        }
+        __syncwarp();
+    }
+    for (int off = 16; off >= 1; off >>= 1) {
+        const float ob = __shfl_xor_sync(full, best, off);
+        const int oi = __shfl_xor_sync(full, besti, off);
+        if (oi >= 0 && (besti < 0 || ob > best || (ob == best && oi < besti))) { best = ob; besti = oi; }
+    }
+    m_out = m;
+    ls_out = static_cast<double>(lsf);
+    amax_out = besti;
+    nsel_out = nsel;
+    return true;
+}
+#endif
+
 // CPython iteration order of set(ascending ints of `mask`) | {amax} for at most 3 selected tokens < 32 with
 // amax among them (or none selected): the table keeps its initial 8 slots (no resize below 5 entries, the
 // linear-probe window i+9 <= mask is never open at mask 7), one byte per slot in a 64-bit register.
@@ -727,7 +794,16 @@ B2C_HD void b2c_tokens_run(const B2cPrepArgs& A, u64 run, int lane, u16* set0, u
     const bool is_prob = A.mode == 1;
     const T* x = static_cast<const T*>(A.logits) + f0 * static_cast<u64>(V);
     const u64 base = (f0 + static_cast<u64>(t0)) * static_cast<u64>(V);
-    if (A.mode == 0) b2c_accum_approx<T>(A.approx + 2 * u, x + static_cast<u64>(t0) * V, static_cast<long>(t1 - t0) * V, lane);
+#if defined(__CUDA_ARCH__)
+    // float32 streaming pass: the row sums of the probabilities-or-logits decision come out of pass 1 of the fast row
+    // routine (float32 per row and lane, float64 across rows) instead of a separate read of the run
+    constexpr bool kFastRows = sizeof(T) == 4;
+    const bool fast_rows = kFastRows && A.mode == 0;
+    double run_sx = 0.0, run_sa = 0.0;
+#else
+    const bool fast_rows = false;
+#endif
+    if (A.mode == 0 && !fast_rows) b2c_accum_approx<T>(A.approx + 2 * u, x + static_cast<u64>(t0) * V, static_cast<long>(t1 - t0) * V, lane);
     u32* ids = A.tok_ids + base;
     double* lps = A.tok_lp + base;
     u32 off = 0, mx = 0;
@@ -740,7 +816,19 @@ B2C_HD void b2c_tokens_run(const B2cPrepArgs& A, u64 run, int lane, u16* set0, u
         double ls;
         int amax;
         u32 nsel;
-        b2c_prep_row<T, false>(row, V, is_prob, A.token_min_logp, lane, set, m, ls, amax, nsel);
+        bool row_done = false;
+#if defined(__CUDA_ARCH__)
+        if constexpr (kFastRows) {
+            if (fast_rows) {
+                float fm, fsx, fsa;
+                row_done = b2c_prep_row_f32_fast(reinterpret_cast<const float*>(row), V, A.token_min_logp, lane, set, fm, ls, amax, nsel, fsx, fsa);
+                m = fm;
+                run_sx += static_cast<double>(fsx);
+                run_sa += static_cast<double>(fsa);
+            }
+        }
+#endif
+        if (!row_done) b2c_prep_row<T, false>(row, V, is_prob, A.token_min_logp, lane, set, m, ls, amax, nsel);
         if (lane == 0) {
             b2c_pyset_copy_or(set, static_cast<u32>(amax));
             const u32 cnt = set.fill;
@@ -770,6 +858,15 @@ B2C_HD void b2c_tokens_run(const B2cPrepArgs& A, u64 run, int lane, u16* set0, u
         b2c_atomic_max_u32(&A.max_k[u], mx);
         b2c_atomic_add_u32(&A.sum_k[u], off);
     }
+#if defined(__CUDA_ARCH__)
+    if (fast_rows) {
+        for (int o = 16; o >= 1; o >>= 1) {
+            run_sx += __shfl_xor_sync(0xFFFFFFFFu, run_sx, o);
+            run_sa += __shfl_xor_sync(0xFFFFFFFFu, run_sa, o);
+        }
+        if (lane == 0) { atomicAdd(A.approx + 2 * u, run_sx); atomicAdd(A.approx + 2 * u + 1, run_sa); }
+    }
+#endif
 }
 
 template <class T>

@@ -48,6 +48,41 @@ B2C_SM_HD float b2c_sm_expf(float x) {
     return b2c_sm_from_bits(b2c_sm_bits(p) + (static_cast<uint32_t>(ni) << 23));
 }
 
+// rint(exp(d) * 2^32) as an integer -- the addend of one element in the softmax denominator -- for d <= 0 that is finite
+// or -inf (rows without NaN / +inf; the caller has checked).  The SAME sequence of operations as b2c_sm_expf followed
+// by the scaling and rounding of b2c_sm_quantum, without their special-value branches: d is clamped at -87 (there
+// exp(d) 2^32 < 0.5, the same addend 0 as the definition's cut-off), n is read from the bits of the magic-number sum
+// instead of converted, and the factor 2^32 is folded into the exponent arithmetic (an exact scaling either way).
+// Bit-identical to b2c_sm_quantum(b2c_sm_expf(d)) on that domain (tools/softmath_check.cpp, tests/test_host_logic.py).
+B2C_SM_HD uint64_t b2c_sm_quantum_fast(float d) {
+#if defined(__CUDA_ARCH__)
+    const float x = fmaxf(d, -87.0f);
+#else
+    const float x = d < -87.0f ? -87.0f : d;
+#endif
+    const float t = B2C_SM_FMA(x, 1.44269504088896341f, 12582912.0f);
+    const float n = B2C_SM_ADD(t, -12582912.0f);
+    float r = B2C_SM_FMA(n, -0.693359375f, x);
+    r = B2C_SM_FMA(n, 2.12194440e-4f, r);
+    float p = 1.9875691500e-4f;
+    p = B2C_SM_FMA(p, r, 1.3981999507e-3f);
+    p = B2C_SM_FMA(p, r, 8.3334519073e-3f);
+    p = B2C_SM_FMA(p, r, 4.1665795894e-2f);
+    p = B2C_SM_FMA(p, r, 1.6666665459e-1f);
+    p = B2C_SM_FMA(p, r, 5.0000001201e-1f);
+    const float r2 = B2C_SM_MUL(r, r);
+    p = B2C_SM_FMA(p, r2, r);
+    p = B2C_SM_ADD(p, 1.0f);
+    // t = 1.5 * 2^23 + n exactly (|n| <= 126): n sits in the low mantissa bits of t
+    const uint32_t ni32 = b2c_sm_bits(t) - 0x4B400000u + 32u;
+    const float e32 = b2c_sm_from_bits(b2c_sm_bits(p) + (ni32 << 23));
+#if defined(__CUDA_ARCH__)
+    return __float2ull_rn(e32);
+#else
+    return static_cast<uint64_t>(llrintf(e32));
+#endif
+}
+
 // log(x), float32, x > 0 normal (the softmax denominator is in [1, V]); Cephes-style: x = m 2^e with
 // m in [sqrt(1/2), sqrt(2)), polynomial in f = m - 1, e ln2 added in two parts.
 B2C_SM_HD float b2c_sm_logf(float x) {

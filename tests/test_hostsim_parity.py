@@ -615,3 +615,38 @@ def test_hostsim_gated_launch_gives_up_cleanly(sim, monkeypatch):
     want = ora.decode_batch(list(xs), beam_width=24)
     for _ in range(3):
         assert dec.decode_batch(None, xs, beam_width=24) == want
+
+
+def test_hostsim_hinted_plain_calls(sim):
+    """Hinted plain calls (any input that is not pipelined: lists of arrays, device tensors): from the second call of
+    a configuration the beam kernel is planned from the previous call's statistics and launched without waiting for
+    this call's -- the same results; a batch whose statistics ask for another plan (here: diffuse posteriors after
+    peaky ones) is found out (hint-only plan != last statistics-based plan, or the refresh every 32nd call) and is
+    planned from its statistics."""
+    wkw, lmkw = FAMILIES["B_nolm"]
+    wl = synth.make_workload(wkw)
+    dec = sim.build_ctcdecoder(wl.labels)
+    ora = orc.OracleDecoder(wl.labels)
+    peaky = [wl.utterance(9500 + i, 200 + 10 * i, "peaky") for i in range(4)]
+    want = ora.decode_batch(peaky, beam_width=32)
+    flags = []
+    for _ in range(3):
+        assert dec.decode_batch(None, peaky, beam_width=32) == want
+        flags.append(dec.last_timings()["hinted"])
+    assert flags == [0, 1, 1]
+    # another beam width is another configuration: its first call plans from the statistics
+    want16 = ora.decode_batch(peaky, beam_width=16)
+    assert dec.decode_batch(None, peaky, beam_width=16) == want16
+    assert dec.last_timings()["hinted"] == 0
+    assert dec.decode_batch(None, peaky, beam_width=16) == want16
+    assert dec.last_timings()["hinted"] == 1
+    # full beams (decode_beams_batch) through hinted calls
+    ref = ora.decode_beams_batch(peaky, beam_width=16)
+    for w, g in zip(ref, dec.decode_beams_batch(None, peaky, beam_width=16)):
+        _compare(w, _beams(g))
+    # diffuse posteriors behind the same configuration: correct whichever way each call was planned, over a refresh
+    diffuse = [wl.utterance(9600 + i, 120, "diffuse") for i in range(3)]
+    want_d = ora.decode_batch(diffuse, beam_width=16)
+    for _ in range(40):
+        assert dec.decode_batch(None, diffuse, beam_width=16) == want_d
+    assert dec.decode_batch(None, peaky, beam_width=16) == want16
