@@ -118,6 +118,7 @@ struct B2cFastSmem {
     u32 holes;                                        // the current beam table has history-pruned slots (see b2c_fast_step)
     u32 cheap_bad;                                    // a thread's exactness check of b2c_fast_scored_step failed (rare)
     u32 run_fail;                                     // b2c_fast_run_step: first frame of the run whose exactness check failed
+    u32 n_merged;                                     // b2c_fast_step, list-ranked form: merged groups of the frame
     u32 wmask[B2C_FAST_NW];                           // per warp: live slots of the current table (b2c_fast_sorted_step)
 #if defined(B2C_PHASE_CLOCKS)
     u64 pclk[32];                                     // profiling builds: cycles between marks, thread 0
@@ -140,7 +141,7 @@ struct B2cFastSmem {
     u32 cmeta[CAP];          // partial length | canonical token << 16
     u32 cslot[CAP], cnext[CAP], clast[CAP];
     u32 cbk[CAP];            // beam | token index << 16
-    u32 ht_idx[HT], ht_min[HT], ht_max[HT], ht_cnt[HT];
+    u32 ht_idx[HT + 1], ht_min[HT + 1], ht_max[HT + 1], ht_cnt[HT + 1];   // slot HT: never claimed (candidates of dead beams)
     // token lists: label records of the current / next frame, rings of frame records and of (id, log-prob) lists
     alignas(16) B2cTok stok[2][LT > 0 ? 1 : KR];   // staged label records (large alphabets only)
     alignas(16) B2cFrameRec rh[B2C_FAST_HR];
@@ -272,11 +273,11 @@ B2C_HD void b2c_bucket_scan_warp_v(const u32* bcnt, u32* pre) {
 
 #define B2C_INVALID_TOK 0xFFFEu      // last_tok of a history-pruned slot (BPE force logic skips it)
 
-// candidate i (a group leader) becomes beam j of the next frame (decoder.py:452-534 metadata); called by the
-// thread that owns the candidate, inside the ranking loop
+// a group (merged logit_score `logit_new`, metadata of its last member `last`) becomes beam j of the next frame
+// (decoder.py:452-534); called by the thread that owns the group's leader, inside the ranking loop
 template <int WC, int CAP, int LT>
 B2C_HD void b2c_fast_commit(const B2cParams& P, B2cFastSmem<WC, CAP, LT>& S, const B2cFastTab<WC>& cur, B2cFastTab<WC>& nx,
-                            B2cChain* chain_arena, B2cText* text_arena, u32 text_cap, int sb, int slot, int t, u32 j, u32 i,
+                            B2cChain* chain_arena, B2cText* text_arena, u32 text_cap, int sb, int slot, int t, u32 j, double logit_new,
                             u32 last, u32 flags) {
     const u32 bk = S.cbk[last];
     const u32 bl = bk & 0xFFFFu, k = bk >> 16;
@@ -288,7 +289,7 @@ B2C_HD void b2c_fast_commit(const B2cParams& P, B2cFastSmem<WC, CAP, LT>& S, con
     const u32 word_len = (type == 1 || type == 2) ? static_cast<u32>(cur.part_len[bl]) : 0u;
     u64 th = cur.text_hash[bl];
     if (word_len > 0) th = b2c_text_append(th, cur.part_hash[bl]);
-    nx.logit[j] = S.cfold[i];
+    nx.logit[j] = logit_new;
     nx.text_hash[j] = th;
     nx.part_hash[j] = part_hash;
     nx.part_len[j] = static_cast<u16>(part_len);
@@ -355,6 +356,173 @@ B2C_HD void b2c_fast_commit(const B2cParams& P, B2cFastSmem<WC, CAP, LT>& S, con
 // hold the number of slots and the best score key of the previous frame (per-warp maxima).
 // Invariants on entry: grouping table clear; prune table = entries pslot[0 .. n) iff S.holes.
 // -----------------------------------------------------------------------------------------
+// ---- helpers of the search-ranked steps (b2c_fast_sorted_step, list-ranked form of b2c_fast_step) ----------------
+#define B2C_SORTED_MAXK 8
+B2C_HD u32 b2c_live_before(const u32* wm, u32 pos) {   // live slots with index < pos (pos <= 32 * B2C_FAST_NW)
+    u32 c = 0;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (u32 w = 0; w < B2C_FAST_NW; ++w) {
+        const u32 lo = w * 32;
+        u32 m = wm[w];
+        if (pos < lo + 32) m = pos > lo ? (m & ((1u << (pos - lo)) - 1u)) : 0u;
+#if defined(__CUDA_ARCH__)
+        c += static_cast<u32>(__popc(m));
+#else
+        c += static_cast<u32>(__builtin_popcount(m));
+#endif
+    }
+    return c;
+}
+
+// The candidate scores of token k2 form the list cf[k2 * n + p] = (logit[p] + lp[k2]) + 0.0, p < n, non-increasing in p
+// (written once per frame by the slots' owners, phase 1 of b2c_fast_sorted_step).  b2c_sorted_counts answers NS
+// questions at once: how many leading entries of list q sort before the score s[q] -- entry >= s (ge) or > s.
+// "> s" is asked as ">= the next double above s" (scores are finite and never -0.0: x + 0.0), so a probe is ONE
+// shared-memory load and ONE comparison.  Three levels of independent probes per question (3 x stride 32, 3 x stride 8,
+// 8 x stride 1: 14 probes, 3 dependent rounds) and the NS questions interleaved: the frame is bound by
+// dependent-instruction latency, so the rounds of different questions overlap.
+B2C_HD double b2c_next_up(double s) {        // smallest double > s, for finite s that is not -0.0
+    union { double d; u64 u; } c;
+    c.d = s;
+    c.u = (c.u >> 63) ? c.u - 1 : c.u + 1;
+    return c.d;
+}
+B2C_HD u32 b2c_list_probe(const double* list, u32 n, u32 p, double s) {
+    const u32 q = p < n ? p : n - 1;        // clamped: the load is unconditional (no branch), the answer is masked
+    return (p < n && list[q] >= s) ? 1u : 0u;
+}
+template <int NS>
+B2C_HD void b2c_sorted_counts(const double* const (&list)[NS], u32 n, const double (&s)[NS], u32 (&cnt)[NS]) {
+    u32 base[NS];
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int q = 0; q < NS; ++q)
+        base[q] = 32 * (b2c_list_probe(list[q], n, 31, s[q]) + b2c_list_probe(list[q], n, 63, s[q]) + b2c_list_probe(list[q], n, 95, s[q]));
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int q = 0; q < NS; ++q)
+        base[q] += 8 * (b2c_list_probe(list[q], n, base[q] + 7, s[q]) + b2c_list_probe(list[q], n, base[q] + 15, s[q]) +
+                        b2c_list_probe(list[q], n, base[q] + 23, s[q]));
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int q = 0; q < NS; ++q) {
+        u32 c = 0;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+        for (u32 r = 0; r < 8; ++r) c += b2c_list_probe(list[q], n, base[q] + r, s[q]);    // 8: in the last block of 8
+        cnt[q] = base[q] + c;                                                               // entry base + 7 was never probed
+    }
+}
+// one question against the list logit[p] + lp2 computed on the fly (unit test: tests/hostsim/t_sorted_count.cpp)
+template <int WC>
+B2C_HD u32 b2c_sorted_count(const double* logit, u32 n, double lp2, double s, bool ge) {
+    static_assert(WC <= 128, "radix search covers 128 slots");
+    double tmp[WC];
+    for (u32 p = 0; p < n; ++p) tmp[p] = (logit[p] + lp2) + 0.0;
+    const double* const l1[1] = {tmp};
+    const double s1[1] = {ge ? s : b2c_next_up(s)};
+    u32 c1[1];
+    b2c_sorted_counts<1>(l1, n, s1, c1);
+    return c1[0];
+}
+
+// Ranks of the candidates of a frame whose K candidate lists cf[k * n + b] are non-increasing in b (b2c_fast_sorted_step,
+// list-ranked form of b2c_fast_step).  Work items are the candidates i = k * n + b, strided over the threads -- NOT
+// "a slot and its K candidates per thread": the candidates that can still land inside the beam width are the first few
+// entries of every list (a candidate of the r-th best token has at least r + 1 lists in front of its own position), so
+// per-slot work would leave the whole frame waiting for the threads of the first slots (K (K - 1) searches each).
+// An item first looks at ENTRY b OF EVERY OTHER LIST: where that entry already sorts before the candidate, so do all
+// entries above it -- a lower bound on the rank that needs no search and discards most items; the survivors run one
+// three-level search per other list (three lists interleaved).
+//   masks + mstride * k   eligible entries of list k (bit b; 4 words): live slots (sorted step, mstride 0) or unmerged
+//                         live entries (list-ranked step, mstride 4)
+//   mask_all              entries eligible in EVERY list (a subset of each list's mask: the lower bound counts it)
+//   extra(s, i)           groups outside the lists that sort before score s / enumeration index i (merged groups)
+//   place(i, k, b, rank)  called for every candidate with score >= thr whose rank is < width
+template <class Extra, class Place>
+B2C_HD void b2c_rank_list_items(const double* cf, u32 n, int K, const u32* masks, u32 mstride, const u32* mask_all, double thr,
+                                u32 width, Extra extra, Place place) {
+    const u32 M = n * static_cast<u32>(K);
+    const float rcp_n = 1.0f / static_cast<float>(n);
+    B2C_FOR(i, M) {
+        u32 k, b;
+        b2c_divmod(static_cast<u32>(i), n, rcp_n, k, b);
+        const u32* const mk = masks + mstride * k;
+        if (!((mk[b >> 5] >> (b & 31)) & 1u)) continue;
+        const double s = cf[i] + 0.0;
+        if (!(s >= thr)) continue;
+        const double su = b2c_next_up(s);       // "> s" asked as ">= next_up(s)"
+        // same list: the eligible entries above this one (equal scores keep slot order)
+        u32 rank = b2c_live_before(mk, b) + extra(s, static_cast<u32>(i));
+        if (K > 1) {
+            // another list k2: its entries that sort before (k, b) -- score greater, or equal and enumerated earlier (k2 < k)
+            u32 npass = 0;
+            for (int k2 = 0; k2 < K; ++k2) {
+                if (k2 == static_cast<int>(k)) continue;
+                npass += cf[static_cast<u32>(k2) * n + b] >= (k2 < static_cast<int>(k) ? s : su) ? 1u : 0u;
+            }
+            if (npass > 0 && rank + npass * b2c_live_before(mask_all, b + 1) >= width) continue;
+            for (int q0 = 0; q0 < K - 1 && rank < width; q0 += 3) {
+                // the other lists in order, three at a time: list index q -> token q + (q >= k)
+                const int left = K - 1 - q0;
+                const u32 ka = static_cast<u32>(q0) + (static_cast<u32>(q0) >= k ? 1u : 0u);
+                const u32 kb = static_cast<u32>(q0 + 1) + (static_cast<u32>(q0 + 1) >= k ? 1u : 0u);
+                const u32 kc = static_cast<u32>(q0 + 2) + (static_cast<u32>(q0 + 2) >= k ? 1u : 0u);
+                if (left >= 3) {
+                    const double* const l3[3] = {cf + ka * n, cf + kb * n, cf + kc * n};
+                    const double q3[3] = {ka < k ? s : su, kb < k ? s : su, kc < k ? s : su};
+                    u32 c3[3];
+                    b2c_sorted_counts<3>(l3, n, q3, c3);
+                    rank += b2c_live_before(masks + mstride * ka, c3[0]) + b2c_live_before(masks + mstride * kb, c3[1]) +
+                            b2c_live_before(masks + mstride * kc, c3[2]);
+                } else if (left == 2) {
+                    const double* const l2[2] = {cf + ka * n, cf + kb * n};
+                    const double q2[2] = {ka < k ? s : su, kb < k ? s : su};
+                    u32 c2[2];
+                    b2c_sorted_counts<2>(l2, n, q2, c2);
+                    rank += b2c_live_before(masks + mstride * ka, c2[0]) + b2c_live_before(masks + mstride * kb, c2[1]);
+                } else {
+                    const double* const l1[1] = {cf + ka * n};
+                    const double q1[1] = {ka < k ? s : su};
+                    u32 c1[1];
+                    b2c_sorted_counts<1>(l1, n, q1, c1);
+                    rank += b2c_live_before(masks + mstride * ka, c1[0]);
+                }
+            }
+        }
+        if (rank < width) place(static_cast<u32>(i), k, b, rank);
+    }
+}
+
+#define B2C_LISTS_GMAX 64       // most merged groups of a frame the list-ranked form handles (more: score buckets)
+
+// -----------------------------------------------------------------------------------------
+// b2c_fast_step ranks in one of two ways after the same expansion and grouping (phase A):
+//
+// (1) LISTS (no LM, no hotwords, regular alphabet, K <= 8 tokens): lm_score == logit_score + 0, the slots of the
+//     current table are in score order, so the candidates of token k -- cfold[k * n + b] = logit[b] + lp_k, b in slot
+//     order -- are a NON-INCREASING list.  Merging (decoder.py:211-224) touches few of them: a group of >= 2 equal
+//     keys becomes ONE "merged group" whose score is the log-sum-exp of its members and whose place among equal scores
+//     is its first member's.  So the rank of a candidate in the stable sort of decoder.py:548 is
+//         sum over the K lists of (unmerged live entries that sort before it)  +  (merged groups that sort before it)
+//     -- a prefix population count in its own list, one three-level search per other list (b2c_sorted_counts, the
+//     searches of a thread interleaved), and a walk over the short list of merged groups; for a merged group two
+//     searches per list (scores greater / greater-or-equal: among equal scores the entries enumerated before its
+//     first member precede it).  No score buckets: no bucket clear, no bucket atomics, no prefix scan, no in-bucket
+//     walk.  Per-list masks of the unmerged live entries come from warp ballots (U, behind the merged groups); the merged groups
+//     (score, first member, last member) live in the bucket arrays, which this form does not use otherwise.
+//     More than B2C_LISTS_GMAX merged groups, or a best score that is not finite: the frame continues with (2) on
+//     the same grouping (nothing of phase A is redone).
+// (2) BUCKETS (everything else): fold, fuse, 256 monotone score buckets | threshold, bucket prefix + order inside the
+//     bucket, commit.
+// Both commit through b2c_fast_commit and leave the same state (beam table with holes, prune table, wtop / wmax).
+// -----------------------------------------------------------------------------------------
 template <int WC, int CAP, int LT>
 B2C_HD void b2c_fast_step(const B2cParams& P, B2cFastSmem<WC, CAP, LT>& S, B2cChain* chain_arena, B2cText* text_arena,
                           u32 text_cap, int par, int t, int sb, int slot, int K) {
@@ -369,6 +537,14 @@ B2C_HD void b2c_fast_step(const B2cParams& P, B2cFastSmem<WC, CAP, LT>& S, B2cCh
     const double ref = b2c_key_f64(b2c_max_slots(S.wmax));     // best score of the previous frame
     const double bscale = P.bucket_scale;
     constexpr u32 hmask = SM::HT - 1, ptmask = SM::PT - 1;
+    constexpr u32 kDeadSlot = SM::HT;                          // grouping slot of the candidates of dead beams: never claimed
+    const bool lists = !is_bpe && (flags & B2C_FL_PSCORE) == 0 && K <= B2C_SORTED_MAXK && P.no_lists == 0;
+    // lists: U[k][warp], unmerged live entries of list k (+ one row: unmerged in every list), behind the merged groups
+    u32* const umask = &S.bpre[0][0] + 2 * B2C_LISTS_GMAX;
+    static_assert(2 * B2C_LISTS_GMAX + B2C_FAST_NW * (B2C_SORTED_MAXK + 1) <= B2C_NBUCKET, "scratch of the list-ranked form fits one prefix row");
+    double* const mg_score = reinterpret_cast<double*>(&S.bpre[0][0]);   // lists: merged groups
+    u32* const mg_first = S.bcnt;
+    u32* const mg_last = S.bhead;
     B2C_FMARK(0);
 
     if (is_bpe) {
@@ -383,9 +559,27 @@ B2C_HD void b2c_fast_step(const B2cParams& P, B2cFastSmem<WC, CAP, LT>& S, B2cCh
     }
 
     // ---- phase A: expand (decoder.py:447-534), merge key, grouping ---------------------------------
-    B2C_FOR(s, B2C_NBUCKET) { S.bcnt[s] = 0; S.bhead[s] = B2C_NONE_U32; }
-    B2C_FOR(b, n) {
-        const bool live = !holes || S.pt_min[S.pslot[b]] == static_cast<u32>(b);
+    if (!lists) {
+        B2C_FOR(s, B2C_NBUCKET) { S.bcnt[s] = 0; S.bhead[s] = B2C_NONE_U32; }
+    } else {
+        B2C_LEADER { S.n_merged = 0; }
+        B2C_FOR(q, B2C_FAST_NW * (B2C_SORTED_MAXK + 1)) { umask[q] = 0; }    // words of warps that do not exist (one-warp variant) stay 0
+#if !defined(__CUDA_ARCH__)
+        for (int w = 0; w < B2C_FAST_NW; ++w) S.wmask[w] = 0;
+#endif
+    }
+    B2C_FOR(b, (lists ? static_cast<u32>(WC) : n)) {
+        const bool in_range = static_cast<u32>(b) < n;
+        const bool live = in_range && (!holes || S.pt_min[S.pslot[b]] == static_cast<u32>(b));
+        if (lists) {      // which slots are live: the later phases must not look at the prune table (it is released in between)
+#if defined(__CUDA_ARCH__)
+            const u32 lm = __ballot_sync(0xFFFFFFFFu, live);
+            if ((threadIdx.x & 31) == 0) S.wmask[threadIdx.x >> 5] = lm;
+#else
+            if (live) S.wmask[b >> 5] |= 1u << (b & 31);
+#endif
+        }
+        if (!in_range) continue;
         const u32 plen = cur.part_len[b];
         const u64 ph = cur.part_hash[b];
         const u64 th0 = cur.text_hash[b];
@@ -393,7 +587,11 @@ B2C_HD void b2c_fast_step(const B2cParams& P, B2cFastSmem<WC, CAP, LT>& S, B2cCh
         const double lg = cur.logit[b];
         for (int k = 0; k < K; ++k) {
             const u32 i = static_cast<u32>(k) * n + static_cast<u32>(b);
-            if (!live) { S.cslot[i] = 0; continue; }           // never a group leader (phase B), key 0 in phase C
+            if (!live) {                                           // never a group leader (phase B), key 0 in phase C;
+                S.cslot[i] = kDeadSlot;                            // a dead slot keeps its place in the lists
+                if (lists) S.cfold[i] = lg + S.rlp[slot][k];
+                continue;
+            }
             const B2cTok ti = b2c_fast_tok<WC, CAP, LT>(S, sb, slot, k);
             u64 th = th0;
             u64 nph;
@@ -437,14 +635,167 @@ B2C_HD void b2c_fast_step(const B2cParams& P, B2cFastSmem<WC, CAP, LT>& S, B2cCh
     B2C_SYNC();
     B2C_FMARK(1);
 
-    // ---- phase B: fold each group (decoder.py:211-224), LM / hotword fusion (:346-424), bucket, max ---
-    if (holes) {   // the validity tests of phase A are done: release the previous frame's prune entries
+    // the validity tests of phase A are done: release the previous frame's prune entries
+    if (holes) {
         B2C_FOR(r, n) {
             const u32 s = S.pslot[r];
             S.pt_idx[s] = B2C_NONE_U32;
             S.pt_min[s] = B2C_NONE_U32;
         }
     }
+    const u32 width = static_cast<u32>(P.beam_width);
+    // the owner of a selected group commits it as beam `rank` of the next frame and enters its history key into the
+    // prune table (decoder.py:550-552); `i`: first member (leader), `last`: last member, `lg`: merged logit_score
+    u32 my_top = 0;
+    auto select = [&](u32 rank, u32 i, u32 last, double lg, u32 fl) {
+        if (rank >= width) return;
+        if (WC < 128 && rank >= static_cast<u32>(WC)) {        // lean variant: more survivors than slots
+            b2c_atomic_or_u32(&S.sc.status, B2C_ERR_SLOTS);
+            return;
+        }
+        if (rank + 1 > my_top) my_top = rank + 1;
+        if (prune) {
+            const u32 bl = S.cbk[last] & 0xFFFFu;
+            const u64 cph = S.cph[last];
+            const u32 type = static_cast<u32>(cph >> 61);
+            const u32 meta = S.cmeta[last];
+            u64 hh = cur.hist_hash[bl];
+            if ((type == 1 || type == 2) && cur.part_len[bl] > 0)       // a one-word history does not depend on the parent
+                hh = P.hist_n == 1 ? b2c_hist_fold(B2C_HIST_SEED, cur.part_hash[bl])
+                                   : b2c_hist_extend(text_arena + cur.text_node[bl], P.hist_n, cur.part_hash[bl]);
+            const u64 hk = b2c_fast_key(hh, cph & B2C_PH_MASK, meta & 0xFFFFu, meta >> 16);
+            S.phk[rank] = hk;
+            b2c_fence_block();
+            u32 pslot = static_cast<u32>(hk) & ptmask;
+            while (true) {
+                const u32 rep = b2c_atomic_cas_u32(&S.pt_idx[pslot], B2C_NONE_U32, rank);
+                if (rep == B2C_NONE_U32) break;
+                b2c_fence_block();
+                if (S.phk[rep] == hk) break;
+                pslot = (pslot + 1) & ptmask;
+            }
+            S.pslot[rank] = pslot;
+            b2c_atomic_min_u32(&S.pt_min[pslot], rank);
+        }
+        b2c_fast_commit(P, S, cur, nx, chain_arena, text_arena, text_cap, sb, slot, t, rank, lg, last, fl);
+    };
+    // list-ranked form: no LM, no hotwords, regular alphabet -- known at compile time in its copies of the commit code
+    const u32 lflags = flags & ~static_cast<u32>(B2C_FL_PSCORE | B2C_FL_LM | B2C_FL_BPE);
+
+    bool buckets = !lists;
+    if (lists) {
+        // ---- lists, phase B: merged groups (fold, decoder.py:211-224), masks of the unmerged live entries, max ----
+        u64 tmax = 0;
+        B2C_FOR(b, WC) {
+            const bool live = static_cast<u32>(b) < n && ((S.wmask[b >> 5] >> (b & 31)) & 1u) != 0;
+            bool unmerged_all = live;                               // unmerged in every list (row B2C_SORTED_MAXK of U)
+            for (int k = 0; k < K; ++k) {
+                const u32 i = static_cast<u32>(k) * n + static_cast<u32>(b);
+                bool unmerged = false;
+                if (live) {
+                    const u32 gs = S.cslot[i];
+                    const u32 cnt = S.ht_cnt[gs] + 1;
+                    if (cnt == 1) {
+                        unmerged = true;
+                        const u64 key = b2c_f64_key(S.cfold[i] + 0.0);
+                        if (key > tmax) tmax = key;
+                    } else {
+                        u32 first = S.ht_idx[gs], last = first;
+                        const u32 lo = S.ht_min[gs], hi = S.ht_max[gs];
+                        first = lo < first ? lo : first;
+                        last = hi > last ? hi : last;
+                        if (first == i) {
+                            double sm = S.cfold[i];
+                            for (u32 j = (cnt == 2) ? last : i + 1; j <= last; ++j) {
+                                if (S.cslot[j] != gs) continue;
+                                sm = b2c_sum_log_scores_ool(sm, S.cfold[j]);
+                            }
+                            const u32 g = b2c_atomic_add_u32(&S.n_merged, 1u);
+                            if (g < B2C_LISTS_GMAX) {
+                                mg_score[g] = sm;
+                                mg_first[g] = i;
+                                mg_last[g] = last;
+                            }
+                            const u64 key = b2c_f64_key(sm + 0.0);
+                            if (key > tmax) tmax = key;
+                        }
+                    }
+                }
+                unmerged_all = unmerged_all && unmerged;
+#if defined(__CUDA_ARCH__)
+                const u32 um = __ballot_sync(0xFFFFFFFFu, unmerged);
+                if ((threadIdx.x & 31) == 0) umask[B2C_FAST_NW * k + (threadIdx.x >> 5)] = um;
+#else
+                if (unmerged) umask[B2C_FAST_NW * k + (b >> 5)] |= 1u << (b & 31);
+#endif
+            }
+#if defined(__CUDA_ARCH__)
+            const u32 ua = __ballot_sync(0xFFFFFFFFu, unmerged_all);
+            if ((threadIdx.x & 31) == 0) umask[B2C_FAST_NW * B2C_SORTED_MAXK + (threadIdx.x >> 5)] = ua;
+#else
+            if (unmerged_all) umask[B2C_FAST_NW * B2C_SORTED_MAXK + (b >> 5)] |= 1u << (b & 31);
+#endif
+        }
+        b2c_warp_max_u64_slot(tmax, S.wmax);
+        B2C_SYNC();
+        B2C_FMARK(2);
+        const u32 G = S.n_merged;
+        const double max_score = b2c_key_f64(b2c_max_slots(S.wmax));
+        if (G > static_cast<u32>(P.lists_gmax) || !(max_score >= -1.7976931348623157e308)) {
+            // block-uniform, rare: rank this frame with the score buckets (its arrays were the merged-group scratch)
+            buckets = true;
+            B2C_SYNC();
+            B2C_FOR(s, B2C_NBUCKET) { S.bcnt[s] = 0; S.bhead[s] = B2C_NONE_U32; }
+            B2C_SYNC();
+        } else {
+            // ---- lists, phase C: threshold (:545-546), rank by search (:548), commit; grouping slots are released ----
+            const double thr = max_score + P.prune_logp;
+            const double* const cf = S.cfold;
+            // merged groups that sort before a group of score s whose first member is candidate i
+            auto merged_ahead = [&](double s, u32 i) {
+                u32 c = 0;
+                for (u32 g = 0; g < G; ++g) {
+                    const double sg = mg_score[g] + 0.0;
+                    c += (sg > s || (sg == s && mg_first[g] < i)) ? 1u : 0u;
+                }
+                return c;
+            };
+            B2C_FOR(i, M) {                                         // every candidate releases its grouping slot
+                const u32 gs = S.cslot[i];
+                S.ht_idx[gs] = B2C_NONE_U32;
+                S.ht_min[gs] = B2C_NONE_U32;
+                S.ht_max[gs] = 0;
+                S.ht_cnt[gs] = 0;
+            }
+            // the unmerged candidates
+            b2c_rank_list_items(cf, n, K, umask, static_cast<u32>(B2C_FAST_NW), umask + B2C_FAST_NW * B2C_SORTED_MAXK, thr, width, merged_ahead,
+                                [&](u32 i, u32, u32, u32 rank) { select(rank, i, i, cf[i], lflags); });
+            // the merged groups, one per work item: entries with a greater score, or an equal score and enumerated
+            // before the group's first member, precede it
+            B2C_FOR(g, G) {
+                const double sm = mg_score[g], s = sm + 0.0;
+                if (!(s >= thr)) continue;
+                const u32 i = mg_first[g];
+                const double su = b2c_next_up(s);
+                u32 rank = merged_ahead(s, i);
+                for (int k2 = 0; k2 < K && rank < width; ++k2) {
+                    const double* const l2[2] = {cf + static_cast<u32>(k2) * n, cf + static_cast<u32>(k2) * n};
+                    const double q2[2] = {su, s};
+                    u32 c2[2];
+                    b2c_sorted_counts<2>(l2, n, q2, c2);               // entries > s, entries >= s
+                    const u32 base_k2 = static_cast<u32>(k2) * n;
+                    u32 pos = i > base_k2 ? i - base_k2 : 0u;          // entries of this list enumerated before candidate i
+                    pos = pos < c2[0] ? c2[0] : (pos > c2[1] ? c2[1] : pos);
+                    rank += b2c_live_before(umask + B2C_FAST_NW * k2, pos);
+                }
+                select(rank, i, mg_last[g], sm, lflags);
+            }
+            b2c_warp_max_u32_slot(my_top, S.wtop);         // the selected ranks are exactly 0 .. max(wtop)-1
+        }
+    }
+
+    if (buckets) {
+    // ---- buckets, phase B: fold each group (decoder.py:211-224), LM / hotword fusion (:346-424), bucket, max ---
     {
         u64 tmax = 0;
         B2C_FOR(i, M) {
@@ -496,16 +847,13 @@ B2C_HD void b2c_fast_step(const B2cParams& P, B2cFastSmem<WC, CAP, LT>& S, B2cCh
     B2C_SYNC();
     B2C_FMARK(2);
 
-    // ---- phase C: threshold (:545-546), stable top-N (:548): rank = bucket prefix + order inside the
-    //      bucket; the owner of a selected candidate commits it as beam `rank` of the next frame and enters
-    //      its history key into the prune table (:550-552); grouping slots are released -------------------
+    // ---- buckets, phase C: threshold (:545-546), stable top-N (:548): rank = bucket prefix + order inside the
+    //      bucket; grouping slots are released -----------------------------------------------------------------
     u32* const bpre = S.bpre[b2c_warp_id()];
     b2c_bucket_scan_warp_v(S.bcnt, bpre);
     const double max_score = b2c_key_f64(b2c_max_slots(S.wmax));
     const double thr = max_score + P.prune_logp;
-    const u32 width = static_cast<u32>(P.beam_width);
     {
-        u32 my_top = 0;
         B2C_FOR(i, M) {
             const u64 key = S.ckey[i];
             {
@@ -526,39 +874,10 @@ B2C_HD void b2c_fast_step(const B2cParams& P, B2cFastSmem<WC, CAP, LT>& S, B2cCh
                 const u64 kj = S.ckey[j];
                 rank += (kj > key || (kj == key && j < static_cast<u32>(i))) ? 1u : 0u;
             }
-            if (rank >= width) continue;
-            if (WC < 128 && rank >= static_cast<u32>(WC)) {        // lean variant: more survivors than slots
-                b2c_atomic_or_u32(&S.sc.status, B2C_ERR_SLOTS);
-                continue;
-            }
-            if (rank + 1 > my_top) my_top = rank + 1;
-            const u32 last = S.clast[i];
-            if (prune) {
-                const u32 bl = S.cbk[last] & 0xFFFFu;
-                const u64 cph = S.cph[last];
-                const u32 type = static_cast<u32>(cph >> 61);
-                const u32 meta = S.cmeta[last];
-                u64 hh = cur.hist_hash[bl];
-                if ((type == 1 || type == 2) && cur.part_len[bl] > 0)       // a one-word history does not depend on the parent
-                    hh = P.hist_n == 1 ? b2c_hist_fold(B2C_HIST_SEED, cur.part_hash[bl])
-                                       : b2c_hist_extend(text_arena + cur.text_node[bl], P.hist_n, cur.part_hash[bl]);
-                const u64 hk = b2c_fast_key(hh, cph & B2C_PH_MASK, meta & 0xFFFFu, meta >> 16);
-                S.phk[rank] = hk;
-                b2c_fence_block();
-                u32 slot = static_cast<u32>(hk) & ptmask;
-                while (true) {
-                    const u32 rep = b2c_atomic_cas_u32(&S.pt_idx[slot], B2C_NONE_U32, rank);
-                    if (rep == B2C_NONE_U32) break;
-                    b2c_fence_block();
-                    if (S.phk[rep] == hk) break;
-                    slot = (slot + 1) & ptmask;
-                }
-                S.pslot[rank] = slot;
-                b2c_atomic_min_u32(&S.pt_min[slot], rank);
-            }
-            b2c_fast_commit(P, S, cur, nx, chain_arena, text_arena, text_cap, sb, slot, t, rank, static_cast<u32>(i), last, flags);
+            select(rank, static_cast<u32>(i), S.clast[i], S.cfold[i], flags);
         }
         b2c_warp_max_u32_slot(my_top, S.wtop);         // the selected ranks are exactly 0 .. max(wtop)-1
+    }
     }
     B2C_LAST_THREAD { S.holes = prune ? 1u : 0u; }
     B2C_FMARK(3);
@@ -813,7 +1132,6 @@ B2C_HD bool b2c_fast_scored_step(const B2cParams& P, B2cFastSmem<WC, CAP, LT>& S
 // fold, no score buckets.  Phases: liveness masks (and release of the previous prune entries) | ranks | commit
 // (one new beam per thread) -- the third barrier is the caller's.
 // -----------------------------------------------------------------------------------------
-#define B2C_SORTED_MAXK 8
 template <int WC, int CAP, int LT>
 B2C_HD bool b2c_fast_sorted_ok(const B2cParams& P, const B2cFastSmem<WC, CAP, LT>& S, int sb, int slot, int K, u32 prev_single) {
     if (prev_single == B2C_NONE_U32 || K < 2 || K > B2C_SORTED_MAXK || P.has_dup_labels) return false;
@@ -821,80 +1139,6 @@ B2C_HD bool b2c_fast_sorted_ok(const B2cParams& P, const B2cFastSmem<WC, CAP, LT
     u32 fl = 0;
     for (int k = 0; k < K; ++k) fl |= b2c_fast_tok<WC, CAP, LT>(S, sb, slot, k).flags;
     return (fl & B2C_TF_SPACE) == 0;
-}
-
-B2C_HD u32 b2c_live_before(const u32* wm, u32 pos) {   // live slots with index < pos (pos <= 32 * B2C_FAST_NW)
-    u32 c = 0;
-#if defined(__CUDACC__)
-#pragma unroll
-#endif
-    for (u32 w = 0; w < B2C_FAST_NW; ++w) {
-        const u32 lo = w * 32;
-        u32 m = wm[w];
-        if (pos < lo + 32) m = pos > lo ? (m & ((1u << (pos - lo)) - 1u)) : 0u;
-#if defined(__CUDA_ARCH__)
-        c += static_cast<u32>(__popc(m));
-#else
-        c += static_cast<u32>(__builtin_popcount(m));
-#endif
-    }
-    return c;
-}
-
-// The candidate scores of token k2 form the list cf[k2 * n + p] = (logit[p] + lp[k2]) + 0.0, p < n, non-increasing in p
-// (written once per frame by the slots' owners, phase 1 of b2c_fast_sorted_step).  b2c_sorted_counts answers NS
-// questions at once: how many leading entries of list q sort before the score s[q] -- entry >= s (ge) or > s.
-// "> s" is asked as ">= the next double above s" (scores are finite and never -0.0: x + 0.0), so a probe is ONE
-// shared-memory load and ONE comparison.  Three levels of independent probes per question (3 x stride 32, 3 x stride 8,
-// 8 x stride 1: 14 probes, 3 dependent rounds) and the NS questions interleaved: the frame is bound by
-// dependent-instruction latency, so the rounds of different questions overlap.
-B2C_HD double b2c_next_up(double s) {        // smallest double > s, for finite s that is not -0.0
-    union { double d; u64 u; } c;
-    c.d = s;
-    c.u = (c.u >> 63) ? c.u - 1 : c.u + 1;
-    return c.d;
-}
-B2C_HD u32 b2c_list_probe(const double* list, u32 n, u32 p, double s) {
-    const u32 q = p < n ? p : n - 1;        // clamped: the load is unconditional (no branch), the answer is masked
-    return (p < n && list[q] >= s) ? 1u : 0u;
-}
-template <int NS>
-B2C_HD void b2c_sorted_counts(const double* const (&list)[NS], u32 n, const double (&s)[NS], u32 (&cnt)[NS]) {
-    u32 base[NS];
-#if defined(__CUDACC__)
-#pragma unroll
-#endif
-    for (int q = 0; q < NS; ++q)
-        base[q] = 32 * (b2c_list_probe(list[q], n, 31, s[q]) + b2c_list_probe(list[q], n, 63, s[q]) + b2c_list_probe(list[q], n, 95, s[q]));
-#if defined(__CUDACC__)
-#pragma unroll
-#endif
-    for (int q = 0; q < NS; ++q)
-        base[q] += 8 * (b2c_list_probe(list[q], n, base[q] + 7, s[q]) + b2c_list_probe(list[q], n, base[q] + 15, s[q]) +
-                        b2c_list_probe(list[q], n, base[q] + 23, s[q]));
-#if defined(__CUDACC__)
-#pragma unroll
-#endif
-    for (int q = 0; q < NS; ++q) {
-        u32 c = 0;
-#if defined(__CUDACC__)
-#pragma unroll
-#endif
-        for (u32 r = 0; r < 8; ++r) c += b2c_list_probe(list[q], n, base[q] + r, s[q]);    // 8: in the last block of 8
-        cnt[q] = base[q] + c;                                                               // entry base + 7 was never probed
-    }
-}
-// one question against the list logit[p] + lp2 computed on the fly (unit test: tests/hostsim/t_sorted_count.cpp)
-template <int WC>
-B2C_HD u32 b2c_sorted_count(const double* logit, u32 n, double lp2, double s, bool ge) {
-    static_assert(WC <= 128, "radix search covers 128 slots");
-    double tmp[WC];
-    for (u32 p = 0; p < n; ++p) tmp[p] = (logit[p] + lp2) + 0.0;
-    const double* const l1[1] = {tmp};
-    const double s1[1] = {ge ? s : b2c_next_up(s)};
-    u32 c1[1];
-    b2c_sorted_counts<1>(l1, n, s1, c1);
-    return c1[0];
 }
 
 // returns false (state untouched) when the best score is not finite
@@ -947,76 +1191,17 @@ B2C_HD bool b2c_fast_sorted_step(const B2cParams& P, B2cFastSmem<WC, CAP, LT>& S
 
     // ---- phase 2: threshold (:545-546) and rank (:548) of every candidate ---------------------------
     {
-        u32 wm[B2C_FAST_NW];
-        for (int w = 0; w < B2C_FAST_NW; ++w) wm[w] = S.wmask[w];
         u32 my_top = 0;
-        const double* const cf = S.cfold;
-        // candidate (b, k) takes rank `rank` (if it is inside the beam width)
-        auto place = [&](u32 b, u32 k, u32 rank) {
-            if (rank >= width) return;
-            if (WC < 128 && rank >= static_cast<u32>(WC)) {        // lean variant: more survivors than slots
-                b2c_atomic_or_u32(&S.sc.status, B2C_ERR_SLOTS);
-                return;
-            }
-            S.ord[rank] = b | (k << 16);
-            if (rank + 1 > my_top) my_top = rank + 1;
-        };
-        B2C_FOR(b, n) {
-            if (!((S.wmask[b >> 5] >> (b & 31)) & 1u)) continue;
-            // same token: the live beams before this one (equal scores keep beam order).  Another token k2: its
-            // candidates that sort before (k, b) -- score greater, or equal and enumerated earlier (k2 < k).
-            const u32 lb = b2c_live_before(wm, static_cast<u32>(b));
-            const u32 ub = static_cast<u32>(b);
-            if (K == 2) {                       // both candidates of the beam at once
-                const double s0 = cf[ub], s1 = cf[n + ub];
-                const double* const l2[2] = {cf + n, cf};
-                const double q2[2] = {b2c_next_up(s0), s1};
-                u32 c2[2];
-                b2c_sorted_counts<2>(l2, n, q2, c2);
-                if (s0 >= thr) place(ub, 0u, lb + b2c_live_before(wm, c2[0]));
-                if (s1 >= thr) place(ub, 1u, lb + b2c_live_before(wm, c2[1]));
-            } else if (K == 3) {                // all six questions at once
-                const double s0 = cf[ub], s1 = cf[n + ub], s2 = cf[2 * n + ub];
-                const double u0 = b2c_next_up(s0), u1 = b2c_next_up(s1);
-                const double* const l6[6] = {cf + n, cf + 2 * n, cf, cf + 2 * n, cf, cf + n};
-                const double q6[6] = {u0, u0, s1, u1, s2, s2};
-                u32 c6[6];
-                b2c_sorted_counts<6>(l6, n, q6, c6);
-                if (s0 >= thr) place(ub, 0u, lb + b2c_live_before(wm, c6[0]) + b2c_live_before(wm, c6[1]));
-                if (s1 >= thr) place(ub, 1u, lb + b2c_live_before(wm, c6[2]) + b2c_live_before(wm, c6[3]));
-                if (s2 >= thr) place(ub, 2u, lb + b2c_live_before(wm, c6[4]) + b2c_live_before(wm, c6[5]));
-            } else {                            // K >= 4: per candidate, the other tokens three at a time
-                for (int k = 0; k < K; ++k) {
-                    const double s = cf[static_cast<u32>(k) * n + ub];
-                    if (!(s >= thr)) continue;
-                    const double su = b2c_next_up(s);
-                    u32 rank = lb;
-                    for (int k0 = 0; k0 < K && rank < width; k0 += 3) {
-                        const double* l3[3];
-                        double q3[3];
-                        bool on[3];
-#if defined(__CUDACC__)
-#pragma unroll
-#endif
-                        for (int j = 0; j < 3; ++j) {
-                            const int k2 = k0 + j;
-                            on[j] = k2 < K && k2 != k;
-                            l3[j] = cf + static_cast<u32>(on[j] ? k2 : k) * n;
-                            q3[j] = k2 < k ? s : su;
-                        }
-                        const double* const l3c[3] = {l3[0], l3[1], l3[2]};
-                        u32 c3[3];
-                        b2c_sorted_counts<3>(l3c, n, q3, c3);
-#if defined(__CUDACC__)
-#pragma unroll
-#endif
-                        for (int j = 0; j < 3; ++j)
-                            if (on[j]) rank += b2c_live_before(wm, c3[j]);
-                    }
-                    place(ub, static_cast<u32>(k), rank);
-                }
-            }
-        }
+        b2c_rank_list_items(S.cfold, n, K, S.wmask, 0u, S.wmask, thr, width,
+                            [](double, u32) { return 0u; },
+                            [&](u32, u32 k, u32 b, u32 rank) {
+                                if (WC < 128 && rank >= static_cast<u32>(WC)) {        // lean variant: more survivors than slots
+                                    b2c_atomic_or_u32(&S.sc.status, B2C_ERR_SLOTS);
+                                    return;
+                                }
+                                S.ord[rank] = b | (k << 16);
+                                if (rank + 1 > my_top) my_top = rank + 1;
+                            });
         b2c_warp_max_u32_slot(my_top, S.wtop);         // the selected ranks are exactly 0 .. max(wtop)-1
     }
     B2C_FMARK(21);
@@ -1255,7 +1440,7 @@ B2C_HD void b2c_beam_block_fast(const B2cBeamArgs& A, int slot_cta, u8* smem) {
             b2c_fast_work(S, L, g, 0, false, W);
             b2c_utt_begin(A.P, W, A.start_states ? A.start_states + u : nullptr, 1, B2cStreamIn{nullptr, 0u, nullptr, nullptr});
         }
-        B2C_FOR(s, SM::HT) {
+        B2C_FOR(s, SM::HT + 1) {
             S.ht_idx[s] = B2C_NONE_U32;
             S.ht_min[s] = B2C_NONE_U32;
             S.ht_max[s] = 0;
@@ -1269,6 +1454,7 @@ B2C_HD void b2c_beam_block_fast(const B2cBeamArgs& A, int slot_cta, u8* smem) {
             S.holes = 0;
             S.cheap_bad = 0;
             S.run_fail = B2C_NONE_U32;
+            S.n_merged = 0;
             for (int c = 0; c < B2C_FAST_NW; ++c) { S.wmax[c] = 0; S.wtop[c] = 0; S.wmask[c] = 0; }
             S.wtop[0] = 1;
             S.wmax[0] = b2c_f64_key(0.0);

@@ -1027,10 +1027,12 @@ __device__ inline void b2c_tokens_tiles_v32(const B2cPrepArgs& A, int block_idx,
 #pragma unroll
                 for (int qq = 0; qq < 8; ++qq) {
                     const float4 v = *reinterpret_cast<const float4*>(row + 4 * ((qq + lane) & 7));
-                    qs += __float2ull_rn(B2C_SM_MUL(b2c_sm_expf(v.x - m), 4294967296.0f));
-                    qs += __float2ull_rn(B2C_SM_MUL(b2c_sm_expf(v.y - m), 4294967296.0f));
-                    qs += __float2ull_rn(B2C_SM_MUL(b2c_sm_expf(v.z - m), 4294967296.0f));
-                    qs += __float2ull_rn(B2C_SM_MUL(b2c_sm_expf(v.w - m), 4294967296.0f));
+                    // rows with NaN / infinity (odd_row) are redone by the general routine below: the branch-free form
+                    // of the definition (bit-identical for finite rows) is enough here
+                    qs += b2c_sm_quantum_fast(v.x - m);
+                    qs += b2c_sm_quantum_fast(v.y - m);
+                    qs += b2c_sm_quantum_fast(v.z - m);
+                    qs += b2c_sm_quantum_fast(v.w - m);
                 }
                 lsf = b2c_sm_finish(qs, false, false);
                 // pass 3 in float32: (double)lp >= thr  <=>  lp >= thr rounded up to float32; the clip at log(1e-15)
