@@ -1224,12 +1224,6 @@ static int decode_batch_locked(b2c_decoder_t* d, const void* const* logits, cons
     P.prune_history = opts->prune_history ? 1 : 0;
     P.out_beams = OB;
     P.narrow_chain = (opts->text_only != 0 && !streaming) ? 1 : 0;
-    {
-        static const bool no_lists = std::getenv("B200CTC_NO_LISTS") != nullptr;
-        static const int gmax = std::getenv("B200CTC_LISTS_GMAX") ? std::atoi(std::getenv("B200CTC_LISTS_GMAX")) : B2C_LISTS_GMAX;
-        P.no_lists = no_lists ? 1 : 0;
-        P.lists_gmax = std::max(0, std::min(gmax, B2C_LISTS_GMAX));
-    }
     P.prune_logp = opts->beam_prune_logp;
     P.token_min_logp = opts->token_min_logp;
     P.alpha = d->alpha; P.beta = d->beta; P.unk_offset = d->unk;

@@ -118,7 +118,6 @@ struct B2cFastSmem {
     u32 holes;                                        // the current beam table has history-pruned slots (see b2c_fast_step)
     u32 cheap_bad;                                    // a thread's exactness check of b2c_fast_scored_step failed (rare)
     u32 run_fail;                                     // b2c_fast_run_step: first frame of the run whose exactness check failed
-    u32 n_merged;                                     // b2c_fast_step, list-ranked form: merged groups of the frame
     u32 wmask[B2C_FAST_NW];                           // per warp: live slots of the current table (b2c_fast_sorted_step)
 #if defined(B2C_PHASE_CLOCKS)
     u64 pclk[32];                                     // profiling builds: cycles between marks, thread 0
@@ -273,11 +272,11 @@ B2C_HD void b2c_bucket_scan_warp_v(const u32* bcnt, u32* pre) {
 
 #define B2C_INVALID_TOK 0xFFFEu      // last_tok of a history-pruned slot (BPE force logic skips it)
 
-// a group (merged logit_score `logit_new`, metadata of its last member `last`) becomes beam j of the next frame
-// (decoder.py:452-534); called by the thread that owns the group's leader, inside the ranking loop
+// candidate i (a group leader) becomes beam j of the next frame (decoder.py:452-534 metadata); called by the
+// thread that owns the candidate, inside the ranking loop
 template <int WC, int CAP, int LT>
 B2C_HD void b2c_fast_commit(const B2cParams& P, B2cFastSmem<WC, CAP, LT>& S, const B2cFastTab<WC>& cur, B2cFastTab<WC>& nx,
-                            B2cChain* chain_arena, B2cText* text_arena, u32 text_cap, int sb, int slot, int t, u32 j, double logit_new,
+                            B2cChain* chain_arena, B2cText* text_arena, u32 text_cap, int sb, int slot, int t, u32 j, u32 i,
                             u32 last, u32 flags) {
     const u32 bk = S.cbk[last];
     const u32 bl = bk & 0xFFFFu, k = bk >> 16;
@@ -289,7 +288,7 @@ B2C_HD void b2c_fast_commit(const B2cParams& P, B2cFastSmem<WC, CAP, LT>& S, con
     const u32 word_len = (type == 1 || type == 2) ? static_cast<u32>(cur.part_len[bl]) : 0u;
     u64 th = cur.text_hash[bl];
     if (word_len > 0) th = b2c_text_append(th, cur.part_hash[bl]);
-    nx.logit[j] = logit_new;
+    nx.logit[j] = S.cfold[i];
     nx.text_hash[j] = th;
     nx.part_hash[j] = part_hash;
     nx.part_len[j] = static_cast<u16>(part_len);
@@ -344,19 +343,7 @@ B2C_HD void b2c_fast_commit(const B2cParams& P, B2cFastSmem<WC, CAP, LT>& S, con
     nx.pscore[j] = ps;
 }
 
-// -----------------------------------------------------------------------------------------
-// one frame with at most CAP candidates and at most B2C_FAST_KS tokens, all in shared memory: three phases,
-// three block barriers (the third is issued by the caller after it has staged the next frame's tokens).
-//
-// Beam tables may have HOLES: the beam of rank r is written to slot r by the thread that ranked it, before the
-// history prune (decoder.py:550-552) is known; a slot is live iff it holds the best rank of its history key
-// (pt_min[pslot[r]] == r).  The next frame simply skips dead slots -- the relative order of the live beams,
-// which is all the reference's order dependence needs, is the rank order either way -- so there is no
-// compaction pass and no fourth phase.  S.holes says whether the current table is in that form; wtop / wmax
-// hold the number of slots and the best score key of the previous frame (per-warp maxima).
-// Invariants on entry: grouping table clear; prune table = entries pslot[0 .. n) iff S.holes.
-// -----------------------------------------------------------------------------------------
-// ---- helpers of the search-ranked steps (b2c_fast_sorted_step, list-ranked form of b2c_fast_step) ----------------
+// ---- helpers of the search-ranked step (b2c_fast_sorted_step) ---------------------------------------------------
 #define B2C_SORTED_MAXK 8
 B2C_HD u32 b2c_live_before(const u32* wm, u32 pos) {   // live slots with index < pos (pos <= 32 * B2C_FAST_NW)
     u32 c = 0;
@@ -390,8 +377,12 @@ B2C_HD double b2c_next_up(double s) {        // smallest double > s, for finite 
     return c.d;
 }
 B2C_HD u32 b2c_list_probe(const double* list, u32 n, u32 p, double s) {
-    const u32 q = p < n ? p : n - 1;        // clamped: the load is unconditional (no branch), the answer is masked
-    return (p < n && list[q] >= s) ? 1u : 0u;
+    // branch-free on purpose (a short-circuit && puts every probe into its own divergence region and serialises the
+    // loads): the index is clamped, the load unconditional, the answer masked
+    const u32 q = p < n ? p : n - 1;
+    const double v = list[q];
+    const u32 in_range = p < n ? 1u : 0u, hit = v >= s ? 1u : 0u;
+    return in_range & hit;
 }
 template <int NS>
 B2C_HD void b2c_sorted_counts(const double* const (&list)[NS], u32 n, const double (&s)[NS], u32 (&cnt)[NS]) {
@@ -432,8 +423,7 @@ B2C_HD u32 b2c_sorted_count(const double* logit, u32 n, double lp2, double s, bo
     return c1[0];
 }
 
-// Ranks of the candidates of a frame whose K candidate lists cf[k * n + b] are non-increasing in b (b2c_fast_sorted_step,
-// list-ranked form of b2c_fast_step).  Work items are the candidates i = k * n + b, strided over the threads -- NOT
+// Ranks of the candidates of a frame whose K candidate lists cf[k * n + b] are non-increasing in b (b2c_fast_sorted_step).  Work items are the candidates i = k * n + b, strided over the threads -- NOT
 // "a slot and its K candidates per thread": the candidates that can still land inside the beam width are the first few
 // entries of every list (a candidate of the r-th best token has at least r + 1 lists in front of its own position), so
 // per-slot work would leave the whole frame waiting for the threads of the first slots (K (K - 1) searches each).
@@ -463,9 +453,11 @@ B2C_HD void b2c_rank_list_items(const double* cf, u32 n, int K, const u32* masks
         if (K > 1) {
             // another list k2: its entries that sort before (k, b) -- score greater, or equal and enumerated earlier (k2 < k)
             u32 npass = 0;
-            for (int k2 = 0; k2 < K; ++k2) {
-                if (k2 == static_cast<int>(k)) continue;
-                npass += cf[static_cast<u32>(k2) * n + b] >= (k2 < static_cast<int>(k) ? s : su) ? 1u : 0u;
+            for (int k2 = 0; k2 < K; ++k2) {        // branch-free: the own list is probed too and masked
+                const double v = cf[static_cast<u32>(k2) * n + b];
+                const u32 other = static_cast<u32>(k2) != k ? 1u : 0u;
+                const u32 hit = v >= (static_cast<u32>(k2) < k ? s : su) ? 1u : 0u;
+                npass += other & hit;
             }
             if (npass > 0 && rank + npass * b2c_live_before(mask_all, b + 1) >= width) continue;
             for (int q0 = 0; q0 < K - 1 && rank < width; q0 += 3) {
@@ -500,28 +492,17 @@ B2C_HD void b2c_rank_list_items(const double* cf, u32 n, int K, const u32* masks
     }
 }
 
-#define B2C_LISTS_GMAX 64       // most merged groups of a frame the list-ranked form handles (more: score buckets)
-
 // -----------------------------------------------------------------------------------------
-// b2c_fast_step ranks in one of two ways after the same expansion and grouping (phase A):
+// one frame with at most CAP candidates and at most B2C_FAST_KS tokens, all in shared memory: three phases,
+// three block barriers (the third is issued by the caller after it has staged the next frame's tokens).
 //
-// (1) LISTS (no LM, no hotwords, regular alphabet, K <= 8 tokens): lm_score == logit_score + 0, the slots of the
-//     current table are in score order, so the candidates of token k -- cfold[k * n + b] = logit[b] + lp_k, b in slot
-//     order -- are a NON-INCREASING list.  Merging (decoder.py:211-224) touches few of them: a group of >= 2 equal
-//     keys becomes ONE "merged group" whose score is the log-sum-exp of its members and whose place among equal scores
-//     is its first member's.  So the rank of a candidate in the stable sort of decoder.py:548 is
-//         sum over the K lists of (unmerged live entries that sort before it)  +  (merged groups that sort before it)
-//     -- a prefix population count in its own list, one three-level search per other list (b2c_sorted_counts, the
-//     searches of a thread interleaved), and a walk over the short list of merged groups; for a merged group two
-//     searches per list (scores greater / greater-or-equal: among equal scores the entries enumerated before its
-//     first member precede it).  No score buckets: no bucket clear, no bucket atomics, no prefix scan, no in-bucket
-//     walk.  Per-list masks of the unmerged live entries come from warp ballots (U, behind the merged groups); the merged groups
-//     (score, first member, last member) live in the bucket arrays, which this form does not use otherwise.
-//     More than B2C_LISTS_GMAX merged groups, or a best score that is not finite: the frame continues with (2) on
-//     the same grouping (nothing of phase A is redone).
-// (2) BUCKETS (everything else): fold, fuse, 256 monotone score buckets | threshold, bucket prefix + order inside the
-//     bucket, commit.
-// Both commit through b2c_fast_commit and leave the same state (beam table with holes, prune table, wtop / wmax).
+// Beam tables may have HOLES: the beam of rank r is written to slot r by the thread that ranked it, before the
+// history prune (decoder.py:550-552) is known; a slot is live iff it holds the best rank of its history key
+// (pt_min[pslot[r]] == r).  The next frame simply skips dead slots -- the relative order of the live beams,
+// which is all the reference's order dependence needs, is the rank order either way -- so there is no
+// compaction pass and no fourth phase.  S.holes says whether the current table is in that form; wtop / wmax
+// hold the number of slots and the best score key of the previous frame (per-warp maxima).
+// Invariants on entry: grouping table clear; prune table = entries pslot[0 .. n) iff S.holes.
 // -----------------------------------------------------------------------------------------
 template <int WC, int CAP, int LT>
 B2C_HD void b2c_fast_step(const B2cParams& P, B2cFastSmem<WC, CAP, LT>& S, B2cChain* chain_arena, B2cText* text_arena,
@@ -537,14 +518,6 @@ B2C_HD void b2c_fast_step(const B2cParams& P, B2cFastSmem<WC, CAP, LT>& S, B2cCh
     const double ref = b2c_key_f64(b2c_max_slots(S.wmax));     // best score of the previous frame
     const double bscale = P.bucket_scale;
     constexpr u32 hmask = SM::HT - 1, ptmask = SM::PT - 1;
-    constexpr u32 kDeadSlot = SM::HT;                          // grouping slot of the candidates of dead beams: never claimed
-    const bool lists = !is_bpe && (flags & B2C_FL_PSCORE) == 0 && K <= B2C_SORTED_MAXK && P.no_lists == 0;
-    // lists: U[k][warp], unmerged live entries of list k (+ one row: unmerged in every list), behind the merged groups
-    u32* const umask = &S.bpre[0][0] + 2 * B2C_LISTS_GMAX;
-    static_assert(2 * B2C_LISTS_GMAX + B2C_FAST_NW * (B2C_SORTED_MAXK + 1) <= B2C_NBUCKET, "scratch of the list-ranked form fits one prefix row");
-    double* const mg_score = reinterpret_cast<double*>(&S.bpre[0][0]);   // lists: merged groups
-    u32* const mg_first = S.bcnt;
-    u32* const mg_last = S.bhead;
     B2C_FMARK(0);
 
     if (is_bpe) {
@@ -559,27 +532,9 @@ B2C_HD void b2c_fast_step(const B2cParams& P, B2cFastSmem<WC, CAP, LT>& S, B2cCh
     }
 
     // ---- phase A: expand (decoder.py:447-534), merge key, grouping ---------------------------------
-    if (!lists) {
-        B2C_FOR(s, B2C_NBUCKET) { S.bcnt[s] = 0; S.bhead[s] = B2C_NONE_U32; }
-    } else {
-        B2C_LEADER { S.n_merged = 0; }
-        B2C_FOR(q, B2C_FAST_NW * (B2C_SORTED_MAXK + 1)) { umask[q] = 0; }    // words of warps that do not exist (one-warp variant) stay 0
-#if !defined(__CUDA_ARCH__)
-        for (int w = 0; w < B2C_FAST_NW; ++w) S.wmask[w] = 0;
-#endif
-    }
-    B2C_FOR(b, (lists ? static_cast<u32>(WC) : n)) {
-        const bool in_range = static_cast<u32>(b) < n;
-        const bool live = in_range && (!holes || S.pt_min[S.pslot[b]] == static_cast<u32>(b));
-        if (lists) {      // which slots are live: the later phases must not look at the prune table (it is released in between)
-#if defined(__CUDA_ARCH__)
-            const u32 lm = __ballot_sync(0xFFFFFFFFu, live);
-            if ((threadIdx.x & 31) == 0) S.wmask[threadIdx.x >> 5] = lm;
-#else
-            if (live) S.wmask[b >> 5] |= 1u << (b & 31);
-#endif
-        }
-        if (!in_range) continue;
+    B2C_FOR(s, B2C_NBUCKET) { S.bcnt[s] = 0; S.bhead[s] = B2C_NONE_U32; }
+    B2C_FOR(b, n) {
+        const bool live = !holes || S.pt_min[S.pslot[b]] == static_cast<u32>(b);
         const u32 plen = cur.part_len[b];
         const u64 ph = cur.part_hash[b];
         const u64 th0 = cur.text_hash[b];
@@ -587,11 +542,9 @@ B2C_HD void b2c_fast_step(const B2cParams& P, B2cFastSmem<WC, CAP, LT>& S, B2cCh
         const double lg = cur.logit[b];
         for (int k = 0; k < K; ++k) {
             const u32 i = static_cast<u32>(k) * n + static_cast<u32>(b);
-            if (!live) {                                           // never a group leader (phase B), key 0 in phase C;
-                S.cslot[i] = kDeadSlot;                            // a dead slot keeps its place in the lists
-                if (lists) S.cfold[i] = lg + S.rlp[slot][k];
-                continue;
-            }
+            // a dead beam's candidates sit in a grouping slot of their own that nobody claims: never a group leader
+            // (phase B), key 0 in phase C, and never mistaken for a member of the group that owns slot 0
+            if (!live) { S.cslot[i] = SM::HT; continue; }
             const B2cTok ti = b2c_fast_tok<WC, CAP, LT>(S, sb, slot, k);
             u64 th = th0;
             u64 nph;
@@ -635,167 +588,14 @@ B2C_HD void b2c_fast_step(const B2cParams& P, B2cFastSmem<WC, CAP, LT>& S, B2cCh
     B2C_SYNC();
     B2C_FMARK(1);
 
-    // the validity tests of phase A are done: release the previous frame's prune entries
-    if (holes) {
+    // ---- phase B: fold each group (decoder.py:211-224), LM / hotword fusion (:346-424), bucket, max ---
+    if (holes) {   // the validity tests of phase A are done: release the previous frame's prune entries
         B2C_FOR(r, n) {
             const u32 s = S.pslot[r];
             S.pt_idx[s] = B2C_NONE_U32;
             S.pt_min[s] = B2C_NONE_U32;
         }
     }
-    const u32 width = static_cast<u32>(P.beam_width);
-    // the owner of a selected group commits it as beam `rank` of the next frame and enters its history key into the
-    // prune table (decoder.py:550-552); `i`: first member (leader), `last`: last member, `lg`: merged logit_score
-    u32 my_top = 0;
-    auto select = [&](u32 rank, u32 i, u32 last, double lg, u32 fl) {
-        if (rank >= width) return;
-        if (WC < 128 && rank >= static_cast<u32>(WC)) {        // lean variant: more survivors than slots
-            b2c_atomic_or_u32(&S.sc.status, B2C_ERR_SLOTS);
-            return;
-        }
-        if (rank + 1 > my_top) my_top = rank + 1;
-        if (prune) {
-            const u32 bl = S.cbk[last] & 0xFFFFu;
-            const u64 cph = S.cph[last];
-            const u32 type = static_cast<u32>(cph >> 61);
-            const u32 meta = S.cmeta[last];
-            u64 hh = cur.hist_hash[bl];
-            if ((type == 1 || type == 2) && cur.part_len[bl] > 0)       // a one-word history does not depend on the parent
-                hh = P.hist_n == 1 ? b2c_hist_fold(B2C_HIST_SEED, cur.part_hash[bl])
-                                   : b2c_hist_extend(text_arena + cur.text_node[bl], P.hist_n, cur.part_hash[bl]);
-            const u64 hk = b2c_fast_key(hh, cph & B2C_PH_MASK, meta & 0xFFFFu, meta >> 16);
-            S.phk[rank] = hk;
-            b2c_fence_block();
-            u32 pslot = static_cast<u32>(hk) & ptmask;
-            while (true) {
-                const u32 rep = b2c_atomic_cas_u32(&S.pt_idx[pslot], B2C_NONE_U32, rank);
-                if (rep == B2C_NONE_U32) break;
-                b2c_fence_block();
-                if (S.phk[rep] == hk) break;
-                pslot = (pslot + 1) & ptmask;
-            }
-            S.pslot[rank] = pslot;
-            b2c_atomic_min_u32(&S.pt_min[pslot], rank);
-        }
-        b2c_fast_commit(P, S, cur, nx, chain_arena, text_arena, text_cap, sb, slot, t, rank, lg, last, fl);
-    };
-    // list-ranked form: no LM, no hotwords, regular alphabet -- known at compile time in its copies of the commit code
-    const u32 lflags = flags & ~static_cast<u32>(B2C_FL_PSCORE | B2C_FL_LM | B2C_FL_BPE);
-
-    bool buckets = !lists;
-    if (lists) {
-        // ---- lists, phase B: merged groups (fold, decoder.py:211-224), masks of the unmerged live entries, max ----
-        u64 tmax = 0;
-        B2C_FOR(b, WC) {
-            const bool live = static_cast<u32>(b) < n && ((S.wmask[b >> 5] >> (b & 31)) & 1u) != 0;
-            bool unmerged_all = live;                               // unmerged in every list (row B2C_SORTED_MAXK of U)
-            for (int k = 0; k < K; ++k) {
-                const u32 i = static_cast<u32>(k) * n + static_cast<u32>(b);
-                bool unmerged = false;
-                if (live) {
-                    const u32 gs = S.cslot[i];
-                    const u32 cnt = S.ht_cnt[gs] + 1;
-                    if (cnt == 1) {
-                        unmerged = true;
-                        const u64 key = b2c_f64_key(S.cfold[i] + 0.0);
-                        if (key > tmax) tmax = key;
-                    } else {
-                        u32 first = S.ht_idx[gs], last = first;
-                        const u32 lo = S.ht_min[gs], hi = S.ht_max[gs];
-                        first = lo < first ? lo : first;
-                        last = hi > last ? hi : last;
-                        if (first == i) {
-                            double sm = S.cfold[i];
-                            for (u32 j = (cnt == 2) ? last : i + 1; j <= last; ++j) {
-                                if (S.cslot[j] != gs) continue;
-                                sm = b2c_sum_log_scores_ool(sm, S.cfold[j]);
-                            }
-                            const u32 g = b2c_atomic_add_u32(&S.n_merged, 1u);
-                            if (g < B2C_LISTS_GMAX) {
-                                mg_score[g] = sm;
-                                mg_first[g] = i;
-                                mg_last[g] = last;
-                            }
-                            const u64 key = b2c_f64_key(sm + 0.0);
-                            if (key > tmax) tmax = key;
-                        }
-                    }
-                }
-                unmerged_all = unmerged_all && unmerged;
-#if defined(__CUDA_ARCH__)
-                const u32 um = __ballot_sync(0xFFFFFFFFu, unmerged);
-                if ((threadIdx.x & 31) == 0) umask[B2C_FAST_NW * k + (threadIdx.x >> 5)] = um;
-#else
-                if (unmerged) umask[B2C_FAST_NW * k + (b >> 5)] |= 1u << (b & 31);
-#endif
-            }
-#if defined(__CUDA_ARCH__)
-            const u32 ua = __ballot_sync(0xFFFFFFFFu, unmerged_all);
-            if ((threadIdx.x & 31) == 0) umask[B2C_FAST_NW * B2C_SORTED_MAXK + (threadIdx.x >> 5)] = ua;
-#else
-            if (unmerged_all) umask[B2C_FAST_NW * B2C_SORTED_MAXK + (b >> 5)] |= 1u << (b & 31);
-#endif
-        }
-        b2c_warp_max_u64_slot(tmax, S.wmax);
-        B2C_SYNC();
-        B2C_FMARK(2);
-        const u32 G = S.n_merged;
-        const double max_score = b2c_key_f64(b2c_max_slots(S.wmax));
-        if (G > static_cast<u32>(P.lists_gmax) || !(max_score >= -1.7976931348623157e308)) {
-            // block-uniform, rare: rank this frame with the score buckets (its arrays were the merged-group scratch)
-            buckets = true;
-            B2C_SYNC();
-            B2C_FOR(s, B2C_NBUCKET) { S.bcnt[s] = 0; S.bhead[s] = B2C_NONE_U32; }
-            B2C_SYNC();
-        } else {
-            // ---- lists, phase C: threshold (:545-546), rank by search (:548), commit; grouping slots are released ----
-            const double thr = max_score + P.prune_logp;
-            const double* const cf = S.cfold;
-            // merged groups that sort before a group of score s whose first member is candidate i
-            auto merged_ahead = [&](double s, u32 i) {
-                u32 c = 0;
-                for (u32 g = 0; g < G; ++g) {
-                    const double sg = mg_score[g] + 0.0;
-                    c += (sg > s || (sg == s && mg_first[g] < i)) ? 1u : 0u;
-                }
-                return c;
-            };
-            B2C_FOR(i, M) {                                         // every candidate releases its grouping slot
-                const u32 gs = S.cslot[i];
-                S.ht_idx[gs] = B2C_NONE_U32;
-                S.ht_min[gs] = B2C_NONE_U32;
-                S.ht_max[gs] = 0;
-                S.ht_cnt[gs] = 0;
-            }
-            // the unmerged candidates
-            b2c_rank_list_items(cf, n, K, umask, static_cast<u32>(B2C_FAST_NW), umask + B2C_FAST_NW * B2C_SORTED_MAXK, thr, width, merged_ahead,
-                                [&](u32 i, u32, u32, u32 rank) { select(rank, i, i, cf[i], lflags); });
-            // the merged groups, one per work item: entries with a greater score, or an equal score and enumerated
-            // before the group's first member, precede it
-            B2C_FOR(g, G) {
-                const double sm = mg_score[g], s = sm + 0.0;
-                if (!(s >= thr)) continue;
-                const u32 i = mg_first[g];
-                const double su = b2c_next_up(s);
-                u32 rank = merged_ahead(s, i);
-                for (int k2 = 0; k2 < K && rank < width; ++k2) {
-                    const double* const l2[2] = {cf + static_cast<u32>(k2) * n, cf + static_cast<u32>(k2) * n};
-                    const double q2[2] = {su, s};
-                    u32 c2[2];
-                    b2c_sorted_counts<2>(l2, n, q2, c2);               // entries > s, entries >= s
-                    const u32 base_k2 = static_cast<u32>(k2) * n;
-                    u32 pos = i > base_k2 ? i - base_k2 : 0u;          // entries of this list enumerated before candidate i
-                    pos = pos < c2[0] ? c2[0] : (pos > c2[1] ? c2[1] : pos);
-                    rank += b2c_live_before(umask + B2C_FAST_NW * k2, pos);
-                }
-                select(rank, i, mg_last[g], sm, lflags);
-            }
-            b2c_warp_max_u32_slot(my_top, S.wtop);         // the selected ranks are exactly 0 .. max(wtop)-1
-        }
-    }
-
-    if (buckets) {
-    // ---- buckets, phase B: fold each group (decoder.py:211-224), LM / hotword fusion (:346-424), bucket, max ---
     {
         u64 tmax = 0;
         B2C_FOR(i, M) {
@@ -847,13 +647,16 @@ B2C_HD void b2c_fast_step(const B2cParams& P, B2cFastSmem<WC, CAP, LT>& S, B2cCh
     B2C_SYNC();
     B2C_FMARK(2);
 
-    // ---- buckets, phase C: threshold (:545-546), stable top-N (:548): rank = bucket prefix + order inside the
-    //      bucket; grouping slots are released -----------------------------------------------------------------
+    // ---- phase C: threshold (:545-546), stable top-N (:548): rank = bucket prefix + order inside the
+    //      bucket; the owner of a selected candidate commits it as beam `rank` of the next frame and enters
+    //      its history key into the prune table (:550-552); grouping slots are released -------------------
     u32* const bpre = S.bpre[b2c_warp_id()];
     b2c_bucket_scan_warp_v(S.bcnt, bpre);
     const double max_score = b2c_key_f64(b2c_max_slots(S.wmax));
     const double thr = max_score + P.prune_logp;
+    const u32 width = static_cast<u32>(P.beam_width);
     {
+        u32 my_top = 0;
         B2C_FOR(i, M) {
             const u64 key = S.ckey[i];
             {
@@ -874,10 +677,39 @@ B2C_HD void b2c_fast_step(const B2cParams& P, B2cFastSmem<WC, CAP, LT>& S, B2cCh
                 const u64 kj = S.ckey[j];
                 rank += (kj > key || (kj == key && j < static_cast<u32>(i))) ? 1u : 0u;
             }
-            select(rank, static_cast<u32>(i), S.clast[i], S.cfold[i], flags);
+            if (rank >= width) continue;
+            if (WC < 128 && rank >= static_cast<u32>(WC)) {        // lean variant: more survivors than slots
+                b2c_atomic_or_u32(&S.sc.status, B2C_ERR_SLOTS);
+                continue;
+            }
+            if (rank + 1 > my_top) my_top = rank + 1;
+            const u32 last = S.clast[i];
+            if (prune) {
+                const u32 bl = S.cbk[last] & 0xFFFFu;
+                const u64 cph = S.cph[last];
+                const u32 type = static_cast<u32>(cph >> 61);
+                const u32 meta = S.cmeta[last];
+                u64 hh = cur.hist_hash[bl];
+                if ((type == 1 || type == 2) && cur.part_len[bl] > 0)       // a one-word history does not depend on the parent
+                    hh = P.hist_n == 1 ? b2c_hist_fold(B2C_HIST_SEED, cur.part_hash[bl])
+                                       : b2c_hist_extend(text_arena + cur.text_node[bl], P.hist_n, cur.part_hash[bl]);
+                const u64 hk = b2c_fast_key(hh, cph & B2C_PH_MASK, meta & 0xFFFFu, meta >> 16);
+                S.phk[rank] = hk;
+                b2c_fence_block();
+                u32 slot = static_cast<u32>(hk) & ptmask;
+                while (true) {
+                    const u32 rep = b2c_atomic_cas_u32(&S.pt_idx[slot], B2C_NONE_U32, rank);
+                    if (rep == B2C_NONE_U32) break;
+                    b2c_fence_block();
+                    if (S.phk[rep] == hk) break;
+                    slot = (slot + 1) & ptmask;
+                }
+                S.pslot[rank] = slot;
+                b2c_atomic_min_u32(&S.pt_min[slot], rank);
+            }
+            b2c_fast_commit(P, S, cur, nx, chain_arena, text_arena, text_cap, sb, slot, t, rank, static_cast<u32>(i), last, flags);
         }
         b2c_warp_max_u32_slot(my_top, S.wtop);         // the selected ranks are exactly 0 .. max(wtop)-1
-    }
     }
     B2C_LAST_THREAD { S.holes = prune ? 1u : 0u; }
     B2C_FMARK(3);
@@ -1454,7 +1286,6 @@ B2C_HD void b2c_beam_block_fast(const B2cBeamArgs& A, int slot_cta, u8* smem) {
             S.holes = 0;
             S.cheap_bad = 0;
             S.run_fail = B2C_NONE_U32;
-            S.n_merged = 0;
             for (int c = 0; c < B2C_FAST_NW; ++c) { S.wmax[c] = 0; S.wtop[c] = 0; S.wmask[c] = 0; }
             S.wtop[0] = 1;
             S.wmax[0] = b2c_f64_key(0.0);

@@ -178,8 +178,6 @@ struct B2cParams {
     int hist_n;                // max(1, lm order - 1)   (reference decoder.py:244)
     int out_beams;             // beams returned per utterance (1 for decode_batch)
     int narrow_chain;          // text-only calls: 8-byte backtrack nodes (no word frames), b2c_chain_store / _load
-    int no_lists;              // latency-first kernel: rank every frame with the score buckets (B200CTC_NO_LISTS; measurements, tests)
-    int lists_gmax;            // latency-first kernel: most merged groups of a list-ranked frame (<= B2C_LISTS_GMAX; tests lower it)
     double prune_logp;
     double token_min_logp;
     double alpha, beta, unk_offset, log_base_change;

@@ -15,14 +15,13 @@ if [ -f $V/libb200ctc_base.so ]; then
   B200CTC_PROFILING_LIB=$V/libb200ctc_base.so timeout 300 python bench.py --no-secondary --no-cpu-baseline > $O/bench_base.json 2> $O/bench_base.err
 fi
 B200CTC_NO_HINTED=1 timeout 300 python bench.py --no-secondary --no-cpu-baseline > $O/bench_new_nohint.json 2> $O/bench_new_nohint.err
-B200CTC_NO_LISTS=1 timeout 300 python bench.py --no-secondary --no-cpu-baseline > $O/bench_new_nolists.json 2> $O/bench_new_nolists.err
 timeout 300 python bench.py --no-secondary --no-cpu-baseline > $O/bench_new.json 2> $O/bench_new.err
 B200CTC_HOST_PROFILE=1 timeout 300 python bench.py --no-secondary --no-cpu-baseline --steps 5 > /dev/null 2> $O/bench_new_hostprof.err
 if [ -f $V/libb200ctc_clk.so ]; then
   B200CTC_PROFILING_LIB=$V/libb200ctc_clk.so timeout 300 python bench.py --no-secondary --no-cpu-baseline --steps 3 > $O/bench_clk.json 2> $O/phase_clocks.txt
 fi
 echo "== secondary entries"; date
-timeout 600 python bench.py --no-cpu-baseline --secondary c4,c3,diffuse,beam10,beam50 > $O/bench_new_secondary.json 2> $O/bench_new_secondary.err
+timeout 600 python bench.py --no-cpu-baseline --secondary c3,beam10,beam50 > $O/bench_new_secondary.json 2> $O/bench_new_secondary.err
 if [ -f $V/libb200ctc_base.so ]; then
   B200CTC_PROFILING_LIB=$V/libb200ctc_base.so timeout 600 python bench.py --no-cpu-baseline --secondary c4 > $O/bench_base_secondary.json 2> $O/bench_base_secondary.err
 fi
