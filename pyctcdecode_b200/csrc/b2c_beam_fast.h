@@ -367,9 +367,7 @@ B2C_HD u32 b2c_live_before(const u32* wm, u32 pos) {   // live slots with index 
 // (written once per frame by the slots' owners, phase 1 of b2c_fast_sorted_step).  b2c_sorted_counts answers NS
 // questions at once: how many leading entries of list q sort before the score s[q] -- entry >= s (ge) or > s.
 // "> s" is asked as ">= the next double above s" (scores are finite and never -0.0: x + 0.0), so a probe is ONE
-// shared-memory load and ONE comparison.  Three levels of independent probes per question (3 x stride 32, 3 x stride 8,
-// 8 x stride 1: 14 probes, 3 dependent rounds) and the NS questions interleaved: the frame is bound by
-// dependent-instruction latency, so the rounds of different questions overlap.
+// shared-memory load and ONE comparison; the NS questions advance in lockstep so that their rounds overlap.
 B2C_HD double b2c_next_up(double s) {        // smallest double > s, for finite s that is not -0.0
     union { double d; u64 u; } c;
     c.d = s;
@@ -386,29 +384,29 @@ B2C_HD u32 b2c_list_probe(const double* list, u32 n, u32 p, double s) {
 }
 template <int NS>
 B2C_HD void b2c_sorted_counts(const double* const (&list)[NS], u32 n, const double (&s)[NS], u32 (&cnt)[NS]) {
-    u32 base[NS];
+    // branch-free binary search, the NS questions in lockstep: the count grows by `step` whenever entry count + step - 1
+    // still sorts before s.  ~7 instructions per probe and question, log2(n) dependent rounds; the rounds of the NS
+    // questions overlap (the frame is bound by instruction count x dependent-issue latency, not by the loads).
+    u32 pos[NS];
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
-    for (int q = 0; q < NS; ++q)
-        base[q] = 32 * (b2c_list_probe(list[q], n, 31, s[q]) + b2c_list_probe(list[q], n, 63, s[q]) + b2c_list_probe(list[q], n, 95, s[q]));
+    for (int q = 0; q < NS; ++q) pos[q] = 0;
+    u32 step = 128;
+    while (step > n) step >>= 1;            // n >= 1; block-uniform
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+    for (; step > 0; step >>= 1) {
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
-    for (int q = 0; q < NS; ++q)
-        base[q] += 8 * (b2c_list_probe(list[q], n, base[q] + 7, s[q]) + b2c_list_probe(list[q], n, base[q] + 15, s[q]) +
-                        b2c_list_probe(list[q], n, base[q] + 23, s[q]));
-#if defined(__CUDACC__)
-#pragma unroll
-#endif
-    for (int q = 0; q < NS; ++q) {
-        u32 c = 0;
-#if defined(__CUDACC__)
-#pragma unroll
-#endif
-        for (u32 r = 0; r < 8; ++r) c += b2c_list_probe(list[q], n, base[q] + r, s[q]);    // 8: in the last block of 8
-        cnt[q] = base[q] + c;                                                               // entry base + 7 was never probed
+        for (int q = 0; q < NS; ++q) pos[q] += step * b2c_list_probe(list[q], n, pos[q] + step - 1, s[q]);
     }
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int q = 0; q < NS; ++q) cnt[q] = pos[q];
 }
 // one question against the list logit[p] + lp2 computed on the fly (unit test: tests/hostsim/t_sorted_count.cpp)
 template <int WC>
@@ -429,7 +427,7 @@ B2C_HD u32 b2c_sorted_count(const double* logit, u32 n, double lp2, double s, bo
 // per-slot work would leave the whole frame waiting for the threads of the first slots (K (K - 1) searches each).
 // An item first looks at ENTRY b OF EVERY OTHER LIST: where that entry already sorts before the candidate, so do all
 // entries above it -- a lower bound on the rank that needs no search and discards most items; the survivors run one
-// three-level search per other list (three lists interleaved).
+// binary search per other list (three lists in lockstep).
 //   masks + mstride * k   eligible entries of list k (bit b; 4 words): live slots (sorted step, mstride 0) or unmerged
 //                         live entries (list-ranked step, mstride 4)
 //   mask_all              entries eligible in EVERY list (a subset of each list's mask: the lower bound counts it)
@@ -672,10 +670,12 @@ B2C_HD void b2c_fast_step(const B2cParams& P, B2cFastSmem<WC, CAP, LT>& S, B2cCh
             const u32 bkt = b2c_bucket(ref, sco, bscale);
             u32 rank = bpre[bkt];
             if (rank >= width) continue;          // every candidate of a better bucket outranks it: no need to walk its own
-            for (u32 j = S.bhead[bkt]; j != B2C_NONE_U32; j = S.cnext[j]) {
-                if (j == static_cast<u32>(i)) continue;
+            for (u32 j = S.bhead[bkt]; j != B2C_NONE_U32;) {      // the candidate itself adds 0; both loads of a step are independent
                 const u64 kj = S.ckey[j];
-                rank += (kj > key || (kj == key && j < static_cast<u32>(i))) ? 1u : 0u;
+                const u32 jn = S.cnext[j];
+                const u32 gt = kj > key ? 1u : 0u, eq_before = (kj == key ? 1u : 0u) & (j < static_cast<u32>(i) ? 1u : 0u);
+                rank += gt | eq_before;
+                j = jn;
             }
             if (rank >= width) continue;
             if (WC < 128 && rank >= static_cast<u32>(WC)) {        // lean variant: more survivors than slots
@@ -1024,16 +1024,53 @@ B2C_HD bool b2c_fast_sorted_step(const B2cParams& P, B2cFastSmem<WC, CAP, LT>& S
     // ---- phase 2: threshold (:545-546) and rank (:548) of every candidate ---------------------------
     {
         u32 my_top = 0;
-        b2c_rank_list_items(S.cfold, n, K, S.wmask, 0u, S.wmask, thr, width,
-                            [](double, u32) { return 0u; },
-                            [&](u32, u32 k, u32 b, u32 rank) {
-                                if (WC < 128 && rank >= static_cast<u32>(WC)) {        // lean variant: more survivors than slots
-                                    b2c_atomic_or_u32(&S.sc.status, B2C_ERR_SLOTS);
-                                    return;
-                                }
-                                S.ord[rank] = b | (k << 16);
-                                if (rank + 1 > my_top) my_top = rank + 1;
-                            });
+        // candidate (b, k) takes rank `rank` (if it is inside the beam width)
+        auto place = [&](u32 b, u32 k, u32 rank) {
+            if (rank >= width) return;
+            if (WC < 128 && rank >= static_cast<u32>(WC)) {        // lean variant: more survivors than slots
+                b2c_atomic_or_u32(&S.sc.status, B2C_ERR_SLOTS);
+                return;
+            }
+            S.ord[rank] = b | (k << 16);
+            if (rank + 1 > my_top) my_top = rank + 1;
+        };
+        if (K <= 3) {
+            // two or three tokens (84 % of these frames): a slot and its candidates per thread, all its questions in
+            // lockstep.  Same token: the live beams before this one (equal scores keep beam order); another token k2:
+            // its candidates that sort before (k, b) -- score greater, or equal and enumerated earlier (k2 < k).
+            u32 wm[B2C_FAST_NW];
+            for (int w = 0; w < B2C_FAST_NW; ++w) wm[w] = S.wmask[w];
+            const double* const cf = S.cfold;
+            B2C_FOR(b, n) {
+                if (!((S.wmask[b >> 5] >> (b & 31)) & 1u)) continue;
+                const u32 ub = static_cast<u32>(b);
+                const u32 lb = b2c_live_before(wm, ub);
+                if (K == 2) {
+                    const double s0 = cf[ub], s1 = cf[n + ub];
+                    const double* const l2[2] = {cf + n, cf};
+                    const double q2[2] = {b2c_next_up(s0), s1};
+                    u32 c2[2];
+                    b2c_sorted_counts<2>(l2, n, q2, c2);
+                    if (s0 >= thr) place(ub, 0u, lb + b2c_live_before(wm, c2[0]));
+                    if (s1 >= thr) place(ub, 1u, lb + b2c_live_before(wm, c2[1]));
+                } else {
+                    const double s0 = cf[ub], s1 = cf[n + ub], s2 = cf[2 * n + ub];
+                    const double u0 = b2c_next_up(s0), u1 = b2c_next_up(s1);
+                    const double* const l6[6] = {cf + n, cf + 2 * n, cf, cf + 2 * n, cf, cf + n};
+                    const double q6[6] = {u0, u0, s1, u1, s2, s2};
+                    u32 c6[6];
+                    b2c_sorted_counts<6>(l6, n, q6, c6);
+                    if (s0 >= thr) place(ub, 0u, lb + b2c_live_before(wm, c6[0]) + b2c_live_before(wm, c6[1]));
+                    if (s1 >= thr) place(ub, 1u, lb + b2c_live_before(wm, c6[2]) + b2c_live_before(wm, c6[3]));
+                    if (s2 >= thr) place(ub, 2u, lb + b2c_live_before(wm, c6[4]) + b2c_live_before(wm, c6[5]));
+                }
+            }
+        } else {
+            // four to eight tokens: K (K - 1) questions per slot would leave the frame waiting for the first slots --
+            // candidates strided over the threads, most of them discarded by a bound that needs no search
+            b2c_rank_list_items(S.cfold, n, K, S.wmask, 0u, S.wmask, thr, width, [](double, u32) { return 0u; },
+                                [&](u32, u32 k, u32 b, u32 rank) { place(b, k, rank); });
+        }
         b2c_warp_max_u32_slot(my_top, S.wtop);         // the selected ranks are exactly 0 .. max(wtop)-1
     }
     B2C_FMARK(21);
