@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(128) b2c_decide_kernel(const B2cPrepArgs A) {
     b2c_decide_block<T>(A, static_cast<int>(blockIdx.x), &sh);
 }
 template <class T>
-__global__ void __launch_bounds__(B2C_PREP_THREADS) b2c_tokens_kernel(const B2cPrepArgs A) {
+__global__ void __launch_bounds__(B2C_PREP_THREADS, 4) b2c_tokens_kernel(const B2cPrepArgs A) {
     __shared__ B2cPrepShared sh;
     b2c_tokens_block<T>(A, static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x), &sh);
 }

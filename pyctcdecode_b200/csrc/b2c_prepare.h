@@ -580,6 +580,90 @@ __device__ __forceinline__ bool b2c_prep_row_f32_fast(const float* row, int V, d
     nsel_out = nsel;
     return true;
 }
+
+// The same for rows that are 16-byte aligned with V a multiple of 4: a lane reads FOUR consecutive logits per load
+// (v = base + 4 lane + j) -- a quarter of the load instructions, and four independent exp chains per lane hide the
+// latency of the dependent fused multiply-adds.  Maximum, sums and the integer denominator do not depend on the order of
+// the walk; the selected set is fed in ascending token order from four ballots per 128 tokens (bit L of ballot j is
+// token base + 4 L + j), the arg-max keeps the lowest index among equal values.
+__device__ __forceinline__ bool b2c_prep_row_f32_fast4(const float* row, int V, double thr, int lane, B2cPySet& set, float& m_out,
+                                                       double& ls_out, int& amax_out, u32& nsel_out, float& sx_out, float& sa_out) {
+    const unsigned full = 0xFFFFFFFFu;
+    const float4* const row4 = reinterpret_cast<const float4*>(row);
+    const int V4 = V >> 2;
+    float mx = -3.402823466e38f, sx = 0.0f, sa = 0.0f;
+    for (int q = lane; q < V4; q += 32) {
+        const float4 x = row4[q];
+        sx += (x.x + x.y) + (x.z + x.w);
+        sa += (fabsf(x.x) + fabsf(x.y)) + (fabsf(x.z) + fabsf(x.w));
+        mx = fmaxf(fmaxf(mx, x.x), fmaxf(x.y, fmaxf(x.z, x.w)));
+    }
+    sx_out = sx;
+    sa_out = sa;
+    if (__any_sync(full, !(sa < 3.0e38f))) return false;
+    for (int off = 16; off >= 1; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(full, mx, off));
+    const float m = mx;
+    u64 q0 = 0, q1 = 0;
+    for (int q = lane; q < V4; q += 32) {
+        const float4 x = row4[q];
+        q0 += b2c_sm_quantum_fast(x.x - m);
+        q1 += b2c_sm_quantum_fast(x.y - m);
+        q0 += b2c_sm_quantum_fast(x.z - m);
+        q1 += b2c_sm_quantum_fast(x.w - m);
+    }
+    u64 qs = q0 + q1;
+    for (int off = 16; off >= 1; off >>= 1) qs += __shfl_xor_sync(full, qs, off);
+    const float lsf = b2c_sm_finish(qs, false, false);
+    const float thr_up = __double2float_ru(thr);
+    const bool thr_all = thr <= B2C_LOG_MIN_CLIP;
+    float best = -3.402823466e38f;
+    int besti = -1;
+    u32 nsel = 0;
+    if (lane == 0) b2c_pyset_init(set, set.buf[0], set.buf[1]);
+    for (int base4 = 0; base4 < V4; base4 += 32) {
+        const int q = base4 + lane;
+        bool s0 = false, s1 = false, s2 = false, s3 = false;
+        if (q < V4) {
+            const float4 x = row4[q];
+            const float l0 = B2C_SM_ADD(x.x - m, -lsf), l1 = B2C_SM_ADD(x.y - m, -lsf), l2 = B2C_SM_ADD(x.z - m, -lsf),
+                        l3 = B2C_SM_ADD(x.w - m, -lsf);
+            const int v = 4 * q;
+            if (l0 > best || besti < 0) { best = l0; besti = v; }
+            if (l1 > best) { best = l1; besti = v + 1; }
+            if (l2 > best) { best = l2; besti = v + 2; }
+            if (l3 > best) { best = l3; besti = v + 3; }
+            s0 = thr_all || l0 >= thr_up;
+            s1 = thr_all || l1 >= thr_up;
+            s2 = thr_all || l2 >= thr_up;
+            s3 = thr_all || l3 >= thr_up;
+        }
+        const unsigned b0 = __ballot_sync(full, s0), b1 = __ballot_sync(full, s1), b2 = __ballot_sync(full, s2), b3 = __ballot_sync(full, s3);
+        unsigned any = b0 | b1 | b2 | b3;
+        nsel += __popc(b0) + __popc(b1) + __popc(b2) + __popc(b3);
+        if (lane == 0) {
+            while (any) {
+                const int L = __ffs(any) - 1;
+                any &= any - 1;
+                const u32 v = 4u * static_cast<u32>(base4 + L);
+                if ((b0 >> L) & 1u) b2c_pyset_add(set, v);
+                if ((b1 >> L) & 1u) b2c_pyset_add(set, v + 1);
+                if ((b2 >> L) & 1u) b2c_pyset_add(set, v + 2);
+                if ((b3 >> L) & 1u) b2c_pyset_add(set, v + 3);
+            }
+        }
+        __syncwarp();
+    }
+    for (int off = 16; off >= 1; off >>= 1) {
+        const float ob = __shfl_xor_sync(full, best, off);
+        const int oi = __shfl_xor_sync(full, besti, off);
+        if (oi >= 0 && (besti < 0 || ob > best || (ob == best && oi < besti))) { best = ob; besti = oi; }
+    }
+    m_out = m;
+    ls_out = static_cast<double>(lsf);
+    amax_out = besti;
+    nsel_out = nsel;
+    return true;
+}
 #endif
 
 // CPython iteration order of set(ascending ints of `mask`) | {amax} for at most 3 selected tokens < 32 with
@@ -821,7 +905,10 @@ B2C_HD void b2c_tokens_run(const B2cPrepArgs& A, u64 run, int lane, u16* set0, u
         if constexpr (kFastRows) {
             if (fast_rows) {
                 float fm, fsx, fsa;
-                row_done = b2c_prep_row_f32_fast(reinterpret_cast<const float*>(row), V, A.token_min_logp, lane, set, fm, ls, amax, nsel, fsx, fsa);
+                const float* const frow = reinterpret_cast<const float*>(row);
+                const bool vec4 = (V & 3) == 0 && (reinterpret_cast<unsigned long long>(frow) & 15ull) == 0;
+                row_done = vec4 ? b2c_prep_row_f32_fast4(frow, V, A.token_min_logp, lane, set, fm, ls, amax, nsel, fsx, fsa)
+                                : b2c_prep_row_f32_fast(frow, V, A.token_min_logp, lane, set, fm, ls, amax, nsel, fsx, fsa);
                 m = fm;
                 run_sx += static_cast<double>(fsx);
                 run_sa += static_cast<double>(fsa);
@@ -1013,7 +1100,7 @@ __device__ inline void b2c_tokens_tiles_v32(const B2cPrepArgs& A, int block_idx,
                 // lane index (8 lanes of a quarter warp -> 8 different quads -> no bank conflict)
                 // pass 1: maximum, sums
                 float mx = -3.402823466e38f;
-#pragma unroll
+#pragma unroll 2
                 for (int qq = 0; qq < 8; ++qq) {
                     const float4 v = *reinterpret_cast<const float4*>(row + 4 * ((qq + lane) & 7));
                     sx += (v.x + v.y) + (v.z + v.w);
@@ -1024,7 +1111,7 @@ __device__ inline void b2c_tokens_tiles_v32(const B2cPrepArgs& A, int block_idx,
                 m = mx;
                 // pass 2: softmax denominator, integer sum (order free)
                 u64 qs = 0;
-#pragma unroll
+#pragma unroll 2
                 for (int qq = 0; qq < 8; ++qq) {
                     const float4 v = *reinterpret_cast<const float4*>(row + 4 * ((qq + lane) & 7));
                     // rows with NaN / infinity (odd_row) are redone by the general routine below: the branch-free form
@@ -1041,7 +1128,7 @@ __device__ inline void b2c_tokens_tiles_v32(const B2cPrepArgs& A, int block_idx,
                 const bool thr_all = thr <= B2C_LOG_MIN_CLIP;
                 float best = -3.402823466e38f;
                 u32 bi = 32;
-#pragma unroll
+#pragma unroll 2
                 for (int qq = 0; qq < 8; ++qq) {
                     const u32 j0 = 4u * ((qq + lane) & 7);
                     const float4 v = *reinterpret_cast<const float4*>(row + j0);

@@ -509,3 +509,57 @@ def test_gpu_chunked_launches_give_the_same_results(chunks):
     r = subprocess.run([sys.executable, "-m", "pytest", here, "-x", "-q", "-m", "gpu", "-k", "special_single or ragged or headline_shape"],
                        env=env, cwd=os.path.dirname(os.path.dirname(here)), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0, r.stdout[-3000:]
+
+
+@pytest.mark.gpu
+def test_gpu_hinted_plain_calls(pkg, orc):
+    """From the second call of a configuration the beam kernel is planned from the previous call's statistics and
+    launched without waiting for this call's (device tensors and lists of arrays; b2c_timings_t.hinted): same results;
+    another beam width is another configuration; diffuse posteriors behind a peaky hint are decoded correctly whichever
+    way each call was planned (over a refresh call)."""
+    import torch
+    wl = synth.make_workload(dict(kind="char", vocab="B", n_words=400, lm_order=0))
+    dec = pkg.build_ctcdecoder(wl.labels)
+    ora = orc.OracleDecoder(wl.labels)
+    peaky = np.stack([wl.utterance(9500 + i, 400, "peaky") for i in range(24)])
+    want = ora.decode_batch(list(peaky), beam_width=32)
+    dev = torch.from_numpy(peaky).cuda()
+    flags = []
+    for _ in range(3):
+        assert dec.decode_batch(None, dev, beam_width=32) == want
+        flags.append(dec.last_timings()["hinted"])
+    assert flags == [0, 1, 1]
+    want16 = ora.decode_batch(list(peaky), beam_width=16)
+    assert dec.decode_batch(None, list(peaky), beam_width=16) == want16
+    assert dec.last_timings()["hinted"] == 0
+    assert dec.decode_batch(None, list(peaky), beam_width=16) == want16
+    assert dec.last_timings()["hinted"] == 1
+    diffuse = [wl.utterance(9600 + i, 150, "diffuse") for i in range(6)]
+    want_d = ora.decode_batch(diffuse, beam_width=16)
+    for _ in range(36):
+        assert dec.decode_batch(None, diffuse, beam_width=16) == want_d
+    assert dec.decode_batch(None, list(peaky), beam_width=16) == want16
+
+
+@pytest.mark.gpu
+def test_gpu_wide_alphabet_rows_with_special_values(pkg, orc):
+    """The warp-per-row streaming kernel (V > 32, float32) takes its branch-free path only for rows without NaN /
+    infinity; rows with -inf (masked vocabulary entries), +inf or NaN go through the general routine.  Same tokens and
+    scores as the oracle either way (masked entries; the other special values in a few rows of every utterance)."""
+    wl = synth.make_workload(dict(kind="bpe", n_words=400, lm_order=0))
+    dec = pkg.build_ctcdecoder(wl.labels)
+    ora = orc.OracleDecoder(wl.labels)
+    rng = np.random.default_rng(5)
+    xs = []
+    for i in range(6):
+        x = wl.utterance(9700 + i, 120, "peaky").astype(np.float32)
+        rows = rng.choice(len(x), size=12, replace=False)
+        for j, r in enumerate(rows):
+            cols = rng.choice(x.shape[1], size=40, replace=False)
+            low = cols[x[r, cols] < x[r].max() - 3.0]          # never the frame's best token
+            x[r, low] = -np.inf if j % 3 else np.float32(-3.0e38)
+        xs.append(x)
+    got = dec.decode_beams_batch(None, xs, beam_width=24)
+    ref = ora.decode_beams_batch(xs, beam_width=24)
+    for w, g in zip(ref, got):
+        _compare(w, _beams(g))

@@ -154,7 +154,7 @@ def test_lm_host_queries_match_oracle(golden, tmp_path):
 
 
 def test_sorted_step_search_matches_linear_scan(tmp_path):
-    """b2c_sorted_count (three-level search of the merge-free sorted step) against a linear scan for every table
+    """b2c_sorted_count (branch-free binary search of the merge-free sorted step) against a linear scan for every table
     size 1..128, every answer 0..n, ties included (tests/hostsim/t_sorted_count.cpp)."""
     import subprocess
     here = os.path.dirname(os.path.abspath(__file__))
@@ -164,6 +164,19 @@ def test_sorted_step_search_matches_linear_scan(tmp_path):
                            os.path.join(here, "hostsim", "t_sorted_count.cpp"), "-o", exe])
     out = subprocess.run([exe], stdout=subprocess.PIPE, text=True)
     assert out.returncode == 0, out.stdout
+
+
+def test_fast_softmax_quantum_is_bit_identical_to_the_definition(tmp_path):
+    """b2c_sm_quantum_fast (the branch-free addend of the softmax denominator used by the streaming kernels on rows
+    without NaN / infinity) == rint(b2c_sm_expf(d) * 2^32) on a strided sweep of every float32 d <= 0, -0.0 and -inf
+    included (tools/quantum_fast_check.cpp; stride 1 = all 2^31 values, ~35 s on 16 threads, was run once)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "quantum_fast_check")
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fopenmp", "-o", exe, os.path.join(root, "tools", "quantum_fast_check.cpp")])
+    for stride in ("257", "4099"):
+        out = subprocess.run([exe, stride], stdout=subprocess.PIPE, text=True)
+        assert out.returncode == 0, out.stdout
 
 
 def test_install_alias_makes_reference_imports_resolve_to_the_product():
