@@ -529,16 +529,18 @@ def test_gpu_hinted_plain_calls(pkg, orc):
         assert dec.decode_batch(None, dev, beam_width=32) == want
         flags.append(dec.last_timings()["hinted"])
     assert flags == [0, 1, 1]
-    want16 = ora.decode_batch(list(peaky), beam_width=16)
-    assert dec.decode_batch(None, list(peaky), beam_width=16) == want16
+    # a ragged list of host arrays (not one [B, T, V] block, so not a pipelined call): hinted as well
+    ragged = [wl.utterance(9550 + i, 300 + 7 * i, "peaky") for i in range(12)]
+    want16 = ora.decode_batch(ragged, beam_width=16)
+    assert dec.decode_batch(None, ragged, beam_width=16) == want16
     assert dec.last_timings()["hinted"] == 0
-    assert dec.decode_batch(None, list(peaky), beam_width=16) == want16
+    assert dec.decode_batch(None, ragged, beam_width=16) == want16
     assert dec.last_timings()["hinted"] == 1
-    diffuse = [wl.utterance(9600 + i, 150, "diffuse") for i in range(6)]
+    diffuse = [wl.utterance(9600 + i, 150 + i, "diffuse") for i in range(6)]
     want_d = ora.decode_batch(diffuse, beam_width=16)
     for _ in range(36):
         assert dec.decode_batch(None, diffuse, beam_width=16) == want_d
-    assert dec.decode_batch(None, list(peaky), beam_width=16) == want16
+    assert dec.decode_batch(None, ragged, beam_width=16) == want16
 
 
 @pytest.mark.gpu
