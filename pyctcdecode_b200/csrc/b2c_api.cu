@@ -657,6 +657,7 @@ static void build_hot(const b2c_decode_opts_t* o, std::vector<B2cHot>& tab, int&
 // decode() / decode_batch() want the text only: no word vector, no frames
 static void assemble_text(const b2c_decoder* d, const u32* toks, int nt, BeamRes& br) {
     br.text.clear();
+    br.text.reserve(static_cast<size_t>(nt > 0 ? nt : 0) + 16);      // one allocation (most tokens are one byte)
     br.words.clear();
     br.frames.clear();
     bool open_word = false;      // the current word has at least one character

@@ -587,8 +587,7 @@ __device__ __forceinline__ bool b2c_prep_row_f32_fast(const float* row, int V, d
 // the walk; the selected set is fed in ascending token order from four ballots per 128 tokens (bit L of ballot j is
 // token base + 4 L + j), the arg-max keeps the lowest index among equal values.
 __device__ __forceinline__ bool b2c_prep_row_f32_fast4(const float* row, int V, double thr, int lane, B2cPySet& set, float& m_out,
-                                                       double& ls_out, int& amax_out, u32& nsel_out, float& sx_out, float& sa_out,
-                                                       u32 (&small_keys)[3]) {
+                                                       double& ls_out, int& amax_out, u32& nsel_out, float& sx_out, float& sa_out) {
     const unsigned full = 0xFFFFFFFFu;
     const float4* const row4 = reinterpret_cast<const float4*>(row);
     const int V4 = V >> 2;
@@ -620,23 +619,7 @@ __device__ __forceinline__ bool b2c_prep_row_f32_fast4(const float* row, int V, 
     float best = -3.402823466e38f;
     int besti = -1;
     u32 nsel = 0;
-    // lane 0 keeps the first three selected tokens in registers; only a fourth one starts the general set emulation
-    u32 kk0 = 0, kk1 = 0, kk2 = 0;
-    auto feed = [&](u32 v) {
-        if (nsel == 0) kk0 = v;
-        else if (nsel == 1) kk1 = v;
-        else if (nsel == 2) kk2 = v;
-        else {
-            if (nsel == 3) {
-                b2c_pyset_init(set, set.buf[0], set.buf[1]);
-                b2c_pyset_add(set, kk0);
-                b2c_pyset_add(set, kk1);
-                b2c_pyset_add(set, kk2);
-            }
-            b2c_pyset_add(set, v);
-        }
-        ++nsel;
-    };
+    if (lane == 0) b2c_pyset_init(set, set.buf[0], set.buf[1]);
     for (int base4 = 0; base4 < V4; base4 += 32) {
         const int q = base4 + lane;
         bool s0 = false, s1 = false, s2 = false, s3 = false;
@@ -656,26 +639,25 @@ __device__ __forceinline__ bool b2c_prep_row_f32_fast4(const float* row, int V, 
         }
         const unsigned b0 = __ballot_sync(full, s0), b1 = __ballot_sync(full, s1), b2 = __ballot_sync(full, s2), b3 = __ballot_sync(full, s3);
         unsigned any = b0 | b1 | b2 | b3;
+        nsel += __popc(b0) + __popc(b1) + __popc(b2) + __popc(b3);
         if (lane == 0) {
             while (any) {
                 const int L = __ffs(any) - 1;
                 any &= any - 1;
                 const u32 v = 4u * static_cast<u32>(base4 + L);
-                if ((b0 >> L) & 1u) feed(v);
-                if ((b1 >> L) & 1u) feed(v + 1);
-                if ((b2 >> L) & 1u) feed(v + 2);
-                if ((b3 >> L) & 1u) feed(v + 3);
+                if ((b0 >> L) & 1u) b2c_pyset_add(set, v);
+                if ((b1 >> L) & 1u) b2c_pyset_add(set, v + 1);
+                if ((b2 >> L) & 1u) b2c_pyset_add(set, v + 2);
+                if ((b3 >> L) & 1u) b2c_pyset_add(set, v + 3);
             }
         }
         __syncwarp();
     }
-    nsel = __shfl_sync(full, nsel, 0);
     for (int off = 16; off >= 1; off >>= 1) {
         const float ob = __shfl_xor_sync(full, best, off);
         const int oi = __shfl_xor_sync(full, besti, off);
         if (oi >= 0 && (besti < 0 || ob > best || (ob == best && oi < besti))) { best = ob; besti = oi; }
     }
-    small_keys[0] = kk0; small_keys[1] = kk1; small_keys[2] = kk2;     // lane 0's copy is the one that is used
     m_out = m;
     ls_out = static_cast<double>(lsf);
     amax_out = besti;
@@ -711,50 +693,6 @@ B2C_HD u32 b2c_pyset_small_order(u32 mask, u32 amax, u32* out) {
     for (u32 i = 0; i < 8; ++i) {
         const u32 e = static_cast<u32>((tab >> (8 * i)) & 0xFFull);
         if (e != 0xFFu) out[n++] = e;
-    }
-    return n;
-}
-
-// The same for token ids of any size (wide alphabets): iteration order of set(keys ascending) | {amax} for at most
-// three selected tokens, amax among them or not.  Up to four entries never leave the initial 8-slot table (CPython
-// resizes at fill * 5 >= mask * 3), the copy made by `|` keeps the slots (same table size) and the linear-probe window
-// is closed at mask 7, so the result is: insert the keys in ascending order, then amax, each at the first free slot of
-// its probe sequence i <- (5 i + 1 + (perturb >>= 5)) & 7 -- and read the slots in order.  Only the occupancy bitmap and
-// the (slot, key) pairs are kept, in registers.  Writes the tokens to out[0..3], returns how many.
-B2C_HD u32 b2c_pyset_small_order_any(u32 k0, u32 k1, u32 k2, u32 nk, u32 amax, u32* out) {
-    u32 occ = 0, n = 0;
-    u32 key[4] = {0, 0, 0, 0}, slot_of[4] = {8, 8, 8, 8};
-    const u32 cand[4] = {k0, k1, k2, amax};
-#if defined(__CUDACC__)
-#pragma unroll
-#endif
-    for (u32 j = 0; j < 4; ++j) {
-        const bool is_key = j < 3;
-        if (is_key && j >= nk) continue;
-        const u32 c = cand[j];
-        if (!is_key && ((nk > 0 && c == k0) || (nk > 1 && c == k1) || (nk > 2 && c == k2))) continue;      // amax already in the set
-        u32 perturb = c, i = c & 7u;
-        while ((occ >> i) & 1u) {
-            perturb >>= 5;
-            i = (i * 5 + 1 + perturb) & 7u;
-        }
-        occ |= 1u << i;
-        key[j] = c;
-        slot_of[j] = i;
-        ++n;
-    }
-    // tokens in slot order: entry j is preceded by the entries with a smaller slot (absent entries carry slot 8)
-#if defined(__CUDACC__)
-#pragma unroll
-#endif
-    for (u32 j = 0; j < 4; ++j) {
-        if (slot_of[j] > 7) continue;
-        u32 pos = 0;
-#if defined(__CUDACC__)
-#pragma unroll
-#endif
-        for (u32 q = 0; q < 4; ++q) pos += slot_of[q] < slot_of[j] ? 1u : 0u;
-        out[pos] = key[j];
     }
     return n;
 }
@@ -963,17 +901,14 @@ B2C_HD void b2c_tokens_run(const B2cPrepArgs& A, u64 run, int lane, u16* set0, u
         int amax;
         u32 nsel;
         bool row_done = false;
-        bool row_small = false;          // at most three selected tokens, kept in lane 0's registers (no set tables)
-        u32 small_keys[3] = {0, 0, 0};
 #if defined(__CUDA_ARCH__)
         if constexpr (kFastRows) {
             if (fast_rows) {
                 float fm, fsx, fsa;
                 const float* const frow = reinterpret_cast<const float*>(row);
                 const bool vec4 = (V & 3) == 0 && (reinterpret_cast<unsigned long long>(frow) & 15ull) == 0;
-                row_done = vec4 ? b2c_prep_row_f32_fast4(frow, V, A.token_min_logp, lane, set, fm, ls, amax, nsel, fsx, fsa, small_keys)
+                row_done = vec4 ? b2c_prep_row_f32_fast4(frow, V, A.token_min_logp, lane, set, fm, ls, amax, nsel, fsx, fsa)
                                 : b2c_prep_row_f32_fast(frow, V, A.token_min_logp, lane, set, fm, ls, amax, nsel, fsx, fsa);
-                row_small = row_done && vec4 && nsel <= 3;
                 m = fm;
                 run_sx += static_cast<double>(fsx);
                 run_sa += static_cast<double>(fsa);
@@ -981,24 +916,7 @@ B2C_HD void b2c_tokens_run(const B2cPrepArgs& A, u64 run, int lane, u16* set0, u
         }
 #endif
         if (!row_done) b2c_prep_row<T, false>(row, V, is_prob, A.token_min_logp, lane, set, m, ls, amax, nsel);
-        if (lane == 0 && row_small) {
-            // up to three selected tokens (+ the arg-max): their CPython set order from registers, no set tables
-            u32 toks[4];
-            const u32 cnt = b2c_pyset_small_order_any(small_keys[0], small_keys[1], small_keys[2], nsel, static_cast<u32>(amax), toks);
-            B2cFrameRec rec;
-            rec.off = off;
-            rec.cnt = static_cast<u16>(cnt);
-            rec.id0 = static_cast<u16>(toks[0]);
-            for (u32 q = 0; q < cnt; ++q) {
-                const double lp = b2c_lp<T>(row[toks[q]], is_prob, m, ls);
-                ids[off] = toks[q];
-                lps[off] = lp;
-                if (q == 0) rec.lp0 = lp;
-                ++off;
-            }
-            A.tok_rec[f0 + static_cast<u64>(t)] = rec;
-            if (cnt > mx) mx = cnt;
-        } else if (lane == 0) {
+        if (lane == 0) {
             b2c_pyset_copy_or(set, static_cast<u32>(amax));
             const u32 cnt = set.fill;
             B2cFrameRec rec;

@@ -166,20 +166,6 @@ def test_sorted_step_search_matches_linear_scan(tmp_path):
     assert out.returncode == 0, out.stdout
 
 
-def test_small_set_order_in_registers_matches_the_set_emulation(tmp_path):
-    """b2c_pyset_small_order_any (wide-alphabet streaming kernel: CPython set order of <= 3 selected tokens | {arg-max},
-    occupancy bitmap + (slot, key) pairs in registers) against the general table emulation for every subset of size 0..3
-    of a token pool with low-bit collisions and every arg-max of the pool (tests/hostsim/t_small_order.cpp)."""
-    import subprocess
-    here = os.path.dirname(os.path.abspath(__file__))
-    exe = str(tmp_path / "t_small_order")
-    subprocess.check_call(["g++", "-std=c++17", "-O1", "-DB2C_HOSTSIM", "-I" + os.path.join(here, "hostsim"),
-                           "-I" + os.path.join(os.path.dirname(here), "pyctcdecode_b200", "csrc"),
-                           os.path.join(here, "hostsim", "t_small_order.cpp"), "-o", exe])
-    out = subprocess.run([exe], stdout=subprocess.PIPE, text=True)
-    assert out.returncode == 0, out.stdout
-
-
 def test_fast_softmax_quantum_is_bit_identical_to_the_definition(tmp_path):
     """b2c_sm_quantum_fast (the branch-free addend of the softmax denominator used by the streaming kernels on rows
     without NaN / infinity) == rint(b2c_sm_expf(d) * 2^32) on a strided sweep of every float32 d <= 0, -0.0 and -inf
