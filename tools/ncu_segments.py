@@ -1,6 +1,17 @@
+"""One ncu capture cut at the block barriers: for every barrier-to-barrier stretch of the kernel's SASS (address order)
+the warp instructions executed, the stall samples, how often the closing barrier ran and the source lines with the most
+samples.  TEST / PROFILING TOOL.
+
+    python tools/ncu_segments.py <report.ncu-rep> <library.so>
+
+Reading guide: a warp that waits at a barrier is sampled at the instruction AFTER it, so barrier waits show up as a short
+stretch with many samples and few instructions right behind the barrier; the `bar execs` column identifies the stretch
+(e.g. warps x iterations for the closing barrier of the frame loop, warps x general frames for the barriers of the
+general step).  SASS order is not execution order: a stretch holds whatever code the compiler placed between two barriers.
+"""
 import csv, io, re, subprocess, os, sys, tempfile, collections
 rep, lib = sys.argv[1], os.path.abspath(sys.argv[2])
-lines=open('/tmp/src.csv').read().splitlines()
+lines = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout.splitlines()
 kernel = next(csv.reader([lines[0]]))[1]
 rows=list(csv.DictReader(io.StringIO("\n".join(lines[1:]))))
 base=int(rows[0]['Address'],16)
