@@ -1,4 +1,4 @@
-// TEST INFRASTRUCTURE ONLY: exhaustive check of b2c_sorted_count (csrc/b2c_beam_fast.h, the three-level search of
+// TEST INFRASTRUCTURE ONLY: exhaustive check of b2c_sorted_count (csrc/b2c_beam_fast.h, the branch-free binary search of
 // the merge-free sorted step) against a linear scan, for every table size 1..128 and every answer 0..n.
 #include <cmath>
 #include <cstdio>
