@@ -1698,8 +1698,10 @@ static int decode_batch_locked(b2c_decoder_t* d, const void* const* logits, cons
         }
     };
     plan_launches(!(pipe_candidate || hinted));
-    if (hinted && !(launches.size() == 1 && launches[0].v5 == d->plain_v5 && static_cast<int>(launches[0].L.cap_s) == d->plain_cap)) {
-        // not the plan the last statistics-based call ran: wait for this call's statistics and plan from them
+    if (hinted && !(launches.size() == 1 && launches[0].v5 == d->plain_v5 && static_cast<int>(launches[0].L.cap_s) == d->plain_cap &&
+                    launches[0].slots == std::min(launches[0].count, d->n_sm * launches[0].per_sm))) {
+        // not the plan the last statistics-based call ran -- or the worst-case workspace of a plan without statistics (V tokens
+        // in a frame: large alphabets) would cost resident CTAs: wait for this call's statistics and plan from them
         hinted = false;
         d->hinted_refused = true;
         CUDA_OK(cudaStreamSynchronize(st));
