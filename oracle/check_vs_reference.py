@@ -38,11 +38,16 @@ SCORE_TOL = 2e-4  # numpy evaluates log-softmax in float32 with its own SIMD exp
 
 def reference_unstable(ref_dec, x, dkw, orc_beams, n=16, eps=1e-13):
     """(b) of the module docstring -> (number of distinct outcomes of the reference, '' or why the oracle is outside)"""
-    if x.dtype == np.float32:
-        return 1, "float32 input: no sub-ulp perturbation"
-    x = x.astype(np.float64)        # integer / float64 input: the reference computes in float64
     from oracle import gen_golden_unstable as gu
-    beams, n_out, same_set = gu.reference_family(ref_dec, x, dkw, n=n, eps=eps)
+    if x.dtype == np.float32:
+        # float32 input is computed in float32 (decoder.py:180-197): the smallest perturbation is a step to a neighbouring
+        # float32 -- the size of the run-to-run differences of numpy's own float32 exp / log (SIMD body vs scalar head /
+        # tail of a row, depending on the alignment of the buffer), which were seen to flip this case between two runs of
+        # this very script
+        beams, n_out, same_set = gu.reference_family(ref_dec, x, dkw, n=4 * n, perturb=gu.one_ulp_float32)   # every tied cut doubles the family
+    else:
+        x = x.astype(np.float64)        # integer / float64 input: the reference computes in float64
+        beams, n_out, same_set = gu.reference_family(ref_dec, x, dkw, n=n, eps=eps)
     if n_out < 2:
         return n_out, "the reference is stable under the perturbation"
     if not same_set:
@@ -85,7 +90,8 @@ def compare(ref_beams, orc_beams, tag, stats, ref_dec=None, x=None, dkw=None):
         verdict = "tie permutation (reference scores within %g)" % tie
         if why and ref_dec is not None:
             n_out, outside = reference_unstable(ref_dec, x, dkw, orc_beams)
-            verdict = ("reference-unstable: %d distinct reference outcomes under 1e-13 input noise, oracle inside the family" % n_out
+            noise = "one-ulp float32 input noise" if (x is not None and x.dtype == np.float32) else "1e-13 input noise"
+            verdict = ("reference-unstable: %d distinct reference outcomes under %s, oracle inside the family" % (n_out, noise)
                        if not outside else "HARD: %s; %s" % (why, outside))
         elif why:
             verdict = "HARD: " + why

@@ -51,16 +51,31 @@ def signature(beams):
     return tuple(sorted((b.text, tuple(tuple(f) for _, f in b.text_frames), round(b.lm_score, 6)) for b in beams))
 
 
-def reference_family(dec, x, dkw, n=N_PERTURB, eps=EPS):
-    """the unmodified reference on x and on n copies of x perturbed by eps * N(0, 1): -> (beams of the unperturbed
-    run with, per beam, every distinct score pair the family gives it; number of distinct outcomes; whether every
-    outcome has the same beam set)"""
+def one_ulp_float32(x, seed):
+    """float32 input: the smallest perturbation there is -- about half of the elements move to a neighbouring float32"""
+    rng = np.random.default_rng(seed)
+    step = rng.integers(-1, 2, size=x.shape)
+    out = x.copy()
+    out[step > 0] = np.nextafter(x[step > 0], np.float32(np.inf))
+    out[step < 0] = np.nextafter(x[step < 0], np.float32(-np.inf))
+    return out.astype(np.float32)
+
+
+def reference_family(dec, x, dkw, n=N_PERTURB, eps=EPS, perturb=None):
+    """the unmodified reference on x and on n copies of x perturbed by eps * N(0, 1) (or by `perturb(x, seed)`): ->
+    (beams of the unperturbed run with, per beam, every distinct score pair the family gives it; number of distinct
+    outcomes; whether every outcome has the same beam set)"""
     seen = set()
     allowed = {}
     base = None
     same_set = True
     for seed in range(n + 1):
-        xp = x if seed == 0 else x + np.random.default_rng(seed).standard_normal(x.shape) * eps
+        if seed == 0:
+            xp = x
+        elif perturb is not None:
+            xp = perturb(x, seed)
+        else:
+            xp = x + np.random.default_rng(seed).standard_normal(x.shape) * eps
         beams = dec.decode_beams(xp, **dkw)
         seen.add(signature(beams))
         ids = set()
