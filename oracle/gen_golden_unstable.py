@@ -109,10 +109,23 @@ def main():
                       "reference_outcomes": n_out, "beams": beams})
         print(name, "distinct reference outcomes under %g perturbation: %d; beams with more than one score: %d" %
               (EPS, n_out, sum(len(b["scores"]) > 1 for b in beams)))
+    # the same logits as float32: the reference computes the log-softmax in float32 then, and the smallest perturbation is a
+    # step to a neighbouring float32 (numpy's own float32 exp / log differ by that much between two runs on identical input:
+    # SIMD body vs scalar head / tail of a row, depending on the alignment of the buffer).  Every tied cut doubles the
+    # family, so many more perturbations are drawn.  "cpu_only": pinned on the oracle and on the kernel logic (hostsim).
+    libri32 = libri.astype(np.float32)
+    for name, dkw in (("libri_f32_prune20_tok8", dict(beam_prune_logp=-20.0, token_min_logp=-8.0)),):
+        beams, n_out, same_set = reference_family(dec, libri32, dkw, n=6 * N_PERTURB, perturb=one_ulp_float32)
+        assert same_set, "the family does not share one beam set: record alternatives instead"
+        cases.append({"name": name, "labels": synth.LIBRI_LABELS, "array": "libri_f32", "decode": dkw, "cpu_only": True,
+                      "reference_outcomes": n_out, "beams": beams})
+        print(name, "distinct reference outcomes under one-ulp float32 perturbations: %d; beams with more than one score: %d" %
+              (n_out, sum(len(b["scores"]) > 1 for b in beams)))
     with open(OUT, "w", encoding="utf-8") as fh:
         json.dump({"cases": cases, "generator": "oracle/gen_golden_unstable.py",
                    "reference": "pyctcdecode 0.6.0 @ afecb676, numpy %s" % np.__version__,
-                   "perturbation": "x + %g * N(0,1), seeds 1..%d, plus x itself" % (EPS, N_PERTURB)}, fh, ensure_ascii=False, indent=0)
+                   "perturbation": "x + %g * N(0,1), seeds 1..%d, plus x itself; float32 cases: about half of the elements moved "
+                                   "to a neighbouring float32, seeds 1..%d" % (EPS, N_PERTURB, 6 * N_PERTURB)}, fh, ensure_ascii=False, indent=0)
 
 
 if __name__ == "__main__":

@@ -55,7 +55,7 @@ def _names():
     return [c["name"] for c in goldens.load()["meta"]["cases"]]
 
 
-@pytest.mark.parametrize("name", goldens.unstable_case_names())
+@pytest.mark.parametrize("name", goldens.unstable_case_names(gpu=True))
 def test_gpu_on_reference_unstable_goldens(pkg, name):
     """Cases the unmodified reference decides by rounding noise (oracle/gen_golden_unstable.py): the CUDA path must
     lie inside the family of reference outcomes (same beam set, per-beam scores among the family's, sorted)."""
