@@ -870,10 +870,12 @@ B2C_HD void b2c_frame_step(const B2cParams& P, B2cWork& W, int t, const u32* tk_
             const u32 bkt = b2c_bucket_n(ref, sco, bscale, nb);
             u32 rank = bpre[bkt];
             if (rank >= width) continue;          // every candidate of a better bucket outranks it: no need to walk its own
-            for (u32 j = bhead[bkt]; j != B2C_NONE_U32; j = C.cnext[j]) {
-                if (j == static_cast<u32>(i)) continue;
-                const u64 kj = C.ckey[j];
-                rank += (kj > key || (kj == key && j < static_cast<u32>(i))) ? 1u : 0u;
+            for (u32 j = bhead[bkt]; j != B2C_NONE_U32;) {      // the candidate itself adds 0; the two loads of a step are
+                const u64 kj = C.ckey[j];                        // independent (on the HBM tier: one L2 round trip, not two)
+                const u32 jn = C.cnext[j];
+                const u32 gt = kj > key ? 1u : 0u, eq_before = (kj == key ? 1u : 0u) & (j < static_cast<u32>(i) ? 1u : 0u);
+                rank += gt | eq_before;
+                j = jn;
             }
             if (rank >= width) continue;
             ord[rank] = static_cast<u32>(i);
